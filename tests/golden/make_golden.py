@@ -1,0 +1,98 @@
+#!/usr/bin/env python3
+"""Regenerate tests/golden/*.npz from the UNMODIFIED reference (needs /root/reference).
+
+Run in the build container after ``make -C oracle ref``:   python tests/golden/make_golden.py
+
+Every fixture is produced by oracle/_ref/gne_ref_driver reading the text instance through the
+reference's own loader (graph.cpp) and solving with the reference's own compiled code; the
+driver only adds the trace line the reference keeps commented out (gnePivot.cpp:49-50).
+The same instances are also pushed through the driver's sparse initialiser and must give the
+identical trace (that is what lets the oracle run sizes the dense loader cannot hold).
+"""
+import hashlib
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+from gen_instance import generate, write_col  # noqa: E402
+from oracle_util import REF_DRIVER, RULES, Instance, run_reference  # noqa: E402
+
+
+def ref_cli(col, rule1, rule2, tmp):
+    tr = os.path.join(tmp, "trace.txt")
+    dump = os.path.join(tmp, "dump.txt")
+    r = subprocess.run([REF_DRIVER, "-1", str(rule1), "-2", str(rule2), "-T", tr, "-D", dump, col],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        return None
+    last = [ln for ln in r.stdout.splitlines() if ln.startswith("REF pivots")][-1].split()
+    p1, p2 = int(last[2]), int(last[3])
+    txt = open(tr).read()
+    rows = [ln.split() for ln in txt.splitlines()]
+    e = np.array([int(x[2]) for x in rows], np.int32)
+    l = np.array([int(x[3]) for x in rows], np.int32)
+    flows, pots, obj = [], [], None
+    for ln in open(dump):
+        p = ln.split()
+        if p[0] == "objective":
+            obj = float(p[1])
+        elif p[0] == "x":
+            flows.append(float(p[2]))
+        elif p[0] == "pi":
+            pots.append(float(p[2]))
+    return dict(e=e, l=l, p1=p1, p2=p2, objective=obj, flows=np.array(flows), potentials=np.array(pots),
+                trace_md5=hashlib.md5(txt.encode()).hexdigest())
+
+
+def make(name, n, m, seed, mode, rules, keep_state=True, save_instance=False):
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        col = os.path.join(tmp, "inst.col")
+        arcs, sup = generate(n, m, seed, mode)
+        write_col(col, n, arcs, sup)
+        out["col_md5"] = hashlib.md5(open(col, "rb").read()).hexdigest()
+        out["params"] = np.array([n, m, seed])
+        out["mode"] = mode
+        inst = Instance.from_col(col)
+        if save_instance:
+            inst.save(os.path.join(HERE, name + "_instance.npz"))
+        for rn in rules:
+            r = RULES[rn]
+            g = ref_cli(col, r, r, tmp)
+            if g is None:
+                print("  %s %s: reference aborted" % (name, rn))
+                out[rn + "_aborted"] = 1
+                continue
+            z = run_reference(inst, r)
+            same = np.array_equal(z["e"], g["e"]) and np.array_equal(z["l"], g["l"]) and z["objective"] == g["objective"]
+            assert same, "sparse initialiser diverges from the dense loader on %s %s" % (name, rn)
+            print("  %s %-4s pivots %d+%d obj %.9f trace md5 %s" % (name, rn, g["p1"], g["p2"], g["objective"], g["trace_md5"]))
+            out[rn + "_e"] = g["e"]
+            out[rn + "_l"] = g["l"]
+            out[rn + "_p"] = np.array([g["p1"], g["p2"]])
+            out[rn + "_objective"] = g["objective"]
+            out[rn + "_md5"] = g["trace_md5"]
+            if keep_state:
+                out[rn + "_flows"] = g["flows"]
+                out[rn + "_potentials"] = g["potentials"]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "small", "lossy3k"]
+    if "c1" in which:
+        make("c1_wide_s7", 1000, 10000, 7, "wide", ["LV", "LVW", "QS", "CL"], save_instance=True)
+    if "small" in which:
+        allr = ["LV", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "CL2", "QS", "QSW"]
+        make("s_wide_s3", 120, 1200, 3, "wide", allr)
+        make("s_lossy_s4", 150, 1500, 4, "lossy", allr)
+        make("s_pow2_s5", 100, 900, 5, "pow2", allr)
+        make("s_near1_s6", 130, 1100, 6, "near1", allr)
+    if "lossy3k" in which:
+        make("lossy3k_s5", 3000, 60000, 5, "lossy", ["LV"], keep_state=False)

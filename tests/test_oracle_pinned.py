@@ -1,0 +1,126 @@
+"""The CPU restatement (oracle/gne_oracle.cpp) against fixtures produced by the unmodified reference.
+
+tests/golden/*.npz were written by tests/golden/make_golden.py from oracle/_ref (the reference
+compiled from /root/reference); the reference itself ships no tests or golden vectors.
+Bar: identical (entering, leaving) sequences, bit-equal objective, flows and potentials.
+"""
+import ctypes as C
+import hashlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from gen_instance import generate, write_col
+from oracle_util import RULES, Instance, Oracle, oracle_lib, trace_md5
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+SURVEY_MD5 = {  # SURVEY.md Appendix A (measured on the unmodified reference before this repo existed)
+    "LV": "fcdf39b7dc68ed79381ad33527f75d21",
+    "QS": "8531c9b53e422e4b6aa0586f82b00f16",
+    "CL": "d97d6defef2bbdaded3cf780ac6444fe",
+}
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    n, m, seed = (int(v) for v in z["params"])
+    mode = str(z["mode"])
+    with tempfile.TemporaryDirectory() as tmp:
+        col = os.path.join(tmp, "i.col")
+        arcs, sup = generate(n, m, seed, mode)
+        write_col(col, n, arcs, sup)
+        assert hashlib.md5(open(col, "rb").read()).hexdigest() == str(z["col_md5"]), "generator drifted"
+        inst = Instance.from_col(col)
+    return z, inst
+
+
+def check(z, inst, rn, state=True):
+    if rn + "_aborted" in z:
+        pytest.skip("reference aborts on this instance/rule")
+    o = Oracle(inst, RULES[rn])
+    p1, p2 = o.solve_both()
+    assert o.status == 0
+    e, l = o.trace
+    assert (p1, p2) == tuple(int(v) for v in z[rn + "_p"])
+    assert np.array_equal(e, z[rn + "_e"]) and np.array_equal(l, z[rn + "_l"])
+    assert trace_md5(e, l, p1) == str(z[rn + "_md5"])
+    assert o.objective == float(z[rn + "_objective"])
+    if state:
+        assert np.array_equal(o.flows(), z[rn + "_flows"])
+        assert np.array_equal(o.potentials(), z[rn + "_potentials"])
+    o.close()
+
+
+def test_c1_instance_md5_is_the_surveys():
+    z, inst = load("c1_wide_s7")
+    assert str(z["col_md5"]) == "470d58bff433c7067fab92fe50990e08"
+    saved = Instance.load(os.path.join(GOLD, "c1_wide_s7_instance.npz"))
+    for k in ("tail", "head", "ub", "cost", "mult", "supply"):
+        assert np.array_equal(getattr(saved, k), getattr(inst, k))
+
+
+@pytest.mark.parametrize("rn", ["LV", "LVW", "QS", "CL"])
+def test_c1_trace(rn):
+    z, inst = load("c1_wide_s7")
+    if rn in SURVEY_MD5:
+        assert str(z[rn + "_md5"]) == SURVEY_MD5[rn]
+    check(z, inst, rn)
+
+
+SMALL = ["s_wide_s3", "s_lossy_s4", "s_pow2_s5", "s_near1_s6"]
+SMALL_RULES = ["LV", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "CL2", "QS", "QSW"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("rn", SMALL_RULES)
+def test_small_all_rules(name, rn):
+    z, inst = load(name)
+    check(z, inst, rn)
+
+
+def test_lossy3k_lv_trace_md5():
+    z, inst = load("lossy3k_s5")
+    assert str(z["LV_md5"]) == "aec265f38ddd3e1d1999fb257d45d4b5"
+    check(z, inst, "LV", state=False)
+
+
+def test_drand48_restatement_matches_libc():
+    lib = oracle_lib()
+    libc = C.CDLL(None)
+    libc.drand48.restype = C.c_double
+    libc.seed48.restype = C.POINTER(C.c_ushort)
+    # the reference never seeds: glibc's never-seeded state is X = 0
+    zero = (C.c_ushort * 3)(0, 0, 0)
+    libc.seed48(zero)
+    st = C.c_ulonglong(lib.orc_drand48_initial_state())
+    for _ in range(20000):
+        assert lib.orc_drand48(C.byref(st)) == libc.drand48()
+    first = C.c_ulonglong(0)
+    assert lib.orc_drand48(C.byref(first)) == 0xB / 2.0 ** 48
+
+
+def test_stateless_kernels_agree_with_solver_state():
+    """orc_price_* on the extracted nonbasic SoA reproduce what the solver's own rules pick."""
+    lib = oracle_lib()
+    inst = Instance.load(os.path.join(GOLD, "c1_wide_s7_instance.npz"))
+    from oracle_util import dp, ip, lp, bp
+    for K in (0, 37, 600, 2500):
+        o = Oracle(inst, RULES["LV"])
+        o.solve(True, K)
+        pi = o.compute_potentials()
+        nb = o.nonbasic_soa()
+        N = len(nb["order"])
+        lst = np.zeros(N, np.int64)
+        L = C.c_double(0)
+        anyv = C.c_int(0)
+        k = lib.orc_price_lv(C.c_long(N), ip(nb["tail"]), ip(nb["head"]), dp(nb["cost"]), dp(nb["mult"]),
+                             bp(nb["state"]), dp(pi), lp(lst), C.c_long(N), C.byref(L), C.byref(anyv))
+        cand = set(int(v) for v in nb["order"][lst[:k]])
+        o.solve(True, 1)               # one more pivot from the same state
+        e, _ = o.trace
+        if len(e) > K:
+            assert int(e[K]) in cand
+        o.close()
