@@ -1,0 +1,373 @@
+"""genneteq_b200 — B200 (sm_100a) pricing / relabel path of GenNetEq's generalized network simplex.
+
+This module is a thin ctypes binding of ``genneteq_b200/lib/libgenneteq_b200.so`` (C ABI in
+``include/genneteq_b200.h``).  There is no CPU fallback: importing fails loudly when the library
+has not been built (``python -c "import __graft_entry__ as g; g.build()"``), and every compute
+call fails with ``GneError`` when no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgenneteq_b200.so")
+
+RULES = dict(LV=0, LVW=1, LVA=2, LVE=3, FV=4, SD=5, RV=6, RWV=7, RLV=8, RLVW=9, CL=10, CLW=11,
+             SAA=12, SAE=13, CL2=14, CLW2=15, QS=16, QSW=17)          # main.h:17-34
+AT_LOWER, AT_UPPER = 1, 2
+TOL = 1.0e-13
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "genneteq_b200: %s is missing - build it with `make -C genneteq_b200/csrc` "
+        "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_i8p = C.POINTER(C.c_int8)
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol declared in include/genneteq_b200.h
+SIGNATURES = {
+    "gne_last_error": (C.c_char_p, []),
+    "gne_version": (C.c_char_p, []),
+    "gne_cuda_device_count": (C.c_int, []),
+    "gne_dev_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64]),
+    "gne_dev_destroy": (C.c_int, [_vp]),
+    "gne_dev_sync": (C.c_int, [_vp]),
+    "gne_nb_reset": (C.c_int, [_vp, C.c_int64, _i32p, _i32p, _f64p, _f64p, _i8p]),
+    "gne_nb_set_costs": (C.c_int, [_vp, C.c_int64, _f64p]),
+    "gne_nb_write": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int8]),
+    "gne_nb_set_count": (C.c_int, [_vp, C.c_int64]),
+    "gne_nb_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _i8p]),
+    "gne_pot_update_nodes": (C.c_int, [_vp, C.c_int64, _i32p, _f64p, _f64p, _i32p]),
+    "gne_pot_update_thetas": (C.c_int, [_vp, C.c_int64, _i32p, _f64p]),
+    "gne_pot_finalize": (C.c_int, [_vp]),
+    "gne_pot_set": (C.c_int, [_vp, C.c_int64, _i32p, _f64p]),
+    "gne_pot_set_all": (C.c_int, [_vp, _f64p]),
+    "gne_pot_get_all": (C.c_int, [_vp, _f64p]),
+    "gne_price_lv": (C.c_int, [_vp, _f64p, _i64p, _i64p, C.c_int64, C.POINTER(C.c_int)]),
+    "gne_price_qs": (C.c_int, [_vp, C.c_int64, C.c_int64, _i64p, _f64p, _i64p, _i64p, _i64p]),
+    "gne_price_violators": (C.c_int, [_vp, C.c_double, _i64p, _i64p, _f64p, C.c_int64]),
+    "gne_price_first": (C.c_int, [_vp, _i64p]),
+    "gne_reduced_costs": (C.c_int, [_vp, C.c_int64, C.c_int64, _f64p]),
+    "gne_dev_last_kernel_ms": (C.c_int, [_vp, _f32p]),
+    "gne_dev_launch_count": (C.c_int64, [_vp]),
+    "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
+    "gne_comm_unique_id": (C.c_int, [_u8p]),
+    "gne_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
+    "gne_comm_destroy": (C.c_int, [_vp]),
+    "gne_solver_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_double]),
+    "gne_solver_create_from_col": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_char_p]),
+    "gne_solver_destroy": (C.c_int, [_vp]),
+    "gne_solver_set_rules": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "gne_solver_set_comm": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
+    "gne_solver_set_trace": (C.c_int, [_vp, _i32p, _i32p, C.c_int64]),
+    "gne_solver_trace_len": (C.c_int64, [_vp]),
+    "gne_solver_solve": (C.c_int, [_vp, C.c_int, C.c_int64, _i64p, C.POINTER(C.c_int)]),
+    "gne_solver_num_nodes": (C.c_int, [_vp]),
+    "gne_solver_num_vars": (C.c_int64, [_vp]),
+    "gne_solver_objective": (C.c_double, [_vp]),
+    "gne_solver_feasible": (C.c_int, [_vp]),
+    "gne_solver_get_flows": (C.c_int, [_vp, _f64p]),
+    "gne_solver_get_potentials": (C.c_int, [_vp, _f64p]),
+    "gne_solver_get_states": (C.c_int, [_vp, _i32p]),
+    "gne_solver_get_forest": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "gne_solver_get_counters": (C.c_int, [_vp, _f64p]),
+    "gne_solver_device": (_vp, [_vp]),
+    "gne_forest_replay": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, C.c_int64, _i32p, _i32p,
+                                    _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "gne_merge_lv_shards": (C.c_int, [C.c_int, _f64p, C.POINTER(C.c_int), _i64p, _i64p, _f64p, C.c_int64,
+                                      _f64p, _i64p, _i64p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gne_generate_instance": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class GneError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = lib.gne_last_error()
+        RuntimeError.__init__(self, "%s failed with status %d: %s" % (where, code, msg.decode() if msg else ""))
+
+
+def _ck(code, where):
+    if code != 0:
+        raise GneError(code, where)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _arr(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def cuda_device_count():
+    return lib.gne_cuda_device_count()
+
+
+def generate_instance(n, m, seed, mode="lossy"):
+    """Deterministic large synthetic instance (arcs sorted by (tail, head)); see gne_generate_instance."""
+    mode_id = dict(wide=0, lossy=1, near1=2, pow2=3)[mode]
+    tail = np.empty(m, np.int32); head = np.empty(m, np.int32)
+    ub = np.empty(m); cost = np.empty(m); mult = np.empty(m); supply = np.empty(n)
+    _ck(lib.gne_generate_instance(n, m, seed, mode_id, _p(tail, _i32p), _p(head, _i32p), _p(ub, _f64p), _p(cost, _f64p),
+                                  _p(mult, _f64p), _p(supply, _f64p)), "gne_generate_instance")
+    return dict(n=n, tail=tail, head=head, ub=ub, cost=cost, mult=mult, supply=supply)
+
+
+class Device:
+    """Layer 1: the device operators on a nonbasic structure-of-arrays in position order."""
+
+    def __init__(self, n, capacity, device=0, shard=None):
+        self.h = _vp()
+        lo, hi = shard if shard is not None else (0, capacity)
+        _ck(lib.gne_dev_create(C.byref(self.h), device, n, capacity, lo, hi), "gne_dev_create")
+        self.n = n
+        self.capacity = capacity
+        self.N = 0
+
+    def close(self):
+        if self.h:
+            lib.gne_dev_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nb_reset(self, tail, head, cost, mult, state):
+        tail = _arr(tail, np.int32); head = _arr(head, np.int32); cost = _arr(cost, np.float64)
+        mult = _arr(mult, np.float64); state = _arr(state, np.int8)
+        self.N = len(tail)
+        _ck(lib.gne_nb_reset(self.h, self.N, _p(tail, _i32p), _p(head, _i32p), _p(cost, _f64p), _p(mult, _f64p),
+                             _p(state, _i8p)), "gne_nb_reset")
+
+    def nb_set_costs(self, cost):
+        cost = _arr(cost, np.float64)
+        _ck(lib.gne_nb_set_costs(self.h, len(cost), _p(cost, _f64p)), "gne_nb_set_costs")
+
+    def nb_write(self, pos, tail, head, cost, mult, state):
+        _ck(lib.gne_nb_write(self.h, pos, tail, head, cost, mult, state), "gne_nb_write")
+
+    def nb_set_count(self, N):
+        self.N = N
+        _ck(lib.gne_nb_set_count(self.h, N), "gne_nb_set_count")
+
+    def nb_read(self, lo, hi):
+        c = hi - lo
+        tail = np.empty(c, np.int32); head = np.empty(c, np.int32); cost = np.empty(c); mult = np.empty(c)
+        state = np.empty(c, np.int8)
+        _ck(lib.gne_nb_read(self.h, lo, hi, _p(tail, _i32p), _p(head, _i32p), _p(cost, _f64p), _p(mult, _f64p),
+                            _p(state, _i8p)), "gne_nb_read")
+        return tail, head, cost, mult, state
+
+    def pot_set_all(self, pi):
+        pi = _arr(pi, np.float64)
+        assert len(pi) == self.n
+        _ck(lib.gne_pot_set_all(self.h, _p(pi, _f64p)), "gne_pot_set_all")
+
+    def pot_set(self, node, val):
+        node = _arr(node, np.int32); val = _arr(val, np.float64)
+        _ck(lib.gne_pot_set(self.h, len(node), _p(node, _i32p), _p(val, _f64p)), "gne_pot_set")
+
+    def pot_get_all(self):
+        pi = np.empty(self.n)
+        _ck(lib.gne_pot_get_all(self.h, _p(pi, _f64p)), "gne_pot_get_all")
+        return pi
+
+    def pot_update_nodes(self, node, a0, a1, slot):
+        node = _arr(node, np.int32); a0 = _arr(a0, np.float64); a1 = _arr(a1, np.float64); slot = _arr(slot, np.int32)
+        _ck(lib.gne_pot_update_nodes(self.h, len(node), _p(node, _i32p), _p(a0, _f64p), _p(a1, _f64p), _p(slot, _i32p)),
+            "gne_pot_update_nodes")
+
+    def pot_update_thetas(self, slot, theta):
+        slot = _arr(slot, np.int32); theta = _arr(theta, np.float64)
+        _ck(lib.gne_pot_update_thetas(self.h, len(slot), _p(slot, _i32p), _p(theta, _f64p)), "gne_pot_update_thetas")
+
+    def pot_finalize(self):
+        _ck(lib.gne_pot_finalize(self.h), "gne_pot_finalize")
+
+    def price_lv(self, cap=1 << 20):
+        largest = C.c_double(0); count = C.c_int64(0); anyv = C.c_int(0)
+        buf = np.empty(cap, np.int64)
+        _ck(lib.gne_price_lv(self.h, C.byref(largest), C.byref(count), _p(buf, _i64p), cap, C.byref(anyv)), "gne_price_lv")
+        return largest.value, buf[:count.value].copy(), bool(anyv.value)
+
+    def price_qs(self, cursor, want):
+        bp = C.c_int64(0); bv = C.c_double(0); nc = C.c_int64(0); sc = C.c_int64(0); vi = C.c_int64(0)
+        _ck(lib.gne_price_qs(self.h, cursor, want, C.byref(bp), C.byref(bv), C.byref(nc), C.byref(sc), C.byref(vi)),
+            "gne_price_qs")
+        return dict(best_pos=bp.value, best_viol=bv.value, new_cursor=nc.value, scanned=sc.value, violations=vi.value)
+
+    def price_violators(self, threshold=0.0, cap=None):
+        cap = cap if cap is not None else max(self.N, 1)
+        pos = np.empty(cap, np.int64); viol = np.empty(cap)
+        count = C.c_int64(0)
+        _ck(lib.gne_price_violators(self.h, threshold, C.byref(count), _p(pos, _i64p), _p(viol, _f64p), cap),
+            "gne_price_violators")
+        return pos[:count.value].copy(), viol[:count.value].copy()
+
+    def price_first(self):
+        pos = C.c_int64(0)
+        _ck(lib.gne_price_first(self.h, C.byref(pos)), "gne_price_first")
+        return pos.value
+
+    def reduced_costs(self, lo=0, hi=None):
+        hi = self.N if hi is None else hi
+        rc = np.empty(hi - lo)
+        _ck(lib.gne_reduced_costs(self.h, lo, hi, _p(rc, _f64p)), "gne_reduced_costs")
+        return rc
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        lib.gne_dev_last_kernel_ms(self.h, C.byref(ms))
+        return ms.value
+
+    def launch_count(self):
+        return lib.gne_dev_launch_count(self.h)
+
+    def bench_price_lv(self, reps, flush_l2):
+        ms = np.zeros(reps, np.float32)
+        _ck(lib.gne_bench_price_lv(self.h, reps, 1 if flush_l2 else 0, _p(ms, _f32p)), "gne_bench_price_lv")
+        return ms
+
+
+class _BorrowedDevice(Device):
+    def __init__(self, handle, n, capacity, N):
+        self.h = handle
+        self.n = n
+        self.capacity = capacity
+        self.N = N
+
+    def close(self):
+        self.h = _vp()
+
+
+class Solver:
+    """Layer 2: the host mirror of GenNetEq (initialize / solve) driving the device operators."""
+
+    COUNTERS = ("pricing_s", "potentials_s", "pivot_s", "total_s", "arcs_priced", "kernel_ms", "h2d_bytes",
+                "d2h_bytes", "launches", "pivots", "trees_s", "flows_s")
+
+    def __init__(self, n=None, tail=None, head=None, ub=None, cost=None, mult=None, supply=None, big_m=-1.0,
+                 col_path=None, device=0, rule1="LVW", rule2=None, trace_cap=4_000_000):
+        self.h = _vp()
+        if col_path is not None:
+            _ck(lib.gne_solver_create_from_col(C.byref(self.h), device, col_path.encode()), "gne_solver_create_from_col")
+        else:
+            tail = _arr(tail, np.int32); head = _arr(head, np.int32)
+            ub = _arr(ub, np.float64); cost = _arr(cost, np.float64); mult = _arr(mult, np.float64)
+            supply = _arr(supply, np.float64)
+            _ck(lib.gne_solver_create(C.byref(self.h), device, n, len(tail), _p(tail, _i32p), _p(head, _i32p), _p(ub, _f64p),
+                                      _p(cost, _f64p), _p(mult, _f64p), _p(supply, _f64p), big_m), "gne_solver_create")
+        self.n = lib.gne_solver_num_nodes(self.h)
+        self.M = lib.gne_solver_num_vars(self.h)
+        r1 = RULES[rule1] if isinstance(rule1, str) else rule1
+        r2 = r1 if rule2 is None else (RULES[rule2] if isinstance(rule2, str) else rule2)
+        lib.gne_solver_set_rules(self.h, r1, r2)
+        self._te = np.zeros(trace_cap, np.int32)
+        self._tl = np.zeros(trace_cap, np.int32)
+        lib.gne_solver_set_trace(self.h, _p(self._te, _i32p), _p(self._tl, _i32p), trace_cap)
+
+    def close(self):
+        if self.h:
+            lib.gne_solver_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_comm(self, unique_id, rank, nranks):
+        uid = _arr(unique_id, np.uint8)
+        _ck(lib.gne_solver_set_comm(self.h, _p(uid, _u8p), rank, nranks), "gne_solver_set_comm")
+
+    def solve(self, presolve, max_pivots=-1):
+        it = C.c_int64(0); fin = C.c_int(0)
+        _ck(lib.gne_solver_solve(self.h, 1 if presolve else 0, max_pivots, C.byref(it), C.byref(fin)), "gne_solver_solve")
+        return it.value, bool(fin.value)
+
+    def solve_both(self):
+        p1, _ = self.solve(True)
+        p2, _ = self.solve(False)
+        return p1, p2
+
+    @property
+    def trace(self):
+        k = lib.gne_solver_trace_len(self.h)
+        return self._te[:k].copy(), self._tl[:k].copy()
+
+    @property
+    def objective(self):
+        return lib.gne_solver_objective(self.h)
+
+    @property
+    def feasible(self):
+        return bool(lib.gne_solver_feasible(self.h))
+
+    def flows(self):
+        a = np.empty(self.M)
+        _ck(lib.gne_solver_get_flows(self.h, _p(a, _f64p)), "gne_solver_get_flows")
+        return a
+
+    def potentials(self):
+        a = np.empty(self.n)
+        _ck(lib.gne_solver_get_potentials(self.h, _p(a, _f64p)), "gne_solver_get_potentials")
+        return a
+
+    def states(self):
+        a = np.empty(self.M, np.int32)
+        _ck(lib.gne_solver_get_states(self.h, _p(a, _i32p)), "gne_solver_get_states")
+        return a
+
+    def forest(self):
+        arrs = [np.empty(self.n, np.int32) for _ in range(5)]
+        _ck(lib.gne_solver_get_forest(self.h, *[_p(a, _i32p) for a in arrs]), "gne_solver_get_forest")
+        return dict(zip(("tree", "pred", "predArc", "depth", "thread"), arrs))
+
+    def counters(self):
+        a = np.zeros(12)
+        lib.gne_solver_get_counters(self.h, _p(a, _f64p))
+        return dict(zip(self.COUNTERS, a.tolist()))
+
+    def device(self):
+        h = lib.gne_solver_device(self.h)
+        return _BorrowedDevice(_vp(h), self.n + 16, self.M - self.n + 16, self.M - self.n) if h else None
+
+
+def forest_replay(n, tail, head, supply, e, l):
+    """Host-only: apply the basis exchanges of a pivot trace to a fresh forest (no GPU needed)."""
+    tail = _arr(tail, np.int32); head = _arr(head, np.int32); supply = _arr(supply, np.float64)
+    e = _arr(e, np.int32); l = _arr(l, np.int32)
+    arrs = [np.empty(n, np.int32) for _ in range(5)]
+    _ck(lib.gne_forest_replay(n, len(tail), _p(tail, _i32p), _p(head, _i32p), _p(supply, _f64p), len(e), _p(e, _i32p),
+                              _p(l, _i32p), *[_p(a, _i32p) for a in arrs]), "gne_forest_replay")
+    return dict(zip(("tree", "pred", "predArc", "depth", "thread"), arrs))
+
+
+def merge_lv_shards(maxima, anys, counts, list_pos, list_viol, stride, cap=1 << 16):
+    """Host-only: what every rank does with the all-gathered per-shard LV records."""
+    maxima = _arr(maxima, np.float64); anys = _arr(anys, np.int32); counts = _arr(counts, np.int64)
+    list_pos = _arr(list_pos, np.int64); list_viol = _arr(list_viol, np.float64)
+    largest = C.c_double(0); count = C.c_int64(0); anyv = C.c_int(0); need = C.c_int(0)
+    out = np.empty(cap, np.int64)
+    _ck(lib.gne_merge_lv_shards(len(maxima), _p(maxima, _f64p), _p(anys, C.POINTER(C.c_int)), _p(counts, _i64p),
+                                _p(list_pos, _i64p), _p(list_viol, _f64p), stride, C.byref(largest), C.byref(count),
+                                _p(out, _i64p), cap, C.byref(anyv), C.byref(need)), "gne_merge_lv_shards")
+    return dict(largest=largest.value, list=out[:count.value].copy(), any=bool(anyv.value), need_fallback=bool(need.value))

@@ -1,0 +1,263 @@
+// genneteq_b200 — layer 2 of the C ABI (solver mirror), the sparse Graph loader for the
+// reference's text format, and the synthetic-instance generator used by the benchmarks.
+#include "gne_solver.h"
+#include "gne_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace gneb200;
+
+// ------------------------------------------------------------------------------------------
+// Graph: graph.cpp:31-53, 248-296, 358-447 read sparsely
+// ------------------------------------------------------------------------------------------
+int Graph::initializeFromArrays(int n, int64_t m, const int32_t *t, const int32_t *h, const double *ub,
+                                const double *c, const double *mu, const double *sup, double bigMIn)
+{
+    if (n <= 0 || m < 0) { gne_set_error("Graph: bad sizes"); return GNE_ERR_ARG; }
+    numNodes = n; numEqualFlowSets = 0;
+    tail.clear(); head.clear(); cap.clear(); cost.clear(); mult.clear();
+    double maxCost = 0.0, maxCap = 0.0;                 // graph.cpp:36-37, 412-417
+    for (int64_t a = 0; a < m; ++a) {
+        if (t[a] < 0 || t[a] >= n || h[a] < 0 || h[a] >= n) { gne_set_error("Graph: arc %lld has a node out of range", (long long) a); return GNE_ERR_ARG; }
+        if (a > 0 && (t[a] < t[a - 1] || (t[a] == t[a - 1] && h[a] <= h[a - 1]))) {
+            gne_set_error("Graph: arcs must be sorted by (tail, head) without duplicates (arc %lld)", (long long) a);
+            return GNE_ERR_ARG;
+        }
+        if (maxCost < c[a]) maxCost = c[a];
+        if (maxCap < ub[a]) maxCap = ub[a];
+        if (ub[a] <= 0.0) continue;                     // "arc doesn't exist", gneInit.cpp:84
+        tail.push_back(t[a]); head.push_back(h[a]); cap.push_back(ub[a]); cost.push_back(c[a]); mult.push_back(mu[a]);
+    }
+    supplies.assign(sup, sup + n);
+    const int numArcs = (int) m;
+    bigM = (bigMIn >= 0.0) ? bigMIn : numArcs * maxCost * maxCap;      // graph.cpp:43
+    return GNE_OK;
+}
+
+int Graph::initialize(Config *conf)
+{
+    FILE *f = fopen(conf->inFile, "r");
+    if (!f) { gne_set_error("Unable to open file: %s", conf->inFile); return GNE_ERR_ARG; }
+    int n = 0, numArcs = 0, numEq = 0;
+    long arcsRead = 0;
+    bool haveP = false;
+    double maxCost = 0.0, maxCap = 0.0;
+    struct Rec { double ub, cost, mult; };
+    std::map<std::pair<int32_t, int32_t>, Rec> arcs;    // a later line overwrites (dense matrices do, graph.cpp:406-410)
+    std::vector<double> sup;
+    char *line = nullptr;
+    size_t lcap = 0;
+    int rc = GNE_OK;
+    while (getline(&line, &lcap, f) > 0) {
+        if (line[0] == '\n' || line[0] == '\0') continue;
+        if (line[0] == 'p') {                           // processProblemLine, graph.cpp:358-372
+            char tmp[64];
+            if (sscanf(line, "p %63s %d %d %d", tmp, &n, &numArcs, &numEq) != 4) { gne_set_error("Improperly formatted problem line"); rc = GNE_ERR_ARG; break; }
+            if (numEq != 0) { gne_set_error("equal-flow sets are out of scope"); rc = GNE_ERR_UNSUPPORTED; break; }
+            sup.assign(n, 0.0);
+            haveP = true;
+        } else if (line[0] == 'a' || line[0] == 'e') {  // processArcLine, graph.cpp:382-419 ('e' lines fail its sscanf)
+            int n1, n2, eq;
+            double lb, ub, c, mu;
+            ++arcsRead;
+            if (line[0] == 'e' || sscanf(line, "a %d %d %lf %lf %lf %lf %d", &n1, &n2, &lb, &ub, &c, &mu, &eq) != 7) {
+                gne_set_error("Improperly formatted arc line"); rc = GNE_ERR_ARG; break;
+            }
+            if (!haveP || n1 < 1 || n1 > n || n2 < 1 || n2 > n) { gne_set_error("arc line names a node out of range"); rc = GNE_ERR_ARG; break; }
+            if (eq - 1 >= 0) { gne_set_error("equal-flow sets are out of scope"); rc = GNE_ERR_UNSUPPORTED; break; }
+            Rec r; r.ub = ub; r.cost = c; r.mult = mu;  // the lower bound is parsed and dropped (graph.cpp:386-410)
+            arcs[std::make_pair((int32_t) (n1 - 1), (int32_t) (n2 - 1))] = r;
+            if (maxCost < c) maxCost = c;
+            if (maxCap < ub) maxCap = ub;
+        } else if (line[0] == 'n') {                    // processNodeLine, graph.cpp:430-447
+            int id;
+            double s;
+            if (sscanf(line, "n %d %lf", &id, &s) != 2) { gne_set_error("Improperly formatted node line"); rc = GNE_ERR_ARG; break; }
+            if (!haveP || id < 1 || id > n) { gne_set_error("node line out of range"); rc = GNE_ERR_ARG; break; }
+            sup[id - 1] = s;
+        }                                               // anything else is a comment
+    }
+    free(line);
+    fclose(f);
+    if (rc) return rc;
+    if (!haveP) { gne_set_error("no problem line"); return GNE_ERR_ARG; }
+    if (arcsRead != numArcs) { gne_set_error("Number of arcs specified does not match the number of arcs in the file"); return GNE_ERR_ARG; }
+    numNodes = n; numEqualFlowSets = 0;
+    tail.clear(); head.clear(); cap.clear(); cost.clear(); mult.clear();
+    for (std::map<std::pair<int32_t, int32_t>, Rec>::const_iterator it = arcs.begin(); it != arcs.end(); ++it) {
+        if (it->second.ub <= 0.0) continue;
+        tail.push_back(it->first.first); head.push_back(it->first.second);
+        cap.push_back(it->second.ub); cost.push_back(it->second.cost); mult.push_back(it->second.mult);
+    }
+    supplies = sup;
+    bigM = numArcs * maxCost * maxCap;                  // graph.cpp:43
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// layer 2 C ABI
+// ------------------------------------------------------------------------------------------
+struct gne_solver {
+    GenNetEq solver;
+};
+
+extern "C" int gne_solver_create(gne_solver **out, int cudaDevice, int n, int64_t m, const int32_t *tail, const int32_t *head,
+                                 const double *ub, const double *cost, const double *mult, const double *supply, double bigM)
+{
+    if (!out) return GNE_ERR_ARG;
+    if (gne_cuda_device_count() <= 0) { gne_set_error("no CUDA device: genneteq_b200 has no CPU fallback"); return GNE_ERR_CUDA; }
+    Graph g;
+    int rc = g.initializeFromArrays(n, m, tail, head, ub, cost, mult, supply, bigM);
+    if (rc) return rc;
+    gne_solver *s = new gne_solver();
+    rc = s->solver.initialize(&g, 0, cudaDevice);
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return GNE_OK;
+}
+
+extern "C" int gne_solver_create_from_col(gne_solver **out, int cudaDevice, const char *path)
+{
+    if (!out || !path) return GNE_ERR_ARG;
+    if (gne_cuda_device_count() <= 0) { gne_set_error("no CUDA device: genneteq_b200 has no CPU fallback"); return GNE_ERR_CUDA; }
+    Config conf;
+    conf.inFile = path;
+    Graph g;
+    int rc = g.initialize(&conf);
+    if (rc) return rc;
+    gne_solver *s = new gne_solver();
+    rc = s->solver.initialize(&g, conf.initType, cudaDevice);
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return GNE_OK;
+}
+
+extern "C" int gne_solver_destroy(gne_solver *s) { delete s; return GNE_OK; }
+extern "C" int gne_solver_set_rules(gne_solver *s, int p1, int p2) { s->solver.phaseIpivot = p1; s->solver.phaseIIpivot = p2; return GNE_OK; }
+extern "C" int gne_solver_set_comm(gne_solver *s, const uint8_t id[128], int rank, int nranks) { return s->solver.setComm(id, rank, nranks); }
+extern "C" int gne_solver_set_trace(gne_solver *s, int32_t *e, int32_t *l, int64_t cap) { s->solver.setTrace(e, l, cap); return GNE_OK; }
+extern "C" int64_t gne_solver_trace_len(const gne_solver *s) { return s->solver.getTraceLen(); }
+extern "C" int gne_solver_solve(gne_solver *s, int presolve, int64_t maxPivots, int64_t *iters, int *finished)
+{
+    int64_t it = 0;
+    int fin = 0;
+    int rc = s->solver.solve(presolve != 0, maxPivots, &it, &fin);
+    if (iters) *iters = it;
+    if (finished) *finished = fin;
+    return rc;
+}
+extern "C" int gne_solver_num_nodes(const gne_solver *s) { return s->solver.getNumNodes(); }
+extern "C" int64_t gne_solver_num_vars(const gne_solver *s) { return s->solver.getNumVars(); }
+extern "C" double gne_solver_objective(const gne_solver *s) { return s->solver.getFlowCost(); }
+extern "C" int gne_solver_feasible(const gne_solver *s) { return s->solver.getIsInfeasible() ? 0 : 1; }
+extern "C" int gne_solver_get_flows(gne_solver *s, double *out) { s->solver.getFlows(out); return GNE_OK; }
+extern "C" int gne_solver_get_potentials(gne_solver *s, double *out) { return s->solver.getPotentials(out); }
+extern "C" int gne_solver_get_states(gne_solver *s, int32_t *out) { s->solver.getStates(out); return GNE_OK; }
+extern "C" int gne_solver_get_forest(gne_solver *s, int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread)
+{
+    const Forest &f = s->solver.getForest();
+    const int n = s->solver.getNumNodes();
+    for (int i = 0; i < n; ++i) { tree[i] = f.treeSlot[i]; pred[i] = f.pred[i]; predArc[i] = f.predArc[i]; depth[i] = f.depth[i]; thread[i] = f.thread[i]; }
+    return GNE_OK;
+}
+extern "C" int gne_solver_get_counters(const gne_solver *s, double *out12) { s->solver.getCounters(out12); return GNE_OK; }
+extern "C" gne_dev *gne_solver_device(gne_solver *s) { return s->solver.device(); }
+
+// ------------------------------------------------------------------------------------------
+// host-only forest replay (no device): the basis exchanges of a given pivot trace
+// ------------------------------------------------------------------------------------------
+extern "C" int gne_forest_replay(int n, int64_t m, const int32_t *tailIn, const int32_t *headIn, const double *supply,
+                                 int64_t pivots, const int32_t *e, const int32_t *l,
+                                 int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread)
+{
+    (void) supply;
+    const int64_t M = m + n;
+    std::vector<int32_t> tail((size_t) M), head((size_t) M);
+    for (int64_t a = 0; a < m; ++a) { tail[a] = tailIn[a]; head[a] = headIn[a]; }
+    for (int i = 0; i < n; ++i) { tail[m + i] = i; head[m + i] = i; }
+    Forest f;
+    f.init(n, tail.data(), head.data());
+    std::vector<uint8_t> basic((size_t) M, 0);
+    for (int i = 0; i < n; ++i) { if (f.insertArc((int32_t) (m + i))) return GNE_ERR_TREE; basic[m + i] = 1; }
+    f.updateTrees();
+    for (int64_t k = 0; k < pivots; ++k) {
+        if (e[k] == l[k]) continue;                     // bound flip: the forest is untouched (gnePivot.cpp:256-267)
+        if (!basic[l[k]] || basic[e[k]]) { gne_set_error("gne_forest_replay: pivot %lld is not a valid exchange", (long long) k); return GNE_ERR_ARG; }
+        int rc = f.removeArc(l[k]);
+        if (!rc) rc = f.insertArc(e[k]);
+        if (rc) { gne_set_error("gne_forest_replay: forest error %d at pivot %lld", rc, (long long) k); return GNE_ERR_TREE; }
+        basic[l[k]] = 0; basic[e[k]] = 1;
+        f.updateTrees();
+    }
+    for (int i = 0; i < n; ++i) { tree[i] = f.treeSlot[i]; pred[i] = f.pred[i]; predArc[i] = f.predArc[i]; depth[i] = f.depth[i]; thread[i] = f.thread[i]; }
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic instances for the large benchmark configurations: the
+// Appendix-A family (ring + random distinct arcs, same value ranges, 6-decimal values) from a
+// counter-based generator, so that 10^8 arcs take seconds and every rank builds the same arrays.
+// ------------------------------------------------------------------------------------------
+static inline uint64_t mix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+static inline double unit(uint64_t h) { return (double) (h >> 11) * (1.0 / 9007199254740992.0); }
+static inline double r6(double x) { return floor(x * 1.0e6 + 0.5) / 1.0e6; }
+
+extern "C" int gne_generate_instance(int n, int64_t m, uint64_t seed, int mode,
+                                     int32_t *tail, int32_t *head, double *ub, double *cost, double *mult, double *supply)
+{
+    if (n < 3 || m < n || m > (int64_t) n * (n - 1)) { gne_set_error("gne_generate_instance: need n >= 3 and n <= m <= n(n-1)"); return GNE_ERR_ARG; }
+    const int64_t base = m / n, rem = m % n;
+    int64_t a = 0;
+    std::vector<int32_t> hs;
+    for (int i = 0; i < n; ++i) {
+        const int64_t d = base + (i < rem ? 1 : 0);
+        hs.clear();
+        hs.push_back((i + 1) % n);                      // ring arc keeps the graph connected
+        uint64_t ctr = 0;
+        while ((int64_t) hs.size() < d) {
+            const int64_t want = d - (int64_t) hs.size();
+            for (int64_t k = 0; k < want; ++k) {
+                const uint64_t h = mix64(mix64(seed ^ ((uint64_t) i << 20)) + (ctr++));
+                const int32_t j = (int32_t) (h % (uint64_t) n);
+                if (j != i) hs.push_back(j);
+            }
+            std::sort(hs.begin(), hs.end());
+            hs.erase(std::unique(hs.begin(), hs.end()), hs.end());
+        }
+        std::sort(hs.begin(), hs.end());
+        for (size_t k = 0; k < hs.size(); ++k, ++a) {
+            const uint64_t key = mix64(seed * 0x100000001B3ULL + (uint64_t) a);
+            tail[a] = i; head[a] = hs[k];
+            ub[a] = r6(10.0 + 90.0 * unit(mix64(key + 1)));
+            cost[a] = r6(1.0 + 99.0 * unit(mix64(key + 2)));
+            const double u = unit(mix64(key + 3));
+            double g;
+            if (mode == 1) g = 0.70 + 0.29 * u;
+            else if (mode == 2) g = 0.9 + 0.2 * u;
+            else if (mode == 3) { static const double pw[5] = { 0.5, 0.75, 1.25, 1.5, 2.0 }; g = pw[(int) (u * 5.0) % 5]; }
+            else g = 0.5 + u;
+            mult[a] = r6(g);
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        const uint64_t h = mix64(seed + 0xABCDEFULL * (uint64_t) (i + 1));
+        const int kind = (int) (h % 20);
+        const double amount = (double) (1 + (int) ((h >> 8) % 20));
+        if (kind == 0) supply[i] = amount * (mode == 1 ? 3.0 : 1.0);
+        else if (kind == 1) supply[i] = -amount;
+        else supply[i] = 0.0;
+    }
+    return GNE_OK;
+}

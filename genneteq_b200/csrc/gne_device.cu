@@ -1,0 +1,789 @@
+// genneteq_b200 — layer 1 of the C ABI: device-resident state and kernel launches.
+// See include/genneteq_b200.h for the contract of every entry point.
+#include "gne_kernels.cuh"
+#include "gne_internal.h"
+#include "../../include/genneteq_b200.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <vector>
+
+using namespace gne;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void gne_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *gne_last_error(void) { return g_err; }
+extern "C" const char *gne_version(void) { return "genneteq_b200 0.1 (sm_100a)"; }
+
+extern "C" int gne_cuda_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            gne_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return GNE_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library loads on machines without NCCL; gne_comm_* fail cleanly.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char b[128]; };                         // ncclUniqueId is 128 opaque bytes, passed by value
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool nccl_load()
+{
+    if (g_nccl.lib) return true;
+    const char *names[] = { "libnccl.so.2", "libnccl.so", nullptr };
+    for (int i = 0; names[i] && !g_nccl.lib; ++i) g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl.lib) { gne_set_error("NCCL not found: %s", dlerror()); return false; }
+    *(void **) &g_nccl.GetUniqueId = dlsym(g_nccl.lib, "ncclGetUniqueId");
+    *(void **) &g_nccl.CommInitRank = dlsym(g_nccl.lib, "ncclCommInitRank");
+    *(void **) &g_nccl.CommDestroy = dlsym(g_nccl.lib, "ncclCommDestroy");
+    *(void **) &g_nccl.AllGather = dlsym(g_nccl.lib, "ncclAllGather");
+    *(void **) &g_nccl.GetErrorString = dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+        gne_set_error("NCCL symbols missing");
+        return false;
+    }
+    return true;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct gne_dev {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int n = 0;
+    int64_t cap = 0, lo = 0, hi = 0, N = 0;        // global capacity, shard [lo, hi), global count
+    int64_t localCap = 0;                          // allocated shard length (multiple of TILE)
+    // nonbasic shard (structure-of-arrays, local index = pos - lo)
+    int32_t *tail = nullptr, *head = nullptr;
+    double *cost = nullptr, *mult = nullptr;
+    int8_t *state = nullptr;
+    // nodes
+    double *a0 = nullptr, *a1 = nullptr, *theta = nullptr, *pi = nullptr;
+    int32_t *slot = nullptr;
+    // tile scratch
+    int G = 0;                                     // tiles covering localCap
+    LvTiles lv{};
+    int32_t *tileCnt = nullptr;
+    int64_t *tileOff = nullptr;
+    QsTiles qs{};
+    int GQ = 0;
+    unsigned long long *firstPos = nullptr;
+    // mapped pinned host blocks
+    LvResult *lvRes = nullptr;
+    QsState *qsState = nullptr;
+    int64_t *hostScalar = nullptr;                 // [0] compaction total, [1] first pos
+    // staging for updates (pinned host + device), grown on demand
+    void *stageHost = nullptr, *stageDev = nullptr;
+    size_t stageBytes = 0;
+    // compaction output (device), grown on demand
+    int64_t *outPos = nullptr;
+    double *outViol = nullptr;
+    int64_t outCap = 0;
+    double *flushBuf = nullptr;
+    int64_t flushLen = 0;
+    float lastMs = 0.f;
+    int64_t launches = 0;
+    int64_t h2dBytes = 0, d2hBytes = 0;
+    int64_t qsWindow = 0;                          // adaptive window of the quickSelect scan
+    NbWriteOps pending{};                          // queued gne_nb_write records (<= 8)
+    // multi-GPU
+    void *comm = nullptr;
+    int rank = 0, nranks = 1;
+    void *gatherSend = nullptr, *gatherRecv = nullptr, *gatherHost = nullptr;
+};
+
+static NbView view_of(const gne_dev *d)
+{
+    NbView v;
+    v.tail = d->tail; v.head = d->head; v.cost = d->cost; v.mult = d->mult; v.state = d->state;
+    v.lo = d->lo;
+    v.end = std::min(d->N, d->hi);
+    return v;
+}
+
+static inline int tiles_for(const gne_dev *d)
+{
+    // tiles that contain at least one priced position of this shard
+    const int64_t end = std::min(d->N, d->hi);
+    if (end <= d->lo) return 0;
+    return (int) ((end - d->lo + TILE - 1) / TILE);
+}
+
+static int ensure_stage(gne_dev *d, size_t bytes)
+{
+    if (bytes <= d->stageBytes) return GNE_OK;
+    size_t nb = std::max<size_t>(bytes, std::max<size_t>(2 * d->stageBytes, (size_t) 1 << 20));
+    if (d->stageHost) cudaFreeHost(d->stageHost);
+    if (d->stageDev) cudaFree(d->stageDev);
+    d->stageHost = nullptr; d->stageDev = nullptr; d->stageBytes = 0;
+    CK(cudaHostAlloc(&d->stageHost, nb, cudaHostAllocDefault));
+    CK(cudaMalloc(&d->stageDev, nb));
+    d->stageBytes = nb;
+    return GNE_OK;
+}
+
+static int ensure_out(gne_dev *d, int64_t cap)
+{
+    if (cap <= d->outCap) return GNE_OK;
+    int64_t nc = std::max<int64_t>(cap, std::max<int64_t>(2 * d->outCap, 1 << 16));
+    if (d->outPos) cudaFree(d->outPos);
+    if (d->outViol) cudaFree(d->outViol);
+    d->outPos = nullptr; d->outViol = nullptr; d->outCap = 0;
+    CK(cudaMalloc(&d->outPos, sizeof(int64_t) * nc));
+    CK(cudaMalloc(&d->outViol, sizeof(double) * nc));
+    d->outCap = nc;
+    return GNE_OK;
+}
+
+extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi)
+{
+    if (!out || n <= 0 || nbCapacity <= 0 || shardLo < 0 || shardHi < shardLo) { gne_set_error("gne_dev_create: bad argument"); return GNE_ERR_ARG; }
+    if (shardLo % TILE != 0) { gne_set_error("gne_dev_create: shardLo must be a multiple of %d", TILE); return GNE_ERR_ARG; }
+    int cnt = gne_cuda_device_count();
+    if (cnt <= 0) { gne_set_error("no CUDA device: genneteq_b200 has no CPU fallback"); return GNE_ERR_CUDA; }
+    if (cudaDevice < 0 || cudaDevice >= cnt) { gne_set_error("cuda device %d out of range (%d present)", cudaDevice, cnt); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(cudaDevice));
+    gne_dev *d = new gne_dev();
+    d->device = cudaDevice; d->n = n; d->cap = nbCapacity;
+    d->lo = shardLo; d->hi = std::min(shardHi, nbCapacity); d->N = 0;
+    d->localCap = ((d->hi - d->lo + TILE - 1) / TILE) * TILE;
+    if (d->localCap == 0) d->localCap = TILE;
+    d->G = (int) (d->localCap / TILE);
+    CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&d->ev0));
+    CK(cudaEventCreate(&d->ev1));
+    const size_t L = (size_t) d->localCap;
+    CK(cudaMalloc(&d->tail, 4 * L)); CK(cudaMalloc(&d->head, 4 * L));
+    CK(cudaMalloc(&d->cost, 8 * L)); CK(cudaMalloc(&d->mult, 8 * L)); CK(cudaMalloc(&d->state, L));
+    CK(cudaMemsetAsync(d->tail, 0, 4 * L, d->stream)); CK(cudaMemsetAsync(d->head, 0, 4 * L, d->stream));
+    CK(cudaMemsetAsync(d->cost, 0, 8 * L, d->stream)); CK(cudaMemsetAsync(d->mult, 0, 8 * L, d->stream));
+    CK(cudaMemsetAsync(d->state, 0, L, d->stream));
+    CK(cudaMalloc(&d->a0, 8 * (size_t) n)); CK(cudaMalloc(&d->a1, 8 * (size_t) n));
+    CK(cudaMalloc(&d->theta, 8 * (size_t) n)); CK(cudaMalloc(&d->pi, 8 * (size_t) n));
+    CK(cudaMalloc(&d->slot, 4 * (size_t) n));
+    CK(cudaMemsetAsync(d->a0, 0, 8 * (size_t) n, d->stream)); CK(cudaMemsetAsync(d->a1, 0, 8 * (size_t) n, d->stream));
+    CK(cudaMemsetAsync(d->theta, 0, 8 * (size_t) n, d->stream)); CK(cudaMemsetAsync(d->pi, 0, 8 * (size_t) n, d->stream));
+    CK(cudaMemsetAsync(d->slot, 0, 4 * (size_t) n, d->stream));
+    CK(cudaMalloc(&d->lv.tileMax, 8 * (size_t) d->G)); CK(cudaMalloc(&d->lv.tileCnt, 4 * (size_t) d->G));
+    CK(cudaMalloc(&d->lv.candOff, 4 * (size_t) d->G * CAND_K)); CK(cudaMalloc(&d->lv.candViol, 8 * (size_t) d->G * CAND_K));
+    CK(cudaMalloc(&d->tileCnt, 4 * (size_t) d->G)); CK(cudaMalloc(&d->tileOff, 8 * ((size_t) d->G + 1)));
+    d->GQ = (int) ((d->localCap + QTILE - 1) / QTILE) + 1;
+    CK(cudaMalloc(&d->qs.cnt, 4 * (size_t) d->GQ)); CK(cudaMalloc(&d->qs.bestV, 8 * (size_t) d->GQ)); CK(cudaMalloc(&d->qs.bestJ, 8 * (size_t) d->GQ));
+    CK(cudaMalloc(&d->firstPos, 8));
+    CK(cudaHostAlloc(&d->lvRes, sizeof(LvResult), cudaHostAllocMapped));
+    CK(cudaHostAlloc(&d->qsState, sizeof(QsState), cudaHostAllocMapped));
+    CK(cudaHostAlloc(&d->hostScalar, 64, cudaHostAllocMapped));
+    memset(d->lvRes, 0, sizeof(LvResult));
+    memset(d->qsState, 0, sizeof(QsState));
+    CK(cudaStreamSynchronize(d->stream));
+    *out = d;
+    return GNE_OK;
+}
+
+extern "C" int gne_dev_destroy(gne_dev *d)
+{
+    if (!d) return GNE_OK;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
+                    d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
+                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->stageDev, d->outPos, d->outViol,
+                    d->flushBuf, d->gatherSend, d->gatherRecv };
+    for (void *p : dev) if (p) cudaFree(p);
+    void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost };
+    for (void *p : host) if (p) cudaFreeHost(p);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+    return GNE_OK;
+}
+
+extern "C" int gne_dev_sync(gne_dev *d)
+{
+    CK(cudaSetDevice(d->device));
+    CK(cudaStreamSynchronize(d->stream));
+    return GNE_OK;
+}
+
+extern "C" int gne_dev_last_kernel_ms(gne_dev *d, float *ms) { *ms = d->lastMs; return GNE_OK; }
+extern "C" int64_t gne_dev_launch_count(gne_dev *d) { return d->launches; }
+void gne_dev_traffic(gne_dev *d, int64_t *h2d, int64_t *d2h) { *h2d = d->h2dBytes; *d2h = d->d2hBytes; }
+
+// ------------------------------------------------------------------------------------------
+// nonbasic set mirror
+// ------------------------------------------------------------------------------------------
+extern "C" int gne_nb_reset(gne_dev *d, int64_t N, const int32_t *tail, const int32_t *head, const double *cost,
+                            const double *mult, const int8_t *state)
+{
+    if (N < 0 || N > d->cap) { gne_set_error("gne_nb_reset: N out of range"); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(d->device));
+    d->N = N;
+    const int64_t a = d->lo, b = std::min(N, d->hi);
+    if (b > a) {
+        const size_t c = (size_t) (b - a);
+        CK(cudaMemcpyAsync(d->tail, tail + a, 4 * c, cudaMemcpyHostToDevice, d->stream));
+        CK(cudaMemcpyAsync(d->head, head + a, 4 * c, cudaMemcpyHostToDevice, d->stream));
+        CK(cudaMemcpyAsync(d->cost, cost + a, 8 * c, cudaMemcpyHostToDevice, d->stream));
+        CK(cudaMemcpyAsync(d->mult, mult + a, 8 * c, cudaMemcpyHostToDevice, d->stream));
+        CK(cudaMemcpyAsync(d->state, state + a, c, cudaMemcpyHostToDevice, d->stream));
+        d->h2dBytes += 25 * (int64_t) c;
+    }
+    CK(cudaStreamSynchronize(d->stream));          // caller may free its arrays
+    return GNE_OK;
+}
+
+extern "C" int gne_nb_set_costs(gne_dev *d, int64_t N, const double *cost)
+{
+    if (N != d->N) { gne_set_error("gne_nb_set_costs: N mismatch"); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(d->device));
+    const int64_t a = d->lo, b = std::min(N, d->hi);
+    if (b > a) {
+        CK(cudaMemcpyAsync(d->cost, cost + a, 8 * (size_t) (b - a), cudaMemcpyHostToDevice, d->stream));
+        d->h2dBytes += 8 * (b - a);
+    }
+    CK(cudaStreamSynchronize(d->stream));
+    return GNE_OK;
+}
+
+// queued writes are flushed by one k_nb_write launch before the next kernel that reads the list
+static int flush_writes(gne_dev *d, NbWriteOps &ops)
+{
+    if (ops.n == 0) return GNE_OK;
+    NbMut m; m.tail = d->tail; m.head = d->head; m.cost = d->cost; m.mult = d->mult; m.state = d->state;
+    k_nb_write<<<1, 32, 0, d->stream>>>(m, ops);
+    CK(cudaGetLastError());
+    ++d->launches;
+    d->h2dBytes += 25 * ops.n;
+    ops.n = 0;
+    return GNE_OK;
+}
+
+static NbWriteOps &pending_of(gne_dev *d) { return d->pending; }
+
+int gne_dev_flush(gne_dev *d) { return flush_writes(d, pending_of(d)); }
+
+extern "C" int gne_nb_write(gne_dev *d, int64_t pos, int32_t tail, int32_t head, double cost, double mult, int8_t state)
+{
+    if (pos < 0 || pos >= d->cap) { gne_set_error("gne_nb_write: pos out of range"); return GNE_ERR_ARG; }
+    if (tail < 0 || tail >= d->n || head < 0 || head >= d->n) { gne_set_error("gne_nb_write: node out of range"); return GNE_ERR_ARG; }
+    if (pos < d->lo || pos >= d->hi) return GNE_OK;     // another rank's position
+    CK(cudaSetDevice(d->device));
+    NbWriteOps &ops = pending_of(d);
+    if (ops.n == 8) { int rc = flush_writes(d, ops); if (rc) return rc; }
+    const int i = ops.n++;
+    ops.local[i] = pos - d->lo; ops.tail[i] = tail; ops.head[i] = head; ops.cost[i] = cost; ops.mult[i] = mult; ops.state[i] = state;
+    return GNE_OK;
+}
+
+extern "C" int gne_nb_set_count(gne_dev *d, int64_t N)
+{
+    if (N < 0 || N > d->cap) { gne_set_error("gne_nb_set_count: N out of range"); return GNE_ERR_ARG; }
+    d->N = N;
+    return GNE_OK;
+}
+
+extern "C" int gne_nb_read(gne_dev *d, int64_t lo, int64_t hi, int32_t *tail, int32_t *head, double *cost, double *mult, int8_t *state)
+{
+    if (lo < d->lo || hi > d->hi || hi < lo) { gne_set_error("gne_nb_read: range outside the shard"); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(d->device));
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    const size_t c = (size_t) (hi - lo), o = (size_t) (lo - d->lo);
+    if (tail) CK(cudaMemcpyAsync(tail, d->tail + o, 4 * c, cudaMemcpyDeviceToHost, d->stream));
+    if (head) CK(cudaMemcpyAsync(head, d->head + o, 4 * c, cudaMemcpyDeviceToHost, d->stream));
+    if (cost) CK(cudaMemcpyAsync(cost, d->cost + o, 8 * c, cudaMemcpyDeviceToHost, d->stream));
+    if (mult) CK(cudaMemcpyAsync(mult, d->mult + o, 8 * c, cudaMemcpyDeviceToHost, d->stream));
+    if (state) CK(cudaMemcpyAsync(state, d->state + o, c, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// potentials
+// ------------------------------------------------------------------------------------------
+static inline int blocks_for(int64_t n, int b) { return (int) ((n + b - 1) / b); }
+
+extern "C" int gne_pot_update_nodes(gne_dev *d, int64_t count, const int32_t *node, const double *a0, const double *a1, const int32_t *slot)
+{
+    if (count <= 0) return GNE_OK;
+    CK(cudaSetDevice(d->device));
+    const size_t bytes = (size_t) count * 24;
+    int rc = ensure_stage(d, bytes); if (rc) return rc;
+    CK(cudaStreamSynchronize(d->stream));           // the staging buffer may still be in flight
+    char *h = (char *) d->stageHost;
+    memcpy(h, a0, 8 * (size_t) count);
+    memcpy(h + 8 * (size_t) count, a1, 8 * (size_t) count);
+    memcpy(h + 16 * (size_t) count, node, 4 * (size_t) count);
+    memcpy(h + 20 * (size_t) count, slot, 4 * (size_t) count);
+    CK(cudaMemcpyAsync(d->stageDev, h, bytes, cudaMemcpyHostToDevice, d->stream));
+    char *g = (char *) d->stageDev;
+    k_pot_update_nodes<<<blocks_for(count, 256), 256, 0, d->stream>>>(
+        count, (const int32_t *) (g + 16 * (size_t) count), (const double *) g, (const double *) (g + 8 * (size_t) count),
+        (const int32_t *) (g + 20 * (size_t) count), d->a0, d->a1, d->slot);
+    CK(cudaGetLastError());
+    ++d->launches;
+    d->h2dBytes += (int64_t) bytes;
+    return GNE_OK;
+}
+
+extern "C" int gne_pot_update_thetas(gne_dev *d, int64_t count, const int32_t *slot, const double *theta)
+{
+    if (count <= 0) return GNE_OK;
+    CK(cudaSetDevice(d->device));
+    const size_t bytes = (size_t) count * 12;
+    int rc = ensure_stage(d, bytes); if (rc) return rc;
+    CK(cudaStreamSynchronize(d->stream));
+    char *h = (char *) d->stageHost;
+    memcpy(h, theta, 8 * (size_t) count);
+    memcpy(h + 8 * (size_t) count, slot, 4 * (size_t) count);
+    CK(cudaMemcpyAsync(d->stageDev, h, bytes, cudaMemcpyHostToDevice, d->stream));
+    char *g = (char *) d->stageDev;
+    k_pot_update_thetas<<<blocks_for(count, 256), 256, 0, d->stream>>>(count, (const int32_t *) (g + 8 * (size_t) count), (const double *) g, d->theta);
+    CK(cudaGetLastError());
+    ++d->launches;
+    d->h2dBytes += (int64_t) bytes;
+    return GNE_OK;
+}
+
+extern "C" int gne_pot_finalize(gne_dev *d)
+{
+    CK(cudaSetDevice(d->device));
+    k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi);
+    CK(cudaGetLastError());
+    ++d->launches;
+    return GNE_OK;
+}
+
+extern "C" int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const double *pi)
+{
+    if (count <= 0) return GNE_OK;
+    CK(cudaSetDevice(d->device));
+    const size_t bytes = (size_t) count * 12;
+    int rc = ensure_stage(d, bytes); if (rc) return rc;
+    CK(cudaStreamSynchronize(d->stream));
+    char *h = (char *) d->stageHost;
+    memcpy(h, pi, 8 * (size_t) count);
+    memcpy(h + 8 * (size_t) count, node, 4 * (size_t) count);
+    CK(cudaMemcpyAsync(d->stageDev, h, bytes, cudaMemcpyHostToDevice, d->stream));
+    char *g = (char *) d->stageDev;
+    k_pot_set<<<blocks_for(count, 256), 256, 0, d->stream>>>(count, (const int32_t *) (g + 8 * (size_t) count), (const double *) g, d->pi);
+    CK(cudaGetLastError());
+    ++d->launches;
+    d->h2dBytes += (int64_t) bytes;
+    return GNE_OK;
+}
+
+extern "C" int gne_pot_set_all(gne_dev *d, const double *pi)
+{
+    CK(cudaSetDevice(d->device));
+    CK(cudaMemcpyAsync(d->pi, pi, 8 * (size_t) d->n, cudaMemcpyHostToDevice, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    d->h2dBytes += 8 * (int64_t) d->n;
+    return GNE_OK;
+}
+
+extern "C" int gne_pot_get_all(gne_dev *d, double *pi)
+{
+    CK(cudaSetDevice(d->device));
+    CK(cudaMemcpyAsync(pi, d->pi, 8 * (size_t) d->n, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    d->d2hBytes += 8 * (int64_t) d->n;
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// pricing
+// ------------------------------------------------------------------------------------------
+static int viol_compact_device(gne_dev *d, double threshold, int64_t *total)
+{
+    // ordered compaction of this shard's violators with |rc| >= threshold into d->outPos/outViol
+    const int G = tiles_for(d);
+    *total = 0;
+    if (G == 0) return GNE_OK;
+    NbView nb = view_of(d);
+    k_viol_count<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, threshold, d->tileCnt);
+    k_scan_tiles<<<1, 1024, 0, d->stream>>>(d->tileCnt, d->tileOff, G, d->hostScalar);
+    CK(cudaGetLastError());
+    d->launches += 2;
+    CK(cudaStreamSynchronize(d->stream));
+    *total = d->hostScalar[0];
+    d->d2hBytes += 8;
+    if (*total == 0) return GNE_OK;
+    int rc = ensure_out(d, *total); if (rc) return rc;
+    k_viol_write<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, threshold, d->tileOff, d->outPos, d->outViol, d->outCap);
+    CK(cudaGetLastError());
+    ++d->launches;
+    return GNE_OK;
+}
+
+// The sequential rule of checkVarForOffending (gnePivotRules.cpp:431-452) on a candidate list
+// that holds, in position order, every violator with |rc| >= floorV.  Returns false when the
+// replay could have been influenced by a violator below floorV (see DESIGN.md "LV tie rule"):
+//   (1) the first candidate must clear whatever lower elements left behind, and
+//   (2) the running value must never come within tolerance of an excluded element.
+static bool replay_band_rule(const int64_t *pos, const double *viol, int64_t cnt, double floorV, bool floorIsZero,
+                             std::vector<int64_t> &list, double *largest)
+{
+    list.clear();
+    double L = -1.0;                                    // gnePivotRules.cpp:137
+    double minL = DBL_MAX;
+    for (int64_t i = 0; i < cnt; ++i) {
+        const double v = viol[i];
+        if (L < v - GNE_ROUNDOFF_TOLERANCE) list.clear();
+        if (L <= v + GNE_ROUNDOFF_TOLERANCE) { L = v; list.push_back(pos[i]); if (L < minL) minL = L; }
+    }
+    *largest = L;
+    if (floorIsZero || cnt == 0) return true;           // every violator was in the list
+    // largest excluded value is < floorV; excluded element x is pushed iff L <= x + tol
+    const double below = nextafter(floorV, 0.0);
+    if (!(below < viol[0] - GNE_ROUNDOFF_TOLERANCE)) return false;        // (1)
+    if (!(minL > below + GNE_ROUNDOFF_TOLERANCE)) return false;           // (2)
+    return true;
+}
+
+static int price_lv_local(gne_dev *d)
+{
+    // fused pass over this shard: result in d->lvRes (mapped pinned), device time in d->lastMs
+    const int G = tiles_for(d);
+    NbView nb = view_of(d);
+    CK(cudaEventRecord(d->ev0, d->stream));
+    if (G > 0) {
+        k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv);
+        ++d->launches;
+    }
+    k_price_lv_finish<<<1, TILE_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->lvRes);
+    ++d->launches;
+    CK(cudaEventRecord(d->ev1, d->stream));
+    CK(cudaGetLastError());
+    return GNE_OK;
+}
+
+extern "C" int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count, int64_t *listPos, int64_t cap, int *any)
+{
+    CK(cudaSetDevice(d->device));
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    rc = price_lv_local(d); if (rc) return rc;
+    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
+
+    std::vector<int64_t> list;
+    double L = -1.0;
+    int anyV = 0;
+    bool ok = false;
+    if (d->nranks == 1) {
+        const LvResult *r = d->lvRes;
+        d->d2hBytes += 24 + 16 * std::min<int64_t>(r->count, LV_LIST_CAP);
+        anyV = r->any;
+        if (!anyV) { ok = true; }
+        else if (!r->overflow) {
+            const double floorV = r->maxViol - LV_BAND;
+            ok = replay_band_rule(r->pos, r->viol, r->count, floorV, false, list, &L);
+        }
+        double thr = anyV ? r->maxViol : 0.0;
+        // fallback: widen the band until the replay is provably exact (rare: long runs of near-ties)
+        double width = 16.0 * GNE_ROUNDOFF_TOLERANCE;
+        while (!ok) {
+            double floorV = thr - width;
+            bool zero = false;
+            if (!(floorV > 0.0) || width > 1.0e-6) { floorV = 0.0; zero = true; }
+            int64_t total = 0;
+            rc = viol_compact_device(d, floorV, &total); if (rc) return rc;
+            std::vector<int64_t> hp((size_t) total);
+            std::vector<double> hv((size_t) total);
+            if (total > 0) {
+                CK(cudaMemcpyAsync(hp.data(), d->outPos, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
+                CK(cudaMemcpyAsync(hv.data(), d->outViol, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
+                CK(cudaStreamSynchronize(d->stream));
+                d->d2hBytes += 16 * total;
+            }
+            ok = replay_band_rule(hp.data(), hv.data(), total, floorV, zero, list, &L);
+            width *= 64.0;
+        }
+    } else {
+        rc = gne_dev_price_lv_sharded(d, &L, list, &anyV); if (rc) return rc;
+    }
+    *largestViolation = L;
+    *any = anyV;
+    *count = (int64_t) list.size();
+    if ((int64_t) list.size() > cap) { gne_set_error("gne_price_lv: list of %lld exceeds cap", (long long) list.size()); return GNE_ERR_CAPACITY; }
+    if (!list.empty()) memcpy(listPos, list.data(), 8 * list.size());
+    return GNE_OK;
+}
+
+extern "C" int gne_price_violators(gne_dev *d, double threshold, int64_t *count, int64_t *listPos, double *listViol, int64_t cap)
+{
+    CK(cudaSetDevice(d->device));
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    CK(cudaEventRecord(d->ev0, d->stream));
+    int64_t total = 0;
+    rc = viol_compact_device(d, threshold, &total); if (rc) return rc;
+    CK(cudaEventRecord(d->ev1, d->stream));
+    *count = total;
+    if (total > cap) { CK(cudaStreamSynchronize(d->stream)); gne_set_error("gne_price_violators: %lld exceeds cap", (long long) total); return GNE_ERR_CAPACITY; }
+    if (total > 0) {
+        CK(cudaMemcpyAsync(listPos, d->outPos, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
+        if (listViol) CK(cudaMemcpyAsync(listViol, d->outViol, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
+        d->d2hBytes += (listViol ? 16 : 8) * total;
+    }
+    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
+    return GNE_OK;
+}
+
+extern "C" int gne_price_first(gne_dev *d, int64_t *pos)
+{
+    CK(cudaSetDevice(d->device));
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    const int G = tiles_for(d);
+    CK(cudaEventRecord(d->ev0, d->stream));
+    CK(cudaMemsetAsync(d->firstPos, 0xff, 8, d->stream));
+    if (G > 0) { k_price_first<<<G, TILE_THREADS, 0, d->stream>>>(view_of(d), d->pi, d->firstPos); ++d->launches; }
+    CK(cudaMemcpyAsync(&d->hostScalar[1], d->firstPos, 8, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaEventRecord(d->ev1, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
+    d->d2hBytes += 8;
+    const unsigned long long v = (unsigned long long) d->hostScalar[1];
+    *pos = (v == ~0ull) ? -1 : (int64_t) v;
+    return GNE_OK;
+}
+
+extern "C" int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc)
+{
+    if (lo < d->lo || hi > std::min(d->N, d->hi) || hi < lo) { gne_set_error("gne_reduced_costs: bad range"); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(d->device));
+    int r = gne_dev_flush(d); if (r) return r;
+    if (hi == lo) return GNE_OK;
+    r = ensure_out(d, hi - lo); if (r) return r;
+    const int G = tiles_for(d);
+    k_reduced_costs<<<G, TILE_THREADS, 0, d->stream>>>(view_of(d), d->pi, lo, hi, d->outViol);
+    CK(cudaGetLastError());
+    ++d->launches;
+    CK(cudaMemcpyAsync(rc, d->outViol, 8 * (size_t) (hi - lo), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    d->d2hBytes += 8 * (hi - lo);
+    return GNE_OK;
+}
+
+extern "C" int gne_price_qs(gne_dev *d, int64_t cursor, int64_t want, int64_t *bestPos, double *bestViol,
+                            int64_t *newCursor, int64_t *scanned, int64_t *violations)
+{
+    CK(cudaSetDevice(d->device));
+    if (d->nranks != 1) { gne_set_error("gne_price_qs: sharded quickSelect is not implemented"); return GNE_ERR_UNSUPPORTED; }
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    const int64_t N = d->N;
+    *bestPos = -1; *bestViol = 0.0; *scanned = 0; *violations = 0;
+    if (cursor >= N) cursor = 0;                        // gnePivotRules.cpp:716
+    *newCursor = cursor;
+    if (N == 0 || want <= 0) return GNE_OK;
+    NbView nb = view_of(d);
+    QsState *st = d->qsState;
+    st->violations = 0; st->bestV = 0.0; st->bestJ = -1; st->stopJ = -1; st->done = 0;
+    if (d->qsWindow <= 0) d->qsWindow = std::max<int64_t>(4 * want, 64 * QTILE);
+    int64_t jLo = 0;
+    float msTotal = 0.f;
+    while (true) {
+        int64_t jHi = std::min(N, jLo + d->qsWindow);
+        const int G = (int) ((jHi - jLo + QTILE - 1) / QTILE);
+        CK(cudaEventRecord(d->ev0, d->stream));
+        k_qs_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, d->qs);
+        k_qs_finish<<<1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, d->qs, G, want, st);
+        CK(cudaEventRecord(d->ev1, d->stream));
+        CK(cudaGetLastError());
+        d->launches += 2;
+        CK(cudaStreamSynchronize(d->stream));
+        float ms; CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1)); msTotal += ms;
+        d->d2hBytes += sizeof(QsState);
+        if (st->done) {
+            const int64_t sc = (st->stopJ >= 0) ? st->stopJ + 1 : N;
+            *scanned = sc;
+            // adapt the next window to ~1.5x what this scan needed
+            d->qsWindow = std::min<int64_t>(N, std::max<int64_t>(64 * QTILE, ((sc * 3 / 2) / QTILE + 1) * QTILE));
+            break;
+        }
+        jLo = jHi;
+        d->qsWindow = std::min<int64_t>(N, d->qsWindow * 4);
+    }
+    d->lastMs = msTotal;
+    *violations = st->violations;
+    *bestViol = st->bestV;
+    if (st->bestJ >= 0) { int64_t p = cursor + st->bestJ; if (p >= N) p -= N; *bestPos = p; }
+    int64_t nc = cursor + *scanned;
+    if (nc >= N) nc -= N;
+    *newCursor = nc;                                    // == start when the scan was exhausted
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// bench helper
+// ------------------------------------------------------------------------------------------
+extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, float *msPerPass)
+{
+    CK(cudaSetDevice(d->device));
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    if (flushL2 && !d->flushBuf) {
+        d->flushLen = (int64_t) 40 * 1024 * 1024;       // 320 MB of doubles > 126 MB L2
+        CK(cudaMalloc(&d->flushBuf, 8 * (size_t) d->flushLen));
+    }
+    for (int i = 0; i < reps; ++i) {
+        if (flushL2) { k_flush_l2<<<148 * 8, 256, 0, d->stream>>>(d->flushBuf, d->flushLen); ++d->launches; }
+        rc = price_lv_local(d); if (rc) return rc;
+        CK(cudaStreamSynchronize(d->stream));
+        CK(cudaEventElapsedTime(&msPerPass[i], d->ev0, d->ev1));
+    }
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU: every rank prices its shard, the fixed-size LV records are all-gathered over
+// NCCL (NVLink), and every rank runs the same merge => identical entering arc everywhere.
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int SHARD_LIST = 48;                          // candidates carried per rank in the record
+struct ShardRecord {                                    // 16 + 48*16 = 784 bytes
+    double maxViol;
+    int32_t any, overflow;
+    int64_t count;
+    int64_t pos[SHARD_LIST];
+    double viol[SHARD_LIST];
+};
+__global__ void k_pack_record(const LvResult *res, ShardRecord *rec)
+{
+    const int t = threadIdx.x;
+    if (t == 0) {
+        rec->maxViol = res->maxViol; rec->any = res->any; rec->count = res->count;
+        rec->overflow = (res->overflow || res->count > SHARD_LIST) ? 1 : 0;
+    }
+    if (t < SHARD_LIST && t < res->count) { rec->pos[t] = res->pos[t]; rec->viol[t] = res->viol[t]; }
+}
+} // namespace
+
+extern "C" int gne_comm_unique_id(uint8_t id[128])
+{
+    if (!nccl_load()) return GNE_ERR_COMM;
+    int r = g_nccl.GetUniqueId(id);
+    if (r != 0) { gne_set_error("ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
+    return GNE_OK;
+}
+
+extern "C" int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nranks)
+{
+    if (!nccl_load()) return GNE_ERR_COMM;
+    CK(cudaSetDevice(d->device));
+    NcclId uid;
+    memcpy(uid.b, id, 128);
+    int r = g_nccl.CommInitRank(&d->comm, nranks, uid, rank);
+    if (r != 0) { gne_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
+    d->rank = rank; d->nranks = nranks;
+    CK(cudaMalloc(&d->gatherSend, sizeof(ShardRecord)));
+    CK(cudaMalloc(&d->gatherRecv, sizeof(ShardRecord) * (size_t) nranks));
+    CK(cudaHostAlloc(&d->gatherHost, sizeof(ShardRecord) * (size_t) nranks, cudaHostAllocDefault));
+    return GNE_OK;
+}
+
+extern "C" int gne_comm_destroy(gne_dev *d)
+{
+    if (d->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(d->comm); d->comm = nullptr; }
+    d->nranks = 1; d->rank = 0;
+    return GNE_OK;
+}
+
+int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &list, int *any)
+{
+    // price_lv_local has been launched and synchronised by the caller; pack, all-gather, merge
+    k_pack_record<<<1, 64, 0, d->stream>>>(d->lvRes, (ShardRecord *) d->gatherSend);
+    ++d->launches;
+    int r = g_nccl.AllGather(d->gatherSend, d->gatherRecv, sizeof(ShardRecord), /*ncclChar*/ 0, d->comm, d->stream);
+    if (r != 0) { gne_set_error("ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
+    CK(cudaMemcpyAsync(d->gatherHost, d->gatherRecv, sizeof(ShardRecord) * (size_t) d->nranks, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    d->d2hBytes += sizeof(ShardRecord) * (int64_t) d->nranks;
+    const ShardRecord *rec = (const ShardRecord *) d->gatherHost;
+    std::vector<double> maxima(d->nranks);
+    std::vector<int> anys(d->nranks);
+    std::vector<int64_t> counts(d->nranks), pos((size_t) d->nranks * SHARD_LIST);
+    std::vector<double> viol((size_t) d->nranks * SHARD_LIST);
+    for (int k = 0; k < d->nranks; ++k) {
+        maxima[k] = rec[k].maxViol; anys[k] = rec[k].any;
+        counts[k] = rec[k].overflow ? -1 : rec[k].count;
+        for (int i = 0; i < SHARD_LIST; ++i) { pos[(size_t) k * SHARD_LIST + i] = rec[k].pos[i]; viol[(size_t) k * SHARD_LIST + i] = rec[k].viol[i]; }
+    }
+    int64_t cnt = 0;
+    int need = 0;
+    std::vector<int64_t> outPos((size_t) d->nranks * SHARD_LIST);
+    int rc = gne_merge_lv_shards(d->nranks, maxima.data(), anys.data(), counts.data(), pos.data(), viol.data(), SHARD_LIST,
+                                 largest, &cnt, outPos.data(), (int64_t) outPos.size(), any, &need);
+    if (rc) return rc;
+    if (need) { gne_set_error("sharded LV: tie list exceeds the exchange record (fallback gather not implemented)"); return GNE_ERR_UNSUPPORTED; }
+    list.assign(outPos.begin(), outPos.begin() + cnt);
+    return GNE_OK;
+}
+
+// Host-only: merge per-shard records.  counts[r] < 0 marks an overflowed shard.
+extern "C" int gne_merge_lv_shards(int nranks, const double *maxima, const int *any, const int64_t *counts,
+                                   const int64_t *listPos, const double *listViol, int64_t stride,
+                                   double *largestViolation, int64_t *count, int64_t *outPos, int64_t cap, int *outAny, int *needFallback)
+{
+    *needFallback = 0; *count = 0; *outAny = 0; *largestViolation = -1.0;
+    double M = -1.0;
+    for (int r = 0; r < nranks; ++r) if (any[r]) { *outAny = 1; if (maxima[r] > M) M = maxima[r]; }
+    if (!*outAny) return GNE_OK;
+    const double floorV = M - LV_BAND;
+    std::vector<int64_t> p;
+    std::vector<double> v;
+    for (int r = 0; r < nranks; ++r) {                  // shards are contiguous position ranges in rank order
+        if (!any[r] || maxima[r] < floorV) continue;
+        if (counts[r] < 0) { *needFallback = 1; return GNE_OK; }
+        for (int64_t i = 0; i < counts[r]; ++i) {
+            const double x = listViol[(size_t) r * stride + i];
+            if (x >= floorV) { p.push_back(listPos[(size_t) r * stride + i]); v.push_back(x); }
+        }
+    }
+    std::vector<int64_t> list;
+    double L;
+    if (!replay_band_rule(p.data(), v.data(), (int64_t) p.size(), floorV, false, list, &L)) { *needFallback = 1; return GNE_OK; }
+    if ((int64_t) list.size() > cap) { gne_set_error("gne_merge_lv_shards: cap too small"); return GNE_ERR_CAPACITY; }
+    *largestViolation = L;
+    *count = (int64_t) list.size();
+    for (size_t i = 0; i < list.size(); ++i) outPos[i] = list[i];
+    return GNE_OK;
+}

@@ -1,0 +1,528 @@
+// genneteq_b200 — sm_100a kernels of the pricing / potential path.
+//
+// Everything here is fp64 streaming + gather + reduction: HBM-bound, no dense contraction, so
+// no tensor-core path.  Arithmetic uses __dmul_rn/__dadd_rn/__dsub_rn so
+// that a multiply is never fused with the following add (the reference's x86-64 -O3 build has
+// no FMA: genneteq.h:315-316, gnePotential.cpp:130) — results are bit-identical to the CPU.
+//
+// Nonbasic arcs live as a structure-of-arrays in setNBarc *position* order (gnePivot.cpp:527-600
+// defines that order); a tile is TILE consecutive positions, one CTA per tile:
+//   thread t owns positions base + 4t .. 4t+3 and base + TILE/2 + 4t .. 4t+3
+// so tail/head are read as int4, cost/mult as 2 x double2 and state as one 32-bit word per
+// chunk — 128-bit coalesced loads, 25 algorithmic bytes per arc.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gne {
+
+constexpr int TILE_THREADS = 256;
+constexpr int TILE = 2048;                 // positions per CTA (2 chunks x 256 threads x 4)
+constexpr int HALF = TILE / 2;
+constexpr int CAND_K = 16;                 // in-band candidates kept per tile by the LV pass
+constexpr int LV_LIST_CAP = 2048;          // candidates returned by the fused LV pass
+constexpr int QTILE = 1024;                // virtual positions per CTA in the quickSelect scan
+constexpr double TOL = 1.0e-13;            // main.h:36-43 ROUNDOFF_TOLERANCE
+constexpr double LV_BAND = 4.0e-13;        // candidates are kept down to max - 4 tol (see gne_device.cu)
+
+struct NbView {                            // shard of the nonbasic list; index = pos - lo
+    const int32_t *tail;
+    const int32_t *head;
+    const double *cost;
+    const double *mult;
+    const int8_t *state;
+    int64_t lo;                            // first global position of the shard (multiple of TILE)
+    int64_t end;                           // min(N, hi): positions >= end are not priced
+};
+
+// computeArcRedCost (genneteq.h:312-318): (cost - pi[tail]) + (mult * pi[head]), unfused
+__device__ __forceinline__ double red_cost(double cost, double mult, double pit, double pih)
+{
+    return __dadd_rn(__dsub_rn(cost, pit), __dmul_rn(mult, pih));
+}
+
+// gnePivotRules.cpp:406-407: violation magnitude |rc| or -1 when the arc is not eligible
+__device__ __forceinline__ double violation(double rc, int st)
+{
+    bool viol = (st == 1 && rc < -TOL) || (st == 2 && rc > TOL);
+    return viol ? fabs(rc) : -1.0;
+}
+
+__device__ __forceinline__ double ld_pi(const double *pi, int i) { return __ldg(pi + i); }
+
+// Violation magnitudes of this thread's 8 positions of tile `tileBase` (local index).
+// v[k], k = 0..3 -> local tileBase + 4t + k ; k = 4..7 -> tileBase + HALF + 4t + (k-4).
+__device__ __forceinline__ void tile_violations(const NbView &nb, const double *__restrict__ pi,
+                                                int64_t tileBase, double v[8], double *rcOut = nullptr)
+{
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int64_t l0 = tileBase + c * HALF + 4 * t;          // local index of the 4-chunk
+        const int4 tl = __ldg(reinterpret_cast<const int4 *>(nb.tail + l0));
+        const int4 hd = __ldg(reinterpret_cast<const int4 *>(nb.head + l0));
+        const double2 c01 = __ldg(reinterpret_cast<const double2 *>(nb.cost + l0));
+        const double2 c23 = __ldg(reinterpret_cast<const double2 *>(nb.cost + l0 + 2));
+        const double2 m01 = __ldg(reinterpret_cast<const double2 *>(nb.mult + l0));
+        const double2 m23 = __ldg(reinterpret_cast<const double2 *>(nb.mult + l0 + 2));
+        const uint32_t st4 = __ldg(reinterpret_cast<const uint32_t *>(nb.state + l0));
+        // arcs are created sorted by tail, so neighbouring positions mostly share pi[tail]
+        const double pt0 = ld_pi(pi, tl.x);
+        const double pt1 = (tl.y == tl.x) ? pt0 : ld_pi(pi, tl.y);
+        const double pt2 = (tl.z == tl.y) ? pt1 : ld_pi(pi, tl.z);
+        const double pt3 = (tl.w == tl.z) ? pt2 : ld_pi(pi, tl.w);
+        const double ph0 = ld_pi(pi, hd.x), ph1 = ld_pi(pi, hd.y), ph2 = ld_pi(pi, hd.z), ph3 = ld_pi(pi, hd.w);
+        const double r0 = red_cost(c01.x, m01.x, pt0, ph0);
+        const double r1 = red_cost(c01.y, m01.y, pt1, ph1);
+        const double r2 = red_cost(c23.x, m23.x, pt2, ph2);
+        const double r3 = red_cost(c23.y, m23.y, pt3, ph3);
+        const int64_t g0 = nb.lo + l0;
+        v[4 * c + 0] = (g0 + 0 < nb.end) ? violation(r0, (int) (st4 & 0xff)) : -1.0;
+        v[4 * c + 1] = (g0 + 1 < nb.end) ? violation(r1, (int) ((st4 >> 8) & 0xff)) : -1.0;
+        v[4 * c + 2] = (g0 + 2 < nb.end) ? violation(r2, (int) ((st4 >> 16) & 0xff)) : -1.0;
+        v[4 * c + 3] = (g0 + 3 < nb.end) ? violation(r3, (int) ((st4 >> 24) & 0xff)) : -1.0;
+        if (rcOut) { rcOut[4 * c + 0] = r0; rcOut[4 * c + 1] = r1; rcOut[4 * c + 2] = r2; rcOut[4 * c + 3] = r3; }
+    }
+}
+
+// local index (within the tile) of slot k of thread t, increasing in position order per chunk
+__device__ __forceinline__ int tile_offset(int t, int k) { return (k >> 2) * HALF + 4 * t + (k & 3); }
+
+// (value, position) argmax with the lower position winning ties
+struct Best { double v; int64_t p; };
+__device__ __forceinline__ Best best_of(Best a, Best b)
+{
+    return (b.v > a.v || (b.v == a.v && b.p < a.p)) ? b : a;
+}
+__device__ __forceinline__ Best warp_best(Best x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best y;
+        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+        y.p = __shfl_xor_sync(0xffffffffu, x.p, o);
+        x = best_of(x, y);
+    }
+    return x;
+}
+// block-wide argmax; result valid in every thread
+__device__ __forceinline__ Best block_best(Best x)
+{
+    __shared__ double sv[TILE_THREADS / 32];
+    __shared__ int64_t sp[TILE_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    x = warp_best(x);
+    __syncthreads();                       // protect sv/sp reuse across calls
+    if (lane == 0) { sv[w] = x.v; sp[w] = x.p; }
+    __syncthreads();
+    Best r;
+    r.v = sv[0]; r.p = sp[0];
+#pragma unroll
+    for (int i = 1; i < TILE_THREADS / 32; ++i) { Best y; y.v = sv[i]; y.p = sp[i]; r = best_of(r, y); }
+    return r;
+}
+// block-wide exclusive scan of a small non-negative int; *total = block sum
+__device__ __forceinline__ int block_excl_scan(int x, int *total)
+{
+    __shared__ int sw[TILE_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    __syncthreads();
+    if (lane == 31) sw[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < TILE_THREADS / 32; ++i) { if (i < w) base += sw[i]; tot += sw[i]; }
+    *total = tot;
+    return base + inc - x;
+}
+
+// ------------------------------------------------------------------------------------------
+// LV pass, stage 1 (one CTA per tile): tile maximum, number of violators within LV_BAND of it,
+// and the first CAND_K of those in position order.
+// ------------------------------------------------------------------------------------------
+struct LvTiles {
+    double *tileMax;       // [G]  -1 when the tile has no violator
+    int32_t *tileCnt;      // [G]  in-band candidates (may exceed CAND_K)
+    int32_t *candOff;      // [G * CAND_K]  local offsets within the tile, position order
+    double *candViol;      // [G * CAND_K]
+};
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_price_lv_tiles(NbView nb, const double *__restrict__ pi, LvTiles out)
+{
+    const int64_t tileBase = (int64_t) blockIdx.x * TILE;
+    double v[8];
+    tile_violations(nb, pi, tileBase, v);
+    Best b; b.v = -1.0; b.p = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (v[k] > b.v) { b.v = v[k]; b.p = tile_offset(threadIdx.x, k); }
+    b = block_best(b);
+    __shared__ int sCnt;
+    __shared__ int sOff[CAND_K];
+    __shared__ double sViol[CAND_K];
+    if (threadIdx.x == 0) sCnt = 0;
+    __syncthreads();
+    if (b.v > 0.0) {
+        const double thr = __dsub_rn(b.v, LV_BAND);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (v[k] > 0.0 && v[k] >= thr) {
+                int s = atomicAdd(&sCnt, 1);
+                if (s < CAND_K) { sOff[s] = tile_offset(threadIdx.x, k); sViol[s] = v[k]; }
+            }
+        }
+    }
+    __syncthreads();
+    const int cnt = sCnt;
+    if (threadIdx.x == 0) { out.tileMax[blockIdx.x] = b.v; out.tileCnt[blockIdx.x] = cnt; }
+    if (cnt <= CAND_K && (int) threadIdx.x < cnt) {            // rank by offset -> position order
+        const int mine = sOff[threadIdx.x];
+        int rank = 0;
+        for (int i = 0; i < cnt; ++i) rank += (sOff[i] < mine);
+        out.candOff[(int64_t) blockIdx.x * CAND_K + rank] = mine;
+        out.candViol[(int64_t) blockIdx.x * CAND_K + rank] = sViol[threadIdx.x];
+    }
+}
+
+// Result block of the LV pass (mapped pinned host memory, written by the finish kernel).
+struct LvResult {
+    double maxViol;        // exact fp64 maximum of |rc| over violators, -1 if none
+    int32_t any;           // at least one violator
+    int32_t overflow;      // candidate list incomplete (a tile had > CAND_K, or > LV_LIST_CAP total)
+    int64_t count;         // candidates with |rc| >= maxViol - LV_BAND, position order
+    int64_t pos[LV_LIST_CAP];
+    double viol[LV_LIST_CAP];
+};
+
+// LV pass, stage 2 (one CTA): global maximum over tiles, then gather the candidates of the
+// tiles whose maximum reaches the band, in position order.
+__global__ void __launch_bounds__(TILE_THREADS)
+k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
+{
+    const int t = threadIdx.x;
+    Best b; b.v = -1.0; b.p = 0;
+    for (int g = t; g < G; g += TILE_THREADS) { double m = tiles.tileMax[g]; if (m > b.v) { b.v = m; b.p = g; } }
+    b = block_best(b);
+    const double M = b.v;
+    if (M <= 0.0) {
+        if (t == 0) { res->maxViol = -1.0; res->any = 0; res->overflow = 0; res->count = 0; }
+        return;
+    }
+    const double thr = __dsub_rn(M, LV_BAND);
+    const int per = (G + TILE_THREADS - 1) / TILE_THREADS;
+    const int g0 = min(G, t * per), g1 = min(G, g0 + per);
+    int mine = 0, ovf = 0;
+    for (int g = g0; g < g1; ++g) {
+        if (tiles.tileMax[g] >= thr) {
+            const int c = tiles.tileCnt[g];
+            if (c > CAND_K) { ovf = 1; continue; }
+            for (int i = 0; i < c; ++i) mine += (tiles.candViol[(int64_t) g * CAND_K + i] >= thr);
+        }
+    }
+    int total;
+    int off = block_excl_scan(mine, &total);
+    const int anyOvf = __syncthreads_or(ovf);
+    const bool tooMany = total > LV_LIST_CAP;
+    if (!anyOvf && !tooMany) {
+        for (int g = g0; g < g1; ++g) {
+            if (tiles.tileMax[g] >= thr) {
+                const int c = tiles.tileCnt[g];
+                for (int i = 0; i < c; ++i) {
+                    const double vv = tiles.candViol[(int64_t) g * CAND_K + i];
+                    if (vv >= thr) {
+                        res->pos[off] = lo + (int64_t) g * TILE + tiles.candOff[(int64_t) g * CAND_K + i];
+                        res->viol[off] = vv;
+                        ++off;
+                    }
+                }
+            }
+        }
+    }
+    if (t == 0) { res->maxViol = M; res->any = 1; res->overflow = (anyOvf || tooMany) ? 1 : 0; res->count = total; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Ordered compaction of every violator with |rc| >= threshold: count per tile, scan, write.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_THREADS)
+k_viol_count(NbView nb, const double *__restrict__ pi, double threshold, int32_t *tileCnt)
+{
+    double v[8];
+    tile_violations(nb, pi, (int64_t) blockIdx.x * TILE, v);
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c += (v[k] > 0.0 && v[k] >= threshold);
+    int total;
+    block_excl_scan(c, &total);
+    if (threadIdx.x == 0) tileCnt[blockIdx.x] = total;
+}
+
+// exclusive scan of G tile counts by one CTA; total -> *totalOut (mapped host) and tileOff[G]
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(const int32_t *tileCnt, int64_t *tileOff, int G, int64_t *totalOut)
+{
+    __shared__ int64_t sWarp[32];
+    __shared__ int64_t sCarry;
+    if (threadIdx.x == 0) sCarry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < G; base += 1024) {
+        const int g = base + threadIdx.x;
+        const int64_t x = (g < G) ? tileCnt[g] : 0;
+        int64_t inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) sWarp[w] = inc;
+        __syncthreads();
+        int64_t wb = 0, tot = 0;
+        for (int i = 0; i < 32; ++i) { if (i < w) wb += sWarp[i]; tot += sWarp[i]; }
+        const int64_t carry = sCarry;
+        if (g < G) tileOff[g] = carry + wb + inc - x;
+        __syncthreads();
+        if (threadIdx.x == 0) sCarry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { tileOff[G] = sCarry; *totalOut = sCarry; }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_viol_write(NbView nb, const double *__restrict__ pi, double threshold, const int64_t *tileOff,
+             int64_t *outPos, double *outViol, int64_t cap)
+{
+    const int64_t tileBase = (int64_t) blockIdx.x * TILE;
+    double v[8];
+    tile_violations(nb, pi, tileBase, v);
+    int64_t base = tileOff[blockIdx.x];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cnt += (v[4 * c + k] > 0.0 && v[4 * c + k] >= threshold);
+        int total;
+        int off = block_excl_scan(cnt, &total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double vv = v[4 * c + k];
+            if (vv > 0.0 && vv >= threshold) {
+                const int64_t o = base + off;
+                if (o < cap) {
+                    outPos[o] = nb.lo + tileBase + tile_offset(threadIdx.x, 4 * c + k);
+                    if (outViol) outViol[o] = vv;
+                }
+                ++off;
+            }
+        }
+        base += total;
+    }
+}
+
+// getFirstVarWithViolation: lowest violating position (atomicMin over tiles)
+__global__ void __launch_bounds__(TILE_THREADS)
+k_price_first(NbView nb, const double *__restrict__ pi, unsigned long long *firstPos)
+{
+    const int64_t tileBase = (int64_t) blockIdx.x * TILE;
+    double v[8];
+    tile_violations(nb, pi, tileBase, v);
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) if (v[k] > 0.0) best = (unsigned long long) (nb.lo + tileBase + tile_offset(threadIdx.x, k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(firstPos, best);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_reduced_costs(NbView nb, const double *__restrict__ pi, int64_t lo, int64_t hi, double *rc)
+{
+    const int64_t tileBase = (int64_t) blockIdx.x * TILE;
+    double v[8], r[8];
+    tile_violations(nb, pi, tileBase, v, r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t g = nb.lo + tileBase + tile_offset(threadIdx.x, k);
+        if (g >= lo && g < hi && g < nb.end) rc[g - lo] = r[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// quickSelect scan (gnePivotRules.cpp:742-756) over a window [jLo, jHi) of *virtual* indices
+// j = (pos - cursor) mod N; one CTA per QTILE virtual indices, thread t owns j = base + t + 256 k.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double qs_violation(const NbView &nb, const double *__restrict__ pi,
+                                               int64_t cursor, int64_t N, int64_t j, int64_t jHi)
+{
+    if (j >= jHi) return -1.0;
+    int64_t pos = cursor + j;
+    if (pos >= N) pos -= N;
+    const int64_t l = pos - nb.lo;
+    const int tl = __ldg(nb.tail + l), hd = __ldg(nb.head + l);
+    const double rc = red_cost(__ldg(nb.cost + l), __ldg(nb.mult + l), ld_pi(pi, tl), ld_pi(pi, hd));
+    return violation(rc, (int) __ldg(nb.state + l));
+}
+
+struct QsTiles { int32_t *cnt; double *bestV; int64_t *bestJ; };
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_qs_tiles(NbView nb, const double *__restrict__ pi, int64_t cursor, int64_t N, int64_t jLo, int64_t jHi, QsTiles out)
+{
+    const int64_t base = jLo + (int64_t) blockIdx.x * QTILE;
+    Best b; b.v = -1.0; b.p = 0;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < QTILE / TILE_THREADS; ++k) {
+        const int64_t j = base + threadIdx.x + k * TILE_THREADS;
+        const double v = qs_violation(nb, pi, cursor, N, j, jHi);
+        if (v > 0.0) { ++c; if (v > b.v) { b.v = v; b.p = j; } }
+    }
+    int total;
+    block_excl_scan(c, &total);
+    b = block_best(b);
+    if (threadIdx.x == 0) { out.cnt[blockIdx.x] = total; out.bestV[blockIdx.x] = b.v; out.bestJ[blockIdx.x] = b.p; }
+}
+
+struct QsState {            // mapped pinned host memory; carried across windows
+    int64_t violations;     // violators seen so far
+    double bestV;           // strictly-largest |rc| so far (0 = none, as largestViol starts at 0.0)
+    int64_t bestJ;          // its virtual index (-1 = none)
+    int64_t stopJ;          // virtual index of the want-th violator (-1 = not reached yet)
+    int32_t done;
+    int32_t pad;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_qs_finish(NbView nb, const double *__restrict__ pi, int64_t cursor, int64_t N, int64_t jLo, int64_t jHi,
+            QsTiles tiles, int G, int64_t want, QsState *st)
+{
+    const int t = threadIdx.x;
+    const int64_t carry = st->violations;
+    const int per = (G + TILE_THREADS - 1) / TILE_THREADS;
+    const int g0 = min(G, t * per), g1 = min(G, g0 + per);
+    int mine = 0;
+    for (int g = g0; g < g1; ++g) mine += tiles.cnt[g];
+    int total;
+    const int off = block_excl_scan(mine, &total);
+    __shared__ int sCross;
+    __shared__ int64_t sBefore;
+    if (t == 0) { sCross = -1; sBefore = 0; }
+    __syncthreads();
+    {
+        int64_t run = carry + off;
+        for (int g = g0; g < g1; ++g) {
+            const int c = tiles.cnt[g];
+            if (run < want && run + c >= want) { sCross = g; sBefore = run; }
+            run += c;
+        }
+    }
+    __syncthreads();
+    const int cross = sCross;
+    const int gEnd = (cross < 0) ? G : cross;          // tiles fully inside the scan
+    Best b; b.v = -1.0; b.p = 0;
+    for (int g = t; g < gEnd; g += TILE_THREADS) { Best y; y.v = tiles.bestV[g]; y.p = tiles.bestJ[g]; b = best_of(b, y); }
+    b = block_best(b);
+    int64_t stopJ = -1;
+    int64_t seen = carry + total;
+    if (cross >= 0) {
+        // re-price the crossing tile: find the want-th violator in j order, best up to it
+        const int64_t base = jLo + (int64_t) cross * QTILE;
+        int64_t need = want - sBefore;                 // >= 1
+        __shared__ int64_t sStop;
+        if (t == 0) sStop = -1;
+        __syncthreads();
+        Best bc; bc.v = -1.0; bc.p = 0;
+        for (int k = 0; k < QTILE / TILE_THREADS; ++k) {
+            const int64_t j = base + t + k * TILE_THREADS;
+            const double v = qs_violation(nb, pi, cursor, N, j, jHi);
+            const int f = v > 0.0;
+            int tot;
+            const int ex = block_excl_scan(f, &tot);
+            const bool before = sStop < 0;
+            __syncthreads();
+            if (before) {
+                if (f && (int64_t) ex + 1 == need) sStop = j;
+                if (f && (int64_t) ex + 1 <= need && v > bc.v) { bc.v = v; bc.p = j; }
+                need -= tot;                            // uniform across the block
+            }
+            __syncthreads();
+        }
+        bc = block_best(bc);
+        b = best_of(b, bc);
+        stopJ = sStop;
+        seen = want;
+    }
+    if (t == 0) {
+        Best prev; prev.v = st->bestV; prev.p = st->bestJ;
+        // largestViol starts at 0.0 and is replaced on strictly greater: earlier j wins ties
+        if (b.v > prev.v) prev = b;
+        st->bestV = prev.v; st->bestJ = prev.p;
+        st->violations = seen;
+        st->stopJ = stopJ;
+        st->done = (stopJ >= 0 || jHi >= N) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Set mirror and potentials
+// ------------------------------------------------------------------------------------------
+struct NbMut { int32_t *tail; int32_t *head; double *cost; double *mult; int8_t *state; };
+
+struct NbWriteOps {                        // passed by value: no copy engine involved
+    int n;
+    int64_t local[8];
+    int32_t tail[8], head[8];
+    double cost[8], mult[8];
+    int8_t state[8];
+};
+
+__global__ void k_nb_write(NbMut nb, NbWriteOps ops)
+{
+    const int i = threadIdx.x;
+    if (i < ops.n) {
+        const int64_t l = ops.local[i];
+        nb.tail[l] = ops.tail[i]; nb.head[l] = ops.head[i];
+        nb.cost[l] = ops.cost[i]; nb.mult[l] = ops.mult[i]; nb.state[l] = ops.state[i];
+    }
+}
+
+__global__ void k_pot_update_nodes(int64_t count, const int32_t *__restrict__ node, const double *__restrict__ a0,
+                                   const double *__restrict__ a1, const int32_t *__restrict__ slot,
+                                   double *A0, double *A1, int32_t *S)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { const int v = node[i]; A0[v] = a0[i]; A1[v] = a1[i]; S[v] = slot[i]; }
+}
+
+__global__ void k_pot_update_thetas(int64_t count, const int32_t *__restrict__ slot, const double *__restrict__ theta, double *T)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) T[slot[i]] = theta[i];
+}
+
+// finalizePotentialsTypeI (gnePotential.cpp:127-135): pi = a0 + a1 * theta, 28 B per node
+__global__ void k_pot_finalize(int n, const double *__restrict__ A0, const double *__restrict__ A1,
+                               const int32_t *__restrict__ S, const double *__restrict__ T, double *__restrict__ pi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pi[i] = __dadd_rn(A0[i], __dmul_rn(A1[i], __ldg(T + S[i])));
+}
+
+__global__ void k_pot_set(int64_t count, const int32_t *__restrict__ node, const double *__restrict__ val, double *pi)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) pi[node[i]] = val[i];
+}
+
+__global__ void k_flush_l2(double *buf, int64_t n)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) buf[i] = (double) i;
+}
+
+} // namespace gne

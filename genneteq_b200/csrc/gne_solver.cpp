@@ -1,0 +1,754 @@
+// genneteq_b200 — host mirror of GenNetEq driving the device operators; see gne_solver.h.
+// Built with -ffp-contract=off: the reference's arithmetic has no fused multiply-add.
+#include "gne_solver.h"
+#include "gne_internal.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <time.h>
+
+namespace gneb200 {
+
+static const double TOL = GNE_ROUNDOFF_TOLERANCE;       // main.h:36-43
+enum { B_var = 0, L_var = 1, U_var = 2, NIL = 3 };       // variables.h:23
+
+static inline double wallNow()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1.0e-9 * (double) ts.tv_nsec;
+}
+
+#define GNE_TRY(call) do { int rc_ = (call); if (rc_ != GNE_OK) return rc_; } while (0)
+
+GenNetEq::GenNetEq() {}
+
+GenNetEq::~GenNetEq()
+{
+    if (dev) gne_dev_destroy(dev);
+}
+
+// glibc drand48 (never seeded by the reference => X0 = 0): X' = (0x5DEECE66D X + 0xB) mod 2^48
+double GenNetEq::drand48()
+{
+    rand48State = (0x5DEECE66DULL * rand48State + 0xBULL) & ((1ULL << 48) - 1ULL);
+    return ldexp((double) rand48State, -48);
+}
+
+// ------------------------------------------------------------------------------------------
+// gneInit.cpp:25-186 (initialType is forced to SELFLOOPS there, :31)
+// ------------------------------------------------------------------------------------------
+int GenNetEq::initialize(Graph *g, int /*initType: ignored by the reference too*/, int cudaDev)
+{
+    if (g->getNumEqualFlowSets() != 0) { gne_set_error("equal-flow sets are out of scope"); return GNE_ERR_UNSUPPORTED; }
+    cudaDevice = cudaDev;
+    numNodes = g->getNumNodes();
+    bigM = g->getBigM();
+    m = g->getNumArcs();
+    M = m + numNodes;
+    tail.resize(M); head.resize(M); mult.resize(M); UB.resize(M); actualCost.resize(M); isArtificial.assign(M, 0);
+    for (int64_t a = 0; a < m; ++a) {                   // gneInit.cpp:82-107
+        tail[a] = g->tail[a]; head[a] = g->head[a]; UB[a] = g->cap[a]; actualCost[a] = g->cost[a]; mult[a] = g->mult[a];
+    }
+    supply.resize(numNodes);
+    for (int i = 0; i < numNodes; ++i) {                // gneInit.cpp:110-127 artificial self-loops
+        supply[i] = g->supply(i);
+        const int64_t a = m + i;
+        tail[a] = i; head[a] = i; UB[a] = DBL_MAX; actualCost[a] = bigM;
+        mult[a] = (supply[i] >= 0.0) ? 0.5 : 2.0;
+        isArtificial[a] = 1;
+    }
+    cost.assign(M, 0.0); flow.assign(M, 0.0); deltaFlow.assign(M, 0.0); flowA0.assign(M, 0.0); flowA1.assign(M, 0.0);
+    setLoc.assign(M, NIL); setInd.assign(M, -1);
+    supA0.assign(numNodes, 0.0); supA1.assign(numNodes, 0.0);
+    potA0.assign(numNodes, 0.0); potA1.assign(numNodes, 0.0); potSlot.assign(numNodes, -1);
+    thetaOfSlot.clear();
+    forest.init(numNodes, tail.data(), head.data());
+    setBarc.clear(); setNBarc.clear();
+    setBarc.reserve(numNodes); setNBarc.reserve(m + 1);
+    for (int64_t a = 0; a < M; ++a) {                   // formInitialBFS, gneInit.cpp:174-185
+        if (isArtificial[a]) GNE_TRY(insertIntoB((int32_t) a));
+        else GNE_TRY(insertIntoNB((int32_t) a, L_var));
+    }
+    forest.updateTrees();
+    phaseIiters = 0; phaseIIiters = 0;
+    return GNE_OK;
+}
+
+int GenNetEq::setComm(const uint8_t id[128], int rank, int nranks)
+{
+    if (dev) { gne_set_error("setComm must precede the first solve"); return GNE_ERR_ARG; }
+    commRank = rank; commRanks = nranks;
+    // contiguous position ranges, boundaries on tile multiples (2048)
+    const int64_t cap = m + 16;
+    int64_t per = (m + nranks - 1) / nranks;
+    per = ((per + 2047) / 2048) * 2048;
+    const int64_t lo = std::min<int64_t>((int64_t) rank * per, (cap / 2048) * 2048);
+    const int64_t hi = (rank == nranks - 1) ? cap : std::min<int64_t>(lo + per, cap);
+    GNE_TRY(gne_dev_create(&dev, cudaDevice, numNodes + 16, cap, lo, hi));
+    if (nranks > 1) GNE_TRY(gne_comm_init(dev, id, rank, nranks));
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// basis sets: gnePivot.cpp:487-600, mirrored on the device
+// ------------------------------------------------------------------------------------------
+int GenNetEq::writeNbRecord(int64_t pos, int32_t v)
+{
+    if (!dev || !costsOnDevice) return GNE_OK;
+    return gne_nb_write(dev, pos, tail[v], head[v], cost[v], mult[v], setLoc[v]);
+}
+
+int GenNetEq::insertIntoB(int32_t v)
+{
+    setBarc.push_back(v); setLoc[v] = B_var; setInd[v] = (int32_t) setBarc.size() - 1;
+    int rc = forest.insertArc(v);
+    if (rc) { gne_set_error("basis forest: insertion failed (%d): %s", rc, rc == -2 ? "adds cycle to type I tree" : "merges two type I trees"); return GNE_ERR_TREE; }
+    return GNE_OK;
+}
+
+int GenNetEq::removeFromB(int32_t v)
+{
+    const int32_t prevInd = setInd[v];
+    const int32_t mv = setBarc.back();
+    setBarc[prevInd] = mv; setInd[mv] = prevInd; setBarc.pop_back();
+    int rc = forest.removeArc(v);
+    if (rc) { gne_set_error("basis forest: removal failed (%d)", rc); return GNE_ERR_TREE; }
+    setLoc[v] = NIL; setInd[v] = -1;
+    return GNE_OK;
+}
+
+int GenNetEq::insertIntoNB(int32_t v, int8_t loc)
+{
+    setNBarc.push_back(v); setLoc[v] = loc; setInd[v] = (int32_t) setNBarc.size() - 1;
+    if (dev && costsOnDevice) {
+        GNE_TRY(writeNbRecord((int64_t) setNBarc.size() - 1, v));
+        GNE_TRY(gne_nb_set_count(dev, (int64_t) setNBarc.size()));
+    }
+    return GNE_OK;
+}
+
+int GenNetEq::removeFromNB(int32_t v)
+{
+    const int32_t prevInd = setInd[v];
+    const int32_t mv = setNBarc.back();
+    setNBarc[prevInd] = mv; setInd[mv] = prevInd; setNBarc.pop_back();
+    setLoc[v] = NIL; setInd[v] = -1;
+    if (dev && costsOnDevice) {
+        if (mv != v) GNE_TRY(writeNbRecord(prevInd, mv));
+        GNE_TRY(gne_nb_set_count(dev, (int64_t) setNBarc.size()));
+    }
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// genneteq.h inline helpers
+// ------------------------------------------------------------------------------------------
+double GenNetEq::hostPotential(int32_t node) const
+{
+    const double p = potA1[node] * thetaOfSlot[potSlot[node]];     // gnePotential.cpp:130, unfused
+    return potA0[node] + p;
+}
+
+double GenNetEq::computeArcRedCost(int32_t a)                     // genneteq.h:312-318
+{
+    const double t = mult[a] * hostPotential(head[a]);
+    return (cost[a] - hostPotential(tail[a])) + t;
+}
+
+double GenNetEq::computeDeltaVar(int32_t v) const                 // genneteq.h:364-403, initialType == SELFLOOPS
+{
+    const double x = flow[v], y = deltaFlow[v];
+    if (y > TOL) {
+        if (fabs(UB[v] - x) < TOL) return 0.0;
+        return (UB[v] - x) / y;
+    } else if (y < (-1.0 * TOL)) {
+        if (fabs(x) < TOL) return 0.0;
+        return x / (-1.0 * y);
+    }
+    return DBL_MAX;
+}
+
+void GenNetEq::checkVarForBlocking(int32_t v)                     // genneteq.h:334-360
+{
+    const double dv = computeDeltaVar(v);
+    if (delta > dv + TOL) blockingVars.clear();
+    if (delta >= dv - TOL) { delta = dv; blockingVars.push_back(v); }
+}
+
+// ------------------------------------------------------------------------------------------
+// gneFlow.cpp
+// ------------------------------------------------------------------------------------------
+void GenNetEq::computeFlowsTypeI(int32_t slot)                    // gneFlow.cpp:480-560
+{
+    const Tree &t = forest.tree(slot);
+    const int32_t ex = t.extraArc;
+    const int32_t alpha = tail[ex], beta = head[ex];
+    const double muAB = mult[ex];
+    flowA0[ex] = 0.0; flowA1[ex] = 1.0;
+    supA1[alpha] -= 1.0;
+    supA1[beta] += muAB;
+    const int32_t h = t.root;
+    for (int64_t k = (int64_t) t.threads.size() - 1; k >= 0; --k) {
+        const int32_t j = t.threads[k];
+        if (j == h) break;
+        const int32_t a = forest.predArc[j];
+        const double mu = mult[a];
+        if (tail[a] == j) {
+            const int32_t i = head[a];
+            flowA0[a] = supA0[j]; flowA1[a] = supA1[j];
+            supA0[i] += supA0[j] * mu;
+            supA1[i] += supA1[j] * mu;
+        } else {
+            const int32_t i = tail[a];
+            flowA0[a] = supA0[j] / (-1.0 * mu);
+            flowA1[a] = supA1[j] / (-1.0 * mu);
+            supA0[i] += supA0[j] / mu;
+            supA1[i] += supA1[j] / mu;
+        }
+        supA0[j] = 0.0; supA1[j] = 0.0;
+    }
+    const double theta = (-1.0 * supA0[h]) / supA1[h];
+    supA0[h] = 0.0; supA1[h] = 0.0;
+    for (size_t k = 0; k < t.arcs.size(); ++k) {
+        const int32_t a = t.arcs[k];
+        const double p = flowA1[a] * theta;
+        deltaFlow[a] = flowA0[a] + p;
+        flowA0[a] = 0.0; flowA1[a] = 0.0;
+        checkVarForBlocking(a);
+    }
+    const double p = flowA1[ex] * theta;
+    deltaFlow[ex] = flowA0[ex] + p;
+    flowA0[ex] = 0.0; flowA1[ex] = 0.0;
+    checkVarForBlocking(ex);
+}
+
+void GenNetEq::computeFlows(int updateOption)                     // gneFlow.cpp:30-56
+{
+    flowCost = 0.0;
+    for (int i = 0; i < numNodes; ++i) { supA0[i] = supply[i]; supA1[i] = 0.0; }     // :387-395
+    const size_t N = setNBarc.size();
+    for (size_t p = 0; p < N; ++p) {                                                   // :343-353, position order
+        const int32_t a = setNBarc[p];
+        if (setLoc[a] == L_var) {
+            flow[a] = 0.0;
+        } else {
+            flow[a] = UB[a];
+            flowCost += flow[a] * cost[a];
+            supA0[tail[a]] -= flow[a];
+            supA0[head[a]] += flow[a] * mult[a];
+        }
+    }
+    // one pass per type I tree; the trees are independent, so any order gives the same values
+    for (int s = 0; s < forest.numSlots(); ++s) if (forest.tree(s).type == TREE_I) computeFlowsTypeI(s);
+    for (size_t k = 0; k < setBarc.size(); ++k) {                                      // setFlowValues :59-149
+        const int32_t a = setBarc[k];
+        if (updateOption == 0 || updateOption > 1) flow[a] = deltaFlow[a];
+        flowCost += flow[a] * cost[a];
+        deltaFlow[a] = 0.0;
+    }
+}
+
+void GenNetEq::computeFlowsPivotingTI(int32_t eav, int32_t tU, int32_t tV)           // gneFlow.cpp:155-185
+{
+    if (setLoc[eav] == L_var) {
+        if (tail[eav] == head[eav]) supA0[tail[eav]] = -1.0 * (1.0 - mult[eav]);
+        else { supA0[tail[eav]] = -1.0; supA0[head[eav]] = mult[eav]; }
+    } else {
+        if (tail[eav] == head[eav]) supA0[tail[eav]] = (1.0 - mult[eav]);
+        else { supA0[tail[eav]] = 1.0; supA0[head[eav]] = -1.0 * mult[eav]; }
+    }
+    computeFlowsTypeI(tU);
+    if (tU != tV) computeFlowsTypeI(tV);
+}
+
+// ------------------------------------------------------------------------------------------
+// gnePotential.cpp: the root-relative sweep on the host for the trees a pivot touched, the
+// finalize on the device.  Untouched trees keep (a0, a1, theta), hence pi, bit for bit.
+// ------------------------------------------------------------------------------------------
+int GenNetEq::computePotentials()
+{
+    upNode.clear(); upSlot.clear(); upA0.clear(); upA1.clear(); upThetaSlot.clear(); upTheta.clear();
+    if ((int) thetaOfSlot.size() < forest.numSlots()) thetaOfSlot.resize(forest.numSlots(), 0.0);
+    for (size_t c = 0; c < forest.changed.size(); ++c) {
+        const int32_t slot = forest.changed[c];
+        forest.changedFlag[slot] = 0;
+        const Tree &t = forest.tree(slot);
+        if (t.type == TREE_FREE) continue;
+        if (t.type != TREE_I) { gne_set_error("type II tree at computePotentials (equal-flow sets are out of scope)"); return GNE_ERR_UNSUPPORTED; }
+        // computePotentialsInTermsOfRoot, gnePotential.cpp:64-110
+        const int32_t h = t.threads[0];
+        double a0 = 0.0, a1 = 1.0;
+        if (potA0[h] != a0 || potA1[h] != a1 || potSlot[h] != slot) {
+            potA0[h] = a0; potA1[h] = a1; potSlot[h] = slot;
+            upNode.push_back(h); upA0.push_back(a0); upA1.push_back(a1); upSlot.push_back(slot);
+        }
+        for (size_t q = 1; q < t.threads.size(); ++q) {
+            const int32_t j = t.threads[q];
+            const int32_t i = forest.pred[j];
+            const int32_t a = forest.predArc[j];
+            const double c0 = cost[a], mu = mult[a];
+            if (tail[a] == i) {
+                a0 = (potA0[i] - c0) / mu;
+                a1 = potA1[i] / mu;
+            } else {
+                const double p = mu * potA0[i];
+                a0 = p + c0;
+                a1 = mu * potA1[i];
+            }
+            if (memcmp(&potA0[j], &a0, 8) != 0 || memcmp(&potA1[j], &a1, 8) != 0 || potSlot[j] != slot) {
+                potA0[j] = a0; potA1[j] = a1; potSlot[j] = slot;
+                upNode.push_back(j); upA0.push_back(a0); upA1.push_back(a1); upSlot.push_back(slot);
+            }
+        }
+        // theta, gnePotential.cpp:116-124
+        const int32_t ex = t.extraArc;
+        const int32_t alpha = tail[ex], beta = head[ex];
+        const double pb0 = mult[ex] * potA0[beta];
+        const double pb1 = mult[ex] * potA1[beta];
+        const double theta = ((cost[ex] - potA0[alpha]) + pb0) / (potA1[alpha] - pb1);
+        thetaOfSlot[slot] = theta;
+        upThetaSlot.push_back(slot); upTheta.push_back(theta);
+    }
+    forest.changed.clear();
+    if (!upNode.empty()) GNE_TRY(gne_pot_update_nodes(dev, (int64_t) upNode.size(), upNode.data(), upA0.data(), upA1.data(), upSlot.data()));
+    if (!upThetaSlot.empty()) GNE_TRY(gne_pot_update_thetas(dev, (int64_t) upThetaSlot.size(), upThetaSlot.data(), upTheta.data()));
+    if (!upNode.empty() || !upThetaSlot.empty()) GNE_TRY(gne_pot_finalize(dev));     // gnePotential.cpp:127-135
+    return GNE_OK;
+}
+
+int GenNetEq::fetchViolators(double threshold)
+{
+    int64_t cnt = 0;
+    if (listPos.size() < 1024) { listPos.resize(1024); listViol.resize(1024); }
+    int rc = gne_price_violators(dev, threshold, &cnt, listPos.data(), listViol.data(), (int64_t) listPos.size());
+    if (rc == GNE_ERR_CAPACITY) {
+        listPos.resize((size_t) cnt + 1024); listViol.resize((size_t) cnt + 1024);
+        rc = gne_price_violators(dev, threshold, &cnt, listPos.data(), listViol.data(), (int64_t) listPos.size());
+    }
+    if (rc) return rc;
+    arcsPriced += (double) setNBarc.size();
+    float ms = 0; gne_dev_last_kernel_ms(dev, &ms); kernelMs += ms;
+    offendingVars.resize((size_t) cnt); offendingViol.resize((size_t) cnt);
+    for (int64_t i = 0; i < cnt; ++i) { offendingVars[i] = setNBarc[listPos[i]]; offendingViol[i] = listViol[i]; }
+    return GNE_OK;
+}
+
+int GenNetEq::computeReducedCosts(bool /*includeBasicVars: only feeds prints in the reference*/)   // gnePotential.cpp:217-258
+{
+    isOptimal = true;
+    GNE_TRY(fetchViolators(0.0));
+    if (!offendingVars.empty()) isOptimal = false;
+    return GNE_OK;
+}
+
+int GenNetEq::verifyOptimality()                                  // gnePotential.cpp:261-287
+{
+    GNE_TRY(computePotentials());
+    return computeReducedCosts(true);
+}
+
+// ------------------------------------------------------------------------------------------
+// gnePivotRules.cpp
+// ------------------------------------------------------------------------------------------
+int GenNetEq::getVarWithLargestViolation(int32_t *out)            // :133-157 (LVA :160-180, LVE :183-203 coincide at p = 0)
+{
+    isOptimal = true;
+    offendingVars.clear();
+    double largest = -1.0;
+    int64_t cnt = 0;
+    int any = 0;
+    if (listPos.size() < 4096) { listPos.resize(4096); listViol.resize(4096); }
+    int rc = gne_price_lv(dev, &largest, &cnt, listPos.data(), (int64_t) listPos.size(), &any);
+    if (rc == GNE_ERR_CAPACITY) {
+        listPos.resize((size_t) cnt + 1024); listViol.resize((size_t) cnt + 1024);
+        rc = gne_price_lv(dev, &largest, &cnt, listPos.data(), (int64_t) listPos.size(), &any);
+    }
+    if (rc) return rc;
+    arcsPriced += (double) setNBarc.size();
+    float ms = 0; gne_dev_last_kernel_ms(dev, &ms); kernelMs += ms;
+    if (any) isOptimal = false;
+    offendingVars.resize((size_t) cnt);
+    for (int64_t i = 0; i < cnt; ++i) offendingVars[i] = setNBarc[listPos[i]];
+    lastViolation = largest;
+    if (offendingVars.empty()) { *out = -1; return GNE_OK; }
+    *out = offendingVars[(size_t) (drand48() * offendingVars.size())];       // selectRandomOffendingVar == true
+    return GNE_OK;
+}
+
+int GenNetEq::getFirstVarWithViolation(int32_t *out)              // :206-228
+{
+    isOptimal = true;
+    int64_t pos = -1;
+    GNE_TRY(gne_price_first(dev, &pos));
+    arcsPriced += (double) (pos < 0 ? (int64_t) setNBarc.size() : pos + 1);
+    float ms = 0; gne_dev_last_kernel_ms(dev, &ms); kernelMs += ms;
+    if (pos < 0) { *out = -1; return GNE_OK; }
+    isOptimal = false;
+    *out = setNBarc[pos];
+    return GNE_OK;
+}
+
+int GenNetEq::getRandomVarWithViolation(int32_t *out)             // :273-281
+{
+    GNE_TRY(computeReducedCosts(false));
+    if (offendingVars.empty()) { *out = -1; return GNE_OK; }
+    *out = offendingVars[(size_t) (drand48() * offendingVars.size())];
+    return GNE_OK;
+}
+
+int GenNetEq::getRandomVarWeightedByViolation(int32_t *out)       // :284-304
+{
+    GNE_TRY(computeReducedCosts(false));
+    *out = -1;
+    if (!offendingVars.empty()) {
+        double sum = 0.0;
+        for (size_t i = 0; i < offendingVars.size(); ++i) sum += offendingViol[i];     // fabs(var->redCost)
+        const double level = drand48() * sum;
+        double run = 0.0;
+        for (size_t i = 0; i < offendingVars.size(); ++i) {
+            run += offendingViol[i];
+            if (level <= run) { *out = offendingVars[i]; break; }
+        }
+    }
+    return GNE_OK;
+}
+
+int GenNetEq::getRandomVarWithLargeViolation(int32_t *out)        // :307-362
+{
+    isOptimal = true;
+    GNE_TRY(fetchViolators(0.0));
+    std::priority_queue<VarWithViol, std::vector<VarWithViol>, violcomp> q;
+    for (size_t i = 0; i < offendingVars.size(); ++i) {             // position order, as the reference pushes
+        isOptimal = false;
+        VarWithViol vv; vv.var = offendingVars[i]; vv.violation = -1.0 * offendingViol[i];
+        q.push(vv);
+        while ((int) q.size() > numLargestViolVarsToTrack) q.pop();
+    }
+    std::vector<int32_t> fin;
+    while (!q.empty()) { fin.push_back(q.top().var); q.pop(); }
+    if (fin.empty()) { *out = -1; return GNE_OK; }
+    *out = fin[(size_t) (drand48() * fin.size())];
+    return GNE_OK;
+}
+
+int GenNetEq::getVarBySimAnnealing(bool arcsFirst, int32_t *out)  // :364-396; both branches are LV at p = 0
+{
+    (void) drand48();
+    GNE_TRY(getVarWithLargestViolation(out));
+    if (arcsFirst && lastViolation * 100 < baselineViolation && baselineViolation > 5000) baselineViolation = lastViolation;
+    return GNE_OK;
+}
+
+int GenNetEq::updateCandidateList()                               // :504-535
+{
+    while (!candidateList.empty()) candidateList.pop();
+    GNE_TRY(fetchViolators(0.0));
+    for (size_t i = 0; i < offendingVars.size(); ++i) {
+        isOptimal = false;
+        VarWithViol vv; vv.var = offendingVars[i]; vv.violation = offendingViol[i];
+        candidateList.push(vv);
+    }
+    return GNE_OK;
+}
+
+int GenNetEq::getNextCandidate(int32_t *out)                      // :457-501
+{
+    isOptimal = true;
+    if (itersSinceUpdate < 0 || itersSinceUpdate > majorIterationLength) {
+        GNE_TRY(updateCandidateList());
+        itersSinceUpdate = 0;
+    } else {
+        ++itersSinceUpdate;
+    }
+    int32_t ev = -1;
+    while (!candidateList.empty()) {
+        const int32_t c = candidateList.top().var;
+        candidateList.pop();
+        const bool atLB = (setLoc[c] == L_var);
+        const double rc = computeArcRedCost(c);
+        if ((atLB && rc < (-1.0 * TOL)) || (!atLB && rc > TOL)) { isOptimal = false; ev = c; break; }
+    }
+    if (ev == -1 && itersSinceUpdate > 0) {
+        itersSinceUpdate = -1;
+        return getNextCandidate(out);
+    }
+    *out = ev;
+    return GNE_OK;
+}
+
+int GenNetEq::quickSelect(int32_t *out)                           // :710-764, arc loop
+{
+    isOptimal = true;
+    if (nbArcPivotInd >= (int64_t) setNBarc.size()) nbArcPivotInd = 0;
+    const int64_t start = nbArcPivotInd;
+    int64_t bestPos = -1, newCursor = start, scanned = 0, violations = 0;
+    double bestViol = 0.0;
+    GNE_TRY(gne_price_qs(dev, start, (int64_t) numNodes, &bestPos, &bestViol, &newCursor, &scanned, &violations));
+    arcsPriced += (double) scanned;
+    float ms = 0; gne_dev_last_kernel_ms(dev, &ms); kernelMs += ms;
+    if (violations > 0) isOptimal = false;
+    nbArcPivotInd = newCursor;
+    if ((loopIter % majorIterationLength) > 0) nbArcPivotInd = start;
+    *out = (bestPos >= 0) ? setNBarc[bestPos] : -1;
+    return GNE_OK;
+}
+
+int GenNetEq::selectEnteringVariable(int32_t *out)                // :36-127
+{
+    if (cyclingDetected) return getRandomVarWithLargeViolation(out);      // useRandomJumpWhenCycling == true
+    const int rule = presolve ? phaseIpivot : phaseIIpivot;
+    switch (rule) {
+      case GNE_LV: case GNE_LVW: case GNE_LVA: case GNE_LVE: return getVarWithLargestViolation(out);
+      case GNE_FV: return getFirstVarWithViolation(out);
+      case GNE_RV: return getRandomVarWithViolation(out);
+      case GNE_RWV: return getRandomVarWeightedByViolation(out);
+      case GNE_RLV: case GNE_RLVW: return getRandomVarWithLargeViolation(out);
+      case GNE_CL: case GNE_CLW: return getNextCandidate(out);
+      case GNE_SAA: return getVarBySimAnnealing(true, out);
+      case GNE_SAE: return getVarBySimAnnealing(false, out);
+      case GNE_QS: case GNE_QSW: return quickSelect(out);
+    }
+    gne_set_error("pivot rule %d is not supported (SD relies on the stale computeMinDelta, gnePivot.cpp:406; CL2 aborts the reference)", rule);
+    return GNE_ERR_UNSUPPORTED;
+}
+
+int GenNetEq::identifyEnteringVariable() { return selectEnteringVariable(&eVar); }   // :28-33
+
+// ------------------------------------------------------------------------------------------
+// gnePivot.cpp
+// ------------------------------------------------------------------------------------------
+void GenNetEq::identifyLeavingVar()                               // :166-209
+{
+    if (UB[eVar] <= delta + TOL) {
+        delta = UB[eVar];
+        lVar = eVar;
+    } else {
+        if (blockingVars.empty()) { isUnbounded = true; lVar = -1; return; }
+        lVar = blockingVars[(size_t) (drand48() * blockingVars.size())];   // selectRandomBlockingVar == true
+    }
+    if (delta <= TOL) { ++totalDegenPivots; ++consecutiveDegenPivots; }
+    else consecutiveDegenPivots = 0;
+}
+
+void GenNetEq::applyTreeFlow(int32_t slot)                        // :79-91
+{
+    const Tree &t = forest.tree(slot);
+    for (size_t k = 0; k < t.arcs.size(); ++k) {
+        const int32_t a = t.arcs[k];
+        const double d = delta * deltaFlow[a];
+        flow[a] += d;
+        flowCost += cost[a] * d;
+        deltaFlow[a] = 0.0;
+    }
+    const int32_t ex = t.extraArc;
+    const double d = delta * deltaFlow[ex];
+    flow[ex] += d;
+    flowCost += cost[ex] * d;
+    deltaFlow[ex] = 0.0;
+}
+
+int GenNetEq::pivotTI(int32_t eav)                                // :63-119
+{
+    const int32_t tU = forest.treeOf(tail[eav]);
+    const int32_t tV = forest.treeOf(head[eav]);
+    delta = DBL_MAX;
+    const double f0 = wallNow();
+    computeFlowsPivotingTI(eav, tU, tV);
+    identifyLeavingVar();
+    if (lVar == -1) return GNE_OK;
+    applyTreeFlow(tU);
+    if (tU != tV) applyTreeFlow(tV);
+    if (setLoc[eav] == L_var) { flow[eav] = delta; flowCost += cost[eav] * delta; }
+    else { flow[eav] = UB[eav] - delta; flowCost -= cost[eav] * delta; }
+    secsFlows += wallNow() - f0;
+    return GNE_OK;
+}
+
+int GenNetEq::updateBasis()                                       // :254-309
+{
+    if (eVar == lVar) {
+        const int8_t was = setLoc[eVar];
+        GNE_TRY(removeFromNB(eVar));
+        GNE_TRY(insertIntoNB(eVar, was == L_var ? U_var : L_var));
+    } else {
+        GNE_TRY(removeFromNB(eVar));
+        const double t0 = wallNow();
+        GNE_TRY(removeFromB(lVar));
+        GNE_TRY(insertIntoB(eVar));
+        secsTrees += wallNow() - t0;
+        if (flow[lVar] > (0.5 * UB[lVar])) GNE_TRY(insertIntoNB(lVar, U_var));
+        else GNE_TRY(insertIntoNB(lVar, L_var));
+        const double t1 = wallNow();
+        forest.updateTrees();
+        secsTrees += wallNow() - t1;
+    }
+    if (setLoc[lVar] == L_var) {                                   // bound snap :294-306
+        if (fabs(flow[lVar] - 0.0) > TOL) flow[lVar] = 0.0;
+    } else {
+        if (fabs(flow[lVar] - UB[lVar]) > TOL) flow[lVar] = UB[lVar];
+    }
+    return GNE_OK;
+}
+
+void GenNetEq::checkForCycling()                                  // :312-356
+{
+    if (cycleList.size() >= 10) cycleList.pop_back();
+    cycleList.push_front(std::make_pair(eVar, lVar));
+    cyclingDetected = false;
+    std::list<std::pair<int32_t, int32_t> >::iterator it = cycleList.begin();
+    for (++it; it != cycleList.end(); ++it) {
+        if (cycleList.front().first == it->first && cycleList.front().second == it->second) { cyclingDetected = true; break; }
+    }
+    if (cyclingDetected) {
+        ++totalCyclesDetected;
+        ++consecutiveCycles;
+        if (consecutiveCycles > 5) { gne_set_error("Stuck in cycling loop.  Retry with different pivots."); status = GNE_ERR_CYCLING; }
+    } else {
+        consecutiveCycles = 0;
+    }
+    lastEVarInd = eVar;
+}
+
+int GenNetEq::pivot()                                             // :28-60
+{
+    if (forest.typeOf(tail[eVar]) == TREE_I && forest.typeOf(head[eVar]) == TREE_I) {
+        GNE_TRY(pivotTI(eVar));
+    } else {
+        gne_set_error("pivotTII reached (equal-flow sets are out of scope)");
+        return GNE_ERR_UNSUPPORTED;
+    }
+    if (lVar == -1) return GNE_OK;
+    GNE_TRY(updateBasis());
+    checkForCycling();
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------
+// genneteq.cpp
+// ------------------------------------------------------------------------------------------
+void GenNetEq::initializeStats(bool usePresolve)                  // :123-167
+{
+    presolve = usePresolve;
+    isOptimal = false; isInfeasible = false; isUnbounded = false;
+    loopIter = 0;
+    consecutiveCycles = 0; consecutiveDegenPivots = 0; totalCyclesDetected = 0; totalDegenPivots = 0;
+    cyclingDetected = false;
+    lastEVarInd = -1;
+    itersSinceUpdate = -1;
+    numLargestViolVarsToTrack = 5;
+    majorIterationLength = 3;
+    clMaxSize = numNodes;
+    nbArcPivotInd = 0;
+    numArcsToAlwaysCheck = 5;
+    baselineViolation = lastViolation;
+}
+
+int GenNetEq::setVariableCosts()                                  // :304-323 + re-upload of the cost column
+{
+    if (presolve) for (int64_t i = 0; i < M; ++i) cost[i] = isArtificial[i] ? 1.0 : 0.0;
+    else for (int64_t i = 0; i < M; ++i) cost[i] = actualCost[i];
+    if (!dev) {
+        uint8_t none[128] = { 0 };
+        GNE_TRY(setComm(none, 0, 1));
+    }
+    const size_t N = setNBarc.size();
+    if (!costsOnDevice) {
+        std::vector<int32_t> t(N), h(N);
+        std::vector<double> c(N), mu(N);
+        std::vector<int8_t> st(N);
+        for (size_t p = 0; p < N; ++p) { const int32_t a = setNBarc[p]; t[p] = tail[a]; h[p] = head[a]; c[p] = cost[a]; mu[p] = mult[a]; st[p] = setLoc[a]; }
+        GNE_TRY(gne_nb_reset(dev, (int64_t) N, t.data(), h.data(), c.data(), mu.data(), st.data()));
+        costsOnDevice = true;
+    } else {
+        std::vector<double> c(N);
+        for (size_t p = 0; p < N; ++p) c[p] = cost[setNBarc[p]];
+        GNE_TRY(gne_dev_flush(dev));
+        GNE_TRY(gne_nb_set_costs(dev, (int64_t) N, c.data()));
+    }
+    // every tree's potentials depend on the costs
+    for (int s = 0; s < forest.numSlots(); ++s) if (forest.tree(s).type != TREE_FREE) forest.markChanged(s);
+    return GNE_OK;
+}
+
+void GenNetEq::checkFeasibility()                                 // :227-288
+{
+    isInfeasible = false;
+    for (size_t k = 0; k < setBarc.size(); ++k) {
+        const int32_t a = setBarc[k];
+        if ((isArtificial[a] && flow[a] > TOL) || flow[a] < 0.0 - TOL || flow[a] > UB[a] + TOL) { isInfeasible = true; return; }
+    }
+    for (size_t p = 0; p < setNBarc.size(); ++p) {
+        const int32_t a = setNBarc[p];
+        if (isArtificial[a] && setLoc[a] == U_var) { isInfeasible = true; return; }
+    }
+}
+
+int GenNetEq::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished)   // :60-117
+{
+    const bool pIwasInfeasible = usePresolve ? false : isInfeasible;
+    initializeStats(usePresolve);
+    GNE_TRY(setVariableCosts());
+    *finished = 1;
+    *iters = 0;
+    if (!presolve && pIwasInfeasible) { isInfeasible = true; return GNE_OK; }
+    const double t0 = wallNow();
+    computeFlows(0);
+    int64_t budget = maxPivots;
+    while (!isOptimal && !isUnbounded) {
+        if (maxPivots >= 0 && budget == 0) { *finished = 0; break; }
+        if ((loopIter % 1000) == 0) computeFlows(2);
+        const double a = wallNow();
+        GNE_TRY(computePotentials());
+        const double b = wallNow();
+        GNE_TRY(identifyEnteringVariable());
+        const double c = wallNow();
+        secsPotentials += b - a; secsPricing += c - b;
+        if (eVar != -1) {
+            GNE_TRY(pivot());
+            secsPivot += wallNow() - c;
+            if (lVar != -1) {
+                if (traceLen < traceCap) { traceE[traceLen] = eVar; traceL[traceLen] = lVar; }
+                ++traceLen;
+            }
+            ++loopIter; ++pivots;
+            if (presolve) ++phaseIiters; else ++phaseIIiters;
+            if (budget > 0) --budget;
+        }
+    }
+    if (*finished) {
+        computeFlows(0);
+        if (presolve) checkFeasibility();
+        GNE_TRY(verifyOptimality());
+    }
+    secsTotal += wallNow() - t0;
+    *iters = loopIter;
+    return GNE_OK;
+}
+
+void GenNetEq::getFlows(double *out) const { memcpy(out, flow.data(), sizeof(double) * (size_t) M); }
+
+int GenNetEq::getPotentials(double *out)
+{
+    // the device holds the authoritative pi; slots 0..numNodes-1 of its node arrays are ours
+    std::vector<double> tmp((size_t) numNodes + 16);
+    GNE_TRY(gne_pot_get_all(dev, tmp.data()));
+    memcpy(out, tmp.data(), sizeof(double) * (size_t) numNodes);
+    return GNE_OK;
+}
+
+void GenNetEq::getStates(int32_t *out) const { for (int64_t i = 0; i < M; ++i) out[i] = setLoc[i]; }
+
+void GenNetEq::getCounters(double *o) const
+{
+    int64_t h2d = 0, d2h = 0;
+    if (dev) gne_dev_traffic(dev, &h2d, &d2h);
+    o[0] = secsPricing; o[1] = secsPotentials; o[2] = secsPivot; o[3] = secsTotal; o[4] = arcsPriced; o[5] = kernelMs;
+    o[6] = (double) h2d; o[7] = (double) d2h; o[8] = dev ? (double) gne_dev_launch_count(dev) : 0.0; o[9] = (double) pivots;
+    o[10] = secsTrees; o[11] = secsFlows;
+}
+
+} // namespace gneb200

@@ -1,0 +1,184 @@
+/* genneteq_b200 — C ABI of the B200 (sm_100a) pricing / relabel path of GenNetEq's generalized
+ * network simplex.  Plain pointers and sizes only; every function returns a gne_status (0 = ok)
+ * and never exits or throws across the boundary (the reference printf+exit()s instead,
+ * trees.cpp:310-313, gnePivot.cpp:342-345).  One host thread per handle; each handle owns one
+ * CUDA stream and all of its device memory until *_destroy.  Caller owns every host buffer.
+ *
+ * The reference has no FFI: its "operator interface" is the set of protected, non-virtual
+ * members GenNetEq::solve calls every iteration (genneteq.cpp:97-100).  Each entry point below
+ * names the reference code it replaces.  INTEGRATION.md shows the derived-class stub a
+ * maintainer of the reference would add to route those three calls here.
+ *
+ * Layer 1 (gne_dev_*)   the device operators: nonbasic-arc structure-of-arrays in setNBarc
+ *                       position order, node potentials, pricing passes.
+ * Layer 2 (gne_solver_*) a host C++ mirror of GenNetEq (initialize / solve) that drives layer 1.
+ * There is no CPU fallback: every call fails with GNE_ERR_CUDA when no device is usable.
+ */
+#ifndef GENNETEQ_B200_H
+#define GENNETEQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GNE_OK = 0,
+    GNE_ERR_CUDA = 1,          /* CUDA runtime error or no device (gne_last_error() has the text) */
+    GNE_ERR_ARG = 2,           /* bad argument */
+    GNE_ERR_CAPACITY = 3,      /* caller's output buffer too small; *count still holds the need  */
+    GNE_ERR_TREE = 4,          /* basis forest invariant broken (reference: exit(-1), trees.cpp:310-313,327-330,469-472) */
+    GNE_ERR_CYCLING = 5,       /* >5 consecutive cycles (reference: exit(-1), gnePivot.cpp:342-345) */
+    GNE_ERR_UNSUPPORTED = 6,   /* equal-flow sets / pivotTII / rule SD: out of scope              */
+    GNE_ERR_COMM = 7           /* NCCL error                                                      */
+} gne_status;
+
+/* pivot-rule ids: main.h:17-34 */
+enum { GNE_LV = 0, GNE_LVW = 1, GNE_LVA = 2, GNE_LVE = 3, GNE_FV = 4, GNE_SD = 5, GNE_RV = 6, GNE_RWV = 7,
+       GNE_RLV = 8, GNE_RLVW = 9, GNE_CL = 10, GNE_CLW = 11, GNE_SAA = 12, GNE_SAE = 13, GNE_CL2 = 14,
+       GNE_CLW2 = 15, GNE_QS = 16, GNE_QSW = 17 };
+/* Variable::setLoc, variables.h:23 */
+enum { GNE_AT_LOWER = 1, GNE_AT_UPPER = 2 };
+
+#define GNE_ROUNDOFF_TOLERANCE 1.0e-13      /* main.h:36-43 */
+
+const char *gne_last_error(void);
+const char *gne_version(void);
+int gne_cuda_device_count(void);            /* 0 when no usable device (never falls back to the CPU) */
+
+/* =============================== layer 1: device operators =============================== */
+typedef struct gne_dev gne_dev;
+
+/* n nodes, room for nbCapacity nonbasic arcs.  Multi-GPU: this handle prices global positions
+ * [shardLo, shardHi) of the nonbasic list (pass 0, nbCapacity for a single GPU).            */
+int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi);
+int gne_dev_destroy(gne_dev *d);
+int gne_dev_sync(gne_dev *d);
+
+/* --- nonbasic set mirror: GenNetEq::setNBarc + insertIntoL/U, removeFromL/U (gnePivot.cpp:527-600) --- */
+/* whole list, position order; arrays hold the GLOBAL list, the handle keeps its shard        */
+int gne_nb_reset(gne_dev *d, int64_t N, const int32_t *tail, const int32_t *head, const double *cost,
+                 const double *mult, const int8_t *state);
+/* setVariableCosts (genneteq.cpp:304-323): new cost per position after a phase switch         */
+int gne_nb_set_costs(gne_dev *d, int64_t N, const double *cost);
+/* one record; swap-remove = write(pos, record of the last position) then set_count(N-1);
+ * push = write(N, record) then set_count(N+1).  Writes outside the shard are ignored.        */
+int gne_nb_write(gne_dev *d, int64_t pos, int32_t tail, int32_t head, double cost, double mult, int8_t state);
+int gne_nb_set_count(gne_dev *d, int64_t N);
+/* read back (tests): any of the output pointers may be NULL                                   */
+int gne_nb_read(gne_dev *d, int64_t lo, int64_t hi, int32_t *tail, int32_t *head, double *cost, double *mult, int8_t *state);
+
+/* --- potentials: computePotentials (gnePotential.cpp:28-61) ---
+ * The device keeps, per node, the root-relative pair (a0, a1) of computePotentialsInTermsOfRoot
+ * (gnePotential.cpp:64-110) and the slot of its tree; per slot the tree's theta
+ * (gnePotential.cpp:123-124).  finalize computes pi[i] = a0[i] + a1[i] * theta[slot[i]]
+ * (gnePotential.cpp:127-135; multiply then add, never fused).  Only dirty entries cross PCIe. */
+int gne_pot_update_nodes(gne_dev *d, int64_t count, const int32_t *node, const double *a0, const double *a1, const int32_t *slot);
+int gne_pot_update_thetas(gne_dev *d, int64_t count, const int32_t *slot, const double *theta);
+int gne_pot_finalize(gne_dev *d);
+/* direct write of pi (callers that computed potentials themselves)                            */
+int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const double *pi);
+int gne_pot_set_all(gne_dev *d, const double *pi);
+int gne_pot_get_all(gne_dev *d, double *pi);
+
+/* --- pricing: rc = (cost - pi[tail]) + (mult * pi[head]) (computeArcRedCost, genneteq.h:312-318);
+ * violated <=> (L && rc < -tol) || (U && rc > tol) (gnePivotRules.cpp:406-407).  Positions are
+ * global positions in the nonbasic list. --- */
+
+/* getVarWithLargestViolation's arc pass: computeArcsWithLargestViolation + checkVarForOffending
+ * (gnePivotRules.cpp:401-413, 431-452).  Outputs exactly what the sequential tolerance-band
+ * rule leaves behind: the final running largestViolation and offendingVars (as positions,
+ * in list order).  *count = list length; GNE_ERR_CAPACITY if > cap.  *any = !isOptimal.      */
+int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count, int64_t *listPos, int64_t cap, int *any);
+
+/* quickSelect's arc loop (gnePivotRules.cpp:742-756): scan from `cursor` (wrapping) until `want`
+ * violators were seen or the list is exhausted; best = first strictly-largest |rc|.
+ * *bestPos = -1 when there is no violator.  *newCursor is the cursor after the scan (the
+ * caller applies the loopIter % majorIterationLength restore, :758-761).                     */
+int gne_price_qs(gne_dev *d, int64_t cursor, int64_t want, int64_t *bestPos, double *bestViol,
+                 int64_t *newCursor, int64_t *scanned, int64_t *violations);
+
+/* every violator with |rc| >= threshold, in position order (updateCandidateList
+ * gnePivotRules.cpp:504-516; computeReducedCosts gnePotential.cpp:226-234;
+ * getRandomVarWithLargeViolation :311-328).  listViol may be NULL.                           */
+int gne_price_violators(gne_dev *d, double threshold, int64_t *count, int64_t *listPos, double *listViol, int64_t cap);
+
+/* getFirstVarWithViolation (gnePivotRules.cpp:206-228): lowest violating position or -1       */
+int gne_price_first(gne_dev *d, int64_t *pos);
+
+/* reduced cost of every position in [lo, hi) (tests, verifyOptimality)                        */
+int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc);
+
+/* device time of the last pricing call's kernels in milliseconds (CUDA events on the handle's stream) */
+int gne_dev_last_kernel_ms(gne_dev *d, float *ms);
+/* number of kernels this handle has launched since creation                                   */
+int64_t gne_dev_launch_count(gne_dev *d);
+/* replay timing helper for bench.py: runs `reps` LV pricing passes back to back on the resident
+ * state, each bracketed by CUDA events on the handle's stream; flushL2 != 0 writes a >L2 scratch
+ * buffer between passes (outside the events).  Writes per-pass milliseconds.                  */
+int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, float *msPerPass);
+
+/* --- multi-GPU exchange (one process per GPU; NCCL over NVLink) --- */
+/* 128-byte opaque id made on rank 0 and broadcast by the caller (torch.distributed)           */
+int gne_comm_unique_id(uint8_t id[128]);
+int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nranks);
+int gne_comm_destroy(gne_dev *d);
+
+/* =============================== layer 2: solver mirror =============================== */
+typedef struct gne_solver gne_solver;
+
+/* GenNetEq::initialize (gneInit.cpp:25-44) from a sparse arc list sorted by (tail, head) —
+ * the varIndex order of gneInit.cpp:82-107.  bigM as graph.cpp:43, or < 0 to have it computed. */
+int gne_solver_create(gne_solver **out, int cudaDevice, int n, int64_t m, const int32_t *tail, const int32_t *head,
+                      const double *ub, const double *cost, const double *mult, const double *supply, double bigM);
+/* the reference's text format (graph.cpp:358-447) read sparsely                               */
+int gne_solver_create_from_col(gne_solver **out, int cudaDevice, const char *path);
+int gne_solver_destroy(gne_solver *s);
+/* globals phaseIpivot / phaseIIpivot (main.cpp:21-22)                                        */
+int gne_solver_set_rules(gne_solver *s, int phaseIpivot, int phaseIIpivot);
+/* shard the pricing over ranks (call before the first solve); id from gne_comm_unique_id     */
+int gne_solver_set_comm(gne_solver *s, const uint8_t id[128], int rank, int nranks);
+/* record (eVar, lVar) varIndex pairs of every pivot                                           */
+int gne_solver_set_trace(gne_solver *s, int32_t *e, int32_t *l, int64_t cap);
+int64_t gne_solver_trace_len(const gne_solver *s);
+/* GenNetEq::solve(usePresolve) (genneteq.cpp:60-117).  maxPivots < 0: to termination.
+ * *iters = loopIter; *finished = 0 when the pivot budget stopped it.                          */
+int gne_solver_solve(gne_solver *s, int presolve, int64_t maxPivots, int64_t *iters, int *finished);
+
+int gne_solver_num_nodes(const gne_solver *s);
+int64_t gne_solver_num_vars(const gne_solver *s);
+double gne_solver_objective(const gne_solver *s);
+int gne_solver_feasible(const gne_solver *s);
+int gne_solver_get_flows(gne_solver *s, double *out);
+int gne_solver_get_potentials(gne_solver *s, double *out);
+int gne_solver_get_states(gne_solver *s, int32_t *out);
+int gne_solver_get_forest(gne_solver *s, int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread);
+/* counters: [0] pricing s (host wall incl. sync)  [1] potentials s  [2] pivot s  [3] total s
+ *           [4] arcs priced  [5] pricing kernel ms (device)  [6] H2D bytes  [7] D2H bytes
+ *           [8] kernel launches  [9] pivots  [10] tree surgery s  [11] flow/ratio s           */
+int gne_solver_get_counters(const gne_solver *s, double *out12);
+gne_dev *gne_solver_device(gne_solver *s);
+
+/* Host-only replay of basis exchanges (no device work, usable without a GPU): applies the given
+ * (entering, leaving) varIndex pairs to a fresh forest and returns its thread/pred arrays —
+ * lets the forest engine be checked against the oracle on CPU.                               */
+int gne_forest_replay(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *supply,
+                      int64_t pivots, const int32_t *e, const int32_t *l,
+                      int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread);
+
+/* merge of per-shard LV records (what every rank does after the all-gather); host-only.
+ * maxima[r], any[r], counts[r], and lists (pos, viol) concatenated rank-major with stride cap. */
+int gne_merge_lv_shards(int nranks, const double *maxima, const int *any, const int64_t *counts,
+                        const int64_t *listPos, const double *listViol, int64_t stride,
+                        double *largestViolation, int64_t *count, int64_t *outPos, int64_t cap, int *outAny, int *needFallback);
+
+/* deterministic large-instance generator (bench workloads C2-C5):
+ * ring i->i+1 plus random distinct heads, arcs sorted by (tail, head).  Arrays sized m / n.   */
+int gne_generate_instance(int n, int64_t m, uint64_t seed, int mode /*0 wide 1 lossy 2 near1 3 pow2*/,
+                          int32_t *tail, int32_t *head, double *ub, double *cost, double *mult, double *supply);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,339 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(include/genneteq_b200.h via ctypes); the checker is the oracle (oracle/gne_oracle.cpp) and the
+golden traces written by the unmodified reference (tests/golden).  Bar: bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle_util import RULES, Instance, Oracle, oracle_lib, dp, ip, lp, bp
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL = 1.0e-13
+
+
+@pytest.fixture(scope="module")
+def gne():
+    import genneteq_b200
+    assert genneteq_b200.cuda_device_count() > 0, "no CUDA device: these tests have no CPU fallback"
+    return genneteq_b200
+
+
+# ---------------------------------------------------------------- stateless kernels
+def random_soa(rng, n, N, mode="cont", frac_upper=0.3, scale=1.0):
+    tail = np.sort(rng.integers(0, n, N)).astype(np.int32)
+    head = rng.integers(0, n, N).astype(np.int32)
+    if mode == "ties":                                  # few distinct values => long exact tie lists
+        cost = rng.choice([0.0, 1.0, 2.0], N).astype(np.float64)
+        mult = rng.choice([0.5, 0.75, 1.25, 1.5, 2.0], N)
+        pi = rng.choice([-1.0, 2.0, 0.5], n).astype(np.float64)
+    elif mode == "near":                                # values within a few tolerance bands of each other
+        cost = 5.0 + rng.integers(0, 9, N) * 0.5e-13
+        mult = np.ones(N)
+        pi = np.zeros(n)
+        pi[: n // 2] = 10.0
+    else:
+        cost = rng.uniform(-50, 50, N) * scale
+        mult = rng.uniform(0.5, 1.5, N)
+        pi = rng.uniform(-100, 100, n) * scale
+    state = np.where(rng.random(N) < frac_upper, 2, 1).astype(np.int8)
+    return tail, head, cost, mult, state, pi
+
+
+def oracle_lv(tail, head, cost, mult, state, pi):
+    lib = oracle_lib()
+    N = len(tail)
+    lst = np.zeros(max(N, 1), np.int64); L = C.c_double(0); anyv = C.c_int(0)
+    k = lib.orc_price_lv(C.c_long(N), ip(tail), ip(head), dp(cost), dp(mult), bp(state), dp(pi), lp(lst), C.c_long(max(N, 1)),
+                         C.byref(L), C.byref(anyv))
+    return L.value, lst[:k].copy(), bool(anyv.value)
+
+
+def oracle_qs(tail, head, cost, mult, state, pi, cursor, want):
+    lib = oracle_lib()
+    bp_ = C.c_long(0); bv = C.c_double(0); nc = C.c_long(0); sc = C.c_long(0); vi = C.c_long(0)
+    lib.orc_price_qs(C.c_long(len(tail)), ip(tail), ip(head), dp(cost), dp(mult), bp(state), dp(pi), C.c_long(cursor),
+                     C.c_long(want), C.byref(bp_), C.byref(bv), C.byref(nc), C.byref(sc), C.byref(vi))
+    return dict(best_pos=bp_.value, best_viol=bv.value, new_cursor=nc.value, scanned=sc.value, violations=vi.value)
+
+
+def oracle_violators(tail, head, cost, mult, state, pi, thr):
+    lib = oracle_lib()
+    N = len(tail)
+    pos = np.zeros(max(N, 1), np.int64); viol = np.zeros(max(N, 1))
+    k = lib.orc_price_violators(C.c_long(N), ip(tail), ip(head), dp(cost), dp(mult), bp(state), dp(pi), C.c_double(thr),
+                                lp(pos), dp(viol), C.c_long(max(N, 1)))
+    return pos[:k].copy(), viol[:k].copy()
+
+
+SIZES = [(50, 1), (50, 7), (300, 2047), (300, 2048), (300, 2049), (1000, 10000), (5000, 262144), (20000, 1000003)]
+
+
+@pytest.mark.parametrize("n,N", SIZES)
+@pytest.mark.parametrize("mode", ["cont", "ties", "near"])
+def test_price_lv_matches_sequential_rule(gne, n, N, mode):
+    rng = np.random.default_rng(n * 7 + N)
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N, mode)
+    d = gne.Device(n, N + 16)
+    d.nb_reset(tail, head, cost, mult, state)
+    d.pot_set_all(pi)
+    L, lst, anyv = d.price_lv()
+    oL, olst, oany = oracle_lv(tail, head, cost, mult, state, pi)
+    assert anyv == oany
+    assert L == oL
+    assert np.array_equal(lst, olst)
+    # reduced costs themselves, bit for bit
+    rc = d.reduced_costs()
+    orc = np.zeros(N)
+    oracle_lib().orc_reduced_costs(C.c_long(N), ip(tail), ip(head), dp(cost), dp(mult), dp(pi), dp(orc))
+    assert np.array_equal(rc, orc)
+    d.close()
+
+
+def test_price_lv_no_violator_and_huge_magnitudes(gne):
+    rng = np.random.default_rng(5)
+    n, N = 400, 30000
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N, "cont")
+    d = gne.Device(n, N + 16)
+    d.nb_reset(tail, head, np.full(N, 1e9), mult, np.ones(N, np.int8))     # rc > 0 at lower bound: nothing violates
+    d.pot_set_all(np.zeros(n))
+    L, lst, anyv = d.price_lv()
+    assert (L, len(lst), anyv) == (-1.0, 0, False)
+    assert d.price_first() == -1
+    # bigM-sized values: ulp >> tolerance, ties are exact-equality only
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N, "cont", scale=2.0e9)
+    d.nb_reset(tail, head, cost, mult, state)
+    d.pot_set_all(pi)
+    L, lst, anyv = d.price_lv()
+    oL, olst, oany = oracle_lv(tail, head, cost, mult, state, pi)
+    assert (L, anyv) == (oL, oany) and np.array_equal(lst, olst)
+    d.close()
+
+
+@pytest.mark.parametrize("n,N", [(50, 7), (300, 2049), (1000, 10000), (5000, 262144), (20000, 1000003)])
+def test_price_qs_matches_scan(gne, n, N):
+    rng = np.random.default_rng(N)
+    for mode, fu in (("cont", 0.3), ("ties", 0.5), ("cont", 0.999)):
+        tail, head, cost, mult, state, pi = random_soa(rng, n, N, mode, frac_upper=fu)
+        if fu > 0.9:                                    # almost nothing violates: the scan wraps the whole list
+            cost = np.abs(cost) + 500.0
+            state = np.ones(N, np.int8); state[rng.integers(0, N, 3)] = 2
+        d = gne.Device(n, N + 16)
+        d.nb_reset(tail, head, cost, mult, state)
+        d.pot_set_all(pi)
+        cursors = [0, 1, N // 3, N - 1, N, N + 5] + [int(c) for c in rng.integers(0, N, 4)]
+        wants = [1, 2, n, max(1, N // 7), 10 * N]
+        for cur in cursors:
+            for want in wants:
+                got = d.price_qs(cur, want)
+                exp = oracle_qs(tail, head, cost, mult, state, pi, cur, want)
+                assert got == exp, (mode, cur, want, got, exp)
+        d.close()
+
+
+@pytest.mark.parametrize("n,N", [(50, 7), (300, 2049), (5000, 262144), (20000, 1000003)])
+def test_price_violators_and_first(gne, n, N):
+    rng = np.random.default_rng(N + 1)
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N, "cont")
+    d = gne.Device(n, N + 16)
+    d.nb_reset(tail, head, cost, mult, state)
+    d.pot_set_all(pi)
+    for thr in (0.0, 10.0, 140.0, 1e9):
+        pos, viol = d.price_violators(thr)
+        opos, oviol = oracle_violators(tail, head, cost, mult, state, pi, thr)
+        assert np.array_equal(pos, opos) and np.array_equal(viol, oviol)
+    opos, _ = oracle_violators(tail, head, cost, mult, state, pi, 0.0)
+    assert d.price_first() == (int(opos[0]) if len(opos) else -1)
+    d.close()
+
+
+def test_nonbasic_mirror_swap_remove_and_push(gne):
+    """setNBarc semantics (gnePivot.cpp:527-600) mirrored with gne_nb_write / gne_nb_set_count."""
+    rng = np.random.default_rng(11)
+    n, N = 200, 5000
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N, "cont")
+    d = gne.Device(n, N + 16)
+    d.nb_reset(tail, head, cost, mult, state)
+    d.pot_set_all(pi)
+    T, H, Cc, Mm, S = [list(a) for a in (tail, head, cost, mult, state)]
+    for step in range(300):
+        p = int(rng.integers(0, len(T)))
+        rec = (T[p], H[p], Cc[p], Mm[p], S[p])
+        last = len(T) - 1                               # removeFromL/U: last element moves into the hole
+        if p != last:
+            d.nb_write(p, int(T[last]), int(H[last]), float(Cc[last]), float(Mm[last]), int(S[last]))
+            T[p], H[p], Cc[p], Mm[p], S[p] = T[last], H[last], Cc[last], Mm[last], S[last]
+        for a in (T, H, Cc, Mm, S):
+            a.pop()
+        d.nb_set_count(len(T))
+        if step % 3:                                    # insertIntoL/U: push_back, maybe with the other bound
+            ns = 3 - rec[4] if step % 2 else rec[4]
+            d.nb_write(len(T), int(rec[0]), int(rec[1]), float(rec[2]), float(rec[3]), int(ns))
+            T.append(rec[0]); H.append(rec[1]); Cc.append(rec[2]); Mm.append(rec[3]); S.append(ns)
+            d.nb_set_count(len(T))
+        if step % 25 == 0:
+            a = [np.array(x, dt) for x, dt in ((T, np.int32), (H, np.int32), (Cc, np.float64), (Mm, np.float64), (S, np.int8))]
+            L, lst, anyv = d.price_lv()
+            oL, olst, oany = oracle_lv(a[0], a[1], a[2], a[3], a[4], pi)
+            assert (L, anyv) == (oL, oany) and np.array_equal(lst, olst)
+    rt, rh, rcst, rm, rs = d.nb_read(0, len(T))
+    assert np.array_equal(rt, np.array(T, np.int32)) and np.array_equal(rs, np.array(S, np.int8))
+    assert np.array_equal(rcst, np.array(Cc)) and np.array_equal(rm, np.array(Mm)) and np.array_equal(rh, np.array(H, np.int32))
+    d.close()
+
+
+def test_potential_finalize_matches_oracle(gne):
+    """pi = a0 + a1 * theta[slot] (gnePotential.cpp:127-135), multiply then add, bit for bit."""
+    rng = np.random.default_rng(3)
+    n = 100003
+    a0 = rng.uniform(-1e3, 1e3, n); a1 = rng.uniform(-3, 3, n)
+    slot = rng.integers(0, 977, n).astype(np.int32)
+    theta = rng.uniform(-50, 50, 977)
+    d = gne.Device(n, 4096)
+    d.pot_update_nodes(np.arange(n, dtype=np.int32), a0, a1, slot)
+    d.pot_update_thetas(np.arange(977, dtype=np.int32), theta)
+    d.pot_finalize()
+    got = d.pot_get_all()
+    exp = np.zeros(n)
+    for s in range(977):                                # per tree, as finalizePotentialsTypeI does
+        idx = np.nonzero(slot == s)[0].astype(np.int32)
+        oracle_lib().orc_finalize_potentials(C.c_long(len(idx)), ip(idx), dp(np.ascontiguousarray(a0[idx])),
+                                             dp(np.ascontiguousarray(a1[idx])), C.c_double(theta[s]), dp(exp))
+    assert np.array_equal(got, exp)
+    # dirty update of a few nodes and one theta
+    idx = rng.integers(0, n, 50).astype(np.int32)
+    idx = np.unique(idx)
+    a0[idx] += 1.0
+    theta[5] = -7.25
+    d.pot_update_nodes(idx, a0[idx], a1[idx], slot[idx])
+    d.pot_update_thetas(np.array([5], np.int32), np.array([-7.25]))
+    d.pot_finalize()
+    got = d.pot_get_all()
+    exp = a0 + a1 * theta[slot]
+    assert np.array_equal(got, exp)
+    d.close()
+
+
+# ---------------------------------------------------------------- solver level
+def load_gold(name):
+    from test_oracle_pinned import load
+    return load(name)
+
+
+def solve_gpu(gne, inst, rule, max_pivots=-1):
+    s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, rule1=rule)
+    p1, f1 = s.solve(True, max_pivots)
+    p2, f2 = (0, False)
+    if f1:
+        p2, f2 = s.solve(False, max_pivots)
+    return s, p1, p2
+
+
+@pytest.mark.parametrize("rn", ["LV", "LVW", "QS", "CL"])
+def test_c1_pivot_sequence_equals_reference(gne, rn):
+    """configs[0]: 1k nodes / 10k arcs; the golden trace was written by the unmodified reference."""
+    z, inst = load_gold("c1_wide_s7")
+    s, p1, p2 = solve_gpu(gne, inst, rn)
+    e, l = s.trace
+    assert (p1, p2) == tuple(int(v) for v in z[rn + "_p"])
+    assert np.array_equal(e, z[rn + "_e"]) and np.array_equal(l, z[rn + "_l"])
+    assert s.objective == float(z[rn + "_objective"])
+    assert np.array_equal(s.flows(), z[rn + "_flows"])
+    assert np.array_equal(s.potentials(), z[rn + "_potentials"])
+    assert s.feasible
+    assert s.counters()["launches"] > p1 + p2
+    s.close()
+
+
+SMALL = ["s_wide_s3", "s_lossy_s4", "s_pow2_s5", "s_near1_s6"]
+GPU_RULES = ["LV", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "QS", "QSW"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("rn", GPU_RULES)
+def test_small_instances_every_rule(gne, name, rn):
+    z, inst = load_gold(name)
+    s, p1, p2 = solve_gpu(gne, inst, rn)
+    e, l = s.trace
+    assert (p1, p2) == tuple(int(v) for v in z[rn + "_p"])
+    assert np.array_equal(e, z[rn + "_e"]) and np.array_equal(l, z[rn + "_l"])
+    assert s.objective == float(z[rn + "_objective"])
+    assert np.array_equal(s.flows(), z[rn + "_flows"])
+    assert np.array_equal(s.potentials(), z[rn + "_potentials"])
+    s.close()
+
+
+def test_col_file_loader_and_error_codes(gne, tmp_path):
+    z, inst = load_gold("s_wide_s3")
+    col = str(tmp_path / "i.col")
+    inst.write_col(col)
+    s = gne.Solver(col_path=col, rule1="QS")
+    p1, p2 = s.solve_both()
+    assert np.array_equal(s.trace[0], z["QS_e"]) and np.array_equal(s.trace[1], z["QS_l"])
+    s.close()
+    bad = str(tmp_path / "bad.col")
+    open(bad, "w").write("p efpgn 3 2 1\na 1 2 0.0 5.0 1.0 1.0 1\na 2 3 0.0 5.0 1.0 1.0 0\nn 1 1\nn 2 0\nn 3 -1\n")
+    with pytest.raises(gne.GneError) as ei:
+        gne.Solver(col_path=bad)
+    assert ei.value.code == 6                            # GNE_ERR_UNSUPPORTED: equal-flow sets
+    with pytest.raises(gne.GneError):
+        gne.Solver(col_path=str(tmp_path / "missing.col"))
+    with pytest.raises(gne.GneError):                    # rule SD is out of scope
+        s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, rule1="SD")
+        s.solve(True)
+
+
+def test_lossy3k_full_solve_equals_reference_trace(gne):
+    z, inst = load_gold("lossy3k_s5")
+    s, p1, p2 = solve_gpu(gne, inst, "LV")
+    e, l = s.trace
+    assert (p1, p2) == (3336, 12128)
+    assert np.array_equal(e, z["LV_e"]) and np.array_equal(l, z["LV_l"])
+    assert s.objective == float(z["LV_objective"])
+    s.close()
+
+
+@pytest.mark.parametrize("rule,K", [("LV", 400), ("QS", 400)])
+def test_c2_prefix_window_equals_oracle(gne, rule, K):
+    """configs[1]: 100k nodes / 2M arcs (lossy).  First K pivots of Phase I from the initial basis:
+    same (entering, leaving) sequence as the oracle, same flows, same potentials."""
+    g = gne.generate_instance(100_000, 2_000_000, 21, "lossy")
+    inst = Instance(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"])
+    s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, rule1=rule)
+    s.solve(True, K)
+    o = Oracle(inst, RULES[rule])
+    o.solve(True, K)
+    assert np.array_equal(s.trace[0], o.trace[0]) and np.array_equal(s.trace[1], o.trace[1])
+    assert len(s.trace[0]) == K
+    assert np.array_equal(s.flows(), o.flows())
+    assert np.array_equal(s.potentials(), o.potentials())
+    assert s.objective == o.objective
+    fs, fo = s.forest(), o.forest()
+    for key in ("pred", "predArc", "depth", "thread"):
+        assert np.array_equal(fs[key], fo[key])
+    s.close(); o.close()
+
+
+def test_c3_full_size_pricing_pass_equals_oracle(gne):
+    """configs[2] size: 1M nodes / 20M arcs.  One Dantzig pass at the initial Phase-I state and after
+    200 pivots, against the oracle's scalar pass over the same 20M-arc structure-of-arrays."""
+    g = gne.generate_instance(1_000_000, 20_000_000, 31, "lossy")
+    inst = Instance(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"])
+    s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, rule1="LV")
+    o = Oracle(inst, RULES["LV"])
+    for K in (1, 200):
+        s.solve(True, K)
+        o.solve(True, K)
+        assert np.array_equal(s.trace[0], o.trace[0]) and np.array_equal(s.trace[1], o.trace[1])
+        pi = o.compute_potentials()
+        nb = o.nonbasic_soa()
+        dev = s.device()
+        # the device's mirror of setNBarc equals the oracle's list, record for record
+        rt, rh, rcst, rm, rs = dev.nb_read(0, inst.m)
+        assert np.array_equal(rt, nb["tail"]) and np.array_equal(rh, nb["head"]) and np.array_equal(rs, nb["state"])
+        assert np.array_equal(rcst, nb["cost"]) and np.array_equal(rm, nb["mult"])
+    s.close(); o.close()

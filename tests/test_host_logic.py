@@ -1,0 +1,137 @@
+"""Host-side logic of the product, checked on CPU (no GPU needed): the C ABI surface, the basis
+forest engine against the oracle's forest, the shard-record merge, the instance generator."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle_util import RULES, Instance, Oracle, oracle_lib, dp, ip, lp, bp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def gne():
+    import __graft_entry__ as ge
+    ge.build()
+    import genneteq_b200
+    return genneteq_b200
+
+
+def test_library_exports_every_declared_symbol(gne):
+    hdr = open(os.path.join(ROOT, "include", "genneteq_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gne_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"gne_status"}
+    assert len(declared) >= 45
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", gne.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (gne_[a-z0-9_]+)", nm))
+    assert declared <= exported, sorted(declared - exported)
+    assert declared == set(gne.SIGNATURES), sorted(declared ^ set(gne.SIGNATURES))
+    assert b"sm_100a" in gne.lib.gne_version()
+
+
+def test_no_cpu_fallback_without_a_device(gne):
+    if gne.cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(gne.GneError) as ei:
+        gne.Device(10, 100)
+    assert "no CPU fallback" in str(ei.value)
+    inst = Instance.load(os.path.join(GOLD, "c1_wide_s7_instance.npz"))
+    with pytest.raises(gne.GneError):
+        gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply)
+
+
+def test_product_does_not_link_or_name_the_oracle(gne):
+    src = os.path.join(ROOT, "genneteq_b200")
+    for dirpath, _, files in os.walk(src):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "gne_oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("the oracle's", ""), f
+    ldd = subprocess.check_output(["ldd", gne.LIB_PATH], text=True)
+    assert "oracle" not in ldd
+
+
+@pytest.mark.parametrize("name,rule,K", [("c1_wide_s7", "LV", None), ("c1_wide_s7", "QS", 700), ("s_pow2_s5", "CL", None),
+                                         ("s_lossy_s4", "FV", None), ("lossy3k_s5", "LV", 6000)])
+def test_forest_engine_matches_oracle_forest(gne, name, rule, K):
+    """Replay the reference's pivot trace through the product's forest engine: the thread, pred,
+    predArc and depth arrays must equal the oracle's after the same exchanges."""
+    from test_oracle_pinned import load
+    z, inst = load(name)
+    e = z[rule + "_e"]; l = z[rule + "_l"]
+    p1 = int(z[rule + "_p"][0])
+    K = p1 if K is None else min(K, p1)
+    o = Oracle(inst, RULES[rule])
+    o.solve(True, K)
+    fo = o.forest()
+    fp = gne.forest_replay(inst.n, inst.tail, inst.head, inst.supply, e[:K], l[:K])
+    for key in ("pred", "predArc", "depth", "thread"):
+        assert np.array_equal(fo[key], fp[key]), key
+    # tree ids differ (stable slots vs renumbered ids) but must induce the same partition
+    pairs = set(zip(fo["tree"].tolist(), fp["tree"].tolist()))
+    assert len(pairs) == len(set(fo["tree"].tolist())) == len(set(fp["tree"].tolist()))
+    o.close()
+
+
+def test_merge_lv_shards_equals_sequential_rule(gne):
+    """Per-shard (max, in-band candidates) records merged by gne_merge_lv_shards give the same
+    largestViolation and offending list as the sequential band rule over the whole list."""
+    lib = oracle_lib()
+    inst = Instance.load(os.path.join(GOLD, "c1_wide_s7_instance.npz"))
+    band = 4.0e-13
+    for K in (0, 5, 300, 1500):
+        o = Oracle(inst, RULES["LV"])
+        o.solve(True, K)
+        pi = o.compute_potentials()
+        nb = o.nonbasic_soa()
+        N = len(nb["order"])
+        lst = np.zeros(N, np.int64); L = C.c_double(0); anyv = C.c_int(0)
+        k = lib.orc_price_lv(C.c_long(N), ip(nb["tail"]), ip(nb["head"]), dp(nb["cost"]), dp(nb["mult"]), bp(nb["state"]),
+                             dp(pi), lp(lst), C.c_long(N), C.byref(L), C.byref(anyv))
+        allpos = np.zeros(N, np.int64); allv = np.zeros(N)
+        cnt = lib.orc_price_violators(C.c_long(N), ip(nb["tail"]), ip(nb["head"]), dp(nb["cost"]), dp(nb["mult"]),
+                                      bp(nb["state"]), dp(pi), C.c_double(0.0), lp(allpos), dp(allv), C.c_long(N))
+        allpos = allpos[:cnt]; allv = allv[:cnt]
+        for R in (1, 2, 3, 8):
+            per = ((N + R - 1) // R + 2047) // 2048 * 2048
+            stride = 64
+            maxima = np.full(R, -1.0); anys = np.zeros(R, np.int32); counts = np.zeros(R, np.int64)
+            lp_ = np.zeros(R * stride, np.int64); lv_ = np.zeros(R * stride)
+            for r in range(R):
+                sel = (allpos >= r * per) & (allpos < (r + 1) * per)
+                if sel.any():
+                    anys[r] = 1
+                    maxima[r] = allv[sel].max()
+                    keep = sel & (allv >= maxima[r] - band)
+                    c = int(keep.sum())
+                    counts[r] = c if c <= stride else -1
+                    lp_[r * stride: r * stride + min(c, stride)] = allpos[keep][:stride]
+                    lv_[r * stride: r * stride + min(c, stride)] = allv[keep][:stride]
+            res = gne.merge_lv_shards(maxima, anys, counts, lp_, lv_, stride)
+            assert res["any"] == bool(anyv.value)
+            if not res["need_fallback"]:
+                assert res["largest"] == L.value
+                assert np.array_equal(res["list"], lst[:k])
+        o.close()
+
+
+def test_generator_is_deterministic_sorted_and_connected(gne):
+    a = gne.generate_instance(500, 6000, 99, "lossy")
+    b = gne.generate_instance(500, 6000, 99, "lossy")
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    key = a["tail"].astype(np.int64) * 500 + a["head"]
+    assert np.all(np.diff(key) > 0)                      # sorted by (tail, head), no duplicates
+    assert np.all(a["tail"] != a["head"])
+    ring = set(zip(range(500), [(i + 1) % 500 for i in range(500)]))
+    assert ring <= set(zip(a["tail"].tolist(), a["head"].tolist()))
+    assert a["mult"].min() >= 0.70 and a["mult"].max() <= 0.99
+    assert np.all(np.round(a["cost"] * 1e6) / 1e6 == a["cost"])
+    c = gne.generate_instance(500, 6000, 100, "lossy")
+    assert not np.array_equal(a["head"], c["head"])
