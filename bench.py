@@ -1,0 +1,338 @@
+#!/usr/bin/env python3
+"""Benchmark of the GenNetEq pricing / relabel hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3-lv|c2-lv|c2-qs|c1-lv]
+
+A step is one simplex iteration of the hot path: relabel the potentials the last pivot made dirty,
+price every nonbasic arc, pick the entering arc, pivot.  The default workload is BASELINE.json's
+configs[2] (the one its target is quoted on): 1M nodes / 20M arcs, `lossy` gains, Dantzig rule
+(reference rule LV), Phase I from the initial basis; for N > 1 the nonbasic list is sharded by
+contiguous position range across the N GPUs with an NCCL exchange of the per-shard record
+(fixed total work: "scaling": "strong").
+
+  value  arcs priced per second with everything resident in HBM: K device steps (potential
+         finalize + pricing pass + reduction [+ NCCL exchange]) timed with CUDA events on the
+         launching stream, max over ranks.  The pass streams 533 MB > 126 MB of L2.
+  e2e    the same metric through the public C ABI (gne_solver_solve) over K real pivots after W
+         warm-up pivots: host basis-forest work, the host->device copy of each step's dirty
+         potentials / set updates and the device->host read of the pricing result are all inside
+         the timed region.
+  roofline  the tile kernel k_price_lv_tiles alone: (25 B x arcs + 8 B x nodes) / its CUDA-event time
+         against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the unmodified reference (oracle/_ref, built from /root/reference by oracle/Makefile)
+         timed on this box's host cores on a bounded number of pivots of the same workload.
+
+`--impl reference` times the reference's own CPU solver on the same workload (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (nodes, arcs, seed, mode, rule, description)
+    "c3-lv": (1_000_000, 20_000_000, 31, "lossy", "LV", "configs[2]: 1M nodes / 20M arcs, lossy gains, seed 31, Dantzig rule (LV)"),
+    "c2-lv": (100_000, 2_000_000, 21, "lossy", "LV", "configs[1] size: 100k nodes / 2M arcs, lossy gains, seed 21, Dantzig rule (LV)"),
+    "c2-qs": (100_000, 2_000_000, 21, "lossy", "QS", "configs[1]: 100k nodes / 2M arcs, lossy gains, seed 21, block rule (QS)"),
+    "c5-lv": (200_000, 100_000_000, 51, "lossy", "LV", "configs[4]: 200k nodes / 100M arcs, lossy gains, seed 51, Dantzig rule (LV)"),
+    "c1-lv": (1_000, 10_000, 7, "wide", "LV", "configs[0] size: 1k nodes / 10k arcs (native generator), Dantzig rule (LV)"),
+}
+METRIC = "arcs priced/sec"
+UNIT = "arcs/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_instance(wl):
+    import genneteq_b200 as gne
+    n, m, seed, mode, rule, desc = WORKLOADS[wl]
+    return gne.generate_instance(n, m, seed, mode), rule, desc
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference, in a subprocess (Tree statics: one solver
+# per process).  Times whole simplex iterations (computePotentials + pricing + pivot) like e2e.
+# ------------------------------------------------------------------------------------------------
+_REF_CHILD = r"""
+import ctypes as C, json, sys, time, os
+import numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+req = json.load(open(sys.argv[1]))
+import genneteq_b200 as gne                      # only for the instance generator (no device work)
+from oracle_util import REF_SO, ORACLE_SO, dp, ip, oracle_lib, RULES
+g = gne.generate_instance(req["n"], req["m"], req["seed"], req["mode"])
+big_m = oracle_lib().orc_big_m(C.c_long(req["m"]), dp(g["cost"]), dp(g["ub"]))
+kind = "reference" if os.path.exists(REF_SO) else "port"
+if kind == "reference":
+    ref = C.CDLL(REF_SO)
+    ref.ref_solve.restype = C.c_long
+    t0 = time.time()
+    ref.ref_init_sparse(req["n"], C.c_long(req["m"]), ip(g["tail"]), ip(g["head"]), dp(g["ub"]), dp(g["cost"]), dp(g["mult"]),
+                        dp(g["supply"]), C.c_double(big_m))
+    init_s = time.time() - t0
+    ref.ref_set_rules(RULES[req["rule"]], RULES[req["rule"]])
+    fin = C.c_int(0)
+    def run(w, k):
+        ref.ref_set_window(C.c_long(w))
+        ref.ref_solve(1, C.c_long(w + k), C.byref(fin))
+        t0 = np.zeros(5); t1 = np.zeros(5)
+        ref.ref_get_window_timers(dp(t0)); ref.ref_get_timers(dp(t1))
+        return t1 - t0
+else:
+    lib = oracle_lib()
+    t0 = time.time()
+    h = C.c_void_p(lib.orc_create(req["n"], C.c_long(req["m"]), ip(g["tail"]), ip(g["head"]), dp(g["ub"]), dp(g["cost"]),
+                                  dp(g["mult"]), dp(g["supply"]), C.c_double(big_m)))
+    init_s = time.time() - t0
+    lib.orc_set_rules(h, RULES[req["rule"]], RULES[req["rule"]])
+    fin = C.c_int(0)
+    def run(w, k):
+        lib.orc_set_window(h, C.c_long(w))
+        lib.orc_solve(h, 1, C.c_long(w + k), C.byref(fin))
+        t0 = np.zeros(5); t1 = np.zeros(5)
+        lib.orc_get_window_timers(h, dp(t0)); lib.orc_get_timers(h, dp(t1))
+        return t1 - t0
+# One solve() call; the window starts after `warmup` pivots.  The per-stage timers cover
+# computePotentials + pricing + pivot of every iteration (the whole loop body of genneteq.cpp:82-106).
+# The sample is sized from a per-arc estimate (~55 ns per arc priced once the arc objects no longer fit in
+# cache) so that the run stays within the time budget; the window is pivots [warmup, warmup + steps).
+per = 55e-9 * req["m"] + 1.0e-7 * req["n"]
+steps, warmup = req["steps"], req["warmup"]
+if per * (steps + warmup) > req["budget_s"]:
+    steps = max(3, int(req["budget_s"] / per) - warmup)
+    if steps < 3: steps, warmup = 3, 1
+tm = run(warmup, steps)
+loop_s = tm[0] + tm[1] + tm[2]
+out = dict(kind=kind, steps=steps, loop_s=loop_s, pricing_s=tm[0], potentials_s=tm[1], pivot_s=tm[2], arcs_priced=tm[4],
+           init_s=init_s, warmup=warmup)
+json.dump(out, open(req["out"], "w"))
+"""
+
+
+def run_reference_sample(wl, steps, warmup, budget_s):
+    n, m, seed, mode, rule, desc = WORKLOADS[wl]
+    d = tempfile.mkdtemp(prefix="gne_bench_")
+    req = dict(n=n, m=m, seed=seed, mode=mode, rule=rule, steps=steps, warmup=warmup, budget_s=budget_s,
+               out=os.path.join(d, "out.json"))
+    rp = os.path.join(d, "req.json")
+    json.dump(req, open(rp, "w"))
+    code = _REF_CHILD % dict(root=ROOT)
+    subprocess.check_call([sys.executable, "-c", code, rp], stdout=subprocess.DEVNULL)
+    return json.load(open(req["out"]))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n, m, seed, mode, rule, desc = WORKLOADS[args.workload]
+    r = run_reference_sample(args.workload, args.steps, max(args.warmup, 1), budget_s=150.0)
+    value = r["arcs_priced"] / r["loop_s"]
+    cores = 1
+    sample = "%d simplex iterations after %d warm-up iterations, Phase I from the initial basis, single thread (the reference has none)" % (
+        r["steps"], r["warmup"])
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": r["steps"],
+        "warmup": r["warmup"], "ms_per_step": 1e3 * r["loop_s"] / r["steps"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule, "host_cores_present": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample,
+                         "pricing_only_arcs_per_s": r["arcs_priced"] / r["pricing_s"] if r["pricing_s"] > 0 else None},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pivots_per_s": r["steps"] / r["loop_s"],
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import torch
+    import genneteq_b200 as gne
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if gne.cuda_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device - genneteq_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, m, seed, mode, rule, desc = WORKLOADS[args.workload]
+    g, rule, desc = make_instance(args.workload)
+    s = gne.Solver(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"], device=local, rule1=rule,
+                   trace_cap=max(1024, args.steps + args.warmup + 16))
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = np.zeros(128, np.uint8)
+            gne._ck(gne.lib.gne_comm_unique_id(buf.ctypes.data_as(gne._u8p)), "gne_comm_unique_id")
+            uid = torch.from_numpy(buf)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        s.set_comm(uid.cpu().numpy(), rank, world)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- e2e: one gne_solver_solve call; W warm-up pivots, then exactly K pivots timed inside the
+    # library's loop (host clock, device synchronised at both edges of the window)
+    W = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    s.set_window(W, args.steps)
+    s.solve(True, W + args.steps)
+    barrier()
+    e2e_s, c0, c1 = s.window()
+    if e2e_s <= 0:
+        raise SystemExit("bench.py: the solve ended before the timed window completed")
+    pivots = int(c1["pivots"] - c0["pivots"])
+    arcs_e2e = c1["arcs_priced"] - c0["arcs_priced"]
+    dev = s.device()
+    N = m
+    # ---- device-resident steps: K x (finalize + pricing pass + reduction [+ exchange]), CUDA events
+    flush = (25 * N + 8 * n) < 200e6            # working set not larger than L2 => flush between steps
+    dev.bench_price_lv(max(args.warmup, 3), flush)
+    barrier()
+    ms_step, ms_tiles = dev.bench_price_lv(args.steps, flush)
+    barrier()
+    clocks = sampler.stop()
+    launches = int(s.counters()["launches"] - c0["launches"])     # e2e window + device steps (warm-up excluded from neither)
+    if dist is not None:
+        t = torch.tensor([e2e_s, float(ms_step.sum()), float(ms_tiles.mean())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s, step_sum_ms, tiles_ms = (float(x) for x in t.cpu())
+    else:
+        step_sum_ms, tiles_ms = float(ms_step.sum()), float(ms_tiles.mean())
+    if rank != 0:
+        return 0
+    value = N * args.steps / (step_sum_ms * 1e-3)
+    peak, peak_src = peaks()
+    shard_arcs = N / world
+    alg_bytes = 25.0 * shard_arcs + 8.0 * n
+    achieved = alg_bytes / (tiles_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": step_sum_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule,
+                   "l2": ("L2 flushed between timed steps (320 MB write)" if flush else
+                          "inputs larger than L2 (%.0f MB streamed per pass per GPU)" % (alg_bytes / 1e6)),
+                   "sharding": "contiguous position ranges over %d GPU(s), NCCL all-gather of the per-shard record" % world},
+        "e2e": {"value": arcs_e2e / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(pivots, 1),
+                "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / max(pivots, 1),
+                "pivots_per_s": pivots / e2e_s, "ms_per_pivot": 1e3 * e2e_s / max(pivots, 1),
+                "host_split_s": {k: c1[k] - c0[k] for k in ("pricing_s", "potentials_s", "pivot_s", "trees_s", "flows_s")}},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_price_lv_tiles", "kernel_ms": tiles_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_reference_sample(args.workload, 12, 2, budget_s=25.0)
+            line["cpu_baseline"] = {
+                "value": r["arcs_priced"] / r["loop_s"], "unit": UNIT, "cores": 1, "kind": r["kind"],
+                "sample": "%d simplex iterations after %d warm-up iterations of the same workload, single thread "
+                          "(the reference has none; %d host cores present)" % (r["steps"], r["warmup"], os.cpu_count()),
+                "ms_per_pivot": 1e3 * r["loop_s"] / r["steps"],
+                "pricing_only_arcs_per_s": r["arcs_priced"] / r["pricing_s"] if r["pricing_s"] > 0 else None}
+        except Exception as ex:                      # the oracle always exists; report why it could not run
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: %r" % (ex,)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3-lv", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,7 +59,7 @@ SIGNATURES = {
     "gne_reduced_costs": (C.c_int, [_vp, C.c_int64, C.c_int64, _f64p]),
     "gne_dev_last_kernel_ms": (C.c_int, [_vp, _f32p]),
     "gne_dev_launch_count": (C.c_int64, [_vp]),
-    "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
+    "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
     "gne_comm_unique_id": (C.c_int, [_u8p]),
     "gne_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
     "gne_comm_destroy": (C.c_int, [_vp]),
@@ -81,6 +81,8 @@ SIGNATURES = {
     "gne_solver_get_forest": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "gne_solver_get_counters": (C.c_int, [_vp, _f64p]),
     "gne_solver_device": (_vp, [_vp]),
+    "gne_solver_set_window": (C.c_int, [_vp, C.c_int64, C.c_int64]),
+    "gne_solver_get_window": (C.c_int, [_vp, _f64p]),
     "gne_forest_replay": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, C.c_int64, _i32p, _i32p,
                                     _i32p, _i32p, _i32p, _i32p, _i32p]),
     "gne_merge_lv_shards": (C.c_int, [C.c_int, _f64p, C.POINTER(C.c_int), _i64p, _i64p, _f64p, C.c_int64,
@@ -240,10 +242,12 @@ class Device:
     def launch_count(self):
         return lib.gne_dev_launch_count(self.h)
 
-    def bench_price_lv(self, reps, flush_l2):
-        ms = np.zeros(reps, np.float32)
-        _ck(lib.gne_bench_price_lv(self.h, reps, 1 if flush_l2 else 0, _p(ms, _f32p)), "gne_bench_price_lv")
-        return ms
+    def bench_price_lv(self, reps, flush_l2, with_finalize=True):
+        """(ms per device step, ms of the tile kernel alone), CUDA events on the handle's stream."""
+        ms = np.zeros(reps, np.float32); mt = np.zeros(reps, np.float32)
+        _ck(lib.gne_bench_price_lv(self.h, reps, 1 if flush_l2 else 0, 1 if with_finalize else 0, _p(ms, _f32p),
+                                   _p(mt, _f32p)), "gne_bench_price_lv")
+        return ms, mt
 
 
 class _BorrowedDevice(Device):
@@ -345,6 +349,15 @@ class Solver:
         a = np.zeros(12)
         lib.gne_solver_get_counters(self.h, _p(a, _f64p))
         return dict(zip(self.COUNTERS, a.tolist()))
+
+    def set_window(self, start_pivot, num_pivots):
+        lib.gne_solver_set_window(self.h, start_pivot, num_pivots)
+
+    def window(self):
+        """(seconds, counters at the window's start, counters at its end) of the last windowed solve."""
+        a = np.zeros(25)
+        lib.gne_solver_get_window(self.h, _p(a, _f64p))
+        return a[0], dict(zip(self.COUNTERS, a[1:13].tolist())), dict(zip(self.COUNTERS, a[13:25].tolist()))
 
     def device(self):
         h = lib.gne_solver_device(self.h)

@@ -87,7 +87,7 @@ bool nccl_load()
 struct gne_dev {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     int n = 0;
     int64_t cap = 0, lo = 0, hi = 0, N = 0;        // global capacity, shard [lo, hi), global count
     int64_t localCap = 0;                          // allocated shard length (multiple of TILE)
@@ -233,6 +233,8 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     for (void *p : host) if (p) cudaFreeHost(p);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->ev2) cudaEventDestroy(d->ev2);
+    if (d->ev3) cudaEventDestroy(d->ev3);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
     return GNE_OK;
@@ -309,8 +311,14 @@ extern "C" int gne_nb_write(gne_dev *d, int64_t pos, int32_t tail, int32_t head,
     if (pos < d->lo || pos >= d->hi) return GNE_OK;     // another rank's position
     CK(cudaSetDevice(d->device));
     NbWriteOps &ops = pending_of(d);
-    if (ops.n == 8) { int rc = flush_writes(d, ops); if (rc) return rc; }
-    const int i = ops.n++;
+    // the batch is applied by concurrent threads: a later write to the same position replaces
+    // the queued one instead of racing with it
+    int i = -1;
+    for (int k = 0; k < ops.n; ++k) if (ops.local[k] == pos - d->lo) i = k;
+    if (i < 0) {
+        if (ops.n == 8) { int rc = flush_writes(d, ops); if (rc) return rc; }
+        i = ops.n++;
+    }
     ops.local[i] = pos - d->lo; ops.tail[i] = tail; ops.head[i] = head; ops.cost[i] = cost; ops.mult[i] = mult; ops.state[i] = state;
     return GNE_OK;
 }
@@ -656,7 +664,9 @@ extern "C" int gne_price_qs(gne_dev *d, int64_t cursor, int64_t want, int64_t *b
 // ------------------------------------------------------------------------------------------
 // bench helper
 // ------------------------------------------------------------------------------------------
-extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, float *msPerPass)
+static int launch_shard_exchange(gne_dev *d);
+
+extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles)
 {
     CK(cudaSetDevice(d->device));
     int rc = gne_dev_flush(d); if (rc) return rc;
@@ -664,11 +674,24 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, float *msPe
         d->flushLen = (int64_t) 40 * 1024 * 1024;       // 320 MB of doubles > 126 MB L2
         CK(cudaMalloc(&d->flushBuf, 8 * (size_t) d->flushLen));
     }
+    if (!d->ev2) { CK(cudaEventCreate(&d->ev2)); CK(cudaEventCreate(&d->ev3)); }
+    const int G = tiles_for(d);
+    NbView nb = view_of(d);
     for (int i = 0; i < reps; ++i) {
         if (flushL2) { k_flush_l2<<<148 * 8, 256, 0, d->stream>>>(d->flushBuf, d->flushLen); ++d->launches; }
-        rc = price_lv_local(d); if (rc) return rc;
+        CK(cudaEventRecord(d->ev2, d->stream));
+        if (withFinalize) { k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi); ++d->launches; }
+        CK(cudaEventRecord(d->ev0, d->stream));
+        if (G > 0) { k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); ++d->launches; }
+        CK(cudaEventRecord(d->ev1, d->stream));
+        k_price_lv_finish<<<1, TILE_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->lvRes);
+        ++d->launches;
+        if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
+        CK(cudaEventRecord(d->ev3, d->stream));
+        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(d->stream));
-        CK(cudaEventElapsedTime(&msPerPass[i], d->ev0, d->ev1));
+        CK(cudaEventElapsedTime(&msStep[i], d->ev2, d->ev3));
+        CK(cudaEventElapsedTime(&msTiles[i], d->ev0, d->ev1));
     }
     return GNE_OK;
 }
@@ -727,14 +750,21 @@ extern "C" int gne_comm_destroy(gne_dev *d)
     return GNE_OK;
 }
 
-int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &list, int *any)
+static int launch_shard_exchange(gne_dev *d)
 {
-    // price_lv_local has been launched and synchronised by the caller; pack, all-gather, merge
+    // pack this shard's record, all-gather over NCCL (NVLink), copy the gathered records to pinned host
     k_pack_record<<<1, 64, 0, d->stream>>>(d->lvRes, (ShardRecord *) d->gatherSend);
     ++d->launches;
     int r = g_nccl.AllGather(d->gatherSend, d->gatherRecv, sizeof(ShardRecord), /*ncclChar*/ 0, d->comm, d->stream);
     if (r != 0) { gne_set_error("ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
     CK(cudaMemcpyAsync(d->gatherHost, d->gatherRecv, sizeof(ShardRecord) * (size_t) d->nranks, cudaMemcpyDeviceToHost, d->stream));
+    return GNE_OK;
+}
+
+int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &list, int *any)
+{
+    // price_lv_local has been launched by the caller; exchange, then the same merge on every rank
+    int rcx = launch_shard_exchange(d); if (rcx) return rcx;
     CK(cudaStreamSynchronize(d->stream));
     d->d2hBytes += sizeof(ShardRecord) * (int64_t) d->nranks;
     const ShardRecord *rec = (const ShardRecord *) d->gatherHost;

@@ -698,7 +698,10 @@ int GenNetEq::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *fi
     const double t0 = wallNow();
     computeFlows(0);
     int64_t budget = maxPivots;
+    callPivots = 0;
     while (!isOptimal && !isUnbounded) {
+        if (winStart >= 0 && callPivots == winStart && winT0 == 0.0) { gne_dev_sync(dev); getCounters(winC0); winT0 = wallNow(); }
+        if (winStart >= 0 && callPivots == winStart + winLen && winT1 == 0.0) { gne_dev_sync(dev); winT1 = wallNow(); getCounters(winC1); }
         if (maxPivots >= 0 && budget == 0) { *finished = 0; break; }
         if ((loopIter % 1000) == 0) computeFlows(2);
         const double a = wallNow();
@@ -714,7 +717,7 @@ int GenNetEq::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *fi
                 if (traceLen < traceCap) { traceE[traceLen] = eVar; traceL[traceLen] = lVar; }
                 ++traceLen;
             }
-            ++loopIter; ++pivots;
+            ++loopIter; ++pivots; ++callPivots;
             if (presolve) ++phaseIiters; else ++phaseIIiters;
             if (budget > 0) --budget;
         }
@@ -741,6 +744,12 @@ int GenNetEq::getPotentials(double *out)
 }
 
 void GenNetEq::getStates(int32_t *out) const { for (int64_t i = 0; i < M; ++i) out[i] = setLoc[i]; }
+
+void GenNetEq::getWindow(double *o) const
+{
+    o[0] = (winT1 > 0.0 && winT0 > 0.0) ? winT1 - winT0 : -1.0;
+    for (int i = 0; i < 12; ++i) { o[1 + i] = winC0[i]; o[13 + i] = winC1[i]; }
+}
 
 void GenNetEq::getCounters(double *o) const
 {

@@ -82,6 +82,10 @@ class GenNetEq {
     void getStates(int32_t *out) const;
     const Forest &getForest() const { return forest; }
     void getCounters(double *out12) const;
+    // wall-clock window over pivots [start, start + len) of the next solve() call, taken inside the loop
+    // with the device synchronised at both edges; out = {seconds, 12 counters at start, 12 at end}
+    void setWindow(int64_t start, int64_t len) { winStart = start; winLen = len; winT0 = winT1 = 0.0; }
+    void getWindow(double *out25) const;
     gne_dev *device() { return dev; }
 
   protected:
@@ -142,6 +146,8 @@ class GenNetEq {
     double secsPricing = 0, secsPotentials = 0, secsPivot = 0, secsTotal = 0, secsTrees = 0, secsFlows = 0;
     double arcsPriced = 0, kernelMs = 0;
     int64_t pivots = 0;
+    int64_t winStart = -1, winLen = 0, callPivots = 0;
+    double winT0 = 0.0, winT1 = 0.0, winC0[12] = { 0 }, winC1[12] = { 0 };
 
     // ---- functions, named as in genneteq.h:153-271
     void initializeStats(bool usePresolve);

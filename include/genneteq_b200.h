@@ -114,10 +114,12 @@ int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc);
 int gne_dev_last_kernel_ms(gne_dev *d, float *ms);
 /* number of kernels this handle has launched since creation                                   */
 int64_t gne_dev_launch_count(gne_dev *d);
-/* replay timing helper for bench.py: runs `reps` LV pricing passes back to back on the resident
- * state, each bracketed by CUDA events on the handle's stream; flushL2 != 0 writes a >L2 scratch
- * buffer between passes (outside the events).  Writes per-pass milliseconds.                  */
-int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, float *msPerPass);
+/* replay timing helper for bench.py: runs `reps` device steps on the resident state — potential
+ * finalize (if withFinalize), the LV pricing pass, its reduction and, when sharded, the NCCL
+ * exchange — each step bracketed by CUDA events on the handle's stream (msStep) with a second
+ * event pair around the tile kernel alone (msTiles).  flushL2 != 0 writes a >L2 scratch buffer
+ * between steps, outside the events.                                                          */
+int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles);
 
 /* --- multi-GPU exchange (one process per GPU; NCCL over NVLink) --- */
 /* 128-byte opaque id made on rank 0 and broadcast by the caller (torch.distributed)           */
@@ -159,6 +161,11 @@ int gne_solver_get_forest(gne_solver *s, int32_t *tree, int32_t *pred, int32_t *
  *           [8] kernel launches  [9] pivots  [10] tree surgery s  [11] flow/ratio s           */
 int gne_solver_get_counters(const gne_solver *s, double *out12);
 gne_dev *gne_solver_device(gne_solver *s);
+/* wall-clock window over pivots [startPivot, startPivot + numPivots) of the next gne_solver_solve
+ * call, taken inside the loop with the device synchronised at both edges (bench.py's e2e):
+ * out25 = { seconds (-1 if the window was not completed), the 12 counters at its start, at its end } */
+int gne_solver_set_window(gne_solver *s, int64_t startPivot, int64_t numPivots);
+int gne_solver_get_window(const gne_solver *s, double *out25);
 
 /* Host-only replay of basis exchanges (no device work, usable without a GPU): applies the given
  * (entering, leaving) varIndex pairs to a fresh forest and returns its thread/pred arrays —

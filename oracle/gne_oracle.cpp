@@ -90,6 +90,7 @@ struct OrcSolver {
     // ---- trace / timers
     int *traceE, *traceL; long traceCap, traceLen;
     double secsPricing, secsPotentials, secsPivot, secsTotal; long arcsPriced;
+    long windowStart; double winTimers[5];
 
     OrcSolver() : lastViolation(100000), baselineViolation(100000) {}      // genneteq.cpp:20-24
 
@@ -851,7 +852,9 @@ struct OrcSolver {
         double t0 = wallNow();
         computeFlows(0);
         long budget = maxPivots;
+        long callPivots = 0;
         while (!isOptimal && !isUnbounded && status == 0) {
+            if (callPivots == windowStart) { winTimers[0] = secsPricing; winTimers[1] = secsPotentials; winTimers[2] = secsPivot; winTimers[3] = 0.0; winTimers[4] = (double) arcsPriced; }
             if (maxPivots >= 0 && budget == 0) { *finished = 0; break; }
             if ((loopIter % 1000) == 0) computeFlows(2);
             double a = wallNow();
@@ -868,7 +871,7 @@ struct OrcSolver {
                     if (traceLen < traceCap) { traceE[traceLen] = eVar; traceL[traceLen] = lVar; }
                     ++traceLen;
                 }
-                ++loopIter;
+                ++loopIter; ++callPivots;
                 if (presolve) ++phaseIiters; else ++phaseIIiters;
                 if (budget > 0) --budget;
             }
@@ -916,6 +919,7 @@ OrcSolver *orc_create(int n, long m, const int *tailIn, const int *headIn, const
     s->rng = orc_drand48_initial_state();
     s->ruleI = R_LVW; s->ruleII = R_LVW;                    // main.cpp:72-73
     s->traceE = s->traceL = NULL; s->traceCap = 0; s->traceLen = 0;
+    s->windowStart = -1; for (int k = 0; k < 5; ++k) s->winTimers[k] = 0.0;
     s->secsPricing = s->secsPotentials = s->secsPivot = s->secsTotal = 0.0; s->arcsPriced = 0;
     s->isInfeasible = false; s->isOptimal = false; s->isUnbounded = false; s->presolve = true;
     s->cyclingDetected = false; s->eVar = s->lVar = -1; s->delta = 0.0; s->flowCost = 0.0;
@@ -980,6 +984,8 @@ void orc_get_timers(const OrcSolver *s, double *o)
 {
     o[0] = s->secsPricing; o[1] = s->secsPotentials; o[2] = s->secsPivot; o[3] = s->secsTotal; o[4] = (double) s->arcsPriced;
 }
+void orc_set_window(OrcSolver *s, long start) { s->windowStart = start; }
+void orc_get_window_timers(const OrcSolver *s, double *o) { for (int k = 0; k < 5; ++k) o[k] = s->winTimers[k]; }
 void orc_get_forest(const OrcSolver *s, int *treeId, int *pred, int *predArc, int *depth, int *thread)
 {
     for (int i = 0; i < s->n; ++i) {

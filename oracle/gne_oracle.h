@@ -38,6 +38,9 @@ void orc_get_states(const OrcSolver *s, int *out);            /* var_loc: 0 B, 1
 void orc_get_nonbasic_order(const OrcSolver *s, int *out);    /* setNBarc[pos] -> varIndex */
 void orc_get_costs(const OrcSolver *s, double *out);
 void orc_get_timers(const OrcSolver *s, double *out5);        /* pricing, potentials, pivot, total s; arcs priced */
+/* the timers as they stood when pivot `start` of the next orc_solve call began (bench windows) */
+void orc_set_window(OrcSolver *s, long start);
+void orc_get_window_timers(const OrcSolver *s, double *out5);
 /* forest snapshot for checking a host tree engine: per node tree id, pred, predArc, depth, thread */
 void orc_get_forest(const OrcSolver *s, int *treeId, int *pred, int *predArc, int *depth, int *thread);
 /* recompute potentials from the current basis (gnePotential.cpp:28-61) */

@@ -125,7 +125,9 @@ class RefDriver : public GenNetEq
         double t0 = wallNow();
         computeFlows();
         long budget = maxPivots;
+        long callPivots = 0;
         while ((!isOptimal) && (!isUnbounded)) {
+            if (callPivots == windowStart) { winTimers[0] = secsPricing; winTimers[1] = secsPotentials; winTimers[2] = secsPivot; winTimers[3] = 0.0; winTimers[4] = (double) arcsPriced; }
             if (maxPivots >= 0 && budget == 0) { *finished = 0; break; }
             if ((loopIter % 1000) == 0) {
                 computeFlows(2);
@@ -152,6 +154,7 @@ class RefDriver : public GenNetEq
                 }
                 ++loopIter;
                 ++pivotsDone;
+                ++callPivots;
                 presolve ? ++phaseIiters : ++phaseIIiters;
                 if (budget > 0) --budget;
             }
@@ -204,6 +207,8 @@ class RefDriver : public GenNetEq
     void getStates(int *out) const { for (size_t i = 0; i < vars.size(); ++i) out[i] = (int) vars[i]->setLoc; }
     void getNonbasicOrder(int *out) const { for (size_t i = 0; i < setNBarc.size(); ++i) out[i] = setNBarc[i]->varIndex; }
 
+    long windowStart = -1;
+    double winTimers[5] = { 0, 0, 0, 0, 0 };
     int *traceE, *traceL;
     long traceCap, traceLen;
     FILE *traceFile;
@@ -266,6 +271,10 @@ void ref_get_timers(double *out5)
     out5[2] = g_solver->secsPivot;   out5[3] = g_solver->secsTotal;
     out5[4] = (double) g_solver->arcsPriced;
 }
+
+/* timers as they stood when pivot `start` of the next ref_solve call began */
+void ref_set_window(long start) { g_solver->windowStart = start; }
+void ref_get_window_timers(double *out5) { for (int i = 0; i < 5; ++i) out5[i] = g_solver->winTimers[i]; }
 
 int ref_num_nodes(void) { return g_solver->nNodes(); }
 long ref_num_vars(void) { return g_solver->nVars(); }
