@@ -60,6 +60,8 @@ SIGNATURES = {
     "gne_dev_last_kernel_ms": (C.c_int, [_vp, _f32p]),
     "gne_dev_launch_count": (C.c_int64, [_vp]),
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
+    "gne_bench_variants": (C.c_int, [_vp, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int)]),
+    "gne_bench_variant_name": (C.c_char_p, [C.c_int]),
     "gne_comm_unique_id": (C.c_int, [_u8p]),
     "gne_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
     "gne_comm_destroy": (C.c_int, [_vp]),
@@ -248,6 +250,12 @@ class Device:
         _ck(lib.gne_bench_price_lv(self.h, reps, 1 if flush_l2 else 0, 1 if with_finalize else 0, _p(ms, _f32p),
                                    _p(mt, _f32p)), "gne_bench_price_lv")
         return ms, mt
+
+
+    def bench_variants(self, reps=10):
+        ms = np.zeros(64, np.float32); nv = C.c_int(0)
+        _ck(lib.gne_bench_variants(self.h, reps, _p(ms, _f32p), 32, C.byref(nv)), "gne_bench_variants")
+        return [(lib.gne_bench_variant_name(i).decode(), float(ms[2 * i]), float(ms[2 * i + 1])) for i in range(nv.value)]
 
 
 class _BorrowedDevice(Device):

@@ -1,6 +1,7 @@
 // genneteq_b200 — layer 1 of the C ABI: device-resident state and kernel launches.
 // See include/genneteq_b200.h for the contract of every entry point.
 #include "gne_kernels.cuh"
+#include "gne_variants.cuh"
 #include "gne_internal.h"
 #include "../../include/genneteq_b200.h"
 
@@ -498,7 +499,7 @@ static int price_lv_local(gne_dev *d)
         k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv);
         ++d->launches;
     }
-    k_price_lv_finish<<<1, TILE_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->lvRes);
+    k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->lvRes);
     ++d->launches;
     CK(cudaEventRecord(d->ev1, d->stream));
     CK(cudaGetLastError());
@@ -666,6 +667,59 @@ extern "C" int gne_price_qs(gne_dev *d, int64_t cursor, int64_t want, int64_t *b
 // ------------------------------------------------------------------------------------------
 static int launch_shard_exchange(gne_dev *d);
 
+// tuning harness: the LV tile kernel and its experimental variants, each timed `reps` times
+static const char *g_variantNames[] = {
+    "production k_price_lv_tiles", "tiles<2 chunks, minb 5>", "tiles<2,6>", "tiles<2,8>", "tiles<1,8>", "tiles<4,4>",
+    "tiles<2,6,no_allocate>", "tiles<1,8,no_allocate>", "persistent<minb 6> 148x6", "persistent<8> 148x8",
+    "persistent<8,no_allocate> 148x8", "strided<4,8>", "strided<8,6>" };
+extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants)
+{
+    CK(cudaSetDevice(d->device));
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    const int NV = (int) (sizeof(g_variantNames) / sizeof(g_variantNames[0]));
+    *nVariants = NV;
+    if (maxVariants < NV) return GNE_ERR_CAPACITY;
+    NbView nb = view_of(d);
+    const int64_t len = std::min(d->N, d->hi) - d->lo;
+    const int G2 = (int) ((len + 2047) / 2048), G1 = (int) ((len + 1023) / 1024), G4 = (int) ((len + 4095) / 4096);
+    rc = ensure_out(d, G1 + 4096); if (rc) return rc;
+    double *o = d->outViol;
+    for (int v = 0; v < NV; ++v) {
+        float best = 1e30f, sum = 0.f;
+        for (int r = 0; r < reps + 2; ++r) {
+            CK(cudaEventRecord(d->ev0, d->stream));
+            switch (v) {
+              case 0: k_price_lv_tiles<<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); break;
+              case 1: k_var_tiles<2, 5, false><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+              case 2: k_var_tiles<2, 6, false><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+              case 3: k_var_tiles<2, 8, false><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+              case 4: k_var_tiles<1, 8, false><<<G1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+              case 5: k_var_tiles<4, 4, false><<<G4, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+              case 6: k_var_tiles<2, 6, true><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+              case 7: k_var_tiles<1, 8, true><<<G1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+              case 8: k_var_persistent<6, false><<<148 * 6, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o, G1); break;
+              case 9: k_var_persistent<8, false><<<148 * 8, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o, G1); break;
+              case 10: k_var_persistent<8, true><<<148 * 8, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o, G1); break;
+              case 11: k_var_strided<4, 8><<<G1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+              case 12: k_var_strided<8, 6><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+            }
+            CK(cudaEventRecord(d->ev1, d->stream));
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(d->stream));
+            float ms; CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
+            if (r >= 2) { sum += ms; best = std::min(best, ms); }
+            ++d->launches;
+        }
+        msOut[2 * v] = sum / reps; msOut[2 * v + 1] = best;
+    }
+    return GNE_OK;
+}
+extern "C" const char *gne_bench_variant_name(int i)
+{
+    const int NV = (int) (sizeof(g_variantNames) / sizeof(g_variantNames[0]));
+    return (i >= 0 && i < NV) ? g_variantNames[i] : "";
+}
+
 extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles)
 {
     CK(cudaSetDevice(d->device));
@@ -684,7 +738,7 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
         CK(cudaEventRecord(d->ev0, d->stream));
         if (G > 0) { k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); ++d->launches; }
         CK(cudaEventRecord(d->ev1, d->stream));
-        k_price_lv_finish<<<1, TILE_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->lvRes);
+        k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->lvRes);
         ++d->launches;
         if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
         CK(cudaEventRecord(d->ev3, d->stream));

@@ -200,51 +200,84 @@ struct LvResult {
     double viol[LV_LIST_CAP];
 };
 
-// LV pass, stage 2 (one CTA): global maximum over tiles, then gather the candidates of the
-// tiles whose maximum reaches the band, in position order.
-__global__ void __launch_bounds__(TILE_THREADS)
+// LV pass, stage 2 (one CTA of 1024 threads): global maximum over the tile maxima, then the
+// candidates of the (few) tiles whose maximum reaches the band, gathered in position order.
+constexpr int FIN_THREADS = 1024;
+constexpr int FIN_QCAP = 1024;             // tiles within the band handled on the device
+
+__global__ void __launch_bounds__(FIN_THREADS)
 k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
 {
-    const int t = threadIdx.x;
-    Best b; b.v = -1.0; b.p = 0;
-    for (int g = t; g < G; g += TILE_THREADS) { double m = tiles.tileMax[g]; if (m > b.v) { b.v = m; b.p = g; } }
-    b = block_best(b);
-    const double M = b.v;
+    __shared__ double sMax[FIN_THREADS / 32];
+    __shared__ int sQ[FIN_QCAP];
+    __shared__ int sSorted[FIN_QCAP];
+    __shared__ int sScan[FIN_THREADS / 32];
+    __shared__ int sCount, sOvf;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) { sCount = 0; sOvf = 0; }
+    double m = -1.0;
+    for (int g = t; g < G; g += FIN_THREADS) m = fmax(m, tiles.tileMax[g]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) sMax[w] = m;
+    __syncthreads();
+    double M = sMax[0];
+#pragma unroll
+    for (int i = 1; i < FIN_THREADS / 32; ++i) M = fmax(M, sMax[i]);
     if (M <= 0.0) {
         if (t == 0) { res->maxViol = -1.0; res->any = 0; res->overflow = 0; res->count = 0; }
         return;
     }
     const double thr = __dsub_rn(M, LV_BAND);
-    const int per = (G + TILE_THREADS - 1) / TILE_THREADS;
-    const int g0 = min(G, t * per), g1 = min(G, g0 + per);
-    int mine = 0, ovf = 0;
-    for (int g = g0; g < g1; ++g) {
+    for (int g = t; g < G; g += FIN_THREADS) {
         if (tiles.tileMax[g] >= thr) {
-            const int c = tiles.tileCnt[g];
-            if (c > CAND_K) { ovf = 1; continue; }
-            for (int i = 0; i < c; ++i) mine += (tiles.candViol[(int64_t) g * CAND_K + i] >= thr);
+            const int s = atomicAdd(&sCount, 1);
+            if (s < FIN_QCAP) sQ[s] = g;
         }
     }
-    int total;
-    int off = block_excl_scan(mine, &total);
-    const int anyOvf = __syncthreads_or(ovf);
-    const bool tooMany = total > LV_LIST_CAP;
-    if (!anyOvf && !tooMany) {
-        for (int g = g0; g < g1; ++g) {
-            if (tiles.tileMax[g] >= thr) {
-                const int c = tiles.tileCnt[g];
-                for (int i = 0; i < c; ++i) {
-                    const double vv = tiles.candViol[(int64_t) g * CAND_K + i];
-                    if (vv >= thr) {
-                        res->pos[off] = lo + (int64_t) g * TILE + tiles.candOff[(int64_t) g * CAND_K + i];
-                        res->viol[off] = vv;
-                        ++off;
-                    }
-                }
+    __syncthreads();
+    const int q = sCount;
+    if (q > FIN_QCAP) {
+        if (t == 0) { res->maxViol = M; res->any = 1; res->overflow = 1; res->count = 0; }
+        return;
+    }
+    if (t < q) {                                       // rank sort: tile order == position order
+        const int mine = sQ[t];
+        int rank = 0;
+        for (int i = 0; i < q; ++i) rank += (sQ[i] < mine);
+        sSorted[rank] = mine;
+    }
+    __syncthreads();
+    int cnt = 0;
+    if (t < q) {
+        const int g = sSorted[t];
+        const int c = tiles.tileCnt[g];
+        if (c > CAND_K) atomicExch(&sOvf, 1);
+        else for (int i = 0; i < c; ++i) cnt += (tiles.candViol[(int64_t) g * CAND_K + i] >= thr);
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) sScan[w] = inc;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < FIN_THREADS / 32; ++i) { if (i < w) base += sScan[i]; total += sScan[i]; }
+    const bool bad = sOvf || total > LV_LIST_CAP;
+    if (!bad && t < q && cnt > 0) {
+        const int g = sSorted[t];
+        const int c = tiles.tileCnt[g];
+        int off = base + inc - cnt;
+        for (int i = 0; i < c; ++i) {
+            const double vv = tiles.candViol[(int64_t) g * CAND_K + i];
+            if (vv >= thr) {
+                res->pos[off] = lo + (int64_t) g * TILE + tiles.candOff[(int64_t) g * CAND_K + i];
+                res->viol[off] = vv;
+                ++off;
             }
         }
     }
-    if (t == 0) { res->maxViol = M; res->any = 1; res->overflow = (anyOvf || tooMany) ? 1 : 0; res->count = total; }
+    if (t == 0) { res->maxViol = M; res->any = 1; res->overflow = bad ? 1 : 0; res->count = total; }
 }
 
 // ------------------------------------------------------------------------------------------

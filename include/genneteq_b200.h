@@ -121,6 +121,11 @@ int64_t gne_dev_launch_count(gne_dev *d);
  * between steps, outside the events.                                                          */
 int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles);
 
+/* tuning harness: times the LV tile kernel and its experimental variants (msOut[2v] = mean ms,
+ * msOut[2v+1] = best ms over reps); gne_bench_variant_name(v) describes variant v.             */
+int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants);
+const char *gne_bench_variant_name(int i);
+
 /* --- multi-GPU exchange (one process per GPU; NCCL over NVLink) --- */
 /* 128-byte opaque id made on rank 0 and broadcast by the caller (torch.distributed)           */
 int gne_comm_unique_id(uint8_t id[128]);
