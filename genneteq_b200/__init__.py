@@ -49,6 +49,7 @@ SIGNATURES = {
     "gne_pot_update_nodes": (C.c_int, [_vp, C.c_int64, _i32p, _f64p, _f64p, _i32p]),
     "gne_pot_update_thetas": (C.c_int, [_vp, C.c_int64, _i32p, _f64p]),
     "gne_pot_finalize": (C.c_int, [_vp]),
+    "gne_pot_update_fused": (C.c_int, [_vp, C.c_int64, _i32p, _f64p, _f64p, _i32p, C.c_int64, _i32p, _f64p, C.c_int64, _i32p]),
     "gne_pot_set": (C.c_int, [_vp, C.c_int64, _i32p, _f64p]),
     "gne_pot_set_all": (C.c_int, [_vp, _f64p]),
     "gne_pot_get_all": (C.c_int, [_vp, _f64p]),
@@ -201,6 +202,14 @@ class Device:
     def pot_update_thetas(self, slot, theta):
         slot = _arr(slot, np.int32); theta = _arr(theta, np.float64)
         _ck(lib.gne_pot_update_thetas(self.h, len(slot), _p(slot, _i32p), _p(theta, _f64p)), "gne_pot_update_thetas")
+
+    def pot_update_fused(self, node, a0, a1, slot, tslot, theta, fnode=None):
+        node = _arr(node, np.int32); a0 = _arr(a0, np.float64); a1 = _arr(a1, np.float64); slot = _arr(slot, np.int32)
+        tslot = _arr(tslot, np.int32); theta = _arr(theta, np.float64)
+        nf = -1 if fnode is None else len(fnode)
+        fn = _arr(fnode if fnode is not None else [], np.int32)
+        _ck(lib.gne_pot_update_fused(self.h, len(node), _p(node, _i32p), _p(a0, _f64p), _p(a1, _f64p), _p(slot, _i32p),
+                                     len(tslot), _p(tslot, _i32p), _p(theta, _f64p), nf, _p(fn, _i32p)), "gne_pot_update_fused")
 
     def pot_finalize(self):
         _ck(lib.gne_pot_finalize(self.h), "gne_pot_finalize")

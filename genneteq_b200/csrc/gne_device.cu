@@ -125,6 +125,7 @@ struct gne_dev {
     int64_t h2dBytes = 0, d2hBytes = 0;
     int64_t qsWindow = 0;                          // adaptive window of the quickSelect scan
     NbWriteOps pending{};                          // queued gne_nb_write records (<= 8)
+    bool stageInFlight = false;                    // the staging buffer feeds a kernel not yet synchronised
     // multi-GPU
     void *comm = nullptr;
     int rank = 0, nranks = 1;
@@ -155,7 +156,7 @@ static int ensure_stage(gne_dev *d, size_t bytes)
     if (d->stageHost) cudaFreeHost(d->stageHost);
     if (d->stageDev) cudaFree(d->stageDev);
     d->stageHost = nullptr; d->stageDev = nullptr; d->stageBytes = 0;
-    CK(cudaHostAlloc(&d->stageHost, nb, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&d->stageHost, nb, cudaHostAllocMapped));
     CK(cudaMalloc(&d->stageDev, nb));
     d->stageBytes = nb;
     return GNE_OK;
@@ -214,7 +215,7 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     CK(cudaHostAlloc(&d->hostScalar, 64, cudaHostAllocMapped));
     memset(d->lvRes, 0, sizeof(LvResult));
     memset(d->qsState, 0, sizeof(QsState));
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     *out = d;
     return GNE_OK;
 }
@@ -244,7 +245,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
 extern "C" int gne_dev_sync(gne_dev *d)
 {
     CK(cudaSetDevice(d->device));
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     return GNE_OK;
 }
 
@@ -271,7 +272,7 @@ extern "C" int gne_nb_reset(gne_dev *d, int64_t N, const int32_t *tail, const in
         CK(cudaMemcpyAsync(d->state, state + a, c, cudaMemcpyHostToDevice, d->stream));
         d->h2dBytes += 25 * (int64_t) c;
     }
-    CK(cudaStreamSynchronize(d->stream));          // caller may free its arrays
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;          // caller may free its arrays
     return GNE_OK;
 }
 
@@ -284,7 +285,7 @@ extern "C" int gne_nb_set_costs(gne_dev *d, int64_t N, const double *cost)
         CK(cudaMemcpyAsync(d->cost, cost + a, 8 * (size_t) (b - a), cudaMemcpyHostToDevice, d->stream));
         d->h2dBytes += 8 * (b - a);
     }
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     return GNE_OK;
 }
 
@@ -342,7 +343,7 @@ extern "C" int gne_nb_read(gne_dev *d, int64_t lo, int64_t hi, int32_t *tail, in
     if (cost) CK(cudaMemcpyAsync(cost, d->cost + o, 8 * c, cudaMemcpyDeviceToHost, d->stream));
     if (mult) CK(cudaMemcpyAsync(mult, d->mult + o, 8 * c, cudaMemcpyDeviceToHost, d->stream));
     if (state) CK(cudaMemcpyAsync(state, d->state + o, c, cudaMemcpyDeviceToHost, d->stream));
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     return GNE_OK;
 }
 
@@ -357,7 +358,7 @@ extern "C" int gne_pot_update_nodes(gne_dev *d, int64_t count, const int32_t *no
     CK(cudaSetDevice(d->device));
     const size_t bytes = (size_t) count * 24;
     int rc = ensure_stage(d, bytes); if (rc) return rc;
-    CK(cudaStreamSynchronize(d->stream));           // the staging buffer may still be in flight
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;           // the staging buffer may still be in flight
     char *h = (char *) d->stageHost;
     memcpy(h, a0, 8 * (size_t) count);
     memcpy(h + 8 * (size_t) count, a1, 8 * (size_t) count);
@@ -371,6 +372,7 @@ extern "C" int gne_pot_update_nodes(gne_dev *d, int64_t count, const int32_t *no
     CK(cudaGetLastError());
     ++d->launches;
     d->h2dBytes += (int64_t) bytes;
+    d->stageInFlight = true;
     return GNE_OK;
 }
 
@@ -380,7 +382,7 @@ extern "C" int gne_pot_update_thetas(gne_dev *d, int64_t count, const int32_t *s
     CK(cudaSetDevice(d->device));
     const size_t bytes = (size_t) count * 12;
     int rc = ensure_stage(d, bytes); if (rc) return rc;
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     char *h = (char *) d->stageHost;
     memcpy(h, theta, 8 * (size_t) count);
     memcpy(h + 8 * (size_t) count, slot, 4 * (size_t) count);
@@ -390,6 +392,59 @@ extern "C" int gne_pot_update_thetas(gne_dev *d, int64_t count, const int32_t *s
     CK(cudaGetLastError());
     ++d->launches;
     d->h2dBytes += (int64_t) bytes;
+    d->stageInFlight = true;
+    return GNE_OK;
+}
+
+// One call per pivot from the solver: queued set writes + dirty records + thetas + finalize.
+// nFinal < 0 => finalize every node.  Small updates ride in a single one-CTA kernel that reads the
+// mapped pinned staging buffer directly; large ones are copied to the device first.
+extern "C" int gne_pot_update_fused(gne_dev *d, int64_t nNodes, const int32_t *node, const double *a0, const double *a1,
+                                    const int32_t *slot, int64_t nTheta, const int32_t *tslot, const double *theta,
+                                    int64_t nFinal, const int32_t *fnode)
+{
+    CK(cudaSetDevice(d->device));
+    const bool full = nFinal < 0;
+    const int64_t nf = full ? 0 : nFinal;
+    const size_t bytes = (size_t) nNodes * 24 + (size_t) nTheta * 12 + (size_t) nf * 4 + 64;
+    if (nNodes == 0 && nTheta == 0 && nf == 0 && !full) return gne_dev_flush(d);
+    int rc = ensure_stage(d, bytes); if (rc) return rc;
+    if (d->stageInFlight) { CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false; d->stageInFlight = false; }
+    char *h = (char *) d->stageHost;
+    size_t o = 0;
+    const size_t oA0 = o; memcpy(h + o, a0, 8 * (size_t) nNodes); o += 8 * (size_t) nNodes;
+    const size_t oA1 = o; memcpy(h + o, a1, 8 * (size_t) nNodes); o += 8 * (size_t) nNodes;
+    const size_t oTh = o; memcpy(h + o, theta, 8 * (size_t) nTheta); o += 8 * (size_t) nTheta;
+    const size_t oNd = o; memcpy(h + o, node, 4 * (size_t) nNodes); o += 4 * (size_t) nNodes;
+    const size_t oSl = o; memcpy(h + o, slot, 4 * (size_t) nNodes); o += 4 * (size_t) nNodes;
+    const size_t oTs = o; memcpy(h + o, tslot, 4 * (size_t) nTheta); o += 4 * (size_t) nTheta;
+    const size_t oFn = o; if (nf) memcpy(h + o, fnode, 4 * (size_t) nf); o += 4 * (size_t) nf;
+    d->h2dBytes += (int64_t) o;
+    d->stageInFlight = true;
+    NbMut m; m.tail = d->tail; m.head = d->head; m.cost = d->cost; m.mult = d->mult; m.state = d->state;
+    const bool small = !full && o <= (size_t) 96 * 1024;
+    const char *src = small ? h : (const char *) d->stageDev;
+    if (!small) CK(cudaMemcpyAsync(d->stageDev, h, o, cudaMemcpyHostToDevice, d->stream));
+    FusedUpdate u;
+    u.nNodes = nNodes; u.node = (const int32_t *) (src + oNd); u.a0 = (const double *) (src + oA0); u.a1 = (const double *) (src + oA1);
+    u.slot = (const int32_t *) (src + oSl);
+    u.nTheta = nTheta; u.tslot = (const int32_t *) (src + oTs); u.theta = (const double *) (src + oTh);
+    u.nFinal = nf; u.fnode = (const int32_t *) (src + oFn);
+    NbWriteOps &ops = pending_of(d);
+    if (small) {
+        d->h2dBytes += 25 * ops.n;
+        k_update_fused<<<1, 1024, 0, d->stream>>>(m, ops, u, d->a0, d->a1, d->slot, d->theta, d->pi);
+        ops.n = 0;
+        ++d->launches;
+    } else {
+        rc = flush_writes(d, ops); if (rc) return rc;
+        if (nNodes) { k_pot_update_nodes<<<blocks_for(nNodes, 256), 256, 0, d->stream>>>(nNodes, u.node, u.a0, u.a1, u.slot, d->a0, d->a1, d->slot); ++d->launches; }
+        if (nTheta) { k_pot_update_thetas<<<blocks_for(nTheta, 256), 256, 0, d->stream>>>(nTheta, u.tslot, u.theta, d->theta); ++d->launches; }
+        if (full) k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi);
+        else k_pot_finalize_list<<<blocks_for(nf, 256), 256, 0, d->stream>>>(nf, u.fnode, d->a0, d->a1, d->slot, d->theta, d->pi);
+        ++d->launches;
+    }
+    CK(cudaGetLastError());
     return GNE_OK;
 }
 
@@ -408,7 +463,7 @@ extern "C" int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const
     CK(cudaSetDevice(d->device));
     const size_t bytes = (size_t) count * 12;
     int rc = ensure_stage(d, bytes); if (rc) return rc;
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     char *h = (char *) d->stageHost;
     memcpy(h, pi, 8 * (size_t) count);
     memcpy(h + 8 * (size_t) count, node, 4 * (size_t) count);
@@ -418,6 +473,7 @@ extern "C" int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const
     CK(cudaGetLastError());
     ++d->launches;
     d->h2dBytes += (int64_t) bytes;
+    d->stageInFlight = true;
     return GNE_OK;
 }
 
@@ -425,7 +481,7 @@ extern "C" int gne_pot_set_all(gne_dev *d, const double *pi)
 {
     CK(cudaSetDevice(d->device));
     CK(cudaMemcpyAsync(d->pi, pi, 8 * (size_t) d->n, cudaMemcpyHostToDevice, d->stream));
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->h2dBytes += 8 * (int64_t) d->n;
     return GNE_OK;
 }
@@ -434,7 +490,7 @@ extern "C" int gne_pot_get_all(gne_dev *d, double *pi)
 {
     CK(cudaSetDevice(d->device));
     CK(cudaMemcpyAsync(pi, d->pi, 8 * (size_t) d->n, cudaMemcpyDeviceToHost, d->stream));
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->d2hBytes += 8 * (int64_t) d->n;
     return GNE_OK;
 }
@@ -453,7 +509,7 @@ static int viol_compact_device(gne_dev *d, double threshold, int64_t *total)
     k_scan_tiles<<<1, 1024, 0, d->stream>>>(d->tileCnt, d->tileOff, G, d->hostScalar);
     CK(cudaGetLastError());
     d->launches += 2;
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     *total = d->hostScalar[0];
     d->d2hBytes += 8;
     if (*total == 0) return GNE_OK;
@@ -511,7 +567,7 @@ extern "C" int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count
     CK(cudaSetDevice(d->device));
     int rc = gne_dev_flush(d); if (rc) return rc;
     rc = price_lv_local(d); if (rc) return rc;
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
 
     std::vector<int64_t> list;
@@ -541,7 +597,7 @@ extern "C" int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count
             if (total > 0) {
                 CK(cudaMemcpyAsync(hp.data(), d->outPos, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
                 CK(cudaMemcpyAsync(hv.data(), d->outViol, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
-                CK(cudaStreamSynchronize(d->stream));
+                CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
                 d->d2hBytes += 16 * total;
             }
             ok = replay_band_rule(hp.data(), hv.data(), total, floorV, zero, list, &L);
@@ -567,13 +623,13 @@ extern "C" int gne_price_violators(gne_dev *d, double threshold, int64_t *count,
     rc = viol_compact_device(d, threshold, &total); if (rc) return rc;
     CK(cudaEventRecord(d->ev1, d->stream));
     *count = total;
-    if (total > cap) { CK(cudaStreamSynchronize(d->stream)); gne_set_error("gne_price_violators: %lld exceeds cap", (long long) total); return GNE_ERR_CAPACITY; }
+    if (total > cap) { CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false; gne_set_error("gne_price_violators: %lld exceeds cap", (long long) total); return GNE_ERR_CAPACITY; }
     if (total > 0) {
         CK(cudaMemcpyAsync(listPos, d->outPos, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
         if (listViol) CK(cudaMemcpyAsync(listViol, d->outViol, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
         d->d2hBytes += (listViol ? 16 : 8) * total;
     }
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
     return GNE_OK;
 }
@@ -588,7 +644,7 @@ extern "C" int gne_price_first(gne_dev *d, int64_t *pos)
     if (G > 0) { k_price_first<<<G, TILE_THREADS, 0, d->stream>>>(view_of(d), d->pi, d->firstPos); ++d->launches; }
     CK(cudaMemcpyAsync(&d->hostScalar[1], d->firstPos, 8, cudaMemcpyDeviceToHost, d->stream));
     CK(cudaEventRecord(d->ev1, d->stream));
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
     d->d2hBytes += 8;
     const unsigned long long v = (unsigned long long) d->hostScalar[1];
@@ -608,7 +664,7 @@ extern "C" int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc)
     CK(cudaGetLastError());
     ++d->launches;
     CK(cudaMemcpyAsync(rc, d->outViol, 8 * (size_t) (hi - lo), cudaMemcpyDeviceToHost, d->stream));
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->d2hBytes += 8 * (hi - lo);
     return GNE_OK;
 }
@@ -639,7 +695,7 @@ extern "C" int gne_price_qs(gne_dev *d, int64_t cursor, int64_t want, int64_t *b
         CK(cudaEventRecord(d->ev1, d->stream));
         CK(cudaGetLastError());
         d->launches += 2;
-        CK(cudaStreamSynchronize(d->stream));
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
         float ms; CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1)); msTotal += ms;
         d->d2hBytes += sizeof(QsState);
         if (st->done) {
@@ -689,7 +745,7 @@ extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVar
         for (int r = 0; r < reps + 2; ++r) {
             CK(cudaEventRecord(d->ev0, d->stream));
             switch (v) {
-              case 0: k_price_lv_tiles<<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); break;
+              case 0: k_price_lv_tiles<<<(int) ((len + TILE - 1) / TILE), TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); break;
               case 1: k_var_tiles<2, 5, false><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
               case 2: k_var_tiles<2, 6, false><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
               case 3: k_var_tiles<2, 8, false><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
@@ -705,7 +761,7 @@ extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVar
             }
             CK(cudaEventRecord(d->ev1, d->stream));
             CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(d->stream));
+            CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
             float ms; CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
             if (r >= 2) { sum += ms; best = std::min(best, ms); }
             ++d->launches;
@@ -743,7 +799,7 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
         if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
         CK(cudaEventRecord(d->ev3, d->stream));
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(d->stream));
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
         CK(cudaEventElapsedTime(&msStep[i], d->ev2, d->ev3));
         CK(cudaEventElapsedTime(&msTiles[i], d->ev0, d->ev1));
     }
@@ -819,7 +875,7 @@ int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &
 {
     // price_lv_local has been launched by the caller; exchange, then the same merge on every rank
     int rcx = launch_shard_exchange(d); if (rcx) return rcx;
-    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->d2hBytes += sizeof(ShardRecord) * (int64_t) d->nranks;
     const ShardRecord *rec = (const ShardRecord *) d->gatherHost;
     std::vector<double> maxima(d->nranks);

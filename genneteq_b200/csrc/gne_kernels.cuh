@@ -6,10 +6,13 @@
 // no FMA: genneteq.h:315-316, gnePotential.cpp:130) — results are bit-identical to the CPU.
 //
 // Nonbasic arcs live as a structure-of-arrays in setNBarc *position* order (gnePivot.cpp:527-600
-// defines that order); a tile is TILE consecutive positions, one CTA per tile:
-//   thread t owns positions base + 4t .. 4t+3 and base + TILE/2 + 4t .. 4t+3
-// so tail/head are read as int4, cost/mult as 2 x double2 and state as one 32-bit word per
-// chunk — 128-bit coalesced loads, 25 algorithmic bytes per arc.
+// defines that order); a tile is TILE consecutive positions, one CTA per tile, thread t owning
+// positions base + t + 256 k (k = 0..ITEMS-1): every load instruction of a warp covers 32
+// consecutive elements (one 128-byte line for the 4-byte columns, two for the 8-byte ones), 25
+// algorithmic bytes per arc.  The pass is bound by L1TEX wavefronts, not by HBM: the gather of
+// pi[head] costs one wavefront per arc (32 distinct lines per warp instruction), against ~0.3 for
+// everything else.  Measured on B200 (profiles/): 128-bit vector loads with 48 registers (62%
+// occupancy) ran the 20M-arc pass in 121 us, this scalar layout with 32 registers (100%) in 113 us.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,8 +20,8 @@
 namespace gne {
 
 constexpr int TILE_THREADS = 256;
-constexpr int TILE = 2048;                 // positions per CTA (2 chunks x 256 threads x 4)
-constexpr int HALF = TILE / 2;
+constexpr int ITEMS = 4;                   // positions per thread
+constexpr int TILE = ITEMS * TILE_THREADS;  // 1024 positions per CTA
 constexpr int CAND_K = 16;                 // in-band candidates kept per tile by the LV pass
 constexpr int LV_LIST_CAP = 2048;          // candidates returned by the fused LV pass
 constexpr int QTILE = 1024;                // virtual positions per CTA in the quickSelect scan
@@ -50,43 +53,32 @@ __device__ __forceinline__ double violation(double rc, int st)
 
 __device__ __forceinline__ double ld_pi(const double *pi, int i) { return __ldg(pi + i); }
 
-// Violation magnitudes of this thread's 8 positions of tile `tileBase` (local index).
-// v[k], k = 0..3 -> local tileBase + 4t + k ; k = 4..7 -> tileBase + HALF + 4t + (k-4).
+// Violation magnitudes of this thread's ITEMS positions of the tile starting at local index
+// `tileBase`: v[k] belongs to local index tileBase + t + 256 k.
 __device__ __forceinline__ void tile_violations(const NbView &nb, const double *__restrict__ pi,
-                                                int64_t tileBase, double v[8], double *rcOut = nullptr)
+                                                int64_t tileBase, double v[ITEMS], double *rcOut = nullptr)
 {
-    const int t = threadIdx.x;
+    const int64_t base = tileBase + threadIdx.x;
+    int tl[ITEMS], hd[ITEMS], st[ITEMS];
+    double cs[ITEMS], mu[ITEMS];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const int64_t l0 = tileBase + c * HALF + 4 * t;          // local index of the 4-chunk
-        const int4 tl = __ldg(reinterpret_cast<const int4 *>(nb.tail + l0));
-        const int4 hd = __ldg(reinterpret_cast<const int4 *>(nb.head + l0));
-        const double2 c01 = __ldg(reinterpret_cast<const double2 *>(nb.cost + l0));
-        const double2 c23 = __ldg(reinterpret_cast<const double2 *>(nb.cost + l0 + 2));
-        const double2 m01 = __ldg(reinterpret_cast<const double2 *>(nb.mult + l0));
-        const double2 m23 = __ldg(reinterpret_cast<const double2 *>(nb.mult + l0 + 2));
-        const uint32_t st4 = __ldg(reinterpret_cast<const uint32_t *>(nb.state + l0));
-        // arcs are created sorted by tail, so neighbouring positions mostly share pi[tail]
-        const double pt0 = ld_pi(pi, tl.x);
-        const double pt1 = (tl.y == tl.x) ? pt0 : ld_pi(pi, tl.y);
-        const double pt2 = (tl.z == tl.y) ? pt1 : ld_pi(pi, tl.z);
-        const double pt3 = (tl.w == tl.z) ? pt2 : ld_pi(pi, tl.w);
-        const double ph0 = ld_pi(pi, hd.x), ph1 = ld_pi(pi, hd.y), ph2 = ld_pi(pi, hd.z), ph3 = ld_pi(pi, hd.w);
-        const double r0 = red_cost(c01.x, m01.x, pt0, ph0);
-        const double r1 = red_cost(c01.y, m01.y, pt1, ph1);
-        const double r2 = red_cost(c23.x, m23.x, pt2, ph2);
-        const double r3 = red_cost(c23.y, m23.y, pt3, ph3);
-        const int64_t g0 = nb.lo + l0;
-        v[4 * c + 0] = (g0 + 0 < nb.end) ? violation(r0, (int) (st4 & 0xff)) : -1.0;
-        v[4 * c + 1] = (g0 + 1 < nb.end) ? violation(r1, (int) ((st4 >> 8) & 0xff)) : -1.0;
-        v[4 * c + 2] = (g0 + 2 < nb.end) ? violation(r2, (int) ((st4 >> 16) & 0xff)) : -1.0;
-        v[4 * c + 3] = (g0 + 3 < nb.end) ? violation(r3, (int) ((st4 >> 24) & 0xff)) : -1.0;
-        if (rcOut) { rcOut[4 * c + 0] = r0; rcOut[4 * c + 1] = r1; rcOut[4 * c + 2] = r2; rcOut[4 * c + 3] = r3; }
+    for (int k = 0; k < ITEMS; ++k) {
+        const int64_t l = base + k * TILE_THREADS;
+        tl[k] = __ldg(nb.tail + l); hd[k] = __ldg(nb.head + l);
+        cs[k] = __ldg(nb.cost + l); mu[k] = __ldg(nb.mult + l);
+        st[k] = __ldg(nb.state + l);
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int64_t l = base + k * TILE_THREADS;
+        const double r = red_cost(cs[k], mu[k], ld_pi(pi, tl[k]), ld_pi(pi, hd[k]));
+        v[k] = (nb.lo + l < nb.end) ? violation(r, st[k]) : -1.0;
+        if (rcOut) rcOut[k] = r;
     }
 }
 
-// local index (within the tile) of slot k of thread t, increasing in position order per chunk
-__device__ __forceinline__ int tile_offset(int t, int k) { return (k >> 2) * HALF + 4 * t + (k & 3); }
+// local index (within the tile) of slot k of thread t; position order == (k, t) lexicographic
+__device__ __forceinline__ int tile_offset(int t, int k) { return t + k * TILE_THREADS; }
 
 // (value, position) argmax with the lower position winning ties
 struct Best { double v; int64_t p; };
@@ -153,15 +145,15 @@ struct LvTiles {
     double *candViol;      // [G * CAND_K]
 };
 
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 8)
 k_price_lv_tiles(NbView nb, const double *__restrict__ pi, LvTiles out)
 {
     const int64_t tileBase = (int64_t) blockIdx.x * TILE;
-    double v[8];
+    double v[ITEMS];
     tile_violations(nb, pi, tileBase, v);
     Best b; b.v = -1.0; b.p = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) if (v[k] > b.v) { b.v = v[k]; b.p = tile_offset(threadIdx.x, k); }
+    for (int k = 0; k < ITEMS; ++k) if (v[k] > b.v) { b.v = v[k]; b.p = tile_offset(threadIdx.x, k); }
     b = block_best(b);
     __shared__ int sCnt;
     __shared__ int sOff[CAND_K];
@@ -171,7 +163,7 @@ k_price_lv_tiles(NbView nb, const double *__restrict__ pi, LvTiles out)
     if (b.v > 0.0) {
         const double thr = __dsub_rn(b.v, LV_BAND);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < ITEMS; ++k) {
             if (v[k] > 0.0 && v[k] >= thr) {
                 int s = atomicAdd(&sCnt, 1);
                 if (s < CAND_K) { sOff[s] = tile_offset(threadIdx.x, k); sViol[s] = v[k]; }
@@ -286,11 +278,11 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
 __global__ void __launch_bounds__(TILE_THREADS)
 k_viol_count(NbView nb, const double *__restrict__ pi, double threshold, int32_t *tileCnt)
 {
-    double v[8];
+    double v[ITEMS];
     tile_violations(nb, pi, (int64_t) blockIdx.x * TILE, v);
     int c = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) c += (v[k] > 0.0 && v[k] >= threshold);
+    for (int k = 0; k < ITEMS; ++k) c += (v[k] > 0.0 && v[k] >= threshold);
     int total;
     block_excl_scan(c, &total);
     if (threadIdx.x == 0) tileCnt[blockIdx.x] = total;
@@ -332,26 +324,19 @@ k_viol_write(NbView nb, const double *__restrict__ pi, double threshold, const i
              int64_t *outPos, double *outViol, int64_t cap)
 {
     const int64_t tileBase = (int64_t) blockIdx.x * TILE;
-    double v[8];
+    double v[ITEMS];
     tile_violations(nb, pi, tileBase, v);
     int64_t base = tileOff[blockIdx.x];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cnt += (v[4 * c + k] > 0.0 && v[4 * c + k] >= threshold);
+    for (int k = 0; k < ITEMS; ++k) {                   // position order is (k, t) lexicographic
+        const int f = (v[k] > 0.0 && v[k] >= threshold) ? 1 : 0;
         int total;
-        int off = block_excl_scan(cnt, &total);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double vv = v[4 * c + k];
-            if (vv > 0.0 && vv >= threshold) {
-                const int64_t o = base + off;
-                if (o < cap) {
-                    outPos[o] = nb.lo + tileBase + tile_offset(threadIdx.x, 4 * c + k);
-                    if (outViol) outViol[o] = vv;
-                }
-                ++off;
+        const int off = block_excl_scan(f, &total);
+        if (f) {
+            const int64_t o = base + off;
+            if (o < cap) {
+                outPos[o] = nb.lo + tileBase + tile_offset(threadIdx.x, k);
+                if (outViol) outViol[o] = v[k];
             }
         }
         base += total;
@@ -363,11 +348,11 @@ __global__ void __launch_bounds__(TILE_THREADS)
 k_price_first(NbView nb, const double *__restrict__ pi, unsigned long long *firstPos)
 {
     const int64_t tileBase = (int64_t) blockIdx.x * TILE;
-    double v[8];
+    double v[ITEMS];
     tile_violations(nb, pi, tileBase, v);
     unsigned long long best = ~0ull;
 #pragma unroll
-    for (int k = 7; k >= 0; --k) if (v[k] > 0.0) best = (unsigned long long) (nb.lo + tileBase + tile_offset(threadIdx.x, k));
+    for (int k = ITEMS - 1; k >= 0; --k) if (v[k] > 0.0) best = (unsigned long long) (nb.lo + tileBase + tile_offset(threadIdx.x, k));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
     if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(firstPos, best);
@@ -377,10 +362,10 @@ __global__ void __launch_bounds__(TILE_THREADS)
 k_reduced_costs(NbView nb, const double *__restrict__ pi, int64_t lo, int64_t hi, double *rc)
 {
     const int64_t tileBase = (int64_t) blockIdx.x * TILE;
-    double v[8], r[8];
+    double v[ITEMS], r[ITEMS];
     tile_violations(nb, pi, tileBase, v, r);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const int64_t g = nb.lo + tileBase + tile_offset(threadIdx.x, k);
         if (g >= lo && g < hi && g < nb.end) rc[g - lo] = r[k];
     }
@@ -551,6 +536,42 @@ __global__ void k_pot_set(int64_t count, const int32_t *__restrict__ node, const
 {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) pi[node[i]] = val[i];
+}
+
+// Fused per-pivot update for small dirty sets (one CTA, inputs read straight from mapped pinned
+// host memory): queued set-mirror writes, dirty (node, a0, a1, slot) records, dirty thetas, then
+// — after a barrier — the finalize of the listed nodes.  One launch instead of four + two copies.
+struct FusedUpdate {
+    int64_t nNodes;  const int32_t *node;  const double *a0;  const double *a1;  const int32_t *slot;
+    int64_t nTheta;  const int32_t *tslot; const double *theta;
+    int64_t nFinal;  const int32_t *fnode;              // nodes whose pi must be recomputed
+};
+
+__global__ void __launch_bounds__(1024)
+k_update_fused(NbMut nb, NbWriteOps ops, FusedUpdate u, double *A0, double *A1, int32_t *S, double *T, double *pi)
+{
+    const int t = threadIdx.x;
+    if (t < ops.n) {
+        const int64_t l = ops.local[t];
+        nb.tail[l] = ops.tail[t]; nb.head[l] = ops.head[t];
+        nb.cost[l] = ops.cost[t]; nb.mult[l] = ops.mult[t]; nb.state[l] = ops.state[t];
+    }
+    for (int64_t i = t; i < u.nNodes; i += blockDim.x) { const int v = u.node[i]; A0[v] = u.a0[i]; A1[v] = u.a1[i]; S[v] = u.slot[i]; }
+    for (int64_t i = t; i < u.nTheta; i += blockDim.x) T[u.tslot[i]] = u.theta[i];
+    __syncthreads();
+    for (int64_t i = t; i < u.nFinal; i += blockDim.x) {
+        const int v = u.fnode[i];
+        pi[v] = __dadd_rn(A0[v], __dmul_rn(A1[v], T[S[v]]));
+    }
+}
+
+// finalize of a node list (larger dirty sets, inputs already copied to the device)
+__global__ void k_pot_finalize_list(int64_t count, const int32_t *__restrict__ fnode, const double *__restrict__ A0,
+                                    const double *__restrict__ A1, const int32_t *__restrict__ S, const double *__restrict__ T,
+                                    double *__restrict__ pi)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { const int v = fnode[i]; pi[v] = __dadd_rn(A0[v], __dmul_rn(A1[v], __ldg(T + S[v]))); }
 }
 
 __global__ void k_flush_l2(double *buf, int64_t n)

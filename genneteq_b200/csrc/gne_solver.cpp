@@ -271,7 +271,8 @@ void GenNetEq::computeFlowsPivotingTI(int32_t eav, int32_t tU, int32_t tV)      
 // ------------------------------------------------------------------------------------------
 int GenNetEq::computePotentials()
 {
-    upNode.clear(); upSlot.clear(); upA0.clear(); upA1.clear(); upThetaSlot.clear(); upTheta.clear();
+    upNode.clear(); upSlot.clear(); upA0.clear(); upA1.clear(); upThetaSlot.clear(); upTheta.clear(); upFinal.clear();
+    bool finalizeAll = false;
     if ((int) thetaOfSlot.size() < forest.numSlots()) thetaOfSlot.resize(forest.numSlots(), 0.0);
     for (size_t c = 0; c < forest.changed.size(); ++c) {
         const int32_t slot = forest.changed[c];
@@ -312,12 +313,17 @@ int GenNetEq::computePotentials()
         const double theta = ((cost[ex] - potA0[alpha]) + pb0) / (potA1[alpha] - pb1);
         thetaOfSlot[slot] = theta;
         upThetaSlot.push_back(slot); upTheta.push_back(theta);
+        // every node of a touched tree gets a new pi (theta multiplies a1 != 0)
+        if (!finalizeAll) {
+            if (upFinal.size() + t.nodes.size() > (size_t) numNodes / 4) finalizeAll = true;
+            else upFinal.insert(upFinal.end(), t.nodes.begin(), t.nodes.end());
+        }
     }
     forest.changed.clear();
-    if (!upNode.empty()) GNE_TRY(gne_pot_update_nodes(dev, (int64_t) upNode.size(), upNode.data(), upA0.data(), upA1.data(), upSlot.data()));
-    if (!upThetaSlot.empty()) GNE_TRY(gne_pot_update_thetas(dev, (int64_t) upThetaSlot.size(), upThetaSlot.data(), upTheta.data()));
-    if (!upNode.empty() || !upThetaSlot.empty()) GNE_TRY(gne_pot_finalize(dev));     // gnePotential.cpp:127-135
-    return GNE_OK;
+    // one call: queued setNBarc writes + dirty records + thetas + finalize (gnePotential.cpp:127-135)
+    return gne_pot_update_fused(dev, (int64_t) upNode.size(), upNode.data(), upA0.data(), upA1.data(), upSlot.data(),
+                                (int64_t) upThetaSlot.size(), upThetaSlot.data(), upTheta.data(),
+                                finalizeAll ? -1 : (int64_t) upFinal.size(), upFinal.data());
 }
 
 int GenNetEq::fetchViolators(double threshold)

@@ -136,7 +136,7 @@ class GenNetEq {
     bool costsOnDevice = false;
     std::vector<int64_t> listPos;
     std::vector<double> listViol;
-    std::vector<int32_t> upNode, upSlot, upThetaSlot;
+    std::vector<int32_t> upNode, upSlot, upThetaSlot, upFinal;
     std::vector<double> upA0, upA1, upTheta;
     int status = GNE_OK;
 

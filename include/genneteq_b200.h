@@ -77,6 +77,12 @@ int gne_nb_read(gne_dev *d, int64_t lo, int64_t hi, int32_t *tail, int32_t *head
 int gne_pot_update_nodes(gne_dev *d, int64_t count, const int32_t *node, const double *a0, const double *a1, const int32_t *slot);
 int gne_pot_update_thetas(gne_dev *d, int64_t count, const int32_t *slot, const double *theta);
 int gne_pot_finalize(gne_dev *d);
+/* all of the above for one pivot in one call (what the solver uses): queued gne_nb_write records,
+ * dirty node records, dirty thetas, then the finalize of the nodes in fnode[0..nFinal)
+ * (nFinal < 0: every node).  Small updates are one one-CTA kernel reading pinned host memory.  */
+int gne_pot_update_fused(gne_dev *d, int64_t nNodes, const int32_t *node, const double *a0, const double *a1,
+                         const int32_t *slot, int64_t nTheta, const int32_t *tslot, const double *theta,
+                         int64_t nFinal, const int32_t *fnode);
 /* direct write of pi (callers that computed potentials themselves)                            */
 int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const double *pi);
 int gne_pot_set_all(gne_dev *d, const double *pi);

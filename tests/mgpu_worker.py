@@ -1,0 +1,105 @@
+"""Worker for the multi-rank tests (launched with torch.distributed.run).
+
+mode "nccl": one rank per GPU; the solver prices its shard of the nonbasic list on its GPU and the
+             per-shard records are exchanged with NCCL inside the library.  Every rank must produce
+             the reference's pivot trace.
+mode "gloo": CPU only; each rank prices its position range with the oracle's scalar pass, the
+             records are all-gathered with gloo and merged by gne_merge_lv_shards (host logic of the
+             N > 1 path).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE, os.path.join(HERE, "golden")):
+    sys.path.insert(0, p)
+
+import genneteq_b200 as gne  # noqa: E402
+from oracle_util import RULES, Instance, Oracle, oracle_lib, dp, ip, lp, bp  # noqa: E402
+
+
+def main():
+    mode, out = sys.argv[1], sys.argv[2]
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", "0"))
+    gold = np.load(os.path.join(HERE, "golden", "c1_wide_s7.npz"))
+    inst = Instance.load(os.path.join(HERE, "golden", "c1_wide_s7_instance.npz"))
+    if mode == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = np.zeros(128, np.uint8)
+            gne._ck(gne.lib.gne_comm_unique_id(buf.ctypes.data_as(gne._u8p)), "gne_comm_unique_id")
+            uid = torch.from_numpy(buf)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, device=local, rule1="LV")
+        s.set_comm(uid.cpu().numpy(), rank, world)
+        p1, p2 = s.solve_both()
+        e, l = s.trace
+        ok = (p1, p2) == tuple(int(v) for v in gold["LV_p"]) and np.array_equal(e, gold["LV_e"]) and np.array_equal(l, gold["LV_l"])
+        ok = ok and s.objective == float(gold["LV_objective"]) and np.array_equal(s.flows(), gold["LV_flows"])
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            open(out, "w").write("OK" if int(flag.item()) == 1 else "MISMATCH")
+        dist.destroy_process_group()
+        return
+    # ---- gloo: host logic of the sharded LV exchange
+    dist.init_process_group("gloo")
+    lib = oracle_lib()
+    band = 4.0e-13
+    stride = 48
+    good = True
+    for K in (0, 40, 900):
+        o = Oracle(inst, RULES["LV"])
+        o.solve(True, K)
+        pi = o.compute_potentials()
+        nb = o.nonbasic_soa()
+        N = len(nb["order"])
+        per = ((N + world - 1) // world + 2047) // 2048 * 2048
+        lo, hi = rank * per, min(N, (rank + 1) * per)
+        sl = slice(lo, max(lo, hi))
+        cnt_cap = max(hi - lo, 1)
+        pos = np.zeros(cnt_cap, np.int64); viol = np.zeros(cnt_cap)
+        t, h, c, m, st = (np.ascontiguousarray(nb[k][sl]) for k in ("tail", "head", "cost", "mult", "state"))
+        k = lib.orc_price_violators(C.c_long(max(hi - lo, 0)), ip(t), ip(h), dp(c), dp(m), bp(st), dp(pi), C.c_double(0.0),
+                                    lp(pos), dp(viol), C.c_long(cnt_cap))
+        pos = pos[:k] + lo; viol = viol[:k]
+        rec = np.zeros(3 + 2 * stride)
+        if k:
+            mx = viol.max()
+            keep = viol >= mx - band
+            c = int(keep.sum())
+            rec[0] = mx; rec[1] = 1; rec[2] = c if c <= stride else -1
+            rec[3:3 + min(c, stride)] = pos[keep][:stride]
+            rec[3 + stride:3 + stride + min(c, stride)] = viol[keep][:stride]
+        else:
+            rec[0] = -1.0
+        mine = torch.from_numpy(rec)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = np.stack([a.numpy() for a in allr])
+        res = gne.merge_lv_shards(allr[:, 0], allr[:, 1].astype(np.int32), allr[:, 2].astype(np.int64),
+                                  allr[:, 3:3 + stride].astype(np.int64).ravel(), allr[:, 3 + stride:].ravel(), stride)
+        lst = np.zeros(N, np.int64); L = C.c_double(0); anyv = C.c_int(0)
+        kk = lib.orc_price_lv(C.c_long(N), ip(nb["tail"]), ip(nb["head"]), dp(nb["cost"]), dp(nb["mult"]), bp(nb["state"]),
+                              dp(pi), lp(lst), C.c_long(N), C.byref(L), C.byref(anyv))
+        good = good and res["any"] == bool(anyv.value) and not res["need_fallback"]
+        good = good and res["largest"] == L.value and np.array_equal(res["list"], lst[:kk])
+        o.close()
+    flag = torch.tensor([1 if good else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        open(out, "w").write("OK" if int(flag.item()) == 1 else "MISMATCH")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,31 @@
+"""N > 1 path: world_size-2 gloo test of the host logic on CPU, NCCL test on >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def launch(mode, nproc, out, port):
+    env = dict(os.environ)
+    env["MASTER_ADDR"] = "127.0.0.1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py"), mode, out]
+    subprocess.run(cmd, check=True, env=env, timeout=900, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    return open(out).read()
+
+
+def test_sharded_lv_exchange_host_logic_gloo(tmp_path):
+    import __graft_entry__ as ge
+    ge.build()
+    assert launch("gloo", 2, str(tmp_path / "gloo.txt"), 29611) == "OK"
+
+
+@pytest.mark.gpu
+def test_sharded_solve_two_gpus_nccl(tmp_path):
+    import genneteq_b200 as gne
+    if gne.cuda_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    assert launch("nccl", 2, str(tmp_path / "nccl.txt"), 29612) == "OK"
