@@ -130,6 +130,9 @@ struct gne_dev {
     void *comm = nullptr;
     int rank = 0, nranks = 1;
     void *gatherSend = nullptr, *gatherRecv = nullptr, *gatherHost = nullptr;
+    int64_t *cntDev = nullptr;                     // [1 + nranks] counts exchange
+    char *xSend = nullptr, *xRecv = nullptr;       // variable-length list exchange, grown on demand
+    size_t xSendBytes = 0, xRecvBytes = 0;
 };
 
 static NbView view_of(const gne_dev *d)
@@ -229,7 +232,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
                     d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->stageDev, d->outPos, d->outViol,
-                    d->flushBuf, d->gatherSend, d->gatherRecv };
+                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv };
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost };
     for (void *p : host) if (p) cudaFreeHost(p);
@@ -498,6 +501,8 @@ extern "C" int gne_pot_get_all(gne_dev *d, double *pi)
 // ------------------------------------------------------------------------------------------
 // pricing
 // ------------------------------------------------------------------------------------------
+static int sharded_gather_lists(gne_dev *d, int64_t localCount, std::vector<int64_t> &pos, std::vector<double> &viol);
+
 static int viol_compact_device(gne_dev *d, double threshold, int64_t *total)
 {
     // ordered compaction of this shard's violators with |rc| >= threshold into d->outPos/outViol
@@ -622,6 +627,16 @@ extern "C" int gne_price_violators(gne_dev *d, double threshold, int64_t *count,
     int64_t total = 0;
     rc = viol_compact_device(d, threshold, &total); if (rc) return rc;
     CK(cudaEventRecord(d->ev1, d->stream));
+    if (d->nranks > 1) {
+        std::vector<int64_t> gp;
+        std::vector<double> gv;
+        rc = sharded_gather_lists(d, total, gp, gv); if (rc) return rc;
+        *count = (int64_t) gp.size();
+        d->lastMs = 0.f;
+        if (*count > cap) { gne_set_error("gne_price_violators: %lld exceeds cap", (long long) *count); return GNE_ERR_CAPACITY; }
+        if (*count > 0) { memcpy(listPos, gp.data(), 8 * gp.size()); if (listViol) memcpy(listViol, gv.data(), 8 * gv.size()); }
+        return GNE_OK;
+    }
     *count = total;
     if (total > cap) { CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false; gne_set_error("gne_price_violators: %lld exceeds cap", (long long) total); return GNE_ERR_CAPACITY; }
     if (total > 0) {
@@ -637,6 +652,7 @@ extern "C" int gne_price_violators(gne_dev *d, double threshold, int64_t *count,
 extern "C" int gne_price_first(gne_dev *d, int64_t *pos)
 {
     CK(cudaSetDevice(d->device));
+    if (d->nranks != 1) { gne_set_error("gne_price_first: not implemented for a sharded list"); return GNE_ERR_UNSUPPORTED; }
     int rc = gne_dev_flush(d); if (rc) return rc;
     const int G = tiles_for(d);
     CK(cudaEventRecord(d->ev0, d->stream));
@@ -871,6 +887,46 @@ static int launch_shard_exchange(gne_dev *d)
     return GNE_OK;
 }
 
+// All-gather of the ranks' variable-length (pos, viol) lists that viol_compact_device left in
+// d->outPos / d->outViol; result concatenated in rank order == global position order.  Every rank
+// runs the same sequence of collectives, so a fallback can never leave a peer waiting.
+static int sharded_gather_lists(gne_dev *d, int64_t localCount, std::vector<int64_t> &pos, std::vector<double> &viol)
+{
+    const int R = d->nranks;
+    if (!d->cntDev) CK(cudaMalloc(&d->cntDev, 8 * (size_t) (R + 1)));
+    d->hostScalar[2] = localCount;
+    CK(cudaMemcpyAsync(d->cntDev, &d->hostScalar[2], 8, cudaMemcpyHostToDevice, d->stream));
+    int r = g_nccl.AllGather(d->cntDev, d->cntDev + 1, 8, /*ncclChar*/ 0, d->comm, d->stream);
+    if (r != 0) { gne_set_error("ncclAllGather(counts): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
+    std::vector<int64_t> counts((size_t) R);
+    CK(cudaMemcpyAsync(counts.data(), d->cntDev + 1, 8 * (size_t) R, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    int64_t maxC = 0, total = 0;
+    for (int k = 0; k < R; ++k) { maxC = std::max(maxC, counts[k]); total += counts[k]; }
+    pos.clear(); viol.clear();
+    if (maxC == 0) return GNE_OK;
+    const size_t per = (size_t) maxC * 16;
+    if (per > d->xSendBytes) { if (d->xSend) cudaFree(d->xSend); d->xSend = nullptr; CK(cudaMalloc(&d->xSend, per)); d->xSendBytes = per; }
+    if (per * R > d->xRecvBytes) { if (d->xRecv) cudaFree(d->xRecv); d->xRecv = nullptr; CK(cudaMalloc(&d->xRecv, per * R)); d->xRecvBytes = per * R; }
+    if (localCount > 0) {
+        CK(cudaMemcpyAsync(d->xSend, d->outPos, 8 * (size_t) localCount, cudaMemcpyDeviceToDevice, d->stream));
+        CK(cudaMemcpyAsync(d->xSend + 8 * (size_t) maxC, d->outViol, 8 * (size_t) localCount, cudaMemcpyDeviceToDevice, d->stream));
+    }
+    r = g_nccl.AllGather(d->xSend, d->xRecv, per, /*ncclChar*/ 0, d->comm, d->stream);
+    if (r != 0) { gne_set_error("ncclAllGather(lists): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
+    std::vector<char> host(per * R);
+    CK(cudaMemcpyAsync(host.data(), d->xRecv, per * R, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    d->d2hBytes += (int64_t) (per * R);
+    pos.reserve((size_t) total); viol.reserve((size_t) total);
+    for (int k = 0; k < R; ++k) {
+        const int64_t *p = (const int64_t *) (host.data() + per * k);
+        const double *v = (const double *) (host.data() + per * k + 8 * (size_t) maxC);
+        for (int64_t i = 0; i < counts[k]; ++i) { pos.push_back(p[i]); viol.push_back(v[i]); }
+    }
+    return GNE_OK;
+}
+
 int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &list, int *any)
 {
     // price_lv_local has been launched by the caller; exchange, then the same merge on every rank
@@ -893,8 +949,24 @@ int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &
     int rc = gne_merge_lv_shards(d->nranks, maxima.data(), anys.data(), counts.data(), pos.data(), viol.data(), SHARD_LIST,
                                  largest, &cnt, outPos.data(), (int64_t) outPos.size(), any, &need);
     if (rc) return rc;
-    if (need) { gne_set_error("sharded LV: tie list exceeds the exchange record (fallback gather not implemented)"); return GNE_ERR_UNSUPPORTED; }
-    list.assign(outPos.begin(), outPos.begin() + cnt);
+    if (!need) { list.assign(outPos.begin(), outPos.begin() + cnt); return GNE_OK; }
+    // fallback (long tie lists): every rank compacts its shard down to a widening band below the
+    // global maximum, the lists are all-gathered, and the sequential rule is replayed on the union
+    double M = -1.0;
+    for (int k = 0; k < d->nranks; ++k) if (anys[k] && maxima[k] > M) M = maxima[k];
+    double width = 16.0 * GNE_ROUNDOFF_TOLERANCE;
+    std::vector<int64_t> gp;
+    std::vector<double> gv;
+    while (true) {
+        double floorV = M - width;
+        bool zero = false;
+        if (!(floorV > 0.0) || width > 1.0e-6) { floorV = 0.0; zero = true; }
+        int64_t localCount = 0;
+        rc = viol_compact_device(d, floorV, &localCount); if (rc) return rc;
+        rc = sharded_gather_lists(d, localCount, gp, gv); if (rc) return rc;
+        if (replay_band_rule(gp.data(), gv.data(), (int64_t) gp.size(), floorV, zero, list, largest)) break;
+        width *= 64.0;
+    }
     return GNE_OK;
 }
 
