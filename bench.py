@@ -112,6 +112,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def dbg(msg):
+    if os.environ.get("GNE_BENCH_DEBUG"):
+        sys.stderr.write("[bench %s %.1f] %s\n" % (os.environ.get("RANK", "0"), time.time() % 1000, msg))
+        sys.stderr.flush()
+
+
 def make_instance(wl):
     import genneteq_b200 as gne
     n, m, seed, mode, rule, desc = WORKLOADS[wl]
@@ -247,6 +253,8 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    dbg("solver ready")
+
     # ---- e2e: one gne_solver_solve call; W warm-up pivots, then exactly K pivots timed inside the
     # library's loop (host clock, device synchronised at both edges of the window)
     W = max(args.warmup, 3)
@@ -256,6 +264,7 @@ def b200_arm(args):
     s.set_window(W, args.steps)
     s.solve(True, W + args.steps)
     barrier()
+    dbg("e2e window done")
     e2e_s, c0, c1 = s.window()
     if e2e_s <= 0:
         raise SystemExit("bench.py: the solve ended before the timed window completed")
@@ -267,16 +276,24 @@ def b200_arm(args):
     flush = (25 * N + 8 * n) < 200e6            # working set not larger than L2 => flush between steps
     dev.bench_price_lv(max(args.warmup, 3), flush)
     barrier()
+    dbg("device warm-up steps done")
     ms_step, ms_tiles = dev.bench_price_lv(args.steps, flush)
     barrier()
+    dbg("device steps done")
     clocks = sampler.stop()
     launches = int(s.counters()["launches"] - c0["launches"])     # e2e window + device steps (warm-up excluded from neither)
+    dev.close()
     if dist is not None:
         t = torch.tensor([e2e_s, float(ms_step.sum()), float(ms_tiles.mean())], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s, step_sum_ms, tiles_ms = (float(x) for x in t.cpu())
     else:
         step_sum_ms, tiles_ms = float(ms_step.sum()), float(ms_tiles.mean())
+    # orderly teardown on every rank: the library's NCCL communicator first, then torch's
+    s.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     value = N * args.steps / (step_sum_ms * 1e-3)
@@ -315,8 +332,7 @@ def b200_arm(args):
         except Exception as ex:                      # the oracle always exists; report why it could not run
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: %r" % (ex,)}
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    sys.stdout.flush()
     return 0
 
 
