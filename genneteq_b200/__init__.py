@@ -86,6 +86,8 @@ SIGNATURES = {
     "gne_solver_device": (_vp, [_vp]),
     "gne_solver_set_window": (C.c_int, [_vp, C.c_int64, C.c_int64]),
     "gne_solver_get_window": (C.c_int, [_vp, _f64p]),
+    "gne_solver_set_progress": (C.c_int, [_vp, C.c_int64, _f64p, C.c_int64]),
+    "gne_solver_progress_rows": (C.c_int64, [_vp]),
     "gne_forest_replay": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, C.c_int64, _i32p, _i32p,
                                     _i32p, _i32p, _i32p, _i32p, _i32p]),
     "gne_merge_lv_shards": (C.c_int, [C.c_int, _f64p, C.POINTER(C.c_int), _i64p, _i64p, _f64p, C.c_int64,
@@ -375,6 +377,15 @@ class Solver:
         a = np.zeros(25)
         lib.gne_solver_get_window(self.h, _p(a, _f64p))
         return a[0], dict(zip(self.COUNTERS, a[1:13].tolist())), dict(zip(self.COUNTERS, a[13:25].tolist()))
+
+    def set_progress(self, every, cap_rows=100000):
+        self._prog = np.zeros((cap_rows, 14))
+        lib.gne_solver_set_progress(self.h, every, _p(self._prog, _f64p), cap_rows)
+
+    def progress(self):
+        """rows of {wall s, counters..., largest tree size}, one per `every` pivots."""
+        k = lib.gne_solver_progress_rows(self.h)
+        return self._prog[:k].copy()
 
     def device(self):
         h = lib.gne_solver_device(self.h)

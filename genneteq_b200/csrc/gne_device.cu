@@ -411,6 +411,23 @@ extern "C" int gne_pot_update_fused(gne_dev *d, int64_t nNodes, const int32_t *n
     const int64_t nf = full ? 0 : nFinal;
     const size_t bytes = (size_t) nNodes * 24 + (size_t) nTheta * 12 + (size_t) nf * 4 + 64;
     if (nNodes == 0 && nTheta == 0 && nf == 0 && !full) return gne_dev_flush(d);
+    if (!full && nNodes <= SU_NODES && nTheta <= SU_THETAS && nf <= SU_FINAL) {
+        // tiny update: everything as kernel arguments (no staging buffer, no host memory reads)
+        SmallUpdate su;
+        NbWriteOps &q = pending_of(d);
+        su.ops = q;
+        su.nNodes = (int) nNodes; su.nTheta = (int) nTheta; su.nFinal = (int) nf; su.pad = 0;
+        for (int64_t i = 0; i < nNodes; ++i) { su.node[i] = node[i]; su.a0[i] = a0[i]; su.a1[i] = a1[i]; su.slot[i] = slot[i]; }
+        for (int64_t i = 0; i < nTheta; ++i) { su.tslot[i] = tslot[i]; su.theta[i] = theta[i]; }
+        for (int64_t i = 0; i < nf; ++i) su.fnode[i] = fnode[i];
+        NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
+        k_update_small<<<1, 256, 0, d->stream>>>(mm, su, d->a0, d->a1, d->slot, d->theta, d->pi);
+        CK(cudaGetLastError());
+        ++d->launches;
+        d->h2dBytes += 25 * q.n + 24 * nNodes + 12 * nTheta + 4 * nf;
+        q.n = 0;
+        return GNE_OK;
+    }
     int rc = ensure_stage(d, bytes); if (rc) return rc;
     if (d->stageInFlight) { CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false; d->stageInFlight = false; }
     char *h = (char *) d->stageHost;

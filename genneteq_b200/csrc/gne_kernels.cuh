@@ -207,8 +207,17 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
     __shared__ int sCount, sOvf;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) { sCount = 0; sOvf = 0; }
+    // pass 1: maximum of the tile maxima; loads issued in independent batches of 8 (a dependent
+    // one-load-per-iteration loop costs a full memory latency per iteration)
     double m = -1.0;
-    for (int g = t; g < G; g += FIN_THREADS) m = fmax(m, tiles.tileMax[g]);
+    for (int g0 = t; g0 < G; g0 += 8 * FIN_THREADS) {
+        double x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int g = g0 + k * FIN_THREADS; x[k] = (g < G) ? __ldg(tiles.tileMax + g) : -1.0; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m = fmax(m, x[k]);
+    }
+    const double mine = m;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) sMax[w] = m;
@@ -221,10 +230,13 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
         return;
     }
     const double thr = __dsub_rn(M, LV_BAND);
-    for (int g = t; g < G; g += FIN_THREADS) {
-        if (tiles.tileMax[g] >= thr) {
-            const int s = atomicAdd(&sCount, 1);
-            if (s < FIN_QCAP) sQ[s] = g;
+    // pass 2: only the threads that saw a tile within the band look again
+    if (mine >= thr) {
+        for (int g = t; g < G; g += FIN_THREADS) {
+            if (__ldg(tiles.tileMax + g) >= thr) {
+                const int s = atomicAdd(&sCount, 1);
+                if (s < FIN_QCAP) sQ[s] = g;
+            }
         }
     }
     __syncthreads();
@@ -561,6 +573,34 @@ k_update_fused(NbMut nb, NbWriteOps ops, FusedUpdate u, double *A0, double *A1, 
     __syncthreads();
     for (int64_t i = t; i < u.nFinal; i += blockDim.x) {
         const int v = u.fnode[i];
+        pi[v] = __dadd_rn(A0[v], __dmul_rn(A1[v], T[S[v]]));
+    }
+}
+
+// The same for tiny dirty sets (the common case while trees are small): everything travels as
+// kernel arguments, so the kernel touches no host memory at all.
+constexpr int SU_NODES = 48, SU_THETAS = 16, SU_FINAL = 160;
+struct SmallUpdate {
+    NbWriteOps ops;
+    int nNodes, nTheta, nFinal, pad;
+    double a0[SU_NODES], a1[SU_NODES], theta[SU_THETAS];
+    int32_t node[SU_NODES], slot[SU_NODES], tslot[SU_THETAS], fnode[SU_FINAL];
+};
+
+__global__ void __launch_bounds__(256)
+k_update_small(NbMut nb, const __grid_constant__ SmallUpdate u, double *A0, double *A1, int32_t *S, double *T, double *pi)
+{
+    const int t = threadIdx.x;
+    if (t < u.ops.n) {
+        const int64_t l = u.ops.local[t];
+        nb.tail[l] = u.ops.tail[t]; nb.head[l] = u.ops.head[t];
+        nb.cost[l] = u.ops.cost[t]; nb.mult[l] = u.ops.mult[t]; nb.state[l] = u.ops.state[t];
+    }
+    if (t < u.nNodes) { const int v = u.node[t]; A0[v] = u.a0[t]; A1[v] = u.a1[t]; S[v] = u.slot[t]; }
+    if (t < u.nTheta) T[u.tslot[t]] = u.theta[t];
+    __syncthreads();
+    if (t < u.nFinal) {
+        const int v = u.fnode[t];
         pi[v] = __dadd_rn(A0[v], __dmul_rn(A1[v], T[S[v]]));
     }
 }

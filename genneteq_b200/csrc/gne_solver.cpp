@@ -708,6 +708,14 @@ int GenNetEq::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *fi
     while (!isOptimal && !isUnbounded) {
         if (winStart >= 0 && callPivots == winStart && winT0 == 0.0) { gne_dev_sync(dev); getCounters(winC0); winT0 = wallNow(); }
         if (winStart >= 0 && callPivots == winStart + winLen && winT1 == 0.0) { gne_dev_sync(dev); winT1 = wallNow(); getCounters(winC1); }
+        if (progEvery > 0 && progBuf && callPivots % progEvery == 0 && progRows < progCap) {
+            double *row = progBuf + 14 * progRows++;
+            row[0] = wallNow();
+            getCounters(row + 1);
+            size_t big = 0;
+            for (int sl = 0; sl < forest.numSlots(); ++sl) if (forest.tree(sl).type != TREE_FREE) big = std::max(big, forest.tree(sl).nodes.size());
+            row[13] = (double) big;
+        }
         if (maxPivots >= 0 && budget == 0) { *finished = 0; break; }
         if ((loopIter % 1000) == 0) computeFlows(2);
         const double a = wallNow();

@@ -86,6 +86,9 @@ class GenNetEq {
     // with the device synchronised at both edges; out = {seconds, 12 counters at start, 12 at end}
     void setWindow(int64_t start, int64_t len) { winStart = start; winLen = len; winT0 = winT1 = 0.0; }
     void getWindow(double *out25) const;
+    // every `every` pivots append {wall seconds, 12 counters, largest tree size} to buf (13+1 doubles per row)
+    void setProgress(int64_t every, double *buf, int64_t capRows) { progEvery = every; progBuf = buf; progCap = capRows; progRows = 0; }
+    int64_t getProgressRows() const { return progRows; }
     gne_dev *device() { return dev; }
 
   protected:
@@ -147,6 +150,8 @@ class GenNetEq {
     double arcsPriced = 0, kernelMs = 0;
     int64_t pivots = 0;
     int64_t winStart = -1, winLen = 0, callPivots = 0;
+    int64_t progEvery = 0, progCap = 0, progRows = 0;
+    double *progBuf = nullptr;
     double winT0 = 0.0, winT1 = 0.0, winC0[12] = { 0 }, winC1[12] = { 0 };
 
     // ---- functions, named as in genneteq.h:153-271

@@ -177,6 +177,10 @@ gne_dev *gne_solver_device(gne_solver *s);
  * out25 = { seconds (-1 if the window was not completed), the 12 counters at its start, at its end } */
 int gne_solver_set_window(gne_solver *s, int64_t startPivot, int64_t numPivots);
 int gne_solver_get_window(const gne_solver *s, double *out25);
+/* progress log: every `every` pivots of a solve call append a row of 14 doubles to buf —
+ * { wall-clock seconds, the 12 counters, size of the largest basis tree }                     */
+int gne_solver_set_progress(gne_solver *s, int64_t every, double *buf, int64_t capRows);
+int64_t gne_solver_progress_rows(const gne_solver *s);
 
 /* Host-only replay of basis exchanges (no device work, usable without a GPU): applies the given
  * (entering, leaving) varIndex pairs to a fresh forest and returns its thread/pred arrays —
