@@ -54,6 +54,8 @@ SIGNATURES = {
     "gne_pot_set_all": (C.c_int, [_vp, _f64p]),
     "gne_pot_get_all": (C.c_int, [_vp, _f64p]),
     "gne_price_lv": (C.c_int, [_vp, _f64p, _i64p, _i64p, C.c_int64, C.POINTER(C.c_int)]),
+    "gne_price_lv_begin": (C.c_int, [_vp, _f64p, _i64p, C.POINTER(C.c_int)]),
+    "gne_price_lv_at": (C.c_int, [_vp, C.c_int64, _i64p]),
     "gne_price_qs": (C.c_int, [_vp, C.c_int64, C.c_int64, _i64p, _f64p, _i64p, _i64p, _i64p]),
     "gne_price_violators": (C.c_int, [_vp, C.c_double, _i64p, _i64p, _f64p, C.c_int64]),
     "gne_price_first": (C.c_int, [_vp, _i64p]),
@@ -90,6 +92,8 @@ SIGNATURES = {
     "gne_solver_progress_rows": (C.c_int64, [_vp]),
     "gne_forest_replay": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, C.c_int64, _i32p, _i32p,
                                     _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "gne_host_replay": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_int, C.c_int,
+                                  C.c_int64, C.c_int64, _i32p, _i32p, _i64p, _f64p, _f64p, _f64p]),
     "gne_merge_lv_shards": (C.c_int, [C.c_int, _f64p, C.POINTER(C.c_int), _i64p, _i64p, _f64p, C.c_int64,
                                       _f64p, _i64p, _i64p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gne_generate_instance": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
@@ -221,6 +225,16 @@ class Device:
         buf = np.empty(cap, np.int64)
         _ck(lib.gne_price_lv(self.h, C.byref(largest), C.byref(count), _p(buf, _i64p), cap, C.byref(anyv)), "gne_price_lv")
         return largest.value, buf[:count.value].copy(), bool(anyv.value)
+
+    def price_lv_begin(self):
+        largest = C.c_double(0); count = C.c_int64(0); anyv = C.c_int(0)
+        _ck(lib.gne_price_lv_begin(self.h, C.byref(largest), C.byref(count), C.byref(anyv)), "gne_price_lv_begin")
+        return largest.value, count.value, bool(anyv.value)
+
+    def price_lv_at(self, index):
+        pos = C.c_int64(0)
+        _ck(lib.gne_price_lv_at(self.h, index, C.byref(pos)), "gne_price_lv_at")
+        return pos.value
 
     def price_qs(self, cursor, want):
         bp = C.c_int64(0); bv = C.c_double(0); nc = C.c_int64(0); sc = C.c_int64(0); vi = C.c_int64(0)
@@ -400,6 +414,18 @@ def forest_replay(n, tail, head, supply, e, l):
     _ck(lib.gne_forest_replay(n, len(tail), _p(tail, _i32p), _p(head, _i32p), _p(supply, _f64p), len(e), _p(e, _i32p),
                               _p(l, _i32p), *[_p(a, _i32p) for a in arrs]), "gne_forest_replay")
     return dict(zip(("tree", "pred", "predArc", "depth", "thread"), arrs))
+
+
+def host_replay(n, tail, head, ub, cost, mult, supply, big_m, draws, p1, e, l, sparse_flows=True):
+    """Host-only replay of a recorded solve (no GPU): returns (first mismatching pivot or -1, flows, potentials, objective)."""
+    tail = _arr(tail, np.int32); head = _arr(head, np.int32); ub = _arr(ub, np.float64); cost = _arr(cost, np.float64)
+    mult = _arr(mult, np.float64); supply = _arr(supply, np.float64); e = _arr(e, np.int32); l = _arr(l, np.int32)
+    mm = C.c_int64(0); obj = C.c_double(0)
+    flows = np.empty(len(tail) + n); pots = np.empty(n)
+    _ck(lib.gne_host_replay(n, len(tail), _p(tail, _i32p), _p(head, _i32p), _p(ub, _f64p), _p(cost, _f64p), _p(mult, _f64p),
+                            _p(supply, _f64p), big_m, draws, 1 if sparse_flows else 0, p1, len(e), _p(e, _i32p), _p(l, _i32p),
+                            C.byref(mm), _p(flows, _f64p), _p(pots, _f64p), C.byref(obj)), "gne_host_replay")
+    return mm.value, flows, pots, obj.value
 
 
 def merge_lv_shards(maxima, anys, counts, list_pos, list_viol, stride, cap=1 << 16):

@@ -186,7 +186,7 @@ extern "C" int gne_forest_replay(int n, int64_t m, const int32_t *tailIn, const 
     for (int64_t a = 0; a < m; ++a) { tail[a] = tailIn[a]; head[a] = headIn[a]; }
     for (int i = 0; i < n; ++i) { tail[m + i] = i; head[m + i] = i; }
     Forest f;
-    f.init(n, tail.data(), head.data());
+    f.init(n, M, tail.data(), head.data());
     std::vector<uint8_t> basic((size_t) M, 0);
     for (int i = 0; i < n; ++i) { if (f.insertArc((int32_t) (m + i))) return GNE_ERR_TREE; basic[m + i] = 1; }
     f.updateTrees();
@@ -200,6 +200,28 @@ extern "C" int gne_forest_replay(int n, int64_t m, const int32_t *tailIn, const 
         f.updateTrees();
     }
     for (int i = 0; i < n; ++i) { tree[i] = f.treeSlot[i]; pred[i] = f.pred[i]; predArc[i] = f.predArc[i]; depth[i] = f.depth[i]; thread[i] = f.thread[i]; }
+    return GNE_OK;
+}
+
+// host-only replay of a whole recorded solve: flows, ratio test, leaving arc, basis update and
+// the root-relative potential sweep run exactly as in gne_solver_solve, without any device
+extern "C" int gne_host_replay(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub, const double *cost,
+                               const double *mult, const double *supply, double bigM, int drawsPerPricing, int sparseFlows,
+                               int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
+                               int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective)
+{
+    Graph g;
+    int rc = g.initializeFromArrays(n, m, tail, head, ub, cost, mult, supply, bigM);
+    if (rc) return rc;
+    GenNetEq s;
+    rc = s.initialize(&g, 0, 0);
+    if (rc) return rc;
+    s.setSparseFlows(sparseFlows != 0);
+    rc = s.replayTrace(drawsPerPricing, phase1Pivots, totalPivots, e, l, mismatch);
+    if (rc) return rc;
+    if (flowsOut) s.getFlows(flowsOut);
+    if (potentialsOut) s.getHostPotentials(potentialsOut);
+    if (objective) *objective = s.getFlowCost();
     return GNE_OK;
 }
 

@@ -104,6 +104,13 @@ struct gne_dev {
     LvTiles lv{};
     int32_t *tileCnt = nullptr;
     int64_t *tileOff = nullptr;
+    double *tileVmin = nullptr, *tileVmax = nullptr;
+    SelectResult *selRes = nullptr;                // mapped pinned
+    // state of the last gne_price_lv_begin
+    int lvMode = 0;                                // 0: list on the host, 1: all compacted candidates, on the device
+    std::vector<int64_t> lvList;
+    int64_t lvCount = 0;
+    double lvFloor = 0.0;
     QsTiles qs{};
     int GQ = 0;
     unsigned long long *firstPos = nullptr;
@@ -210,6 +217,8 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     CK(cudaMalloc(&d->lv.tileMax, 8 * (size_t) d->G)); CK(cudaMalloc(&d->lv.tileCnt, 4 * (size_t) d->G));
     CK(cudaMalloc(&d->lv.candOff, 4 * (size_t) d->G * CAND_K)); CK(cudaMalloc(&d->lv.candViol, 8 * (size_t) d->G * CAND_K));
     CK(cudaMalloc(&d->tileCnt, 4 * (size_t) d->G)); CK(cudaMalloc(&d->tileOff, 8 * ((size_t) d->G + 1)));
+    CK(cudaMalloc(&d->tileVmin, 8 * (size_t) d->G)); CK(cudaMalloc(&d->tileVmax, 8 * (size_t) d->G));
+    CK(cudaHostAlloc(&d->selRes, sizeof(SelectResult), cudaHostAllocMapped));
     d->GQ = (int) ((d->localCap + QTILE - 1) / QTILE) + 1;
     CK(cudaMalloc(&d->qs.cnt, 4 * (size_t) d->GQ)); CK(cudaMalloc(&d->qs.bestV, 8 * (size_t) d->GQ)); CK(cudaMalloc(&d->qs.bestJ, 8 * (size_t) d->GQ));
     CK(cudaMalloc(&d->firstPos, 8));
@@ -231,10 +240,10 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
-                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->stageDev, d->outPos, d->outViol,
+                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->stageDev, d->outPos, d->outViol,
                     d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv };
     for (void *p : dev) if (p) cudaFree(p);
-    void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost };
+    void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes };
     for (void *p : host) if (p) cudaFreeHost(p);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
@@ -520,26 +529,40 @@ extern "C" int gne_pot_get_all(gne_dev *d, double *pi)
 // ------------------------------------------------------------------------------------------
 static int sharded_gather_lists(gne_dev *d, int64_t localCount, std::vector<int64_t> &pos, std::vector<double> &viol);
 
-static int viol_compact_device(gne_dev *d, double threshold, int64_t *total)
+// ordered compaction of this shard's violators with |rc| >= threshold, in two steps: count per tile
+// + offsets (+ min / max of the qualifying values in hostScalar[4..5]), then the write pass
+static int viol_count_device(gne_dev *d, double threshold, int64_t *total, double *vmin, double *vmax)
 {
-    // ordered compaction of this shard's violators with |rc| >= threshold into d->outPos/outViol
     const int G = tiles_for(d);
     *total = 0;
+    if (vmin) { *vmin = 0.0; *vmax = 0.0; }
     if (G == 0) return GNE_OK;
     NbView nb = view_of(d);
-    k_viol_count<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, threshold, d->tileCnt);
-    k_scan_tiles<<<1, 1024, 0, d->stream>>>(d->tileCnt, d->tileOff, G, d->hostScalar);
+    k_viol_count<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, threshold, d->tileCnt, d->tileVmin, d->tileVmax);
+    k_scan_tiles<<<1, 1024, 0, d->stream>>>(d->tileCnt, d->tileOff, G, d->hostScalar, d->tileVmin, d->tileVmax, (double *) (d->hostScalar + 4));
     CK(cudaGetLastError());
     d->launches += 2;
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     *total = d->hostScalar[0];
-    d->d2hBytes += 8;
-    if (*total == 0) return GNE_OK;
-    int rc = ensure_out(d, *total); if (rc) return rc;
-    k_viol_write<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, threshold, d->tileOff, d->outPos, d->outViol, d->outCap);
+    if (vmin) { *vmin = ((double *) (d->hostScalar + 4))[0]; *vmax = ((double *) (d->hostScalar + 4))[1]; }
+    d->d2hBytes += 24;
+    return GNE_OK;
+}
+
+static int viol_write_device(gne_dev *d, double threshold, int64_t total)
+{
+    if (total == 0) return GNE_OK;
+    int rc = ensure_out(d, total); if (rc) return rc;
+    k_viol_write<<<tiles_for(d), TILE_THREADS, 0, d->stream>>>(view_of(d), d->pi, threshold, d->tileOff, d->outPos, d->outViol, d->outCap);
     CK(cudaGetLastError());
     ++d->launches;
     return GNE_OK;
+}
+
+static int viol_compact_device(gne_dev *d, double threshold, int64_t *total)
+{
+    int rc = viol_count_device(d, threshold, total, nullptr, nullptr); if (rc) return rc;
+    return viol_write_device(d, threshold, *total);
 }
 
 // The sequential rule of checkVarForOffending (gnePivotRules.cpp:431-452) on a candidate list
@@ -584,36 +607,59 @@ static int price_lv_local(gne_dev *d)
     return GNE_OK;
 }
 
-extern "C" int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count, int64_t *listPos, int64_t cap, int *any)
+// Long tie lists (hundreds of thousands of arcs share the maximal |rc| once a large zero-potential
+// tree exists in Phase I) are never moved to the host: when every compacted candidate lies within
+// tol/2 of the others, the sequential rule keeps all of them (no element can clear, every element
+// is pushed) and leaves L = the last one's value, so only the count, the picked element and the last
+// element are needed — k_viol_select resolves them from the tile offsets.
+static const int64_t LV_DEVICE_LIST_MIN = 4096;
+
+extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t *count, int *any)
 {
     CK(cudaSetDevice(d->device));
     int rc = gne_dev_flush(d); if (rc) return rc;
     rc = price_lv_local(d); if (rc) return rc;
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
-
-    std::vector<int64_t> list;
+    d->lvMode = 0; d->lvList.clear(); d->lvCount = 0;
     double L = -1.0;
     int anyV = 0;
-    bool ok = false;
-    if (d->nranks == 1) {
+    if (d->nranks > 1) {
+        rc = gne_dev_price_lv_sharded(d, &L, d->lvList, &anyV); if (rc) return rc;
+    } else {
         const LvResult *r = d->lvRes;
         d->d2hBytes += 24 + 16 * std::min<int64_t>(r->count, LV_LIST_CAP);
         anyV = r->any;
-        if (!anyV) { ok = true; }
-        else if (!r->overflow) {
-            const double floorV = r->maxViol - LV_BAND;
-            ok = replay_band_rule(r->pos, r->viol, r->count, floorV, false, list, &L);
-        }
-        double thr = anyV ? r->maxViol : 0.0;
-        // fallback: widen the band until the replay is provably exact (rare: long runs of near-ties)
+        bool ok = !anyV;
+        if (anyV && !r->overflow) ok = replay_band_rule(r->pos, r->viol, r->count, r->maxViol - LV_BAND, false, d->lvList, &L);
+        const double M = anyV ? r->maxViol : 0.0;
+        // fallback: widen the band until the replay is provably exact
         double width = 16.0 * GNE_ROUNDOFF_TOLERANCE;
         while (!ok) {
-            double floorV = thr - width;
+            double floorV = M - width;
             bool zero = false;
             if (!(floorV > 0.0) || width > 1.0e-6) { floorV = 0.0; zero = true; }
             int64_t total = 0;
-            rc = viol_compact_device(d, floorV, &total); if (rc) return rc;
+            double vmin = 0.0, vmax = 0.0;
+            rc = viol_count_device(d, floorV, &total, &vmin, &vmax); if (rc) return rc;
+            const double tol = GNE_ROUNDOFF_TOLERANCE;
+            const double below = zero ? 0.0 : nextafter(floorV, 0.0);
+            // within tol/4 of each other and small enough that rounding (ulp <= tol/16) cannot tip a comparison
+            const bool tight = (vmax == vmin) || ((vmax - vmin) <= 0.25 * tol && vmax < 16.0);
+            const bool sealed = zero || ((below < vmin - tol) && (vmin > below + tol));
+            if (total >= LV_DEVICE_LIST_MIN && tight && sealed) {
+                // every candidate stays in the list; resolve the last one (the final running value)
+                k_viol_select<<<2, TILE_THREADS, 0, d->stream>>>(view_of(d), d->pi, floorV, d->tileOff, tiles_for(d), 0, d->selRes);
+                CK(cudaGetLastError());
+                ++d->launches;
+                CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+                d->d2hBytes += sizeof(SelectResult);
+                L = d->selRes->lastViol;
+                d->lvMode = 1; d->lvCount = total; d->lvFloor = floorV;
+                ok = true;
+                break;
+            }
+            rc = viol_write_device(d, floorV, total); if (rc) return rc;
             std::vector<int64_t> hp((size_t) total);
             std::vector<double> hv((size_t) total);
             if (total > 0) {
@@ -622,17 +668,44 @@ extern "C" int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count
                 CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
                 d->d2hBytes += 16 * total;
             }
-            ok = replay_band_rule(hp.data(), hv.data(), total, floorV, zero, list, &L);
+            ok = replay_band_rule(hp.data(), hv.data(), total, floorV, zero, d->lvList, &L);
             width *= 64.0;
         }
-    } else {
-        rc = gne_dev_price_lv_sharded(d, &L, list, &anyV); if (rc) return rc;
     }
+    if (d->lvMode == 0) d->lvCount = (int64_t) d->lvList.size();
     *largestViolation = L;
     *any = anyV;
-    *count = (int64_t) list.size();
-    if ((int64_t) list.size() > cap) { gne_set_error("gne_price_lv: list of %lld exceeds cap", (long long) list.size()); return GNE_ERR_CAPACITY; }
-    if (!list.empty()) memcpy(listPos, list.data(), 8 * list.size());
+    *count = d->lvCount;
+    return GNE_OK;
+}
+
+extern "C" int gne_price_lv_at(gne_dev *d, int64_t index, int64_t *pos)
+{
+    if (index < 0 || index >= d->lvCount) { gne_set_error("gne_price_lv_at: index out of range"); return GNE_ERR_ARG; }
+    if (d->lvMode == 0) { *pos = d->lvList[(size_t) index]; return GNE_OK; }
+    CK(cudaSetDevice(d->device));
+    k_viol_select<<<1, TILE_THREADS, 0, d->stream>>>(view_of(d), d->pi, d->lvFloor, d->tileOff, tiles_for(d), index, d->selRes);
+    CK(cudaGetLastError());
+    ++d->launches;
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    d->d2hBytes += 16;
+    *pos = d->selRes->pos;
+    return GNE_OK;
+}
+
+extern "C" int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count, int64_t *listPos, int64_t cap, int *any)
+{
+    int rc = gne_price_lv_begin(d, largestViolation, count, any); if (rc) return rc;
+    if (*count > cap) { gne_set_error("gne_price_lv: list of %lld exceeds cap", (long long) *count); return GNE_ERR_CAPACITY; }
+    if (d->lvMode == 0) {
+        if (*count > 0) memcpy(listPos, d->lvList.data(), 8 * (size_t) *count);
+        return GNE_OK;
+    }
+    // the list lives on the device (every compacted candidate is a member): materialise it
+    rc = viol_write_device(d, d->lvFloor, d->lvCount); if (rc) return rc;
+    CK(cudaMemcpyAsync(listPos, d->outPos, 8 * (size_t) d->lvCount, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    d->d2hBytes += 8 * d->lvCount;
     return GNE_OK;
 }
 

@@ -5,11 +5,13 @@
 
 namespace gneb200 {
 
-void Forest::init(int nNodes, const int32_t *tailIn, const int32_t *headIn)
+void Forest::init(int nNodes, int64_t numVars, const int32_t *tailIn, const int32_t *headIn)
 {
     n = nNodes; tail = tailIn; head = headIn;
     treeSlot.assign(n, -1); pred.assign(n, -1); predArc.assign(n, -1); depth.assign(n, -1); thread.assign(n, -1);
-    trees.clear(); freeSlots.clear(); stale.clear(); changed.clear(); changedFlag.clear();
+    threadPos.assign(n, -1); nodeFlag.assign(n, 1);
+    arcPos.assign((size_t) numVars, -1);
+    trees.clear(); freeSlots.clear(); stale.clear(); changed.clear(); changedFlag.clear(); dirtyNodes.clear();
     trees.reserve((size_t) n + 8);
     pool.clear(); pool.reserve((size_t) 4 * n + 64);
     incStart.assign(n, 0); incLen.assign(n, 0); incCap.assign(n, 0);
@@ -42,7 +44,7 @@ int32_t Forest::newTree(int8_t type, int32_t rootNode)
     if (rootNode >= 0) {
         t.root = rootNode;
         t.nodes.push_back(rootNode);
-        treeSlot[rootNode] = slot;
+        setSlot(rootNode, slot);
     }
     return slot;
 }
@@ -51,9 +53,12 @@ void Forest::freeTree(int32_t slot)
 {
     Tree &t = trees[slot];
     t.type = TREE_FREE; t.root = -1; t.extraArc = -1;
-    std::vector<int32_t>().swap(t.nodes);
-    std::vector<int32_t>().swap(t.arcs);
-    std::vector<int32_t>().swap(t.threads);
+    t.nodes.clear(); t.arcs.clear(); t.threads.clear();
+    if (t.nodes.capacity() > 4096) {                    // give big buffers back, keep small ones for reuse
+        std::vector<int32_t>().swap(t.nodes);
+        std::vector<int32_t>().swap(t.arcs);
+        std::vector<int32_t>().swap(t.threads);
+    }
     freeSlots.push_back(slot);
 }
 
@@ -61,10 +66,10 @@ void Forest::freeTree(int32_t slot)
 void Forest::relabel(int32_t slot, int32_t newSlot)
 {
     const std::vector<int32_t> &nd = trees[slot].nodes;
-    for (size_t k = 0; k < nd.size(); ++k) treeSlot[nd[k]] = newSlot;
+    for (size_t k = 0; k < nd.size(); ++k) setSlot(nd[k], newSlot);
 }
 
-void Forest::incPush(int32_t node, int32_t arc)
+void Forest::incPush(int32_t node, int32_t arc, int32_t nbr)
 {
     if (incLen[node] == incCap[node]) {
         const int32_t nc = std::max(4, 2 * incCap[node]);
@@ -73,12 +78,13 @@ void Forest::incPush(int32_t node, int32_t arc)
         for (int32_t k = 0; k < incLen[node]; ++k) pool[ns + k] = pool[incStart[node] + k];
         incStart[node] = ns; incCap[node] = nc;
     }
-    pool[incStart[node] + incLen[node]++] = arc;
+    Inc e; e.arc = arc; e.nbr = nbr;
+    pool[incStart[node] + incLen[node]++] = e;
 }
 
 void Forest::compactPool()
 {
-    std::vector<int32_t> np;
+    std::vector<Inc> np;
     np.reserve((size_t) 4 * n + 64);
     for (int i = 0; i < n; ++i) {
         if (incLen[i] == 0) { incStart[i] = 0; incCap[i] = 0; continue; }
@@ -99,10 +105,11 @@ void Forest::mergeInto(int32_t tX, int32_t tII, int32_t av)
     Tree &x = trees[tX];
     Tree &y = trees[tII];
     x.nodes.insert(x.nodes.end(), y.nodes.begin(), y.nodes.end());
-    x.arcs.insert(x.arcs.end(), y.arcs.begin(), y.arcs.end());
+    for (size_t k = 0; k < y.arcs.size(); ++k) { arcPos[y.arcs[k]] = (int32_t) x.arcs.size(); x.arcs.push_back(y.arcs[k]); }
+    arcPos[av] = (int32_t) x.arcs.size();
     x.arcs.push_back(av);
-    incPush(tail[av], av);
-    incPush(head[av], av);
+    incPush(tail[av], av, head[av]);
+    incPush(head[av], av, tail[av]);
     touch(tX);
     freeTree(tII);
 }
@@ -112,12 +119,13 @@ void Forest::expandWithArc(int32_t t, int32_t av)
 {
     const int32_t u = tail[av], v = head[av];
     Tree &x = trees[t];
-    if (treeSlot[u] != t) { x.nodes.push_back(u); treeSlot[u] = t; }
-    else if (treeSlot[v] != t) { x.nodes.push_back(v); treeSlot[v] = t; }
+    if (treeSlot[u] != t) { x.nodes.push_back(u); setSlot(u, t); }
+    else if (treeSlot[v] != t) { x.nodes.push_back(v); setSlot(v, t); }
     if (u != v) {
+        arcPos[av] = (int32_t) x.arcs.size();
         x.arcs.push_back(av);
-        incPush(u, av);
-        incPush(v, av);
+        incPush(u, av, v);
+        incPush(v, av, u);
     } else {
         x.extraArc = av;
     }
@@ -153,15 +161,24 @@ int Forest::insertArc(int32_t av)
 
 // Tree::splitTree (trees.cpp:502-566): DFS from the old root over the incident lists; the part
 // reached through the removed arc becomes `bottom`, the rest `top`.  The discovery order IS the
-// new arcsInTree / nodesInTree order.
-void Forest::split(int32_t tOld, int32_t removedArc, int32_t *topOut, int32_t *bottomOut)
+// new arcsInTree / nodesInTree order.  `top` keeps the old tree's slot (the reference creates two
+// fresh trees; tree ids have no observable effect), so its nodes keep their slot.
+int32_t Forest::split(int32_t tOld, int32_t removedArc)
 {
-    const int32_t top = newTree(TREE_II, -1);
-    const int32_t bottom = newTree(TREE_II, -1);
+    const int32_t bottom = newTree(TREE_II, -1);         // may grow `trees`: take references afterwards
+    const int32_t top = tOld;
+    const int32_t oldRoot = trees[top].root;
+    {
+        Tree &o = trees[top];
+        oldNodes.clear(); oldArcs.clear();
+        oldNodes.swap(o.nodes); oldArcs.swap(o.arcs);    // recycle capacity; contents are rebuilt below
+        o.type = TREE_II; o.extraArc = -1; o.root = -1;
+        touch(top);
+    }
     int32_t cur = top;
     std::vector<int32_t> &curStack = stackA, &prevStack = stackB;
     curStack.clear(); prevStack.clear();
-    curStack.push_back(trees[tOld].root);
+    curStack.push_back(oldRoot);
     prevStack.push_back(-1);
     while (!curStack.empty()) {
         int32_t node = curStack.back(); curStack.pop_back();
@@ -172,19 +189,19 @@ void Forest::split(int32_t tOld, int32_t removedArc, int32_t *topOut, int32_t *b
         }
         const int32_t prev = prevStack.back(); prevStack.pop_back();
         Tree &tc = trees[cur];
-        treeSlot[node] = cur;
+        setSlot(node, cur);
         if (tc.nodes.empty()) tc.root = node;
         tc.nodes.push_back(node);
-        int32_t removedInd = -1;
+        int32_t removedInd = -1, removedNbr = -1;
         const int64_t base = incStart[node];
         const int32_t len = incLen[node];
         for (int32_t k = 0; k < len; ++k) {
-            const int32_t a = pool[base + k];
-            if (a == removedArc) { removedInd = k; continue; }
-            const int32_t next = (tail[a] == node) ? head[a] : tail[a];
-            if (next != prev) {
-                tc.arcs.push_back(a);
-                curStack.push_back(next);
+            const Inc e = pool[base + k];
+            if (e.arc == removedArc) { removedInd = k; removedNbr = e.nbr; continue; }
+            if (e.nbr != prev) {
+                arcPos[e.arc] = (int32_t) tc.arcs.size();
+                tc.arcs.push_back(e.arc);
+                curStack.push_back(e.nbr);
                 prevStack.push_back(node);
             }
         }
@@ -192,15 +209,15 @@ void Forest::split(int32_t tOld, int32_t removedArc, int32_t *topOut, int32_t *b
             pool[base + removedInd] = pool[base + len - 1];
             --incLen[node];
             if (prev > -2) {
-                const int32_t next = (tail[removedArc] == node) ? head[removedArc] : tail[removedArc];
                 curStack.push_back(-1);
-                curStack.push_back(next);
+                curStack.push_back(removedNbr);
                 prevStack.push_back(-2);
                 cur = bottom;
             }
         }
     }
-    *topOut = top; *bottomOut = bottom;
+    if (trees[bottom].nodes.empty()) { freeTree(bottom); return -1; }
+    return bottom;
 }
 
 // Tree::removeFromTrees (trees.cpp:456-499)
@@ -214,50 +231,51 @@ int Forest::removeArc(int32_t av)
         trees[t].extraArc = -1;
         markChanged(t);
     } else {
-        int32_t top, bottom;
-        split(t, av, &top, &bottom);
-        int rc = 0;
-        if (trees[t].type == TREE_I) rc = insertArc(trees[t].extraArc);
-        freeTree(t);
-        if (rc) return rc;
+        const int8_t oldType = trees[t].type;
+        const int32_t oldExtra = trees[t].extraArc;
+        split(t, av);
+        if (oldType == TREE_I) { const int rc = insertArc(oldExtra); if (rc) return rc; }
     }
     return 0;
 }
 
-// Tree::initializeTreeIndices (trees.cpp:597-644)
+// Tree::initializeTreeIndices (trees.cpp:597-644) + the dirty-node list
 void Forest::reindex(int32_t slot)
 {
     Tree &t = trees[slot];
-    std::vector<int32_t> &nodeStack = stackA, &arcStack = stackB;
-    nodeStack.clear(); arcStack.clear();
+    std::vector<int32_t> &nodeStack = stackA, &arcStack = stackB, &predStack = stackC;
+    nodeStack.clear(); arcStack.clear(); predStack.clear();
     t.threads.clear();
     t.threads.reserve(t.nodes.size());
     nodeStack.push_back(t.root);
+    arcStack.push_back(-1);
+    predStack.push_back(-1);
+    int32_t last = -1;
     while (!nodeStack.empty()) {
         const int32_t cur = nodeStack.back(); nodeStack.pop_back();
-        int32_t predNode = -1;
-        if (!t.threads.empty()) {
-            const int32_t pa = arcStack.back(); arcStack.pop_back();
-            predNode = (cur == tail[pa]) ? head[pa] : tail[pa];
-            depth[cur] = depth[predNode] + 1;
-            predArc[cur] = pa;
-            thread[t.threads.back()] = cur;
-        } else {
-            depth[cur] = 0;
-            predArc[cur] = -1;
-        }
+        const int32_t pa = arcStack.back(); arcStack.pop_back();
+        const int32_t predNode = predStack.back(); predStack.pop_back();
+        const bool dirty = (nodeFlag[cur] & 1) || pred[cur] != predNode || predArc[cur] != pa ||
+                           (predNode >= 0 && (nodeFlag[predNode] & 2));
+        nodeFlag[cur] = dirty ? 2 : 0;
+        if (dirty) dirtyNodes.push_back(cur);
+        depth[cur] = (predNode >= 0) ? depth[predNode] + 1 : 0;
+        predArc[cur] = pa;
         pred[cur] = predNode;
+        if (last >= 0) thread[last] = cur;
+        last = cur;
+        threadPos[cur] = (int32_t) t.threads.size();
         t.threads.push_back(cur);
         const int64_t base = incStart[cur];
         for (int32_t k = incLen[cur] - 1; k >= 0; --k) {
-            const int32_t a = pool[base + k];
-            const int32_t x = tail[a], y = head[a];
-            if (x == predNode || y == predNode) continue;
-            nodeStack.push_back(cur == x ? y : x);
-            arcStack.push_back(a);
+            const Inc e = pool[base + k];
+            if (e.nbr == predNode) continue;
+            nodeStack.push_back(e.nbr);
+            arcStack.push_back(e.arc);
+            predStack.push_back(cur);
         }
     }
-    thread[t.threads.back()] = t.root;
+    thread[last] = t.root;
 }
 
 // Tree::updateTrees (trees.cpp:572-591), restricted to the trees touched since the last call

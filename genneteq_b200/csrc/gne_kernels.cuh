@@ -288,25 +288,49 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
 // Ordered compaction of every violator with |rc| >= threshold: count per tile, scan, write.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE_THREADS)
-k_viol_count(NbView nb, const double *__restrict__ pi, double threshold, int32_t *tileCnt)
+k_viol_count(NbView nb, const double *__restrict__ pi, double threshold, int32_t *tileCnt, double *tileVmin, double *tileVmax)
 {
     double v[ITEMS];
     tile_violations(nb, pi, (int64_t) blockIdx.x * TILE, v);
     int c = 0;
+    double lo = 1.0e308, hi = -1.0;
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) c += (v[k] > 0.0 && v[k] >= threshold);
+    for (int k = 0; k < ITEMS; ++k) if (v[k] > 0.0 && v[k] >= threshold) { ++c; lo = fmin(lo, v[k]); hi = fmax(hi, v[k]); }
     int total;
     block_excl_scan(c, &total);
-    if (threadIdx.x == 0) tileCnt[blockIdx.x] = total;
+    __shared__ double sLo[TILE_THREADS / 32], sHi[TILE_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { sLo[threadIdx.x >> 5] = lo; sHi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < TILE_THREADS / 32; ++i) { lo = fmin(lo, sLo[i]); hi = fmax(hi, sHi[i]); }
+        tileCnt[blockIdx.x] = total; tileVmin[blockIdx.x] = lo; tileVmax[blockIdx.x] = hi;
+    }
 }
 
 // exclusive scan of G tile counts by one CTA; total -> *totalOut (mapped host) and tileOff[G]
 __global__ void __launch_bounds__(1024)
-k_scan_tiles(const int32_t *tileCnt, int64_t *tileOff, int G, int64_t *totalOut)
+k_scan_tiles(const int32_t *tileCnt, int64_t *tileOff, int G, int64_t *totalOut,
+             const double *tileVmin, const double *tileVmax, double *minMaxOut)
 {
     __shared__ int64_t sWarp[32];
     __shared__ int64_t sCarry;
+    __shared__ double sLo[32], sHi[32];
     if (threadIdx.x == 0) sCarry = 0;
+    {
+        double lo = 1.0e308, hi = -1.0;
+        for (int g = threadIdx.x; g < G; g += 1024) { lo = fmin(lo, tileVmin[g]); hi = fmax(hi, tileVmax[g]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if ((threadIdx.x & 31) == 0) { sLo[threadIdx.x >> 5] = lo; sHi[threadIdx.x >> 5] = hi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < 32; ++i) { lo = fmin(lo, sLo[i]); hi = fmax(hi, sHi[i]); }
+            minMaxOut[0] = lo; minMaxOut[1] = hi;
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int base = 0; base < G; base += 1024) {
@@ -352,6 +376,42 @@ k_viol_write(NbView nb, const double *__restrict__ pi, double threshold, const i
             }
         }
         base += total;
+    }
+}
+
+// Position and violation of the idx-th (and of the last) violator >= threshold in position order,
+// from the tile offsets of the compaction — the pick of a long tie list without moving the list.
+struct SelectResult { int64_t pos; double viol; int64_t lastPos; double lastViol; };
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_viol_select(NbView nb, const double *__restrict__ pi, double threshold, const int64_t *tileOff, int G,
+              int64_t idx, SelectResult *out)
+{
+    // blockIdx 0 resolves idx, blockIdx 1 the last element
+    const int64_t total = tileOff[G];
+    const int64_t want = (blockIdx.x == 0) ? idx : total - 1;
+    __shared__ int sTile;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = G - 1;                          // last tile with tileOff[g] <= want
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tileOff[mid] <= want) lo = mid; else hi = mid - 1; }
+        sTile = lo;
+    }
+    __syncthreads();
+    const int g = sTile;
+    const int64_t tileBase = (int64_t) g * TILE;
+    double v[ITEMS];
+    tile_violations(nb, pi, tileBase, v);
+    int64_t base = tileOff[g];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int f = (v[k] > 0.0 && v[k] >= threshold) ? 1 : 0;
+        int tot;
+        const int off = block_excl_scan(f, &tot);
+        if (f && base + off == want) {
+            const int64_t p = nb.lo + tileBase + tile_offset(threadIdx.x, k);
+            if (blockIdx.x == 0) { out->pos = p; out->viol = v[k]; } else { out->lastPos = p; out->lastViol = v[k]; }
+        }
+        base += tot;
     }
 }
 

@@ -66,7 +66,8 @@ int GenNetEq::initialize(Graph *g, int /*initType: ignored by the reference too*
     supA0.assign(numNodes, 0.0); supA1.assign(numNodes, 0.0);
     potA0.assign(numNodes, 0.0); potA1.assign(numNodes, 0.0); potSlot.assign(numNodes, -1);
     thetaOfSlot.clear();
-    forest.init(numNodes, tail.data(), head.data());
+    forest.init(numNodes, M, tail.data(), head.data());
+    nodeMark.assign(numNodes, 0);
     setBarc.clear(); setNBarc.clear();
     setBarc.reserve(numNodes); setNBarc.reserve(m + 1);
     for (int64_t a = 0; a < M; ++a) {                   // formInitialBFS, gneInit.cpp:174-185
@@ -265,61 +266,167 @@ void GenNetEq::computeFlowsPivotingTI(int32_t eav, int32_t tU, int32_t tV)      
     if (tU != tV) computeFlowsTypeI(tV);
 }
 
+// computeFlowsTypeI for a pivot, restricted to where it is non-zero.  During a pivot every supply is
+// zero except at the entering arc's ends and at the extra arc's ends (theta coefficient), so e(j)
+// and x(predArc(j)) are +-0 off the root paths of those (at most four) nodes; +-0 neither changes a
+// sum nor blocks (genneteq.h:399-402).  Nodes on the paths are processed in reverse thread order
+// (the order of the reference's sweep, hence the same order of additions at every junction), the
+// arcs with a flow change are ratio-tested in arcsInTree order.  Values are identical to the full
+// sweep; only the sign of exact zeros can differ.
+void GenNetEq::computeFlowsSparse(int32_t slot, const int32_t *starts, int nStarts, std::vector<int32_t> &activeArcs)
+{
+    const Tree &t = forest.tree(slot);
+    const int32_t ex = t.extraArc;
+    const int32_t alpha = tail[ex], beta = head[ex];
+    const double muAB = mult[ex];
+    flowA0[ex] = 0.0; flowA1[ex] = 1.0;
+    supA1[alpha] -= 1.0;
+    supA1[beta] += muAB;
+    const int32_t h = t.root;
+    activeNodes.clear();
+    int32_t st[6];
+    int ns = 0;
+    for (int k = 0; k < nStarts; ++k) st[ns++] = starts[k];
+    st[ns++] = alpha; st[ns++] = beta;
+    for (int k = 0; k < ns; ++k) {
+        int32_t v = st[k];
+        while (v >= 0 && !nodeMark[v]) { nodeMark[v] = 1; activeNodes.push_back(v); v = forest.pred[v]; }
+    }
+    const std::vector<int32_t> &tp = forest.threadPos;
+    std::sort(activeNodes.begin(), activeNodes.end(), [&tp](int32_t a, int32_t b) { return tp[a] > tp[b]; });
+    activeArcs.clear();
+    for (size_t q = 0; q < activeNodes.size(); ++q) {
+        const int32_t j = activeNodes[q];
+        nodeMark[j] = 0;
+        if (j == h) continue;
+        const int32_t a = forest.predArc[j];
+        const double mu = mult[a];
+        if (tail[a] == j) {
+            const int32_t i = head[a];
+            flowA0[a] = supA0[j]; flowA1[a] = supA1[j];
+            supA0[i] += supA0[j] * mu;
+            supA1[i] += supA1[j] * mu;
+        } else {
+            const int32_t i = tail[a];
+            flowA0[a] = supA0[j] / (-1.0 * mu);
+            flowA1[a] = supA1[j] / (-1.0 * mu);
+            supA0[i] += supA0[j] / mu;
+            supA1[i] += supA1[j] / mu;
+        }
+        supA0[j] = 0.0; supA1[j] = 0.0;
+        activeArcs.push_back(a);
+    }
+    const double theta = (-1.0 * supA0[h]) / supA1[h];
+    supA0[h] = 0.0; supA1[h] = 0.0;
+    const std::vector<int32_t> &ap = forest.arcPos;
+    std::sort(activeArcs.begin(), activeArcs.end(), [&ap](int32_t a, int32_t b) { return ap[a] < ap[b]; });
+    for (size_t k = 0; k < activeArcs.size(); ++k) {
+        const int32_t a = activeArcs[k];
+        const double p = flowA1[a] * theta;
+        deltaFlow[a] = flowA0[a] + p;
+        flowA0[a] = 0.0; flowA1[a] = 0.0;
+        checkVarForBlocking(a);
+    }
+    const double p = flowA1[ex] * theta;
+    deltaFlow[ex] = flowA0[ex] + p;
+    flowA0[ex] = 0.0; flowA1[ex] = 0.0;
+    checkVarForBlocking(ex);
+}
+
+void GenNetEq::applyFlowSparse(int32_t slot, const std::vector<int32_t> &activeArcs)   // gnePivot.cpp:79-91 on the changed arcs
+{
+    for (size_t k = 0; k < activeArcs.size(); ++k) {
+        const int32_t a = activeArcs[k];
+        const double d = delta * deltaFlow[a];
+        flow[a] += d;
+        flowCost += cost[a] * d;
+        deltaFlow[a] = 0.0;
+    }
+    const int32_t ex = forest.tree(slot).extraArc;
+    const double d = delta * deltaFlow[ex];
+    flow[ex] += d;
+    flowCost += cost[ex] * d;
+    deltaFlow[ex] = 0.0;
+}
+
 // ------------------------------------------------------------------------------------------
 // gnePotential.cpp: the root-relative sweep on the host for the trees a pivot touched, the
 // finalize on the device.  Untouched trees keep (a0, a1, theta), hence pi, bit for bit.
 // ------------------------------------------------------------------------------------------
+// One node of computePotentialsInTermsOfRoot (gnePotential.cpp:89-108): (a0, a1) of j from its
+// predecessor; records the node for upload when (a0, a1, slot) differ from what the device holds.
+inline bool GenNetEq::relabelNode(int32_t j, int32_t slot)
+{
+    const int32_t i = forest.pred[j];
+    double a0, a1;
+    if (i < 0) {                                        // root: pi_h = theta  (:78-82)
+        a0 = 0.0; a1 = 1.0;
+    } else {
+        const int32_t a = forest.predArc[j];
+        const double c0 = cost[a], mu = mult[a];
+        if (tail[a] == i) {                             // pi(j) = (pi(i) - c_ij) / mu_ij
+            a0 = (potA0[i] - c0) / mu;
+            a1 = potA1[i] / mu;
+        } else {                                        // pi(j) = mu_ji pi(i) + c_ji
+            const double p = mu * potA0[i];
+            a0 = p + c0;
+            a1 = mu * potA1[i];
+        }
+    }
+    if (memcmp(&potA0[j], &a0, 8) != 0 || memcmp(&potA1[j], &a1, 8) != 0 || potSlot[j] != slot) {
+        potA0[j] = a0; potA1[j] = a1; potSlot[j] = slot;
+        upNode.push_back(j); upA0.push_back(a0); upA1.push_back(a1); upSlot.push_back(slot);
+        return true;
+    }
+    return false;
+}
+
 int GenNetEq::computePotentials()
 {
     upNode.clear(); upSlot.clear(); upA0.clear(); upA1.clear(); upThetaSlot.clear(); upTheta.clear(); upFinal.clear();
     bool finalizeAll = false;
     if ((int) thetaOfSlot.size() < forest.numSlots()) thetaOfSlot.resize(forest.numSlots(), 0.0);
+    if (allPotDirty) {
+        // costs changed (phase start): every tree is swept in thread order
+        for (size_t c = 0; c < forest.changed.size(); ++c) {
+            const Tree &t = forest.tree(forest.changed[c]);
+            if (t.type == TREE_FREE) continue;
+            for (size_t q = 0; q < t.threads.size(); ++q) relabelNode(t.threads[q], forest.changed[c]);
+        }
+        finalizeAll = true;
+    } else {
+        // only the nodes whose root path or tree changed in the last re-threading, parents first
+        for (size_t q = 0; q < forest.dirtyNodes.size(); ++q) {
+            const int32_t j = forest.dirtyNodes[q];
+            if (relabelNode(j, forest.treeOf(j))) upFinal.push_back(j);
+        }
+    }
+    forest.dirtyNodes.clear();
     for (size_t c = 0; c < forest.changed.size(); ++c) {
         const int32_t slot = forest.changed[c];
         forest.changedFlag[slot] = 0;
         const Tree &t = forest.tree(slot);
         if (t.type == TREE_FREE) continue;
         if (t.type != TREE_I) { gne_set_error("type II tree at computePotentials (equal-flow sets are out of scope)"); return GNE_ERR_UNSUPPORTED; }
-        // computePotentialsInTermsOfRoot, gnePotential.cpp:64-110
-        const int32_t h = t.threads[0];
-        double a0 = 0.0, a1 = 1.0;
-        if (potA0[h] != a0 || potA1[h] != a1 || potSlot[h] != slot) {
-            potA0[h] = a0; potA1[h] = a1; potSlot[h] = slot;
-            upNode.push_back(h); upA0.push_back(a0); upA1.push_back(a1); upSlot.push_back(slot);
-        }
-        for (size_t q = 1; q < t.threads.size(); ++q) {
-            const int32_t j = t.threads[q];
-            const int32_t i = forest.pred[j];
-            const int32_t a = forest.predArc[j];
-            const double c0 = cost[a], mu = mult[a];
-            if (tail[a] == i) {
-                a0 = (potA0[i] - c0) / mu;
-                a1 = potA1[i] / mu;
-            } else {
-                const double p = mu * potA0[i];
-                a0 = p + c0;
-                a1 = mu * potA1[i];
-            }
-            if (memcmp(&potA0[j], &a0, 8) != 0 || memcmp(&potA1[j], &a1, 8) != 0 || potSlot[j] != slot) {
-                potA0[j] = a0; potA1[j] = a1; potSlot[j] = slot;
-                upNode.push_back(j); upA0.push_back(a0); upA1.push_back(a1); upSlot.push_back(slot);
-            }
-        }
         // theta, gnePotential.cpp:116-124
         const int32_t ex = t.extraArc;
         const int32_t alpha = tail[ex], beta = head[ex];
         const double pb0 = mult[ex] * potA0[beta];
         const double pb1 = mult[ex] * potA1[beta];
         const double theta = ((cost[ex] - potA0[alpha]) + pb0) / (potA1[alpha] - pb1);
-        thetaOfSlot[slot] = theta;
-        upThetaSlot.push_back(slot); upTheta.push_back(theta);
-        // every node of a touched tree gets a new pi (theta multiplies a1 != 0)
-        if (!finalizeAll) {
-            if (upFinal.size() + t.nodes.size() > (size_t) numNodes / 4) finalizeAll = true;
-            else upFinal.insert(upFinal.end(), t.nodes.begin(), t.nodes.end());
+        if (allPotDirty || memcmp(&thetaOfSlot[slot], &theta, 8) != 0) {
+            thetaOfSlot[slot] = theta;
+            upThetaSlot.push_back(slot); upTheta.push_back(theta);
+            // every node of the tree gets a new pi (theta multiplies a1 != 0)
+            if (!finalizeAll) {
+                if (upFinal.size() + t.nodes.size() > (size_t) numNodes / 4) finalizeAll = true;
+                else upFinal.insert(upFinal.end(), t.nodes.begin(), t.nodes.end());
+            }
         }
     }
     forest.changed.clear();
+    allPotDirty = false;
+    if (!dev) return GNE_OK;                            // host-only replay
     // one call: queued setNBarc writes + dirty records + thetas + finalize (gnePotential.cpp:127-135)
     return gne_pot_update_fused(dev, (int64_t) upNode.size(), upNode.data(), upA0.data(), upA1.data(), upSlot.data(),
                                 (int64_t) upThetaSlot.size(), upThetaSlot.data(), upTheta.data(),
@@ -367,21 +474,18 @@ int GenNetEq::getVarWithLargestViolation(int32_t *out)            // :133-157 (L
     double largest = -1.0;
     int64_t cnt = 0;
     int any = 0;
-    if (listPos.size() < 4096) { listPos.resize(4096); listViol.resize(4096); }
-    int rc = gne_price_lv(dev, &largest, &cnt, listPos.data(), (int64_t) listPos.size(), &any);
-    if (rc == GNE_ERR_CAPACITY) {
-        listPos.resize((size_t) cnt + 1024); listViol.resize((size_t) cnt + 1024);
-        rc = gne_price_lv(dev, &largest, &cnt, listPos.data(), (int64_t) listPos.size(), &any);
-    }
-    if (rc) return rc;
+    // the device leaves offendingVars where it is (it can be hundreds of thousands long in Phase I);
+    // only its length and the member drand48 picks are needed here
+    GNE_TRY(gne_price_lv_begin(dev, &largest, &cnt, &any));
     arcsPriced += (double) setNBarc.size();
     float ms = 0; gne_dev_last_kernel_ms(dev, &ms); kernelMs += ms;
     if (any) isOptimal = false;
-    offendingVars.resize((size_t) cnt);
-    for (int64_t i = 0; i < cnt; ++i) offendingVars[i] = setNBarc[listPos[i]];
     lastViolation = largest;
-    if (offendingVars.empty()) { *out = -1; return GNE_OK; }
-    *out = offendingVars[(size_t) (drand48() * offendingVars.size())];       // selectRandomOffendingVar == true
+    if (cnt == 0) { *out = -1; return GNE_OK; }
+    const int64_t idx = (int64_t) (size_t) (drand48() * (size_t) cnt);       // selectRandomOffendingVar == true (:152-153)
+    int64_t pos = -1;
+    GNE_TRY(gne_price_lv_at(dev, idx, &pos));
+    *out = setNBarc[pos];
     return GNE_OK;
 }
 
@@ -563,11 +667,33 @@ int GenNetEq::pivotTI(int32_t eav)                                // :63-119
     const int32_t tV = forest.treeOf(head[eav]);
     delta = DBL_MAX;
     const double f0 = wallNow();
-    computeFlowsPivotingTI(eav, tU, tV);
-    identifyLeavingVar();
-    if (lVar == -1) return GNE_OK;
-    applyTreeFlow(tU);
-    if (tU != tV) applyTreeFlow(tV);
+    if (!sparseFlows) {
+        computeFlowsPivotingTI(eav, tU, tV);
+        identifyLeavingVar();
+        if (lVar == -1) return GNE_OK;
+        applyTreeFlow(tU);
+        if (tU != tV) applyTreeFlow(tV);
+    } else {
+        // supply injection of computeFlowsPivotingTI (gneFlow.cpp:160-174), then the sparse sweeps
+        if (setLoc[eav] == L_var) {
+            if (tail[eav] == head[eav]) supA0[tail[eav]] = -1.0 * (1.0 - mult[eav]);
+            else { supA0[tail[eav]] = -1.0; supA0[head[eav]] = mult[eav]; }
+        } else {
+            if (tail[eav] == head[eav]) supA0[tail[eav]] = (1.0 - mult[eav]);
+            else { supA0[tail[eav]] = 1.0; supA0[head[eav]] = -1.0 * mult[eav]; }
+        }
+        int32_t starts[2] = { tail[eav], head[eav] };
+        if (tU == tV) {
+            computeFlowsSparse(tU, starts, 2, activeArcsU);
+        } else {
+            computeFlowsSparse(tU, starts, 1, activeArcsU);
+            computeFlowsSparse(tV, starts + 1, 1, activeArcsV);
+        }
+        identifyLeavingVar();
+        if (lVar == -1) return GNE_OK;
+        applyFlowSparse(tU, activeArcsU);
+        if (tU != tV) applyFlowSparse(tV, activeArcsV);
+    }
     if (setLoc[eav] == L_var) { flow[eav] = delta; flowCost += cost[eav] * delta; }
     else { flow[eav] = UB[eav] - delta; flowCost -= cost[eav] * delta; }
     secsFlows += wallNow() - f0;
@@ -657,6 +783,10 @@ int GenNetEq::setVariableCosts()                                  // :304-323 + 
 {
     if (presolve) for (int64_t i = 0; i < M; ++i) cost[i] = isArtificial[i] ? 1.0 : 0.0;
     else for (int64_t i = 0; i < M; ++i) cost[i] = actualCost[i];
+    // every tree's potentials depend on the costs
+    for (int s = 0; s < forest.numSlots(); ++s) if (forest.tree(s).type != TREE_FREE) forest.markChanged(s);
+    allPotDirty = true;
+    if (hostOnly) return GNE_OK;
     if (!dev) {
         uint8_t none[128] = { 0 };
         GNE_TRY(setComm(none, 0, 1));
@@ -675,8 +805,43 @@ int GenNetEq::setVariableCosts()                                  // :304-323 + 
         GNE_TRY(gne_dev_flush(dev));
         GNE_TRY(gne_nb_set_costs(dev, (int64_t) N, c.data()));
     }
-    // every tree's potentials depend on the costs
-    for (int s = 0; s < forest.numSlots(); ++s) if (forest.tree(s).type != TREE_FREE) forest.markChanged(s);
+    return GNE_OK;
+}
+
+// Host-only replay of a recorded pivot sequence (no device, no pricing): the entering arc of each
+// pivot comes from the trace, flows / ratio test / leaving arc / basis update run as in solve(),
+// and the leaving arc is compared with the trace.  `draws` = drand48 calls the pricing rule makes
+// per successful call (LV 1, QS/CL/FV 0, SAA/SAE 2, RV/RWV/RLV 1); the cycling override draws once.
+int GenNetEq::replayTrace(int draws, int64_t p1, int64_t total, const int32_t *e, const int32_t *l, int64_t *mismatch)
+{
+    hostOnly = true;
+    *mismatch = -1;
+    int64_t k = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        const bool pre = (phase == 0);
+        const bool pIwasInfeasible = pre ? false : isInfeasible;
+        initializeStats(pre);
+        GNE_TRY(setVariableCosts());
+        if (!presolve && pIwasInfeasible) { isInfeasible = true; break; }
+        computeFlows(0);
+        const int64_t end = pre ? p1 : total;
+        for (; k < end; ++k) {
+            if ((loopIter % 1000) == 0) computeFlows(2);
+            GNE_TRY(computePotentials());
+            if (cyclingDetected) (void) drand48();
+            else for (int d = 0; d < draws; ++d) (void) drand48();
+            eVar = e[k];
+            GNE_TRY(pivot());
+            if (lVar != l[k]) { *mismatch = k; return GNE_OK; }
+            ++loopIter; ++pivots;
+        }
+        // the terminating pricing call of the phase: the simulated-annealing rules draw before they
+        // price (gnePivotRules.cpp:369,386), every other rule draws only when it found a violator
+        if (!cyclingDetected && draws == 2) (void) drand48();
+        computeFlows(0);
+        if (presolve) checkFeasibility();
+        GNE_TRY(computePotentials());
+    }
     return GNE_OK;
 }
 

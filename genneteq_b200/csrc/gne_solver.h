@@ -82,6 +82,9 @@ class GenNetEq {
     void getStates(int32_t *out) const;
     const Forest &getForest() const { return forest; }
     void getCounters(double *out12) const;
+    int replayTrace(int draws, int64_t p1, int64_t total, const int32_t *e, const int32_t *l, int64_t *mismatch);
+    void setSparseFlows(bool on) { sparseFlows = on; }
+    void getHostPotentials(double *out) const { for (int i = 0; i < numNodes; ++i) out[i] = hostPotential(i); }
     // wall-clock window over pivots [start, start + len) of the next solve() call, taken inside the loop
     // with the device synchronised at both edges; out = {seconds, 12 counters at start, 12 at end}
     void setWindow(int64_t start, int64_t len) { winStart = start; winLen = len; winT0 = winT1 = 0.0; }
@@ -142,6 +145,9 @@ class GenNetEq {
     std::vector<int32_t> upNode, upSlot, upThetaSlot, upFinal;
     std::vector<double> upA0, upA1, upTheta;
     int status = GNE_OK;
+    bool allPotDirty = true, hostOnly = false, sparseFlows = true;
+    std::vector<uint8_t> nodeMark;
+    std::vector<int32_t> activeNodes, activeArcsU, activeArcsV;
 
     // ---- trace / counters
     int32_t *traceE = nullptr, *traceL = nullptr;
@@ -168,6 +174,9 @@ class GenNetEq {
     void computeFlowsTypeI(int32_t slot);
 
     int computePotentials();
+    bool relabelNode(int32_t j, int32_t slot);
+    void computeFlowsSparse(int32_t slot, const int32_t *starts, int nStarts, std::vector<int32_t> &activeArcs);
+    void applyFlowSparse(int32_t slot, const std::vector<int32_t> &activeArcs);
     int computeReducedCosts(bool includeBasicVars);
     int verifyOptimality();
 

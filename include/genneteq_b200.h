@@ -97,6 +97,11 @@ int gne_pot_get_all(gne_dev *d, double *pi);
  * rule leaves behind: the final running largestViolation and offendingVars (as positions,
  * in list order).  *count = list length; GNE_ERR_CAPACITY if > cap.  *any = !isOptimal.      */
 int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count, int64_t *listPos, int64_t cap, int *any);
+/* the same in two steps, for callers that only need the list's length and one member (the reference
+ * picks offendingVars[drand48() * size], gnePivotRules.cpp:152-153): begin runs the pass and keeps
+ * the list inside the handle — long exact-tie lists stay on the device — at(i) returns member i.   */
+int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t *count, int *any);
+int gne_price_lv_at(gne_dev *d, int64_t index, int64_t *pos);
 
 /* quickSelect's arc loop (gnePivotRules.cpp:742-756): scan from `cursor` (wrapping) until `want`
  * violators were seen or the list is exhausted; best = first strictly-largest |rc|.
@@ -188,6 +193,15 @@ int64_t gne_solver_progress_rows(const gne_solver *s);
 int gne_forest_replay(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *supply,
                       int64_t pivots, const int32_t *e, const int32_t *l,
                       int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread);
+
+/* Host-only replay of a recorded solve (no device, no pricing): entering arcs come from the trace,
+ * flows / ratio test / leaving arc / basis update / potential sweep run as in gne_solver_solve and
+ * the leaving arc is compared with the trace (*mismatch = first differing pivot or -1).
+ * drawsPerPricing = drand48 calls the rule makes per call (LV 1, QS/CL/FV 0, SAA/SAE 2, RV/RWV/RLV 1). */
+int gne_host_replay(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub, const double *cost,
+                    const double *mult, const double *supply, double bigM, int drawsPerPricing, int sparseFlows,
+                    int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
+                    int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective);
 
 /* merge of per-shard LV records (what every rank does after the all-gather); host-only.
  * maxima[r], any[r], counts[r], and lists (pos, viol) concatenated rank-major with stride cap. */

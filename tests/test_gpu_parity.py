@@ -86,6 +86,11 @@ def test_price_lv_matches_sequential_rule(gne, n, N, mode):
     assert anyv == oany
     assert L == oL
     assert np.array_equal(lst, olst)
+    # two-step form: length + single members (long exact-tie lists never leave the device)
+    bL, bcount, bany = d.price_lv_begin()
+    assert (bL, bcount, bany) == (oL, len(olst), oany)
+    for idx in sorted(set([0, bcount // 3, bcount // 2, bcount - 1])) if bcount else []:
+        assert d.price_lv_at(idx) == int(olst[idx])
     # reduced costs themselves, bit for bit
     rc = d.reduced_costs()
     orc = np.zeros(N)

@@ -135,3 +135,38 @@ def test_generator_is_deterministic_sorted_and_connected(gne):
     assert np.all(np.round(a["cost"] * 1e6) / 1e6 == a["cost"])
     c = gne.generate_instance(500, 6000, 100, "lossy")
     assert not np.array_equal(a["head"], c["head"])
+
+
+DRAWS = dict(LV=1, LVW=1, LVA=1, LVE=1, FV=0, RV=1, RWV=1, RLV=1, RLVW=1, CL=0, CLW=0, SAA=2, SAE=2, QS=0, QSW=0)
+
+
+@pytest.mark.parametrize("sparse", [True, False])
+@pytest.mark.parametrize("name,rules", [("c1_wide_s7", ["LV", "QS", "CL"]),
+                                        ("s_wide_s3", ["LV", "FV", "RV", "RWV", "RLV", "CL", "SAA", "QS"]),
+                                        ("s_lossy_s4", ["LV", "FV", "RWV", "CL", "SAE", "QS"]),
+                                        ("s_pow2_s5", ["LV", "FV", "RV", "RLV", "CL", "QS"]),
+                                        ("s_near1_s6", ["LV", "FV", "RWV", "CL", "SAA", "QS"])])
+def test_host_pivot_logic_replays_reference_traces(gne, name, rules, sparse):
+    """Flows, ratio test, leaving arc, basis update and the potential sweep of the product's host engine,
+    driven by the reference's entering arcs (no pricing, no GPU): every leaving arc, the final flows, the
+    final potentials and the objective must equal the reference's."""
+    from test_oracle_pinned import load
+    z, inst = load(name)
+    for rn in rules:
+        e = z[rn + "_e"]; l = z[rn + "_l"]
+        p1 = int(z[rn + "_p"][0])
+        mm, flows, pots, obj = gne.host_replay(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply,
+                                               inst.big_m, DRAWS[rn], p1, e, l, sparse_flows=sparse)
+        assert mm == -1, (rn, "leaving arc differs at pivot", mm)
+        assert obj == float(z[rn + "_objective"]), rn
+        assert np.array_equal(flows, z[rn + "_flows"]), rn
+        assert np.array_equal(pots, z[rn + "_potentials"]), rn
+
+
+def test_host_replay_lossy3k(gne):
+    from test_oracle_pinned import load
+    z, inst = load("lossy3k_s5")
+    mm, flows, pots, obj = gne.host_replay(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply,
+                                           inst.big_m, 1, int(z["LV_p"][0]), z["LV_e"], z["LV_l"])
+    assert mm == -1
+    assert obj == float(z["LV_objective"])

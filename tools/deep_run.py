@@ -17,10 +17,10 @@ it, fin = s.solve(True, total)
 P = s.progress()
 names = gne.Solver.COUNTERS
 print(desc, "| pivots", it, "finished", fin)
-print("%8s %9s %9s %9s %9s %9s %9s %9s %10s" % ("pivot", "ms/pivot", "pricing", "potent.", "pivot", "trees", "flows", "kern ms", "maxtree"))
+print("%8s %9s %9s %9s %9s %9s %9s %9s %10s %8s %10s %10s" % ("pivot", "ms/pivot", "pricing", "potent.", "pivot", "trees", "flows", "kern ms", "maxtree", "launch", "h2d B", "d2h B"))
 for i in range(1, len(P)):
     d = P[i] - P[i - 1]
     c = dict(zip(names, d[1:13]))
     k = c["pivots"]
-    print("%8d %9.4f %9.4f %9.4f %9.4f %9.4f %9.4f %9.4f %10d" % (P[i][10], 1e3 * d[0] / k, 1e3 * c["pricing_s"] / k, 1e3 * c["potentials_s"] / k,
-          1e3 * c["pivot_s"] / k, 1e3 * c["trees_s"] / k, 1e3 * c["flows_s"] / k, c["kernel_ms"] / k, P[i][13]))
+    print("%8d %9.4f %9.4f %9.4f %9.4f %9.4f %9.4f %9.4f %10d %8.2f %10.0f %10.0f" % (P[i][10], 1e3 * d[0] / k, 1e3 * c["pricing_s"] / k, 1e3 * c["potentials_s"] / k,
+          1e3 * c["pivot_s"] / k, 1e3 * c["trees_s"] / k, 1e3 * c["flows_s"] / k, c["kernel_ms"] / k, P[i][13], c["launches"] / k, c["h2d_bytes"] / k, c["d2h_bytes"] / k))
