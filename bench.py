@@ -48,6 +48,9 @@ WORKLOADS = {
     "c5-lv": (200_000, 100_000_000, 51, "lossy", "LV", "configs[4]: 200k nodes / 100M arcs, lossy gains, seed 51, Dantzig rule (LV)"),
     "c1-lv": (1_000, 10_000, 7, "wide", "LV", "configs[0] size: 1k nodes / 10k arcs (native generator), Dantzig rule (LV)"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of k_price_lv_tiles per launch, from the committed
+# `ncu --set full` capture (profiles/r1_price_lv_tiles_ncu_summary.txt): 509.1 MB + 4.9 MB on c3-lv, N = 1
+NCU_TRAFFIC_BYTES = {("c3-lv", 1): 514.0e6}
 METRIC = "arcs priced/sec"
 UNIT = "arcs/s"
 
@@ -317,7 +320,7 @@ def b200_arm(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_price_lv_tiles", "kernel_ms": tiles_ms,
+                     "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world)), "kernel": "k_price_lv_tiles", "kernel_ms": tiles_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
     }
     if world == 1 and not args.no_cpu_baseline:
