@@ -268,6 +268,8 @@ def b200_arm(args):
     s.solve(True, W + args.steps)
     barrier()
     dbg("e2e window done")
+    xmode = {0: "none (single GPU)", 1: "ncclAllGather", 2: "NVLink peer-mailbox stores from the exchange kernel (CUDA IPC)"}[
+        gne.lib.gne_comm_mode(s.device().h)]
     e2e_s, c0, c1 = s.window()
     if e2e_s <= 0:
         raise SystemExit("bench.py: the solve ended before the timed window completed")
@@ -311,7 +313,8 @@ def b200_arm(args):
         "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule,
                    "l2": ("L2 flushed between timed steps (320 MB write)" if flush else
                           "inputs larger than L2 (%.0f MB streamed per pass per GPU)" % (alg_bytes / 1e6)),
-                   "sharding": "contiguous position ranges over %d GPU(s), NCCL all-gather of the per-shard record" % world},
+                   "sharding": "contiguous position ranges over %d GPU(s); per-pivot exchange of the per-shard record: %s" % (
+                       world, xmode)},
         "e2e": {"value": arcs_e2e / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(pivots, 1),
                 "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / max(pivots, 1),

@@ -68,6 +68,7 @@ SIGNATURES = {
     "gne_comm_unique_id": (C.c_int, [_u8p]),
     "gne_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
     "gne_comm_destroy": (C.c_int, [_vp]),
+    "gne_comm_mode": (C.c_int, [_vp]),
     "gne_solver_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_double]),
     "gne_solver_create_from_col": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_char_p]),
     "gne_solver_destroy": (C.c_int, [_vp]),

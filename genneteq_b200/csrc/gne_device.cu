@@ -137,6 +137,12 @@ struct gne_dev {
     void *comm = nullptr;
     int rank = 0, nranks = 1;
     void *gatherSend = nullptr, *gatherRecv = nullptr, *gatherHost = nullptr;
+    LvResult *lvResDev = nullptr;                  // sharded mode: the local LV result stays on the device
+    struct Mailbox *mailbox = nullptr;             // this rank's receive buffer, written by the peers over NVLink
+    struct Mailbox **peersDev = nullptr;           // device array [nranks] of every rank's mailbox (IPC-mapped)
+    void *peerPtr[8] = { nullptr };
+    bool p2p = false;
+    unsigned long long xseq = 0;
     int64_t *cntDev = nullptr;                     // [1 + nranks] counts exchange
     char *xSend = nullptr, *xRecv = nullptr;       // variable-length list exchange, grown on demand
     size_t xSendBytes = 0, xRecvBytes = 0;
@@ -237,11 +243,13 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     if (!d) return GNE_OK;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
+    for (int p = 0; p < 8; ++p) if (d->peerPtr[p] && d->peerPtr[p] != (void *) d->mailbox) cudaIpcCloseMemHandle(d->peerPtr[p]);
+    if (d->mailbox) cudaFree(d->mailbox);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
                     d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->stageDev, d->outPos, d->outViol,
-                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv };
+                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev };
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes };
     for (void *p : host) if (p) cudaFreeHost(p);
@@ -600,7 +608,7 @@ static int price_lv_local(gne_dev *d)
         k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv);
         ++d->launches;
     }
-    k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->lvRes);
+    k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->nranks > 1 ? d->lvResDev : d->lvRes);
     ++d->launches;
     CK(cudaEventRecord(d->ev1, d->stream));
     CK(cudaGetLastError());
@@ -900,7 +908,7 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
         CK(cudaEventRecord(d->ev0, d->stream));
         if (G > 0) { k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); ++d->launches; }
         CK(cudaEventRecord(d->ev1, d->stream));
-        k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->lvRes);
+        k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->nranks > 1 ? d->lvResDev : d->lvRes);
         ++d->launches;
         if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
         CK(cudaEventRecord(d->ev3, d->stream));
@@ -918,21 +926,70 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
 // ------------------------------------------------------------------------------------------
 namespace {
 constexpr int SHARD_LIST = 48;                          // candidates carried per rank in the record
-struct ShardRecord {                                    // 16 + 48*16 = 784 bytes
+constexpr int MAX_RANKS = 8;
+struct ShardRecord {                                    // 24 + 48*16 = 792 bytes
     double maxViol;
     int32_t any, overflow;
     int64_t count;
     int64_t pos[SHARD_LIST];
     double viol[SHARD_LIST];
 };
-__global__ void k_pack_record(const LvResult *res, ShardRecord *rec)
+} // namespace
+// Receive buffer of one rank: slot r is written by rank r's k_lv_exchange with NVLink stores.
+// Two generations (seq parity) so that a fast rank's next record never overwrites one being read.
+struct Mailbox {
+    ShardRecord rec[2][MAX_RANKS];
+    unsigned long long flag[2][MAX_RANKS];
+};
+namespace {
+__device__ __forceinline__ void pack_record(const LvResult *res, ShardRecord *rec, int t)
 {
-    const int t = threadIdx.x;
     if (t == 0) {
         rec->maxViol = res->maxViol; rec->any = res->any; rec->count = res->count;
         rec->overflow = (res->overflow || res->count > SHARD_LIST) ? 1 : 0;
     }
     if (t < SHARD_LIST && t < res->count) { rec->pos[t] = res->pos[t]; rec->viol[t] = res->viol[t]; }
+}
+__global__ void k_pack_record(const LvResult *res, ShardRecord *rec) { pack_record(res, rec, threadIdx.x); }
+
+// The exchange step fused with the reduction's tail: one CTA packs the shard's record, stores it
+// into every rank's mailbox (peer memory over NVLink), publishes the sequence flag, waits for the
+// peers' flags and copies all records to mapped pinned host memory.  No NCCL call, no copy engine.
+__global__ void __launch_bounds__(128)
+k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, ShardRecord *hostOut)
+{
+    __shared__ ShardRecord rec;
+    const int t = threadIdx.x;
+    pack_record(res, &rec, t);
+    __syncthreads();
+    const int b = (int) (seq & 1ull);
+    constexpr int WORDS = (int) (sizeof(ShardRecord) / 8);
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&rec);
+    for (int p = 0; p < nranks; ++p) {
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&peers[p]->rec[b][rank]);
+        for (int w = t; w < WORDS; w += blockDim.x) dst[w] = src[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < nranks) *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[b][rank]) = seq;
+    Mailbox *self = peers[rank];
+    __shared__ int sTimeout;
+    if (t == 0) sTimeout = 0;
+    __syncthreads();
+    if (t < nranks) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned long long *>(&self->flag[b][t]) != seq) {
+            if (clock64() - t0 > 8000000000ll) { sTimeout = 1; break; }      // ~4 s: a peer died; fail instead of hanging
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    for (int r = 0; r < nranks; ++r) {
+        const volatile unsigned long long *in = reinterpret_cast<const volatile unsigned long long *>(&self->rec[b][r]);
+        unsigned long long *out = reinterpret_cast<unsigned long long *>(&hostOut[r]);
+        for (int w = t; w < WORDS; w += blockDim.x) out[w] = in[w];
+    }
+    if (sTimeout && t == 0) hostOut[0].count = -2;
 }
 } // namespace
 
@@ -952,12 +1009,51 @@ extern "C" int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nr
     memcpy(uid.b, id, 128);
     int r = g_nccl.CommInitRank(&d->comm, nranks, uid, rank);
     if (r != 0) { gne_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
+    if (nranks > MAX_RANKS) { gne_set_error("gne_comm_init: at most %d ranks", MAX_RANKS); return GNE_ERR_ARG; }
     d->rank = rank; d->nranks = nranks;
     CK(cudaMalloc(&d->gatherSend, sizeof(ShardRecord)));
     CK(cudaMalloc(&d->gatherRecv, sizeof(ShardRecord) * (size_t) nranks));
-    CK(cudaHostAlloc(&d->gatherHost, sizeof(ShardRecord) * (size_t) nranks, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&d->gatherHost, sizeof(ShardRecord) * (size_t) nranks, cudaHostAllocMapped));
+    CK(cudaMalloc(&d->lvResDev, sizeof(LvResult)));
+    CK(cudaMemset(d->lvResDev, 0, sizeof(LvResult)));
+    // peer mailboxes: exchange CUDA IPC handles through the NCCL communicator, map every peer's buffer
+    CK(cudaMalloc(&d->mailbox, sizeof(Mailbox)));
+    CK(cudaMemset(d->mailbox, 0, sizeof(Mailbox)));
+    const char *force = getenv("GNE_EXCHANGE");
+    int okLocal = (force && !strcmp(force, "nccl")) ? 0 : 1;
+    cudaIpcMemHandle_t mine;
+    if (okLocal && cudaIpcGetMemHandle(&mine, d->mailbox) != cudaSuccess) { cudaGetLastError(); okLocal = 0; memset(&mine, 0, sizeof(mine)); }
+    char *hx = nullptr;                                  // [send 64][recv 64 * R] on the device
+    CK(cudaMalloc(&hx, 64 * (size_t) (nranks + 1)));
+    CK(cudaMemcpyAsync(hx, &mine, 64, cudaMemcpyHostToDevice, d->stream));
+    r = g_nccl.AllGather(hx, hx + 64, 64, /*ncclChar*/ 0, d->comm, d->stream);
+    if (r != 0) { gne_set_error("ncclAllGather(ipc handles) failed"); return GNE_ERR_COMM; }
+    std::vector<cudaIpcMemHandle_t> handles((size_t) nranks);
+    CK(cudaMemcpyAsync(handles.data(), hx + 64, 64 * (size_t) nranks, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    for (int p = 0; p < nranks && okLocal; ++p) {
+        if (p == rank) { d->peerPtr[p] = d->mailbox; continue; }
+        if (cudaIpcOpenMemHandle(&d->peerPtr[p], handles[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); d->peerPtr[p] = nullptr; okLocal = 0; }
+    }
+    // every rank must take the same path: all-gather the per-rank verdicts
+    unsigned char flagByte = (unsigned char) okLocal;
+    CK(cudaMemcpyAsync(hx, &flagByte, 1, cudaMemcpyHostToDevice, d->stream));
+    r = g_nccl.AllGather(hx, hx + 64, 1, /*ncclChar*/ 0, d->comm, d->stream);
+    if (r != 0) { gne_set_error("ncclAllGather(ipc verdicts) failed"); return GNE_ERR_COMM; }
+    unsigned char verdicts[MAX_RANKS] = { 0 };
+    CK(cudaMemcpyAsync(verdicts, hx + 64, (size_t) nranks, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    cudaFree(hx);
+    d->p2p = true;
+    for (int p = 0; p < nranks; ++p) if (!verdicts[p]) d->p2p = false;
+    if (d->p2p) {
+        CK(cudaMalloc(&d->peersDev, sizeof(Mailbox *) * MAX_RANKS));
+        CK(cudaMemcpy(d->peersDev, d->peerPtr, sizeof(void *) * (size_t) nranks, cudaMemcpyHostToDevice));
+    }
     return GNE_OK;
 }
+
+extern "C" int gne_comm_mode(gne_dev *d) { return d->nranks <= 1 ? 0 : (d->p2p ? 2 : 1); }
 
 extern "C" int gne_comm_destroy(gne_dev *d)
 {
@@ -968,8 +1064,15 @@ extern "C" int gne_comm_destroy(gne_dev *d)
 
 static int launch_shard_exchange(gne_dev *d)
 {
-    // pack this shard's record, all-gather over NCCL (NVLink), copy the gathered records to pinned host
-    k_pack_record<<<1, 64, 0, d->stream>>>(d->lvRes, (ShardRecord *) d->gatherSend);
+    if (d->p2p) {
+        // fused pack + NVLink peer stores + flag wait + copy to mapped pinned host: one kernel
+        k_lv_exchange<<<1, 128, 0, d->stream>>>(d->lvResDev, d->peersDev, d->rank, d->nranks, ++d->xseq, (ShardRecord *) d->gatherHost);
+        CK(cudaGetLastError());
+        ++d->launches;
+        return GNE_OK;
+    }
+    // fallback: pack this shard's record, all-gather over NCCL, copy the gathered records to pinned host
+    k_pack_record<<<1, 64, 0, d->stream>>>(d->lvResDev, (ShardRecord *) d->gatherSend);
     ++d->launches;
     int r = g_nccl.AllGather(d->gatherSend, d->gatherRecv, sizeof(ShardRecord), /*ncclChar*/ 0, d->comm, d->stream);
     if (r != 0) { gne_set_error("ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
@@ -1024,6 +1127,7 @@ int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->d2hBytes += sizeof(ShardRecord) * (int64_t) d->nranks;
     const ShardRecord *rec = (const ShardRecord *) d->gatherHost;
+    if (rec[0].count == -2) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
     std::vector<double> maxima(d->nranks);
     std::vector<int> anys(d->nranks);
     std::vector<int64_t> counts(d->nranks), pos((size_t) d->nranks * SHARD_LIST);

@@ -142,6 +142,10 @@ const char *gne_bench_variant_name(int i);
 int gne_comm_unique_id(uint8_t id[128]);
 int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nranks);
 int gne_comm_destroy(gne_dev *d);
+/* 0 = single GPU, 1 = per-pivot exchange through ncclAllGather, 2 = through peer mailboxes (NVLink stores from
+ * the exchange kernel into CUDA-IPC-mapped buffers; default when IPC mapping succeeds on every rank;
+ * GNE_EXCHANGE=nccl forces 1)                                                                      */
+int gne_comm_mode(gne_dev *d);
 
 /* =============================== layer 2: solver mirror =============================== */
 typedef struct gne_solver gne_solver;

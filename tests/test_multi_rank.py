@@ -8,8 +8,9 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def launch(mode, nproc, out, port):
+def launch(mode, nproc, out, port, extra_env=None):
     env = dict(os.environ)
+    env.update(extra_env or {})
     env["MASTER_ADDR"] = "127.0.0.1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py"), mode, out]
@@ -24,8 +25,13 @@ def test_sharded_lv_exchange_host_logic_gloo(tmp_path):
 
 
 @pytest.mark.gpu
-def test_sharded_solve_two_gpus_nccl(tmp_path):
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_solve_two_gpus(tmp_path, exchange):
+    """Full C1 solve sharded over 2 GPUs: the per-pivot exchange through NVLink peer mailboxes (default)
+    and through ncclAllGather (GNE_EXCHANGE=nccl) must both reproduce the reference's pivot trace."""
     import genneteq_b200 as gne
     if gne.cuda_device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    assert launch("nccl", 2, str(tmp_path / "nccl.txt"), 29612) == "OK"
+    env = {"GNE_EXCHANGE": "nccl"} if exchange == "nccl" else {}
+    port = 29612 if exchange == "p2p" else 29613
+    assert launch("nccl", 2, str(tmp_path / (exchange + ".txt")), port, env) == "OK"
