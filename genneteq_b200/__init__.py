@@ -57,6 +57,7 @@ SIGNATURES = {
     "gne_price_lv_begin": (C.c_int, [_vp, _f64p, _i64p, C.POINTER(C.c_int)]),
     "gne_price_lv_at": (C.c_int, [_vp, C.c_int64, _i64p]),
     "gne_price_qs": (C.c_int, [_vp, C.c_int64, C.c_int64, _i64p, _f64p, _i64p, _i64p, _i64p]),
+    "gne_price_scan_list": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _f64p, C.c_int64, _i64p, _i64p]),
     "gne_price_violators": (C.c_int, [_vp, C.c_double, _i64p, _i64p, _f64p, C.c_int64]),
     "gne_price_first": (C.c_int, [_vp, _i64p]),
     "gne_reduced_costs": (C.c_int, [_vp, C.c_int64, C.c_int64, _f64p]),
@@ -242,6 +243,14 @@ class Device:
         _ck(lib.gne_price_qs(self.h, cursor, want, C.byref(bp), C.byref(bv), C.byref(nc), C.byref(sc), C.byref(vi)),
             "gne_price_qs")
         return dict(best_pos=bp.value, best_viol=bv.value, new_cursor=nc.value, scanned=sc.value, violations=vi.value)
+
+    def price_scan_list(self, cursor, want, min_scan=5):
+        cap = max(self.N, 1)
+        pos = np.empty(cap, np.int64); viol = np.empty(cap)
+        count = C.c_int64(0); nc = C.c_int64(0); sc = C.c_int64(0)
+        _ck(lib.gne_price_scan_list(self.h, cursor, want, min_scan, C.byref(count), _p(pos, _i64p), _p(viol, _f64p), cap,
+                                    C.byref(nc), C.byref(sc)), "gne_price_scan_list")
+        return pos[:count.value].copy(), viol[:count.value].copy(), nc.value, sc.value
 
     def price_violators(self, threshold=0.0, cap=None):
         cap = cap if cap is not None else max(self.N, 1)

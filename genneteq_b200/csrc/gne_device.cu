@@ -154,6 +154,8 @@ static NbView view_of(const gne_dev *d)
     v.tail = d->tail; v.head = d->head; v.cost = d->cost; v.mult = d->mult; v.state = d->state;
     v.lo = d->lo;
     v.end = std::min(d->N, d->hi);
+    v.begin = d->lo;
+    v.tile0 = 0;
     return v;
 }
 
@@ -539,13 +541,26 @@ static int sharded_gather_lists(gne_dev *d, int64_t localCount, std::vector<int6
 
 // ordered compaction of this shard's violators with |rc| >= threshold, in two steps: count per tile
 // + offsets (+ min / max of the qualifying values in hostScalar[4..5]), then the write pass
-static int viol_count_device(gne_dev *d, double threshold, int64_t *total, double *vmin, double *vmax)
+// view restricted to global positions [rlo, rhi) of this shard; *G = tiles to launch
+static NbView range_view(const gne_dev *d, int64_t rlo, int64_t rhi, int *G)
 {
-    const int G = tiles_for(d);
+    NbView nb = view_of(d);
+    rlo = std::max(rlo, d->lo); rhi = std::min(rhi, nb.end);
+    if (rhi <= rlo) { *G = 0; return nb; }
+    nb.begin = rlo; nb.end = rhi;
+    nb.tile0 = (int32_t) ((rlo - d->lo) / TILE);
+    *G = (int) ((rhi - d->lo + TILE - 1) / TILE) - nb.tile0;
+    return nb;
+}
+
+static int viol_count_device(gne_dev *d, double threshold, int64_t *total, double *vmin, double *vmax,
+                             int64_t rlo = 0, int64_t rhi = INT64_MAX)
+{
+    int G = 0;
+    NbView nb = range_view(d, rlo, rhi, &G);
     *total = 0;
     if (vmin) { *vmin = 0.0; *vmax = 0.0; }
     if (G == 0) return GNE_OK;
-    NbView nb = view_of(d);
     k_viol_count<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, threshold, d->tileCnt, d->tileVmin, d->tileVmax);
     k_scan_tiles<<<1, 1024, 0, d->stream>>>(d->tileCnt, d->tileOff, G, d->hostScalar, d->tileVmin, d->tileVmax, (double *) (d->hostScalar + 4));
     CK(cudaGetLastError());
@@ -557,11 +572,13 @@ static int viol_count_device(gne_dev *d, double threshold, int64_t *total, doubl
     return GNE_OK;
 }
 
-static int viol_write_device(gne_dev *d, double threshold, int64_t total)
+static int viol_write_device(gne_dev *d, double threshold, int64_t total, int64_t rlo = 0, int64_t rhi = INT64_MAX)
 {
     if (total == 0) return GNE_OK;
     int rc = ensure_out(d, total); if (rc) return rc;
-    k_viol_write<<<tiles_for(d), TILE_THREADS, 0, d->stream>>>(view_of(d), d->pi, threshold, d->tileOff, d->outPos, d->outViol, d->outCap);
+    int G = 0;
+    NbView nb = range_view(d, rlo, rhi, &G);
+    k_viol_write<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, threshold, d->tileOff, d->outPos, d->outViol, d->outCap);
     CK(cudaGetLastError());
     ++d->launches;
     return GNE_OK;
@@ -829,6 +846,50 @@ extern "C" int gne_price_qs(gne_dev *d, int64_t cursor, int64_t want, int64_t *b
     int64_t nc = cursor + *scanned;
     if (nc >= N) nc -= N;
     *newCursor = nc;                                    // == start when the scan was exhausted
+    return GNE_OK;
+}
+
+// updateCandidateList2 + tryToAddArc (gnePivotRules.cpp:613-689 with no equal-flow sets): scan from
+// the rolling cursor, always at least minScan arcs, until `want` violators are listed or the list
+// wrapped; returns the violators in SCAN order with |rc| (the stored redCost the first selection
+// pass reads, :571-578).
+extern "C" int gne_price_scan_list(gne_dev *d, int64_t cursor, int64_t want, int64_t minScan, int64_t *count,
+                                   int64_t *listPos, double *listViol, int64_t cap, int64_t *newCursor, int64_t *scanned)
+{
+    CK(cudaSetDevice(d->device));
+    if (d->nranks != 1) { gne_set_error("gne_price_scan_list: not implemented for a sharded list"); return GNE_ERR_UNSUPPORTED; }
+    const int64_t N = d->N;
+    *count = 0; *scanned = 0;
+    if (cursor >= N) cursor = 0;                        // :622
+    *newCursor = cursor;
+    if (N == 0) return GNE_OK;
+    int64_t bestPos, nc, sc = 0, viol = 0;
+    double bestViol;
+    if (want > 0) { int rc = gne_price_qs(d, cursor, want, &bestPos, &bestViol, &nc, &sc, &viol); if (rc) return rc; }
+    sc = std::min(N, std::max(sc, std::min(minScan, N)));     // the first minScan arcs are always tried (:632-636)
+    // violators of the scanned virtual range, in scan order: [cursor, min(N, cursor + sc)) then [0, rest)
+    const int64_t hi1 = std::min(N, cursor + sc), rest = cursor + sc - hi1;
+    int64_t got = 0;
+    const int64_t seg[2][2] = { { cursor, hi1 }, { 0, rest } };
+    for (int k = 0; k < 2; ++k) {
+        if (seg[k][1] <= seg[k][0]) continue;
+        int64_t total = 0;
+        int rc = viol_count_device(d, 0.0, &total, nullptr, nullptr, seg[k][0], seg[k][1]); if (rc) return rc;
+        if (got + total > cap) { *count = got + total; gne_set_error("gne_price_scan_list: cap too small"); return GNE_ERR_CAPACITY; }
+        rc = viol_write_device(d, 0.0, total, seg[k][0], seg[k][1]); if (rc) return rc;
+        if (total > 0) {
+            CK(cudaMemcpyAsync(listPos + got, d->outPos, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
+            CK(cudaMemcpyAsync(listViol + got, d->outViol, 8 * (size_t) total, cudaMemcpyDeviceToHost, d->stream));
+            CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+            d->d2hBytes += 16 * total;
+        }
+        got += total;
+    }
+    *count = got;
+    *scanned = sc;
+    int64_t c2 = cursor + sc;
+    if (c2 >= N) c2 -= N;
+    *newCursor = c2;
     return GNE_OK;
 }
 

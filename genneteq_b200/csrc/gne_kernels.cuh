@@ -36,6 +36,8 @@ struct NbView {                            // shard of the nonbasic list; index 
     const int8_t *state;
     int64_t lo;                            // first global position of the shard (multiple of TILE)
     int64_t end;                           // min(N, hi): positions >= end are not priced
+    int64_t begin;                         // positions < begin are not priced (range-restricted passes; default lo)
+    int32_t tile0;                         // tile index of blockIdx.x == 0 (range-restricted passes; default 0)
 };
 
 // computeArcRedCost (genneteq.h:312-318): (cost - pi[tail]) + (mult * pi[head]), unfused
@@ -72,7 +74,7 @@ __device__ __forceinline__ void tile_violations(const NbView &nb, const double *
     for (int k = 0; k < ITEMS; ++k) {
         const int64_t l = base + k * TILE_THREADS;
         const double r = red_cost(cs[k], mu[k], ld_pi(pi, tl[k]), ld_pi(pi, hd[k]));
-        v[k] = (nb.lo + l < nb.end) ? violation(r, st[k]) : -1.0;
+        v[k] = (nb.lo + l < nb.end && nb.lo + l >= nb.begin) ? violation(r, st[k]) : -1.0;
         if (rcOut) rcOut[k] = r;
     }
 }
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
 k_viol_count(NbView nb, const double *__restrict__ pi, double threshold, int32_t *tileCnt, double *tileVmin, double *tileVmax)
 {
     double v[ITEMS];
-    tile_violations(nb, pi, (int64_t) blockIdx.x * TILE, v);
+    tile_violations(nb, pi, (int64_t) (nb.tile0 + blockIdx.x) * TILE, v);
     int c = 0;
     double lo = 1.0e308, hi = -1.0;
 #pragma unroll
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
 k_viol_write(NbView nb, const double *__restrict__ pi, double threshold, const int64_t *tileOff,
              int64_t *outPos, double *outViol, int64_t cap)
 {
-    const int64_t tileBase = (int64_t) blockIdx.x * TILE;
+    const int64_t tileBase = (int64_t) (nb.tile0 + blockIdx.x) * TILE;
     double v[ITEMS];
     tile_violations(nb, pi, tileBase, v);
     int64_t base = tileOff[blockIdx.x];

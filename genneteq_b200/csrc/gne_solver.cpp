@@ -590,6 +590,71 @@ int GenNetEq::getNextCandidate(int32_t *out)                      // :457-501
     return GNE_OK;
 }
 
+int GenNetEq::updateCandidateList2()                              // :613-677 with setNBeqf empty (tryToAddArc :679-689)
+{
+    candidateList2.clear(); candidateViol2.clear();
+    const int64_t numNB = (int64_t) setNBarc.size();
+    if (nbArcPivotInd >= numNB) nbArcPivotInd = 0;
+    const size_t cap = (size_t) clMaxSize + (size_t) numArcsToAlwaysCheck + 16;
+    if (listPos.size() < cap) { listPos.resize(cap); listViol.resize(cap); }
+    int64_t cnt = 0, nc = nbArcPivotInd, sc = 0;
+    // exhaustedEqfs is true from the start, so the drand48 arc/eqf interleave (:643-653) never runs
+    GNE_TRY(gne_price_scan_list(dev, nbArcPivotInd, (int64_t) clMaxSize, (int64_t) numArcsToAlwaysCheck, &cnt,
+                                listPos.data(), listViol.data(), (int64_t) listPos.size(), &nc, &sc));
+    arcsPriced += (double) sc;
+    if (cnt > 0) isOptimal = false;
+    for (int64_t i = 0; i < cnt; ++i) { candidateList2.push_back(setNBarc[listPos[i]]); candidateViol2.push_back(listViol[i]); }
+    nbArcPivotInd = nc;                                 // rolling cursor: never restored by this rule
+    return GNE_OK;
+}
+
+int GenNetEq::getNextCandidate2(int32_t *out)                     // :550-610
+{
+    isOptimal = true;
+    if (itersSinceUpdate < 0 || itersSinceUpdate > majorIterationLength) {
+        GNE_TRY(updateCandidateList2());
+        itersSinceUpdate = 0;
+    } else {
+        ++itersSinceUpdate;
+    }
+    int32_t ev = -1;
+    int64_t evInd = -1;
+    double largest = -1.0;
+    size_t k = 0;
+    while (k < candidateList2.size()) {
+        const int32_t c = candidateList2[k];
+        const bool atLB = (setLoc[c] == L_var);
+        bool viol;
+        double arc;
+        if (itersSinceUpdate > 0) {
+            const double rc = computeArcRedCost(c);     // re-priced with the current potentials
+            viol = (atLB && rc < (-1.0 * TOL)) || (!atLB && rc > TOL);
+            arc = fabs(rc);
+        } else {                                        // "reduced cost is up to date": the value the list pass stored
+            viol = true;
+            arc = candidateViol2[k];
+        }
+        if (viol) {
+            isOptimal = false;
+            if (largest < arc) { largest = arc; ev = c; evInd = (int64_t) k; }
+            ++k;
+        } else {
+            candidateList2[k] = candidateList2.back(); candidateList2.pop_back();
+            candidateViol2[k] = candidateViol2.back(); candidateViol2.pop_back();
+        }
+    }
+    if (ev == -1 && itersSinceUpdate > 0) {
+        itersSinceUpdate = -1;
+        return getNextCandidate2(out);
+    }
+    if (evInd >= 0) {
+        candidateList2[evInd] = candidateList2.back(); candidateList2.pop_back();
+        candidateViol2[evInd] = candidateViol2.back(); candidateViol2.pop_back();
+    }
+    *out = ev;
+    return GNE_OK;
+}
+
 int GenNetEq::quickSelect(int32_t *out)                           // :710-764, arc loop
 {
     isOptimal = true;
@@ -620,9 +685,10 @@ int GenNetEq::selectEnteringVariable(int32_t *out)                // :36-127
       case GNE_CL: case GNE_CLW: return getNextCandidate(out);
       case GNE_SAA: return getVarBySimAnnealing(true, out);
       case GNE_SAE: return getVarBySimAnnealing(false, out);
+      case GNE_CL2: case GNE_CLW2: return getNextCandidate2(out);
       case GNE_QS: case GNE_QSW: return quickSelect(out);
     }
-    gne_set_error("pivot rule %d is not supported (SD relies on the stale computeMinDelta, gnePivot.cpp:406; CL2 aborts the reference)", rule);
+    gne_set_error("pivot rule %d is not supported (SD relies on the stale computeMinDelta, gnePivot.cpp:406)", rule);
     return GNE_ERR_UNSUPPORTED;
 }
 

@@ -124,7 +124,7 @@ class GenNetEq {
     double delta = 0.0;
     int32_t eVar = -1, lVar = -1;
     std::vector<int32_t> blockingVars, offendingVars, candidateList2;
-    std::vector<double> offendingViol;
+    std::vector<double> offendingViol, candidateViol2;
     bool cyclingDetected = false;
     std::list<std::pair<int32_t, int32_t> > cycleList;
     int lastEVarInd = -1;
@@ -204,6 +204,8 @@ class GenNetEq {
     int getNextCandidate(int32_t *out);
     int updateCandidateList();
     int quickSelect(int32_t *out);
+    int getNextCandidate2(int32_t *out);
+    int updateCandidateList2();
     int fetchViolators(double threshold);
 };
 

@@ -110,6 +110,12 @@ int gne_price_lv_at(gne_dev *d, int64_t index, int64_t *pos);
 int gne_price_qs(gne_dev *d, int64_t cursor, int64_t want, int64_t *bestPos, double *bestViol,
                  int64_t *newCursor, int64_t *scanned, int64_t *violations);
 
+/* updateCandidateList2 / tryToAddArc (gnePivotRules.cpp:613-689): scan from the rolling cursor — at
+ * least minScan arcs (numArcsToAlwaysCheck) — until `want` (clMaxSize) violators are listed or the
+ * list wrapped; the violators come back in scan order with |rc|.                              */
+int gne_price_scan_list(gne_dev *d, int64_t cursor, int64_t want, int64_t minScan, int64_t *count,
+                        int64_t *listPos, double *listViol, int64_t cap, int64_t *newCursor, int64_t *scanned);
+
 /* every violator with |rc| >= threshold, in position order (updateCandidateList
  * gnePivotRules.cpp:504-516; computeReducedCosts gnePotential.cpp:226-234;
  * getRandomVarWithLargeViolation :311-328).  listViol may be NULL.                           */

@@ -156,6 +156,37 @@ def test_price_violators_and_first(gne, n, N):
     d.close()
 
 
+@pytest.mark.parametrize("n,N", [(3, 40), (300, 2049), (5000, 262144)])
+def test_price_scan_list_matches_try_to_add_arc(gne, n, N):
+    """updateCandidateList2 / tryToAddArc (gnePivotRules.cpp:613-689): at least 5 arcs, then until clMaxSize violators."""
+    rng = np.random.default_rng(N + 9)
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N, "cont")
+    d = gne.Device(n, N + 16)
+    d.nb_reset(tail, head, cost, mult, state)
+    d.pot_set_all(pi)
+    allpos, allviol = oracle_violators(tail, head, cost, mult, state, pi, 0.0)
+    isv = np.zeros(N, bool); isv[allpos] = True
+    vv = np.zeros(N); vv[allpos] = allviol
+    for cur in (0, 3, N // 2, N - 2, N + 7):
+        for want in (1, 3, n, 10 * N):
+            c = 0 if cur >= N else cur
+            exp_pos, k, start = [], c, c
+            for i in range(5):                          # numArcsToAlwaysCheck
+                if isv[k]: exp_pos.append(k)
+                k = (k + 1) % N
+                if k == start: break
+            exhausted = (k == start)
+            while len(exp_pos) < want and not exhausted:
+                if isv[k]: exp_pos.append(k)
+                k = (k + 1) % N
+                exhausted = (k == start)
+            pos, viol, nc, sc = d.price_scan_list(cur, want)
+            assert np.array_equal(pos, np.array(exp_pos, np.int64)), (cur, want)
+            assert np.array_equal(viol, vv[pos])
+            assert nc == k
+    d.close()
+
+
 def test_nonbasic_mirror_swap_remove_and_push(gne):
     """setNBarc semantics (gnePivot.cpp:527-600) mirrored with gne_nb_write / gne_nb_set_count."""
     rng = np.random.default_rng(11)
@@ -255,7 +286,7 @@ def test_c1_pivot_sequence_equals_reference(gne, rn):
 
 
 SMALL = ["s_wide_s3", "s_lossy_s4", "s_pow2_s5", "s_near1_s6"]
-GPU_RULES = ["LV", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "QS", "QSW"]
+GPU_RULES = ["LV", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "CL2", "QS", "QSW"]
 
 
 @pytest.mark.parametrize("name", SMALL)
