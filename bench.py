@@ -47,6 +47,8 @@ WORKLOADS = {
     "c2-qs": (100_000, 2_000_000, 21, "lossy", "QS", "configs[1]: 100k nodes / 2M arcs, lossy gains, seed 21, block rule (QS)"),
     "c5-lv": (200_000, 100_000_000, 51, "lossy", "LV", "configs[4]: 200k nodes / 100M arcs, lossy gains, seed 51, Dantzig rule (LV)"),
     "c1-lv": (1_000, 10_000, 7, "wide", "LV", "configs[0] size: 1k nodes / 10k arcs (native generator), Dantzig rule (LV)"),
+    # configs[3]: independent instances, one solver handle (= one CUDA stream) each, `--batch` per GPU, seeds 1000..
+    "c4-batch": (50_000, 1_000_000, 1000, "lossy", "LV", "configs[3]: independent 50k-node / 1M-arc lossy instances (seeds 1000+), one stream per instance, Dantzig rule (LV)"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of k_price_lv_tiles per launch, from the committed
 # `ncu --set full` capture (profiles/r1_price_lv_tiles_ncu_summary.txt): 509.1 MB + 4.9 MB on c3-lv, N = 1
@@ -342,6 +344,167 @@ def b200_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------
+# configs[3]: a batch of independent instances, one solver handle (one CUDA stream) per instance, one host
+# thread per handle (ctypes releases the GIL); replicas only - no collective.  "scaling": "weak".
+# ------------------------------------------------------------------------------------------------
+_BATCH_REF_CHILD = r"""
+import ctypes as C, json, sys, time, os
+import numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+req = json.load(open(sys.argv[1]))
+import genneteq_b200 as gne
+from oracle_util import REF_SO, dp, ip, oracle_lib, RULES
+g = gne.generate_instance(req["n"], req["m"], req["seed"], req["mode"])
+big_m = oracle_lib().orc_big_m(C.c_long(req["m"]), dp(g["cost"]), dp(g["ub"]))
+ref = C.CDLL(REF_SO)
+ref.ref_solve.restype = C.c_long
+ref.ref_init_sparse(req["n"], C.c_long(req["m"]), ip(g["tail"]), ip(g["head"]), dp(g["ub"]), dp(g["cost"]), dp(g["mult"]),
+                    dp(g["supply"]), C.c_double(big_m))
+ref.ref_set_rules(RULES[req["rule"]], RULES[req["rule"]])
+fin = C.c_int(0)
+ref.ref_set_window(C.c_long(req["warmup"]))
+ref.ref_solve(1, C.c_long(req["warmup"] + req["steps"]), C.byref(fin))
+t0 = np.zeros(5); t1 = np.zeros(5)
+ref.ref_get_window_timers(dp(t0)); ref.ref_get_timers(dp(t1))
+tm = t1 - t0
+json.dump(dict(loop_s=tm[0] + tm[1] + tm[2], arcs_priced=tm[4]), open(req["out"], "w"))
+"""
+
+
+def batch_reference(args, count, steps, warmup):
+    """One reference PROCESS per instance (Tree statics forbid two solvers in a process), all host cores."""
+    n, m, seed0, mode, rule, desc = WORKLOADS["c4-batch"]
+    cores = min(os.cpu_count() or 1, count)
+    d = tempfile.mkdtemp(prefix="gne_batch_")
+    procs, outs = [], []
+    code = _BATCH_REF_CHILD % dict(root=ROOT)
+    t0 = time.perf_counter()
+    for i in range(cores):
+        req = dict(n=n, m=m, seed=seed0 + i, mode=mode, rule=rule, steps=steps, warmup=warmup, out=os.path.join(d, "o%d.json" % i))
+        rp = os.path.join(d, "r%d.json" % i)
+        json.dump(req, open(rp, "w"))
+        outs.append(req["out"])
+        procs.append(subprocess.Popen([sys.executable, "-c", code, rp], stdout=subprocess.DEVNULL))
+    for p in procs:
+        p.wait()
+    res = [json.load(open(o)) for o in outs]
+    arcs = sum(r["arcs_priced"] for r in res)
+    worst = max(r["loop_s"] for r in res)
+    return dict(value=arcs / worst, cores=cores, instances=cores, steps=steps, warmup=warmup, ms_per_pivot=1e3 * worst / steps,
+                wall_s=time.perf_counter() - t0)
+
+
+def batch_arm(args):
+    import threading as th
+    import torch
+    import genneteq_b200 as gne
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    n, m, seed0, mode, rule, desc = WORKLOADS["c4-batch"]
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = batch_reference(args, args.batch * max(args.gpus, 1), min(args.steps, 40), max(2, min(args.warmup, 5)))
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": r["steps"],
+                "warmup": r["warmup"], "ms_per_step": r["ms_per_pivot"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule,
+                                                               "instances": r["instances"], "host_cores_present": os.cpu_count()},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                                 "sample": "%d instances, one process each, %d iterations after %d warm-up" % (r["instances"], r["steps"], r["warmup"])},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+    if gne.cuda_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device - genneteq_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    W = max(args.warmup, 3)
+    solvers = []
+    for i in range(B):
+        g = gne.generate_instance(n, m, seed0 + rank * B + i, mode)
+        solvers.append(gne.Solver(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"], device=local, rule1=rule, trace_cap=16))
+    sampler = ClockSampler(local)
+    if dist is not None:
+        dist.barrier()
+    sampler.start()
+
+    def run(s):
+        s.set_window(W, args.steps)
+        s.solve(True, W + args.steps)
+    threads = [th.Thread(target=run, args=(s,)) for s in solvers]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    wins = [s.window() for s in solvers]
+    edges = [s.window_edges for s in solvers]
+    wall = max(e[1] for e in edges) - min(e[0] for e in edges)
+    arcs = sum(w[2]["arcs_priced"] - w[1]["arcs_priced"] for w in wins)
+    pivots = sum(w[2]["pivots"] - w[1]["pivots"] for w in wins)
+    h2d = sum(w[2]["h2d_bytes"] - w[1]["h2d_bytes"] for w in wins)
+    d2h = sum(w[2]["d2h_bytes"] - w[1]["d2h_bytes"] for w in wins)
+    launches = sum(w[2]["launches"] - w[1]["launches"] for w in wins)
+    # device-resident leg: every instance replays K device steps on its own stream, all streams concurrently
+    devs = [s.device() for s in solvers]
+    for d in devs:
+        d.bench_price_lv(3, False)
+    torch.cuda.synchronize()
+    res = [None] * B
+
+    def steps(i):
+        res[i] = devs[i].bench_price_lv(args.steps, False)
+    t0 = time.perf_counter()
+    threads = [th.Thread(target=steps, args=(i,)) for i in range(B)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    dev_wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    tiles_ms = float(np.mean([r[1].mean() for r in res]))
+    launches += int(sum(4 * args.steps for _ in range(B)))
+    for s in solvers:
+        s.close()
+    if dist is not None:
+        t = torch.tensor([wall, dev_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, dev_wall = (float(x) for x in t.cpu())
+        tot = torch.tensor([arcs, pivots, h2d, d2h, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        arcs, pivots, h2d, d2h, launches = (float(x) for x in tot.cpu())
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    peak, peak_src = peaks()
+    alg = 25.0 * m + 8.0 * n
+    line = {"metric": METRIC, "value": world * B * m * args.steps / dev_wall, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": 1e3 * dev_wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule, "instances_per_gpu": B, "instances": world * B,
+                       "l2": "all instances of a GPU priced concurrently: %.0f MB per round of passes > L2" % (B * alg / 1e6),
+                       "sharding": "replicas only: one solver handle / CUDA stream / host thread per instance, no collective"},
+            "e2e": {"value": arcs / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(pivots, 1), "d2h_bytes_per_step": d2h / max(pivots, 1),
+                    "pivots_per_s": pivots / wall, "ms_per_pivot_per_instance": 1e3 * wall / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": alg / (tiles_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (tiles_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_price_lv_tiles (one instance's pass, timed while the other streams run)",
+                         "kernel_ms": tiles_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
+    if not args.no_cpu_baseline and world == 1:
+        r = batch_reference(args, B, 12, 2)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                                "sample": "%d instances, one reference process per instance on %d host cores, %d iterations after %d warm-up" % (
+                                    r["instances"], r["cores"], r["steps"], r["warmup"]), "ms_per_pivot": r["ms_per_pivot"]}
+    print(json.dumps(line))
+    sys.stdout.flush()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -350,7 +513,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3-lv", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=32, help="instances per GPU for --workload c4-batch")
     args = ap.parse_args()
+    if args.workload == "c4-batch":
+        return batch_arm(args)
     if args.impl == "reference":
         return reference_arm(args)
     return b200_arm(args)

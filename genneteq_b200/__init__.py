@@ -398,8 +398,9 @@ class Solver:
 
     def window(self):
         """(seconds, counters at the window's start, counters at its end) of the last windowed solve."""
-        a = np.zeros(25)
+        a = np.zeros(27)
         lib.gne_solver_get_window(self.h, _p(a, _f64p))
+        self.window_edges = (a[25], a[26])
         return a[0], dict(zip(self.COUNTERS, a[1:13].tolist())), dict(zip(self.COUNTERS, a[13:25].tolist()))
 
     def set_progress(self, every, cap_rows=100000):

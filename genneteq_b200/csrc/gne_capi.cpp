@@ -171,7 +171,7 @@ extern "C" gne_dev *gne_solver_device(gne_solver *s) { return s->solver.device()
 extern "C" int gne_solver_set_window(gne_solver *s, int64_t startPivot, int64_t numPivots) { s->solver.setWindow(startPivot, numPivots); return GNE_OK; }
 extern "C" int gne_solver_set_progress(gne_solver *s, int64_t every, double *buf, int64_t capRows) { s->solver.setProgress(every, buf, capRows); return GNE_OK; }
 extern "C" int64_t gne_solver_progress_rows(const gne_solver *s) { return s->solver.getProgressRows(); }
-extern "C" int gne_solver_get_window(const gne_solver *s, double *out25) { s->solver.getWindow(out25); return GNE_OK; }
+extern "C" int gne_solver_get_window(const gne_solver *s, double *out27) { s->solver.getWindow(out27); return GNE_OK; }
 
 // ------------------------------------------------------------------------------------------
 // host-only forest replay (no device): the basis exchanges of a given pivot trace

@@ -994,6 +994,7 @@ void GenNetEq::getWindow(double *o) const
 {
     o[0] = (winT1 > 0.0 && winT0 > 0.0) ? winT1 - winT0 : -1.0;
     for (int i = 0; i < 12; ++i) { o[1 + i] = winC0[i]; o[13 + i] = winC1[i]; }
+    o[25] = winT0; o[26] = winT1;                       // CLOCK_MONOTONIC seconds (comparable across threads)
 }
 
 void GenNetEq::getCounters(double *o) const

@@ -86,9 +86,9 @@ class GenNetEq {
     void setSparseFlows(bool on) { sparseFlows = on; }
     void getHostPotentials(double *out) const { for (int i = 0; i < numNodes; ++i) out[i] = hostPotential(i); }
     // wall-clock window over pivots [start, start + len) of the next solve() call, taken inside the loop
-    // with the device synchronised at both edges; out = {seconds, 12 counters at start, 12 at end}
+    // with the device synchronised at both edges; out = {seconds, 12 counters at start, 12 at end, t0, t1}
     void setWindow(int64_t start, int64_t len) { winStart = start; winLen = len; winT0 = winT1 = 0.0; }
-    void getWindow(double *out25) const;
+    void getWindow(double *out27) const;
     // every `every` pivots append {wall seconds, 12 counters, largest tree size} to buf (13+1 doubles per row)
     void setProgress(int64_t every, double *buf, int64_t capRows) { progEvery = every; progBuf = buf; progCap = capRows; progRows = 0; }
     int64_t getProgressRows() const { return progRows; }

@@ -189,9 +189,10 @@ int gne_solver_get_counters(const gne_solver *s, double *out12);
 gne_dev *gne_solver_device(gne_solver *s);
 /* wall-clock window over pivots [startPivot, startPivot + numPivots) of the next gne_solver_solve
  * call, taken inside the loop with the device synchronised at both edges (bench.py's e2e):
- * out25 = { seconds (-1 if the window was not completed), the 12 counters at its start, at its end } */
+ * out27 = { seconds (-1 if the window was not completed), the 12 counters at its start, at its end,
+ *          CLOCK_MONOTONIC seconds of the two edges } */
 int gne_solver_set_window(gne_solver *s, int64_t startPivot, int64_t numPivots);
-int gne_solver_get_window(const gne_solver *s, double *out25);
+int gne_solver_get_window(const gne_solver *s, double *out27);
 /* progress log: every `every` pivots of a solve call append a row of 14 doubles to buf —
  * { wall-clock seconds, the 12 counters, size of the largest basis tree }                     */
 int gne_solver_set_progress(gne_solver *s, int64_t every, double *buf, int64_t capRows);
