@@ -161,9 +161,10 @@ extern "C" int gne_solver_get_potentials(gne_solver *s, double *out) { return s-
 extern "C" int gne_solver_get_states(gne_solver *s, int32_t *out) { s->solver.getStates(out); return GNE_OK; }
 extern "C" int gne_solver_get_forest(gne_solver *s, int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread)
 {
-    const Forest &f = s->solver.getForest();
+    Forest &f = s->solver.getForestMutable();
     const int n = s->solver.getNumNodes();
-    for (int i = 0; i < n; ++i) { tree[i] = f.treeSlot[i]; pred[i] = f.pred[i]; predArc[i] = f.predArc[i]; depth[i] = f.depth[i]; thread[i] = f.thread[i]; }
+    for (int sl = 0; sl < f.numSlots(); ++sl) f.ensureThreads(sl);
+    for (int i = 0; i < n; ++i) { tree[i] = f.node[i].slot; pred[i] = f.node[i].pred; predArc[i] = f.node[i].predArc; depth[i] = f.node[i].depth; thread[i] = f.node[i].thread; }
     return GNE_OK;
 }
 extern "C" int gne_solver_get_counters(const gne_solver *s, double *out12) { s->solver.getCounters(out12); return GNE_OK; }
@@ -199,7 +200,8 @@ extern "C" int gne_forest_replay(int n, int64_t m, const int32_t *tailIn, const 
         basic[l[k]] = 0; basic[e[k]] = 1;
         f.updateTrees();
     }
-    for (int i = 0; i < n; ++i) { tree[i] = f.treeSlot[i]; pred[i] = f.pred[i]; predArc[i] = f.predArc[i]; depth[i] = f.depth[i]; thread[i] = f.thread[i]; }
+    for (int sl = 0; sl < f.numSlots(); ++sl) f.ensureThreads(sl);
+    for (int i = 0; i < n; ++i) { tree[i] = f.node[i].slot; pred[i] = f.node[i].pred; predArc[i] = f.node[i].predArc; depth[i] = f.node[i].depth; thread[i] = f.node[i].thread; }
     return GNE_OK;
 }
 

@@ -142,7 +142,8 @@ struct gne_dev {
     struct Mailbox **peersDev = nullptr;           // device array [nranks] of every rank's mailbox (IPC-mapped)
     void *peerPtr[8] = { nullptr };
     bool p2p = false;
-    unsigned long long xseq = 0;
+    unsigned long long xseq = 0, bseq = 0;
+    unsigned long long *blobHost = nullptr, *blobDev = nullptr;
     int64_t *cntDev = nullptr;                     // [1 + nranks] counts exchange
     char *xSend = nullptr, *xRecv = nullptr;       // variable-length list exchange, grown on demand
     size_t xSendBytes = 0, xRecvBytes = 0;
@@ -251,9 +252,9 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
                     d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->stageDev, d->outPos, d->outViol,
-                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev };
+                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev };
     for (void *p : dev) if (p) cudaFree(p);
-    void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes };
+    void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes, d->blobHost };
     for (void *p : host) if (p) cudaFreeHost(p);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
@@ -800,46 +801,59 @@ extern "C" int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc)
     return GNE_OK;
 }
 
+// Windowed scan over the virtual indices j in [0, jTotal), pos = (cursor + j) mod N, until `want`
+// violators were seen or jTotal is reached; result in d->qsState (mapped pinned).
+static int qs_scan(gne_dev *d, int64_t cursor, int64_t N, int64_t jTotal, int64_t want, float *msOut)
+{
+    NbView nb = view_of(d);
+    QsState *st = d->qsState;
+    st->violations = 0; st->bestV = 0.0; st->bestJ = -1; st->stopJ = -1; st->done = 0;
+    if (msOut) *msOut = 0.f;
+    if (jTotal <= 0 || want <= 0) { st->done = 1; return GNE_OK; }
+    if (d->qsWindow <= 0) d->qsWindow = std::max<int64_t>(4 * std::min<int64_t>(want, jTotal), 64 * QTILE);
+    int64_t jLo = 0;
+    while (true) {
+        const int64_t jHi = std::min(jTotal, jLo + d->qsWindow);
+        const int G = (int) ((jHi - jLo + QTILE - 1) / QTILE);
+        CK(cudaEventRecord(d->ev0, d->stream));
+        k_qs_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, d->qs);
+        k_qs_finish<<<1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, jTotal, d->qs, G, want, st);
+        CK(cudaEventRecord(d->ev1, d->stream));
+        CK(cudaGetLastError());
+        d->launches += 2;
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+        float ms; CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
+        if (msOut) *msOut += ms;
+        d->d2hBytes += sizeof(QsState);
+        if (st->done) {
+            const int64_t sc = (st->stopJ >= 0) ? st->stopJ + 1 : jTotal;
+            // adapt the next window to ~1.5x what this scan needed
+            d->qsWindow = std::min<int64_t>(std::max<int64_t>(N, QTILE), std::max<int64_t>(64 * QTILE, ((sc * 3 / 2) / QTILE + 1) * QTILE));
+            break;
+        }
+        jLo = jHi;
+        d->qsWindow = std::min<int64_t>(std::max<int64_t>(N, QTILE), d->qsWindow * 4);
+    }
+    return GNE_OK;
+}
+
+static int price_qs_sharded(gne_dev *d, int64_t cursor, int64_t want, int64_t *bestPos, double *bestViol,
+                            int64_t *newCursor, int64_t *scanned, int64_t *violations);
+
 extern "C" int gne_price_qs(gne_dev *d, int64_t cursor, int64_t want, int64_t *bestPos, double *bestViol,
                             int64_t *newCursor, int64_t *scanned, int64_t *violations)
 {
     CK(cudaSetDevice(d->device));
-    if (d->nranks != 1) { gne_set_error("gne_price_qs: sharded quickSelect is not implemented"); return GNE_ERR_UNSUPPORTED; }
     int rc = gne_dev_flush(d); if (rc) return rc;
     const int64_t N = d->N;
     *bestPos = -1; *bestViol = 0.0; *scanned = 0; *violations = 0;
     if (cursor >= N) cursor = 0;                        // gnePivotRules.cpp:716
     *newCursor = cursor;
     if (N == 0 || want <= 0) return GNE_OK;
-    NbView nb = view_of(d);
-    QsState *st = d->qsState;
-    st->violations = 0; st->bestV = 0.0; st->bestJ = -1; st->stopJ = -1; st->done = 0;
-    if (d->qsWindow <= 0) d->qsWindow = std::max<int64_t>(4 * want, 64 * QTILE);
-    int64_t jLo = 0;
-    float msTotal = 0.f;
-    while (true) {
-        int64_t jHi = std::min(N, jLo + d->qsWindow);
-        const int G = (int) ((jHi - jLo + QTILE - 1) / QTILE);
-        CK(cudaEventRecord(d->ev0, d->stream));
-        k_qs_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, d->qs);
-        k_qs_finish<<<1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, d->qs, G, want, st);
-        CK(cudaEventRecord(d->ev1, d->stream));
-        CK(cudaGetLastError());
-        d->launches += 2;
-        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
-        float ms; CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1)); msTotal += ms;
-        d->d2hBytes += sizeof(QsState);
-        if (st->done) {
-            const int64_t sc = (st->stopJ >= 0) ? st->stopJ + 1 : N;
-            *scanned = sc;
-            // adapt the next window to ~1.5x what this scan needed
-            d->qsWindow = std::min<int64_t>(N, std::max<int64_t>(64 * QTILE, ((sc * 3 / 2) / QTILE + 1) * QTILE));
-            break;
-        }
-        jLo = jHi;
-        d->qsWindow = std::min<int64_t>(N, d->qsWindow * 4);
-    }
-    d->lastMs = msTotal;
+    if (d->nranks != 1) return price_qs_sharded(d, cursor, want, bestPos, bestViol, newCursor, scanned, violations);
+    rc = qs_scan(d, cursor, N, N, want, &d->lastMs); if (rc) return rc;
+    const QsState *st = d->qsState;
+    *scanned = (st->stopJ >= 0) ? st->stopJ + 1 : N;
     *violations = st->violations;
     *bestViol = st->bestV;
     if (st->bestJ >= 0) { int64_t p = cursor + st->bestJ; if (p >= N) p -= N; *bestPos = p; }
@@ -998,9 +1012,12 @@ struct ShardRecord {                                    // 24 + 48*16 = 792 byte
 } // namespace
 // Receive buffer of one rank: slot r is written by rank r's k_lv_exchange with NVLink stores.
 // Two generations (seq parity) so that a fast rank's next record never overwrites one being read.
+constexpr int BLOB_WORDS = 16;                          // 128-byte blobs of the sharded quickSelect
 struct Mailbox {
     ShardRecord rec[2][MAX_RANKS];
     unsigned long long flag[2][MAX_RANKS];
+    unsigned long long blob[2][MAX_RANKS][BLOB_WORDS];
+    unsigned long long bflag[2][MAX_RANKS];
 };
 namespace {
 __device__ __forceinline__ void pack_record(const LvResult *res, ShardRecord *rec, int t)
@@ -1052,7 +1069,140 @@ k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, 
     }
     if (sTimeout && t == 0) hostOut[0].count = -2;
 }
+// all-gather of one 128-byte blob per rank through the peer mailboxes (same protocol as k_lv_exchange)
+__global__ void __launch_bounds__(64)
+k_blob_exchange(const unsigned long long *src, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, unsigned long long *hostOut)
+{
+    const int t = threadIdx.x, b = (int) (seq & 1ull);
+    __shared__ unsigned long long mine[BLOB_WORDS];
+    __shared__ int sTimeout;
+    if (t < BLOB_WORDS) mine[t] = src[t];
+    if (t == 0) sTimeout = 0;
+    __syncthreads();
+    for (int p = 0; p < nranks; ++p) if (t < BLOB_WORDS) peers[p]->blob[b][rank][t] = mine[t];
+    __threadfence_system();
+    __syncthreads();
+    if (t < nranks) *reinterpret_cast<volatile unsigned long long *>(&peers[t]->bflag[b][rank]) = seq;
+    Mailbox *self = peers[rank];
+    if (t < nranks) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned long long *>(&self->bflag[b][t]) != seq) {
+            if (clock64() - t0 > 8000000000ll) { sTimeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    for (int r = 0; r < nranks; ++r)
+        if (t < BLOB_WORDS) hostOut[r * BLOB_WORDS + t] = *reinterpret_cast<const volatile unsigned long long *>(&self->blob[b][r][t]);
+    if (sTimeout && t == 0) hostOut[0] = ~0ull;
+}
 } // namespace
+
+// one 128-byte blob per rank -> all ranks (host buffers); mailbox path or NCCL
+static int exchange_blobs(gne_dev *d, const unsigned long long *mine, unsigned long long *all)
+{
+    const int R = d->nranks;
+    if (!d->blobHost) {
+        CK(cudaHostAlloc(&d->blobHost, 8 * BLOB_WORDS * (size_t) (R + 1), cudaHostAllocMapped));
+        CK(cudaMalloc(&d->blobDev, 8 * BLOB_WORDS * (size_t) (R + 1)));
+    }
+    memcpy(d->blobHost, mine, 8 * BLOB_WORDS);
+    if (d->p2p) {
+        k_blob_exchange<<<1, 64, 0, d->stream>>>(d->blobHost, d->peersDev, d->rank, R, ++d->bseq, d->blobHost + BLOB_WORDS);
+        CK(cudaGetLastError());
+        ++d->launches;
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+        if (d->blobHost[BLOB_WORDS] == ~0ull) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
+    } else {
+        CK(cudaMemcpyAsync(d->blobDev, d->blobHost, 8 * BLOB_WORDS, cudaMemcpyHostToDevice, d->stream));
+        int r = g_nccl.AllGather(d->blobDev, d->blobDev + BLOB_WORDS, 8 * BLOB_WORDS, /*ncclChar*/ 0, d->comm, d->stream);
+        if (r != 0) { gne_set_error("ncclAllGather(blobs) failed"); return GNE_ERR_COMM; }
+        CK(cudaMemcpyAsync(d->blobHost + BLOB_WORDS, d->blobDev + BLOB_WORDS, 8 * BLOB_WORDS * (size_t) R, cudaMemcpyDeviceToHost, d->stream));
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    }
+    memcpy(all, d->blobHost + BLOB_WORDS, 8 * BLOB_WORDS * (size_t) R);
+    d->d2hBytes += 8 * BLOB_WORDS * R;
+    return GNE_OK;
+}
+
+// quickSelect over a sharded list: every rank scans its part after the cursor
+// (earlier in scan order) and its part before it, the (count, first-max) pairs are exchanged, every
+// rank finds the segment in which the want-th violator falls, the owner rescans that segment with
+// the remaining budget, and a second exchange publishes the stop position and the partial maximum.
+static int price_qs_sharded(gne_dev *d, int64_t cursor, int64_t want, int64_t *bestPos, double *bestViol,
+                            int64_t *newCursor, int64_t *scanned, int64_t *violations)
+{
+    const int R = d->nranks;
+    const int64_t N = d->N;
+    const int64_t lo = d->lo, end = std::max(lo, std::min(N, d->hi));
+    struct Seg { int64_t a, b, cnt, pos; double v; };
+    union Blob { unsigned long long w[BLOB_WORDS]; struct { int64_t a1, b1, c1, p1, a2, b2, c2, p2; double v1, v2; int64_t stop, pp; double pv; } f; };
+    Blob mine; memset(&mine, 0, sizeof(mine));
+    Seg local[2] = { { std::max(lo, cursor), end, 0, -1, 0.0 }, { lo, std::min(end, cursor), 0, -1, 0.0 } };
+    float msTot = 0.f;
+    for (int k = 0; k < 2; ++k) {
+        Seg &sg = local[k];
+        if (sg.b <= sg.a) { sg.a = sg.b = 0; continue; }
+        float ms = 0.f;
+        int rc = qs_scan(d, sg.a, N, sg.b - sg.a, INT64_MAX / 4, &ms); if (rc) return rc;
+        msTot += ms;
+        sg.cnt = d->qsState->violations; sg.v = d->qsState->bestV;
+        sg.pos = d->qsState->bestJ >= 0 ? sg.a + d->qsState->bestJ : -1;
+    }
+    mine.f.a1 = local[0].a; mine.f.b1 = local[0].b; mine.f.c1 = local[0].cnt; mine.f.p1 = local[0].pos; mine.f.v1 = local[0].v;
+    mine.f.a2 = local[1].a; mine.f.b2 = local[1].b; mine.f.c2 = local[1].cnt; mine.f.p2 = local[1].pos; mine.f.v2 = local[1].v;
+    std::vector<Blob> all((size_t) R);
+    int rc = exchange_blobs(d, mine.w, all[0].w); if (rc) return rc;
+    // scan order: segments after the cursor by rank, then segments before it by rank
+    std::vector<std::pair<int, int> > order;            // (rank, which)
+    for (int r = 0; r < R; ++r) if (all[r].f.b1 > all[r].f.a1) order.push_back(std::make_pair(r, 0));
+    for (int r = 0; r < R; ++r) if (all[r].f.b2 > all[r].f.a2) order.push_back(std::make_pair(r, 1));
+    int64_t cum = 0;
+    int cross = -1;
+    for (size_t k = 0; k < order.size(); ++k) {
+        const Blob &bl = all[order[k].first];
+        const int64_t c = order[k].second ? bl.f.c2 : bl.f.c1;
+        if (cum < want && cum + c >= want) { cross = (int) k; break; }
+        cum += c;
+    }
+    double bv = 0.0;                                    // largestViol starts at 0.0, strictly-greater replaces
+    int64_t bp = -1;
+    const size_t upto = cross < 0 ? order.size() : (size_t) cross;
+    for (size_t k = 0; k < upto; ++k) {
+        const Blob &bl = all[order[k].first];
+        const double v = order[k].second ? bl.f.v2 : bl.f.v1;
+        const int64_t p = order[k].second ? bl.f.p2 : bl.f.p1;
+        if (p >= 0 && v > bv) { bv = v; bp = p; }
+    }
+    if (cross < 0) {
+        *violations = cum; *scanned = N; *newCursor = cursor;
+        *bestViol = bv; *bestPos = bp;
+        d->lastMs = msTot;
+        return GNE_OK;
+    }
+    // the owner of the crossing segment rescans it with the remaining budget
+    Blob second; memset(&second, 0, sizeof(second));
+    second.f.stop = -1; second.f.pp = -1;
+    if (order[cross].first == d->rank) {
+        const Seg &sg = local[order[cross].second];
+        float ms = 0.f;
+        rc = qs_scan(d, sg.a, N, sg.b - sg.a, want - cum, &ms); if (rc) return rc;
+        msTot += ms;
+        second.f.stop = sg.a + d->qsState->stopJ;
+        second.f.pp = d->qsState->bestJ >= 0 ? sg.a + d->qsState->bestJ : -1;
+        second.f.pv = d->qsState->bestV;
+    }
+    rc = exchange_blobs(d, second.w, all[0].w); if (rc) return rc;
+    const Blob &ow = all[order[cross].first];
+    if (ow.f.pp >= 0 && ow.f.pv > bv) { bv = ow.f.pv; bp = ow.f.pp; }
+    const int64_t stop = ow.f.stop;
+    *violations = want;
+    *scanned = (stop >= cursor ? stop - cursor : stop + N - cursor) + 1;
+    *newCursor = (stop + 1 >= N) ? stop + 1 - N : stop + 1;
+    *bestViol = bv; *bestPos = bp;
+    d->lastMs = msTot;
+    return GNE_OK;
+}
 
 extern "C" int gne_comm_unique_id(uint8_t id[128])
 {

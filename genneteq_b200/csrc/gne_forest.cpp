@@ -2,15 +2,17 @@
 #include "gne_forest.h"
 
 #include <algorithm>
+#include <time.h>
 
 namespace gneb200 {
+
+static inline double nowS() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double) ts.tv_sec + 1.0e-9 * (double) ts.tv_nsec; }
 
 void Forest::init(int nNodes, int64_t numVars, const int32_t *tailIn, const int32_t *headIn)
 {
     n = nNodes; tail = tailIn; head = headIn;
-    treeSlot.assign(n, -1); pred.assign(n, -1); predArc.assign(n, -1); depth.assign(n, -1); thread.assign(n, -1);
-    threadPos.assign(n, -1); nodeFlag.assign(n, 1);
-    arcPos.assign((size_t) numVars, -1);
+    (void) numVars;
+    node.assign((size_t) n, NodeRec());
     trees.clear(); freeSlots.clear(); stale.clear(); changed.clear(); changedFlag.clear(); dirtyNodes.clear();
     trees.reserve((size_t) n + 8);
     pool.clear(); pool.reserve((size_t) 4 * n + 64);
@@ -39,7 +41,8 @@ int32_t Forest::newTree(int8_t type, int32_t rootNode)
     else { slot = (int32_t) trees.size(); trees.emplace_back(); }
     Tree &t = trees[slot];
     t.type = type; t.root = -1; t.extraArc = -1;
-    t.nodes.clear(); t.arcs.clear(); t.threads.clear();
+    t.nodes.clear(); t.arcs.clear(); t.threads.clear(); t.pending.clear();
+    t.rooted = false; t.threadsValid = false;
     touch(slot);
     if (rootNode >= 0) {
         t.root = rootNode;
@@ -69,17 +72,27 @@ void Forest::relabel(int32_t slot, int32_t newSlot)
     for (size_t k = 0; k < nd.size(); ++k) setSlot(nd[k], newSlot);
 }
 
-void Forest::incPush(int32_t node, int32_t arc, int32_t nbr)
+void Forest::incPush(int32_t v, int32_t arc, int32_t nbr, int32_t pos)
 {
-    if (incLen[node] == incCap[node]) {
-        const int32_t nc = std::max(4, 2 * incCap[node]);
+    if (incLen[v] == incCap[v]) {
+        const int32_t nc = std::max(4, 2 * incCap[v]);
         const int64_t ns = (int64_t) pool.size();
         pool.resize(pool.size() + (size_t) nc);
-        for (int32_t k = 0; k < incLen[node]; ++k) pool[ns + k] = pool[incStart[node] + k];
-        incStart[node] = ns; incCap[node] = nc;
+        for (int32_t k = 0; k < incLen[v]; ++k) pool[ns + k] = pool[incStart[v] + k];
+        incStart[v] = ns; incCap[v] = nc;
     }
-    Inc e; e.arc = arc; e.nbr = nbr;
-    pool[incStart[node] + incLen[node]++] = e;
+    Inc e; e.arc = arc; e.nbr = nbr; e.pos = pos;
+    pool[incStart[v] + incLen[v]++] = e;
+}
+
+int32_t Forest::posOfArc(int32_t a, int32_t u, int32_t v) const
+{
+    for (int side = 0; side < 2; ++side) {
+        const int32_t w = side ? v : u;
+        const int64_t base = incStart[w];
+        for (int32_t k = 0; k < incLen[w]; ++k) if (pool[base + k].arc == a && pool[base + k].pos >= 0) return pool[base + k].pos;
+    }
+    return -1;
 }
 
 void Forest::compactPool()
@@ -101,17 +114,35 @@ void Forest::compactPool()
 // Tree::mergeTxAndTII (trees.cpp:365-395)
 void Forest::mergeInto(int32_t tX, int32_t tII, int32_t av)
 {
+    const double t0 = nowS();
+    if (trees[tX].rooted) {                              // remember where the new subtree hangs
+        Attach at;
+        at.arc = av;
+        if (node[tail[av]].slot == tX) { at.parent = tail[av]; at.child = head[av]; }
+        else { at.parent = head[av]; at.child = tail[av]; }
+        trees[tX].pending.push_back(at);
+    }
     relabel(tII, tX);
     Tree &x = trees[tX];
     Tree &y = trees[tII];
+    // y's arcs keep their relative order behind x's: shift the positions held in y's incident entries
+    const int32_t shift = (int32_t) x.arcs.size();
+    if (shift && !y.arcs.empty()) {
+        for (size_t q = 0; q < y.nodes.size(); ++q) {
+            const int32_t w = y.nodes[q];
+            const int64_t base = incStart[w];
+            for (int32_t k = 0; k < incLen[w]; ++k) if (pool[base + k].pos >= 0) pool[base + k].pos += shift;
+        }
+    }
     x.nodes.insert(x.nodes.end(), y.nodes.begin(), y.nodes.end());
-    for (size_t k = 0; k < y.arcs.size(); ++k) { arcPos[y.arcs[k]] = (int32_t) x.arcs.size(); x.arcs.push_back(y.arcs[k]); }
-    arcPos[av] = (int32_t) x.arcs.size();
+    x.arcs.insert(x.arcs.end(), y.arcs.begin(), y.arcs.end());
+    const int32_t pav = (int32_t) x.arcs.size();
     x.arcs.push_back(av);
-    incPush(tail[av], av, head[av]);
-    incPush(head[av], av, tail[av]);
+    incPush(tail[av], av, head[av], pav);
+    incPush(head[av], av, tail[av], -1);
     touch(tX);
     freeTree(tII);
+    secsMerge += nowS() - t0;
 }
 
 // Tree::expandTreeUsingArc (trees.cpp:398-437)
@@ -119,16 +150,17 @@ void Forest::expandWithArc(int32_t t, int32_t av)
 {
     const int32_t u = tail[av], v = head[av];
     Tree &x = trees[t];
-    if (treeSlot[u] != t) { x.nodes.push_back(u); setSlot(u, t); }
-    else if (treeSlot[v] != t) { x.nodes.push_back(v); setSlot(v, t); }
+    if (node[u].slot != t) { x.nodes.push_back(u); setSlot(u, t); }
+    else if (node[v].slot != t) { x.nodes.push_back(v); setSlot(v, t); }
     if (u != v) {
-        arcPos[av] = (int32_t) x.arcs.size();
+        const int32_t pav = (int32_t) x.arcs.size();
         x.arcs.push_back(av);
-        incPush(u, av, v);
-        incPush(v, av, u);
+        incPush(u, av, v, pav);
+        incPush(v, av, u, -1);
     } else {
         x.extraArc = av;
     }
+    x.rooted = false;                                    // grown arc by arc: re-thread from the root
     touch(t);
 }
 
@@ -136,7 +168,7 @@ void Forest::expandWithArc(int32_t t, int32_t av)
 int Forest::insertArc(int32_t av)
 {
     const int32_t u = tail[av], v = head[av];
-    const int32_t tU = treeSlot[u], tV = treeSlot[v];
+    const int32_t tU = node[u].slot, tV = node[v].slot;
     if (tU >= 0 && tV >= 0) {
         if (tU == tV) {
             if (trees[tU].type == TREE_I) return -2;     // "Insertion adds cycle to type I tree"
@@ -165,6 +197,7 @@ int Forest::insertArc(int32_t av)
 // fresh trees; tree ids have no observable effect), so its nodes keep their slot.
 int32_t Forest::split(int32_t tOld, int32_t removedArc)
 {
+    const double t0 = nowS();
     const int32_t bottom = newTree(TREE_II, -1);         // may grow `trees`: take references afterwards
     const int32_t top = tOld;
     const int32_t oldRoot = trees[top].root;
@@ -173,6 +206,7 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
         oldNodes.clear(); oldArcs.clear();
         oldNodes.swap(o.nodes); oldArcs.swap(o.arcs);    // recycle capacity; contents are rebuilt below
         o.type = TREE_II; o.extraArc = -1; o.root = -1;
+        o.threadsValid = false;                          // a block of the thread disappears; the rooting of the rest stays
         touch(top);
     }
     int32_t cur = top;
@@ -181,33 +215,35 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
     curStack.push_back(oldRoot);
     prevStack.push_back(-1);
     while (!curStack.empty()) {
-        int32_t node = curStack.back(); curStack.pop_back();
-        if (node < 0) {
+        int32_t nd = curStack.back(); curStack.pop_back();
+        if (nd < 0) {
             cur = top;
             if (curStack.empty()) break;
-            node = curStack.back(); curStack.pop_back();
+            nd = curStack.back(); curStack.pop_back();
         }
         const int32_t prev = prevStack.back(); prevStack.pop_back();
         Tree &tc = trees[cur];
-        setSlot(node, cur);
-        if (tc.nodes.empty()) tc.root = node;
-        tc.nodes.push_back(node);
+        setSlot(nd, cur);
+        if (tc.nodes.empty()) tc.root = nd;
+        tc.nodes.push_back(nd);
         int32_t removedInd = -1, removedNbr = -1;
-        const int64_t base = incStart[node];
-        const int32_t len = incLen[node];
+        const int64_t base = incStart[nd];
+        const int32_t len = incLen[nd];
         for (int32_t k = 0; k < len; ++k) {
-            const Inc e = pool[base + k];
+            Inc &e = pool[base + k];
             if (e.arc == removedArc) { removedInd = k; removedNbr = e.nbr; continue; }
             if (e.nbr != prev) {
-                arcPos[e.arc] = (int32_t) tc.arcs.size();
+                e.pos = (int32_t) tc.arcs.size();       // the arc's index in arcs(tree) lives with its discoverer
                 tc.arcs.push_back(e.arc);
                 curStack.push_back(e.nbr);
-                prevStack.push_back(node);
+                prevStack.push_back(nd);
+            } else {
+                e.pos = -1;
             }
         }
         if (removedInd >= 0) {
             pool[base + removedInd] = pool[base + len - 1];
-            --incLen[node];
+            --incLen[nd];
             if (prev > -2) {
                 curStack.push_back(-1);
                 curStack.push_back(removedNbr);
@@ -216,6 +252,8 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
             }
         }
     }
+    secsSplit += nowS() - t0;
+    nodesSplit += (int64_t) (trees[top].nodes.size() + trees[bottom].nodes.size());
     if (trees[bottom].nodes.empty()) { freeTree(bottom); return -1; }
     return bottom;
 }
@@ -224,8 +262,8 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
 int Forest::removeArc(int32_t av)
 {
     const int32_t u = tail[av], v = head[av];
-    if (treeSlot[u] != treeSlot[v] || treeSlot[u] < 0) return -4;   // "remove arc spanning two trees"
-    const int32_t t = treeSlot[u];
+    if (node[u].slot != node[v].slot || node[u].slot < 0) return -4;   // "remove arc spanning two trees"
+    const int32_t t = node[u].slot;
     if (trees[t].type == TREE_I && av == trees[t].extraArc) {
         trees[t].type = TREE_II;                         // convertTItoTII: threads stay valid
         trees[t].extraArc = -1;
@@ -242,6 +280,7 @@ int Forest::removeArc(int32_t av)
 // Tree::initializeTreeIndices (trees.cpp:597-644) + the dirty-node list
 void Forest::reindex(int32_t slot)
 {
+    const double t0 = nowS();
     Tree &t = trees[slot];
     std::vector<int32_t> &nodeStack = stackA, &arcStack = stackB, &predStack = stackC;
     nodeStack.clear(); arcStack.clear(); predStack.clear();
@@ -255,16 +294,16 @@ void Forest::reindex(int32_t slot)
         const int32_t cur = nodeStack.back(); nodeStack.pop_back();
         const int32_t pa = arcStack.back(); arcStack.pop_back();
         const int32_t predNode = predStack.back(); predStack.pop_back();
-        const bool dirty = (nodeFlag[cur] & 1) || pred[cur] != predNode || predArc[cur] != pa ||
-                           (predNode >= 0 && (nodeFlag[predNode] & 2));
-        nodeFlag[cur] = dirty ? 2 : 0;
+        NodeRec &r = node[cur];
+        const bool dirty = (r.flag & 1) || r.pred != predNode || r.predArc != pa || (predNode >= 0 && (node[predNode].flag & 2));
+        r.flag = dirty ? 2 : 0;
         if (dirty) dirtyNodes.push_back(cur);
-        depth[cur] = (predNode >= 0) ? depth[predNode] + 1 : 0;
-        predArc[cur] = pa;
-        pred[cur] = predNode;
-        if (last >= 0) thread[last] = cur;
+        r.depth = (predNode >= 0) ? node[predNode].depth + 1 : 0;
+        r.predArc = pa;
+        r.pred = predNode;
+        if (last >= 0) node[last].thread = cur;
         last = cur;
-        threadPos[cur] = (int32_t) t.threads.size();
+        r.threadPos = (int32_t) t.threads.size();
         t.threads.push_back(cur);
         const int64_t base = incStart[cur];
         for (int32_t k = incLen[cur] - 1; k >= 0; --k) {
@@ -275,10 +314,85 @@ void Forest::reindex(int32_t slot)
             predStack.push_back(cur);
         }
     }
-    thread[last] = t.root;
+    node[last].thread = t.root;
+    t.rooted = true; t.threadsValid = true; t.pending.clear();
+    secsReindex += nowS() - t0;
+    nodesReindex += (int64_t) t.threads.size(); ++callsReindex;
 }
 
-// Tree::updateTrees (trees.cpp:572-591), restricted to the trees touched since the last call
+// A subtree hung under at.parent through at.arc: pred / predArc / depth of its nodes only.  The
+// rest of the tree keeps its rooting, so nothing else has to be visited.
+void Forest::rethreadSubtree(int32_t slot, const Attach &at)
+{
+    const double t0 = nowS();
+    std::vector<int32_t> &nodeStack = stackA, &arcStack = stackB, &predStack = stackC;
+    nodeStack.clear(); arcStack.clear(); predStack.clear();
+    nodeStack.push_back(at.child);
+    arcStack.push_back(at.arc);
+    predStack.push_back(at.parent);
+    int64_t visited = 0;
+    while (!nodeStack.empty()) {
+        const int32_t cur = nodeStack.back(); nodeStack.pop_back();
+        const int32_t pa = arcStack.back(); arcStack.pop_back();
+        const int32_t predNode = predStack.back(); predStack.pop_back();
+        NodeRec &r = node[cur];
+        const bool dirty = (r.flag & 1) || r.pred != predNode || r.predArc != pa || (node[predNode].flag & 2);
+        r.flag = dirty ? 2 : 0;
+        if (dirty) dirtyNodes.push_back(cur);
+        r.depth = node[predNode].depth + 1;
+        r.predArc = pa;
+        r.pred = predNode;
+        ++visited;
+        const int64_t base = incStart[cur];
+        for (int32_t k = incLen[cur] - 1; k >= 0; --k) {
+            const Inc e = pool[base + k];
+            if (e.nbr == predNode) continue;
+            nodeStack.push_back(e.nbr);
+            arcStack.push_back(e.arc);
+            predStack.push_back(cur);
+        }
+    }
+    (void) slot;
+    secsReindex += nowS() - t0;
+    nodesReindex += visited; ++callsReindex;
+}
+
+// preorder thread (initializeTreeIndices' visiting order) rebuilt from the rooting, when somebody needs it
+void Forest::ensureThreads(int32_t slot)
+{
+    Tree &t = trees[slot];
+    if (t.threadsValid || t.type == TREE_FREE) return;
+    std::vector<int32_t> &nodeStack = stackA;
+    nodeStack.clear();
+    t.threads.clear();
+    t.threads.reserve(t.nodes.size());
+    nodeStack.push_back(t.root);
+    int32_t last = -1;
+    while (!nodeStack.empty()) {
+        const int32_t cur = nodeStack.back(); nodeStack.pop_back();
+        NodeRec &r = node[cur];
+        if (last >= 0) node[last].thread = cur;
+        last = cur;
+        r.threadPos = (int32_t) t.threads.size();
+        t.threads.push_back(cur);
+        const int64_t base = incStart[cur];
+        for (int32_t k = incLen[cur] - 1; k >= 0; --k) if (pool[base + k].nbr != r.pred) nodeStack.push_back(pool[base + k].nbr);
+    }
+    node[last].thread = t.root;
+    t.threadsValid = true;
+}
+
+int32_t Forest::incidentIndex(int32_t v, int32_t a) const
+{
+    const int64_t base = incStart[v];
+    for (int32_t k = 0; k < incLen[v]; ++k) if (pool[base + k].arc == a) return k;
+    return -1;
+}
+
+// Tree::updateTrees (trees.cpp:572-591), restricted to the trees touched since the last call.  A
+// tree whose root stays (the extra arc did not change) keeps the rooting of everything that was in
+// it: removing a subtree changes no other node's predecessor, and a subtree hung in through a
+// new arc only needs its own nodes re-rooted.  Only a changed root forces the full DFS.
 void Forest::updateTrees()
 {
     if (pool.size() > (size_t) 12 * n + 4096) compactPool();
@@ -287,8 +401,15 @@ void Forest::updateTrees()
         Tree &t = trees[slot];
         t.queued = false;
         if (t.type == TREE_FREE || t.upToDate) continue;
-        if (t.type == TREE_I) t.root = tail[t.extraArc];  // keep the root on the cycle (:578)
-        reindex(slot);
+        const int32_t newRoot = (t.type == TREE_I) ? tail[t.extraArc] : t.root;   // keep the root on the cycle (:578)
+        if (!t.rooted || newRoot != t.root) {
+            t.root = newRoot;
+            reindex(slot);
+        } else {
+            for (size_t q = 0; q < t.pending.size(); ++q) rethreadSubtree(slot, t.pending[q]);
+            t.pending.clear();
+            t.threadsValid = false;
+        }
         t.upToDate = true;
     }
     stale.clear();

@@ -10,9 +10,11 @@
 // touched since the last update are re-threaded (trees.cpp:572-591 scans every tree), incident
 // lists sit in one pool and carry the neighbour node, so a DFS never touches the arc arrays.
 // On top of the reference's fields it records what makes the per-pivot work sparse:
-//   * arcPos[a]     index of a in arcs(tree)          -> ratio test over the few arcs with flow change
-//   * threadPos[v]  index of v in threads(tree)       -> flow sweep over the three root paths only
+//   * posOfArc(a)   index of a in arcs(tree)          -> ratio test over the few arcs with flow change
+//   * threadPos     index of a node in threads(tree)  -> flow sweep over the three root paths only
 //   * dirtyNodes    nodes whose root path or tree changed, in thread order -> potential sweep
+// Per-node fields live in one 32-byte record and the arc position rides in the incident entry of
+// the node the arc was discovered from, so a DFS touches about two cache lines per node.
 #pragma once
 #include <stdint.h>
 #include <vector>
@@ -21,18 +23,32 @@ namespace gneb200 {
 
 enum { TREE_FREE = 0, TREE_I = 1, TREE_II = 2 };        // variables.h:25 tree_type
 
+struct Attach { int32_t arc, parent, child; };          // a subtree hung under `parent` through `arc` since the last re-thread
+
 struct Tree {
     int8_t type = TREE_FREE;
     bool upToDate = false;
     bool queued = false;                                // in Forest::stale
+    bool rooted = false;                                // pred/predArc/depth valid w.r.t. root (except `pending` subtrees)
+    bool threadsValid = false;                          // `threads` (and Node::thread / threadPos) match the structure
+    std::vector<Attach> pending;
     int32_t root = -1;
     int32_t extraArc = -1;
     std::vector<int32_t> nodes;                         // Tree::nodesInTree
     std::vector<int32_t> arcs;                          // Tree::arcsInTree
-    std::vector<int32_t> threads;                       // Tree::threads
+    std::vector<int32_t> threads;                       // Tree::threads (rebuilt lazily: Forest::ensureThreads)
 };
 
-struct Inc { int32_t arc, nbr; };                       // incident arc + the node at its other end
+// incident arc, the node at its other end, and (in the entry of the node the arc was discovered
+// from / appended at; -1 in the other one) its index in arcs(tree)
+struct Inc { int32_t arc, nbr, pos; };
+
+struct NodeRec {                                        // Node's tree fields (variables.h:63-76) + bookkeeping
+    int32_t slot = -1;                                  // memberOfTreeID (stable slot)
+    int32_t pred = -1, predArc = -1, depth = -1, thread = -1;
+    int32_t threadPos = -1;
+    uint8_t flag = 1;                                   // bit0: slot changed since last re-thread, bit1: dirty in this pass
+};
 
 class Forest {
   public:
@@ -43,10 +59,21 @@ class Forest {
     int insertArc(int32_t av);
     int removeArc(int32_t av);
     void updateTrees();
+    // The preorder thread of a tree is only needed by the full flow recompute, the full potential
+    // sweep and the accessors used in tests; pivots that keep a tree's root only re-thread the
+    // subtrees that were hung into it, so the thread vector is rebuilt on demand.
+    void ensureThreads(int32_t slot);
+    // index of the incident entry of arc a in node v's list (order of v's children in the thread)
+    int32_t incidentIndex(int32_t v, int32_t a) const;
 
-    int32_t treeOf(int32_t node) const { return treeSlot[node]; }
+    int32_t treeOf(int32_t v) const { return node[v].slot; }
+    int32_t predOf(int32_t v) const { return node[v].pred; }
+    int32_t predArcOf(int32_t v) const { return node[v].predArc; }
+    int32_t threadPosOf(int32_t v) const { return node[v].threadPos; }
     const Tree &tree(int32_t slot) const { return trees[slot]; }
-    int8_t typeOf(int32_t node) const { return treeSlot[node] < 0 ? (int8_t) TREE_FREE : trees[treeSlot[node]].type; }
+    int8_t typeOf(int32_t v) const { return node[v].slot < 0 ? (int8_t) TREE_FREE : trees[node[v].slot].type; }
+    // index of basic arc a (ends u, v) in arcs(tree): scans the two short incident lists
+    int32_t posOfArc(int32_t a, int32_t u, int32_t v) const;
     int numSlots() const { return (int) trees.size(); }
 
     // slots whose structure or extra arc changed since the caller last cleared this list
@@ -56,11 +83,11 @@ class Forest {
     // nodes whose (pred, predArc), an ancestor's, or whose slot changed in the last re-threading,
     // grouped by tree and in thread order (parents before children); cleared by the consumer
     std::vector<int32_t> dirtyNodes;
+    void clearDirty() { for (size_t k = 0; k < dirtyNodes.size(); ++k) node[dirtyNodes[k]].flag &= (uint8_t) ~2; dirtyNodes.clear(); }
 
-    // per node
-    std::vector<int32_t> treeSlot, pred, predArc, depth, thread, threadPos;
-    // per arc variable
-    std::vector<int32_t> arcPos;
+    std::vector<NodeRec> node;
+    double secsSplit = 0, secsReindex = 0, secsMerge = 0;
+    int64_t nodesSplit = 0, nodesReindex = 0, callsReindex = 0;   // wall-clock split of the forest work
 
   private:
     int n = 0;
@@ -68,13 +95,12 @@ class Forest {
     std::vector<Tree> trees;
     std::vector<int32_t> freeSlots;
     std::vector<int32_t> stale;                         // slots with upToDate == false
-    std::vector<uint8_t> nodeFlag;                      // bit0: slot changed since last re-thread, bit1: dirty in this pass
 
     // incident lists (Node::incidentArcs): push_back / swap-with-last removal, pooled
     std::vector<Inc> pool;
     std::vector<int64_t> incStart;
     std::vector<int32_t> incLen, incCap;
-    void incPush(int32_t node, int32_t arc, int32_t nbr);
+    void incPush(int32_t v, int32_t arc, int32_t nbr, int32_t pos);
     void compactPool();
 
     std::vector<int32_t> stackA, stackB, stackC;        // DFS scratch
@@ -84,11 +110,12 @@ class Forest {
     void freeTree(int32_t slot);
     void relabel(int32_t slot, int32_t newSlot);
     void touch(int32_t slot);                           // upToDate = false
-    void setSlot(int32_t node, int32_t slot) { if (treeSlot[node] != slot) { treeSlot[node] = slot; nodeFlag[node] |= 1; } }
+    void setSlot(int32_t v, int32_t slot) { NodeRec &r = node[v]; if (r.slot != slot) { r.slot = slot; r.flag |= 1; } }
     void mergeInto(int32_t tX, int32_t tII, int32_t av);
     void expandWithArc(int32_t t, int32_t av);
     int32_t split(int32_t t, int32_t removedArc);       // returns the slot of the bottom part; t keeps the top
     void reindex(int32_t slot);
+    void rethreadSubtree(int32_t slot, const Attach &at);
 };
 
 } // namespace gneb200

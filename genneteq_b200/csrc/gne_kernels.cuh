@@ -491,7 +491,7 @@ struct QsState {            // mapped pinned host memory; carried across windows
 };
 
 __global__ void __launch_bounds__(TILE_THREADS)
-k_qs_finish(NbView nb, const double *__restrict__ pi, int64_t cursor, int64_t N, int64_t jLo, int64_t jHi,
+k_qs_finish(NbView nb, const double *__restrict__ pi, int64_t cursor, int64_t N, int64_t jLo, int64_t jHi, int64_t jEnd,
             QsTiles tiles, int G, int64_t want, QsState *st)
 {
     const int t = threadIdx.x;
@@ -557,7 +557,7 @@ k_qs_finish(NbView nb, const double *__restrict__ pi, int64_t cursor, int64_t N,
         st->bestV = prev.v; st->bestJ = prev.p;
         st->violations = seen;
         st->stopJ = stopJ;
-        st->done = (stopJ >= 0 || jHi >= N) ? 1 : 0;
+        st->done = (stopJ >= 0 || jHi >= jEnd) ? 1 : 0;
     }
 }
 

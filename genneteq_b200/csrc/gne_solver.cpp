@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <time.h>
 
@@ -185,6 +186,7 @@ void GenNetEq::checkVarForBlocking(int32_t v)                     // genneteq.h:
 // ------------------------------------------------------------------------------------------
 void GenNetEq::computeFlowsTypeI(int32_t slot)                    // gneFlow.cpp:480-560
 {
+    forest.ensureThreads(slot);
     const Tree &t = forest.tree(slot);
     const int32_t ex = t.extraArc;
     const int32_t alpha = tail[ex], beta = head[ex];
@@ -196,7 +198,7 @@ void GenNetEq::computeFlowsTypeI(int32_t slot)                    // gneFlow.cpp
     for (int64_t k = (int64_t) t.threads.size() - 1; k >= 0; --k) {
         const int32_t j = t.threads[k];
         if (j == h) break;
-        const int32_t a = forest.predArc[j];
+        const int32_t a = forest.predArcOf(j);
         const double mu = mult[a];
         if (tail[a] == j) {
             const int32_t i = head[a];
@@ -290,16 +292,44 @@ void GenNetEq::computeFlowsSparse(int32_t slot, const int32_t *starts, int nStar
     st[ns++] = alpha; st[ns++] = beta;
     for (int k = 0; k < ns; ++k) {
         int32_t v = st[k];
-        while (v >= 0 && !nodeMark[v]) { nodeMark[v] = 1; activeNodes.push_back(v); v = forest.pred[v]; }
+        while (v >= 0 && !nodeMark[v]) { activeNodes.push_back(v); nodeMark[v] = (int32_t) activeNodes.size(); v = forest.predOf(v); }
     }
-    const std::vector<int32_t> &tp = forest.threadPos;
-    std::sort(activeNodes.begin(), activeNodes.end(), [&tp](int32_t a, int32_t b) { return tp[a] > tp[b]; });
+    // Reverse thread order restricted to the active nodes = post-order of the tree they form, the
+    // children of a junction taken from the last incident entry to the first (the thread visits a
+    // node's children in incident order, trees.cpp:626-640) - no thread positions needed.
+    const size_t na = activeNodes.size();
+    actHead.assign(na, -1); actNext.assign(na, -1);
+    for (size_t q = 0; q < na; ++q) {
+        const int32_t j = activeNodes[q];
+        if (j == h) continue;
+        const int32_t pq = nodeMark[forest.predOf(j)] - 1;
+        actNext[q] = actHead[pq]; actHead[pq] = (int32_t) q;
+    }
+    actOrder.clear(); actStack.clear();
+    actStack.push_back(nodeMark[h] - 1);
+    while (!actStack.empty()) {
+        const int32_t top = actStack.back(); actStack.pop_back();
+        if (top < 0) { actOrder.push_back(activeNodes[-top - 1]); continue; }
+        actStack.push_back(-top - 1);                   // emit after the children
+        actKids.clear();
+        for (int32_t c = actHead[top]; c >= 0; c = actNext[c]) actKids.push_back(c);
+        if (actKids.size() > 1) {
+            const int32_t p = activeNodes[top];
+            const Forest &fr = forest;
+            const std::vector<int32_t> &an = activeNodes;
+            std::sort(actKids.begin(), actKids.end(), [&fr, &an, p](int32_t x, int32_t y) {
+                return fr.incidentIndex(p, fr.predArcOf(an[x])) < fr.incidentIndex(p, fr.predArcOf(an[y])); });
+        }
+        // the child with the highest incident index is processed first: push it last
+        for (size_t c = 0; c < actKids.size(); ++c) actStack.push_back(actKids[c]);
+    }
+    for (size_t q = 0; q < na; ++q) nodeMark[activeNodes[q]] = 0;
+    activeNodes.swap(actOrder);
     activeArcs.clear();
     for (size_t q = 0; q < activeNodes.size(); ++q) {
         const int32_t j = activeNodes[q];
-        nodeMark[j] = 0;
         if (j == h) continue;
-        const int32_t a = forest.predArc[j];
+        const int32_t a = forest.predArcOf(j);
         const double mu = mult[a];
         if (tail[a] == j) {
             const int32_t i = head[a];
@@ -318,8 +348,14 @@ void GenNetEq::computeFlowsSparse(int32_t slot, const int32_t *starts, int nStar
     }
     const double theta = (-1.0 * supA0[h]) / supA1[h];
     supA0[h] = 0.0; supA1[h] = 0.0;
-    const std::vector<int32_t> &ap = forest.arcPos;
-    std::sort(activeArcs.begin(), activeArcs.end(), [&ap](int32_t a, int32_t b) { return ap[a] < ap[b]; });
+    // ratio test in arcsInTree order: sort the few active arcs by their index in arcs(tree)
+    activeKeys.clear();
+    for (size_t k = 0; k < activeArcs.size(); ++k) {
+        const int32_t a = activeArcs[k];
+        activeKeys.push_back(std::make_pair(forest.posOfArc(a, tail[a], head[a]), a));
+    }
+    std::sort(activeKeys.begin(), activeKeys.end());
+    for (size_t k = 0; k < activeArcs.size(); ++k) activeArcs[k] = activeKeys[k].second;
     for (size_t k = 0; k < activeArcs.size(); ++k) {
         const int32_t a = activeArcs[k];
         const double p = flowA1[a] * theta;
@@ -357,12 +393,12 @@ void GenNetEq::applyFlowSparse(int32_t slot, const std::vector<int32_t> &activeA
 // predecessor; records the node for upload when (a0, a1, slot) differ from what the device holds.
 inline bool GenNetEq::relabelNode(int32_t j, int32_t slot)
 {
-    const int32_t i = forest.pred[j];
+    const int32_t i = forest.predOf(j);
     double a0, a1;
     if (i < 0) {                                        // root: pi_h = theta  (:78-82)
         a0 = 0.0; a1 = 1.0;
     } else {
-        const int32_t a = forest.predArc[j];
+        const int32_t a = forest.predArcOf(j);
         const double c0 = cost[a], mu = mult[a];
         if (tail[a] == i) {                             // pi(j) = (pi(i) - c_ij) / mu_ij
             a0 = (potA0[i] - c0) / mu;
@@ -389,8 +425,9 @@ int GenNetEq::computePotentials()
     if (allPotDirty) {
         // costs changed (phase start): every tree is swept in thread order
         for (size_t c = 0; c < forest.changed.size(); ++c) {
+            if (forest.tree(forest.changed[c]).type == TREE_FREE) continue;
+            forest.ensureThreads(forest.changed[c]);
             const Tree &t = forest.tree(forest.changed[c]);
-            if (t.type == TREE_FREE) continue;
             for (size_t q = 0; q < t.threads.size(); ++q) relabelNode(t.threads[q], forest.changed[c]);
         }
         finalizeAll = true;
@@ -401,7 +438,7 @@ int GenNetEq::computePotentials()
             if (relabelNode(j, forest.treeOf(j))) upFinal.push_back(j);
         }
     }
-    forest.dirtyNodes.clear();
+    forest.clearDirty();
     for (size_t c = 0; c < forest.changed.size(); ++c) {
         const int32_t slot = forest.changed[c];
         forest.changedFlag[slot] = 0;
@@ -892,12 +929,12 @@ int GenNetEq::replayTrace(int draws, int64_t p1, int64_t total, const int32_t *e
         computeFlows(0);
         const int64_t end = pre ? p1 : total;
         for (; k < end; ++k) {
-            if ((loopIter % 1000) == 0) computeFlows(2);
-            GNE_TRY(computePotentials());
+            if ((loopIter % 1000) == 0) { const double q0 = wallNow(); computeFlows(2); secsTotal += wallNow() - q0; }
+            { const double q0 = wallNow(); GNE_TRY(computePotentials()); secsPotentials += wallNow() - q0; }
             if (cyclingDetected) (void) drand48();
             else for (int d = 0; d < draws; ++d) (void) drand48();
             eVar = e[k];
-            GNE_TRY(pivot());
+            { const double q0 = wallNow(); GNE_TRY(pivot()); secsPivot += wallNow() - q0; }
             if (lVar != l[k]) { *mismatch = k; return GNE_OK; }
             ++loopIter; ++pivots;
         }
@@ -908,6 +945,11 @@ int GenNetEq::replayTrace(int draws, int64_t p1, int64_t total, const int32_t *e
         if (presolve) checkFeasibility();
         GNE_TRY(computePotentials());
     }
+    if (getenv("GNE_HOST_PROFILE"))
+        fprintf(stderr, "host replay: pivot %.3f s, potentials %.3f s, periodic full flows %.3f s; flows %.3f s, trees %.3f s (split %.3f, reindex %.3f, merge %.3f)\n",
+                secsPivot, secsPotentials, secsTotal, secsFlows, secsTrees,
+                forest.secsSplit, forest.secsReindex, forest.secsMerge),
+        fprintf(stderr, "  nodes visited: split %lld, reindex %lld in %lld calls\n", (long long) forest.nodesSplit, (long long) forest.nodesReindex, (long long) forest.callsReindex);
     return GNE_OK;
 }
 

@@ -81,6 +81,7 @@ class GenNetEq {
     int getPotentials(double *out);
     void getStates(int32_t *out) const;
     const Forest &getForest() const { return forest; }
+    Forest &getForestMutable() { return forest; }
     void getCounters(double *out12) const;
     int replayTrace(int draws, int64_t p1, int64_t total, const int32_t *e, const int32_t *l, int64_t *mismatch);
     void setSparseFlows(bool on) { sparseFlows = on; }
@@ -146,8 +147,10 @@ class GenNetEq {
     std::vector<double> upA0, upA1, upTheta;
     int status = GNE_OK;
     bool allPotDirty = true, hostOnly = false, sparseFlows = true;
-    std::vector<uint8_t> nodeMark;
+    std::vector<int32_t> nodeMark;
+    std::vector<int32_t> actHead, actNext, actOrder, actStack, actKids;
     std::vector<int32_t> activeNodes, activeArcsU, activeArcsV;
+    std::vector<std::pair<int32_t, int32_t> > activeKeys;
 
     // ---- trace / counters
     int32_t *traceE = nullptr, *traceL = nullptr;
