@@ -26,6 +26,7 @@ from oracle_util import RULES, Instance, Oracle, oracle_lib, dp, ip, lp, bp  # n
 
 def main():
     mode, out = sys.argv[1], sys.argv[2]
+    rule = sys.argv[3] if len(sys.argv) > 3 else "LV"
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", "0"))
     gold = np.load(os.path.join(HERE, "golden", "c1_wide_s7.npz"))
     inst = Instance.load(os.path.join(HERE, "golden", "c1_wide_s7_instance.npz"))
@@ -39,12 +40,12 @@ def main():
             uid = torch.from_numpy(buf)
         uid = uid.cuda()
         dist.broadcast(uid, 0)
-        s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, device=local, rule1="LV")
+        s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, device=local, rule1=rule)
         s.set_comm(uid.cpu().numpy(), rank, world)
         p1, p2 = s.solve_both()
         e, l = s.trace
-        ok = (p1, p2) == tuple(int(v) for v in gold["LV_p"]) and np.array_equal(e, gold["LV_e"]) and np.array_equal(l, gold["LV_l"])
-        ok = ok and s.objective == float(gold["LV_objective"]) and np.array_equal(s.flows(), gold["LV_flows"])
+        ok = (p1, p2) == tuple(int(v) for v in gold[rule + "_p"]) and np.array_equal(e, gold[rule + "_e"]) and np.array_equal(l, gold[rule + "_l"])
+        ok = ok and s.objective == float(gold[rule + "_objective"]) and np.array_equal(s.flows(), gold[rule + "_flows"])
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:

@@ -8,12 +8,12 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def launch(mode, nproc, out, port, extra_env=None):
+def launch(mode, nproc, out, port, extra_env=None, rule="LV"):
     env = dict(os.environ)
     env.update(extra_env or {})
     env["MASTER_ADDR"] = "127.0.0.1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py"), mode, out]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py"), mode, out, rule]
     subprocess.run(cmd, check=True, env=env, timeout=900, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     return open(out).read()
 
@@ -22,6 +22,18 @@ def test_sharded_lv_exchange_host_logic_gloo(tmp_path):
     import __graft_entry__ as ge
     ge.build()
     assert launch("gloo", 2, str(tmp_path / "gloo.txt"), 29611) == "OK"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rule,exchange", [("QS", "p2p"), ("CL", "p2p"), ("QS", "nccl")])
+def test_sharded_solve_two_gpus_other_rules(tmp_path, rule, exchange):
+    """quickSelect (two-round blob exchange) and the candidate-list rule (gathered violator lists) over 2 GPUs."""
+    import genneteq_b200 as gne
+    if gne.cuda_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    env = {"GNE_EXCHANGE": "nccl"} if exchange == "nccl" else {}
+    port = 29620 + ["QS", "CL"].index(rule) * 2 + (1 if exchange == "nccl" else 0)
+    assert launch("nccl", 2, str(tmp_path / (rule + exchange + ".txt")), port, env, rule) == "OK"
 
 
 @pytest.mark.gpu
