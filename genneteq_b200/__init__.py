@@ -62,6 +62,7 @@ SIGNATURES = {
     "gne_price_first": (C.c_int, [_vp, _i64p]),
     "gne_reduced_costs": (C.c_int, [_vp, C.c_int64, C.c_int64, _f64p]),
     "gne_dev_last_kernel_ms": (C.c_int, [_vp, _f32p]),
+    "gne_dev_set_timing": (C.c_int, [_vp, C.c_int]),
     "gne_dev_launch_count": (C.c_int64, [_vp]),
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
     "gne_bench_variants": (C.c_int, [_vp, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int)]),
@@ -98,6 +99,11 @@ SIGNATURES = {
                                   C.c_int64, C.c_int64, _i32p, _i32p, _i64p, _f64p, _f64p, _f64p]),
     "gne_merge_lv_shards": (C.c_int, [C.c_int, _f64p, C.POINTER(C.c_int), _i64p, _i64p, _f64p, C.c_int64,
                                       _f64p, _i64p, _i64p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gne_write_col": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
+    "gne_read_col": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), _i64p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p]),
+    "gne_write_bin": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
+    "gne_read_bin_header": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), _i64p]),
+    "gne_read_bin": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
     "gne_generate_instance": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
@@ -138,6 +144,35 @@ def generate_instance(n, m, seed, mode="lossy"):
     _ck(lib.gne_generate_instance(n, m, seed, mode_id, _p(tail, _i32p), _p(head, _i32p), _p(ub, _f64p), _p(cost, _f64p),
                                   _p(mult, _f64p), _p(supply, _f64p)), "gne_generate_instance")
     return dict(n=n, tail=tail, head=head, ub=ub, cost=cost, mult=mult, supply=supply)
+
+
+def write_instance(path, inst, binary=False):
+    """inst: dict(n, tail, head, ub, cost, mult, supply); text (reference format) or binary SoA."""
+    t = _arr(inst["tail"], np.int32); h = _arr(inst["head"], np.int32); ub = _arr(inst["ub"], np.float64)
+    c = _arr(inst["cost"], np.float64); mu = _arr(inst["mult"], np.float64); s = _arr(inst["supply"], np.float64)
+    fn = lib.gne_write_bin if binary else lib.gne_write_col
+    _ck(fn(path.encode(), int(inst["n"]), len(t), _p(t, _i32p), _p(h, _i32p), _p(ub, _f64p), _p(c, _f64p), _p(mu, _f64p),
+           _p(s, _f64p)), "gne_write_bin" if binary else "gne_write_col")
+
+
+def read_instance(path, binary=False):
+    n = C.c_int(0); m = C.c_int64(0); big = C.c_double(0)
+    if binary:
+        _ck(lib.gne_read_bin_header(path.encode(), C.byref(n), C.byref(m)), "gne_read_bin_header")
+    else:
+        _ck(lib.gne_read_col(path.encode(), C.byref(n), C.byref(m), None, None, None, None, None, None, C.byref(big)), "gne_read_col")
+    t = np.empty(m.value, np.int32); h = np.empty(m.value, np.int32)
+    ub = np.empty(m.value); c = np.empty(m.value); mu = np.empty(m.value); s = np.empty(n.value)
+    if binary:
+        _ck(lib.gne_read_bin(path.encode(), n.value, m.value, _p(t, _i32p), _p(h, _i32p), _p(ub, _f64p), _p(c, _f64p),
+                             _p(mu, _f64p), _p(s, _f64p)), "gne_read_bin")
+    else:
+        _ck(lib.gne_read_col(path.encode(), C.byref(n), C.byref(m), _p(t, _i32p), _p(h, _i32p), _p(ub, _f64p), _p(c, _f64p),
+                             _p(mu, _f64p), _p(s, _f64p), C.byref(big)), "gne_read_col")
+    out = dict(n=n.value, tail=t, head=h, ub=ub, cost=c, mult=mu, supply=s)
+    if not binary:
+        out["big_m"] = big.value
+    return out
 
 
 class Device:

@@ -101,6 +101,92 @@ int Graph::initialize(Config *conf)
 }
 
 // ------------------------------------------------------------------------------------------
+// instance files: the reference's text format, written the way
+// Graph::exportColFile does (graph.cpp:94-121: comment line, `p efpgn n m 0`, `a i j 0.0 UB cost mult 0`
+// with %lf = 6 decimals, one `n` line per node), and a binary structure-of-arrays form for the sizes
+// a text file is impractical for (header + the six columns, arcs sorted by (tail, head)).
+// ------------------------------------------------------------------------------------------
+extern "C" int gne_write_col(const char *path, int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub,
+                             const double *cost, const double *mult, const double *supply)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) { gne_set_error("Unable to open file %s", path); return GNE_ERR_ARG; }
+    fprintf(f, "c   n1  n2      LB  UB  COST    MULT    EQFLW\n");
+    fprintf(f, "p efpgn %d %lld %d\n", n, (long long) m, 0);
+    for (int64_t a = 0; a < m; ++a) fprintf(f, "a %d %d %lf %lf %lf %lf %d\n", tail[a] + 1, head[a] + 1, 0.0, ub[a], cost[a], mult[a], 0);
+    for (int i = 0; i < n; ++i) fprintf(f, "n %d %lf\n", i + 1, supply[i]);
+    fclose(f);
+    return GNE_OK;
+}
+
+static const char GNE_BIN_MAGIC[8] = { 'G', 'N', 'E', 'S', 'O', 'A', '1', 0 };
+
+extern "C" int gne_write_bin(const char *path, int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub,
+                             const double *cost, const double *mult, const double *supply)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) { gne_set_error("Unable to open file %s", path); return GNE_ERR_ARG; }
+    int64_t hdr[2] = { (int64_t) n, m };
+    bool ok = fwrite(GNE_BIN_MAGIC, 1, 8, f) == 8 && fwrite(hdr, 8, 2, f) == 2;
+    ok = ok && fwrite(tail, 4, (size_t) m, f) == (size_t) m && fwrite(head, 4, (size_t) m, f) == (size_t) m;
+    ok = ok && fwrite(ub, 8, (size_t) m, f) == (size_t) m && fwrite(cost, 8, (size_t) m, f) == (size_t) m;
+    ok = ok && fwrite(mult, 8, (size_t) m, f) == (size_t) m && fwrite(supply, 8, (size_t) n, f) == (size_t) n;
+    fclose(f);
+    if (!ok) { gne_set_error("short write to %s", path); return GNE_ERR_ARG; }
+    return GNE_OK;
+}
+
+extern "C" int gne_read_bin_header(const char *path, int *n, int64_t *m)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) { gne_set_error("Unable to open file: %s", path); return GNE_ERR_ARG; }
+    char magic[8];
+    int64_t hdr[2];
+    const bool ok = fread(magic, 1, 8, f) == 8 && !memcmp(magic, GNE_BIN_MAGIC, 8) && fread(hdr, 8, 2, f) == 2;
+    fclose(f);
+    if (!ok) { gne_set_error("%s is not a genneteq_b200 binary instance", path); return GNE_ERR_ARG; }
+    *n = (int) hdr[0]; *m = hdr[1];
+    return GNE_OK;
+}
+
+extern "C" int gne_read_bin(const char *path, int n, int64_t m, int32_t *tail, int32_t *head, double *ub, double *cost,
+                            double *mult, double *supply)
+{
+    int n2; int64_t m2;
+    int rc = gne_read_bin_header(path, &n2, &m2); if (rc) return rc;
+    if (n2 != n || m2 != m) { gne_set_error("gne_read_bin: sizes differ from the header"); return GNE_ERR_ARG; }
+    FILE *f = fopen(path, "rb");
+    if (!f) { gne_set_error("Unable to open file: %s", path); return GNE_ERR_ARG; }
+    fseek(f, 24, SEEK_SET);
+    bool ok = fread(tail, 4, (size_t) m, f) == (size_t) m && fread(head, 4, (size_t) m, f) == (size_t) m;
+    ok = ok && fread(ub, 8, (size_t) m, f) == (size_t) m && fread(cost, 8, (size_t) m, f) == (size_t) m;
+    ok = ok && fread(mult, 8, (size_t) m, f) == (size_t) m && fread(supply, 8, (size_t) n, f) == (size_t) n;
+    fclose(f);
+    if (!ok) { gne_set_error("short read from %s", path); return GNE_ERR_ARG; }
+    return GNE_OK;
+}
+
+// the text format parsed sparsely into caller-sized arrays (two calls: sizes, then data)
+extern "C" int gne_read_col(const char *path, int *n, int64_t *m, int32_t *tail, int32_t *head, double *ub, double *cost,
+                            double *mult, double *supply, double *bigM)
+{
+    Config conf;
+    conf.inFile = path;
+    Graph g;
+    int rc = g.initialize(&conf);
+    if (rc) return rc;
+    const int64_t cnt = g.getNumArcs();
+    if (tail) {
+        if (*m < cnt || *n < g.getNumNodes()) { gne_set_error("gne_read_col: arrays too small"); return GNE_ERR_CAPACITY; }
+        for (int64_t a = 0; a < cnt; ++a) { tail[a] = g.tail[a]; head[a] = g.head[a]; ub[a] = g.cap[a]; cost[a] = g.cost[a]; mult[a] = g.mult[a]; }
+        for (int i = 0; i < g.getNumNodes(); ++i) supply[i] = g.supply(i);
+    }
+    *n = g.getNumNodes(); *m = cnt;
+    if (bigM) *bigM = g.getBigM();
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // layer 2 C ABI
 // ------------------------------------------------------------------------------------------
 struct gne_solver {

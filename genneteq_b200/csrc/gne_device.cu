@@ -133,6 +133,8 @@ struct gne_dev {
     int64_t qsWindow = 0;                          // adaptive window of the quickSelect scan
     NbWriteOps pending{};                          // queued gne_nb_write records (<= 8)
     bool stageInFlight = false;                    // the staging buffer feeds a kernel not yet synchronised
+    bool timing = false;                           // bracket pricing kernels with CUDA events (gne_dev_set_timing)
+    unsigned long long lvSeq = 0;                  // sequence number of the last LV pass launched
     // multi-GPU
     void *comm = nullptr;
     int rank = 0, nranks = 1;
@@ -235,6 +237,7 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     CK(cudaHostAlloc(&d->qsState, sizeof(QsState), cudaHostAllocMapped));
     CK(cudaHostAlloc(&d->hostScalar, 64, cudaHostAllocMapped));
     memset(d->lvRes, 0, sizeof(LvResult));
+    { const char *tm = getenv("GNE_TIMING"); d->timing = tm && tm[0] == '1'; }
     memset(d->qsState, 0, sizeof(QsState));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     *out = d;
@@ -273,6 +276,7 @@ extern "C" int gne_dev_sync(gne_dev *d)
 }
 
 extern "C" int gne_dev_last_kernel_ms(gne_dev *d, float *ms) { *ms = d->lastMs; return GNE_OK; }
+extern "C" int gne_dev_set_timing(gne_dev *d, int on) { d->timing = on != 0; return GNE_OK; }
 extern "C" int64_t gne_dev_launch_count(gne_dev *d) { return d->launches; }
 void gne_dev_traffic(gne_dev *d, int64_t *h2d, int64_t *d2h) { *h2d = d->h2dBytes; *d2h = d->d2hBytes; }
 
@@ -618,18 +622,39 @@ static bool replay_band_rule(const int64_t *pos, const double *viol, int64_t cnt
 
 static int price_lv_local(gne_dev *d)
 {
-    // fused pass over this shard: result in d->lvRes (mapped pinned), device time in d->lastMs
+    // fused pass over this shard: result in d->lvRes (mapped pinned) with sequence number d->lvSeq
     const int G = tiles_for(d);
     NbView nb = view_of(d);
-    CK(cudaEventRecord(d->ev0, d->stream));
+    if (d->timing) CK(cudaEventRecord(d->ev0, d->stream));
     if (G > 0) {
         k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv);
         ++d->launches;
     }
-    k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->nranks > 1 ? d->lvResDev : d->lvRes);
+    k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->nranks > 1 ? d->lvResDev : d->lvRes, ++d->lvSeq);
     ++d->launches;
-    CK(cudaEventRecord(d->ev1, d->stream));
+    if (d->timing) CK(cudaEventRecord(d->ev1, d->stream));
     CK(cudaGetLastError());
+    return GNE_OK;
+}
+
+// Wait for the result block of the pass just launched.  The reduction kernel publishes a sequence
+// number in mapped pinned memory after a system-scope fence, so the host polls that word (a few
+// hundred ns of latency) instead of paying a stream synchronisation; the stream is queried now and
+// then so that a faulted kernel is reported instead of spinning forever.
+static int wait_lv_result(gne_dev *d)
+{
+    const volatile unsigned long long *seq = &d->lvRes->seq;
+    unsigned long spins = 0;
+    while (*seq != d->lvSeq) {
+        if ((++spins & 0xfffff) == 0) {                  // ~ every millisecond
+            cudaError_t q = cudaStreamQuery(d->stream);
+            if (q == cudaSuccess) { if (*seq == d->lvSeq) break; gne_set_error("pricing pass finished without publishing its result"); return GNE_ERR_CUDA; }
+            if (q != cudaErrorNotReady) { gne_set_error("pricing pass failed: %s", cudaGetErrorString(q)); return GNE_ERR_CUDA; }
+        }
+    }
+    d->stageInFlight = false;
+    if (d->timing) { CK(cudaEventSynchronize(d->ev1)); CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1)); }
+    else d->lastMs = 0.f;
     return GNE_OK;
 }
 
@@ -645,8 +670,7 @@ extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t 
     CK(cudaSetDevice(d->device));
     int rc = gne_dev_flush(d); if (rc) return rc;
     rc = price_lv_local(d); if (rc) return rc;
-    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
-    CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
+    if (d->nranks == 1) { rc = wait_lv_result(d); if (rc) return rc; }
     d->lvMode = 0; d->lvList.clear(); d->lvCount = 0;
     double L = -1.0;
     int anyV = 0;
@@ -983,7 +1007,7 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
         CK(cudaEventRecord(d->ev0, d->stream));
         if (G > 0) { k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); ++d->launches; }
         CK(cudaEventRecord(d->ev1, d->stream));
-        k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->nranks > 1 ? d->lvResDev : d->lvRes);
+        k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->nranks > 1 ? d->lvResDev : d->lvRes, ++d->lvSeq);
         ++d->launches;
         if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
         CK(cudaEventRecord(d->ev3, d->stream));

@@ -192,6 +192,7 @@ struct LvResult {
     int64_t count;         // candidates with |rc| >= maxViol - LV_BAND, position order
     int64_t pos[LV_LIST_CAP];
     double viol[LV_LIST_CAP];
+    unsigned long long seq;        // written last (after a system-scope fence): the host spins on it instead of a stream sync
 };
 
 // LV pass, stage 2 (one CTA of 1024 threads): global maximum over the tile maxima, then the
@@ -200,7 +201,7 @@ constexpr int FIN_THREADS = 1024;
 constexpr int FIN_QCAP = 1024;             // tiles within the band handled on the device
 
 __global__ void __launch_bounds__(FIN_THREADS)
-k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
+k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long long seq)
 {
     __shared__ double sMax[FIN_THREADS / 32];
     __shared__ int sQ[FIN_QCAP];
@@ -228,7 +229,11 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
 #pragma unroll
     for (int i = 1; i < FIN_THREADS / 32; ++i) M = fmax(M, sMax[i]);
     if (M <= 0.0) {
-        if (t == 0) { res->maxViol = -1.0; res->any = 0; res->overflow = 0; res->count = 0; }
+        if (t == 0) {
+            res->maxViol = -1.0; res->any = 0; res->overflow = 0; res->count = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+        }
         return;
     }
     const double thr = __dsub_rn(M, LV_BAND);
@@ -244,7 +249,11 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
     __syncthreads();
     const int q = sCount;
     if (q > FIN_QCAP) {
-        if (t == 0) { res->maxViol = M; res->any = 1; res->overflow = 1; res->count = 0; }
+        if (t == 0) {
+            res->maxViol = M; res->any = 1; res->overflow = 1; res->count = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+        }
         return;
     }
     if (t < q) {                                       // rank sort: tile order == position order
@@ -283,7 +292,13 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res)
             }
         }
     }
-    if (t == 0) { res->maxViol = M; res->any = 1; res->overflow = bad ? 1 : 0; res->count = total; }
+    __threadfence_system();                             // the candidate entries before the header and the sequence number
+    __syncthreads();
+    if (t == 0) {
+        res->maxViol = M; res->any = 1; res->overflow = bad ? 1 : 0; res->count = total;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -127,8 +127,11 @@ int gne_price_first(gne_dev *d, int64_t *pos);
 /* reduced cost of every position in [lo, hi) (tests, verifyOptimality)                        */
 int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc);
 
-/* device time of the last pricing call's kernels in milliseconds (CUDA events on the handle's stream) */
+/* device time of the last pricing call's kernels in milliseconds (CUDA events on the handle's stream);
+ * 0 unless timing is on (gne_dev_set_timing, or GNE_TIMING=1 in the environment at create time): the
+ * events cost ~2 us per pivot, so the solver path leaves them off by default                    */
 int gne_dev_last_kernel_ms(gne_dev *d, float *ms);
+int gne_dev_set_timing(gne_dev *d, int on);
 /* number of kernels this handle has launched since creation                                   */
 int64_t gne_dev_launch_count(gne_dev *d);
 /* replay timing helper for bench.py: runs `reps` device steps on the resident state — potential
@@ -219,6 +222,20 @@ int gne_host_replay(int n, int64_t m, const int32_t *tail, const int32_t *head, 
 int gne_merge_lv_shards(int nranks, const double *maxima, const int *any, const int64_t *counts,
                         const int64_t *listPos, const double *listViol, int64_t stride,
                         double *largestViolation, int64_t *count, int64_t *outPos, int64_t cap, int *outAny, int *needFallback);
+
+/* instance files.  Text: the reference's format (graph.cpp:358-447), read sparsely, written like
+ * Graph::exportColFile (graph.cpp:94-121).  gne_read_col: call with tail == NULL for the sizes (*n, *m,
+ * *bigM as graph.cpp:43), then with arrays of those sizes; arcs come back sorted by (tail, head), arcs
+ * with capacity <= 0 dropped (gneInit.cpp:84).  Binary: "GNESOA1" + n, m + the six columns.          */
+int gne_write_col(const char *path, int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub,
+                  const double *cost, const double *mult, const double *supply);
+int gne_read_col(const char *path, int *n, int64_t *m, int32_t *tail, int32_t *head, double *ub, double *cost,
+                 double *mult, double *supply, double *bigM);
+int gne_write_bin(const char *path, int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub,
+                  const double *cost, const double *mult, const double *supply);
+int gne_read_bin_header(const char *path, int *n, int64_t *m);
+int gne_read_bin(const char *path, int n, int64_t m, int32_t *tail, int32_t *head, double *ub, double *cost,
+                 double *mult, double *supply);
 
 /* deterministic large-instance generator (bench workloads C2-C5):
  * ring i->i+1 plus random distinct heads, arcs sorted by (tail, head).  Arrays sized m / n.   */

@@ -170,3 +170,31 @@ def test_host_replay_lossy3k(gne):
                                            inst.big_m, 1, int(z["LV_p"][0]), z["LV_e"], z["LV_l"])
     assert mm == -1
     assert obj == float(z["LV_objective"])
+
+
+def test_instance_files_round_trip(gne, tmp_path):
+    """Text format as the reference reads / writes it (graph.cpp:94-121, 358-447) and the binary SoA form."""
+    from test_oracle_pinned import load
+    z, inst = load("s_wide_s3")
+    d = dict(n=inst.n, tail=inst.tail, head=inst.head, ub=inst.ub, cost=inst.cost, mult=inst.mult, supply=inst.supply)
+    col = str(tmp_path / "i.col"); binp = str(tmp_path / "i.bin")
+    gne.write_instance(col, d)
+    gne.write_instance(binp, d, binary=True)
+    a = gne.read_instance(col); b = gne.read_instance(binp, binary=True)
+    for k in ("tail", "head", "ub", "cost", "mult", "supply"):
+        assert np.array_equal(a[k], d[k]), k
+        assert np.array_equal(b[k], d[k]), k
+    assert a["n"] == b["n"] == inst.n
+    assert a["big_m"] == inst.big_m                       # graph.cpp:43
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "gne_ref_driver")):   # the reference's own loader accepts the file
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "gne_ref_driver"), "-1", "16", "-2", "16", col],
+                           stdout=subprocess.PIPE, text=True)
+        last = [ln for ln in r.stdout.splitlines() if ln.startswith("REF pivots")][-1].split()
+        assert (int(last[2]), int(last[3])) == tuple(int(v) for v in z["QS_p"])
+    # quirks of the reference's parser: unsorted input is sorted, a later duplicate wins, capacity <= 0 drops the arc
+    q = str(tmp_path / "q.col")
+    open(q, "w").write("c x\np efpgn 3 4 0\na 2 3 0.0 5.0 1.0 1.0 0\na 1 2 0.0 5.0 2.0 0.9 0\na 1 2 0.0 7.0 3.0 0.8 0\na 3 1 0.0 0.0 9.0 1.0 0\nn 1 1\nn 2 0\nn 3 -1\n")
+    g = gne.read_instance(q)
+    assert g["tail"].tolist() == [0, 1] and g["head"].tolist() == [1, 2]
+    assert g["ub"].tolist() == [7.0, 5.0] and g["cost"].tolist() == [3.0, 1.0]
+    assert g["big_m"] == 4 * 9.0 * 7.0

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Per-window cost of the GPU-driven solve as the basis trees grow (host forest work vs pricing)."""
 import sys, os
+os.environ.setdefault("GNE_TIMING", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import genneteq_b200 as gne
