@@ -10,9 +10,9 @@ configs[2] (the one its target is quoted on): 1M nodes / 20M arcs, `lossy` gains
 contiguous position range across the N GPUs with an NCCL exchange of the per-shard record
 (fixed total work: "scaling": "strong").
 
-  value  arcs priced per second with everything resident in HBM: K device steps (potential
-         finalize + pricing pass + reduction [+ NCCL exchange]) timed with CUDA events on the
-         launching stream, max over ranks.  The pass streams 533 MB > 126 MB of L2.
+  value  arcs priced per second with everything resident in HBM: K device steps (the relabel kernel of
+         a pivot of this window, replayed + pricing pass + reduction [+ exchange]) timed with CUDA
+         events on the launching stream, max over ranks.  The pass streams 508 MB > 126 MB of L2.
   e2e    the same metric through the public C ABI (gne_solver_solve) over K real pivots after W
          warm-up pivots: host basis-forest work, the host->device copy of each step's dirty
          potentials / set updates and the device->host read of the pricing result are all inside

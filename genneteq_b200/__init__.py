@@ -314,10 +314,10 @@ class Device:
     def launch_count(self):
         return lib.gne_dev_launch_count(self.h)
 
-    def bench_price_lv(self, reps, flush_l2, with_finalize=True):
+    def bench_price_lv(self, reps, flush_l2, with_finalize=2):
         """(ms per device step, ms of the tile kernel alone), CUDA events on the handle's stream."""
         ms = np.zeros(reps, np.float32); mt = np.zeros(reps, np.float32)
-        _ck(lib.gne_bench_price_lv(self.h, reps, 1 if flush_l2 else 0, 1 if with_finalize else 0, _p(ms, _f32p),
+        _ck(lib.gne_bench_price_lv(self.h, reps, 1 if flush_l2 else 0, int(with_finalize), _p(ms, _f32p),
                                    _p(mt, _f32p)), "gne_bench_price_lv")
         return ms, mt
 

@@ -134,9 +134,10 @@ int gne_dev_last_kernel_ms(gne_dev *d, float *ms);
 int gne_dev_set_timing(gne_dev *d, int on);
 /* number of kernels this handle has launched since creation                                   */
 int64_t gne_dev_launch_count(gne_dev *d);
-/* replay timing helper for bench.py: runs `reps` device steps on the resident state — potential
- * finalize (if withFinalize), the LV pricing pass, its reduction and, when sharded, the NCCL
- * exchange — each step bracketed by CUDA events on the handle's stream (msStep) with a second
+/* replay timing helper for bench.py: runs `reps` device steps on the resident state — the relabel
+ * (withFinalize 0: none, 1: finalize of every node, 2: replay of the handle's last argument-only
+ * update, i.e. what a pivot of the current window really launches; falls back to 1), the LV pricing
+ * pass, its reduction and, when sharded, the exchange — each step bracketed by CUDA events on the handle's stream (msStep) with a second
  * event pair around the tile kernel alone (msTiles).  flushL2 != 0 writes a >L2 scratch buffer
  * between steps, outside the events.                                                          */
 int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles);
