@@ -943,7 +943,9 @@ static int launch_shard_exchange(gne_dev *d);
 static const char *g_variantNames[] = {
     "production k_price_lv_tiles", "tiles<2 chunks, minb 5>", "tiles<2,6>", "tiles<2,8>", "tiles<1,8>", "tiles<4,4>",
     "tiles<2,6,no_allocate>", "tiles<1,8,no_allocate>", "persistent<minb 6> 148x6", "persistent<8> 148x8",
-    "persistent<8,no_allocate> 148x8", "strided<4,8>", "strided<8,6>" };
+    "persistent<8,no_allocate> 148x8", "strided<4,8>", "strided<8,6>",
+    "tma<256thr,4it,3st> 148x2", "tma<512thr,4it,2st> 148x2", "tma<1024thr,2it,3st> 148x1", "tma<512thr,2it,3st> 148x2", "tma<256thr,8it,2st> 148x2",
+    "tma<512thr,2it,2st> 148x4", "tma<256thr,4it,2st> 148x4" };
 extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants)
 {
     CK(cudaSetDevice(d->device));
@@ -974,6 +976,20 @@ extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVar
               case 10: k_var_persistent<8, true><<<148 * 8, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o, G1); break;
               case 11: k_var_strided<4, 8><<<G1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
               case 12: k_var_strided<8, 6><<<G2, TILE_THREADS, 0, d->stream>>>(nb, d->pi, o); break;
+#define GNE_TMA_CASE(ID, THR, IT, ST, MINB, CTAS)                                                                      \
+              case ID: {                                                                                               \
+                  const size_t sm = 128 + (size_t) ST * 25 * THR * IT;                                                 \
+                  cudaFuncSetAttribute(k_var_tma<THR, IT, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm); \
+                  k_var_tma<THR, IT, ST, MINB><<<148 * CTAS, THR, sm, d->stream>>>(nb, d->pi, o, len / (THR * IT));     \
+              } break;
+              GNE_TMA_CASE(13, 256, 4, 3, 2, 2)
+              GNE_TMA_CASE(14, 512, 4, 2, 2, 2)
+              GNE_TMA_CASE(15, 1024, 2, 3, 1, 1)
+              GNE_TMA_CASE(16, 512, 2, 3, 2, 2)
+              GNE_TMA_CASE(17, 256, 8, 2, 2, 2)
+              GNE_TMA_CASE(18, 512, 2, 2, 4, 4)
+              GNE_TMA_CASE(19, 256, 4, 2, 4, 4)
+#undef GNE_TMA_CASE
             }
             CK(cudaEventRecord(d->ev1, d->stream));
             CK(cudaGetLastError());

@@ -121,3 +121,100 @@ k_var_strided(NbView nb, const double *__restrict__ pi, double *tileMax)
 }
 
 } // namespace gne
+
+// ------------------------------------------------------------------------------------------
+// TMA-staged persistent variant: one elected thread streams the five columns of the next tiles
+// into shared memory with cp.async.bulk (completion on an mbarrier), all threads read their
+// indices from shared memory and only the pi gathers go through the LSU / L1TEX path.
+// ------------------------------------------------------------------------------------------
+namespace gne {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int THREADS, int IT, int STAGES, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_var_tma(NbView nb, const double *__restrict__ pi, double *ctaMax, int64_t numTiles)
+{
+    constexpr int TT = THREADS * IT;                    // arcs per stage
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);                 // [STAGES]
+    unsigned char *stage0 = smem + 128;
+    constexpr int STAGE_BYTES = 25 * TT;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int s, int64_t tile) {
+        unsigned char *b = stage0 + (size_t) s * STAGE_BYTES;
+        const int64_t l0 = tile * TT;
+        mbar_expect_tx(&full[s], (uint32_t) STAGE_BYTES);
+        bulk_g2s(b, nb.tail + l0, 4 * TT, &full[s]);
+        bulk_g2s(b + 4 * TT, nb.head + l0, 4 * TT, &full[s]);
+        bulk_g2s(b + 8 * TT, nb.cost + l0, 8 * TT, &full[s]);
+        bulk_g2s(b + 16 * TT, nb.mult + l0, 8 * TT, &full[s]);
+        bulk_g2s(b + 24 * TT, nb.state + l0, TT, &full[s]);
+    };
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            const int64_t tile = blockIdx.x + (int64_t) s * gridDim.x;
+            if (tile < numTiles) issue(s, tile);
+        }
+    }
+    Best b; b.v = -1.0; b.p = 0;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const uint32_t parity = (uint32_t) ((it / STAGES) & 1);
+        mbar_wait(&full[s], parity);
+        const unsigned char *sb = stage0 + (size_t) s * STAGE_BYTES;
+        const int32_t *sTail = reinterpret_cast<const int32_t *>(sb);
+        const int32_t *sHead = reinterpret_cast<const int32_t *>(sb + 4 * TT);
+        const double *sCost = reinterpret_cast<const double *>(sb + 8 * TT);
+        const double *sMult = reinterpret_cast<const double *>(sb + 16 * TT);
+        const int8_t *sState = reinterpret_cast<const int8_t *>(sb + 24 * TT);
+        double pt[IT], ph[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k) { const int o = t + k * THREADS; pt[k] = ld_pi(pi, sTail[o]); ph[k] = ld_pi(pi, sHead[o]); }
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const int o = t + k * THREADS;
+            const int64_t g = nb.lo + tile * TT + o;
+            const double v = (g < nb.end) ? violation(red_cost(sCost[o], sMult[o], pt[k], ph[k]), (int) sState[o]) : -1.0;
+            if (v > b.v) { b.v = v; b.p = g; }
+        }
+        __syncthreads();                                // everyone is done with stage s
+        if (t == 0) {
+            const int64_t nt = tile + (int64_t) STAGES * gridDim.x;
+            if (nt < numTiles) issue(s, nt);
+        }
+    }
+    b = block_best(b);
+    if (t == 0) ctaMax[blockIdx.x] = b.v;
+}
+
+} // namespace gne
