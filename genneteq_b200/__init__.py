@@ -63,6 +63,8 @@ SIGNATURES = {
     "gne_reduced_costs": (C.c_int, [_vp, C.c_int64, C.c_int64, _f64p]),
     "gne_dev_last_kernel_ms": (C.c_int, [_vp, _f32p]),
     "gne_dev_set_timing": (C.c_int, [_vp, C.c_int]),
+    "gne_dev_set_lv_kernel": (C.c_int, [_vp, C.c_int]),
+    "gne_dev_last_lv_kernel": (C.c_int, [_vp]),
     "gne_dev_launch_count": (C.c_int64, [_vp]),
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
     "gne_bench_variants": (C.c_int, [_vp, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int)]),
@@ -305,6 +307,12 @@ class Device:
         rc = np.empty(hi - lo)
         _ck(lib.gne_reduced_costs(self.h, lo, hi, _p(rc, _f64p)), "gne_reduced_costs")
         return rc
+
+    def set_lv_kernel(self, mode):
+        _ck(lib.gne_dev_set_lv_kernel(self.h, dict(auto=0, tiles=1, stream=2)[mode]), "gne_dev_set_lv_kernel")
+
+    def last_lv_kernel(self):
+        return {1: "tiles", 2: "stream"}[lib.gne_dev_last_lv_kernel(self.h)]
 
     def last_kernel_ms(self):
         ms = C.c_float(0)

@@ -1,6 +1,7 @@
 // genneteq_b200 — layer 1 of the C ABI: device-resident state and kernel launches.
 // See include/genneteq_b200.h for the contract of every entry point.
 #include "gne_kernels.cuh"
+#include "gne_stream.cuh"
 #include "gne_variants.cuh"
 #include "gne_internal.h"
 #include "../../include/genneteq_b200.h"
@@ -133,6 +134,11 @@ struct gne_dev {
     int64_t qsWindow = 0;                          // adaptive window of the quickSelect scan
     NbWriteOps pending{};                          // queued gne_nb_write records (<= 8)
     bool stageInFlight = false;                    // the staging buffer feeds a kernel not yet synchronised
+    LvCtas lvc{};                                  // per-CTA records of the TMA-streamed LV pass
+    int streamGrid = 0;                            // 2 CTAs per SM
+    int streamOverflows = 0, streamHoldoff = 0;    // adaptive fallback to the per-tile kernel
+    bool lastWasStream = false;
+    int lvKernelMode = 0;                          // 0 auto, 1 per-tile kernel, 2 TMA-streamed kernel
     SmallUpdate lastSmall{};                       // the last argument-only update (bench replay)
     bool haveLastSmall = false;
     bool timing = false;                           // bracket pricing kernels with CUDA events (gne_dev_set_timing)
@@ -215,7 +221,7 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&d->ev0));
     CK(cudaEventCreate(&d->ev1));
-    const size_t L = (size_t) d->localCap;
+    const size_t L = (size_t) d->localCap + 4 * ST_TILE;       // padding: the streamed pass copies whole tiles
     CK(cudaMalloc(&d->tail, 4 * L)); CK(cudaMalloc(&d->head, 4 * L));
     CK(cudaMalloc(&d->cost, 8 * L)); CK(cudaMalloc(&d->mult, 8 * L)); CK(cudaMalloc(&d->state, L));
     CK(cudaMemsetAsync(d->tail, 0, 4 * L, d->stream)); CK(cudaMemsetAsync(d->head, 0, 4 * L, d->stream));
@@ -235,6 +241,14 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     d->GQ = (int) ((d->localCap + QTILE - 1) / QTILE) + 1;
     CK(cudaMalloc(&d->qs.cnt, 4 * (size_t) d->GQ)); CK(cudaMalloc(&d->qs.bestV, 8 * (size_t) d->GQ)); CK(cudaMalloc(&d->qs.bestJ, 8 * (size_t) d->GQ));
     CK(cudaMalloc(&d->firstPos, 8));
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cudaDevice);
+        d->streamGrid = sms * ST_CTAS_PER_SM;
+        CK(cudaMalloc(&d->lvc.ctaMax, 8 * (size_t) d->streamGrid)); CK(cudaMalloc(&d->lvc.ctaCnt, 4 * (size_t) d->streamGrid));
+        CK(cudaMalloc(&d->lvc.candPos, 8 * (size_t) d->streamGrid * ST_CAND)); CK(cudaMalloc(&d->lvc.candViol, 8 * (size_t) d->streamGrid * ST_CAND));
+        CK(cudaFuncSetAttribute(k_price_lv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    }
     CK(cudaHostAlloc(&d->lvRes, sizeof(LvResult), cudaHostAllocMapped));
     CK(cudaHostAlloc(&d->qsState, sizeof(QsState), cudaHostAllocMapped));
     CK(cudaHostAlloc(&d->hostScalar, 64, cudaHostAllocMapped));
@@ -256,7 +270,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
-                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->stageDev, d->outPos, d->outViol,
+                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.ctaMax, d->lvc.ctaCnt, d->lvc.candPos, d->lvc.candViol, d->stageDev, d->outPos, d->outViol,
                     d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev };
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes, d->blobHost };
@@ -279,6 +293,8 @@ extern "C" int gne_dev_sync(gne_dev *d)
 
 extern "C" int gne_dev_last_kernel_ms(gne_dev *d, float *ms) { *ms = d->lastMs; return GNE_OK; }
 extern "C" int gne_dev_set_timing(gne_dev *d, int on) { d->timing = on != 0; return GNE_OK; }
+extern "C" int gne_dev_set_lv_kernel(gne_dev *d, int mode) { if (mode < 0 || mode > 2) return GNE_ERR_ARG; d->lvKernelMode = mode; return GNE_OK; }
+extern "C" int gne_dev_last_lv_kernel(gne_dev *d) { return d->lastWasStream ? 2 : 1; }
 extern "C" int64_t gne_dev_launch_count(gne_dev *d) { return d->launches; }
 void gne_dev_traffic(gne_dev *d, int64_t *h2d, int64_t *d2h) { *h2d = d->h2dBytes; *d2h = d->d2hBytes; }
 
@@ -623,20 +639,46 @@ static bool replay_band_rule(const int64_t *pos, const double *viol, int64_t cnt
     return true;
 }
 
+// Large shards go through the TMA-streamed persistent kernel, small ones (or a handle whose streamed
+// lists keep overflowing) through the one-CTA-per-tile kernel.
+static bool use_stream_kernel(const gne_dev *d)
+{
+    const int64_t len = std::min(d->N, d->hi) - d->lo;
+    if (d->lvKernelMode == 1 || len <= 0) return false;
+    if (d->lvKernelMode == 2) return true;
+    return d->streamHoldoff == 0 && len >= (int64_t) 4 * d->streamGrid * ST_TILE;
+}
+
+static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEvent_t evB)
+{
+    const int G = tiles_for(d);
+    NbView nb = view_of(d);
+    if (evA) CK(cudaEventRecord(evA, d->stream));
+    d->lastWasStream = use_stream_kernel(d);
+    if (d->lastWasStream) {
+        const int64_t numTiles = (nb.end - nb.lo + ST_TILE - 1) / ST_TILE;
+        k_price_lv_stream<<<d->streamGrid, ST_THREADS, ST_SMEM, d->stream>>>(nb, d->pi, d->lvc, numTiles);
+        ++d->launches;
+        if (evB) CK(cudaEventRecord(evB, d->stream));
+        k_price_lv_finish_stream<<<1, 1024, 0, d->stream>>>(d->lvc, d->streamGrid, target, ++d->lvSeq);
+        ++d->launches;
+    } else {
+        if (G > 0) { k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); ++d->launches; }
+        if (evB) CK(cudaEventRecord(evB, d->stream));
+        k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, target, ++d->lvSeq);
+        ++d->launches;
+        if (d->streamHoldoff > 0) --d->streamHoldoff;
+    }
+    CK(cudaGetLastError());
+    return GNE_OK;
+}
+
 static int price_lv_local(gne_dev *d)
 {
     // fused pass over this shard: result in d->lvRes (mapped pinned) with sequence number d->lvSeq
-    const int G = tiles_for(d);
-    NbView nb = view_of(d);
-    if (d->timing) CK(cudaEventRecord(d->ev0, d->stream));
-    if (G > 0) {
-        k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv);
-        ++d->launches;
-    }
-    k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->nranks > 1 ? d->lvResDev : d->lvRes, ++d->lvSeq);
-    ++d->launches;
+    int rc = launch_lv_pass(d, d->nranks > 1 ? d->lvResDev : d->lvRes, d->timing ? d->ev0 : nullptr, nullptr);
+    if (rc) return rc;
     if (d->timing) CK(cudaEventRecord(d->ev1, d->stream));
-    CK(cudaGetLastError());
     return GNE_OK;
 }
 
@@ -684,6 +726,12 @@ extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t 
         d->d2hBytes += 24 + 16 * std::min<int64_t>(r->count, LV_LIST_CAP);
         anyV = r->any;
         bool ok = !anyV;
+        if (d->lastWasStream) {
+            // a streamed pass whose per-CTA lists overflow repeatedly (values rising along the list) is
+            // cheaper through the per-tile kernel: hold the streamed kernel off for a while
+            if (anyV && r->overflow) { if (++d->streamOverflows >= 3) { d->streamHoldoff = 256; d->streamOverflows = 0; } }
+            else d->streamOverflows = 0;
+        }
         if (anyV && !r->overflow) ok = replay_band_rule(r->pos, r->viol, r->count, r->maxViol - LV_BAND, false, d->lvList, &L);
         const double M = anyV ? r->maxViol : 0.0;
         // fallback: widen the band until the replay is provably exact
@@ -944,8 +992,9 @@ static const char *g_variantNames[] = {
     "production k_price_lv_tiles", "tiles<2 chunks, minb 5>", "tiles<2,6>", "tiles<2,8>", "tiles<1,8>", "tiles<4,4>",
     "tiles<2,6,no_allocate>", "tiles<1,8,no_allocate>", "persistent<minb 6> 148x6", "persistent<8> 148x8",
     "persistent<8,no_allocate> 148x8", "strided<4,8>", "strided<8,6>",
-    "tma<256thr,4it,3st> 148x2", "tma<512thr,4it,2st> 148x2", "tma<1024thr,2it,3st> 148x1", "tma<512thr,2it,3st> 148x2", "tma<256thr,8it,2st> 148x2",
-    "tma<512thr,2it,2st> 148x4", "tma<256thr,4it,2st> 148x4" };
+    "tma<256thr,4it,3st> 148x2", "tma<256thr,4it,4st> 148x2", "tma<256thr,2it,6st> 148x2", "tma<256thr,2it,4st> 148x4", "tma<256thr,2it,3st> 148x5",
+    "tma<512thr,2it,4st> 148x2", "tma<128thr,4it,4st> 148x4", "tma<256thr,1it,8st> 148x4", "tma<512thr,2it,3st> 148x2", "tma<256thr,2it,8st> 148x2",
+    "tma<256thr,4it,3st> 148x1" };
 extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants)
 {
     CK(cudaSetDevice(d->device));
@@ -983,12 +1032,16 @@ extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVar
                   k_var_tma<THR, IT, ST, MINB><<<148 * CTAS, THR, sm, d->stream>>>(nb, d->pi, o, len / (THR * IT));     \
               } break;
               GNE_TMA_CASE(13, 256, 4, 3, 2, 2)
-              GNE_TMA_CASE(14, 512, 4, 2, 2, 2)
-              GNE_TMA_CASE(15, 1024, 2, 3, 1, 1)
-              GNE_TMA_CASE(16, 512, 2, 3, 2, 2)
-              GNE_TMA_CASE(17, 256, 8, 2, 2, 2)
-              GNE_TMA_CASE(18, 512, 2, 2, 4, 4)
-              GNE_TMA_CASE(19, 256, 4, 2, 4, 4)
+              GNE_TMA_CASE(14, 256, 4, 4, 2, 2)
+              GNE_TMA_CASE(15, 256, 2, 6, 2, 2)
+              GNE_TMA_CASE(16, 256, 2, 4, 4, 4)
+              GNE_TMA_CASE(17, 256, 2, 3, 5, 5)
+              GNE_TMA_CASE(18, 512, 2, 4, 2, 2)
+              GNE_TMA_CASE(19, 128, 4, 4, 4, 4)
+              GNE_TMA_CASE(20, 256, 1, 8, 4, 4)
+              GNE_TMA_CASE(21, 512, 2, 3, 2, 2)
+              GNE_TMA_CASE(22, 256, 2, 8, 2, 2)
+              GNE_TMA_CASE(23, 256, 4, 3, 1, 1)
 #undef GNE_TMA_CASE
             }
             CK(cudaEventRecord(d->ev1, d->stream));
@@ -1017,8 +1070,6 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
         CK(cudaMalloc(&d->flushBuf, 8 * (size_t) d->flushLen));
     }
     if (!d->ev2) { CK(cudaEventCreate(&d->ev2)); CK(cudaEventCreate(&d->ev3)); }
-    const int G = tiles_for(d);
-    NbView nb = view_of(d);
     for (int i = 0; i < reps; ++i) {
         if (flushL2) { k_flush_l2<<<148 * 8, 256, 0, d->stream>>>(d->flushBuf, d->flushLen); ++d->launches; }
         CK(cudaEventRecord(d->ev2, d->stream));
@@ -1028,11 +1079,7 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
             k_update_small<<<1, 256, 0, d->stream>>>(mm, d->lastSmall, d->a0, d->a1, d->slot, d->theta, d->pi);
             ++d->launches;
         } else if (withFinalize) { k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi); ++d->launches; }
-        CK(cudaEventRecord(d->ev0, d->stream));
-        if (G > 0) { k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); ++d->launches; }
-        CK(cudaEventRecord(d->ev1, d->stream));
-        k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, d->nranks > 1 ? d->lvResDev : d->lvRes, ++d->lvSeq);
-        ++d->launches;
+        rc = launch_lv_pass(d, d->nranks > 1 ? d->lvResDev : d->lvRes, d->ev0, d->ev1); if (rc) return rc;
         if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
         CK(cudaEventRecord(d->ev3, d->stream));
         CK(cudaGetLastError());

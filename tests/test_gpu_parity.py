@@ -75,13 +75,17 @@ SIZES = [(50, 1), (50, 7), (300, 2047), (300, 2048), (300, 2049), (1000, 10000),
 
 @pytest.mark.parametrize("n,N", SIZES)
 @pytest.mark.parametrize("mode", ["cont", "ties", "near"])
-def test_price_lv_matches_sequential_rule(gne, n, N, mode):
+@pytest.mark.parametrize("kernel", ["tiles", "stream"])
+def test_price_lv_matches_sequential_rule(gne, n, N, mode, kernel):
+    """Both LV kernels (one CTA per tile; TMA-streamed persistent) at every size, incl. ragged tails."""
     rng = np.random.default_rng(n * 7 + N)
     tail, head, cost, mult, state, pi = random_soa(rng, n, N, mode)
     d = gne.Device(n, N + 16)
+    d.set_lv_kernel(kernel)
     d.nb_reset(tail, head, cost, mult, state)
     d.pot_set_all(pi)
     L, lst, anyv = d.price_lv()
+    assert d.last_lv_kernel() == kernel
     oL, olst, oany = oracle_lv(tail, head, cost, mult, state, pi)
     assert anyv == oany
     assert L == oL
@@ -96,6 +100,30 @@ def test_price_lv_matches_sequential_rule(gne, n, N, mode):
     orc = np.zeros(N)
     oracle_lib().orc_reduced_costs(C.c_long(N), ip(tail), ip(head), dp(cost), dp(mult), dp(pi), dp(orc))
     assert np.array_equal(rc, orc)
+    d.close()
+
+
+def test_price_lv_streamed_kernel_is_the_default_for_large_lists_and_survives_rising_values(gne):
+    """>= ~1.2M arcs: automatic choice = TMA-streamed kernel.  Values rising along the list overflow its per-CTA
+    candidate lists; the result must still be exact (fallback) and the handle then holds the kernel off."""
+    rng = np.random.default_rng(77)
+    n, N = 30000, 1_600_000
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N, "cont")
+    d = gne.Device(n, N + 16)
+    d.nb_reset(tail, head, cost, mult, state)
+    d.pot_set_all(pi)
+    L, lst, anyv = d.price_lv()
+    assert d.last_lv_kernel() == "stream"
+    oL, olst, oany = oracle_lv(tail, head, cost, mult, state, pi)
+    assert (L, anyv) == (oL, oany) and np.array_equal(lst, olst)
+    # rc = cost at zero potentials; every arc at upper bound violates with |rc| rising with the position
+    cost2 = 1.0 + np.arange(N) * 1e-3
+    d.nb_reset(tail, head, cost2, mult, np.full(N, 2, np.int8))
+    d.pot_set_all(np.zeros(n))
+    for _ in range(5):
+        L, lst, anyv = d.price_lv()
+        assert L == cost2[-1] and lst.tolist() == [N - 1] and anyv
+    assert d.last_lv_kernel() == "tiles"                 # held off after repeated overflows
     d.close()
 
 
