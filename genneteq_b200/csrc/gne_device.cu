@@ -247,6 +247,7 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
         d->streamGrid = sms * ST_CTAS_PER_SM;
         CK(cudaMalloc(&d->lvc.ctaMax, 8 * (size_t) d->streamGrid)); CK(cudaMalloc(&d->lvc.ctaCnt, 4 * (size_t) d->streamGrid));
         CK(cudaMalloc(&d->lvc.candPos, 8 * (size_t) d->streamGrid * ST_CAND)); CK(cudaMalloc(&d->lvc.candViol, 8 * (size_t) d->streamGrid * ST_CAND));
+        CK(cudaMalloc(&d->lvc.candSecond, 8 * (size_t) d->streamGrid * ST_CAND));
         CK(cudaFuncSetAttribute(k_price_lv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
     }
     CK(cudaHostAlloc(&d->lvRes, sizeof(LvResult), cudaHostAllocMapped));
@@ -270,7 +271,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
-                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.ctaMax, d->lvc.ctaCnt, d->lvc.candPos, d->lvc.candViol, d->stageDev, d->outPos, d->outViol,
+                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.ctaMax, d->lvc.ctaCnt, d->lvc.candPos, d->lvc.candViol, d->lvc.candSecond, d->stageDev, d->outPos, d->outViol,
                     d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev };
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes, d->blobHost };
@@ -994,7 +995,7 @@ static const char *g_variantNames[] = {
     "persistent<8,no_allocate> 148x8", "strided<4,8>", "strided<8,6>",
     "tma<256thr,4it,3st> 148x2", "tma<256thr,4it,4st> 148x2", "tma<256thr,2it,6st> 148x2", "tma<256thr,2it,4st> 148x4", "tma<256thr,2it,3st> 148x5",
     "tma<512thr,2it,4st> 148x2", "tma<128thr,4it,4st> 148x4", "tma<256thr,1it,8st> 148x4", "tma<512thr,2it,3st> 148x2", "tma<256thr,2it,8st> 148x2",
-    "tma<256thr,4it,3st> 148x1" };
+    "tma<256thr,4it,3st> 148x1", "production k_price_lv_stream" };
 extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants)
 {
     CK(cudaSetDevice(d->device));
@@ -1043,6 +1044,7 @@ extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVar
               GNE_TMA_CASE(22, 256, 2, 8, 2, 2)
               GNE_TMA_CASE(23, 256, 4, 3, 1, 1)
 #undef GNE_TMA_CASE
+              case 24: k_price_lv_stream<<<d->streamGrid, ST_THREADS, ST_SMEM, d->stream>>>(nb, d->pi, d->lvc, (len + ST_TILE - 1) / ST_TILE); break;
             }
             CK(cudaEventRecord(d->ev1, d->stream));
             CK(cudaGetLastError());

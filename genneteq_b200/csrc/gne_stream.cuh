@@ -57,24 +57,26 @@ struct LvCtas {
     double *ctaMax;        // [G]  -1 when the CTA saw no violator
     int32_t *ctaCnt;       // [G]  candidates recorded (may exceed ST_CAND: overflow)
     int64_t *candPos;      // [G * ST_CAND] global positions, unordered
-    double *candViol;      // [G * ST_CAND]
+    double *candViol;      // [G * ST_CAND] the thread's largest violation
+    double *candSecond;    // [G * ST_CAND] the same thread's second largest (in band => the thread may hide more)
 };
 
+// Per tile the critical path is: wait for the stage, read the indices from shared memory, gather,
+// compare - nothing else.  Each thread keeps its largest violation (first position on ties) and its
+// second largest in registers; shared memory and atomics are touched once, after the last tile.
+// A thread can therefore contribute one candidate; if its second value is also within the band of
+// the global maximum the pass reports overflow (it may hide a third) and the caller falls back to
+// the ordered compaction - with ~75 k threads that happens only for long tie lists.
 __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
 k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t numTiles)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);                 // [ST_STAGES]
     unsigned char *stage0 = smem + 128;
-    __shared__ unsigned long long sMaxBits;             // running maximum (bits of a non-negative double are ordered)
-    __shared__ int sCnt;
-    __shared__ int64_t sPos[ST_CAND];
-    __shared__ double sViol[ST_CAND];
     const int t = threadIdx.x;
     if (t == 0) {
         for (int s = 0; s < ST_STAGES; ++s) st_mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sMaxBits = 0ull; sCnt = 0;
     }
     __syncthreads();
     auto issue = [&](int s, int64_t tile) {
@@ -93,6 +95,8 @@ k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t 
             if (tile < numTiles) issue(s, tile);
         }
     }
+    double v1 = -1.0, v2 = -1.0;                        // largest (first position on ties) and second largest
+    int64_t p1 = 0;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
         const int s = it % ST_STAGES;
@@ -103,48 +107,45 @@ k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t 
         const double *sCost = reinterpret_cast<const double *>(sb + 8 * ST_TILE);
         const double *sMult = reinterpret_cast<const double *>(sb + 16 * ST_TILE);
         const int8_t *sState = reinterpret_cast<const int8_t *>(sb + 24 * ST_TILE);
-        double pt[ST_ITEMS], ph[ST_ITEMS], v[ST_ITEMS];
+        double pt[ST_ITEMS], ph[ST_ITEMS];
 #pragma unroll
         for (int k = 0; k < ST_ITEMS; ++k) { const int o = t + k * ST_THREADS; pt[k] = ld_pi(pi, sTail[o]); ph[k] = ld_pi(pi, sHead[o]); }
-        double vmax = -1.0;
 #pragma unroll
         for (int k = 0; k < ST_ITEMS; ++k) {
             const int o = t + k * ST_THREADS;
             const int64_t g = nb.lo + tile * ST_TILE + o;
-            v[k] = (g < nb.end && g >= nb.begin) ? violation(red_cost(sCost[o], sMult[o], pt[k], ph[k]), (int) sState[o]) : -1.0;
-            vmax = fmax(vmax, v[k]);
+            const double v = (g < nb.end && g >= nb.begin) ? violation(red_cost(sCost[o], sMult[o], pt[k], ph[k]), (int) sState[o]) : -1.0;
+            if (v > v1) { v2 = v1; v1 = v; p1 = g; }      // positions rise within a thread: the first maximum stays
+            else if (v > v2) v2 = v;
         }
-        if (it == 0) {
-            // the first tile fixes the running maximum exactly, so that the list starts short
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-            if ((t & 31) == 0 && vmax > 0.0) atomicMax(&sMaxBits, (unsigned long long) __double_as_longlong(vmax));
-            __syncthreads();
-        }
-        // candidates against the running maximum as it stands (a lower bound of the final one)
-        const double run = __longlong_as_double((long long) *reinterpret_cast<volatile unsigned long long *>(&sMaxBits));
-        const double thr = __dsub_rn(run, LV_BAND);
-#pragma unroll
-        for (int k = 0; k < ST_ITEMS; ++k) {
-            if (v[k] > 0.0 && v[k] >= thr) {
-                const int slot = atomicAdd(&sCnt, 1);
-                if (slot < ST_CAND) { sPos[slot] = nb.lo + tile * ST_TILE + t + k * ST_THREADS; sViol[slot] = v[k]; }
-                if (v[k] > run) atomicMax(&sMaxBits, (unsigned long long) __double_as_longlong(v[k]));
-            }
-        }
-        __syncthreads();                                // everyone is done with stage s (and with this tile's list updates)
+        __syncthreads();                                // everyone is done with stage s
         if (t == 0) {
             const int64_t nt = tile + (int64_t) ST_STAGES * gridDim.x;
             if (nt < numTiles) issue(s, nt);
         }
     }
+    // once per CTA: maximum, then the threads within the band of it
+    __shared__ int sCnt;
+    __shared__ int64_t sPos[ST_CAND];
+    __shared__ double sViol[ST_CAND], sSecond[ST_CAND];
+    if (t == 0) sCnt = 0;
+    Best b; b.v = v1; b.p = p1;
+    b = block_best(b);                                  // two barriers inside: sCnt = 0 is visible afterwards
+    const double M = b.v;
+    if (M > 0.0) {
+        const double thr = __dsub_rn(M, LV_BAND);
+        if (v1 >= thr) {
+            const int slot = atomicAdd(&sCnt, 1);
+            if (slot < ST_CAND) { sPos[slot] = p1; sViol[slot] = v1; sSecond[slot] = v2; }
+        }
+    }
     __syncthreads();
-    const double M = (sMaxBits == 0ull) ? -1.0 : __longlong_as_double((long long) sMaxBits);
     const int cnt = sCnt;
-    if (t == 0) { out.ctaMax[blockIdx.x] = M; out.ctaCnt[blockIdx.x] = cnt; }
+    if (t == 0) { out.ctaMax[blockIdx.x] = M > 0.0 ? M : -1.0; out.ctaCnt[blockIdx.x] = cnt; }
     for (int i = t; i < min(cnt, ST_CAND); i += ST_THREADS) {
         out.candPos[(int64_t) blockIdx.x * ST_CAND + i] = sPos[i];
         out.candViol[(int64_t) blockIdx.x * ST_CAND + i] = sViol[i];
+        out.candSecond[(int64_t) blockIdx.x * ST_CAND + i] = sSecond[i];
     }
 }
 
@@ -185,6 +186,7 @@ k_price_lv_finish_stream(LvCtas in, int G, LvResult *res, unsigned long long seq
         for (int i = lane; i < c; i += 32) {
             const double vv = in.candViol[(int64_t) g * ST_CAND + i];
             if (vv >= thr) {
+                if (in.candSecond[(int64_t) g * ST_CAND + i] >= thr) sOvf = 1;      // that thread may hide further members
                 const int slot = atomicAdd(&sCount, 1);
                 if (slot < LV_LIST_CAP) { sPos[slot] = in.candPos[(int64_t) g * ST_CAND + i]; sViol[slot] = vv; }
             }

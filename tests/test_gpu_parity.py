@@ -103,9 +103,10 @@ def test_price_lv_matches_sequential_rule(gne, n, N, mode, kernel):
     d.close()
 
 
-def test_price_lv_streamed_kernel_is_the_default_for_large_lists_and_survives_rising_values(gne):
-    """>= ~1.2M arcs: automatic choice = TMA-streamed kernel.  Values rising along the list overflow its per-CTA
-    candidate lists; the result must still be exact (fallback) and the handle then holds the kernel off."""
+def test_price_lv_streamed_kernel_is_the_default_for_large_lists_and_falls_back(gne):
+    """>= ~1.2M arcs: automatic choice = TMA-streamed kernel.  Each of its threads can contribute one tie-list
+    member; longer lists are reported as overflow, the result must still be exact (ordered-compaction fallback) and
+    after repeated overflows the handle holds the streamed kernel off."""
     rng = np.random.default_rng(77)
     n, N = 30000, 1_600_000
     tail, head, cost, mult, state, pi = random_soa(rng, n, N, "cont")
@@ -116,13 +117,18 @@ def test_price_lv_streamed_kernel_is_the_default_for_large_lists_and_survives_ri
     assert d.last_lv_kernel() == "stream"
     oL, olst, oany = oracle_lv(tail, head, cost, mult, state, pi)
     assert (L, anyv) == (oL, oany) and np.array_equal(lst, olst)
-    # rc = cost at zero potentials; every arc at upper bound violates with |rc| rising with the position
+    # rising values: every thread keeps raising its maximum, still one member per thread at most
     cost2 = 1.0 + np.arange(N) * 1e-3
     d.nb_reset(tail, head, cost2, mult, np.full(N, 2, np.int8))
     d.pot_set_all(np.zeros(n))
-    for _ in range(5):
-        L, lst, anyv = d.price_lv()
-        assert L == cost2[-1] and lst.tolist() == [N - 1] and anyv
+    L, lst, anyv = d.price_lv()
+    assert L == cost2[-1] and lst.tolist() == [N - 1] and anyv and d.last_lv_kernel() == "stream"
+    # one exact tie over the whole list: rc = cost at zero potentials, every arc at its upper bound
+    d.nb_reset(tail, head, np.full(N, 5.0), mult, np.full(N, 2, np.int8))
+    for _ in range(4):
+        L, count, anyv = d.price_lv_begin()
+        assert (L, count, anyv) == (5.0, N, True)
+        assert d.price_lv_at(N // 3) == N // 3
     assert d.last_lv_kernel() == "tiles"                 # held off after repeated overflows
     d.close()
 
