@@ -17,7 +17,8 @@ contiguous position range across the N GPUs with an NCCL exchange of the per-sha
          warm-up pivots: host basis-forest work, the host->device copy of each step's dirty
          potentials / set updates and the device->host read of the pricing result are all inside
          the timed region.
-  roofline  the tile kernel k_price_lv_tiles alone: (25 B x arcs + 8 B x nodes) / its CUDA-event time
+  roofline  the pricing kernel alone (k_price_lv_stream, the TMA-streamed persistent kernel, for shards of
+         >= ~1.2M arcs; k_price_lv_tiles below that): (25 B x arcs + 8 B x nodes) / its CUDA-event time
          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the unmodified reference (oracle/_ref, built from /root/reference by oracle/Makefile)
          timed on this box's host cores on a bounded number of pivots of the same workload.
@@ -52,7 +53,7 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of k_price_lv_tiles per launch, from the committed
 # `ncu --set full` capture (profiles/r1_price_lv_tiles_ncu_summary.txt): 509.1 MB + 4.9 MB on c3-lv, N = 1
-NCU_TRAFFIC_BYTES = {("c3-lv", 1): 514.0e6}
+NCU_TRAFFIC_BYTES = {("c3-lv", 1, "k_price_lv_tiles"): 514.0e6}
 METRIC = "arcs priced/sec"
 UNIT = "arcs/s"
 
@@ -289,6 +290,7 @@ def b200_arm(args):
     dbg("device steps done")
     clocks = sampler.stop()
     launches = int(s.counters()["launches"] - c0["launches"])     # e2e window + device steps (warm-up excluded from neither)
+    lv_kernel = {"stream": "k_price_lv_stream", "tiles": "k_price_lv_tiles"}[dev.last_lv_kernel()]
     dev.close()
     if dist is not None:
         t = torch.tensor([e2e_s, float(ms_step.sum()), float(ms_tiles.mean())], dtype=torch.float64, device="cuda")
@@ -325,7 +327,7 @@ def b200_arm(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world)), "kernel": "k_price_lv_tiles", "kernel_ms": tiles_ms,
+                     "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world, lv_kernel)), "kernel": lv_kernel, "kernel_ms": tiles_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
     }
     if world == 1 and not args.no_cpu_baseline:

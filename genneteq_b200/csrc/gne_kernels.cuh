@@ -291,8 +291,8 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long
                 ++off;
             }
         }
+        __threadfence_system();                         // only the threads that wrote entries pay the PCIe round trip
     }
-    __threadfence_system();                             // the candidate entries before the header and the sequence number
     __syncthreads();
     if (t == 0) {
         res->maxViol = M; res->any = 1; res->overflow = bad ? 1 : 0; res->count = total;

@@ -195,21 +195,27 @@ k_price_lv_finish_stream(LvCtas in, int G, LvResult *res, unsigned long long seq
     __syncthreads();
     const int total = sCount;
     const bool bad = sOvf || total > 1024;              // longer lists go through the ordered compaction
+    __shared__ int sRank[1024];
     if (!bad) {
         for (int i = t; i < total; i += 1024) {         // rank sort by position (positions are distinct)
             const int64_t mine = sPos[i];
             int rank = 0;
             for (int j = 0; j < total; ++j) rank += (sPos[j] < mine);
-            res->pos[rank] = mine;
-            res->viol[rank] = sViol[i];
+            sRank[rank] = i;
         }
     }
-    __threadfence_system();
     __syncthreads();
-    if (t == 0) {
-        res->maxViol = M; res->any = 1; res->overflow = bad ? 1 : 0; res->count = total;
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+    // one warp publishes: entries, system-scope fence, header, fence, sequence number (the fences are PCIe
+    // round trips, so as few threads as possible execute them)
+    if (w == 0) {
+        if (!bad) for (int r = lane; r < total; r += 32) { res->pos[r] = sPos[sRank[r]]; res->viol[r] = sViol[sRank[r]]; }
+        if (!bad && total > 0) __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            res->maxViol = M; res->any = 1; res->overflow = bad ? 1 : 0; res->count = total;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+        }
     }
 }
 
