@@ -18,7 +18,7 @@ contiguous position range across the N GPUs with an NCCL exchange of the per-sha
          potentials / set updates and the device->host read of the pricing result are all inside
          the timed region.
   roofline  the pricing kernel alone (k_price_lv_stream, the TMA-streamed persistent kernel, for shards of
-         >= ~1.2M arcs; k_price_lv_tiles below that): (25 B x arcs + 8 B x nodes) / its CUDA-event time
+         >= ~2.4M arcs; k_price_lv_tiles below that): (25 B x arcs + 8 B x nodes) / its CUDA-event time
          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the unmodified reference (oracle/_ref, built from /root/reference by oracle/Makefile)
          timed on this box's host cores on a bounded number of pivots of the same workload.
@@ -52,8 +52,8 @@ WORKLOADS = {
     "c4-batch": (50_000, 1_000_000, 1000, "lossy", "LV", "configs[3]: independent 50k-node / 1M-arc lossy instances (seeds 1000+), one stream per instance, Dantzig rule (LV)"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of k_price_lv_tiles per launch, from the committed
-# `ncu --set full` capture (profiles/r1_price_lv_tiles_ncu_summary.txt): 509.1 MB + 4.9 MB on c3-lv, N = 1
-NCU_TRAFFIC_BYTES = {("c3-lv", 1, "k_price_lv_tiles"): 514.0e6}
+# `ncu --set full` captures under profiles/ (c3-lv, N = 1): stream kernel 508.04 MB + 4.0 MB, per-tile kernel 509.1 MB + 4.9 MB
+NCU_TRAFFIC_BYTES = {("c3-lv", 1, "k_price_lv_tiles"): 514.0e6, ("c3-lv", 1, "k_price_lv_stream"): 512.1e6}
 METRIC = "arcs priced/sec"
 UNIT = "arcs/s"
 

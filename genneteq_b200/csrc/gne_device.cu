@@ -647,7 +647,7 @@ static bool use_stream_kernel(const gne_dev *d)
     const int64_t len = std::min(d->N, d->hi) - d->lo;
     if (d->lvKernelMode == 1 || len <= 0) return false;
     if (d->lvKernelMode == 2) return true;
-    return d->streamHoldoff == 0 && len >= (int64_t) 4 * d->streamGrid * ST_TILE;
+    return d->streamHoldoff == 0 && len >= (int64_t) 8 * d->streamGrid * ST_TILE;
 }
 
 static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEvent_t evB)
@@ -995,7 +995,8 @@ static const char *g_variantNames[] = {
     "persistent<8,no_allocate> 148x8", "strided<4,8>", "strided<8,6>",
     "tma<256thr,4it,3st> 148x2", "tma<256thr,4it,4st> 148x2", "tma<256thr,2it,6st> 148x2", "tma<256thr,2it,4st> 148x4", "tma<256thr,2it,3st> 148x5",
     "tma<512thr,2it,4st> 148x2", "tma<128thr,4it,4st> 148x4", "tma<256thr,1it,8st> 148x4", "tma<512thr,2it,3st> 148x2", "tma<256thr,2it,8st> 148x2",
-    "tma<256thr,4it,3st> 148x1", "production k_price_lv_stream" };
+    "tma<256thr,4it,3st> 148x1", "production k_price_lv_stream", "k_price_lv_finish (per-tile records, mapped host result)",
+    "k_price_lv_finish_stream (per-CTA records, mapped host result)", "k_price_lv_finish_stream (device result)", "k_update_small replay" };
 extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants)
 {
     CK(cudaSetDevice(d->device));
@@ -1045,6 +1046,12 @@ extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVar
               GNE_TMA_CASE(23, 256, 4, 3, 1, 1)
 #undef GNE_TMA_CASE
               case 24: k_price_lv_stream<<<d->streamGrid, ST_THREADS, ST_SMEM, d->stream>>>(nb, d->pi, d->lvc, (len + ST_TILE - 1) / ST_TILE); break;
+              case 25: k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, (int) ((len + TILE - 1) / TILE), d->lo, d->lvRes, ++d->lvSeq); break;
+              case 26: k_price_lv_finish_stream<<<1, 1024, 0, d->stream>>>(d->lvc, d->streamGrid, d->lvRes, ++d->lvSeq); break;
+              case 27: { if (!d->lvResDev) cudaMalloc(&d->lvResDev, sizeof(LvResult));
+                         k_price_lv_finish_stream<<<1, 1024, 0, d->stream>>>(d->lvc, d->streamGrid, d->lvResDev, ++d->lvSeq); } break;
+              case 28: { NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
+                         k_update_small<<<1, 256, 0, d->stream>>>(mm, d->lastSmall, d->a0, d->a1, d->slot, d->theta, d->pi); } break;
             }
             CK(cudaEventRecord(d->ev1, d->stream));
             CK(cudaGetLastError());

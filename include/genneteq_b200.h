@@ -133,7 +133,7 @@ int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc);
 int gne_dev_last_kernel_ms(gne_dev *d, float *ms);
 int gne_dev_set_timing(gne_dev *d, int on);
 /* which kernel prices the LV pass: 0 = automatic (the TMA-streamed persistent kernel for shards of at
- * least ~1.2M arcs, the one-CTA-per-tile kernel below that or while streamed lists keep overflowing),
+ * least ~2.4M arcs, the one-CTA-per-tile kernel below that or while streamed lists keep overflowing),
  * 1 = per-tile kernel, 2 = TMA-streamed kernel.  gne_dev_last_lv_kernel: 1 or 2, the one last used.  */
 int gne_dev_set_lv_kernel(gne_dev *d, int mode);
 int gne_dev_last_lv_kernel(gne_dev *d);

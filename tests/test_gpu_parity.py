@@ -104,11 +104,11 @@ def test_price_lv_matches_sequential_rule(gne, n, N, mode, kernel):
 
 
 def test_price_lv_streamed_kernel_is_the_default_for_large_lists_and_falls_back(gne):
-    """>= ~1.2M arcs: automatic choice = TMA-streamed kernel.  Each of its threads can contribute one tie-list
+    """>= ~2.4M arcs: automatic choice = TMA-streamed kernel.  Each of its threads can contribute one tie-list
     member; longer lists are reported as overflow, the result must still be exact (ordered-compaction fallback) and
     after repeated overflows the handle holds the streamed kernel off."""
     rng = np.random.default_rng(77)
-    n, N = 30000, 1_600_000
+    n, N = 30000, 2_600_000
     tail, head, cost, mult, state, pi = random_soa(rng, n, N, "cont")
     d = gne.Device(n, N + 16)
     d.nb_reset(tail, head, cost, mult, state)
