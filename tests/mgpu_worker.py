@@ -30,6 +30,40 @@ def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", "0"))
     gold = np.load(os.path.join(HERE, "golden", "c1_wide_s7.npz"))
     inst = Instance.load(os.path.join(HERE, "golden", "c1_wide_s7_instance.npz"))
+    if mode == "nccl-c2":
+        # configs[1] size, sharded: first 300 Dantzig pivots on every rank vs the oracle (rank 0 runs it)
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = np.zeros(128, np.uint8)
+            gne._ck(gne.lib.gne_comm_unique_id(buf.ctypes.data_as(gne._u8p)), "gne_comm_unique_id")
+            uid = torch.from_numpy(buf)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        g = gne.generate_instance(100_000, 2_000_000, 21, "lossy")
+        big = Instance(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"])
+        s = gne.Solver(big.n, big.tail, big.head, big.ub, big.cost, big.mult, big.supply, device=local, rule1=rule)
+        s.set_comm(uid.cpu().numpy(), rank, world)
+        s.solve(True, 300)
+        e, l = s.trace
+        tr = torch.from_numpy(np.concatenate([e, l]).astype(np.int64)).cuda()
+        ref = tr.clone()
+        dist.broadcast(ref, 0)
+        ok = bool(torch.equal(tr, ref))                  # every rank produced rank 0's trace
+        if rank == 0:
+            o = Oracle(big, RULES[rule])
+            o.solve(True, 300)
+            ok = ok and np.array_equal(e, o.trace[0]) and np.array_equal(l, o.trace[1]) and np.array_equal(s.flows(), o.flows())
+            ok = ok and np.array_equal(s.potentials(), o.potentials())
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            open(out, "w").write("OK" if int(flag.item()) == 1 else "MISMATCH")
+        s.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if mode == "nccl":
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

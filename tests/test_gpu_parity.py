@@ -407,3 +407,28 @@ def test_c3_full_size_pricing_pass_equals_oracle(gne):
         assert np.array_equal(rt, nb["tail"]) and np.array_equal(rh, nb["head"]) and np.array_equal(rs, nb["state"])
         assert np.array_equal(rcst, nb["cost"]) and np.array_equal(rm, nb["mult"])
     s.close(); o.close()
+
+
+def test_c5_full_size_kernels_equal_oracle(gne):
+    """configs[4] size: 200k nodes / 100M arcs (2.5 GB of arc columns).  Initial Phase-I state (cost 0 on real arcs,
+    pi = 1/(1-mu) of each node's artificial self-loop): both LV kernels, quickSelect from three cursors and the
+    first-violator pass against the oracle's scalar passes over the same structure-of-arrays."""
+    g = gne.generate_instance(200_000, 100_000_000, 51, "lossy")
+    n, N = g["n"], len(g["tail"])
+    pi = np.where(g["supply"] >= 0, 1.0 / (1.0 - 0.5), 1.0 / (1.0 - 2.0))
+    cost = np.zeros(N)
+    state = np.ones(N, np.int8)
+    d = gne.Device(n, N + 16)
+    d.nb_reset(g["tail"], g["head"], cost, g["mult"], state)
+    d.pot_set_all(pi)
+    oL, olst, oany = oracle_lv(g["tail"], g["head"], cost, g["mult"], state, pi)
+    for kernel in ("stream", "tiles"):
+        d.set_lv_kernel(kernel)
+        L, lst, anyv = d.price_lv()
+        assert (L, anyv) == (oL, oany) and np.array_equal(lst, olst), kernel
+    for cur in (0, 41_234_567, N - 3):
+        assert d.price_qs(cur, n) == oracle_qs(g["tail"], g["head"], cost, g["mult"], state, pi, cur, n)
+    opos, _ = oracle_violators(g["tail"], g["head"], cost, g["mult"], state, pi, 2.9)
+    pos, _ = d.price_violators(2.9, cap=len(opos) + 16)
+    assert np.array_equal(pos, opos)
+    d.close()

@@ -47,3 +47,16 @@ def test_sharded_solve_two_gpus(tmp_path, exchange):
     env = {"GNE_EXCHANGE": "nccl"} if exchange == "nccl" else {}
     port = 29612 if exchange == "p2p" else 29613
     assert launch("nccl", 2, str(tmp_path / (exchange + ".txt")), port, env) == "OK"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rule", ["LV", "QS"])
+def test_sharded_c2_prefix_window_all_gpus(tmp_path, rule):
+    """configs[1] size (100k nodes / 2M arcs) sharded over every GPU of the box (2, 4 or 8): the first 300 pivots,
+    flows and potentials equal the oracle's, and every rank holds the same trace."""
+    import genneteq_b200 as gne
+    ngpu = gne.cuda_device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nproc = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
+    assert launch("nccl-c2", nproc, str(tmp_path / ("c2" + rule + ".txt")), 29640 + (1 if rule == "QS" else 0), None, rule) == "OK"
