@@ -143,6 +143,8 @@ struct gne_dev {
     bool haveLastSmall = false;
     bool timing = false;                           // bracket pricing kernels with CUDA events (gne_dev_set_timing)
     unsigned long long lvSeq = 0;                  // sequence number of the last LV pass launched
+    unsigned long long qsSeq = 0;
+    QsState *qsDev = nullptr;                      // device-resident carry of the quickSelect scan
     // multi-GPU
     void *comm = nullptr;
     int rank = 0, nranks = 1;
@@ -271,7 +273,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
-                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.ctaMax, d->lvc.ctaCnt, d->lvc.candPos, d->lvc.candViol, d->lvc.candSecond, d->stageDev, d->outPos, d->outViol,
+                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.ctaMax, d->lvc.ctaCnt, d->lvc.candPos, d->lvc.candViol, d->lvc.candSecond, d->qsDev, d->stageDev, d->outPos, d->outViol,
                     d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev };
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes, d->blobHost };
@@ -882,24 +884,36 @@ extern "C" int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc)
 static int qs_scan(gne_dev *d, int64_t cursor, int64_t N, int64_t jTotal, int64_t want, float *msOut)
 {
     NbView nb = view_of(d);
-    QsState *st = d->qsState;
+    QsState *st = d->qsState;                           // host copy of the result (mapped pinned)
     st->violations = 0; st->bestV = 0.0; st->bestJ = -1; st->stopJ = -1; st->done = 0;
     if (msOut) *msOut = 0.f;
     if (jTotal <= 0 || want <= 0) { st->done = 1; return GNE_OK; }
+    if (!d->qsDev) CK(cudaMalloc(&d->qsDev, sizeof(QsState)));
     if (d->qsWindow <= 0) d->qsWindow = std::max<int64_t>(4 * std::min<int64_t>(want, jTotal), 64 * QTILE);
     int64_t jLo = 0;
+    int first = 1;
     while (true) {
         const int64_t jHi = std::min(jTotal, jLo + d->qsWindow);
         const int G = (int) ((jHi - jLo + QTILE - 1) / QTILE);
-        CK(cudaEventRecord(d->ev0, d->stream));
+        if (d->timing) CK(cudaEventRecord(d->ev0, d->stream));
         k_qs_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, d->qs);
-        k_qs_finish<<<1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, jTotal, d->qs, G, want, st);
-        CK(cudaEventRecord(d->ev1, d->stream));
+        k_qs_finish<<<1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, jTotal, d->qs, G, want, d->qsDev, st, first, ++d->qsSeq);
+        if (d->timing) CK(cudaEventRecord(d->ev1, d->stream));
         CK(cudaGetLastError());
         d->launches += 2;
-        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
-        float ms; CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
-        if (msOut) *msOut += ms;
+        first = 0;
+        // spin on the sequence number the finish kernel publishes (see wait_lv_result)
+        const volatile unsigned long long *seq = &st->seq;
+        unsigned long spins = 0;
+        while (*seq != d->qsSeq) {
+            if ((++spins & 0xfffff) == 0) {
+                cudaError_t q = cudaStreamQuery(d->stream);
+                if (q == cudaSuccess) { if (*seq == d->qsSeq) break; gne_set_error("quickSelect pass finished without publishing its result"); return GNE_ERR_CUDA; }
+                if (q != cudaErrorNotReady) { gne_set_error("quickSelect pass failed: %s", cudaGetErrorString(q)); return GNE_ERR_CUDA; }
+            }
+        }
+        d->stageInFlight = false;
+        if (d->timing && msOut) { float ms; CK(cudaEventSynchronize(d->ev1)); CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1)); *msOut += ms; }
         d->d2hBytes += sizeof(QsState);
         if (st->done) {
             const int64_t sc = (st->stopJ >= 0) ? st->stopJ + 1 : jTotal;

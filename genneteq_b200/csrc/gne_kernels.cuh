@@ -503,14 +503,17 @@ struct QsState {            // mapped pinned host memory; carried across windows
     int64_t stopJ;          // virtual index of the want-th violator (-1 = not reached yet)
     int32_t done;
     int32_t pad;
+    unsigned long long seq; // written last, after a system-scope fence (host copy only)
 };
 
 __global__ void __launch_bounds__(TILE_THREADS)
 k_qs_finish(NbView nb, const double *__restrict__ pi, int64_t cursor, int64_t N, int64_t jLo, int64_t jHi, int64_t jEnd,
-            QsTiles tiles, int G, int64_t want, QsState *st)
+            QsTiles tiles, int G, int64_t want, QsState *st, QsState *hostOut, int first, unsigned long long seq)
 {
+    // `st` is the device-resident carry (first != 0: start from scratch); the result is also written to
+    // `hostOut` (mapped pinned) followed by a fence and the sequence number the host spins on
     const int t = threadIdx.x;
-    const int64_t carry = st->violations;
+    const int64_t carry = first ? 0 : st->violations;
     const int per = (G + TILE_THREADS - 1) / TILE_THREADS;
     const int g0 = min(G, t * per), g1 = min(G, g0 + per);
     int mine = 0;
@@ -566,13 +569,14 @@ k_qs_finish(NbView nb, const double *__restrict__ pi, int64_t cursor, int64_t N,
         seen = want;
     }
     if (t == 0) {
-        Best prev; prev.v = st->bestV; prev.p = st->bestJ;
+        Best prev; prev.v = first ? 0.0 : st->bestV; prev.p = first ? -1 : st->bestJ;
         // largestViol starts at 0.0 and is replaced on strictly greater: earlier j wins ties
         if (b.v > prev.v) prev = b;
-        st->bestV = prev.v; st->bestJ = prev.p;
-        st->violations = seen;
-        st->stopJ = stopJ;
-        st->done = (stopJ >= 0 || jHi >= jEnd) ? 1 : 0;
+        const int done = (stopJ >= 0 || jHi >= jEnd) ? 1 : 0;
+        st->bestV = prev.v; st->bestJ = prev.p; st->violations = seen; st->stopJ = stopJ; st->done = done;
+        hostOut->bestV = prev.v; hostOut->bestJ = prev.p; hostOut->violations = seen; hostOut->stopJ = stopJ; hostOut->done = done;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&hostOut->seq) = seq;
     }
 }
 
