@@ -1,0 +1,159 @@
+// TEST INFRASTRUCTURE — the drop-in claim, executed: the UNMODIFIED reference solver (its own
+// Graph loader, initialisation, potentials, flows, ratio test, tree surgery, libc drand48) with
+// only the pricing pass routed through genneteq_b200's C ABI (layer 1), exactly as INTEGRATION.md
+// section A describes.  Compiled by oracle/Makefile (`ref` target) against the reference's headers
+// and objects where they lie under /root/reference; nothing of the reference is copied.
+//
+//   gne_gpu_driver -1 <rule> -2 <rule> -T trace.txt file.col        rules: 0/1 (LV/LVW), 16/17 (QS/QSW)
+//
+// The pivot trace must equal the reference's own (tests/test_integration.py).
+#include "main.h"
+#include "matrix.h"
+#include "graph.h"
+#include "variables.h"
+#include "trees.h"
+#include "genneteq.h"
+#include "../../include/genneteq_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+int phaseIpivot = LVW;          // main.cpp:21-22 (main.cpp is not part of this build)
+int phaseIIpivot = LVW;
+
+#define GCK(call) do { int rc_ = (call); if (rc_) { fprintf(stderr, "%s failed: %d %s\n", #call, rc_, gne_last_error()); exit(3); } } while (0)
+
+class GpuGenNetEq : public GenNetEq
+{
+    gne_dev *dev;
+    std::vector<int64_t> pos;
+
+    void upload()                                           // after setVariableCosts(), genneteq.cpp:66
+    {
+        const int64_t N = (int64_t) setNBarc.size();
+        if (!dev) GCK(gne_dev_create(&dev, 0, numNodes, N + 16, 0, N + 16));
+        std::vector<int32_t> t(N), h(N);
+        std::vector<double> c(N), m(N);
+        std::vector<int8_t> s(N);
+        for (int64_t p = 0; p < N; ++p) {                   // setNBarc POSITION order (gnePivotRules.cpp:401-413)
+            ArcVar *a = setNBarc[p];
+            t[p] = a->tail; h[p] = a->head; c[p] = a->cost; m[p] = a->mult; s[p] = (int8_t) a->setLoc;
+        }
+        GCK(gne_nb_reset(dev, N, t.data(), h.data(), c.data(), m.data(), s.data()));
+    }
+    void mirrorWrite(int64_t p)                             // after the set moves of updateBasis (gnePivot.cpp:254-309)
+    {
+        if (p < 0 || p >= (int64_t) setNBarc.size()) return;
+        ArcVar *a = setNBarc[p];
+        GCK(gne_nb_write(dev, p, a->tail, a->head, a->cost, a->mult, (int8_t) a->setLoc));
+    }
+    void pushPotentials()                                   // after computePotentials(), genneteq.cpp:97
+    {
+        std::vector<double> pi(numNodes);
+        for (int i = 0; i < numNodes; ++i) pi[i] = nodes[i].potential;
+        GCK(gne_pot_set_all(dev, pi.data()));
+    }
+    Variable *gpuLargestViolation()                         // getVarWithLargestViolation, gnePivotRules.cpp:133-157
+    {
+        double L; int64_t cnt; int any;
+        pos.resize(setNBarc.size() + 16);
+        GCK(gne_price_lv(dev, &L, &cnt, pos.data(), (int64_t) pos.size(), &any));
+        isOptimal = !any;
+        lastViolation = L;
+        offendingVars.clear();
+        for (int64_t i = 0; i < cnt; ++i) offendingVars.push_back(setNBarc[pos[i]]);
+        if (offendingVars.empty()) return NULL;
+        return offendingVars[drand48() * offendingVars.size()];          // the reference's own draw (:153)
+    }
+    Variable *gpuQuickSelect()                              // quickSelect, gnePivotRules.cpp:710-764
+    {
+        isOptimal = true;
+        if (nbArcPivotInd >= (int) setNBarc.size()) nbArcPivotInd = 0;
+        int64_t best, cur, scanned, viol;
+        double bv;
+        const int start = nbArcPivotInd;
+        GCK(gne_price_qs(dev, start, numNodes, &best, &bv, &cur, &scanned, &viol));
+        if (viol > 0) isOptimal = false;
+        nbArcPivotInd = ((loopIter % majorIterationLength) > 0) ? start : (int) cur;
+        return best >= 0 ? setNBarc[best] : NULL;
+    }
+    Variable *gpuSelect()
+    {
+        if (cyclingDetected && useRandomJumpWhenCycling) return getRandomVarWithLargeViolation();   // host (:43-46), rare
+        const int rule = presolve ? phaseIpivot : phaseIIpivot;
+        if (rule == QS || rule == QSW) return gpuQuickSelect();
+        return gpuLargestViolation();
+    }
+
+  public:
+    GpuGenNetEq() : dev(NULL) {}
+    ~GpuGenNetEq() { if (dev) gne_dev_destroy(dev); }
+
+    // body of GenNetEq::solve (genneteq.cpp:60-117); the three marked lines are the only changes
+    int solveGpu(bool usePresolve, FILE *trace)
+    {
+        bool pIwasInfeasible = usePresolve ? false : isInfeasible;
+        initializeStats(usePresolve);
+        setVariableCosts();
+        upload();                                                           // <-- device mirror of setNBarc
+        if (!presolve && pIwasInfeasible) { isInfeasible = true; return loopIter; }
+        computeFlows();
+        while ((!isOptimal) && (!isUnbounded)) {
+            if ((loopIter % 1000) == 0) computeFlows(2);
+            computePotentials();
+            pushPotentials();                                               // <-- potentials to the device
+            eVar = gpuSelect();                                             // <-- identifyEnteringVariable() on the GPU
+            if (eVar != NULL) {
+                const int64_t pe = eVar->setInd, last = (int64_t) setNBarc.size() - 1;
+                pivot();
+                if (lVar != NULL) {
+                    if (trace) fprintf(trace, "P %d %d %d\n", loopIter, eVar->varIndex, lVar->varIndex);
+                    // the positions updateBasis touched: eVar's old slot (the last element moved in),
+                    // the last slot(s) (pushes), and wherever the leaving / flipped variable landed
+                    mirrorWrite(pe); mirrorWrite(last); mirrorWrite(last - 1);
+                    if (lVar->setLoc != B_var) mirrorWrite(lVar->setInd);
+                    if (eVar->setLoc != B_var) mirrorWrite(eVar->setInd);
+                    GCK(gne_nb_set_count(dev, (int64_t) setNBarc.size()));
+                }
+                ++loopIter;
+                presolve ? ++phaseIiters : ++phaseIIiters;
+            }
+        }
+        computeFlows();
+        if (presolve) checkFeasibility();
+        verifyOptimality();
+        printTerminationStatus();
+        return loopIter;
+    }
+    double objective() const { return flowCost; }
+};
+
+int main(int argc, char **argv)
+{
+    const char *tracePath = NULL, *inPath = NULL;
+    for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "-1") && i + 1 < argc) phaseIpivot = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-2") && i + 1 < argc) phaseIIpivot = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-T") && i + 1 < argc) tracePath = argv[++i];
+        else inPath = argv[i];
+    }
+    if (!inPath) { fprintf(stderr, "usage: %s [-1 r] [-2 r] [-T trace] file.col\n", argv[0]); return 2; }
+    Config conf;
+    conf.initType = INFEASIBLE;
+    conf.debug = 0;
+    conf.inFile = inPath;
+    Graph *g = new Graph();
+    g->initialize(&conf);                                   // the reference's own dense loader
+    GpuGenNetEq *solver = new GpuGenNetEq();
+    solver->initialize(g, conf.initType);
+    delete g;
+    FILE *trace = tracePath ? fopen(tracePath, "w") : NULL;
+    const int p1 = solver->solveGpu(USE_PRESOLVE, trace);
+    const int p2 = solver->solveGpu(USE_SOLVE, trace);
+    if (trace) fclose(trace);
+    printf("GPU-REF pivots %d %d objective %.17g\n", p1, p2, solver->objective());
+    delete solver;
+    return 0;
+}

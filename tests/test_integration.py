@@ -1,0 +1,67 @@
+"""Drop-in boundary, executed: the UNMODIFIED reference host engine (compiled from /root/reference into
+oracle/_ref/gne_gpu_driver by oracle/Makefile) with only its pricing pass routed through the product's C ABI
+(layer 1: gne_nb_reset / gne_nb_write / gne_pot_set_all / gne_price_lv / gne_price_qs), as INTEGRATION.md
+section A describes.  The pivot trace must equal the reference's own golden trace.
+
+Reference: GenNetEq::solve genneteq.cpp:60-117, getVarWithLargestViolation gnePivotRules.cpp:133-157,
+quickSelect gnePivotRules.cpp:710-764, updateBasis gnePivot.cpp:254-309.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+from oracle_util import RULES  # noqa: E402
+import gen_instance  # noqa: E402
+
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "gne_gpu_driver")
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def _run_driver(col, r1, r2, trace_path):
+    out = subprocess.run([DRIVER, "-1", str(r1), "-2", str(r2), "-T", trace_path, col],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    piv = []
+    with open(trace_path) as f:
+        for line in f:
+            if line.startswith("P "):
+                _, it, e, l = line.split()
+                piv.append((int(it), int(e), int(l)))
+    obj = None
+    for line in out.stdout.splitlines():
+        if line.startswith("GPU-REF pivots"):
+            obj = float(line.split()[-1])
+    return np.array(piv, dtype=np.int64).reshape(-1, 3), obj
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture,rule", [
+    ("s_wide_s3", "LV"), ("s_wide_s3", "QS"), ("s_lossy_s4", "LV"), ("s_pow2_s5", "LV"),
+    ("s_near1_s6", "QSW"), ("c1_wide_s7", "LV"), ("c1_wide_s7", "QS"),
+])
+def test_reference_engine_with_gpu_pricing(fixture, rule, tmp_path):
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/gne_gpu_driver not built (needs /root/reference at build time)")
+    z = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    if rule + "_e" not in z.files:
+        pytest.skip("no golden trace for %s/%s" % (fixture, rule))
+    n, m, seed = (int(v) for v in z["params"])
+    arcs, sup = gen_instance.generate(n, m, seed, str(z["mode"]))
+    col = str(tmp_path / (fixture + ".col"))
+    gen_instance.write_col(col, n, arcs, sup)
+    assert hashlib.md5(open(col, "rb").read()).hexdigest() == str(z["col_md5"])
+    r = RULES[rule]
+    trace = str(tmp_path / "trace.txt")
+    piv, obj = _run_driver(col, r, r, trace)
+    assert np.array_equal(piv[:, 1], z[rule + "_e"]) and np.array_equal(piv[:, 2], z[rule + "_l"])
+    assert hashlib.md5(open(trace, "rb").read()).hexdigest() == str(z[rule + "_md5"])
+    assert obj == float(z[rule + "_objective"])
