@@ -87,6 +87,7 @@ SIGNATURES = {
     "gne_solver_feasible": (C.c_int, [_vp]),
     "gne_solver_get_flows": (C.c_int, [_vp, _f64p]),
     "gne_solver_get_potentials": (C.c_int, [_vp, _f64p]),
+    "gne_solver_compute_potentials": (C.c_int, [_vp]),
     "gne_solver_get_states": (C.c_int, [_vp, _i32p]),
     "gne_solver_get_forest": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "gne_solver_get_counters": (C.c_int, [_vp, _f64p]),
@@ -420,6 +421,10 @@ class Solver:
         a = np.empty(self.n)
         _ck(lib.gne_solver_get_potentials(self.h, _p(a, _f64p)), "gne_solver_get_potentials")
         return a
+
+    def compute_potentials(self):
+        """computePotentials() for the current basis; device potentials + nonbasic mirror brought up to date."""
+        _ck(lib.gne_solver_compute_potentials(self.h), "gne_solver_compute_potentials")
 
     def states(self):
         a = np.empty(self.M, np.int32)

@@ -244,6 +244,12 @@ extern "C" double gne_solver_objective(const gne_solver *s) { return s->solver.g
 extern "C" int gne_solver_feasible(const gne_solver *s) { return s->solver.getIsInfeasible() ? 0 : 1; }
 extern "C" int gne_solver_get_flows(gne_solver *s, double *out) { s->solver.getFlows(out); return GNE_OK; }
 extern "C" int gne_solver_get_potentials(gne_solver *s, double *out) { return s->solver.getPotentials(out); }
+extern "C" int gne_solver_compute_potentials(gne_solver *s)
+{
+    int rc = s->solver.refreshPotentials();
+    if (rc) return rc;
+    return gne_dev_sync(s->solver.device());
+}
 extern "C" int gne_solver_get_states(gne_solver *s, int32_t *out) { s->solver.getStates(out); return GNE_OK; }
 extern "C" int gne_solver_get_forest(gne_solver *s, int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread)
 {

@@ -142,6 +142,7 @@ struct gne_dev {
     SmallUpdate lastSmall{};                       // the last argument-only update (bench replay)
     bool haveLastSmall = false;
     bool timing = false;                           // bracket pricing kernels with CUDA events (gne_dev_set_timing)
+    bool pdl = true;                               // programmatic dependent launch between a pivot's kernels (GNE_PDL=0 disables)
     unsigned long long lvSeq = 0;                  // sequence number of the last LV pass launched
     unsigned long long qsSeq = 0;
     QsState *qsDev = nullptr;                      // device-resident carry of the quickSelect scan
@@ -257,6 +258,7 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     CK(cudaHostAlloc(&d->hostScalar, 64, cudaHostAllocMapped));
     memset(d->lvRes, 0, sizeof(LvResult));
     { const char *tm = getenv("GNE_TIMING"); d->timing = tm && tm[0] == '1'; }
+    { const char *pd = getenv("GNE_PDL"); d->pdl = !(pd && pd[0] == '0'); }
     memset(d->qsState, 0, sizeof(QsState));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     *out = d;
@@ -652,6 +654,22 @@ static bool use_stream_kernel(const gne_dev *d)
     return d->streamHoldoff == 0 && len >= (int64_t) 8 * d->streamGrid * ST_TILE;
 }
 
+// Launch on the handle's stream; with `dependent` the kernel may become resident while its predecessor
+// still runs (programmatic stream serialization) - it calls pdl_wait() before touching anything the
+// predecessor wrote.  Used only between the kernels of one pivot.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(gne_dev *d, bool dependent, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&... args)
+{
+    cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = d->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (dependent && d->pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEvent_t evB)
 {
     const int G = tiles_for(d);
@@ -660,15 +678,15 @@ static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEve
     d->lastWasStream = use_stream_kernel(d);
     if (d->lastWasStream) {
         const int64_t numTiles = (nb.end - nb.lo + ST_TILE - 1) / ST_TILE;
-        k_price_lv_stream<<<d->streamGrid, ST_THREADS, ST_SMEM, d->stream>>>(nb, d->pi, d->lvc, numTiles);
+        CK(launch_k(d, true, k_price_lv_stream, dim3(d->streamGrid), dim3(ST_THREADS), ST_SMEM, nb, (const double *) d->pi, d->lvc, numTiles));
         ++d->launches;
         if (evB) CK(cudaEventRecord(evB, d->stream));
-        k_price_lv_finish_stream<<<1, 1024, 0, d->stream>>>(d->lvc, d->streamGrid, target, ++d->lvSeq);
+        CK(launch_k(d, true, k_price_lv_finish_stream, dim3(1), dim3(1024), 0, d->lvc, d->streamGrid, target, (unsigned long long) ++d->lvSeq));
         ++d->launches;
     } else {
-        if (G > 0) { k_price_lv_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, d->lv); ++d->launches; }
+        if (G > 0) { CK(launch_k(d, true, k_price_lv_tiles, dim3(G), dim3(TILE_THREADS), 0, nb, (const double *) d->pi, d->lv)); ++d->launches; }
         if (evB) CK(cudaEventRecord(evB, d->stream));
-        k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, G, d->lo, target, ++d->lvSeq);
+        CK(launch_k(d, true, k_price_lv_finish, dim3(1), dim3(FIN_THREADS), 0, d->lv, G, d->lo, target, (unsigned long long) ++d->lvSeq));
         ++d->launches;
         if (d->streamHoldoff > 0) --d->streamHoldoff;
     }
@@ -689,18 +707,23 @@ static int price_lv_local(gne_dev *d)
 // number in mapped pinned memory after a system-scope fence, so the host polls that word (a few
 // hundred ns of latency) instead of paying a stream synchronisation; the stream is queried now and
 // then so that a faulted kernel is reported instead of spinning forever.
-static int wait_lv_result(gne_dev *d)
+static int wait_host_seq(gne_dev *d, const volatile unsigned long long *seq, unsigned long long expect)
 {
-    const volatile unsigned long long *seq = &d->lvRes->seq;
     unsigned long spins = 0;
-    while (*seq != d->lvSeq) {
+    while (*seq != expect) {
         if ((++spins & 0xfffff) == 0) {                  // ~ every millisecond
             cudaError_t q = cudaStreamQuery(d->stream);
-            if (q == cudaSuccess) { if (*seq == d->lvSeq) break; gne_set_error("pricing pass finished without publishing its result"); return GNE_ERR_CUDA; }
+            if (q == cudaSuccess) { if (*seq == expect) break; gne_set_error("pricing pass finished without publishing its result"); return GNE_ERR_CUDA; }
             if (q != cudaErrorNotReady) { gne_set_error("pricing pass failed: %s", cudaGetErrorString(q)); return GNE_ERR_CUDA; }
         }
     }
     d->stageInFlight = false;
+    return GNE_OK;
+}
+
+static int wait_lv_result(gne_dev *d)
+{
+    int rc = wait_host_seq(d, &d->lvRes->seq, d->lvSeq); if (rc) return rc;
     if (d->timing) { CK(cudaEventSynchronize(d->ev1)); CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1)); }
     else d->lastMs = 0.f;
     return GNE_OK;
@@ -1094,21 +1117,25 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
     }
     if (!d->ev2) { CK(cudaEventCreate(&d->ev2)); CK(cudaEventCreate(&d->ev3)); }
     for (int i = 0; i < reps; ++i) {
-        if (flushL2) { k_flush_l2<<<148 * 8, 256, 0, d->stream>>>(d->flushBuf, d->flushLen); ++d->launches; }
-        CK(cudaEventRecord(d->ev2, d->stream));
-        if (withFinalize == 2 && d->haveLastSmall) {
-            // the relabel of a typical pivot of this window: the last argument-only update, replayed (idempotent)
-            NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
-            k_update_small<<<1, 256, 0, d->stream>>>(mm, d->lastSmall, d->a0, d->a1, d->slot, d->theta, d->pi);
-            ++d->launches;
-        } else if (withFinalize) { k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi); ++d->launches; }
-        rc = launch_lv_pass(d, d->nranks > 1 ? d->lvResDev : d->lvRes, d->ev0, d->ev1); if (rc) return rc;
-        if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
-        CK(cudaEventRecord(d->ev3, d->stream));
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
-        CK(cudaEventElapsedTime(&msStep[i], d->ev2, d->ev3));
-        CK(cudaEventElapsedTime(&msTiles[i], d->ev0, d->ev1));
+        // pass 0 brackets the pricing kernel alone (events between the kernels serialise them fully);
+        // pass 1 is the step as the solver launches it - no events inside, the kernels chained by PDL
+        for (int pass = 0; pass < 2; ++pass) {
+            if (flushL2) { k_flush_l2<<<148 * 8, 256, 0, d->stream>>>(d->flushBuf, d->flushLen); ++d->launches; }
+            CK(cudaEventRecord(d->ev2, d->stream));
+            if (withFinalize == 2 && d->haveLastSmall) {
+                // the relabel of a typical pivot of this window: the last argument-only update, replayed (idempotent)
+                NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
+                k_update_small<<<1, 256, 0, d->stream>>>(mm, d->lastSmall, d->a0, d->a1, d->slot, d->theta, d->pi);
+                ++d->launches;
+            } else if (withFinalize) { k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi); ++d->launches; }
+            rc = launch_lv_pass(d, d->nranks > 1 ? d->lvResDev : d->lvRes, pass == 0 ? d->ev0 : nullptr, pass == 0 ? d->ev1 : nullptr); if (rc) return rc;
+            if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
+            CK(cudaEventRecord(d->ev3, d->stream));
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+            if (pass == 0) CK(cudaEventElapsedTime(&msTiles[i], d->ev0, d->ev1));
+            else CK(cudaEventElapsedTime(&msStep[i], d->ev2, d->ev3));
+        }
     }
     return GNE_OK;
 }
@@ -1152,10 +1179,12 @@ __global__ void k_pack_record(const LvResult *res, ShardRecord *rec) { pack_reco
 // into every rank's mailbox (peer memory over NVLink), publishes the sequence flag, waits for the
 // peers' flags and copies all records to mapped pinned host memory.  No NCCL call, no copy engine.
 __global__ void __launch_bounds__(128)
-k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, ShardRecord *hostOut)
+k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, ShardRecord *hostOut,
+              unsigned long long *hostSeq)
 {
     __shared__ ShardRecord rec;
     const int t = threadIdx.x;
+    pdl_wait();                                         // the shard's reduction has published its result block
     pack_record(res, &rec, t);
     __syncthreads();
     const int b = (int) (seq & 1ull);
@@ -1185,7 +1214,12 @@ k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, 
         unsigned long long *out = reinterpret_cast<unsigned long long *>(&hostOut[r]);
         for (int w = t; w < WORDS; w += blockDim.x) out[w] = in[w];
     }
+    __syncthreads();
     if (sTimeout && t == 0) hostOut[0].count = -2;
+    // the host polls hostSeq instead of synchronising the stream: every writer fences its own stores first
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) *reinterpret_cast<volatile unsigned long long *>(hostSeq) = seq;
 }
 // all-gather of one 128-byte blob per rank through the peer mailboxes (same protocol as k_lv_exchange)
 __global__ void __launch_bounds__(64)
@@ -1342,7 +1376,8 @@ extern "C" int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nr
     d->rank = rank; d->nranks = nranks;
     CK(cudaMalloc(&d->gatherSend, sizeof(ShardRecord)));
     CK(cudaMalloc(&d->gatherRecv, sizeof(ShardRecord) * (size_t) nranks));
-    CK(cudaHostAlloc(&d->gatherHost, sizeof(ShardRecord) * (size_t) nranks, cudaHostAllocMapped));
+    CK(cudaHostAlloc(&d->gatherHost, sizeof(ShardRecord) * (size_t) nranks + 64, cudaHostAllocMapped));   // + the sequence word the host polls
+    memset(d->gatherHost, 0, sizeof(ShardRecord) * (size_t) nranks + 64);
     CK(cudaMalloc(&d->lvResDev, sizeof(LvResult)));
     CK(cudaMemset(d->lvResDev, 0, sizeof(LvResult)));
     // peer mailboxes: exchange CUDA IPC handles through the NCCL communicator, map every peer's buffer
@@ -1395,8 +1430,9 @@ static int launch_shard_exchange(gne_dev *d)
 {
     if (d->p2p) {
         // fused pack + NVLink peer stores + flag wait + copy to mapped pinned host: one kernel
-        k_lv_exchange<<<1, 128, 0, d->stream>>>(d->lvResDev, d->peersDev, d->rank, d->nranks, ++d->xseq, (ShardRecord *) d->gatherHost);
-        CK(cudaGetLastError());
+        unsigned long long *hostSeq = reinterpret_cast<unsigned long long *>((char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
+        CK(launch_k(d, true, k_lv_exchange, dim3(1), dim3(128), 0, (const LvResult *) d->lvResDev, (Mailbox *const *) d->peersDev, d->rank, d->nranks,
+                    (unsigned long long) ++d->xseq, (ShardRecord *) d->gatherHost, hostSeq));
         ++d->launches;
         return GNE_OK;
     }
@@ -1453,22 +1489,30 @@ int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &
 {
     // price_lv_local has been launched by the caller; exchange, then the same merge on every rank
     int rcx = launch_shard_exchange(d); if (rcx) return rcx;
-    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    if (d->p2p) {
+        const volatile unsigned long long *hostSeq =
+            reinterpret_cast<const volatile unsigned long long *>((const char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
+        rcx = wait_host_seq(d, hostSeq, d->xseq); if (rcx) return rcx;
+    } else {
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    }
     d->d2hBytes += sizeof(ShardRecord) * (int64_t) d->nranks;
     const ShardRecord *rec = (const ShardRecord *) d->gatherHost;
     if (rec[0].count == -2) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
-    std::vector<double> maxima(d->nranks);
-    std::vector<int> anys(d->nranks);
-    std::vector<int64_t> counts(d->nranks), pos((size_t) d->nranks * SHARD_LIST);
-    std::vector<double> viol((size_t) d->nranks * SHARD_LIST);
+    // scratch kept across pivots (no allocation on the per-pivot path)
+    static thread_local std::vector<double> maxima, viol;
+    static thread_local std::vector<int> anys;
+    static thread_local std::vector<int64_t> counts, pos, outPos;
+    maxima.resize(d->nranks); anys.resize(d->nranks); counts.resize(d->nranks);
+    pos.resize((size_t) d->nranks * SHARD_LIST); viol.resize((size_t) d->nranks * SHARD_LIST); outPos.resize((size_t) d->nranks * SHARD_LIST);
     for (int k = 0; k < d->nranks; ++k) {
         maxima[k] = rec[k].maxViol; anys[k] = rec[k].any;
         counts[k] = rec[k].overflow ? -1 : rec[k].count;
-        for (int i = 0; i < SHARD_LIST; ++i) { pos[(size_t) k * SHARD_LIST + i] = rec[k].pos[i]; viol[(size_t) k * SHARD_LIST + i] = rec[k].viol[i]; }
+        const int64_t c = std::min<int64_t>(std::max<int64_t>(rec[k].count, 0), SHARD_LIST);
+        for (int64_t i = 0; i < c; ++i) { pos[(size_t) k * SHARD_LIST + i] = rec[k].pos[i]; viol[(size_t) k * SHARD_LIST + i] = rec[k].viol[i]; }
     }
     int64_t cnt = 0;
     int need = 0;
-    std::vector<int64_t> outPos((size_t) d->nranks * SHARD_LIST);
     int rc = gne_merge_lv_shards(d->nranks, maxima.data(), anys.data(), counts.data(), pos.data(), viol.data(), SHARD_LIST,
                                  largest, &cnt, outPos.data(), (int64_t) outPos.size(), any, &need);
     if (rc) return rc;

@@ -137,6 +137,12 @@ __device__ __forceinline__ int block_excl_scan(int x, int *total)
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): the kernels of one pivot (update -> price -> reduce -> exchange) are
+// launched back to back; each lets its successor become resident early and the successor waits here until
+// its predecessor has completed and flushed.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // LV pass, stage 1 (one CTA per tile): tile maximum, number of violators within LV_BAND of it,
 // and the first CAND_K of those in position order.
 // ------------------------------------------------------------------------------------------
@@ -150,6 +156,8 @@ struct LvTiles {
 __global__ void __launch_bounds__(TILE_THREADS, 8)
 k_price_lv_tiles(NbView nb, const double *__restrict__ pi, LvTiles out)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t tileBase = (int64_t) blockIdx.x * TILE;
     double v[ITEMS];
     tile_violations(nb, pi, tileBase, v);
@@ -210,6 +218,8 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long
     __shared__ int sCount, sOvf;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) { sCount = 0; sOvf = 0; }
+    pdl_launch_dependents();
+    pdl_wait();
     // pass 1: maximum of the tile maxima; loads issued in independent batches of 8 (a dependent
     // one-load-per-iteration loop costs a full memory latency per iteration)
     double m = -1.0;
@@ -672,6 +682,7 @@ __global__ void __launch_bounds__(256)
 k_update_small(NbMut nb, const __grid_constant__ SmallUpdate u, double *A0, double *A1, int32_t *S, double *T, double *pi)
 {
     const int t = threadIdx.x;
+    pdl_launch_dependents();
     if (t < u.ops.n) {
         const int64_t l = u.ops.local[t];
         nb.tail[l] = u.ops.tail[t]; nb.head[l] = u.ops.head[t];

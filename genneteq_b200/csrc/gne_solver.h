@@ -79,6 +79,7 @@ class GenNetEq {
     bool getIsInfeasible() const { return isInfeasible; }
     void getFlows(double *out) const;
     int getPotentials(double *out);
+    int refreshPotentials() { return computePotentials(); }     // computePotentials() for the CURRENT basis (idempotent)
     void getStates(int32_t *out) const;
     const Forest &getForest() const { return forest; }
     Forest &getForestMutable() { return forest; }

@@ -78,7 +78,9 @@ k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t 
         for (int s = 0; s < ST_STAGES; ++s) st_mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();                                         // the relabel kernel's potentials and list edits are complete
     auto issue = [&](int s, int64_t tile) {
         unsigned char *b = stage0 + (size_t) s * ST_STAGE_BYTES;
         const int64_t l0 = tile * ST_TILE;
@@ -160,6 +162,8 @@ k_price_lv_finish_stream(LvCtas in, int G, LvResult *res, unsigned long long seq
     __shared__ int sCount, sOvf;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) { sCount = 0; sOvf = 0; }
+    pdl_launch_dependents();
+    pdl_wait();
     double m = -1.0;
     for (int g = t; g < G; g += 1024) m = fmax(m, in.ctaMax[g]);
 #pragma unroll

@@ -189,6 +189,11 @@ double gne_solver_objective(const gne_solver *s);
 int gne_solver_feasible(const gne_solver *s);
 int gne_solver_get_flows(gne_solver *s, double *out);
 int gne_solver_get_potentials(gne_solver *s, double *out);
+/* GenNetEq::computePotentials() (gnePotential.cpp:28-61) for the CURRENT basis: relabels the nodes the last pivot
+ * touched and brings the device's potentials and nonbasic mirror up to date, i.e. the state the next pricing pass
+ * will read.  Idempotent, consumes no drand48 draw, does not change the pivot sequence: it is the hook for the
+ * same-state A/B of SURVEY 8(d)(ii) (read the state back with gne_nb_read / gne_pot_get_all on gne_solver_device). */
+int gne_solver_compute_potentials(gne_solver *s);
 int gne_solver_get_states(gne_solver *s, int32_t *out);
 int gne_solver_get_forest(gne_solver *s, int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread);
 /* counters: [0] pricing s (host wall incl. sync)  [1] potentials s  [2] pivot s  [3] total s

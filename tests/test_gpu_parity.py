@@ -388,6 +388,57 @@ def test_c2_prefix_window_equals_oracle(gne, rule, K):
     s.close(); o.close()
 
 
+def test_c2_deep_same_state_ab(gne):
+    """same-state A/B deep into a GPU-driven solve of configs[1] (100k nodes / 2M arcs).  At
+    sampled iterations the state the next pricing pass will read (nonbasic mirror in setNBarc order + potentials)
+    is read back from the device and priced by the oracle's scalar pass: largest violation, the whole tie list and
+    the quickSelect block must be identical, the next entering variable must be a member of the oracle's list, and
+    the extra probe must not disturb the pivot sequence (second solver without probes gives the same trace)."""
+    import time
+    g = gne.generate_instance(100_000, 2_000_000, 21, "lossy")
+    n, m = g["n"], len(g["tail"])
+    key = g["tail"].astype(np.int64) * n + g["head"]
+    assert np.all(np.diff(key) > 0)
+    s = gne.Solver(n, g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"], rule1="LV", trace_cap=60000)
+    plain = gne.Solver(n, g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"], rule1="LV", trace_cap=60000)
+    done = 0
+    for target in (1000, 12000, 25000, 40000):
+        # (re-entering solve() restarts loopIter and recomputes the flows exactly as the reference's solve() would,
+        #  so the probe-free solver below is driven through the same sequence of calls)
+        s.solve(True, target - done)
+        plain.solve(True, target - done)
+        done = target
+        s.compute_potentials()
+        dev = s.device()
+        st = s.states()
+        N = int(np.count_nonzero(st != 0))                          # |setNBarc|: L_var = 1, U_var = 2, basic = 0
+        t, h, c, mu, sta = dev.nb_read(0, N)
+        pi = dev.pot_get_all()[:n]
+        assert np.array_equal(pi, s.potentials())
+        t0 = time.perf_counter()
+        L, lst, anyv = oracle_lv(t, h, c, mu, sta, pi)
+        cpu_s = time.perf_counter() - t0
+        gL, gcount, gany = dev.price_lv_begin()
+        kern_ms = dev.last_kernel_ms()
+        assert (gL, gcount, gany) == (L, len(lst), anyv)
+        for idx in {0, gcount // 2, gcount - 1}:
+            assert dev.price_lv_at(idx) == lst[idx]
+        for cursor in (0, N // 3, N - 5):
+            assert dev.price_qs(cursor, n) == oracle_qs(t, h, c, mu, sta, pi, cursor, n)
+        # the variable the solver enters next is a member of the oracle's tie list at this state
+        var = np.where(t == h, m + t.astype(np.int64), np.searchsorted(key, t.astype(np.int64) * n + h))
+        s.solve(True, 1)
+        plain.solve(True, 1)
+        done += 1
+        assert int(s.trace[0][done - 1]) in set(var[lst].tolist())
+        print("pivot %d: |NB| %d  L %.6g  ties %d  oracle pass %.1f ms  device kernel %.4f ms" %
+              (target, N, L, len(lst), 1e3 * cpu_s, kern_ms))
+    assert len(s.trace[0]) == done
+    assert np.array_equal(plain.trace[0], s.trace[0]) and np.array_equal(plain.trace[1], s.trace[1])
+    assert np.array_equal(plain.flows(), s.flows())
+    s.close(); plain.close()
+
+
 def test_c3_full_size_pricing_pass_equals_oracle(gne):
     """configs[2] size: 1M nodes / 20M arcs.  One Dantzig pass at the initial Phase-I state and after
     200 pivots, against the oracle's scalar pass over the same 20M-arc structure-of-arrays."""
