@@ -287,8 +287,13 @@ def b200_arm(args):
     dbg("device warm-up steps done")
     ms_step, ms_tiles = dev.bench_price_lv(args.steps, flush)
     barrier()
-    dbg("device steps done")
+    dbg("device steps done: kernel ms mean %.4f min %.4f max %.4f | step ms mean %.4f min %.4f max %.4f" % (
+        ms_tiles.mean(), ms_tiles.min(), ms_tiles.max(), ms_step.mean(), ms_step.min(), ms_step.max()))
     clocks = sampler.stop()
+    if os.environ.get("GNE_BENCH_DEBUG") == "2":
+        for name, mean, best in dev.bench_variants(10):
+            if name.startswith(("production", "tma<256thr,4it,3st> 148x2", "k_price_lv")):
+                dbg("variant %-60s mean %.2f us best %.2f us" % (name, mean * 1e3, best * 1e3))
     launches = int(s.counters()["launches"] - c0["launches"])     # e2e window + device steps (warm-up excluded from neither)
     lv_kernel = {"stream": "k_price_lv_stream", "tiles": "k_price_lv_tiles"}[dev.last_lv_kernel()]
     dev.close()

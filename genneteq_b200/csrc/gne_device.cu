@@ -1,6 +1,7 @@
 // genneteq_b200 — layer 1 of the C ABI: device-resident state and kernel launches.
 // See include/genneteq_b200.h for the contract of every entry point.
 #include "gne_kernels.cuh"
+#include "gne_exchange.cuh"
 #include "gne_stream.cuh"
 #include "gne_variants.cuh"
 #include "gne_internal.h"
@@ -136,12 +137,15 @@ struct gne_dev {
     bool stageInFlight = false;                    // the staging buffer feeds a kernel not yet synchronised
     LvCtas lvc{};                                  // per-CTA records of the TMA-streamed LV pass
     int streamGrid = 0;                            // 2 CTAs per SM
+    unsigned int *lvTicket = nullptr;              // last-CTA ticket of the streamed pass (zero between passes)
     int streamOverflows = 0, streamHoldoff = 0;    // adaptive fallback to the per-tile kernel
     bool lastWasStream = false;
     int lvKernelMode = 0;                          // 0 auto, 1 per-tile kernel, 2 TMA-streamed kernel
     SmallUpdate lastSmall{};                       // the last argument-only update (bench replay)
     bool haveLastSmall = false;
     bool timing = false;                           // bracket pricing kernels with CUDA events (gne_dev_set_timing)
+    std::vector<cudaEvent_t> benchEv;              // per-step event pairs of gne_bench_price_lv
+    bool exchangeFused = false;                    // the last streamed pass carried the shard exchange itself
     bool pdl = true;                               // programmatic dependent launch between a pivot's kernels (GNE_PDL=0 disables)
     unsigned long long lvSeq = 0;                  // sequence number of the last LV pass launched
     unsigned long long qsSeq = 0;
@@ -248,7 +252,9 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cudaDevice);
         d->streamGrid = sms * ST_CTAS_PER_SM;
-        CK(cudaMalloc(&d->lvc.ctaMax, 8 * (size_t) d->streamGrid)); CK(cudaMalloc(&d->lvc.ctaCnt, 4 * (size_t) d->streamGrid));
+        if (d->streamGrid > 2 * ST_THREADS) d->streamGrid = 2 * ST_THREADS;        // the reduction reads two records per thread
+        CK(cudaMalloc(&d->lvc.rec, sizeof(CtaRec) * (size_t) d->streamGrid));
+        CK(cudaMalloc(&d->lvTicket, 64)); CK(cudaMemset(d->lvTicket, 0, 64));
         CK(cudaMalloc(&d->lvc.candPos, 8 * (size_t) d->streamGrid * ST_CAND)); CK(cudaMalloc(&d->lvc.candViol, 8 * (size_t) d->streamGrid * ST_CAND));
         CK(cudaMalloc(&d->lvc.candSecond, 8 * (size_t) d->streamGrid * ST_CAND));
         CK(cudaFuncSetAttribute(k_price_lv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
@@ -275,7 +281,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
-                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.ctaMax, d->lvc.ctaCnt, d->lvc.candPos, d->lvc.candViol, d->lvc.candSecond, d->qsDev, d->stageDev, d->outPos, d->outViol,
+                    d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.rec, d->lvTicket, d->lvc.candPos, d->lvc.candViol, d->lvc.candSecond, d->qsDev, d->stageDev, d->outPos, d->outViol,
                     d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev };
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes, d->blobHost };
@@ -284,6 +290,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->ev2) cudaEventDestroy(d->ev2);
     if (d->ev3) cudaEventDestroy(d->ev3);
+    for (cudaEvent_t e : d->benchEv) cudaEventDestroy(e);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
     return GNE_OK;
@@ -660,29 +667,49 @@ static bool use_stream_kernel(const gne_dev *d)
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(gne_dev *d, bool dependent, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&... args)
 {
+    if (!(dependent && d->pdl)) {
+        kernel<<<grid, block, smem, d->stream>>>(std::forward<Args>(args)...);
+        return cudaGetLastError();
+    }
     cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = d->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = (dependent && d->pdl) ? 1 : 0;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEvent_t evB)
+static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEvent_t evB, bool withExchange = true)
 {
     const int G = tiles_for(d);
     NbView nb = view_of(d);
     if (evA) CK(cudaEventRecord(evA, d->stream));
     d->lastWasStream = use_stream_kernel(d);
+    d->exchangeFused = false;
     if (d->lastWasStream) {
         const int64_t numTiles = (nb.end - nb.lo + ST_TILE - 1) / ST_TILE;
-        CK(launch_k(d, true, k_price_lv_stream, dim3(d->streamGrid), dim3(ST_THREADS), ST_SMEM, nb, (const double *) d->pi, d->lvc, numTiles));
+        LvFused f;
+        memset(&f, 0, sizeof(f));
+        f.res = target; f.seq = ++d->lvSeq; f.resOnHost = (target == d->lvRes) ? 1 : 0;
+        f.nranks = 1;
+        if (withExchange && d->nranks > 1 && d->p2p) {
+            // sharded over peer mailboxes - one launch: pricing, reduction by the last CTA, exchange
+            f.ticket = d->lvTicket;
+            f.nranks = d->nranks; f.rank = d->rank; f.peers = (Mailbox *const *) d->peersDev;
+            f.hostOut = (ShardRecord *) d->gatherHost;
+            f.hostSeq = reinterpret_cast<unsigned long long *>((char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
+            f.xseq = ++d->xseq;
+            d->exchangeFused = true;
+        }
+        CK(launch_k(d, true, k_price_lv_stream, dim3(d->streamGrid), dim3(ST_THREADS), ST_SMEM, nb, (const double *) d->pi, d->lvc, numTiles, f));
         ++d->launches;
         if (evB) CK(cudaEventRecord(evB, d->stream));
-        CK(launch_k(d, true, k_price_lv_finish_stream, dim3(1), dim3(1024), 0, d->lvc, d->streamGrid, target, (unsigned long long) ++d->lvSeq));
-        ++d->launches;
+        if (!d->exchangeFused) {
+            CK(launch_k(d, true, k_price_lv_reduce, dim3(1), dim3(ST_THREADS), 0, d->lvc, d->streamGrid, f));
+            ++d->launches;
+        }
     } else {
         if (G > 0) { CK(launch_k(d, true, k_price_lv_tiles, dim3(G), dim3(TILE_THREADS), 0, nb, (const double *) d->pi, d->lv)); ++d->launches; }
         if (evB) CK(cudaEventRecord(evB, d->stream));
@@ -1033,7 +1060,7 @@ static const char *g_variantNames[] = {
     "tma<256thr,4it,3st> 148x2", "tma<256thr,4it,4st> 148x2", "tma<256thr,2it,6st> 148x2", "tma<256thr,2it,4st> 148x4", "tma<256thr,2it,3st> 148x5",
     "tma<512thr,2it,4st> 148x2", "tma<128thr,4it,4st> 148x4", "tma<256thr,1it,8st> 148x4", "tma<512thr,2it,3st> 148x2", "tma<256thr,2it,8st> 148x2",
     "tma<256thr,4it,3st> 148x1", "production k_price_lv_stream", "k_price_lv_finish (per-tile records, mapped host result)",
-    "k_price_lv_finish_stream (per-CTA records, mapped host result)", "k_price_lv_finish_stream (device result)", "k_update_small replay" };
+    "k_price_lv_reduce (per-CTA records, mapped host result)", "k_price_lv_stream + last-CTA reduction (sharded form, device result)", "k_update_small replay" };
 extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants)
 {
     CK(cudaSetDevice(d->device));
@@ -1082,11 +1109,29 @@ extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVar
               GNE_TMA_CASE(22, 256, 2, 8, 2, 2)
               GNE_TMA_CASE(23, 256, 4, 3, 1, 1)
 #undef GNE_TMA_CASE
-              case 24: k_price_lv_stream<<<d->streamGrid, ST_THREADS, ST_SMEM, d->stream>>>(nb, d->pi, d->lvc, (len + ST_TILE - 1) / ST_TILE); break;
+              case 24: case 26: case 27: {
+                  // 24: production streaming pass (per-CTA records); 26: the reduction kernel that follows it on one GPU;
+                  // 27: the sharded form - pricing + last-CTA reduction in one launch (result block in device memory)
+                  LvFused f; memset(&f, 0, sizeof(f));
+                  if (!d->lvResDev) cudaMalloc(&d->lvResDev, sizeof(LvResult));
+                  f.res = (v == 27) ? d->lvResDev : d->lvRes; f.seq = ++d->lvSeq; f.resOnHost = (v == 27) ? 0 : 1; f.nranks = 1;
+                  if (v == 27) f.ticket = d->lvTicket;
+#ifdef GNE_STAMPS
+                  static long long *stampsDev = nullptr;
+                  if (!stampsDev) { cudaMalloc(&stampsDev, 64); cudaMemset(stampsDev, 0, 64); }
+                  f.stamps = stampsDev;
+#endif
+                  if (v == 26) k_price_lv_reduce<<<1, ST_THREADS, 0, d->stream>>>(d->lvc, d->streamGrid, f);
+                  else k_price_lv_stream<<<d->streamGrid, ST_THREADS, ST_SMEM, d->stream>>>(nb, d->pi, d->lvc, (len + ST_TILE - 1) / ST_TILE, f);
+#ifdef GNE_STAMPS
+                  if (r == reps + 1 && v == 27) {
+                      long long h[8]; cudaMemcpy(h, stampsDev, 64, cudaMemcpyDeviceToHost);
+                      fprintf(stderr, "[stamps] epilogue+ticket %lld  fence+loads %lld  reduce+sort %lld  publish+fence %lld  total %lld cycles\n",
+                              h[1] - h[0], h[2] - h[1], h[4] - h[3], h[5] - h[4], h[7] - h[0]);
+                  }
+#endif
+              } break;
               case 25: k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, (int) ((len + TILE - 1) / TILE), d->lo, d->lvRes, ++d->lvSeq); break;
-              case 26: k_price_lv_finish_stream<<<1, 1024, 0, d->stream>>>(d->lvc, d->streamGrid, d->lvRes, ++d->lvSeq); break;
-              case 27: { if (!d->lvResDev) cudaMalloc(&d->lvResDev, sizeof(LvResult));
-                         k_price_lv_finish_stream<<<1, 1024, 0, d->stream>>>(d->lvc, d->streamGrid, d->lvResDev, ++d->lvSeq); } break;
               case 28: { NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
                          k_update_small<<<1, 256, 0, d->stream>>>(mm, d->lastSmall, d->a0, d->a1, d->slot, d->theta, d->pi); } break;
             }
@@ -1116,26 +1161,34 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
         CK(cudaMalloc(&d->flushBuf, 8 * (size_t) d->flushLen));
     }
     if (!d->ev2) { CK(cudaEventCreate(&d->ev2)); CK(cudaEventCreate(&d->ev3)); }
-    for (int i = 0; i < reps; ++i) {
-        // pass 0 brackets the pricing kernel alone (events between the kernels serialise them fully);
-        // pass 1 is the step as the solver launches it - no events inside, the kernels chained by PDL
-        for (int pass = 0; pass < 2; ++pass) {
+    while ((int) d->benchEv.size() < 2 * reps) { cudaEvent_t e; CK(cudaEventCreate(&e)); d->benchEv.push_back(e); }
+    auto relabel = [&]() {
+        if (withFinalize == 2 && d->haveLastSmall) {
+            // the relabel of a typical pivot of this window: the last argument-only update, replayed (idempotent)
+            NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
+            k_update_small<<<1, 256, 0, d->stream>>>(mm, d->lastSmall, d->a0, d->a1, d->slot, d->theta, d->pi);
+            ++d->launches;
+        } else if (withFinalize) { k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi); ++d->launches; }
+    };
+    // The steps are queued back to back and the host synchronises once per loop: per-step host wake-ups
+    // would put their jitter into every cross-rank exchange of a sharded run (the early rank waits inside
+    // its kernel for the late one).  Loop 0 brackets the pricing kernel alone (an event between two kernels
+    // serialises them fully, and the exchange stays in its own kernel); loop 1 is the step as the solver
+    // launches it - no events inside, the kernels chained by PDL, the exchange fused where it can be.
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = 0; i < reps; ++i) {
             if (flushL2) { k_flush_l2<<<148 * 8, 256, 0, d->stream>>>(d->flushBuf, d->flushLen); ++d->launches; }
-            CK(cudaEventRecord(d->ev2, d->stream));
-            if (withFinalize == 2 && d->haveLastSmall) {
-                // the relabel of a typical pivot of this window: the last argument-only update, replayed (idempotent)
-                NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
-                k_update_small<<<1, 256, 0, d->stream>>>(mm, d->lastSmall, d->a0, d->a1, d->slot, d->theta, d->pi);
-                ++d->launches;
-            } else if (withFinalize) { k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi); ++d->launches; }
-            rc = launch_lv_pass(d, d->nranks > 1 ? d->lvResDev : d->lvRes, pass == 0 ? d->ev0 : nullptr, pass == 0 ? d->ev1 : nullptr); if (rc) return rc;
+            if (pass == 1) CK(cudaEventRecord(d->benchEv[2 * i], d->stream));
+            relabel();
+            rc = launch_lv_pass(d, d->nranks > 1 ? d->lvResDev : d->lvRes, pass == 0 ? d->benchEv[2 * i] : nullptr,
+                                pass == 0 ? d->benchEv[2 * i + 1] : nullptr, pass == 1);
+            if (rc) return rc;
             if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
-            CK(cudaEventRecord(d->ev3, d->stream));
-            CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
-            if (pass == 0) CK(cudaEventElapsedTime(&msTiles[i], d->ev0, d->ev1));
-            else CK(cudaEventElapsedTime(&msStep[i], d->ev2, d->ev3));
+            if (pass == 1) CK(cudaEventRecord(d->benchEv[2 * i + 1], d->stream));
         }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+        for (int i = 0; i < reps; ++i) CK(cudaEventElapsedTime(pass == 0 ? &msTiles[i] : &msStep[i], d->benchEv[2 * i], d->benchEv[2 * i + 1]));
     }
     return GNE_OK;
 }
@@ -1144,26 +1197,6 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
 // multi-GPU: every rank prices its shard, the fixed-size LV records are all-gathered over
 // NCCL (NVLink), and every rank runs the same merge => identical entering arc everywhere.
 // ------------------------------------------------------------------------------------------
-namespace {
-constexpr int SHARD_LIST = 48;                          // candidates carried per rank in the record
-constexpr int MAX_RANKS = 8;
-struct ShardRecord {                                    // 24 + 48*16 = 792 bytes
-    double maxViol;
-    int32_t any, overflow;
-    int64_t count;
-    int64_t pos[SHARD_LIST];
-    double viol[SHARD_LIST];
-};
-} // namespace
-// Receive buffer of one rank: slot r is written by rank r's k_lv_exchange with NVLink stores.
-// Two generations (seq parity) so that a fast rank's next record never overwrites one being read.
-constexpr int BLOB_WORDS = 16;                          // 128-byte blobs of the sharded quickSelect
-struct Mailbox {
-    ShardRecord rec[2][MAX_RANKS];
-    unsigned long long flag[2][MAX_RANKS];
-    unsigned long long blob[2][MAX_RANKS][BLOB_WORDS];
-    unsigned long long bflag[2][MAX_RANKS];
-};
 namespace {
 __device__ __forceinline__ void pack_record(const LvResult *res, ShardRecord *rec, int t)
 {
@@ -1175,51 +1208,18 @@ __device__ __forceinline__ void pack_record(const LvResult *res, ShardRecord *re
 }
 __global__ void k_pack_record(const LvResult *res, ShardRecord *rec) { pack_record(res, rec, threadIdx.x); }
 
-// The exchange step fused with the reduction's tail: one CTA packs the shard's record, stores it
-// into every rank's mailbox (peer memory over NVLink), publishes the sequence flag, waits for the
-// peers' flags and copies all records to mapped pinned host memory.  No NCCL call, no copy engine.
+// Stand-alone exchange step (after the per-tile reduction kernel; the TMA-streamed pass runs the same
+// exchange from its own last CTA): pack the shard's record, then exchange_record (gne_exchange.cuh).
 __global__ void __launch_bounds__(128)
 k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, ShardRecord *hostOut,
               unsigned long long *hostSeq)
 {
     __shared__ ShardRecord rec;
-    const int t = threadIdx.x;
-    pdl_wait();                                         // the shard's reduction has published its result block
-    pack_record(res, &rec, t);
-    __syncthreads();
-    const int b = (int) (seq & 1ull);
-    constexpr int WORDS = (int) (sizeof(ShardRecord) / 8);
-    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&rec);
-    for (int p = 0; p < nranks; ++p) {
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&peers[p]->rec[b][rank]);
-        for (int w = t; w < WORDS; w += blockDim.x) dst[w] = src[w];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (t < nranks) *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[b][rank]) = seq;
-    Mailbox *self = peers[rank];
     __shared__ int sTimeout;
-    if (t == 0) sTimeout = 0;
+    pdl_wait();                                         // the shard's reduction has published its result block
+    pack_record(res, &rec, threadIdx.x);
     __syncthreads();
-    if (t < nranks) {
-        const long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned long long *>(&self->flag[b][t]) != seq) {
-            if (clock64() - t0 > 8000000000ll) { sTimeout = 1; break; }      // ~4 s: a peer died; fail instead of hanging
-        }
-    }
-    __syncthreads();
-    __threadfence_system();
-    for (int r = 0; r < nranks; ++r) {
-        const volatile unsigned long long *in = reinterpret_cast<const volatile unsigned long long *>(&self->rec[b][r]);
-        unsigned long long *out = reinterpret_cast<unsigned long long *>(&hostOut[r]);
-        for (int w = t; w < WORDS; w += blockDim.x) out[w] = in[w];
-    }
-    __syncthreads();
-    if (sTimeout && t == 0) hostOut[0].count = -2;
-    // the host polls hostSeq instead of synchronising the stream: every writer fences its own stores first
-    __threadfence_system();
-    __syncthreads();
-    if (t == 0) *reinterpret_cast<volatile unsigned long long *>(hostSeq) = seq;
+    exchange_record(&rec, peers, rank, nranks, seq, hostOut, hostSeq, &sTimeout);
 }
 // all-gather of one 128-byte blob per rank through the peer mailboxes (same protocol as k_lv_exchange)
 __global__ void __launch_bounds__(64)
@@ -1428,6 +1428,7 @@ extern "C" int gne_comm_destroy(gne_dev *d)
 
 static int launch_shard_exchange(gne_dev *d)
 {
+    if (d->exchangeFused) return GNE_OK;                // the pricing kernel's last CTA has already done it
     if (d->p2p) {
         // fused pack + NVLink peer stores + flag wait + copy to mapped pinned host: one kernel
         unsigned long long *hostSeq = reinterpret_cast<unsigned long long *>((char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);

@@ -301,14 +301,14 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long
                 ++off;
             }
         }
-        __threadfence_system();                         // only the threads that wrote entries pay the PCIe round trip
+        if (t != 0) __threadfence_system();             // only the threads that wrote entries pay the PCIe round trip (thread 0 fences below)
     }
-    __syncthreads();
-    if (t == 0) {
+    if (t == 0) {                                       // header in parallel with the entries: one round trip in all
         res->maxViol = M; res->any = 1; res->overflow = bad ? 1 : 0; res->count = total;
         __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
     }
+    __syncthreads();
+    if (t == 0) *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -9,13 +9,16 @@
 // 20M-arc pass with 16 warps/SM against 113.5 us for the per-tile kernel with 64 warps/SM;
 // 2 stages or >150 KB of staging (which starves the L1 the gathers live in) are 50 % slower.
 //
-// Reduction: each CTA keeps a running maximum in shared memory and a short list of the violators
-// that reached (running max - band) when they were priced; the exact global maximum and the final
-// in-band list are produced by k_price_lv_finish_stream from the per-CTA records.  A violator can
-// never be skipped wrongly (the running maximum is a lower bound of the final one); a list that
-// overflows is reported and the caller falls back to the ordered compaction.
+// Reduction: each thread keeps its largest and second-largest violation in registers; once per CTA
+// the threads within the band of the CTA maximum are recorded (CtaRec + candidate arrays).  The last
+// CTA to finish (ticket counter) reduces the per-CTA records to the exact global maximum and the
+// in-band list in position order, publishes the result block, and - in a sharded run - exchanges the
+// shard's record with the peer GPUs from the same kernel (gne_exchange.cuh): one launch per pass.
+// A violator can never be skipped wrongly; a list that overflows is reported and the caller falls
+// back to the ordered compaction.
 #pragma once
 #include "gne_kernels.cuh"
+#include "gne_exchange.cuh"
 
 namespace gne {
 
@@ -53,13 +56,152 @@ __device__ __forceinline__ void st_bulk_g2s(void *dst, const void *src, uint32_t
                  :: "r"(st_smem_u32(dst)), "l"(src), "r"(bytes), "r"(st_smem_u32(bar)) : "memory");
 }
 
+struct CtaRec {            // 64-byte record of one CTA; a lone in-band candidate travels in the record itself
+    double max;            // -1 when the CTA saw no violator
+    int32_t cnt;           // threads whose largest violation lies within the band of `max` (may exceed ST_CAND: overflow)
+    int32_t pad;
+    int64_t pos0;          // cnt == 1: that thread's position, largest and second-largest violation
+    double viol0;
+    double second0;
+    double pad2[3];
+};
 struct LvCtas {
-    double *ctaMax;        // [G]  -1 when the CTA saw no violator
-    int32_t *ctaCnt;       // [G]  candidates recorded (may exceed ST_CAND: overflow)
-    int64_t *candPos;      // [G * ST_CAND] global positions, unordered
+    CtaRec *rec;           // [G]
+    int64_t *candPos;      // [G * ST_CAND] global positions, unordered           (read only when cnt > 1)
     double *candViol;      // [G * ST_CAND] the thread's largest violation
     double *candSecond;    // [G * ST_CAND] the same thread's second largest (in band => the thread may hide more)
 };
+// Where the last CTA of the pass leaves the result, and (sharded runs) the exchange that follows it.
+struct LvFused {
+    unsigned int *ticket;          // device counter, zero between passes
+    LvResult *res;                 // result block: mapped pinned host memory (single GPU) or device memory (sharded)
+    unsigned long long seq;        // published in res->seq last
+    int resOnHost;                 // system-scope fences only when the host polls res
+    int nranks, rank;              // nranks > 1 and peers != nullptr: exchange_record() after the reduction
+    Mailbox *const *peers;
+    ShardRecord *hostOut;
+    unsigned long long *hostSeq;
+    unsigned long long xseq;
+    long long *stamps;             // debug (GNE_STAMPS builds): clock64 stamps of the last CTA
+};
+
+// Reduction over the per-CTA records by ONE CTA of ST_THREADS threads (the last one of the pass): exact
+// global maximum, then every recorded candidate within the band of it, sorted by position (the CTAs
+// interleave tiles, so their lists are merged by rank), published to f.res; in a sharded run the same
+// CTA then exchanges the shard's record with the peers.  `scratch` is the (drained) stage memory.
+// Records are read once, two per thread, straight from L2: the common case (one candidate) costs one
+// dependent load level before the result is written.
+__device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const LvFused &f, unsigned char *scratch)
+{
+    constexpr int NT = ST_THREADS, NW = ST_THREADS / 32, LIST = 1024, PER = 2;
+    double *lViol = reinterpret_cast<double *>(scratch);
+    int64_t *lPos = reinterpret_cast<int64_t *>(scratch + 8 * LIST);
+    int *lRank = reinterpret_cast<int *>(scratch + 16 * LIST);
+    int *qG = reinterpret_cast<int *>(scratch + 20 * LIST);                 // [G] records with several candidates
+    ShardRecord *xrec = reinterpret_cast<ShardRecord *>(scratch + 24 * LIST);
+    __shared__ double sMaxW[NW];
+    __shared__ int sCount, sOvf, sQ, sTimeout;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) { sCount = 0; sOvf = 0; sQ = 0; if (f.ticket) *f.ticket = 0u; }      // re-arm the ticket for the next pass
+    double rmax[PER], rviol[PER], rsec[PER];
+    int64_t rpos[PER];
+    int rcnt[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int g = t + k * NT;
+        rmax[k] = -1.0; rcnt[k] = 0; rpos[k] = 0; rviol[k] = 0.0; rsec[k] = 0.0;
+        if (g < G) {
+            const CtaRec *r = in.rec + g;
+            rmax[k] = __ldcg(&r->max); rcnt[k] = __ldcg(&r->cnt); rpos[k] = __ldcg(&r->pos0);
+            rviol[k] = __ldcg(&r->viol0); rsec[k] = __ldcg(&r->second0);
+        }
+    }
+#ifdef GNE_STAMPS
+    if (t == 0 && f.stamps) f.stamps[2] = clock64();
+#endif
+    double m = fmax(rmax[0], rmax[1]);
+#ifdef GNE_STAMPS
+    if (t == 0 && f.stamps) f.stamps[3] = clock64();
+#endif
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) sMaxW[w] = m;
+    __syncthreads();
+    double M = sMaxW[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) M = fmax(M, sMaxW[i]);
+    const bool any = M > 0.0;
+    const double thr = __dsub_rn(M, LV_BAND);
+    if (any) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int g = t + k * NT;
+            if (g >= G || rmax[k] < thr) continue;
+            if (rcnt[k] == 1) {
+                if (rsec[k] >= thr) sOvf = 1;                             // that thread may hide further members
+                const int slot = atomicAdd(&sCount, 1);
+                if (slot < LIST) { lPos[slot] = rpos[k]; lViol[slot] = rviol[k]; }
+            } else if (rcnt[k] > ST_CAND) sOvf = 1;
+            else qG[atomicAdd(&sQ, 1)] = g;
+        }
+    }
+    __syncthreads();
+    const int nq = sQ;
+    for (int qi = w; qi < nq; qi += NW) {                                 // one warp per multi-candidate record
+        const int g = qG[qi];
+        const int c = __ldcg(&in.rec[g].cnt);
+        for (int i = lane; i < c; i += 32) {
+            const double vv = __ldcg(in.candViol + (int64_t) g * ST_CAND + i);
+            if (vv >= thr) {
+                if (__ldcg(in.candSecond + (int64_t) g * ST_CAND + i) >= thr) sOvf = 1;
+                const int slot = atomicAdd(&sCount, 1);
+                if (slot < LIST) { lPos[slot] = __ldcg(in.candPos + (int64_t) g * ST_CAND + i); lViol[slot] = vv; }
+            }
+        }
+    }
+    if (nq > 0) __syncthreads();
+    const int total = sCount;
+    const bool bad = any && (sOvf || total > LIST);                       // longer lists go through the ordered compaction
+    if (any && !bad) {
+        for (int i = t; i < total; i += NT) {                             // rank sort by position (positions are distinct)
+            const int64_t mine = lPos[i];
+            int rank = 0;
+            for (int j = 0; j < total; ++j) rank += (lPos[j] < mine);
+            lRank[rank] = i;
+        }
+    }
+    __syncthreads();
+#ifdef GNE_STAMPS
+    if (t == 0 && f.stamps) f.stamps[4] = clock64();
+#endif
+    LvResult *res = f.res;
+    // one warp publishes: entries, fence, header, fence, sequence number (towards the host the fences are PCIe
+    // round trips, so as few threads as possible execute them)
+    if (w == 0) {
+        // entries and header go out together; every writing lane fences its own stores (one round trip towards
+        // the host, all lanes in parallel), then the sequence number
+        const int nOut = (any && !bad) ? total : 0;
+        for (int r = lane; r < nOut; r += 32) { res->pos[r] = lPos[lRank[r]]; res->viol[r] = lViol[lRank[r]]; }
+        if (lane == 0) { res->maxViol = any ? M : -1.0; res->any = any ? 1 : 0; res->overflow = bad ? 1 : 0; res->count = nOut; }
+        if (lane == 0 || lane < nOut) { if (f.resOnHost) __threadfence_system(); else __threadfence(); }
+        __syncwarp();
+#ifdef GNE_STAMPS
+        if (lane == 0 && f.stamps) f.stamps[5] = clock64();
+#endif
+        if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&res->seq) = f.seq;
+    }
+    if (f.nranks > 1 && f.peers != nullptr) {
+        // sharded run: this CTA also carries the shard's record to the peers (and theirs to the host)
+        const int nOut = (any && !bad) ? total : 0;
+        if (t == 0) {
+            xrec->maxViol = any ? M : -1.0; xrec->any = any ? 1 : 0; xrec->count = nOut;
+            xrec->overflow = (bad || nOut > SHARD_LIST) ? 1 : 0;
+        }
+        if (t < SHARD_LIST && t < nOut) { xrec->pos[t] = lPos[lRank[t]]; xrec->viol[t] = lViol[lRank[t]]; }
+        __syncthreads();
+        exchange_record(xrec, f.peers, f.rank, f.nranks, f.xseq, f.hostOut, f.hostSeq, &sTimeout);
+    }
+}
 
 // Per tile the critical path is: wait for the stage, read the indices from shared memory, gather,
 // compare - nothing else.  Each thread keeps its largest violation (first position on ties) and its
@@ -68,7 +210,7 @@ struct LvCtas {
 // the global maximum the pass reports overflow (it may hide a third) and the caller falls back to
 // the ordered compaction - with ~75 k threads that happens only for long tie lists.
 __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
-k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t numTiles)
+k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t numTiles, LvFused f)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);                 // [ST_STAGES]
@@ -126,16 +268,19 @@ k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t 
             if (nt < numTiles) issue(s, nt);
         }
     }
+#ifdef GNE_STAMPS
+    const long long st0 = clock64();
+#endif
     // once per CTA: maximum, then the threads within the band of it
-    __shared__ int sCnt;
+    __shared__ int sCnt, sLast;
     __shared__ int64_t sPos[ST_CAND];
     __shared__ double sViol[ST_CAND], sSecond[ST_CAND];
     if (t == 0) sCnt = 0;
     Best b; b.v = v1; b.p = p1;
     b = block_best(b);                                  // two barriers inside: sCnt = 0 is visible afterwards
-    const double M = b.v;
-    if (M > 0.0) {
-        const double thr = __dsub_rn(M, LV_BAND);
+    const double Mc = b.v;
+    if (Mc > 0.0) {
+        const double thr = __dsub_rn(Mc, LV_BAND);
         if (v1 >= thr) {
             const int slot = atomicAdd(&sCnt, 1);
             if (slot < ST_CAND) { sPos[slot] = p1; sViol[slot] = v1; sSecond[slot] = v2; }
@@ -143,84 +288,48 @@ k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t 
     }
     __syncthreads();
     const int cnt = sCnt;
-    if (t == 0) { out.ctaMax[blockIdx.x] = M > 0.0 ? M : -1.0; out.ctaCnt[blockIdx.x] = cnt; }
-    for (int i = t; i < min(cnt, ST_CAND); i += ST_THREADS) {
-        out.candPos[(int64_t) blockIdx.x * ST_CAND + i] = sPos[i];
-        out.candViol[(int64_t) blockIdx.x * ST_CAND + i] = sViol[i];
-        out.candSecond[(int64_t) blockIdx.x * ST_CAND + i] = sSecond[i];
+    if (cnt > 1) {                                      // rare: several threads of this CTA within the band
+        for (int i = t; i < min(cnt, ST_CAND); i += ST_THREADS) {
+            out.candPos[(int64_t) blockIdx.x * ST_CAND + i] = sPos[i];
+            out.candViol[(int64_t) blockIdx.x * ST_CAND + i] = sViol[i];
+            out.candSecond[(int64_t) blockIdx.x * ST_CAND + i] = sSecond[i];
+        }
+        if (f.ticket != nullptr) __threadfence();
+        __syncthreads();
     }
+    // ---- sharded runs: the last CTA to get here reduces the per-CTA records and runs the exchange (one launch
+    // per pass); single GPU: the reduction is its own small kernel behind a programmatic launch boundary, which
+    // costs the same latency as the fence + ticket here and keeps this kernel pure streaming
+    if (t == 0) {
+        CtaRec *r = out.rec + blockIdx.x;
+        r->max = Mc > 0.0 ? Mc : -1.0; r->cnt = cnt; r->pad = 0;
+        r->pos0 = sPos[0]; r->viol0 = sViol[0]; r->second0 = sSecond[0];       // meaningful when cnt == 1
+        sLast = 0;
+        if (f.ticket != nullptr) {                      // (no ticket: k_price_lv_reduce follows as its own launch)
+            __threadfence();
+            sLast = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (!sLast) return;
+#ifdef GNE_STAMPS
+    if (t == 0 && f.stamps) { f.stamps[0] = st0; f.stamps[1] = clock64(); }
+#endif
+    __threadfence();
+    lv_reduce_records(out, (int) gridDim.x, f, stage0);
+#ifdef GNE_STAMPS
+    if (t == 0 && f.stamps) f.stamps[7] = clock64();
+#endif
 }
 
-// Reduction over the per-CTA records: exact global maximum, then every recorded candidate within the
-// band of it, sorted by position (the CTAs interleave tiles, so their lists are merged by rank).
-__global__ void __launch_bounds__(1024)
-k_price_lv_finish_stream(LvCtas in, int G, LvResult *res, unsigned long long seq)
+// The same reduction as its own launch (single-GPU passes): one CTA, resident early through PDL.
+__global__ void __launch_bounds__(ST_THREADS)
+k_price_lv_reduce(LvCtas in, int G, LvFused f)
 {
-    __shared__ double sMax[32];
-    __shared__ int64_t sPos[LV_LIST_CAP];
-    __shared__ double sViol[LV_LIST_CAP];
-    __shared__ int sCount, sOvf;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) { sCount = 0; sOvf = 0; }
+    __shared__ __align__(16) unsigned char scratch[25 * 1024];
     pdl_launch_dependents();
     pdl_wait();
-    double m = -1.0;
-    for (int g = t; g < G; g += 1024) m = fmax(m, in.ctaMax[g]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) sMax[w] = m;
-    __syncthreads();
-    double M = sMax[0];
-#pragma unroll
-    for (int i = 1; i < 32; ++i) M = fmax(M, sMax[i]);
-    if (M <= 0.0) {
-        if (t == 0) {
-            res->maxViol = -1.0; res->any = 0; res->overflow = 0; res->count = 0;
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
-        }
-        return;
-    }
-    const double thr = __dsub_rn(M, LV_BAND);
-    // one warp per CTA record whose maximum reaches the band
-    for (int g = w; g < G; g += 32) {
-        if (in.ctaMax[g] < thr) continue;
-        const int c = in.ctaCnt[g];
-        if (c > ST_CAND) { if (lane == 0) sOvf = 1; continue; }
-        for (int i = lane; i < c; i += 32) {
-            const double vv = in.candViol[(int64_t) g * ST_CAND + i];
-            if (vv >= thr) {
-                if (in.candSecond[(int64_t) g * ST_CAND + i] >= thr) sOvf = 1;      // that thread may hide further members
-                const int slot = atomicAdd(&sCount, 1);
-                if (slot < LV_LIST_CAP) { sPos[slot] = in.candPos[(int64_t) g * ST_CAND + i]; sViol[slot] = vv; }
-            }
-        }
-    }
-    __syncthreads();
-    const int total = sCount;
-    const bool bad = sOvf || total > 1024;              // longer lists go through the ordered compaction
-    __shared__ int sRank[1024];
-    if (!bad) {
-        for (int i = t; i < total; i += 1024) {         // rank sort by position (positions are distinct)
-            const int64_t mine = sPos[i];
-            int rank = 0;
-            for (int j = 0; j < total; ++j) rank += (sPos[j] < mine);
-            sRank[rank] = i;
-        }
-    }
-    __syncthreads();
-    // one warp publishes: entries, system-scope fence, header, fence, sequence number (the fences are PCIe
-    // round trips, so as few threads as possible execute them)
-    if (w == 0) {
-        if (!bad) for (int r = lane; r < total; r += 32) { res->pos[r] = sPos[sRank[r]]; res->viol[r] = sViol[sRank[r]]; }
-        if (!bad && total > 0) __threadfence_system();
-        __syncwarp();
-        if (lane == 0) {
-            res->maxViol = M; res->any = 1; res->overflow = bad ? 1 : 0; res->count = total;
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
-        }
-    }
+    lv_reduce_records(in, G, f, scratch);
 }
 
 } // namespace gne
