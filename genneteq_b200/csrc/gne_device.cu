@@ -265,6 +265,7 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     memset(d->lvRes, 0, sizeof(LvResult));
     { const char *tm = getenv("GNE_TIMING"); d->timing = tm && tm[0] == '1'; }
     { const char *pd = getenv("GNE_PDL"); d->pdl = !(pd && pd[0] == '0'); }
+    { const char *lk = getenv("GNE_LV_KERNEL"); if (lk) d->lvKernelMode = !strcmp(lk, "stream") ? 2 : (!strcmp(lk, "tiles") ? 1 : 0); }
     memset(d->qsState, 0, sizeof(QsState));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     *out = d;

@@ -60,3 +60,19 @@ def test_sharded_c2_prefix_window_all_gpus(tmp_path, rule):
         pytest.skip("needs >= 2 GPUs")
     nproc = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
     assert launch("nccl-c2", nproc, str(tmp_path / ("c2" + rule + ".txt")), 29640 + (1 if rule == "QS" else 0), None, rule) == "OK"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["nccl", "nccl-c2"])
+def test_sharded_streamed_pass_with_fused_exchange(tmp_path, mode):
+    """The TMA-streamed pass whose last CTA runs the reduction AND the NVLink exchange (the path configs[2] takes
+    on 2-8 GPUs), forced onto small shards with GNE_LV_KERNEL=stream: the full C1 solve (long tie lists, overflow
+    fallbacks, both phases) on 2 GPUs and the configs[1] prefix window on every GPU of the box must reproduce the
+    reference / oracle trace on every rank."""
+    import genneteq_b200 as gne
+    ngpu = gne.cuda_device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nproc = 2 if mode == "nccl" else (8 if ngpu >= 8 else (4 if ngpu >= 4 else 2))
+    port = 29660 + (1 if mode == "nccl-c2" else 0)
+    assert launch(mode, nproc, str(tmp_path / ("fused" + mode + ".txt")), port, {"GNE_LV_KERNEL": "stream"}, "LV") == "OK"
