@@ -460,6 +460,7 @@ def batch_arm(args):
     for d in devs:
         d.bench_price_lv(3, False)
     torch.cuda.synchronize()
+    launches_before = sum(d.launch_count() for d in devs)
     res = [None] * B
 
     def steps(i):
@@ -474,7 +475,7 @@ def batch_arm(args):
     dev_wall = time.perf_counter() - t0
     clocks = sampler.stop()
     tiles_ms = float(np.mean([r[1].mean() for r in res]))
-    launches += int(sum(4 * args.steps for _ in range(B)))
+    launches += sum(d.launch_count() for d in devs) - launches_before
     for s in solvers:
         s.close()
     if dist is not None:

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <vector>
+#include <sched.h>
 
 using namespace gne;
 
@@ -739,7 +740,10 @@ static int wait_host_seq(gne_dev *d, const volatile unsigned long long *seq, uns
 {
     unsigned long spins = 0;
     while (*seq != expect) {
-        if ((++spins & 0xfffff) == 0) {                  // ~ every millisecond
+        // batches run one host thread per instance, possibly more threads than cores: after the first few
+        // microseconds of polling give the core away between polls
+        if (++spins > 4096 && (spins & 63) == 0) sched_yield();
+        if ((spins & 0xfffff) == 0) {                    // now and then
             cudaError_t q = cudaStreamQuery(d->stream);
             if (q == cudaSuccess) { if (*seq == expect) break; gne_set_error("pricing pass finished without publishing its result"); return GNE_ERR_CUDA; }
             if (q != cudaErrorNotReady) { gne_set_error("pricing pass failed: %s", cudaGetErrorString(q)); return GNE_ERR_CUDA; }
@@ -954,16 +958,7 @@ static int qs_scan(gne_dev *d, int64_t cursor, int64_t N, int64_t jTotal, int64_
         d->launches += 2;
         first = 0;
         // spin on the sequence number the finish kernel publishes (see wait_lv_result)
-        const volatile unsigned long long *seq = &st->seq;
-        unsigned long spins = 0;
-        while (*seq != d->qsSeq) {
-            if ((++spins & 0xfffff) == 0) {
-                cudaError_t q = cudaStreamQuery(d->stream);
-                if (q == cudaSuccess) { if (*seq == d->qsSeq) break; gne_set_error("quickSelect pass finished without publishing its result"); return GNE_ERR_CUDA; }
-                if (q != cudaErrorNotReady) { gne_set_error("quickSelect pass failed: %s", cudaGetErrorString(q)); return GNE_ERR_CUDA; }
-            }
-        }
-        d->stageInFlight = false;
+        { int rcw = wait_host_seq(d, &st->seq, d->qsSeq); if (rcw) return rcw; }
         if (d->timing && msOut) { float ms; CK(cudaEventSynchronize(d->ev1)); CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1)); *msOut += ms; }
         d->d2hBytes += sizeof(QsState);
         if (st->done) {
@@ -1224,7 +1219,8 @@ k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, 
 }
 // all-gather of one 128-byte blob per rank through the peer mailboxes (same protocol as k_lv_exchange)
 __global__ void __launch_bounds__(64)
-k_blob_exchange(const unsigned long long *src, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, unsigned long long *hostOut)
+k_blob_exchange(const unsigned long long *src, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, unsigned long long *hostOut,
+                unsigned long long *hostSeq)
 {
     const int t = threadIdx.x, b = (int) (seq & 1ull);
     __shared__ unsigned long long mine[BLOB_WORDS];
@@ -1247,7 +1243,11 @@ k_blob_exchange(const unsigned long long *src, Mailbox *const *peers, int rank, 
     __threadfence_system();
     for (int r = 0; r < nranks; ++r)
         if (t < BLOB_WORDS) hostOut[r * BLOB_WORDS + t] = *reinterpret_cast<const volatile unsigned long long *>(&self->blob[b][r][t]);
+    __syncthreads();
     if (sTimeout && t == 0) hostOut[0] = ~0ull;
+    __threadfence_system();                             // every writer fences its own stores, then the word the host polls
+    __syncthreads();
+    if (t == 0) *reinterpret_cast<volatile unsigned long long *>(hostSeq) = seq;
 }
 } // namespace
 
@@ -1256,15 +1256,17 @@ static int exchange_blobs(gne_dev *d, const unsigned long long *mine, unsigned l
 {
     const int R = d->nranks;
     if (!d->blobHost) {
-        CK(cudaHostAlloc(&d->blobHost, 8 * BLOB_WORDS * (size_t) (R + 1), cudaHostAllocMapped));
+        CK(cudaHostAlloc(&d->blobHost, 8 * BLOB_WORDS * (size_t) (R + 2), cudaHostAllocMapped));      // mine, R gathered, the sequence word
+        memset(d->blobHost, 0, 8 * BLOB_WORDS * (size_t) (R + 2));
         CK(cudaMalloc(&d->blobDev, 8 * BLOB_WORDS * (size_t) (R + 1)));
     }
     memcpy(d->blobHost, mine, 8 * BLOB_WORDS);
     if (d->p2p) {
-        k_blob_exchange<<<1, 64, 0, d->stream>>>(d->blobHost, d->peersDev, d->rank, R, ++d->bseq, d->blobHost + BLOB_WORDS);
+        unsigned long long *hostSeq = d->blobHost + BLOB_WORDS * (size_t) (R + 1);
+        k_blob_exchange<<<1, 64, 0, d->stream>>>(d->blobHost, d->peersDev, d->rank, R, ++d->bseq, d->blobHost + BLOB_WORDS, hostSeq);
         CK(cudaGetLastError());
         ++d->launches;
-        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+        { int rcw = wait_host_seq(d, hostSeq, d->bseq); if (rcw) return rcw; }
         if (d->blobHost[BLOB_WORDS] == ~0ull) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
     } else {
         CK(cudaMemcpyAsync(d->blobDev, d->blobHost, 8 * BLOB_WORDS, cudaMemcpyHostToDevice, d->stream));
