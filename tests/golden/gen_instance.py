@@ -52,6 +52,17 @@ def generate(n, m, seed, mode):
     return arcs, sup
 
 
+def apply_tweak(arcs, sup, tweak):
+    """Edge-case derivations of a generated instance (tests/golden/e_*.npz): same arcs, altered supplies."""
+    if tweak in ("", None):
+        return arcs, sup
+    if tweak == "supplyx40":                            # demand far beyond the arc capacities: Phase I ends infeasible
+        return arcs, [40.0 * v for v in sup]
+    if tweak == "nosupply":                             # nothing to ship: both phases end without a pivot
+        return arcs, [0.0 for _ in sup]
+    raise ValueError("unknown tweak %r" % tweak)
+
+
 def write_col(path, n, arcs, sup):
     with open(path, 'w') as f:
         f.write("p efpgn %d %d 0\n" % (n, len(arcs)))

@@ -20,7 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
-from gen_instance import generate, write_col  # noqa: E402
+from gen_instance import apply_tweak, generate, write_col  # noqa: E402
 from oracle_util import REF_DRIVER, RULES, Instance, run_reference  # noqa: E402
 
 
@@ -50,12 +50,13 @@ def ref_cli(col, rule1, rule2, tmp):
                 trace_md5=hashlib.md5(txt.encode()).hexdigest())
 
 
-def make(name, n, m, seed, mode, rules, keep_state=True, save_instance=False):
+def make(name, n, m, seed, mode, rules, keep_state=True, save_instance=False, tweak=""):
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
         col = os.path.join(tmp, "inst.col")
-        arcs, sup = generate(n, m, seed, mode)
+        arcs, sup = apply_tweak(*generate(n, m, seed, mode), tweak)
         write_col(col, n, arcs, sup)
+        out["tweak"] = tweak
         out["col_md5"] = hashlib.md5(open(col, "rb").read()).hexdigest()
         out["params"] = np.array([n, m, seed])
         out["mode"] = mode
@@ -78,6 +79,7 @@ def make(name, n, m, seed, mode, rules, keep_state=True, save_instance=False):
             out[rn + "_p"] = np.array([g["p1"], g["p2"]])
             out[rn + "_objective"] = g["objective"]
             out[rn + "_md5"] = g["trace_md5"]
+            out[rn + "_feasible"] = int(z["feasible"])
             if keep_state:
                 out[rn + "_flows"] = g["flows"]
                 out[rn + "_potentials"] = g["potentials"]
@@ -94,5 +96,11 @@ if __name__ == "__main__":
         make("s_lossy_s4", 150, 1500, 4, "lossy", allr)
         make("s_pow2_s5", 100, 900, 5, "pow2", allr)
         make("s_near1_s6", 130, 1100, 6, "near1", allr)
+    if "edge" in which:
+        er = ["LV", "FV", "CL", "CL2", "QS", "RV"]
+        make("e_infeasible_s11", 80, 400, 11, "wide", er, tweak="supplyx40")
+        make("e_nosupply_s12", 40, 200, 12, "wide", er, tweak="nosupply")
+        make("e_two_nodes_s13", 2, 2, 13, "wide", er)
+        make("e_three_nodes_s14", 3, 6, 14, "pow2", er)
     if "lossy3k" in which:
         make("lossy3k_s5", 3000, 60000, 5, "lossy", ["LV"], keep_state=False)

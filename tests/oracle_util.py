@@ -177,6 +177,10 @@ class Oracle:
     def objective(self):
         return self.lib.orc_objective(self.h)
 
+    @property
+    def feasible(self):
+        return bool(self.lib.orc_feasible(self.h))
+
     def flows(self):
         a = np.zeros(self.M)
         self.lib.orc_get_flows(self.h, dp(a))
@@ -250,6 +254,7 @@ inst = Instance.load(req["instance"])
 ref = C.CDLL(REF_SO)
 ref.ref_solve.restype = C.c_long; ref.ref_trace_len.restype = C.c_long; ref.ref_objective.restype = C.c_double
 ref.ref_num_vars.restype = C.c_long
+ref.ref_feasible.restype = C.c_int
 ref.ref_init_sparse(inst.n, C.c_long(inst.m), ip(inst.tail), ip(inst.head), dp(inst.ub), dp(inst.cost), dp(inst.mult),
                     dp(inst.supply), C.c_double(req["big_m"]))
 ref.ref_set_rules(req["rule1"], req["rule2"])
@@ -267,7 +272,7 @@ x = np.zeros(M); pi = np.zeros(inst.n); st = np.zeros(M, np.int32)
 ref.ref_get_flows(dp(x)); ref.ref_get_potentials(dp(pi)); ref.ref_get_states(ip(st))
 tm = np.zeros(5); ref.ref_get_timers(dp(tm))
 np.savez(req["out"], e=te[:k], l=tl[:k], p1=p1, p2=p2, f1=f1, f2=f2, objective=ref.ref_objective(), flows=x,
-         potentials=pi, states=st, timers=tm)
+         potentials=pi, states=st, timers=tm, feasible=ref.ref_feasible())
 """
 
 

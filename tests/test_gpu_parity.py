@@ -337,6 +337,27 @@ def test_small_instances_every_rule(gne, name, rn):
     s.close()
 
 
+EDGE = ["e_infeasible_s11", "e_nosupply_s12", "e_two_nodes_s13", "e_three_nodes_s14"]
+
+
+@pytest.mark.parametrize("name", EDGE)
+@pytest.mark.parametrize("rn", ["LV", "FV", "CL", "CL2", "QS", "RV"])
+def test_edge_cases_every_rule(gne, name, rn):
+    """Infeasible demand (Phase II skipped, feasibility flag), zero supplies (all pivots degenerate, objective 0, long
+    exact-tie lists) and the smallest graphs the format allows: trace, flows, potentials, objective and the
+    feasibility verdict equal the unmodified reference's."""
+    z, inst = load_gold(name)
+    s, p1, p2 = solve_gpu(gne, inst, rn)
+    e, l = s.trace
+    assert (p1, p2) == tuple(int(v) for v in z[rn + "_p"])
+    assert np.array_equal(e, z[rn + "_e"]) and np.array_equal(l, z[rn + "_l"])
+    assert s.objective == float(z[rn + "_objective"])
+    assert s.feasible == bool(z[rn + "_feasible"])
+    assert np.array_equal(s.flows(), z[rn + "_flows"])
+    assert np.array_equal(s.potentials(), z[rn + "_potentials"])
+    s.close()
+
+
 def test_col_file_loader_and_error_codes(gne, tmp_path):
     z, inst = load_gold("s_wide_s3")
     col = str(tmp_path / "i.col")

@@ -145,7 +145,11 @@ DRAWS = dict(LV=1, LVW=1, LVA=1, LVE=1, FV=0, RV=1, RWV=1, RLV=1, RLVW=1, CL=0, 
                                         ("s_wide_s3", ["LV", "FV", "RV", "RWV", "RLV", "CL", "SAA", "QS"]),
                                         ("s_lossy_s4", ["LV", "FV", "RWV", "CL", "SAE", "QS"]),
                                         ("s_pow2_s5", ["LV", "FV", "RV", "RLV", "CL", "QS"]),
-                                        ("s_near1_s6", ["LV", "FV", "RWV", "CL", "SAA", "QS"])])
+                                        ("s_near1_s6", ["LV", "FV", "RWV", "CL", "SAA", "QS"]),
+                                        ("e_infeasible_s11", ["LV", "FV", "CL", "QS", "RV"]),
+                                        ("e_nosupply_s12", ["LV", "FV", "CL", "QS", "RV"]),
+                                        ("e_two_nodes_s13", ["LV", "QS"]),
+                                        ("e_three_nodes_s14", ["LV", "FV", "RV"])])
 def test_host_pivot_logic_replays_reference_traces(gne, name, rules, sparse):
     """Flows, ratio test, leaving arc, basis update and the potential sweep of the product's host engine,
     driven by the reference's entering arcs (no pricing, no GPU): every leaving arc, the final flows, the

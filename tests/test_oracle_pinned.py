@@ -12,7 +12,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from gen_instance import generate, write_col
+from gen_instance import apply_tweak, generate, write_col
 from oracle_util import RULES, Instance, Oracle, oracle_lib, trace_md5
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -30,7 +30,7 @@ def load(name):
     mode = str(z["mode"])
     with tempfile.TemporaryDirectory() as tmp:
         col = os.path.join(tmp, "i.col")
-        arcs, sup = generate(n, m, seed, mode)
+        arcs, sup = apply_tweak(*generate(n, m, seed, mode), str(z["tweak"]) if "tweak" in z.files else "")
         write_col(col, n, arcs, sup)
         assert hashlib.md5(open(col, "rb").read()).hexdigest() == str(z["col_md5"]), "generator drifted"
         inst = Instance.from_col(col)
@@ -48,6 +48,8 @@ def check(z, inst, rn, state=True):
     assert np.array_equal(e, z[rn + "_e"]) and np.array_equal(l, z[rn + "_l"])
     assert trace_md5(e, l, p1) == str(z[rn + "_md5"])
     assert o.objective == float(z[rn + "_objective"])
+    if rn + "_feasible" in z.files:
+        assert o.feasible == bool(z[rn + "_feasible"])
     if state:
         assert np.array_equal(o.flows(), z[rn + "_flows"])
         assert np.array_equal(o.potentials(), z[rn + "_potentials"])
@@ -79,6 +81,24 @@ SMALL_RULES = ["LV", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW"
 def test_small_all_rules(name, rn):
     z, inst = load(name)
     check(z, inst, rn)
+
+
+EDGE = ["e_infeasible_s11", "e_nosupply_s12", "e_two_nodes_s13", "e_three_nodes_s14"]
+EDGE_RULES = ["LV", "FV", "CL", "CL2", "QS", "RV"]
+
+
+@pytest.mark.parametrize("name", EDGE)
+@pytest.mark.parametrize("rn", EDGE_RULES)
+def test_edge_cases(name, rn):
+    """Infeasible demand (Phase II is skipped, genneteq.cpp:70-73), zero supplies (every pivot degenerate, objective 0),
+    and the smallest graphs the format allows."""
+    z, inst = load(name)
+    check(z, inst, rn)
+
+
+def test_edge_fixture_flags():
+    assert not bool(np.load(os.path.join(GOLD, "e_infeasible_s11.npz"))["LV_feasible"])
+    assert bool(np.load(os.path.join(GOLD, "e_nosupply_s12.npz"))["LV_feasible"])
 
 
 def test_lossy3k_lv_trace_md5():
