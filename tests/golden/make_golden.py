@@ -64,13 +64,13 @@ def make(name, n, m, seed, mode, rules, keep_state=True, save_instance=False, tw
         if save_instance:
             inst.save(os.path.join(HERE, name + "_instance.npz"))
         for rn in rules:
-            r = RULES[rn]
-            g = ref_cli(col, r, r, tmp)
+            r, r2 = (RULES[x] for x in rn.split("+")) if "+" in rn else (RULES[rn], RULES[rn])    # "A+B": Phase I rule A, Phase II rule B
+            g = ref_cli(col, r, r2, tmp)
             if g is None:
                 print("  %s %s: reference aborted" % (name, rn))
                 out[rn + "_aborted"] = 1
                 continue
-            z = run_reference(inst, r)
+            z = run_reference(inst, r, r2)
             same = np.array_equal(z["e"], g["e"]) and np.array_equal(z["l"], g["l"]) and z["objective"] == g["objective"]
             assert same, "sparse initialiser diverges from the dense loader on %s %s" % (name, rn)
             print("  %s %-4s pivots %d+%d obj %.9f trace md5 %s" % (name, rn, g["p1"], g["p2"], g["objective"], g["trace_md5"]))
@@ -96,6 +96,8 @@ if __name__ == "__main__":
         make("s_lossy_s4", 150, 1500, 4, "lossy", allr)
         make("s_pow2_s5", 100, 900, 5, "pow2", allr)
         make("s_near1_s6", 130, 1100, 6, "near1", allr)
+    if "mixed" in which:
+        make("s_mixed_s8", 140, 1300, 8, "wide", ["QS+LV", "LV+QS", "CL+LVW", "FV+CL", "CL2+QS", "RV+FV"])
     if "edge" in which:
         er = ["LV", "FV", "CL", "CL2", "QS", "RV"]
         make("e_infeasible_s11", 80, 400, 11, "wide", er, tweak="supplyx40")

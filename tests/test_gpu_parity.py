@@ -295,7 +295,8 @@ def load_gold(name):
 
 
 def solve_gpu(gne, inst, rule, max_pivots=-1):
-    s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, rule1=rule)
+    r1, r2 = rule.split("+") if "+" in rule else (rule, rule)        # "A+B": Phase I rule A, Phase II rule B
+    s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, rule1=r1, rule2=r2)
     p1, f1 = s.solve(True, max_pivots)
     p2, f2 = (0, False)
     if f1:
@@ -327,6 +328,20 @@ GPU_RULES = ["LV", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", 
 @pytest.mark.parametrize("rn", GPU_RULES)
 def test_small_instances_every_rule(gne, name, rn):
     z, inst = load_gold(name)
+    s, p1, p2 = solve_gpu(gne, inst, rn)
+    e, l = s.trace
+    assert (p1, p2) == tuple(int(v) for v in z[rn + "_p"])
+    assert np.array_equal(e, z[rn + "_e"]) and np.array_equal(l, z[rn + "_l"])
+    assert s.objective == float(z[rn + "_objective"])
+    assert np.array_equal(s.flows(), z[rn + "_flows"])
+    assert np.array_equal(s.potentials(), z[rn + "_potentials"])
+    s.close()
+
+
+@pytest.mark.parametrize("rn", ["QS+LV", "LV+QS", "CL+LVW", "FV+CL", "CL2+QS", "RV+FV"])
+def test_mixed_phase_rules(gne, rn):
+    """`-1 A -2 B` (main.cpp:87-92): a different rule per phase; trace, flows, potentials, objective equal the reference's."""
+    z, inst = load_gold("s_mixed_s8")
     s, p1, p2 = solve_gpu(gne, inst, rn)
     e, l = s.trace
     assert (p1, p2) == tuple(int(v) for v in z[rn + "_p"])

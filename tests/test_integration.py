@@ -47,6 +47,7 @@ def _run_driver(col, r1, r2, trace_path):
 @pytest.mark.parametrize("fixture,rule", [
     ("s_wide_s3", "LV"), ("s_wide_s3", "QS"), ("s_lossy_s4", "LV"), ("s_pow2_s5", "LV"),
     ("s_near1_s6", "QSW"), ("c1_wide_s7", "LV"), ("c1_wide_s7", "QS"),
+    ("e_infeasible_s11", "LV"), ("e_nosupply_s12", "QS"), ("e_two_nodes_s13", "LV"),
 ])
 def test_reference_engine_with_gpu_pricing(fixture, rule, tmp_path):
     if not os.path.exists(DRIVER):
@@ -55,7 +56,7 @@ def test_reference_engine_with_gpu_pricing(fixture, rule, tmp_path):
     if rule + "_e" not in z.files:
         pytest.skip("no golden trace for %s/%s" % (fixture, rule))
     n, m, seed = (int(v) for v in z["params"])
-    arcs, sup = gen_instance.generate(n, m, seed, str(z["mode"]))
+    arcs, sup = gen_instance.apply_tweak(*gen_instance.generate(n, m, seed, str(z["mode"])), str(z["tweak"]) if "tweak" in z.files else "")
     col = str(tmp_path / (fixture + ".col"))
     gen_instance.write_col(col, n, arcs, sup)
     assert hashlib.md5(open(col, "rb").read()).hexdigest() == str(z["col_md5"])

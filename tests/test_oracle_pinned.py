@@ -40,7 +40,8 @@ def load(name):
 def check(z, inst, rn, state=True):
     if rn + "_aborted" in z:
         pytest.skip("reference aborts on this instance/rule")
-    o = Oracle(inst, RULES[rn])
+    r1, r2 = (RULES[x] for x in rn.split("+")) if "+" in rn else (RULES[rn], RULES[rn])
+    o = Oracle(inst, r1, r2)
     p1, p2 = o.solve_both()
     assert o.status == 0
     e, l = o.trace
@@ -93,6 +94,17 @@ def test_edge_cases(name, rn):
     """Infeasible demand (Phase II is skipped, genneteq.cpp:70-73), zero supplies (every pivot degenerate, objective 0),
     and the smallest graphs the format allows."""
     z, inst = load(name)
+    check(z, inst, rn)
+
+
+MIXED = ["QS+LV", "LV+QS", "CL+LVW", "FV+CL", "CL2+QS", "RV+FV"]
+
+
+@pytest.mark.parametrize("rn", MIXED)
+def test_mixed_phase_rules(rn):
+    """Different pivot rules in Phase I and Phase II (`-1 A -2 B`, main.cpp:87-92): cursors, candidate lists and the
+    drand48 stream carry over the phase boundary exactly as in the reference."""
+    z, inst = load("s_mixed_s8")
     check(z, inst, rn)
 
 
