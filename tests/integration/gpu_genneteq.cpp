@@ -4,7 +4,12 @@
 // section A describes.  Compiled by oracle/Makefile (`ref` target) against the reference's headers
 // and objects where they lie under /root/reference; nothing of the reference is copied.
 //
-//   gne_gpu_driver -1 <rule> -2 <rule> -T trace.txt file.col        rules: 0/1 (LV/LVW), 16/17 (QS/QSW)
+//   gne_gpu_driver -1 <rule> -2 <rule> -T trace.txt [-A every] file.col        rules: 0/1 (LV/LVW), 16/17 (QS/QSW)
+//
+// -A every: same-state A/B.  At every `every`-th iteration the reference's OWN
+// selectEnteringVariable() (host, gnePivotRules.cpp:36-127) and the GPU path price the same state - the drand48
+// state (seed48), the quickSelect cursor and the optimality flag are saved and restored in between - the two
+// entering variables must be the same object, and both calls are timed.
 //
 // The pivot trace must equal the reference's own (tests/test_integration.py).
 #include "main.h"
@@ -18,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 int phaseIpivot = LVW;          // main.cpp:21-22 (main.cpp is not part of this build)
@@ -87,8 +93,39 @@ class GpuGenNetEq : public GenNetEq
         return gpuLargestViolation();
     }
 
+    static double nowS() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+    // the reference's own rule and the GPU path from the same state
+    Variable *selectBothWays()
+    {
+        unsigned short zero[3] = { 0, 0, 0 }, saved[3];
+        memcpy(saved, seed48(zero), sizeof(saved));         // read the generator state ...
+        seed48(saved);                                      // ... and put it back
+        const int cursor = nbArcPivotInd, sinceUpdate = itersSinceUpdate;
+        const double viol = lastViolation;
+        const bool opt = isOptimal;
+        const double t0 = nowS();
+        Variable *hostVar = selectEnteringVariable();       // reference, host (also writes av->redCost: harmless)
+        const double t1 = nowS();
+        const bool hostOpt = isOptimal;
+        seed48(saved); nbArcPivotInd = cursor; itersSinceUpdate = sinceUpdate; lastViolation = viol; isOptimal = opt;
+        offendingVars.clear();
+        const double t2 = nowS();
+        Variable *gpuVar = gpuSelect();
+        const double t3 = nowS();
+        ++abSamples; abHostS += t1 - t0; abGpuS += t3 - t2;
+        if (hostVar != gpuVar || hostOpt != isOptimal) {
+            ++abMismatch;
+            fprintf(stderr, "A/B mismatch at %s iteration %d: host %d gpu %d\n", presolve ? "Phase I" : "Phase II", loopIter,
+                    hostVar ? hostVar->varIndex : -1, gpuVar ? gpuVar->varIndex : -1);
+        }
+        return gpuVar;
+    }
+
   public:
-    GpuGenNetEq() : dev(NULL) {}
+    int abEvery, abSamples, abMismatch;
+    double abHostS, abGpuS;
+    GpuGenNetEq() : dev(NULL), abEvery(0), abSamples(0), abMismatch(0), abHostS(0.0), abGpuS(0.0) {}
     ~GpuGenNetEq() { if (dev) gne_dev_destroy(dev); }
 
     // body of GenNetEq::solve (genneteq.cpp:60-117); the three marked lines are the only changes
@@ -104,7 +141,7 @@ class GpuGenNetEq : public GenNetEq
             if ((loopIter % 1000) == 0) computeFlows(2);
             computePotentials();
             pushPotentials();                                               // <-- potentials to the device
-            eVar = gpuSelect();                                             // <-- identifyEnteringVariable() on the GPU
+            eVar = (abEvery > 0 && (loopIter % abEvery) == 0) ? selectBothWays() : gpuSelect();   // <-- identifyEnteringVariable() on the GPU
             if (eVar != NULL) {
                 const int64_t pe = eVar->setInd, last = (int64_t) setNBarc.size() - 1;
                 pivot();
@@ -133,10 +170,12 @@ class GpuGenNetEq : public GenNetEq
 int main(int argc, char **argv)
 {
     const char *tracePath = NULL, *inPath = NULL;
+    int abEvery = 0;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "-1") && i + 1 < argc) phaseIpivot = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-2") && i + 1 < argc) phaseIIpivot = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-T") && i + 1 < argc) tracePath = argv[++i];
+        else if (!strcmp(argv[i], "-A") && i + 1 < argc) abEvery = atoi(argv[++i]);
         else inPath = argv[i];
     }
     if (!inPath) { fprintf(stderr, "usage: %s [-1 r] [-2 r] [-T trace] file.col\n", argv[0]); return 2; }
@@ -148,11 +187,15 @@ int main(int argc, char **argv)
     g->initialize(&conf);                                   // the reference's own dense loader
     GpuGenNetEq *solver = new GpuGenNetEq();
     solver->initialize(g, conf.initType);
+    solver->abEvery = abEvery;
     delete g;
     FILE *trace = tracePath ? fopen(tracePath, "w") : NULL;
     const int p1 = solver->solveGpu(USE_PRESOLVE, trace);
     const int p2 = solver->solveGpu(USE_SOLVE, trace);
     if (trace) fclose(trace);
+    if (abEvery > 0)
+        printf("A/B samples %d mismatches %d host_ms %.4f gpu_ms %.4f\n", solver->abSamples, solver->abMismatch,
+               1e3 * solver->abHostS / (solver->abSamples ? solver->abSamples : 1), 1e3 * solver->abGpuS / (solver->abSamples ? solver->abSamples : 1));
     printf("GPU-REF pivots %d %d objective %.17g\n", p1, p2, solver->objective());
     delete solver;
     return 0;

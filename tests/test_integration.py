@@ -26,8 +26,8 @@ DRIVER = os.path.join(ROOT, "oracle", "_ref", "gne_gpu_driver")
 GOLDEN = os.path.join(HERE, "golden")
 
 
-def _run_driver(col, r1, r2, trace_path):
-    out = subprocess.run([DRIVER, "-1", str(r1), "-2", str(r2), "-T", trace_path, col],
+def _run_driver(col, r1, r2, trace_path, extra=()):
+    out = subprocess.run([DRIVER, "-1", str(r1), "-2", str(r2), "-T", trace_path, *extra, col],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     piv = []
@@ -40,6 +40,7 @@ def _run_driver(col, r1, r2, trace_path):
     for line in out.stdout.splitlines():
         if line.startswith("GPU-REF pivots"):
             obj = float(line.split()[-1])
+    _run_driver.last_stdout = out.stdout
     return np.array(piv, dtype=np.int64).reshape(-1, 3), obj
 
 
@@ -64,5 +65,31 @@ def test_reference_engine_with_gpu_pricing(fixture, rule, tmp_path):
     trace = str(tmp_path / "trace.txt")
     piv, obj = _run_driver(col, r, r, trace)
     assert np.array_equal(piv[:, 1], z[rule + "_e"]) and np.array_equal(piv[:, 2], z[rule + "_l"])
+    assert hashlib.md5(open(trace, "rb").read()).hexdigest() == str(z[rule + "_md5"])
+    assert obj == float(z[rule + "_objective"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture,rule,every", [("c1_wide_s7", "LV", 5), ("c1_wide_s7", "QS", 3), ("s_lossy_s4", "LV", 1),
+                                                ("e_nosupply_s12", "QS", 1)])
+def test_same_state_ab_against_the_reference_rule(fixture, rule, every, tmp_path):
+    """SURVEY 8(d)(ii), literally: inside the reference's own solve loop, at every `every`-th iteration the
+    reference's selectEnteringVariable() (host) and the GPU path price the SAME state (drand48 state, cursor and flags
+    saved / restored in between); the two entering variables must be the same object every time, and the extra calls
+    must not disturb the pivot sequence (golden md5)."""
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/gne_gpu_driver not built (needs /root/reference at build time)")
+    z = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    n, m, seed = (int(v) for v in z["params"])
+    arcs, sup = gen_instance.apply_tweak(*gen_instance.generate(n, m, seed, str(z["mode"])), str(z["tweak"]) if "tweak" in z.files else "")
+    col = str(tmp_path / (fixture + ".col"))
+    gen_instance.write_col(col, n, arcs, sup)
+    trace = str(tmp_path / "trace.txt")
+    r = RULES[rule]
+    piv, obj = _run_driver(col, r, r, trace, extra=("-A", str(every)))
+    line = [ln for ln in _run_driver.last_stdout.splitlines() if ln.startswith("A/B samples")][-1].split()
+    samples, mismatches = int(line[2]), int(line[4])
+    print(" ".join(line))
+    assert samples >= len(piv) // every and mismatches == 0
     assert hashlib.md5(open(trace, "rb").read()).hexdigest() == str(z[rule + "_md5"])
     assert obj == float(z[rule + "_objective"])
