@@ -69,7 +69,7 @@ int GenNetEq::initialize(Graph *g, int /*initType: ignored by the reference too*
     thetaOfSlot.clear();
     forest.init(numNodes, M, tail.data(), head.data());
     nodeMark.assign(numNodes, 0);
-    setBarc.clear(); setNBarc.clear();
+    setBarc.clear(); setNBarc.clear(); uPos.clear(); lDirty.clear(); flowStale.clear();
     setBarc.reserve(numNodes); setNBarc.reserve(m + 1);
     for (int64_t a = 0; a < M; ++a) {                   // formInitialBFS, gneInit.cpp:174-185
         if (isArtificial[a]) GNE_TRY(insertIntoB((int32_t) a));
@@ -126,6 +126,7 @@ int GenNetEq::removeFromB(int32_t v)
 int GenNetEq::insertIntoNB(int32_t v, int8_t loc)
 {
     setNBarc.push_back(v); setLoc[v] = loc; setInd[v] = (int32_t) setNBarc.size() - 1;
+    if (loc == U_var) { uPos.insert(setInd[v]); markFlowStale(forest.treeOf(tail[v])); markFlowStale(forest.treeOf(head[v])); }
     if (dev && costsOnDevice) {
         GNE_TRY(writeNbRecord((int64_t) setNBarc.size() - 1, v));
         GNE_TRY(gne_nb_set_count(dev, (int64_t) setNBarc.size()));
@@ -137,6 +138,12 @@ int GenNetEq::removeFromNB(int32_t v)
 {
     const int32_t prevInd = setInd[v];
     const int32_t mv = setNBarc.back();
+    if (setLoc[v] == U_var) { uPos.erase(prevInd); markFlowStale(forest.treeOf(tail[v])); markFlowStale(forest.treeOf(head[v])); }
+    if (mv != v && setLoc[mv] == U_var) {
+        // a U arc changes position: the order of the supply additions at its end nodes may change with it
+        uPos.erase((int32_t) setNBarc.size() - 1); uPos.insert(prevInd);
+        markFlowStale(forest.treeOf(tail[mv])); markFlowStale(forest.treeOf(head[mv]));
+    }
     setNBarc[prevInd] = mv; setInd[mv] = prevInd; setNBarc.pop_back();
     setLoc[v] = NIL; setInd[v] = -1;
     if (dev && costsOnDevice) {
@@ -231,28 +238,54 @@ void GenNetEq::computeFlowsTypeI(int32_t slot)                    // gneFlow.cpp
 
 void GenNetEq::computeFlows(int updateOption)                     // gneFlow.cpp:30-56
 {
-    flowCost = 0.0;
-    for (int i = 0; i < numNodes; ++i) { supA0[i] = supply[i]; supA1[i] = 0.0; }     // :387-395
-    const size_t N = setNBarc.size();
-    for (size_t p = 0; p < N; ++p) {                                                   // :343-353, position order
-        const int32_t a = setNBarc[p];
-        if (setLoc[a] == L_var) {
-            flow[a] = 0.0;
-        } else {
-            flow[a] = UB[a];
-            flowCost += flow[a] * cost[a];
-            supA0[tail[a]] -= flow[a];
-            supA0[head[a]] += flow[a] * mult[a];
+    static const bool selfCheck = getenv("GNE_FLOW_CHECK") != nullptr;
+    if (selfCheck && !inFlowCheck) {
+        // debugging aid: the skipping version against the reference's full walk (every tree, every U arc) - bit for bit
+        inFlowCheck = true;
+        const std::vector<double> flowBefore(flow);
+        const std::vector<int32_t> lDirtyBefore(lDirty);
+        computeFlows(updateOption);
+        const std::vector<double> flowSkipping(flow);
+        const double costSkipping = flowCost;
+        flow = flowBefore; lDirty = lDirtyBefore;
+        flowStale.assign(flowStale.size(), 1);
+        computeFlows(updateOption);
+        inFlowCheck = false;
+        if (memcmp(flowSkipping.data(), flow.data(), sizeof(double) * flow.size()) != 0 || memcmp(&costSkipping, &flowCost, sizeof(double)) != 0) {
+            fprintf(stderr, "GNE_FLOW_CHECK: computeFlows with skipped trees differs from the full walk (iteration %lld)\n", (long long) loopIter);
+            abort();
         }
+        return;
     }
-    // one pass per type I tree; the trees are independent, so any order gives the same values
-    for (int s = 0; s < forest.numSlots(); ++s) if (forest.tree(s).type == TREE_I) computeFlowsTypeI(s);
+    flowCost = 0.0;
+    const int ns = forest.numSlots();
+    if ((int) flowStale.size() < ns) flowStale.resize((size_t) ns, 1);
+    // Trees that no pivot, structure change or U-arc move touched since the last call would be recomputed from the
+    // same supplies, in the same order, to the same bits: they are skipped (their nodes' supplies stay zero).
+    for (int i = 0; i < numNodes; ++i) {                                               // :387-395
+        if (flowStale[forest.treeOf(i)]) { supA0[i] = supply[i]; supA1[i] = 0.0; }
+        else { supA0[i] = 0.0; supA1[i] = 0.0; }
+    }
+    // :343-353 walks setNBarc in position order: L arcs get flow 0, U arcs flow UB and their supply terms.  Only
+    // the recorded L arcs can hold anything but +0.0, and the U arcs are kept in position order (uPos).
+    for (size_t k = 0; k < lDirty.size(); ++k) if (setLoc[lDirty[k]] == L_var) flow[lDirty[k]] = 0.0;
+    lDirty.clear();
+    for (std::set<int32_t>::const_iterator it = uPos.begin(); it != uPos.end(); ++it) {
+        const int32_t a = setNBarc[*it];
+        flow[a] = UB[a];
+        flowCost += flow[a] * cost[a];
+        if (flowStale[forest.treeOf(tail[a])]) supA0[tail[a]] -= flow[a];
+        if (flowStale[forest.treeOf(head[a])]) supA0[head[a]] += flow[a] * mult[a];
+    }
+    // one pass per (stale) type I tree; the trees are independent, so any order gives the same values
+    for (int s = 0; s < ns; ++s) if (forest.tree(s).type == TREE_I && flowStale[s]) computeFlowsTypeI(s);
     for (size_t k = 0; k < setBarc.size(); ++k) {                                      // setFlowValues :59-149
         const int32_t a = setBarc[k];
-        if (updateOption == 0 || updateOption > 1) flow[a] = deltaFlow[a];
+        if (flowStale[forest.treeOf(tail[a])] && (updateOption == 0 || updateOption > 1)) flow[a] = deltaFlow[a];
         flowCost += flow[a] * cost[a];
         deltaFlow[a] = 0.0;
     }
+    for (int s = 0; s < ns; ++s) flowStale[s] = 0;
 }
 
 void GenNetEq::computeFlowsPivotingTI(int32_t eav, int32_t tU, int32_t tV)           // gneFlow.cpp:155-185
@@ -769,6 +802,7 @@ int GenNetEq::pivotTI(int32_t eav)                                // :63-119
     const int32_t tU = forest.treeOf(tail[eav]);
     const int32_t tV = forest.treeOf(head[eav]);
     delta = DBL_MAX;
+    markFlowStale(tU); markFlowStale(tV);                           // their flows change below
     const double f0 = wallNow();
     if (!sparseFlows) {
         computeFlowsPivotingTI(eav, tU, tV);
@@ -823,6 +857,7 @@ int GenNetEq::updateBasis()                                       // :254-309
     }
     if (setLoc[lVar] == L_var) {                                   // bound snap :294-306
         if (fabs(flow[lVar] - 0.0) > TOL) flow[lVar] = 0.0;
+        if (flow[lVar] != 0.0 || std::signbit(flow[lVar])) lDirty.push_back(lVar);      // the next computeFlows resets it to +0.0
     } else {
         if (fabs(flow[lVar] - UB[lVar]) > TOL) flow[lVar] = UB[lVar];
     }
@@ -858,6 +893,9 @@ int GenNetEq::pivot()                                             // :28-60
     }
     if (lVar == -1) return GNE_OK;
     GNE_TRY(updateBasis());
+    for (size_t c = 0; c < forest.changed.size(); ++c) markFlowStale(forest.changed[c]);     // split parts, merged trees
+    markFlowStale(forest.treeOf(tail[eVar])); markFlowStale(forest.treeOf(head[eVar]));
+    markFlowStale(forest.treeOf(tail[lVar])); markFlowStale(forest.treeOf(head[lVar]));
     checkForCycling();
     return status;
 }
@@ -960,10 +998,8 @@ void GenNetEq::checkFeasibility()                                 // :227-288
         const int32_t a = setBarc[k];
         if ((isArtificial[a] && flow[a] > TOL) || flow[a] < 0.0 - TOL || flow[a] > UB[a] + TOL) { isInfeasible = true; return; }
     }
-    for (size_t p = 0; p < setNBarc.size(); ++p) {
-        const int32_t a = setNBarc[p];
-        if (isArtificial[a] && setLoc[a] == U_var) { isInfeasible = true; return; }
-    }
+    for (std::set<int32_t>::const_iterator it = uPos.begin(); it != uPos.end(); ++it)       // nonbasic artificial at its upper bound
+        if (isArtificial[setNBarc[*it]]) { isInfeasible = true; return; }
 }
 
 int GenNetEq::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished)   // :60-117

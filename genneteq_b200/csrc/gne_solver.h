@@ -18,6 +18,7 @@
 #include <list>
 #include <queue>
 #include <string>
+#include <set>
 #include <vector>
 
 namespace gneb200 {
@@ -138,6 +139,16 @@ class GenNetEq {
     double drand48();
 
     // ---- device
+    // computeFlows (every 1000 iterations) without the O(|setNBarc|) walk: the positions of the nonbasic arcs at
+    // their upper bound, in position order (the order of the supply sums, gneFlow.cpp:343-353), and the nonbasic
+    // arcs at the lower bound whose stored flow is not exactly +0.0 (the only ones the reset changes)
+    std::set<int32_t> uPos;
+    std::vector<int32_t> lDirty;
+    // ... and without re-sweeping trees whose flows cannot have changed: a tree is stale when a pivot ran over it,
+    // its structure changed, or a nonbasic U arc at one of its nodes changed state or position since the last computeFlows
+    std::vector<uint8_t> flowStale;
+    bool inFlowCheck = false;                           // GNE_FLOW_CHECK=1: verify the skipping computeFlows against the full walk
+    void markFlowStale(int32_t slot) { if (slot < 0) return; if (slot >= (int32_t) flowStale.size()) flowStale.resize((size_t) slot + 1, 1); flowStale[slot] = 1; }
     gne_dev *dev = nullptr;
     int cudaDevice = 0;
     int commRank = 0, commRanks = 1;
