@@ -16,7 +16,7 @@ void Forest::init(int nNodes, int64_t numVars, const int32_t *tailIn, const int3
     trees.clear(); freeSlots.clear(); stale.clear(); changed.clear(); changedFlag.clear(); dirtyNodes.clear();
     trees.reserve((size_t) n + 8);
     pool.clear(); pool.reserve((size_t) 4 * n + 64);
-    incStart.assign(n, 0); incLen.assign(n, 0); incCap.assign(n, 0);
+    // (incident list position / length / capacity live in the node record: one cache line per node in a DFS)
 }
 
 void Forest::markChanged(int32_t slot)
@@ -74,23 +74,23 @@ void Forest::relabel(int32_t slot, int32_t newSlot)
 
 void Forest::incPush(int32_t v, int32_t arc, int32_t nbr, int32_t pos)
 {
-    if (incLen[v] == incCap[v]) {
-        const int32_t nc = std::max(4, 2 * incCap[v]);
+    if (node[v].incLen == node[v].incCap) {
+        const int32_t nc = std::max(4, 2 * node[v].incCap);
         const int64_t ns = (int64_t) pool.size();
         pool.resize(pool.size() + (size_t) nc);
-        for (int32_t k = 0; k < incLen[v]; ++k) pool[ns + k] = pool[incStart[v] + k];
-        incStart[v] = ns; incCap[v] = nc;
+        for (int32_t k = 0; k < node[v].incLen; ++k) pool[ns + k] = pool[node[v].incStart + k];
+        node[v].incStart = ns; node[v].incCap = nc;
     }
     Inc e; e.arc = arc; e.nbr = nbr; e.pos = pos;
-    pool[incStart[v] + incLen[v]++] = e;
+    pool[node[v].incStart + node[v].incLen++] = e;
 }
 
 int32_t Forest::posOfArc(int32_t a, int32_t u, int32_t v) const
 {
     for (int side = 0; side < 2; ++side) {
         const int32_t w = side ? v : u;
-        const int64_t base = incStart[w];
-        for (int32_t k = 0; k < incLen[w]; ++k) if (pool[base + k].arc == a && pool[base + k].pos >= 0) return pool[base + k].pos;
+        const int64_t base = node[w].incStart;
+        for (int32_t k = 0; k < node[w].incLen; ++k) if (pool[base + k].arc == a && pool[base + k].pos >= 0) return pool[base + k].pos;
     }
     return -1;
 }
@@ -100,13 +100,13 @@ void Forest::compactPool()
     std::vector<Inc> np;
     np.reserve((size_t) 4 * n + 64);
     for (int i = 0; i < n; ++i) {
-        if (incLen[i] == 0) { incStart[i] = 0; incCap[i] = 0; continue; }
+        if (node[i].incLen == 0) { node[i].incStart = 0; node[i].incCap = 0; continue; }
         int32_t c = 4;
-        while (c < incLen[i]) c *= 2;
+        while (c < node[i].incLen) c *= 2;
         const int64_t ns = (int64_t) np.size();
         np.resize(np.size() + (size_t) c);
-        for (int32_t k = 0; k < incLen[i]; ++k) np[ns + k] = pool[incStart[i] + k];
-        incStart[i] = ns; incCap[i] = c;
+        for (int32_t k = 0; k < node[i].incLen; ++k) np[ns + k] = pool[node[i].incStart + k];
+        node[i].incStart = ns; node[i].incCap = c;
     }
     pool.swap(np);
 }
@@ -130,8 +130,8 @@ void Forest::mergeInto(int32_t tX, int32_t tII, int32_t av)
     if (shift && !y.arcs.empty()) {
         for (size_t q = 0; q < y.nodes.size(); ++q) {
             const int32_t w = y.nodes[q];
-            const int64_t base = incStart[w];
-            for (int32_t k = 0; k < incLen[w]; ++k) if (pool[base + k].pos >= 0) pool[base + k].pos += shift;
+            const int64_t base = node[w].incStart;
+            for (int32_t k = 0; k < node[w].incLen; ++k) if (pool[base + k].pos >= 0) pool[base + k].pos += shift;
         }
     }
     x.nodes.insert(x.nodes.end(), y.nodes.begin(), y.nodes.end());
@@ -227,8 +227,8 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
         if (tc.nodes.empty()) tc.root = nd;
         tc.nodes.push_back(nd);
         int32_t removedInd = -1, removedNbr = -1;
-        const int64_t base = incStart[nd];
-        const int32_t len = incLen[nd];
+        const int64_t base = node[nd].incStart;
+        const int32_t len = node[nd].incLen;
         for (int32_t k = 0; k < len; ++k) {
             Inc &e = pool[base + k];
             if (e.arc == removedArc) { removedInd = k; removedNbr = e.nbr; continue; }
@@ -243,7 +243,7 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
         }
         if (removedInd >= 0) {
             pool[base + removedInd] = pool[base + len - 1];
-            --incLen[nd];
+            --node[nd].incLen;
             if (prev > -2) {
                 curStack.push_back(-1);
                 curStack.push_back(removedNbr);
@@ -305,8 +305,8 @@ void Forest::reindex(int32_t slot)
         last = cur;
         r.threadPos = (int32_t) t.threads.size();
         t.threads.push_back(cur);
-        const int64_t base = incStart[cur];
-        for (int32_t k = incLen[cur] - 1; k >= 0; --k) {
+        const int64_t base = node[cur].incStart;
+        for (int32_t k = node[cur].incLen - 1; k >= 0; --k) {
             const Inc e = pool[base + k];
             if (e.nbr == predNode) continue;
             nodeStack.push_back(e.nbr);
@@ -343,8 +343,8 @@ void Forest::rethreadSubtree(int32_t slot, const Attach &at)
         r.predArc = pa;
         r.pred = predNode;
         ++visited;
-        const int64_t base = incStart[cur];
-        for (int32_t k = incLen[cur] - 1; k >= 0; --k) {
+        const int64_t base = node[cur].incStart;
+        for (int32_t k = node[cur].incLen - 1; k >= 0; --k) {
             const Inc e = pool[base + k];
             if (e.nbr == predNode) continue;
             nodeStack.push_back(e.nbr);
@@ -375,8 +375,8 @@ void Forest::ensureThreads(int32_t slot)
         last = cur;
         r.threadPos = (int32_t) t.threads.size();
         t.threads.push_back(cur);
-        const int64_t base = incStart[cur];
-        for (int32_t k = incLen[cur] - 1; k >= 0; --k) if (pool[base + k].nbr != r.pred) nodeStack.push_back(pool[base + k].nbr);
+        const int64_t base = node[cur].incStart;
+        for (int32_t k = node[cur].incLen - 1; k >= 0; --k) if (pool[base + k].nbr != r.pred) nodeStack.push_back(pool[base + k].nbr);
     }
     node[last].thread = t.root;
     t.threadsValid = true;
@@ -384,8 +384,8 @@ void Forest::ensureThreads(int32_t slot)
 
 int32_t Forest::incidentIndex(int32_t v, int32_t a) const
 {
-    const int64_t base = incStart[v];
-    for (int32_t k = 0; k < incLen[v]; ++k) if (pool[base + k].arc == a) return k;
+    const int64_t base = node[v].incStart;
+    for (int32_t k = 0; k < node[v].incLen; ++k) if (pool[base + k].arc == a) return k;
     return -1;
 }
 

@@ -43,10 +43,12 @@ struct Tree {
 // from / appended at; -1 in the other one) its index in arcs(tree)
 struct Inc { int32_t arc, nbr, pos; };
 
-struct NodeRec {                                        // Node's tree fields (variables.h:63-76) + bookkeeping
+struct alignas(64) NodeRec {                            // Node's tree fields (variables.h:63-76) + bookkeeping: one cache line
     int32_t slot = -1;                                  // memberOfTreeID (stable slot)
     int32_t pred = -1, predArc = -1, depth = -1, thread = -1;
     int32_t threadPos = -1;
+    int64_t incStart = 0;                               // this node's incident entries: pool[incStart .. incStart + incLen)
+    int32_t incLen = 0, incCap = 0;
     uint8_t flag = 1;                                   // bit0: slot changed since last re-thread, bit1: dirty in this pass
 };
 
@@ -98,8 +100,6 @@ class Forest {
 
     // incident lists (Node::incidentArcs): push_back / swap-with-last removal, pooled
     std::vector<Inc> pool;
-    std::vector<int64_t> incStart;
-    std::vector<int32_t> incLen, incCap;
     void incPush(int32_t v, int32_t arc, int32_t nbr, int32_t pos);
     void compactPool();
 
