@@ -228,3 +228,23 @@ print("FLOW-CHECK-OK")
     env["GNE_FLOW_CHECK"] = "1"
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "FLOW-CHECK-OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("text,code", [
+    ("p efpgn x 2 0\n", 2),                                                     # improperly formatted problem line
+    ("a 1 2 0.0 5.0 1.0 1.0 0\n", 2),                                           # arc before the problem line
+    ("p efpgn 2 1 0\na 1 3 0.0 5.0 1.0 1.0 0\nn 1 1\nn 2 -1\n", 2),             # arc names a node out of range
+    ("p efpgn 2 2 0\na 1 2 0.0 5.0 1.0 1.0 0\nn 1 1\nn 2 -1\n", 2),             # fewer arcs than announced
+    ("p efpgn 2 1 0\na 1 2 0.0 5.0 1.0\nn 1 1\nn 2 -1\n", 2),                   # short arc line
+    ("p efpgn 2 1 0\na 1 2 0.0 5.0 1.0 1.0 0\nn 7 1\n", 2),                     # node line out of range
+    ("p efpgn 2 1 1\na 1 2 0.0 5.0 1.0 1.0 1\nn 1 1\nn 2 -1\n", 6),             # equal-flow sets: GNE_ERR_UNSUPPORTED
+])
+def test_col_parser_rejects_malformed_files(gne, tmp_path, text, code):
+    """Where the reference prints and exits (graph.cpp:358-447) the loader returns a status code and a message."""
+    p = str(tmp_path / "bad.col")
+    open(p, "w").write(text)
+    with pytest.raises(gne.GneError) as ei:
+        gne.read_instance(p)
+    assert ei.value.code == code, (ei.value.code, str(ei.value))
+    with pytest.raises(gne.GneError):
+        gne.read_instance(str(tmp_path / "missing.col"))
