@@ -18,6 +18,8 @@ RULES = dict(LV=0, LVW=1, LVA=2, LVE=3, FV=4, SD=5, RV=6, RWV=7, RLV=8, RLVW=9, 
 AT_LOWER, AT_UPPER = 1, 2
 TOL = 1.0e-13
 
+if os.environ.get("GNE_TUNING_LIB") == "1":              # tools/variants.py: the library built with `make tuning`
+    LIB_PATH = os.path.join(_HERE, "lib", "libgenneteq_b200_tuning.so")
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "genneteq_b200: %s is missing - build it with `make -C genneteq_b200/csrc` "
@@ -67,8 +69,6 @@ SIGNATURES = {
     "gne_dev_last_lv_kernel": (C.c_int, [_vp]),
     "gne_dev_launch_count": (C.c_int64, [_vp]),
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
-    "gne_bench_variants": (C.c_int, [_vp, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int)]),
-    "gne_bench_variant_name": (C.c_char_p, [C.c_int]),
     "gne_comm_unique_id": (C.c_int, [_u8p]),
     "gne_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
     "gne_comm_destroy": (C.c_int, [_vp]),
@@ -100,6 +100,7 @@ SIGNATURES = {
                                     _i32p, _i32p, _i32p, _i32p, _i32p]),
     "gne_host_replay": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_int, C.c_int,
                                   C.c_int64, C.c_int64, _i32p, _i32p, _i64p, _f64p, _f64p, _f64p]),
+    "gne_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, _i64p, _i64p]),
     "gne_merge_lv_shards": (C.c_int, [C.c_int, _f64p, C.POINTER(C.c_int), _i64p, _i64p, _f64p, C.c_int64,
                                       _f64p, _i64p, _i64p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gne_write_col": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
@@ -332,6 +333,13 @@ class Device:
 
 
     def bench_variants(self, reps=10):
+        """Tuning builds only (GNE_TUNING_LIB=1 + `make -C genneteq_b200/csrc tuning`)."""
+        if not hasattr(lib, "gne_bench_variants"):
+            raise RuntimeError("gne_bench_variants is only in the tuning build (make tuning; GNE_TUNING_LIB=1)")
+        lib.gne_bench_variants.restype = C.c_int
+        lib.gne_bench_variants.argtypes = [_vp, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int)]
+        lib.gne_bench_variant_name.restype = C.c_char_p
+        lib.gne_bench_variant_name.argtypes = [C.c_int]
         ms = np.zeros(64, np.float32); nv = C.c_int(0)
         _ck(lib.gne_bench_variants(self.h, reps, _p(ms, _f32p), 32, C.byref(nv)), "gne_bench_variants")
         return [(lib.gne_bench_variant_name(i).decode(), float(ms[2 * i]), float(ms[2 * i + 1])) for i in range(nv.value)]
@@ -485,6 +493,13 @@ def host_replay(n, tail, head, ub, cost, mult, supply, big_m, draws, p1, e, l, s
                             _p(supply, _f64p), big_m, draws, 1 if sparse_flows else 0, p1, len(e), _p(e, _i32p), _p(l, _i32p),
                             C.byref(mm), _p(flows, _f64p), _p(pots, _f64p), C.byref(obj)), "gne_host_replay")
     return mm.value, flows, pots, obj.value
+
+
+def shard_range(m, rank, nranks):
+    """[lo, hi) of the nonbasic list that `rank` prices (gne_shard_range)."""
+    lo = C.c_int64(0); hi = C.c_int64(0)
+    _ck(lib.gne_shard_range(m, rank, nranks, C.byref(lo), C.byref(hi)), "gne_shard_range")
+    return lo.value, hi.value
 
 
 def merge_lv_shards(maxima, anys, counts, list_pos, list_viol, stride, cap=1 << 16):

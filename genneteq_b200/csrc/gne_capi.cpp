@@ -13,6 +13,17 @@
 
 using namespace gneb200;
 
+// No exception may cross the C ABI (std::length_error / bad_alloc from absurd sizes would call std::terminate in a
+// C caller): every entry point that allocates runs inside guarded().
+template <typename F>
+static int guarded(const char *where, F f)
+{
+    try { return f(); }
+    catch (const std::bad_alloc &) { gne_set_error("%s: out of memory (sizes too large?)", where); return GNE_ERR_ARG; }
+    catch (const std::exception &e) { gne_set_error("%s: %s", where, e.what()); return GNE_ERR_ARG; }
+    catch (...) { gne_set_error("%s: unknown exception", where); return GNE_ERR_ARG; }
+}
+
 // ------------------------------------------------------------------------------------------
 // Graph: graph.cpp:31-53, 248-296, 358-447 read sparsely
 // ------------------------------------------------------------------------------------------
@@ -60,6 +71,7 @@ int Graph::initialize(Config *conf)
             char tmp[64];
             if (sscanf(line, "p %63s %d %d %d", tmp, &n, &numArcs, &numEq) != 4) { gne_set_error("Improperly formatted problem line"); rc = GNE_ERR_ARG; break; }
             if (numEq != 0) { gne_set_error("equal-flow sets are out of scope"); rc = GNE_ERR_UNSUPPORTED; break; }
+            if (n <= 0 || numArcs < 0 || n > (1 << 30)) { gne_set_error("problem line: bad sizes (n = %d, arcs = %d)", n, numArcs); rc = GNE_ERR_ARG; break; }
             sup.assign(n, 0.0);
             haveP = true;
         } else if (line[0] == 'a' || line[0] == 'e') {  // processArcLine, graph.cpp:382-419 ('e' lines fail its sscanf)
@@ -143,8 +155,14 @@ extern "C" int gne_read_bin_header(const char *path, int *n, int64_t *m)
     char magic[8];
     int64_t hdr[2];
     const bool ok = fread(magic, 1, 8, f) == 8 && !memcmp(magic, GNE_BIN_MAGIC, 8) && fread(hdr, 8, 2, f) == 2;
+    int64_t fileBytes = -1;
+    if (fseek(f, 0, SEEK_END) == 0) fileBytes = (int64_t) ftell(f);
     fclose(f);
     if (!ok) { gne_set_error("%s is not a genneteq_b200 binary instance", path); return GNE_ERR_ARG; }
+    if (hdr[0] <= 0 || hdr[0] > (1 << 30) || hdr[1] < 0 || fileBytes != 24 + 32 * hdr[1] + 8 * hdr[0]) {
+        gne_set_error("%s: header sizes (n = %lld, m = %lld) do not match the file length", path, (long long) hdr[0], (long long) hdr[1]);
+        return GNE_ERR_ARG;
+    }
     *n = (int) hdr[0]; *m = hdr[1];
     return GNE_OK;
 }
@@ -170,6 +188,7 @@ extern "C" int gne_read_bin(const char *path, int n, int64_t m, int32_t *tail, i
 extern "C" int gne_read_col(const char *path, int *n, int64_t *m, int32_t *tail, int32_t *head, double *ub, double *cost,
                             double *mult, double *supply, double *bigM)
 {
+    return guarded("gne_read_col", [&]() -> int {
     Config conf;
     conf.inFile = path;
     Graph g;
@@ -184,6 +203,7 @@ extern "C" int gne_read_col(const char *path, int *n, int64_t *m, int32_t *tail,
     *n = g.getNumNodes(); *m = cnt;
     if (bigM) *bigM = g.getBigM();
     return GNE_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -196,6 +216,7 @@ struct gne_solver {
 extern "C" int gne_solver_create(gne_solver **out, int cudaDevice, int n, int64_t m, const int32_t *tail, const int32_t *head,
                                  const double *ub, const double *cost, const double *mult, const double *supply, double bigM)
 {
+    return guarded("gne_solver_create", [&]() -> int {
     if (!out) return GNE_ERR_ARG;
     if (gne_cuda_device_count() <= 0) { gne_set_error("no CUDA device: genneteq_b200 has no CPU fallback"); return GNE_ERR_CUDA; }
     Graph g;
@@ -206,10 +227,12 @@ extern "C" int gne_solver_create(gne_solver **out, int cudaDevice, int n, int64_
     if (rc) { delete s; return rc; }
     *out = s;
     return GNE_OK;
+    });
 }
 
 extern "C" int gne_solver_create_from_col(gne_solver **out, int cudaDevice, const char *path)
 {
+    return guarded("gne_solver_create_from_col", [&]() -> int {
     if (!out || !path) return GNE_ERR_ARG;
     if (gne_cuda_device_count() <= 0) { gne_set_error("no CUDA device: genneteq_b200 has no CPU fallback"); return GNE_ERR_CUDA; }
     Config conf;
@@ -222,28 +245,42 @@ extern "C" int gne_solver_create_from_col(gne_solver **out, int cudaDevice, cons
     if (rc) { delete s; return rc; }
     *out = s;
     return GNE_OK;
+    });
+}
+
+extern "C" int gne_shard_range(int64_t m, int rank, int nranks, int64_t *lo, int64_t *hi)
+{
+    if (m < 0 || nranks < 1 || rank < 0 || rank >= nranks || !lo || !hi) { gne_set_error("gne_shard_range: bad argument"); return GNE_ERR_ARG; }
+    GenNetEq::shardRange(m, rank, nranks, lo, hi);
+    return GNE_OK;
 }
 
 extern "C" int gne_solver_destroy(gne_solver *s) { delete s; return GNE_OK; }
 extern "C" int gne_solver_set_rules(gne_solver *s, int p1, int p2) { s->solver.phaseIpivot = p1; s->solver.phaseIIpivot = p2; return GNE_OK; }
-extern "C" int gne_solver_set_comm(gne_solver *s, const uint8_t id[128], int rank, int nranks) { return s->solver.setComm(id, rank, nranks); }
+extern "C" int gne_solver_set_comm(gne_solver *s, const uint8_t id[128], int rank, int nranks) {
+    return guarded("gne_solver_set_comm", [&]() -> int { return s->solver.setComm(id, rank, nranks);     });
+}
 extern "C" int gne_solver_set_trace(gne_solver *s, int32_t *e, int32_t *l, int64_t cap) { s->solver.setTrace(e, l, cap); return GNE_OK; }
 extern "C" int64_t gne_solver_trace_len(const gne_solver *s) { return s->solver.getTraceLen(); }
 extern "C" int gne_solver_solve(gne_solver *s, int presolve, int64_t maxPivots, int64_t *iters, int *finished)
 {
+    return guarded("gne_solver_solve", [&]() -> int {
     int64_t it = 0;
     int fin = 0;
     int rc = s->solver.solve(presolve != 0, maxPivots, &it, &fin);
     if (iters) *iters = it;
     if (finished) *finished = fin;
     return rc;
+    });
 }
 extern "C" int gne_solver_num_nodes(const gne_solver *s) { return s->solver.getNumNodes(); }
 extern "C" int64_t gne_solver_num_vars(const gne_solver *s) { return s->solver.getNumVars(); }
 extern "C" double gne_solver_objective(const gne_solver *s) { return s->solver.getFlowCost(); }
 extern "C" int gne_solver_feasible(const gne_solver *s) { return s->solver.getIsInfeasible() ? 0 : 1; }
 extern "C" int gne_solver_get_flows(gne_solver *s, double *out) { s->solver.getFlows(out); return GNE_OK; }
-extern "C" int gne_solver_get_potentials(gne_solver *s, double *out) { return s->solver.getPotentials(out); }
+extern "C" int gne_solver_get_potentials(gne_solver *s, double *out) {
+    return guarded("gne_solver_get_potentials", [&]() -> int { return s->solver.getPotentials(out);     });
+}
 extern "C" int gne_solver_compute_potentials(gne_solver *s)
 {
     int rc = s->solver.refreshPotentials();
@@ -273,6 +310,7 @@ extern "C" int gne_forest_replay(int n, int64_t m, const int32_t *tailIn, const 
                                  int64_t pivots, const int32_t *e, const int32_t *l,
                                  int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread)
 {
+    return guarded("gne_forest_replay", [&]() -> int {
     (void) supply;
     const int64_t M = m + n;
     std::vector<int32_t> tail((size_t) M), head((size_t) M);
@@ -295,6 +333,7 @@ extern "C" int gne_forest_replay(int n, int64_t m, const int32_t *tailIn, const 
     for (int sl = 0; sl < f.numSlots(); ++sl) f.ensureThreads(sl);
     for (int i = 0; i < n; ++i) { tree[i] = f.node[i].slot; pred[i] = f.node[i].pred; predArc[i] = f.node[i].predArc; depth[i] = f.node[i].depth; thread[i] = f.node[i].thread; }
     return GNE_OK;
+    });
 }
 
 // host-only replay of a whole recorded solve: flows, ratio test, leaving arc, basis update and
@@ -304,6 +343,7 @@ extern "C" int gne_host_replay(int n, int64_t m, const int32_t *tail, const int3
                                int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
                                int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective)
 {
+    return guarded("gne_host_replay", [&]() -> int {
     Graph g;
     int rc = g.initializeFromArrays(n, m, tail, head, ub, cost, mult, supply, bigM);
     if (rc) return rc;
@@ -317,67 +357,19 @@ extern "C" int gne_host_replay(int n, int64_t m, const int32_t *tail, const int3
     if (potentialsOut) s.getHostPotentials(potentialsOut);
     if (objective) *objective = s.getFlowCost();
     return GNE_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------
-// synthetic instances for the large benchmark configurations: the
-// Appendix-A family (ring + random distinct arcs, same value ranges, 6-decimal values) from a
-// counter-based generator, so that 10^8 arcs take seconds and every rank builds the same arrays.
+// synthetic instances (gne_generate.cpp; the same file also builds the reference arm's stand-alone generator library)
 // ------------------------------------------------------------------------------------------
-static inline uint64_t mix64(uint64_t x)
-{
-    x += 0x9E3779B97F4A7C15ULL;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-    return x ^ (x >> 31);
-}
-static inline double unit(uint64_t h) { return (double) (h >> 11) * (1.0 / 9007199254740992.0); }
-static inline double r6(double x) { return floor(x * 1.0e6 + 0.5) / 1.0e6; }
+extern "C" int gne_generate_instance_impl(int n, int64_t m, uint64_t seed, int mode,
+                                          int32_t *tail, int32_t *head, double *ub, double *cost, double *mult, double *supply);
 
 extern "C" int gne_generate_instance(int n, int64_t m, uint64_t seed, int mode,
                                      int32_t *tail, int32_t *head, double *ub, double *cost, double *mult, double *supply)
 {
-    if (n < 3 || m < n || m > (int64_t) n * (n - 1)) { gne_set_error("gne_generate_instance: need n >= 3 and n <= m <= n(n-1)"); return GNE_ERR_ARG; }
-    const int64_t base = m / n, rem = m % n;
-    int64_t a = 0;
-    std::vector<int32_t> hs;
-    for (int i = 0; i < n; ++i) {
-        const int64_t d = base + (i < rem ? 1 : 0);
-        hs.clear();
-        hs.push_back((i + 1) % n);                      // ring arc keeps the graph connected
-        uint64_t ctr = 0;
-        while ((int64_t) hs.size() < d) {
-            const int64_t want = d - (int64_t) hs.size();
-            for (int64_t k = 0; k < want; ++k) {
-                const uint64_t h = mix64(mix64(seed ^ ((uint64_t) i << 20)) + (ctr++));
-                const int32_t j = (int32_t) (h % (uint64_t) n);
-                if (j != i) hs.push_back(j);
-            }
-            std::sort(hs.begin(), hs.end());
-            hs.erase(std::unique(hs.begin(), hs.end()), hs.end());
-        }
-        std::sort(hs.begin(), hs.end());
-        for (size_t k = 0; k < hs.size(); ++k, ++a) {
-            const uint64_t key = mix64(seed * 0x100000001B3ULL + (uint64_t) a);
-            tail[a] = i; head[a] = hs[k];
-            ub[a] = r6(10.0 + 90.0 * unit(mix64(key + 1)));
-            cost[a] = r6(1.0 + 99.0 * unit(mix64(key + 2)));
-            const double u = unit(mix64(key + 3));
-            double g;
-            if (mode == 1) g = 0.70 + 0.29 * u;
-            else if (mode == 2) g = 0.9 + 0.2 * u;
-            else if (mode == 3) { static const double pw[5] = { 0.5, 0.75, 1.25, 1.5, 2.0 }; g = pw[(int) (u * 5.0) % 5]; }
-            else g = 0.5 + u;
-            mult[a] = r6(g);
-        }
-    }
-    for (int i = 0; i < n; ++i) {
-        const uint64_t h = mix64(seed + 0xABCDEFULL * (uint64_t) (i + 1));
-        const int kind = (int) (h % 20);
-        const double amount = (double) (1 + (int) ((h >> 8) % 20));
-        if (kind == 0) supply[i] = amount * (mode == 1 ? 3.0 : 1.0);
-        else if (kind == 1) supply[i] = -amount;
-        else supply[i] = 0.0;
-    }
-    return GNE_OK;
+    const int rc = gne_generate_instance_impl(n, m, seed, mode, tail, head, ub, cost, mult, supply);
+    if (rc) gne_set_error("gne_generate_instance: need n >= 3 and n <= m <= n(n-1)");
+    return rc;
 }

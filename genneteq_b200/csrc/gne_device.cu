@@ -3,7 +3,9 @@
 #include "gne_kernels.cuh"
 #include "gne_exchange.cuh"
 #include "gne_stream.cuh"
-#include "gne_variants.cuh"
+#ifdef GNE_TUNING
+#include "gne_variants.cuh"            // tuning harness: only in `make tuning` builds (libgenneteq_b200_tuning.so)
+#endif
 #include "gne_internal.h"
 #include "../../include/genneteq_b200.h"
 
@@ -212,6 +214,8 @@ static int ensure_out(gne_dev *d, int64_t cap)
     return GNE_OK;
 }
 
+static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi);
+
 extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi)
 {
     if (!out || n <= 0 || nbCapacity <= 0 || shardLo < 0 || shardHi < shardLo) { gne_set_error("gne_dev_create: bad argument"); return GNE_ERR_ARG; }
@@ -221,8 +225,18 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     if (cudaDevice < 0 || cudaDevice >= cnt) { gne_set_error("cuda device %d out of range (%d present)", cudaDevice, cnt); return GNE_ERR_ARG; }
     CK(cudaSetDevice(cudaDevice));
     gne_dev *d = new gne_dev();
+    const int rc = dev_create_fill(d, cudaDevice, n, nbCapacity, shardLo, shardHi);
+    if (rc != GNE_OK) { gne_dev_destroy(d); return rc; }      // every member is null-initialised: destroy frees what was allocated
+    *out = d;
+    return GNE_OK;
+}
+
+static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi)
+{
     d->device = cudaDevice; d->n = n; d->cap = nbCapacity;
-    d->lo = shardLo; d->hi = std::min(shardHi, nbCapacity); d->N = 0;
+    // a shard that starts at or beyond the capacity is EMPTY (more ranks than tiles): lo == hi, nothing is ever priced
+    if (shardLo >= nbCapacity) shardHi = shardLo;
+    d->lo = shardLo; d->hi = std::max(shardLo, std::min(shardHi, nbCapacity)); d->N = 0;
     d->localCap = ((d->hi - d->lo + TILE - 1) / TILE) * TILE;
     if (d->localCap == 0) d->localCap = TILE;
     d->G = (int) (d->localCap / TILE);
@@ -269,7 +283,6 @@ extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCa
     { const char *lk = getenv("GNE_LV_KERNEL"); if (lk) d->lvKernelMode = !strcmp(lk, "stream") ? 2 : (!strcmp(lk, "tiles") ? 1 : 0); }
     memset(d->qsState, 0, sizeof(QsState));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
-    *out = d;
     return GNE_OK;
 }
 
@@ -320,8 +333,11 @@ extern "C" int gne_nb_reset(gne_dev *d, int64_t N, const int32_t *tail, const in
 {
     if (N < 0 || N > d->cap) { gne_set_error("gne_nb_reset: N out of range"); return GNE_ERR_ARG; }
     CK(cudaSetDevice(d->device));
-    d->N = N;
     const int64_t a = d->lo, b = std::min(N, d->hi);
+    // the pricing kernels gather pi[tail], pi[head] unchecked: reject a bad record here (as gne_nb_write does)
+    for (int64_t p = a; p < b; ++p)
+        if (tail[p] < 0 || tail[p] >= d->n || head[p] < 0 || head[p] >= d->n) { gne_set_error("gne_nb_reset: position %lld names a node out of range", (long long) p); return GNE_ERR_ARG; }
+    d->N = N;
     if (b > a) {
         const size_t c = (size_t) (b - a);
         CK(cudaMemcpyAsync(d->tail, tail + a, 4 * c, cudaMemcpyHostToDevice, d->stream));
@@ -1048,6 +1064,7 @@ extern "C" int gne_price_scan_list(gne_dev *d, int64_t cursor, int64_t want, int
 // ------------------------------------------------------------------------------------------
 static int launch_shard_exchange(gne_dev *d);
 
+#ifdef GNE_TUNING
 // tuning harness: the LV tile kernel and its experimental variants, each timed `reps` times
 static const char *g_variantNames[] = {
     "production k_price_lv_tiles", "tiles<2 chunks, minb 5>", "tiles<2,6>", "tiles<2,8>", "tiles<1,8>", "tiles<4,4>",
@@ -1147,6 +1164,8 @@ extern "C" const char *gne_bench_variant_name(int i)
     const int NV = (int) (sizeof(g_variantNames) / sizeof(g_variantNames[0]));
     return (i >= 0 && i < NV) ? g_variantNames[i] : "";
 }
+
+#endif // GNE_TUNING
 
 extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles)
 {
@@ -1369,13 +1388,13 @@ extern "C" int gne_comm_unique_id(uint8_t id[128])
 
 extern "C" int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nranks)
 {
+    if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) { gne_set_error("gne_comm_init: rank %d of %d (at most %d ranks)", rank, nranks, MAX_RANKS); return GNE_ERR_ARG; }
     if (!nccl_load()) return GNE_ERR_COMM;
     CK(cudaSetDevice(d->device));
     NcclId uid;
     memcpy(uid.b, id, 128);
     int r = g_nccl.CommInitRank(&d->comm, nranks, uid, rank);
     if (r != 0) { gne_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
-    if (nranks > MAX_RANKS) { gne_set_error("gne_comm_init: at most %d ranks", MAX_RANKS); return GNE_ERR_ARG; }
     d->rank = rank; d->nranks = nranks;
     CK(cudaMalloc(&d->gatherSend, sizeof(ShardRecord)));
     CK(cudaMalloc(&d->gatherRecv, sizeof(ShardRecord) * (size_t) nranks));
@@ -1553,12 +1572,16 @@ extern "C" int gne_merge_lv_shards(int nranks, const double *maxima, const int *
     const double floorV = M - LV_BAND;
     std::vector<int64_t> p;
     std::vector<double> v;
+    int64_t lastPos = -1;
     for (int r = 0; r < nranks; ++r) {                  // shards are contiguous position ranges in rank order
         if (!any[r] || maxima[r] < floorV) continue;
         if (counts[r] < 0) { *needFallback = 1; return GNE_OK; }
         for (int64_t i = 0; i < counts[r]; ++i) {
             const double x = listViol[(size_t) r * stride + i];
-            if (x >= floorV) { p.push_back(listPos[(size_t) r * stride + i]); v.push_back(x); }
+            const int64_t q = listPos[(size_t) r * stride + i];
+            if (q <= lastPos) { gne_set_error("gne_merge_lv_shards: positions not increasing (rank %d, entry %lld): overlapping shards?", r, (long long) i); return GNE_ERR_ARG; }
+            lastPos = q;
+            if (x >= floorV) { p.push_back(q); v.push_back(x); }
         }
     }
     std::vector<int64_t> list;

@@ -80,16 +80,27 @@ int GenNetEq::initialize(Graph *g, int /*initType: ignored by the reference too*
     return GNE_OK;
 }
 
-int GenNetEq::setComm(const uint8_t id[128], int rank, int nranks)
+void GenNetEq::shardRange(int64_t m, int rank, int nranks, int64_t *lo, int64_t *hi)
 {
-    if (dev) { gne_set_error("setComm must precede the first solve"); return GNE_ERR_ARG; }
-    commRank = rank; commRanks = nranks;
-    // contiguous position ranges, boundaries on tile multiples (2048)
     const int64_t cap = m + 16;
     int64_t per = (m + nranks - 1) / nranks;
     per = ((per + 2047) / 2048) * 2048;
-    const int64_t lo = std::min<int64_t>((int64_t) rank * per, (cap / 2048) * 2048);
-    const int64_t hi = (rank == nranks - 1) ? cap : std::min<int64_t>(lo + per, cap);
+    if (per == 0) per = 2048;
+    *lo = (int64_t) rank * per;
+    if (*lo >= cap) { *lo = *hi = ((cap + 2047) / 2048) * 2048; return; }      // empty shard, tile-aligned, beyond the list
+    *hi = (rank == nranks - 1) ? cap : std::min<int64_t>(*lo + per, cap);
+}
+
+int GenNetEq::setComm(const uint8_t id[128], int rank, int nranks)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) { gne_set_error("setComm: bad rank %d of %d", rank, nranks); return GNE_ERR_ARG; }
+    if (dev) { gne_set_error("setComm must precede the first solve"); return GNE_ERR_ARG; }
+    commRank = rank; commRanks = nranks;
+    // contiguous position ranges, boundaries on tile multiples (2048); a rank whose range would start at or
+    // beyond the end of the list owns an EMPTY shard (lists shorter than 2048 x ranks): ranges never overlap
+    const int64_t cap = m + 16;
+    int64_t lo = 0, hi = 0;
+    shardRange(m, rank, nranks, &lo, &hi);
     GNE_TRY(gne_dev_create(&dev, cudaDevice, numNodes + 16, cap, lo, hi));
     if (nranks > 1) GNE_TRY(gne_comm_init(dev, id, rank, nranks));
     return GNE_OK;

@@ -147,11 +147,6 @@ int64_t gne_dev_launch_count(gne_dev *d);
  * between steps, outside the events.                                                          */
 int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles);
 
-/* tuning harness: times the LV tile kernel and its experimental variants (msOut[2v] = mean ms,
- * msOut[2v+1] = best ms over reps); gne_bench_variant_name(v) describes variant v.             */
-int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants);
-const char *gne_bench_variant_name(int i);
-
 /* --- multi-GPU exchange (one process per GPU; NCCL over NVLink) --- */
 /* 128-byte opaque id made on rank 0 and broadcast by the caller (torch.distributed)           */
 int gne_comm_unique_id(uint8_t id[128]);
@@ -227,6 +222,11 @@ int gne_host_replay(int n, int64_t m, const int32_t *tail, const int32_t *head, 
                     const double *mult, const double *supply, double bigM, int drawsPerPricing, int sparseFlows,
                     int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
                     int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective);
+
+/* the contiguous position range [*lo, *hi) of the nonbasic list (m real arcs) that `rank` of `nranks` prices:
+ * boundaries on multiples of 2048, ranges never overlap, *lo == *hi for a rank left without positions
+ * (lists shorter than 2048 x nranks).  What gne_solver_set_comm uses; host-only.                     */
+int gne_shard_range(int64_t m, int rank, int nranks, int64_t *lo, int64_t *hi);
 
 /* merge of per-shard LV records (what every rank does after the all-gather); host-only.
  * maxima[r], any[r], counts[r], and lists (pos, viol) concatenated rank-major with stride cap. */

@@ -238,6 +238,10 @@ print("FLOW-CHECK-OK")
     ("p efpgn 2 1 0\na 1 2 0.0 5.0 1.0\nn 1 1\nn 2 -1\n", 2),                   # short arc line
     ("p efpgn 2 1 0\na 1 2 0.0 5.0 1.0 1.0 0\nn 7 1\n", 2),                     # node line out of range
     ("p efpgn 2 1 1\na 1 2 0.0 5.0 1.0 1.0 1\nn 1 1\nn 2 -1\n", 6),             # equal-flow sets: GNE_ERR_UNSUPPORTED
+    ("p efpgn -1 0 0\n", 2),                                                    # negative node count (no exception across the C ABI)
+    ("p efpgn 0 0 0\n", 2),
+    ("p efpgn 3 -5 0\n", 2),                                                    # negative arc count
+    ("p efpgn 2000000000 1 0\n", 2),                                            # absurd node count
 ])
 def test_col_parser_rejects_malformed_files(gne, tmp_path, text, code):
     """Where the reference prints and exits (graph.cpp:358-447) the loader returns a status code and a message."""
@@ -248,3 +252,62 @@ def test_col_parser_rejects_malformed_files(gne, tmp_path, text, code):
     assert ei.value.code == code, (ei.value.code, str(ei.value))
     with pytest.raises(gne.GneError):
         gne.read_instance(str(tmp_path / "missing.col"))
+
+
+def test_bin_header_is_validated_against_the_file_length(gne, tmp_path):
+    """gne_read_bin_header returns sizes callers allocate from: a header that does not match the file is refused."""
+    import struct
+    p = str(tmp_path / "bad.bin")
+    open(p, "wb").write(b"GNESOA1\0" + struct.pack("<qq", -4, 10))
+    with pytest.raises(gne.GneError):
+        gne.read_instance(p, binary=True)
+    open(p, "wb").write(b"GNESOA1\0" + struct.pack("<qq", 1 << 29, 1 << 40))
+    with pytest.raises(gne.GneError):
+        gne.read_instance(p, binary=True)
+
+
+@pytest.mark.parametrize("m,R", [(100, 2), (10_000, 8), (2047, 8), (2048, 2), (2049, 2), (60_000, 4), (20_000_000, 8), (1, 8), (0, 3)])
+def test_shard_ranges_partition_the_list(gne, m, R):
+    """Ranges are tile-aligned, disjoint, in rank order and cover [0, m + slack); ranks without positions own an
+    empty shard (overlapping ranges duplicated candidates when m < 2048 x ranks)."""
+    rng = [gne.shard_range(m, r, R) for r in range(R)]
+    covered = 0
+    for lo, hi in rng:
+        assert lo % 2048 == 0 and hi >= lo
+        if hi > lo:
+            assert lo == covered, rng
+            covered = hi
+    assert covered == m + 16, rng
+
+
+def test_merge_rejects_overlapping_shards(gne):
+    """Duplicate positions from overlapping shards must not silently inflate the tie list."""
+    import numpy as np
+    stride = 4
+    maxima = np.array([5.0, 5.0]); anys = np.array([1, 1], np.int32); counts = np.array([1, 1], np.int64)
+    pos = np.zeros(2 * stride, np.int64); viol = np.zeros(2 * stride)
+    pos[0] = 7; viol[0] = 5.0; pos[stride] = 7; viol[stride] = 5.0
+    with pytest.raises(gne.GneError):
+        gne.merge_lv_shards(maxima, anys, counts, pos, viol, stride)
+    pos[stride] = 9
+    r = gne.merge_lv_shards(maxima, anys, counts, pos, viol, stride)
+    assert list(r["list"]) == [7, 9] and r["largest"] == 5.0
+
+
+def test_reference_arm_generator_library_matches_the_product(gne):
+    """bench.py's reference arm builds its workload from oracle/libgne_gen.so (so that the reference process
+    never maps the product library); both are compiled from the same source with the same flags."""
+    import ctypes as C
+    import numpy as np
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "gen"], stdout=subprocess.DEVNULL)
+    g = C.CDLL(os.path.join(ROOT, "oracle", "libgne_gen.so"))
+    for (n, m, seed, mode) in [(1000, 10_000, 7, "wide"), (5000, 100_000, 21, "lossy"), (300, 4000, 3, "pow2")]:
+        a = gne.generate_instance(n, m, seed, mode)
+        t = np.empty(m, np.int32); h = np.empty(m, np.int32); ub = np.empty(m); c = np.empty(m); mu = np.empty(m); s = np.empty(n)
+        ip = C.POINTER(C.c_int32); dp = C.POINTER(C.c_double)
+        rc = g.gne_generate_instance_impl(n, C.c_int64(m), C.c_uint64(seed), dict(wide=0, lossy=1, near1=2, pow2=3)[mode],
+                                          t.ctypes.data_as(ip), h.ctypes.data_as(ip), ub.ctypes.data_as(dp), c.ctypes.data_as(dp),
+                                          mu.ctypes.data_as(dp), s.ctypes.data_as(dp))
+        assert rc == 0
+        for k, v in (("tail", t), ("head", h), ("ub", ub), ("cost", c), ("mult", mu), ("supply", s)):
+            assert np.array_equal(a[k], v), k
