@@ -51,9 +51,15 @@ WORKLOADS = {
     # configs[3]: independent instances, one solver handle (= one CUDA stream) each, `--batch` per GPU, seeds 1000..
     "c4-batch": (50_000, 1_000_000, 1000, "lossy", "LV", "configs[3]: independent 50k-node / 1M-arc lossy instances (seeds 1000+), one stream per instance, Dantzig rule (LV)"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of k_price_lv_tiles per launch, from the committed
-# `ncu --set full` captures under profiles/ (c3-lv, N = 1): stream kernel 508.04 MB + 4.0 MB, per-tile kernel 509.1 MB + 4.9 MB
-NCU_TRAFFIC_BYTES = {("c3-lv", 1, "k_price_lv_tiles"): 514.0e6, ("c3-lv", 1, "k_price_lv_stream"): 520.4e6}   # ncu: dram read 508.06 MB + write 12.4 MB
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the pricing kernel, read from the committed `ncu --set full`
+# summary of the same workload / kernel under profiles/ (tools/ncu_summary.py writes the "traffic_bytes" line); None when
+# no capture of that (workload, GPUs, kernel) is committed
+def ncu_traffic(workload, world, kernel):
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path)).get("%s/n%d/%s" % (workload, world, kernel))
+    except Exception:
+        return None
 METRIC = "arcs priced/sec"
 UNIT = "arcs/s"
 
@@ -124,6 +130,55 @@ def dbg(msg):
         sys.stderr.flush()
 
 
+def workload_config(wl, gpus, batch=None):
+    """The `config` object - identical in the b200 arm and the reference arm (it describes the workload, not the arm)."""
+    n, m, seed, mode, rule, desc = WORKLOADS[wl]
+    per_gpu = (25.0 * m / max(gpus, 1) + 8.0 * n) if batch is None else batch * (25.0 * m + 8.0 * n)
+    cfg = {"workload": desc, "nodes": n, "arcs": m, "rule": rule,
+           "window": "Phase I from the initial basis: the timed steps are the pivots after the warm-up pivots",
+           "l2": ("inputs larger than L2 (%.0f MB streamed per pass per GPU)" % (per_gpu / 1e6) if per_gpu >= 200e6 else
+                  "L2 flushed between timed device steps (320 MB write)")}
+    if batch is not None:
+        cfg["instances_per_gpu"] = batch
+        cfg["instances"] = batch * max(gpus, 1)
+    return cfg
+
+
+REF_WINDOW_OF = {"c3-lv": "c3_lv", "c2-lv": "c2_lv", "c2-qs": "c2_qs", "c4-batch": "c4_lv"}
+
+
+def parity_block(wl, e, l, dist, rank, world):
+    """The pivots of the e2e window (and its warm-up) checked two ways: every rank holds the same (entering, leaving)
+    sequence, and the sequence equals the prefix the UNMODIFIED reference wrote for this workload
+    (tests/golden/ref_windows.npz, produced by tests/golden/make_ref_windows.py from oracle/_ref)."""
+    import hashlib
+    e = np.ascontiguousarray(e, np.int32); l = np.ascontiguousarray(l, np.int32)
+    blk = {"pivots_checked": int(len(e)), "ranks_identical": True, "vs_ref": "no fixture for this workload"}
+    if dist is not None:
+        import torch
+        mine = torch.from_numpy(np.concatenate([e, l]).astype(np.int64)).cuda()
+        allt = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine)
+        blk["ranks_identical"] = all(bool(torch.equal(t, allt[0])) for t in allt)
+    name = REF_WINDOW_OF.get(wl)
+    if name is not None:
+        from oracle_util import ref_window
+        re_, rl_, md5 = ref_window(name)
+        k = min(len(e), len(re_))
+        ok = bool(np.array_equal(e[:k], re_[:k]) and np.array_equal(l[:k], rl_[:k]))
+        blk["vs_ref"] = "ok" if ok else "MISMATCH"
+        blk["ref_pivots_compared"] = int(k)
+        blk["ref_fixture_md5"] = md5
+        if k == len(re_):
+            h = hashlib.md5()
+            for i in range(k):
+                h.update(("P %d %d %d\n" % (i, e[i], l[i])).encode())
+            blk["trace_md5"] = h.hexdigest()
+            if blk["trace_md5"] != md5:
+                blk["vs_ref"] = "MISMATCH"
+    return blk
+
+
 def make_instance(wl):
     import genneteq_b200 as gne
     n, m, seed, mode, rule, desc = WORKLOADS[wl]
@@ -139,9 +194,8 @@ import ctypes as C, json, sys, time, os
 import numpy as np
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
 req = json.load(open(sys.argv[1]))
-import genneteq_b200 as gne                      # only for the instance generator (no device work)
-from oracle_util import REF_SO, ORACLE_SO, dp, ip, oracle_lib, RULES
-g = gne.generate_instance(req["n"], req["m"], req["seed"], req["mode"])
+from oracle_util import REF_SO, ORACLE_SO, dp, ip, oracle_lib, RULES, generate_native
+g = generate_native(req["n"], req["m"], req["seed"], req["mode"])     # oracle/libgne_gen.so: the product library is never mapped here
 big_m = oracle_lib().orc_big_m(C.c_long(req["m"]), dp(g["cost"]), dp(g["ub"]))
 kind = "reference" if os.path.exists(REF_SO) else "port"
 if kind == "reference":
@@ -216,7 +270,8 @@ def reference_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": r["steps"],
         "warmup": r["warmup"], "ms_per_step": 1e3 * r["loop_s"] / r["steps"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule, "host_cores_present": os.cpu_count()},
+        "config": workload_config(args.workload, args.gpus),
+        "host_cores_present": os.cpu_count(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample,
                          "pricing_only_arcs_per_s": r["arcs_priced"] / r["pricing_s"] if r["pricing_s"] > 0 else None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -278,10 +333,12 @@ def b200_arm(args):
         raise SystemExit("bench.py: the solve ended before the timed window completed")
     pivots = int(c1["pivots"] - c0["pivots"])
     arcs_e2e = c1["arcs_priced"] - c0["arcs_priced"]
+    te, tl = s.trace
+    parity = parity_block(args.workload, te, tl, dist, rank, world)
     dev = s.device()
     N = m
     # ---- device-resident steps: K x (finalize + pricing pass + reduction [+ exchange]), CUDA events
-    flush = (25 * N + 8 * n) < 200e6            # working set not larger than L2 => flush between steps
+    flush = (25.0 * N / world + 8 * n) < 200e6  # per-GPU working set not larger than L2 => flush between steps
     dev.bench_price_lv(max(args.warmup, 3), flush)
     barrier()
     dbg("device warm-up steps done")
@@ -319,11 +376,9 @@ def b200_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": step_sum_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule,
-                   "l2": ("L2 flushed between timed steps (320 MB write)" if flush else
-                          "inputs larger than L2 (%.0f MB streamed per pass per GPU)" % (alg_bytes / 1e6)),
-                   "sharding": "contiguous position ranges over %d GPU(s); per-pivot exchange of the per-shard record: %s" % (
-                       world, xmode)},
+        "config": workload_config(args.workload, world),
+        "sharding": "contiguous position ranges over %d GPU(s); per-pivot exchange of the per-shard record: %s" % (world, xmode),
+        "parity": parity,
         "e2e": {"value": arcs_e2e / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(pivots, 1),
                 "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / max(pivots, 1),
@@ -332,7 +387,7 @@ def b200_arm(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world, lv_kernel)), "kernel": lv_kernel, "kernel_ms": tiles_ms,
+                     "traffic": ncu_traffic(args.workload, world, lv_kernel), "kernel": lv_kernel, "kernel_ms": tiles_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -348,6 +403,9 @@ def b200_arm(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: %r" % (ex,)}
     print(json.dumps(line))
     sys.stdout.flush()
+    if not parity["ranks_identical"] or parity["vs_ref"] == "MISMATCH":
+        sys.stderr.write("bench.py: PARITY FAILURE %r\n" % (parity,))
+        return 3
     return 0
 
 
@@ -360,9 +418,8 @@ import ctypes as C, json, sys, time, os
 import numpy as np
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
 req = json.load(open(sys.argv[1]))
-import genneteq_b200 as gne
-from oracle_util import REF_SO, dp, ip, oracle_lib, RULES
-g = gne.generate_instance(req["n"], req["m"], req["seed"], req["mode"])
+from oracle_util import REF_SO, dp, ip, oracle_lib, RULES, generate_native
+g = generate_native(req["n"], req["m"], req["seed"], req["mode"])     # oracle/libgne_gen.so: the product library is never mapped here
 big_m = oracle_lib().orc_big_m(C.c_long(req["m"]), dp(g["cost"]), dp(g["ub"]))
 ref = C.CDLL(REF_SO)
 ref.ref_solve.restype = C.c_long
@@ -414,8 +471,8 @@ def batch_arm(args):
         r = batch_reference(args, args.batch * max(args.gpus, 1), min(args.steps, 40), max(2, min(args.warmup, 5)))
         line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": r["steps"],
                 "warmup": r["warmup"], "ms_per_step": r["ms_per_pivot"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule,
-                                                               "instances": r["instances"], "host_cores_present": os.cpu_count()},
+                "dtype": "f64", "data": "synthetic", "config": workload_config("c4-batch", max(args.gpus, 1), batch=args.batch),
+                "instances_timed": r["instances"], "host_cores_present": os.cpu_count(),
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
                                  "sample": "%d instances, one process each, %d iterations after %d warm-up" % (r["instances"], r["steps"], r["warmup"])},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -433,7 +490,8 @@ def batch_arm(args):
     solvers = []
     for i in range(B):
         g = gne.generate_instance(n, m, seed0 + rank * B + i, mode)
-        solvers.append(gne.Solver(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"], device=local, rule1=rule, trace_cap=16))
+        solvers.append(gne.Solver(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"], device=local, rule1=rule,
+                                  trace_cap=W + args.steps + 16))
     sampler = ClockSampler(local)
     if dist is not None:
         dist.barrier()
@@ -449,6 +507,8 @@ def batch_arm(args):
         t.join()
     wins = [s.window() for s in solvers]
     edges = [s.window_edges for s in solvers]
+    # instance 0 of rank 0 is the (seed 1000) instance the reference's prefix fixture was written for
+    parity = parity_block("c4-batch", *solvers[0].trace, None, rank, world) if rank == 0 else None
     wall = max(e[1] for e in edges) - min(e[0] for e in edges)
     arcs = sum(w[2]["arcs_priced"] - w[1]["arcs_priced"] for w in wins)
     pivots = sum(w[2]["pivots"] - w[1]["pivots"] for w in wins)
@@ -495,9 +555,9 @@ def batch_arm(args):
     line = {"metric": METRIC, "value": world * B * m * 2 * args.steps / dev_wall, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": 1e3 * dev_wall / (2 * args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "nodes": n, "arcs": m, "rule": rule, "instances_per_gpu": B, "instances": world * B,
-                       "l2": "all instances of a GPU priced concurrently: %.0f MB per round of passes > L2" % (B * alg / 1e6),
-                       "sharding": "replicas only: one solver handle / CUDA stream / host thread per instance, no collective"},
+            "config": workload_config("c4-batch", world, batch=B),
+            "sharding": "replicas only: one solver handle / CUDA stream / host thread per instance, no collective",
+            "parity": parity,
             "e2e": {"value": arcs / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(pivots, 1), "d2h_bytes_per_step": d2h / max(pivots, 1),
                     "pivots_per_s": pivots / wall, "ms_per_pivot_per_instance": 1e3 * wall / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
@@ -511,6 +571,9 @@ def batch_arm(args):
                                     r["instances"], r["cores"], r["steps"], r["warmup"]), "ms_per_pivot": r["ms_per_pivot"]}
     print(json.dumps(line))
     sys.stdout.flush()
+    if parity["vs_ref"] == "MISMATCH":
+        sys.stderr.write("bench.py: PARITY FAILURE %r\n" % (parity,))
+        return 3
     return 0
 
 

@@ -78,6 +78,7 @@ SIGNATURES = {
     "gne_solver_destroy": (C.c_int, [_vp]),
     "gne_solver_set_rules": (C.c_int, [_vp, C.c_int, C.c_int]),
     "gne_solver_set_comm": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
+    "gne_solver_set_comm_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gne_solver_set_trace": (C.c_int, [_vp, _i32p, _i32p, C.c_int64]),
     "gne_solver_trace_len": (C.c_int64, [_vp]),
     "gne_solver_solve": (C.c_int, [_vp, C.c_int, C.c_int64, _i64p, C.POINTER(C.c_int)]),
@@ -114,6 +115,9 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)
     _f.restype = _res
     _f.argtypes = _args
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
 
 
 class GneError(RuntimeError):
@@ -396,6 +400,24 @@ class Solver:
     def set_comm(self, unique_id, rank, nranks):
         uid = _arr(unique_id, np.uint8)
         _ck(lib.gne_solver_set_comm(self.h, _p(uid, _u8p), rank, nranks), "gne_solver_set_comm")
+
+    def set_comm_host(self, rank, nranks, allgather):
+        """Shard over ranks with the caller's all-gather instead of NCCL (gne_solver_set_comm_host):
+        allgather(send: bytes, nbytes) -> bytes of nranks * nbytes in rank order.  Several ranks may share a device."""
+        def _cb(_ctx, send, recv, nbytes):
+            try:
+                out = allgather(C.string_at(send, nbytes), nbytes)
+                if len(out) != nbytes * nranks:
+                    return 1
+                C.memmove(recv, out, len(out))
+                return 0
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._gather_cb = ALLGATHER_FN(_cb)              # keep the thunk alive as long as the solver
+        _ck(lib.gne_solver_set_comm_host(self.h, rank, nranks, C.cast(self._gather_cb, C.c_void_p), None),
+            "gne_solver_set_comm_host")
 
     def solve(self, presolve, max_pivots=-1):
         it = C.c_int64(0); fin = C.c_int(0)

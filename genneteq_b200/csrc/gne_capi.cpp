@@ -257,6 +257,12 @@ extern "C" int gne_shard_range(int64_t m, int rank, int nranks, int64_t *lo, int
 
 extern "C" int gne_solver_destroy(gne_solver *s) { delete s; return GNE_OK; }
 extern "C" int gne_solver_set_rules(gne_solver *s, int p1, int p2) { s->solver.phaseIpivot = p1; s->solver.phaseIIpivot = p2; return GNE_OK; }
+extern "C" int gne_solver_set_comm_host(gne_solver *s, int rank, int nranks, gne_allgather_fn allgather, void *ctx) {
+    return guarded("gne_solver_set_comm_host", [&]() -> int {
+        if (!allgather) { gne_set_error("gne_solver_set_comm_host: no all-gather callback"); return GNE_ERR_ARG; }
+        uint8_t none[128] = { 0 };
+        return s->solver.setComm(none, rank, nranks, allgather, ctx); });
+}
 extern "C" int gne_solver_set_comm(gne_solver *s, const uint8_t id[128], int rank, int nranks) {
     return guarded("gne_solver_set_comm", [&]() -> int { return s->solver.setComm(id, rank, nranks);     });
 }

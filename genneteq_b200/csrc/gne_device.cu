@@ -154,7 +154,12 @@ struct gne_dev {
     unsigned long long qsSeq = 0;
     QsState *qsDev = nullptr;                      // device-resident carry of the quickSelect scan
     // multi-GPU
-    void *comm = nullptr;
+    void *comm = nullptr;                          // NCCL communicator (gne_comm_init) ...
+    gne_allgather_fn hostGather = nullptr;         // ... or the host program's all-gather (gne_comm_init_host)
+    void *hostGatherCtx = nullptr;
+    char *agDev = nullptr;                         // NCCL staging of small host all-gathers
+    size_t agBytes = 0;
+    long long xTimeoutCycles = 8000000000ll;       // peer wait inside the exchange kernels (GNE_EXCHANGE_TIMEOUT_S, default ~4 s)
     int rank = 0, nranks = 1;
     void *gatherSend = nullptr, *gatherRecv = nullptr, *gatherHost = nullptr;
     LvResult *lvResDev = nullptr;                  // sharded mode: the local LV result stays on the device
@@ -297,7 +302,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
                     d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.rec, d->lvTicket, d->lvc.candPos, d->lvc.candViol, d->lvc.candSecond, d->qsDev, d->stageDev, d->outPos, d->outViol,
-                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev };
+                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev, d->agDev };
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes, d->blobHost };
     for (void *p : host) if (p) cudaFreeHost(p);
@@ -592,6 +597,7 @@ extern "C" int gne_pot_get_all(gne_dev *d, double *pi)
 // pricing
 // ------------------------------------------------------------------------------------------
 static int sharded_gather_lists(gne_dev *d, int64_t localCount, std::vector<int64_t> &pos, std::vector<double> &viol);
+static int small_allgather(gne_dev *d, const void *sendHost, void *recvHost, size_t bytes);
 
 // ordered compaction of this shard's violators with |rc| >= threshold, in two steps: count per tile
 // + offsets (+ min / max of the qualifying values in hostScalar[4..5]), then the write pass
@@ -718,7 +724,7 @@ static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEve
             f.nranks = d->nranks; f.rank = d->rank; f.peers = (Mailbox *const *) d->peersDev;
             f.hostOut = (ShardRecord *) d->gatherHost;
             f.hostSeq = reinterpret_cast<unsigned long long *>((char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
-            f.xseq = ++d->xseq;
+            f.xseq = ++d->xseq; f.xTimeout = d->xTimeoutCycles;
             d->exchangeFused = true;
         }
         CK(launch_k(d, true, k_price_lv_stream, dim3(d->streamGrid), dim3(ST_THREADS), ST_SMEM, nb, (const double *) d->pi, d->lvc, numTiles, f));
@@ -1227,19 +1233,19 @@ __global__ void k_pack_record(const LvResult *res, ShardRecord *rec) { pack_reco
 // exchange from its own last CTA): pack the shard's record, then exchange_record (gne_exchange.cuh).
 __global__ void __launch_bounds__(128)
 k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, ShardRecord *hostOut,
-              unsigned long long *hostSeq)
+              unsigned long long *hostSeq, long long timeoutCycles)
 {
     __shared__ ShardRecord rec;
     __shared__ int sTimeout;
     pdl_wait();                                         // the shard's reduction has published its result block
     pack_record(res, &rec, threadIdx.x);
     __syncthreads();
-    exchange_record(&rec, peers, rank, nranks, seq, hostOut, hostSeq, &sTimeout);
+    exchange_record(&rec, peers, rank, nranks, seq, hostOut, hostSeq, &sTimeout, timeoutCycles);
 }
 // all-gather of one 128-byte blob per rank through the peer mailboxes (same protocol as k_lv_exchange)
 __global__ void __launch_bounds__(64)
 k_blob_exchange(const unsigned long long *src, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, unsigned long long *hostOut,
-                unsigned long long *hostSeq)
+                unsigned long long *hostSeq, long long timeoutCycles)
 {
     const int t = threadIdx.x, b = (int) (seq & 1ull);
     __shared__ unsigned long long mine[BLOB_WORDS];
@@ -1254,16 +1260,22 @@ k_blob_exchange(const unsigned long long *src, Mailbox *const *peers, int rank, 
     Mailbox *self = peers[rank];
     if (t < nranks) {
         const long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned long long *>(&self->bflag[b][t]) != seq) {
-            if (clock64() - t0 > 8000000000ll) { sTimeout = 1; break; }
+        while (true) {
+            const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&self->bflag[b][t]);
+            if (v == seq) break;
+            if (v == XCHG_POISON || clock64() - t0 > timeoutCycles) { sTimeout = 1; break; }
         }
     }
     __syncthreads();
+    if (sTimeout && t < nranks) {
+        *reinterpret_cast<volatile unsigned long long *>(&peers[t]->bflag[0][rank]) = XCHG_POISON;
+        *reinterpret_cast<volatile unsigned long long *>(&peers[t]->bflag[1][rank]) = XCHG_POISON;
+    }
     __threadfence_system();
     for (int r = 0; r < nranks; ++r)
         if (t < BLOB_WORDS) hostOut[r * BLOB_WORDS + t] = *reinterpret_cast<const volatile unsigned long long *>(&self->blob[b][r][t]);
     __syncthreads();
-    if (sTimeout && t == 0) hostOut[0] = ~0ull;
+    if (t == 0) hostSeq[1] = sTimeout ? 1ull : 0ull;
     __threadfence_system();                             // every writer fences its own stores, then the word the host polls
     __syncthreads();
     if (t == 0) *reinterpret_cast<volatile unsigned long long *>(hostSeq) = seq;
@@ -1282,17 +1294,13 @@ static int exchange_blobs(gne_dev *d, const unsigned long long *mine, unsigned l
     memcpy(d->blobHost, mine, 8 * BLOB_WORDS);
     if (d->p2p) {
         unsigned long long *hostSeq = d->blobHost + BLOB_WORDS * (size_t) (R + 1);
-        k_blob_exchange<<<1, 64, 0, d->stream>>>(d->blobHost, d->peersDev, d->rank, R, ++d->bseq, d->blobHost + BLOB_WORDS, hostSeq);
+        k_blob_exchange<<<1, 64, 0, d->stream>>>(d->blobHost, d->peersDev, d->rank, R, ++d->bseq, d->blobHost + BLOB_WORDS, hostSeq, d->xTimeoutCycles);
         CK(cudaGetLastError());
         ++d->launches;
         { int rcw = wait_host_seq(d, hostSeq, d->bseq); if (rcw) return rcw; }
-        if (d->blobHost[BLOB_WORDS] == ~0ull) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
+        if (hostSeq[1] != 0ull) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
     } else {
-        CK(cudaMemcpyAsync(d->blobDev, d->blobHost, 8 * BLOB_WORDS, cudaMemcpyHostToDevice, d->stream));
-        int r = g_nccl.AllGather(d->blobDev, d->blobDev + BLOB_WORDS, 8 * BLOB_WORDS, /*ncclChar*/ 0, d->comm, d->stream);
-        if (r != 0) { gne_set_error("ncclAllGather(blobs) failed"); return GNE_ERR_COMM; }
-        CK(cudaMemcpyAsync(d->blobHost + BLOB_WORDS, d->blobDev + BLOB_WORDS, 8 * BLOB_WORDS * (size_t) R, cudaMemcpyDeviceToHost, d->stream));
-        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+        int rcg = small_allgather(d, d->blobHost, d->blobHost + BLOB_WORDS, 8 * BLOB_WORDS); if (rcg) return rcg;
     }
     memcpy(all, d->blobHost + BLOB_WORDS, 8 * BLOB_WORDS * (size_t) R);
     d->d2hBytes += 8 * BLOB_WORDS * R;
@@ -1386,6 +1394,66 @@ extern "C" int gne_comm_unique_id(uint8_t id[128])
     return GNE_OK;
 }
 
+// All-gather of a few host bytes per rank over whichever channel the handle was given: the host program's callback,
+// or NCCL staged through a small device buffer.  Bootstrap and fallback paths only - never the per-pivot mailbox path.
+static int small_allgather(gne_dev *d, const void *sendHost, void *recvHost, size_t bytes)
+{
+    if (d->hostGather) {
+        if (d->hostGather(d->hostGatherCtx, sendHost, recvHost, (int64_t) bytes) != 0) { gne_set_error("the host all-gather callback failed"); return GNE_ERR_COMM; }
+        return GNE_OK;
+    }
+    const size_t need = bytes * (size_t) (d->nranks + 1);
+    if (need > d->agBytes) {
+        if (d->agDev) cudaFree(d->agDev);
+        d->agDev = nullptr; d->agBytes = 0;
+        CK(cudaMalloc(&d->agDev, need));
+        d->agBytes = need;
+    }
+    CK(cudaMemcpyAsync(d->agDev, sendHost, bytes, cudaMemcpyHostToDevice, d->stream));
+    const int r = g_nccl.AllGather(d->agDev, d->agDev + bytes, bytes, /*ncclChar*/ 0, d->comm, d->stream);
+    if (r != 0) { gne_set_error("ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
+    CK(cudaMemcpyAsync(recvHost, d->agDev + bytes, bytes * (size_t) d->nranks, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    return GNE_OK;
+}
+
+// After d->comm or d->hostGather is in place: buffers of the exchange, the peer mailboxes (CUDA IPC handles
+// all-gathered and mapped), and the verdict every rank must share - mailboxes only if EVERY rank mapped them all.
+static int comm_setup(gne_dev *d, int rank, int nranks)
+{
+    d->rank = rank; d->nranks = nranks;
+    { const char *ts = getenv("GNE_EXCHANGE_TIMEOUT_S"); if (ts && atof(ts) > 0.0) d->xTimeoutCycles = (long long) (atof(ts) * 2.0e9); }
+    CK(cudaMalloc(&d->gatherSend, sizeof(ShardRecord)));
+    CK(cudaMalloc(&d->gatherRecv, sizeof(ShardRecord) * (size_t) nranks));
+    CK(cudaHostAlloc(&d->gatherHost, sizeof(ShardRecord) * (size_t) (nranks + 1) + 64, cudaHostAllocMapped));   // [nranks records][seq word ...][own record (host path)]
+    memset(d->gatherHost, 0, sizeof(ShardRecord) * (size_t) (nranks + 1) + 64);
+    CK(cudaMalloc(&d->lvResDev, sizeof(LvResult)));
+    CK(cudaMemset(d->lvResDev, 0, sizeof(LvResult)));
+    CK(cudaMalloc(&d->mailbox, sizeof(Mailbox)));
+    CK(cudaMemset(d->mailbox, 0, sizeof(Mailbox)));
+    const char *force = getenv("GNE_EXCHANGE");
+    int okLocal = (force && (!strcmp(force, "nccl") || !strcmp(force, "host"))) ? 0 : 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (okLocal && cudaIpcGetMemHandle(&mine, d->mailbox) != cudaSuccess) { cudaGetLastError(); okLocal = 0; memset(&mine, 0, sizeof(mine)); }
+    std::vector<cudaIpcMemHandle_t> handles((size_t) nranks);
+    int rc = small_allgather(d, &mine, handles.data(), sizeof(cudaIpcMemHandle_t)); if (rc) return rc;
+    for (int p = 0; p < nranks && okLocal; ++p) {
+        if (p == rank) { d->peerPtr[p] = d->mailbox; continue; }
+        if (cudaIpcOpenMemHandle(&d->peerPtr[p], handles[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); d->peerPtr[p] = nullptr; okLocal = 0; }
+    }
+    // every rank must take the same path: all-gather the per-rank verdicts
+    unsigned char flagByte[8] = { (unsigned char) okLocal }, verdicts[8 * MAX_RANKS] = { 0 };
+    rc = small_allgather(d, flagByte, verdicts, 8); if (rc) return rc;
+    d->p2p = true;
+    for (int p = 0; p < nranks; ++p) if (!verdicts[8 * p]) d->p2p = false;
+    if (d->p2p) {
+        CK(cudaMalloc(&d->peersDev, sizeof(Mailbox *) * MAX_RANKS));
+        CK(cudaMemcpy(d->peersDev, d->peerPtr, sizeof(void *) * (size_t) nranks, cudaMemcpyHostToDevice));
+    }
+    return GNE_OK;
+}
+
 extern "C" int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nranks)
 {
     if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) { gne_set_error("gne_comm_init: rank %d of %d (at most %d ranks)", rank, nranks, MAX_RANKS); return GNE_ERR_ARG; }
@@ -1395,55 +1463,23 @@ extern "C" int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nr
     memcpy(uid.b, id, 128);
     int r = g_nccl.CommInitRank(&d->comm, nranks, uid, rank);
     if (r != 0) { gne_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
-    d->rank = rank; d->nranks = nranks;
-    CK(cudaMalloc(&d->gatherSend, sizeof(ShardRecord)));
-    CK(cudaMalloc(&d->gatherRecv, sizeof(ShardRecord) * (size_t) nranks));
-    CK(cudaHostAlloc(&d->gatherHost, sizeof(ShardRecord) * (size_t) nranks + 64, cudaHostAllocMapped));   // + the sequence word the host polls
-    memset(d->gatherHost, 0, sizeof(ShardRecord) * (size_t) nranks + 64);
-    CK(cudaMalloc(&d->lvResDev, sizeof(LvResult)));
-    CK(cudaMemset(d->lvResDev, 0, sizeof(LvResult)));
-    // peer mailboxes: exchange CUDA IPC handles through the NCCL communicator, map every peer's buffer
-    CK(cudaMalloc(&d->mailbox, sizeof(Mailbox)));
-    CK(cudaMemset(d->mailbox, 0, sizeof(Mailbox)));
-    const char *force = getenv("GNE_EXCHANGE");
-    int okLocal = (force && !strcmp(force, "nccl")) ? 0 : 1;
-    cudaIpcMemHandle_t mine;
-    if (okLocal && cudaIpcGetMemHandle(&mine, d->mailbox) != cudaSuccess) { cudaGetLastError(); okLocal = 0; memset(&mine, 0, sizeof(mine)); }
-    char *hx = nullptr;                                  // [send 64][recv 64 * R] on the device
-    CK(cudaMalloc(&hx, 64 * (size_t) (nranks + 1)));
-    CK(cudaMemcpyAsync(hx, &mine, 64, cudaMemcpyHostToDevice, d->stream));
-    r = g_nccl.AllGather(hx, hx + 64, 64, /*ncclChar*/ 0, d->comm, d->stream);
-    if (r != 0) { gne_set_error("ncclAllGather(ipc handles) failed"); return GNE_ERR_COMM; }
-    std::vector<cudaIpcMemHandle_t> handles((size_t) nranks);
-    CK(cudaMemcpyAsync(handles.data(), hx + 64, 64 * (size_t) nranks, cudaMemcpyDeviceToHost, d->stream));
-    CK(cudaStreamSynchronize(d->stream));
-    for (int p = 0; p < nranks && okLocal; ++p) {
-        if (p == rank) { d->peerPtr[p] = d->mailbox; continue; }
-        if (cudaIpcOpenMemHandle(&d->peerPtr[p], handles[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); d->peerPtr[p] = nullptr; okLocal = 0; }
-    }
-    // every rank must take the same path: all-gather the per-rank verdicts
-    unsigned char flagByte = (unsigned char) okLocal;
-    CK(cudaMemcpyAsync(hx, &flagByte, 1, cudaMemcpyHostToDevice, d->stream));
-    r = g_nccl.AllGather(hx, hx + 64, 1, /*ncclChar*/ 0, d->comm, d->stream);
-    if (r != 0) { gne_set_error("ncclAllGather(ipc verdicts) failed"); return GNE_ERR_COMM; }
-    unsigned char verdicts[MAX_RANKS] = { 0 };
-    CK(cudaMemcpyAsync(verdicts, hx + 64, (size_t) nranks, cudaMemcpyDeviceToHost, d->stream));
-    CK(cudaStreamSynchronize(d->stream));
-    cudaFree(hx);
-    d->p2p = true;
-    for (int p = 0; p < nranks; ++p) if (!verdicts[p]) d->p2p = false;
-    if (d->p2p) {
-        CK(cudaMalloc(&d->peersDev, sizeof(Mailbox *) * MAX_RANKS));
-        CK(cudaMemcpy(d->peersDev, d->peerPtr, sizeof(void *) * (size_t) nranks, cudaMemcpyHostToDevice));
-    }
-    return GNE_OK;
+    return comm_setup(d, rank, nranks);
 }
 
-extern "C" int gne_comm_mode(gne_dev *d) { return d->nranks <= 1 ? 0 : (d->p2p ? 2 : 1); }
+extern "C" int gne_comm_init_host(gne_dev *d, int rank, int nranks, gne_allgather_fn allgather, void *ctx)
+{
+    if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks || !allgather) { gne_set_error("gne_comm_init_host: rank %d of %d (at most %d ranks), callback %p", rank, nranks, MAX_RANKS, (void *) allgather); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(d->device));
+    d->hostGather = allgather; d->hostGatherCtx = ctx;
+    return comm_setup(d, rank, nranks);
+}
+
+extern "C" int gne_comm_mode(gne_dev *d) { return d->nranks <= 1 ? 0 : (d->p2p ? 2 : (d->hostGather ? 3 : 1)); }
 
 extern "C" int gne_comm_destroy(gne_dev *d)
 {
     if (d->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(d->comm); d->comm = nullptr; }
+    d->hostGather = nullptr; d->hostGatherCtx = nullptr;
     d->nranks = 1; d->rank = 0;
     return GNE_OK;
 }
@@ -1455,13 +1491,19 @@ static int launch_shard_exchange(gne_dev *d)
         // fused pack + NVLink peer stores + flag wait + copy to mapped pinned host: one kernel
         unsigned long long *hostSeq = reinterpret_cast<unsigned long long *>((char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
         CK(launch_k(d, true, k_lv_exchange, dim3(1), dim3(128), 0, (const LvResult *) d->lvResDev, (Mailbox *const *) d->peersDev, d->rank, d->nranks,
-                    (unsigned long long) ++d->xseq, (ShardRecord *) d->gatherHost, hostSeq));
+                    (unsigned long long) ++d->xseq, (ShardRecord *) d->gatherHost, hostSeq, d->xTimeoutCycles));
         ++d->launches;
         return GNE_OK;
     }
-    // fallback: pack this shard's record, all-gather over NCCL, copy the gathered records to pinned host
+    // fallback: pack this shard's record, all-gather over NCCL (or through the host program), records to pinned host
     k_pack_record<<<1, 64, 0, d->stream>>>(d->lvResDev, (ShardRecord *) d->gatherSend);
     ++d->launches;
+    if (d->hostGather) {
+        ShardRecord *own = (ShardRecord *) ((char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks + 64);
+        CK(cudaMemcpyAsync(own, d->gatherSend, sizeof(ShardRecord), cudaMemcpyDeviceToHost, d->stream));
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+        return small_allgather(d, own, d->gatherHost, sizeof(ShardRecord));
+    }
     int r = g_nccl.AllGather(d->gatherSend, d->gatherRecv, sizeof(ShardRecord), /*ncclChar*/ 0, d->comm, d->stream);
     if (r != 0) { gne_set_error("ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
     CK(cudaMemcpyAsync(d->gatherHost, d->gatherRecv, sizeof(ShardRecord) * (size_t) d->nranks, cudaMemcpyDeviceToHost, d->stream));
@@ -1474,30 +1516,35 @@ static int launch_shard_exchange(gne_dev *d)
 static int sharded_gather_lists(gne_dev *d, int64_t localCount, std::vector<int64_t> &pos, std::vector<double> &viol)
 {
     const int R = d->nranks;
-    if (!d->cntDev) CK(cudaMalloc(&d->cntDev, 8 * (size_t) (R + 1)));
-    d->hostScalar[2] = localCount;
-    CK(cudaMemcpyAsync(d->cntDev, &d->hostScalar[2], 8, cudaMemcpyHostToDevice, d->stream));
-    int r = g_nccl.AllGather(d->cntDev, d->cntDev + 1, 8, /*ncclChar*/ 0, d->comm, d->stream);
-    if (r != 0) { gne_set_error("ncclAllGather(counts): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
     std::vector<int64_t> counts((size_t) R);
-    CK(cudaMemcpyAsync(counts.data(), d->cntDev + 1, 8 * (size_t) R, cudaMemcpyDeviceToHost, d->stream));
-    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    int rc = small_allgather(d, &localCount, counts.data(), 8); if (rc) return rc;
     int64_t maxC = 0, total = 0;
     for (int k = 0; k < R; ++k) { maxC = std::max(maxC, counts[k]); total += counts[k]; }
     pos.clear(); viol.clear();
     if (maxC == 0) return GNE_OK;
     const size_t per = (size_t) maxC * 16;
-    if (per > d->xSendBytes) { if (d->xSend) cudaFree(d->xSend); d->xSend = nullptr; CK(cudaMalloc(&d->xSend, per)); d->xSendBytes = per; }
-    if (per * R > d->xRecvBytes) { if (d->xRecv) cudaFree(d->xRecv); d->xRecv = nullptr; CK(cudaMalloc(&d->xRecv, per * R)); d->xRecvBytes = per * R; }
-    if (localCount > 0) {
-        CK(cudaMemcpyAsync(d->xSend, d->outPos, 8 * (size_t) localCount, cudaMemcpyDeviceToDevice, d->stream));
-        CK(cudaMemcpyAsync(d->xSend + 8 * (size_t) maxC, d->outViol, 8 * (size_t) localCount, cudaMemcpyDeviceToDevice, d->stream));
-    }
-    r = g_nccl.AllGather(d->xSend, d->xRecv, per, /*ncclChar*/ 0, d->comm, d->stream);
-    if (r != 0) { gne_set_error("ncclAllGather(lists): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
     std::vector<char> host(per * R);
-    CK(cudaMemcpyAsync(host.data(), d->xRecv, per * R, cudaMemcpyDeviceToHost, d->stream));
-    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    if (d->hostGather) {
+        // through the host program: own list to the host, all-gather there
+        std::vector<char> mine(per, 0);
+        if (localCount > 0) {
+            CK(cudaMemcpyAsync(mine.data(), d->outPos, 8 * (size_t) localCount, cudaMemcpyDeviceToHost, d->stream));
+            CK(cudaMemcpyAsync(mine.data() + 8 * (size_t) maxC, d->outViol, 8 * (size_t) localCount, cudaMemcpyDeviceToHost, d->stream));
+            CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+        }
+        rc = small_allgather(d, mine.data(), host.data(), per); if (rc) return rc;
+    } else {
+        if (per > d->xSendBytes) { if (d->xSend) cudaFree(d->xSend); d->xSend = nullptr; d->xSendBytes = 0; CK(cudaMalloc(&d->xSend, per)); d->xSendBytes = per; }
+        if (per * R > d->xRecvBytes) { if (d->xRecv) cudaFree(d->xRecv); d->xRecv = nullptr; d->xRecvBytes = 0; CK(cudaMalloc(&d->xRecv, per * R)); d->xRecvBytes = per * R; }
+        if (localCount > 0) {
+            CK(cudaMemcpyAsync(d->xSend, d->outPos, 8 * (size_t) localCount, cudaMemcpyDeviceToDevice, d->stream));
+            CK(cudaMemcpyAsync(d->xSend + 8 * (size_t) maxC, d->outViol, 8 * (size_t) localCount, cudaMemcpyDeviceToDevice, d->stream));
+        }
+        const int r = g_nccl.AllGather(d->xSend, d->xRecv, per, /*ncclChar*/ 0, d->comm, d->stream);
+        if (r != 0) { gne_set_error("ncclAllGather(lists): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GNE_ERR_COMM; }
+        CK(cudaMemcpyAsync(host.data(), d->xRecv, per * R, cudaMemcpyDeviceToHost, d->stream));
+        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    }
     d->d2hBytes += (int64_t) (per * R);
     pos.reserve((size_t) total); viol.reserve((size_t) total);
     for (int k = 0; k < R; ++k) {
@@ -1516,12 +1563,12 @@ int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &
         const volatile unsigned long long *hostSeq =
             reinterpret_cast<const volatile unsigned long long *>((const char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
         rcx = wait_host_seq(d, hostSeq, d->xseq); if (rcx) return rcx;
+        if (hostSeq[1] != 0ull) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
     } else {
         CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     }
     d->d2hBytes += sizeof(ShardRecord) * (int64_t) d->nranks;
     const ShardRecord *rec = (const ShardRecord *) d->gatherHost;
-    if (rec[0].count == -2) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
     // scratch kept across pivots (no allocation on the per-pivot path)
     static thread_local std::vector<double> maxima, viol;
     static thread_local std::vector<int> anys;

@@ -29,13 +29,17 @@ struct Mailbox {
     unsigned long long bflag[2][MAX_RANKS];
 };
 
+constexpr unsigned long long XCHG_POISON = ~0ull;       // flag value a timed-out rank leaves with every peer: they fail in the same pass
+
 // Whole CTA.  `rec` (shared memory, complete and visible to the block) is stored into every rank's
-// mailbox, the sequence flag published, the peers' flags awaited (~4 s timeout: a dead peer fails the
-// pass instead of hanging it), and all records copied to mapped pinned host memory; hostSeq is written
-// last, after system-scope fences by every writer, so the host can poll it instead of synchronising.
+// mailbox, the sequence flag published, the peers' flags awaited (timeoutCycles, default ~4 s: a dead peer
+// fails the pass instead of hanging it; the rank that gives up poisons its flag at every peer so that they
+// give up in the same pass), and all records copied to mapped pinned host memory; hostSeq[0] is written
+// last, after system-scope fences by every writer, so the host can poll it instead of synchronising;
+// hostSeq[1] = 1 reports the timeout.
 __device__ __forceinline__ void exchange_record(const ShardRecord *rec, Mailbox *const *peers, int rank, int nranks,
                                                 unsigned long long seq, ShardRecord *hostOut, unsigned long long *hostSeq,
-                                                int *sTimeout)
+                                                int *sTimeout, long long timeoutCycles)
 {
     const int t = threadIdx.x, nthr = blockDim.x;
     const int b = (int) (seq & 1ull);
@@ -52,11 +56,17 @@ __device__ __forceinline__ void exchange_record(const ShardRecord *rec, Mailbox 
     Mailbox *self = peers[rank];
     if (t < nranks) {
         const long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned long long *>(&self->flag[b][t]) != seq) {
-            if (clock64() - t0 > 8000000000ll) { *sTimeout = 1; break; }
+        while (true) {
+            const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&self->flag[b][t]);
+            if (v == seq) break;
+            if (v == XCHG_POISON || clock64() - t0 > timeoutCycles) { *sTimeout = 1; break; }
         }
     }
     __syncthreads();
+    if (*sTimeout && t < nranks) {                      // fail fast everywhere: both generations of our flag at every peer
+        *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[0][rank]) = XCHG_POISON;
+        *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[1][rank]) = XCHG_POISON;
+    }
     __threadfence_system();
     for (int r = 0; r < nranks; ++r) {
         const volatile unsigned long long *in = reinterpret_cast<const volatile unsigned long long *>(&self->rec[b][r]);
@@ -64,7 +74,7 @@ __device__ __forceinline__ void exchange_record(const ShardRecord *rec, Mailbox 
         for (int w = t; w < WORDS; w += nthr) out[w] = in[w];
     }
     __syncthreads();
-    if (*sTimeout && t == 0) hostOut[0].count = -2;
+    if (t == 0) hostSeq[1] = *sTimeout ? 1ull : 0ull;
     __threadfence_system();
     __syncthreads();
     if (t == 0) *reinterpret_cast<volatile unsigned long long *>(hostSeq) = seq;

@@ -91,7 +91,7 @@ void GenNetEq::shardRange(int64_t m, int rank, int nranks, int64_t *lo, int64_t 
     *hi = (rank == nranks - 1) ? cap : std::min<int64_t>(*lo + per, cap);
 }
 
-int GenNetEq::setComm(const uint8_t id[128], int rank, int nranks)
+int GenNetEq::setComm(const uint8_t id[128], int rank, int nranks, gne_allgather_fn hostGather, void *hostCtx)
 {
     if (nranks < 1 || rank < 0 || rank >= nranks) { gne_set_error("setComm: bad rank %d of %d", rank, nranks); return GNE_ERR_ARG; }
     if (dev) { gne_set_error("setComm must precede the first solve"); return GNE_ERR_ARG; }
@@ -102,7 +102,10 @@ int GenNetEq::setComm(const uint8_t id[128], int rank, int nranks)
     int64_t lo = 0, hi = 0;
     shardRange(m, rank, nranks, &lo, &hi);
     GNE_TRY(gne_dev_create(&dev, cudaDevice, numNodes + 16, cap, lo, hi));
-    if (nranks > 1) GNE_TRY(gne_comm_init(dev, id, rank, nranks));
+    if (nranks > 1) {
+        if (hostGather) GNE_TRY(gne_comm_init_host(dev, rank, nranks, hostGather, hostCtx));
+        else GNE_TRY(gne_comm_init(dev, id, rank, nranks));
+    }
     return GNE_OK;
 }
 

@@ -70,7 +70,7 @@ class GenNetEq {
 
     int phaseIpivot = GNE_LVW, phaseIIpivot = GNE_LVW;               // main.cpp:72-73 defaults
 
-    int setComm(const uint8_t id[128], int rank, int nranks);
+    int setComm(const uint8_t id[128], int rank, int nranks, gne_allgather_fn hostGather = nullptr, void *hostCtx = nullptr);
     // global position range [lo, hi) of rank's shard of a list of m arcs (lo == hi: empty shard)
     static void shardRange(int64_t m, int rank, int nranks, int64_t *lo, int64_t *hi);
     void setTrace(int32_t *e, int32_t *l, int64_t cap) { traceE = e; traceL = l; traceCap = cap; traceLen = 0; }

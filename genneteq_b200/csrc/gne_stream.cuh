@@ -82,6 +82,7 @@ struct LvFused {
     ShardRecord *hostOut;
     unsigned long long *hostSeq;
     unsigned long long xseq;
+    long long xTimeout;            // cycles a rank waits for its peers before failing the pass
     long long *stamps;             // debug (GNE_STAMPS builds): clock64 stamps of the last CTA
 };
 
@@ -199,7 +200,7 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
         }
         if (t < SHARD_LIST && t < nOut) { xrec->pos[t] = lPos[lRank[t]]; xrec->viol[t] = lViol[lRank[t]]; }
         __syncthreads();
-        exchange_record(xrec, f.peers, f.rank, f.nranks, f.xseq, f.hostOut, f.hostSeq, &sTimeout);
+        exchange_record(xrec, f.peers, f.rank, f.nranks, f.xseq, f.hostOut, f.hostSeq, &sTimeout, f.xTimeout);
     }
 }
 

@@ -152,9 +152,16 @@ int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, floa
 int gne_comm_unique_id(uint8_t id[128]);
 int gne_comm_init(gne_dev *d, const uint8_t id[128], int rank, int nranks);
 int gne_comm_destroy(gne_dev *d);
+/* The same without NCCL: the host program supplies the all-gather (every rank contributes `bytes` bytes at `send`,
+ * `recv` receives nranks x bytes in rank order; 0 = success).  Used for the bootstrap (CUDA IPC handles of the
+ * mailboxes) and, when the mailboxes cannot be mapped on every rank or GNE_EXCHANGE=host, for the per-pivot
+ * records themselves.  Lets several ranks share one device (NCCL refuses that): the sharded path can then be
+ * exercised on a single-GPU box.                                                                      */
+typedef int (*gne_allgather_fn)(void *ctx, const void *send, void *recv, int64_t bytes);
+int gne_comm_init_host(gne_dev *d, int rank, int nranks, gne_allgather_fn allgather, void *ctx);
 /* 0 = single GPU, 1 = per-pivot exchange through ncclAllGather, 2 = through peer mailboxes (NVLink stores from
  * the exchange kernel into CUDA-IPC-mapped buffers; default when IPC mapping succeeds on every rank;
- * GNE_EXCHANGE=nccl forces 1)                                                                      */
+ * GNE_EXCHANGE=nccl forces 1), 3 = through the host program's all-gather (gne_comm_init_host without mailboxes) */
 int gne_comm_mode(gne_dev *d);
 
 /* =============================== layer 2: solver mirror =============================== */
@@ -171,6 +178,7 @@ int gne_solver_destroy(gne_solver *s);
 int gne_solver_set_rules(gne_solver *s, int phaseIpivot, int phaseIIpivot);
 /* shard the pricing over ranks (call before the first solve); id from gne_comm_unique_id     */
 int gne_solver_set_comm(gne_solver *s, const uint8_t id[128], int rank, int nranks);
+int gne_solver_set_comm_host(gne_solver *s, int rank, int nranks, gne_allgather_fn allgather, void *ctx);
 /* record (eVar, lVar) varIndex pairs of every pivot                                           */
 int gne_solver_set_trace(gne_solver *s, int32_t *e, int32_t *l, int64_t cap);
 int64_t gne_solver_trace_len(const gne_solver *s);

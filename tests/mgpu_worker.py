@@ -21,7 +21,63 @@ for p in (ROOT, HERE, os.path.join(HERE, "golden")):
     sys.path.insert(0, p)
 
 import genneteq_b200 as gne  # noqa: E402
-from oracle_util import RULES, Instance, Oracle, oracle_lib, dp, ip, lp, bp  # noqa: E402
+from oracle_util import RULES, Instance, Oracle, oracle_lib, dp, ip, lp, bp, ref_window  # noqa: E402
+
+
+class Boot:
+    """Process group + the way the solver is attached to it.  One rank per GPU with NCCL when the box has enough
+    GPUs; otherwise (single-GPU box) the ranks share device 0, torch's gloo group carries the bootstrap and the
+    library gets its all-gather as a host callback (gne_solver_set_comm_host) - NCCL refuses two ranks on one device."""
+
+    def __init__(self, rank, world, local):
+        self.rank, self.world = rank, world
+        ngpu = torch.cuda.device_count()
+        self.shared = ngpu < world or os.environ.get("GNE_TEST_BOOT") == "host"
+        self.device = local % max(ngpu, 1)
+        torch.cuda.set_device(self.device)
+        if self.shared:
+            dist.init_process_group("gloo")
+            self.tdev = "cpu"
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.device))
+            self.tdev = "cuda"
+
+    def _allgather(self, send, nbytes):
+        mine = torch.frombuffer(bytearray(send), dtype=torch.uint8)
+        outs = [torch.zeros(nbytes, dtype=torch.uint8) for _ in range(self.world)]
+        dist.all_gather(outs, mine)
+        return b"".join(o.numpy().tobytes() for o in outs)
+
+    def attach(self, s):
+        if self.shared:
+            s.set_comm_host(self.rank, self.world, self._allgather)
+            return
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = np.zeros(128, np.uint8)
+            gne._ck(gne.lib.gne_comm_unique_id(buf.ctypes.data_as(gne._u8p)), "gne_comm_unique_id")
+            uid = torch.from_numpy(buf)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        s.set_comm(uid.cpu().numpy(), self.rank, self.world)
+
+    def same_everywhere(self, arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr).astype(np.int64)).to(self.tdev)
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        return bool(torch.equal(t, ref))
+
+    def all_ok(self, ok):
+        flag = torch.tensor([1 if ok else 0], device=self.tdev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return int(flag.item()) == 1
+
+    def finish(self, out, ok, note=""):
+        good = self.all_ok(ok)
+        if self.rank == 0:
+            open(out, "w").write("OK" if good else "MISMATCH " + note)
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -31,60 +87,61 @@ def main():
     gold = np.load(os.path.join(HERE, "golden", "c1_wide_s7.npz"))
     inst = Instance.load(os.path.join(HERE, "golden", "c1_wide_s7_instance.npz"))
     if mode == "nccl-c2":
-        # configs[1] size, sharded: first 300 Dantzig pivots on every rank vs the oracle (rank 0 runs it)
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = np.zeros(128, np.uint8)
-            gne._ck(gne.lib.gne_comm_unique_id(buf.ctypes.data_as(gne._u8p)), "gne_comm_unique_id")
-            uid = torch.from_numpy(buf)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
+        # configs[1] size, sharded: the first 300 pivots on EVERY rank against the prefix the unmodified reference
+        # wrote (tests/golden/ref_windows.npz); flows and potentials against the oracle on rank 0
+        boot = Boot(rank, world, local)
         g = gne.generate_instance(100_000, 2_000_000, 21, "lossy")
         big = Instance(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"])
-        s = gne.Solver(big.n, big.tail, big.head, big.ub, big.cost, big.mult, big.supply, device=local, rule1=rule)
-        s.set_comm(uid.cpu().numpy(), rank, world)
+        s = gne.Solver(big.n, big.tail, big.head, big.ub, big.cost, big.mult, big.supply, device=boot.device, rule1=rule)
+        boot.attach(s)
         s.solve(True, 300)
         e, l = s.trace
-        tr = torch.from_numpy(np.concatenate([e, l]).astype(np.int64)).cuda()
-        ref = tr.clone()
-        dist.broadcast(ref, 0)
-        ok = bool(torch.equal(tr, ref))                  # every rank produced rank 0's trace
+        re_, rl_, _ = ref_window("c2_" + rule.lower())
+        ok = len(e) == 300 and np.array_equal(e, re_[:300]) and np.array_equal(l, rl_[:300])
+        ok = ok and boot.same_everywhere(np.concatenate([e, l]))
         if rank == 0:
             o = Oracle(big, RULES[rule])
             o.solve(True, 300)
             ok = ok and np.array_equal(e, o.trace[0]) and np.array_equal(l, o.trace[1]) and np.array_equal(s.flows(), o.flows())
             ok = ok and np.array_equal(s.potentials(), o.potentials())
-        flag = torch.tensor([1 if ok else 0], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if rank == 0:
-            open(out, "w").write("OK" if int(flag.item()) == 1 else "MISMATCH")
+        mode_id = gne.lib.gne_comm_mode(s.device().h)
         s.close()
-        dist.barrier()
-        dist.destroy_process_group()
+        boot.finish(out, ok, "comm mode %d" % mode_id)
         return
     if mode == "nccl":
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = np.zeros(128, np.uint8)
-            gne._ck(gne.lib.gne_comm_unique_id(buf.ctypes.data_as(gne._u8p)), "gne_comm_unique_id")
-            uid = torch.from_numpy(buf)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, device=local, rule1=rule)
-        s.set_comm(uid.cpu().numpy(), rank, world)
+        boot = Boot(rank, world, local)
+        s = gne.Solver(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, device=boot.device, rule1=rule)
+        boot.attach(s)
+        want = os.environ.get("GNE_TEST_EXPECT_MODE")
         p1, p2 = s.solve_both()
+        mode_id = gne.lib.gne_comm_mode(s.device().h)
         e, l = s.trace
         ok = (p1, p2) == tuple(int(v) for v in gold[rule + "_p"]) and np.array_equal(e, gold[rule + "_e"]) and np.array_equal(l, gold[rule + "_l"])
         ok = ok and s.objective == float(gold[rule + "_objective"]) and np.array_equal(s.flows(), gold[rule + "_flows"])
-        flag = torch.tensor([1 if ok else 0], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if rank == 0:
-            open(out, "w").write("OK" if int(flag.item()) == 1 else "MISMATCH")
-        dist.destroy_process_group()
+        if want:
+            ok = ok and mode_id in [int(x) for x in want.split(",")]
+        s.close()
+        boot.finish(out, ok, "comm mode %d" % mode_id)
+        return
+    if mode == "edge":
+        # lists shorter than 2048 x ranks: some ranks own EMPTY shards; every edge fixture, rules LV / QS / CL
+        boot = Boot(rank, world, local)
+        ok = True
+        note = ""
+        for name in ("e_infeasible_s11", "e_nosupply_s12", "e_two_nodes_s13", "e_three_nodes_s14", "s_wide_s3"):
+            from test_oracle_pinned import load
+            z, ei = load(name)
+            for r in ("LV", "QS", "CL"):
+                s = gne.Solver(ei.n, ei.tail, ei.head, ei.ub, ei.cost, ei.mult, ei.supply, device=boot.device, rule1=r)
+                boot.attach(s)
+                p1, p2 = s.solve_both()
+                e, l = s.trace
+                good = np.array_equal(e, z[r + "_e"]) and np.array_equal(l, z[r + "_l"]) and np.array_equal(s.flows(), z[r + "_flows"])
+                if not good:
+                    note += " %s/%s" % (name, r)
+                ok = ok and good
+                s.close()
+        boot.finish(out, ok, note)
         return
     # ---- gloo: host logic of the sharded LV exchange
     dist.init_process_group("gloo")

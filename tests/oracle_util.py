@@ -45,6 +45,33 @@ def bp(a):
     return a.ctypes.data_as(c_bp)
 
 
+GEN_SO = os.path.join(ORACLE_DIR, "libgne_gen.so")
+REF_WINDOWS = os.path.join(ROOT, "tests", "golden", "ref_windows.npz")
+GEN_MODES = dict(wide=0, lossy=1, near1=2, pow2=3)
+
+
+def generate_native(n, m, seed, mode="lossy"):
+    """The product's synthetic-instance generator through the stand-alone oracle/libgne_gen.so (same source file,
+    same flags => bit-identical instances) - for processes that must not map the product library."""
+    if not os.path.exists(GEN_SO):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "gen"], stdout=subprocess.DEVNULL)
+    gen = C.CDLL(GEN_SO)
+    tail = np.empty(m, np.int32); head = np.empty(m, np.int32)
+    ub = np.empty(m); cost = np.empty(m); mult = np.empty(m); supply = np.empty(n)
+    rc = gen.gne_generate_instance_impl(C.c_int(n), C.c_int64(m), C.c_uint64(seed), C.c_int(GEN_MODES[mode]),
+                                        tail.ctypes.data_as(C.POINTER(C.c_int32)), head.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        dp(ub), dp(cost), dp(mult), dp(supply))
+    if rc != 0:
+        raise ValueError("gne_generate_instance_impl(%d, %d): status %d" % (n, m, rc))
+    return dict(n=n, tail=tail, head=head, ub=ub, cost=cost, mult=mult, supply=supply)
+
+
+def ref_window(name):
+    """(e, l, md5) of a prefix window written by the unmodified reference (tests/golden/make_ref_windows.py)."""
+    z = np.load(REF_WINDOWS)
+    return z[name + "_e"], z[name + "_l"], str(z[name + "_md5"])
+
+
 def build_oracle():
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
             os.path.join(ORACLE_DIR, "gne_oracle.cpp")):

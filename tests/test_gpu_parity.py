@@ -424,6 +424,30 @@ def test_c2_prefix_window_equals_oracle(gne, rule, K):
     s.close(); o.close()
 
 
+REF_WINDOWS = [("c2_lv", 100_000, 2_000_000, 21, "LV", 2000), ("c2_qs", 100_000, 2_000_000, 21, "QS", 2000),
+               ("c4_lv", 50_000, 1_000_000, 1000, "LV", 2000), ("c3_lv", 1_000_000, 20_000_000, 31, "LV", 600)]
+
+
+@pytest.mark.parametrize("name,n,m,seed,rule,K", REF_WINDOWS)
+def test_large_prefix_windows_equal_the_reference_itself(gne, name, n, m, seed, rule, K):
+    """configs[1] (LV and the block rule QS, 2000 pivots), configs[3]'s instance 0 (2000 pivots) and configs[2]
+    (1M nodes / 20M arcs, 600 pivots): the (entering, leaving) sequence from the initial basis equals, pivot for
+    pivot, the one the UNMODIFIED reference produced for the same generated instance
+    (tests/golden/ref_windows.npz, written by tests/golden/make_ref_windows.py through oracle/_ref/libgne_ref.so)."""
+    from oracle_util import ref_window, REF_WINDOWS as path
+    import os
+    re_, rl_, md5 = ref_window(name)
+    assert len(re_) == K
+    g = gne.generate_instance(n, m, seed, "lossy")
+    s = gne.Solver(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"], rule1=rule, trace_cap=K + 16)
+    s.solve(True, K)
+    e, l = s.trace
+    assert len(e) == K
+    bad = np.flatnonzero((e != re_) | (l != rl_))
+    assert bad.size == 0, "first differing pivot %d: (%d, %d) vs reference (%d, %d)" % (bad[0], e[bad[0]], l[bad[0]], re_[bad[0]], rl_[bad[0]])
+    s.close()
+
+
 def test_c2_deep_same_state_ab(gne):
     """same-state A/B deep into a GPU-driven solve of configs[1] (100k nodes / 2M arcs).  At
     sampled iterations the state the next pricing pass will read (nonbasic mirror in setNBarc order + potentials)

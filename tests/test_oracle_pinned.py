@@ -156,3 +156,32 @@ def test_stateless_kernels_agree_with_solver_state():
         if len(e) > K:
             assert int(e[K]) in cand
         o.close()
+
+
+@pytest.mark.parametrize("name,n,m,seed,rule,K", [("c2_qs", 100_000, 2_000_000, 21, "QS", 2000), ("c2_lv", 100_000, 2_000_000, 21, "LV", 250),
+                                                  ("c4_lv", 50_000, 1_000_000, 1000, "LV", 400)])
+def test_port_equals_reference_on_large_prefix_windows(name, n, m, seed, rule, K):
+    """The port against the unmodified reference BEYOND the small fixtures: prefix windows of the configs[1] / configs[3]
+    instances (native generator, 100k nodes / 2M arcs and 50k / 1M) written by the reference itself
+    (tests/golden/ref_windows.npz); sized for the CPU suite - the GPU suite compares the full windows."""
+    from oracle_util import generate_native, ref_window
+    re_, rl_, _ = ref_window(name)
+    g = generate_native(n, m, seed, "lossy")
+    inst = Instance(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"])
+    o = Oracle(inst, RULES[rule], trace_cap=K + 16)
+    o.solve(True, K)
+    e, l = o.trace
+    assert len(e) == K
+    assert np.array_equal(e, re_[:K]) and np.array_equal(l, rl_[:K])
+    o.close()
+
+
+def test_native_generator_library_matches_the_product_generator():
+    """oracle/libgne_gen.so (what the reference arm of bench.py and make_ref_windows.py load) and the product's
+    gne_generate_instance are the same source file with the same flags: identical instances."""
+    import genneteq_b200 as gne
+    from oracle_util import generate_native
+    a = gne.generate_instance(5000, 60000, 77, "lossy")
+    b = generate_native(5000, 60000, 77, "lossy")
+    for k in ("tail", "head", "ub", "cost", "mult", "supply"):
+        assert np.array_equal(a[k], b[k]), k
