@@ -71,6 +71,7 @@ SIGNATURES = {
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
     "gne_comm_unique_id": (C.c_int, [_u8p]),
     "gne_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
+    "gne_comm_init_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gne_comm_destroy": (C.c_int, [_vp]),
     "gne_comm_mode": (C.c_int, [_vp]),
     "gne_solver_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_double]),

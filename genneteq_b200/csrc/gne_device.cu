@@ -140,7 +140,11 @@ struct gne_dev {
     bool stageInFlight = false;                    // the staging buffer feeds a kernel not yet synchronised
     LvCtas lvc{};                                  // per-CTA records of the TMA-streamed LV pass
     int streamGrid = 0;                            // 2 CTAs per SM
-    unsigned int *lvTicket = nullptr;              // last-CTA ticket of the streamed pass (zero between passes)
+    unsigned int *lvTicket = nullptr;              // counters of the streamed pass, one 128-byte line each (zero between passes):
+    unsigned int *lvArrive = nullptr;              //   last-CTA ticket, first-CTA election, next tile, update-visible flag
+    unsigned long long *lvTileCtr = nullptr, *lvUpdFlag = nullptr;
+    SmallUpdate pendingSmall{};                    // argument-only update not launched yet: the next streamed LV pass carries it
+    bool havePendingSmall = false;
     int streamOverflows = 0, streamHoldoff = 0;    // adaptive fallback to the per-tile kernel
     bool lastWasStream = false;
     int lvKernelMode = 0;                          // 0 auto, 1 per-tile kernel, 2 TMA-streamed kernel
@@ -220,6 +224,7 @@ static int ensure_out(gne_dev *d, int64_t cap)
 }
 
 static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi);
+static int flush_pending(gne_dev *d);
 
 extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi)
 {
@@ -274,7 +279,10 @@ static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity
         d->streamGrid = sms * ST_CTAS_PER_SM;
         if (d->streamGrid > 2 * ST_THREADS) d->streamGrid = 2 * ST_THREADS;        // the reduction reads two records per thread
         CK(cudaMalloc(&d->lvc.rec, sizeof(CtaRec) * (size_t) d->streamGrid));
-        CK(cudaMalloc(&d->lvTicket, 64)); CK(cudaMemset(d->lvTicket, 0, 64));
+        CK(cudaMalloc(&d->lvTicket, 512)); CK(cudaMemset(d->lvTicket, 0, 512));
+        d->lvArrive = d->lvTicket + 32;
+        d->lvTileCtr = reinterpret_cast<unsigned long long *>(d->lvTicket + 64);
+        d->lvUpdFlag = reinterpret_cast<unsigned long long *>(d->lvTicket + 96);
         CK(cudaMalloc(&d->lvc.candPos, 8 * (size_t) d->streamGrid * ST_CAND)); CK(cudaMalloc(&d->lvc.candViol, 8 * (size_t) d->streamGrid * ST_CAND));
         CK(cudaMalloc(&d->lvc.candSecond, 8 * (size_t) d->streamGrid * ST_CAND));
         CK(cudaFuncSetAttribute(k_price_lv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
@@ -319,6 +327,7 @@ extern "C" int gne_dev_destroy(gne_dev *d)
 extern "C" int gne_dev_sync(gne_dev *d)
 {
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     return GNE_OK;
 }
@@ -338,6 +347,7 @@ extern "C" int gne_nb_reset(gne_dev *d, int64_t N, const int32_t *tail, const in
 {
     if (N < 0 || N > d->cap) { gne_set_error("gne_nb_reset: N out of range"); return GNE_ERR_ARG; }
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     const int64_t a = d->lo, b = std::min(N, d->hi);
     // the pricing kernels gather pi[tail], pi[head] unchecked: reject a bad record here (as gne_nb_write does)
     for (int64_t p = a; p < b; ++p)
@@ -360,6 +370,7 @@ extern "C" int gne_nb_set_costs(gne_dev *d, int64_t N, const double *cost)
 {
     if (N != d->N) { gne_set_error("gne_nb_set_costs: N mismatch"); return GNE_ERR_ARG; }
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     const int64_t a = d->lo, b = std::min(N, d->hi);
     if (b > a) {
         CK(cudaMemcpyAsync(d->cost, cost + a, 8 * (size_t) (b - a), cudaMemcpyHostToDevice, d->stream));
@@ -384,7 +395,21 @@ static int flush_writes(gne_dev *d, NbWriteOps &ops)
 
 static NbWriteOps &pending_of(gne_dev *d) { return d->pending; }
 
-int gne_dev_flush(gne_dev *d) { return flush_writes(d, pending_of(d)); }
+// Everything queued but not launched yet, in order: the argument-only update that waits for the next streamed LV pass
+// (it carries the set-mirror writes that were queued before it), then the set-mirror writes queued since.
+static int flush_pending(gne_dev *d)
+{
+    if (d->havePendingSmall) {
+        NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
+        k_update_small<<<1, 256, 0, d->stream>>>(mm, d->pendingSmall, d->a0, d->a1, d->slot, d->theta, d->pi);
+        CK(cudaGetLastError());
+        ++d->launches;
+        d->havePendingSmall = false;
+    }
+    return flush_writes(d, pending_of(d));
+}
+
+int gne_dev_flush(gne_dev *d) { return flush_pending(d); }
 
 extern "C" int gne_nb_write(gne_dev *d, int64_t pos, int32_t tail, int32_t head, double cost, double mult, int8_t state)
 {
@@ -436,6 +461,7 @@ extern "C" int gne_pot_update_nodes(gne_dev *d, int64_t count, const int32_t *no
 {
     if (count <= 0) return GNE_OK;
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     const size_t bytes = (size_t) count * 24;
     int rc = ensure_stage(d, bytes); if (rc) return rc;
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;           // the staging buffer may still be in flight
@@ -460,6 +486,7 @@ extern "C" int gne_pot_update_thetas(gne_dev *d, int64_t count, const int32_t *s
 {
     if (count <= 0) return GNE_OK;
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     const size_t bytes = (size_t) count * 12;
     int rc = ensure_stage(d, bytes); if (rc) return rc;
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
@@ -487,21 +514,21 @@ extern "C" int gne_pot_update_fused(gne_dev *d, int64_t nNodes, const int32_t *n
     const bool full = nFinal < 0;
     const int64_t nf = full ? 0 : nFinal;
     const size_t bytes = (size_t) nNodes * 24 + (size_t) nTheta * 12 + (size_t) nf * 4 + 64;
-    if (nNodes == 0 && nTheta == 0 && nf == 0 && !full) return gne_dev_flush(d);
+    if (nNodes == 0 && nTheta == 0 && nf == 0 && !full) return GNE_OK;       // queued set-mirror writes ride with the next pass
+    if (d->havePendingSmall) { int rcf = flush_pending(d); if (rcf) return rcf; }   // two updates without a pass in between: in order
     if (!full && nNodes <= SU_NODES && nTheta <= SU_THETAS && nf <= SU_FINAL) {
-        // tiny update: everything as kernel arguments (no staging buffer, no host memory reads)
-        SmallUpdate su;
+        // tiny update: everything as kernel arguments (no staging buffer, no host memory reads).  Not launched here:
+        // the next streamed LV pass applies it itself (gne_stream.cuh); any other reader of the state launches it
+        // first as k_update_small (flush_pending).
+        SmallUpdate &su = d->pendingSmall;
         NbWriteOps &q = pending_of(d);
         su.ops = q;
         su.nNodes = (int) nNodes; su.nTheta = (int) nTheta; su.nFinal = (int) nf; su.pad = 0;
         for (int64_t i = 0; i < nNodes; ++i) { su.node[i] = node[i]; su.a0[i] = a0[i]; su.a1[i] = a1[i]; su.slot[i] = slot[i]; }
         for (int64_t i = 0; i < nTheta; ++i) { su.tslot[i] = tslot[i]; su.theta[i] = theta[i]; }
         for (int64_t i = 0; i < nf; ++i) su.fnode[i] = fnode[i];
-        NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
-        k_update_small<<<1, 256, 0, d->stream>>>(mm, su, d->a0, d->a1, d->slot, d->theta, d->pi);
-        CK(cudaGetLastError());
+        d->havePendingSmall = true;
         d->lastSmall = su; d->lastSmall.ops.n = 0; d->haveLastSmall = true;     // replayable (idempotent) by the bench helper
-        ++d->launches;
         d->h2dBytes += 25 * q.n + 24 * nNodes + 12 * nTheta + 4 * nf;
         q.n = 0;
         return GNE_OK;
@@ -549,6 +576,7 @@ extern "C" int gne_pot_update_fused(gne_dev *d, int64_t nNodes, const int32_t *n
 extern "C" int gne_pot_finalize(gne_dev *d)
 {
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     k_pot_finalize<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi);
     CK(cudaGetLastError());
     ++d->launches;
@@ -559,6 +587,7 @@ extern "C" int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const
 {
     if (count <= 0) return GNE_OK;
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     const size_t bytes = (size_t) count * 12;
     int rc = ensure_stage(d, bytes); if (rc) return rc;
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
@@ -578,6 +607,7 @@ extern "C" int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const
 extern "C" int gne_pot_set_all(gne_dev *d, const double *pi)
 {
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     CK(cudaMemcpyAsync(d->pi, pi, 8 * (size_t) d->n, cudaMemcpyHostToDevice, d->stream));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->h2dBytes += 8 * (int64_t) d->n;
@@ -587,6 +617,7 @@ extern "C" int gne_pot_set_all(gne_dev *d, const double *pi)
 extern "C" int gne_pot_get_all(gne_dev *d, double *pi)
 {
     CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
     CK(cudaMemcpyAsync(pi, d->pi, 8 * (size_t) d->n, cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->d2hBytes += 8 * (int64_t) d->n;
@@ -675,14 +706,13 @@ static bool replay_band_rule(const int64_t *pos, const double *viol, int64_t cnt
     return true;
 }
 
-// Large shards go through the TMA-streamed persistent kernel, small ones (or a handle whose streamed
-// lists keep overflowing) through the one-CTA-per-tile kernel.
+// The LV pass is the streamed one-launch kernel (gne_stream.cuh) unless the per-tile kernels were asked for
+// (gne_dev_set_lv_kernel / GNE_LV_KERNEL=tiles) or the handle's streamed lists keep overflowing (hold-off).
 static bool use_stream_kernel(const gne_dev *d)
 {
-    const int64_t len = std::min(d->N, d->hi) - d->lo;
-    if (d->lvKernelMode == 1 || len <= 0) return false;
+    if (d->lvKernelMode == 1) return false;
     if (d->lvKernelMode == 2) return true;
-    return d->streamHoldoff == 0 && len >= (int64_t) 8 * d->streamGrid * ST_TILE;
+    return d->streamHoldoff == 0;
 }
 
 // Launch on the handle's stream; with `dependent` the kernel may become resident while its predecessor
@@ -705,36 +735,69 @@ static cudaError_t launch_k(gne_dev *d, bool dependent, void (*kernel)(KArgs...)
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEvent_t evB, bool withExchange = true)
+// One LV pass over this shard.  Streamed kernel: ONE launch - it applies the queued argument-only update (or `replay`,
+// the bench helper's idempotent copy of the last one) and the queued set-mirror writes itself, prices, reduces in its
+// last CTA and, sharded over peer mailboxes, exchanges + merges there too (result block in d->lvRes either way).
+// Per-tile kernels: queued work is launched first, then tiles + finish (+ a stand-alone exchange by the caller).
+static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEvent_t evB, bool withExchange = true,
+                          const SmallUpdate *replay = nullptr)
 {
-    const int G = tiles_for(d);
-    NbView nb = view_of(d);
-    if (evA) CK(cudaEventRecord(evA, d->stream));
     d->lastWasStream = use_stream_kernel(d);
     d->exchangeFused = false;
     if (d->lastWasStream) {
-        const int64_t numTiles = (nb.end - nb.lo + ST_TILE - 1) / ST_TILE;
+        static thread_local SmallUpdate su;
+        const bool fromPending = !replay && d->havePendingSmall;
+        if (replay) su = *replay;
+        else if (fromPending) su = d->pendingSmall;
+        else { su.ops.n = 0; su.nNodes = su.nTheta = su.nFinal = su.pad = 0; }
+        NbWriteOps &q = pending_of(d);
+        if (q.n > 0) {
+            // set-mirror writes queued after the update: fold them in (a later write to a position replaces the earlier one)
+            bool fits = true;
+            NbWriteOps merged = su.ops;
+            for (int k = 0; k < q.n && fits; ++k) {
+                int i = -1;
+                for (int j = 0; j < merged.n; ++j) if (merged.local[j] == q.local[k]) i = j;
+                if (i < 0) { if (merged.n == 8) { fits = false; break; } i = merged.n++; }
+                merged.local[i] = q.local[k]; merged.tail[i] = q.tail[k]; merged.head[i] = q.head[k];
+                merged.cost[i] = q.cost[k]; merged.mult[i] = q.mult[k]; merged.state[i] = q.state[k];
+            }
+            if (fits) { su.ops = merged; d->h2dBytes += 25 * q.n; q.n = 0; }
+            else {                                       // too many: launch everything queued, the pass carries nothing
+                int rc = flush_pending(d); if (rc) return rc;
+                if (!replay) { su.ops.n = 0; su.nNodes = su.nTheta = su.nFinal = 0; }
+            }
+        }
+        if (fromPending) d->havePendingSmall = false;
+        NbView nb = view_of(d);
+        const int64_t numTiles = nb.end > nb.lo ? (nb.end - nb.lo + ST_TILE - 1) / ST_TILE : 0;
         LvFused f;
         memset(&f, 0, sizeof(f));
+        f.ticket = d->lvTicket; f.arrive = d->lvArrive; f.tileCtr = d->lvTileCtr; f.updFlag = d->lvUpdFlag;
         f.res = target; f.seq = ++d->lvSeq; f.resOnHost = (target == d->lvRes) ? 1 : 0;
+        f.single = numTiles <= (int64_t) d->streamGrid ? 1 : 0;
         f.nranks = 1;
         if (withExchange && d->nranks > 1 && d->p2p) {
-            // sharded over peer mailboxes - one launch: pricing, reduction by the last CTA, exchange
-            f.ticket = d->lvTicket;
+            // sharded over peer mailboxes: the last CTA exchanges the shard's record, merges the ranks' records and
+            // publishes the merged block where the host polls
             f.nranks = d->nranks; f.rank = d->rank; f.peers = (Mailbox *const *) d->peersDev;
-            f.hostOut = (ShardRecord *) d->gatherHost;
-            f.hostSeq = reinterpret_cast<unsigned long long *>((char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
+            f.hostOut = d->lvRes;
             f.xseq = ++d->xseq; f.xTimeout = d->xTimeoutCycles;
             d->exchangeFused = true;
         }
-        CK(launch_k(d, true, k_price_lv_stream, dim3(d->streamGrid), dim3(ST_THREADS), ST_SMEM, nb, (const double *) d->pi, d->lvc, numTiles, f));
+        NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
+        PotMut pm; pm.a0 = d->a0; pm.a1 = d->a1; pm.slot = d->slot; pm.theta = d->theta; pm.pi = d->pi;
+        const int grid = f.single ? (int) std::max<int64_t>(1, numTiles) : d->streamGrid;
+        if (evA) CK(cudaEventRecord(evA, d->stream));
+        k_price_lv_stream<<<grid, ST_BLOCK, ST_SMEM, d->stream>>>(nb, (const double *) d->pi, d->lvc, numTiles, f, su, mm, pm);
+        CK(cudaGetLastError());
         ++d->launches;
         if (evB) CK(cudaEventRecord(evB, d->stream));
-        if (!d->exchangeFused) {
-            CK(launch_k(d, true, k_price_lv_reduce, dim3(1), dim3(ST_THREADS), 0, d->lvc, d->streamGrid, f));
-            ++d->launches;
-        }
     } else {
+        int rc = flush_pending(d); if (rc) return rc;
+        const int G = tiles_for(d);
+        NbView nb = view_of(d);
+        if (evA) CK(cudaEventRecord(evA, d->stream));
         if (G > 0) { CK(launch_k(d, true, k_price_lv_tiles, dim3(G), dim3(TILE_THREADS), 0, nb, (const double *) d->pi, d->lv)); ++d->launches; }
         if (evB) CK(cudaEventRecord(evB, d->stream));
         CK(launch_k(d, true, k_price_lv_finish, dim3(1), dim3(FIN_THREADS), 0, d->lv, G, d->lo, target, (unsigned long long) ++d->lvSeq));
@@ -747,8 +810,10 @@ static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEve
 
 static int price_lv_local(gne_dev *d)
 {
-    // fused pass over this shard: result in d->lvRes (mapped pinned) with sequence number d->lvSeq
-    int rc = launch_lv_pass(d, d->nranks > 1 ? d->lvResDev : d->lvRes, d->timing ? d->ev0 : nullptr, nullptr);
+    // one pass over this shard: result in d->lvRes (mapped pinned) with sequence number d->lvSeq - single GPU, or
+    // sharded with the exchange fused into the pass; otherwise in d->lvResDev for the stand-alone exchange
+    const bool hostBlock = d->nranks == 1;
+    int rc = launch_lv_pass(d, hostBlock ? d->lvRes : d->lvResDev, d->timing ? d->ev0 : nullptr, nullptr);
     if (rc) return rc;
     if (d->timing) CK(cudaEventRecord(d->ev1, d->stream));
     return GNE_OK;
@@ -790,23 +855,29 @@ static int wait_lv_result(gne_dev *d)
 // element are needed — k_viol_select resolves them from the tile offsets.
 static const int64_t LV_DEVICE_LIST_MIN = 4096;
 
+static int launch_shard_exchange(gne_dev *d);
+static int sharded_band_fallback(gne_dev *d, double M, std::vector<int64_t> &list, double *largest);
+
 extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t *count, int *any)
 {
     CK(cudaSetDevice(d->device));
-    int rc = gne_dev_flush(d); if (rc) return rc;
-    rc = price_lv_local(d); if (rc) return rc;
-    if (d->nranks == 1) { rc = wait_lv_result(d); if (rc) return rc; }
+    int rc = price_lv_local(d); if (rc) return rc;       // (queued updates ride with the pass or are launched ahead of it)
     d->lvMode = 0; d->lvList.clear(); d->lvCount = 0;
     double L = -1.0;
     int anyV = 0;
-    if (d->nranks > 1) {
+    if (d->nranks > 1 && !d->p2p) {
+        // records through ncclAllGather / the host program's all-gather, merged on the host
         rc = gne_dev_price_lv_sharded(d, &L, d->lvList, &anyV); if (rc) return rc;
     } else {
+        // single GPU, or sharded over peer mailboxes (the merged block arrives like a single GPU's)
+        if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
+        rc = wait_lv_result(d); if (rc) return rc;
         const LvResult *r = d->lvRes;
+        if (r->overflow == XCHG_TIMEOUT) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
         d->d2hBytes += 24 + 16 * std::min<int64_t>(r->count, LV_LIST_CAP);
         anyV = r->any;
         bool ok = !anyV;
-        if (d->lastWasStream) {
+        if (d->lastWasStream && d->nranks == 1) {
             // a streamed pass whose per-CTA lists overflow repeatedly (values rising along the list) is
             // cheaper through the per-tile kernel: hold the streamed kernel off for a while
             if (anyV && r->overflow) { if (++d->streamOverflows >= 3) { d->streamHoldoff = 256; d->streamOverflows = 0; } }
@@ -814,6 +885,7 @@ extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t 
         }
         if (anyV && !r->overflow) ok = replay_band_rule(r->pos, r->viol, r->count, r->maxViol - LV_BAND, false, d->lvList, &L);
         const double M = anyV ? r->maxViol : 0.0;
+        if (!ok && d->nranks > 1) { rc = sharded_band_fallback(d, M, d->lvList, &L); if (rc) return rc; ok = true; }
         // fallback: widen the band until the replay is provably exact
         double width = 16.0 * GNE_ROUNDOFF_TOLERANCE;
         while (!ok) {
@@ -1068,7 +1140,6 @@ extern "C" int gne_price_scan_list(gne_dev *d, int64_t cursor, int64_t want, int
 // ------------------------------------------------------------------------------------------
 // bench helper
 // ------------------------------------------------------------------------------------------
-static int launch_shard_exchange(gne_dev *d);
 
 #ifdef GNE_TUNING
 // tuning harness: the LV tile kernel and its experimental variants, each timed `reps` times
@@ -1079,7 +1150,7 @@ static const char *g_variantNames[] = {
     "tma<256thr,4it,3st> 148x2", "tma<256thr,4it,4st> 148x2", "tma<256thr,2it,6st> 148x2", "tma<256thr,2it,4st> 148x4", "tma<256thr,2it,3st> 148x5",
     "tma<512thr,2it,4st> 148x2", "tma<128thr,4it,4st> 148x4", "tma<256thr,1it,8st> 148x4", "tma<512thr,2it,3st> 148x2", "tma<256thr,2it,8st> 148x2",
     "tma<256thr,4it,3st> 148x1", "production k_price_lv_stream", "k_price_lv_finish (per-tile records, mapped host result)",
-    "k_price_lv_reduce (per-CTA records, mapped host result)", "k_price_lv_stream + last-CTA reduction (sharded form, device result)", "k_update_small replay" };
+    "(unused)", "production k_price_lv_stream, result block in device memory", "k_update_small replay" };
 extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVariants, int *nVariants)
 {
     CK(cudaSetDevice(d->device));
@@ -1129,26 +1200,12 @@ extern "C" int gne_bench_variants(gne_dev *d, int reps, float *msOut, int maxVar
               GNE_TMA_CASE(23, 256, 4, 3, 1, 1)
 #undef GNE_TMA_CASE
               case 24: case 26: case 27: {
-                  // 24: production streaming pass (per-CTA records); 26: the reduction kernel that follows it on one GPU;
-                  // 27: the sharded form - pricing + last-CTA reduction in one launch (result block in device memory)
-                  LvFused f; memset(&f, 0, sizeof(f));
+                  // 24 / 27: the production one-launch pass (no folded update; result block on the host / on the device); 26: unused
+                  if (v == 26) break;
                   if (!d->lvResDev) cudaMalloc(&d->lvResDev, sizeof(LvResult));
-                  f.res = (v == 27) ? d->lvResDev : d->lvRes; f.seq = ++d->lvSeq; f.resOnHost = (v == 27) ? 0 : 1; f.nranks = 1;
-                  if (v == 27) f.ticket = d->lvTicket;
-#ifdef GNE_STAMPS
-                  static long long *stampsDev = nullptr;
-                  if (!stampsDev) { cudaMalloc(&stampsDev, 64); cudaMemset(stampsDev, 0, 64); }
-                  f.stamps = stampsDev;
-#endif
-                  if (v == 26) k_price_lv_reduce<<<1, ST_THREADS, 0, d->stream>>>(d->lvc, d->streamGrid, f);
-                  else k_price_lv_stream<<<d->streamGrid, ST_THREADS, ST_SMEM, d->stream>>>(nb, d->pi, d->lvc, (len + ST_TILE - 1) / ST_TILE, f);
-#ifdef GNE_STAMPS
-                  if (r == reps + 1 && v == 27) {
-                      long long h[8]; cudaMemcpy(h, stampsDev, 64, cudaMemcpyDeviceToHost);
-                      fprintf(stderr, "[stamps] epilogue+ticket %lld  fence+loads %lld  reduce+sort %lld  publish+fence %lld  total %lld cycles\n",
-                              h[1] - h[0], h[2] - h[1], h[4] - h[3], h[5] - h[4], h[7] - h[0]);
-                  }
-#endif
+                  const int keep = d->lvKernelMode; d->lvKernelMode = 2;
+                  launch_lv_pass(d, v == 27 ? d->lvResDev : d->lvRes, nullptr, nullptr, false);
+                  d->lvKernelMode = keep;
               } break;
               case 25: k_price_lv_finish<<<1, FIN_THREADS, 0, d->stream>>>(d->lv, (int) ((len + TILE - 1) / TILE), d->lo, d->lvRes, ++d->lvSeq); break;
               case 28: { NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
@@ -1183,9 +1240,12 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
     }
     if (!d->ev2) { CK(cudaEventCreate(&d->ev2)); CK(cudaEventCreate(&d->ev3)); }
     while ((int) d->benchEv.size() < 2 * reps) { cudaEvent_t e; CK(cudaEventCreate(&e)); d->benchEv.push_back(e); }
+    // the relabel of a typical pivot of this window: the last argument-only update, replayed (idempotent).  The
+    // streamed kernel applies it itself (one launch per step, as in the solver); the per-tile path launches it first.
+    const bool replay = withFinalize == 2 && d->haveLastSmall;
     auto relabel = [&]() {
-        if (withFinalize == 2 && d->haveLastSmall) {
-            // the relabel of a typical pivot of this window: the last argument-only update, replayed (idempotent)
+        if (replay) {
+            if (use_stream_kernel(d)) return;
             NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
             k_update_small<<<1, 256, 0, d->stream>>>(mm, d->lastSmall, d->a0, d->a1, d->slot, d->theta, d->pi);
             ++d->launches;
@@ -1193,18 +1253,18 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
     };
     // The steps are queued back to back and the host synchronises once per loop: per-step host wake-ups
     // would put their jitter into every cross-rank exchange of a sharded run (the early rank waits inside
-    // its kernel for the late one).  Loop 0 brackets the pricing kernel alone (an event between two kernels
-    // serialises them fully, and the exchange stays in its own kernel); loop 1 is the step as the solver
-    // launches it - no events inside, the kernels chained by PDL, the exchange fused where it can be.
+    // its kernel for the late one).  Loop 0 brackets the pricing kernel alone, without the cross-rank exchange
+    // (relabel, pass and reduction are one kernel); loop 1 is the step as the solver launches it.
     for (int pass = 0; pass < 2; ++pass) {
         for (int i = 0; i < reps; ++i) {
             if (flushL2) { k_flush_l2<<<148 * 8, 256, 0, d->stream>>>(d->flushBuf, d->flushLen); ++d->launches; }
             if (pass == 1) CK(cudaEventRecord(d->benchEv[2 * i], d->stream));
             relabel();
-            rc = launch_lv_pass(d, d->nranks > 1 ? d->lvResDev : d->lvRes, pass == 0 ? d->benchEv[2 * i] : nullptr,
-                                pass == 0 ? d->benchEv[2 * i + 1] : nullptr, pass == 1);
+            const bool hostBlock = d->nranks == 1;
+            rc = launch_lv_pass(d, hostBlock ? d->lvRes : d->lvResDev, pass == 0 ? d->benchEv[2 * i] : nullptr,
+                                pass == 0 ? d->benchEv[2 * i + 1] : nullptr, pass == 1, replay ? &d->lastSmall : nullptr);
             if (rc) return rc;
-            if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
+            if (d->nranks > 1 && pass == 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
             if (pass == 1) CK(cudaEventRecord(d->benchEv[2 * i + 1], d->stream));
         }
         CK(cudaGetLastError());
@@ -1231,16 +1291,18 @@ __global__ void k_pack_record(const LvResult *res, ShardRecord *rec) { pack_reco
 
 // Stand-alone exchange step (after the per-tile reduction kernel; the TMA-streamed pass runs the same
 // exchange from its own last CTA): pack the shard's record, then exchange_record (gne_exchange.cuh).
-__global__ void __launch_bounds__(128)
-k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, unsigned long long seq, ShardRecord *hostOut,
-              unsigned long long *hostSeq, long long timeoutCycles)
+__global__ void __launch_bounds__(256)
+k_lv_exchange(const LvResult *res, Mailbox *const *peers, int rank, int nranks, unsigned long long xseq, LvResult *hostOut,
+              unsigned long long outSeq, long long timeoutCycles)
 {
     __shared__ ShardRecord rec;
     __shared__ int sTimeout;
+    __shared__ int64_t mPos[MAX_RANKS * SHARD_LIST];
+    __shared__ double mViol[MAX_RANKS * SHARD_LIST];
     pdl_wait();                                         // the shard's reduction has published its result block
     pack_record(res, &rec, threadIdx.x);
-    __syncthreads();
-    exchange_record(&rec, peers, rank, nranks, seq, hostOut, hostSeq, &sTimeout, timeoutCycles);
+    xchg_sync();
+    exchange_merge(&rec, peers, rank, nranks, xseq, hostOut, outSeq, &sTimeout, timeoutCycles, mPos, mViol);
 }
 // all-gather of one 128-byte blob per rank through the peer mailboxes (same protocol as k_lv_exchange)
 __global__ void __launch_bounds__(64)
@@ -1488,10 +1550,9 @@ static int launch_shard_exchange(gne_dev *d)
 {
     if (d->exchangeFused) return GNE_OK;                // the pricing kernel's last CTA has already done it
     if (d->p2p) {
-        // fused pack + NVLink peer stores + flag wait + copy to mapped pinned host: one kernel
-        unsigned long long *hostSeq = reinterpret_cast<unsigned long long *>((char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
-        CK(launch_k(d, true, k_lv_exchange, dim3(1), dim3(128), 0, (const LvResult *) d->lvResDev, (Mailbox *const *) d->peersDev, d->rank, d->nranks,
-                    (unsigned long long) ++d->xseq, (ShardRecord *) d->gatherHost, hostSeq, d->xTimeoutCycles));
+        // pack + NVLink peer stores + flag wait + merge + merged block to mapped pinned host: one kernel
+        CK(launch_k(d, true, k_lv_exchange, dim3(1), dim3(256), 0, (const LvResult *) d->lvResDev, (Mailbox *const *) d->peersDev, d->rank, d->nranks,
+                    (unsigned long long) ++d->xseq, d->lvRes, d->lvSeq, d->xTimeoutCycles));
         ++d->launches;
         return GNE_OK;
     }
@@ -1555,18 +1616,34 @@ static int sharded_gather_lists(gne_dev *d, int64_t localCount, std::vector<int6
     return GNE_OK;
 }
 
+// Fallback of a sharded pass (long tie lists, overflowed records): every rank compacts its shard down to a widening band
+// below the global maximum M, the lists are all-gathered, and the sequential rule is replayed on the union.  Every rank
+// takes the same branch (same merged block), so no rank can be left waiting.
+static int sharded_band_fallback(gne_dev *d, double M, std::vector<int64_t> &list, double *largest)
+{
+    double width = 16.0 * GNE_ROUNDOFF_TOLERANCE;
+    std::vector<int64_t> gp;
+    std::vector<double> gv;
+    while (true) {
+        double floorV = M - width;
+        bool zero = false;
+        if (!(floorV > 0.0) || width > 1.0e-6) { floorV = 0.0; zero = true; }
+        int64_t localCount = 0;
+        int rc = viol_compact_device(d, floorV, &localCount); if (rc) return rc;
+        rc = sharded_gather_lists(d, localCount, gp, gv); if (rc) return rc;
+        if (replay_band_rule(gp.data(), gv.data(), (int64_t) gp.size(), floorV, zero, list, largest)) break;
+        width *= 64.0;
+    }
+    return GNE_OK;
+}
+
+// Sharded pass WITHOUT peer mailboxes (GNE_EXCHANGE=nccl / host, or IPC mapping refused): the per-shard records are
+// all-gathered (ncclAllGather or the host program's callback) and merged on the host by every rank.
 int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &list, int *any)
 {
-    // price_lv_local has been launched by the caller; exchange, then the same merge on every rank
+    // price_lv_local has been launched by the caller
     int rcx = launch_shard_exchange(d); if (rcx) return rcx;
-    if (d->p2p) {
-        const volatile unsigned long long *hostSeq =
-            reinterpret_cast<const volatile unsigned long long *>((const char *) d->gatherHost + sizeof(ShardRecord) * (size_t) d->nranks);
-        rcx = wait_host_seq(d, hostSeq, d->xseq); if (rcx) return rcx;
-        if (hostSeq[1] != 0ull) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
-    } else {
-        CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
-    }
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->d2hBytes += sizeof(ShardRecord) * (int64_t) d->nranks;
     const ShardRecord *rec = (const ShardRecord *) d->gatherHost;
     // scratch kept across pivots (no allocation on the per-pivot path)
@@ -1587,24 +1664,9 @@ int gne_dev_price_lv_sharded(gne_dev *d, double *largest, std::vector<int64_t> &
                                  largest, &cnt, outPos.data(), (int64_t) outPos.size(), any, &need);
     if (rc) return rc;
     if (!need) { list.assign(outPos.begin(), outPos.begin() + cnt); return GNE_OK; }
-    // fallback (long tie lists): every rank compacts its shard down to a widening band below the
-    // global maximum, the lists are all-gathered, and the sequential rule is replayed on the union
     double M = -1.0;
     for (int k = 0; k < d->nranks; ++k) if (anys[k] && maxima[k] > M) M = maxima[k];
-    double width = 16.0 * GNE_ROUNDOFF_TOLERANCE;
-    std::vector<int64_t> gp;
-    std::vector<double> gv;
-    while (true) {
-        double floorV = M - width;
-        bool zero = false;
-        if (!(floorV > 0.0) || width > 1.0e-6) { floorV = 0.0; zero = true; }
-        int64_t localCount = 0;
-        rc = viol_compact_device(d, floorV, &localCount); if (rc) return rc;
-        rc = sharded_gather_lists(d, localCount, gp, gv); if (rc) return rc;
-        if (replay_band_rule(gp.data(), gv.data(), (int64_t) gp.size(), floorV, zero, list, largest)) break;
-        width *= 64.0;
-    }
-    return GNE_OK;
+    return sharded_band_fallback(d, M, list, largest);
 }
 
 // Host-only: merge per-shard records.  counts[r] < 0 marks an overflowed shard.

@@ -3,12 +3,15 @@
 // Every rank prices a contiguous position range of setNBarc; what the ranks exchange per pivot is one
 // fixed-size record {shard maximum, in-band candidates in position order}.  The records travel as plain
 // stores into the peers' mailboxes (device memory mapped through CUDA IPC, i.e. NVLink / NVSwitch peer
-// writes), followed by a sequence flag; the receiving side polls its own mailbox.  No copy engine, no
-// collective library on this path.  Included by the pricing kernels so that the last CTA of a pass can
-// run the exchange itself (gne_stream.cuh) and by the stand-alone exchange kernel (gne_device.cu).
+// writes), followed by a sequence flag; the receiving side polls its own mailbox and MERGES the ranks'
+// records on the device (global maximum, candidates within the band of it in rank = position order), so
+// that the host reads the same small result block as on one GPU instead of nranks records.  No copy
+// engine, no collective library on this path.  Included by the pricing kernel, whose last CTA runs the
+// exchange itself (gne_stream.cuh), and by the stand-alone exchange kernel (gne_device.cu).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "gne_kernels.cuh"
 
 constexpr int SHARD_LIST = 48;                          // candidates carried per rank in the record
 constexpr int MAX_RANKS = 8;
@@ -30,52 +33,105 @@ struct Mailbox {
 };
 
 constexpr unsigned long long XCHG_POISON = ~0ull;       // flag value a timed-out rank leaves with every peer: they fail in the same pass
+constexpr int XCHG_TIMEOUT = 2;                         // LvResult::overflow value reporting that a peer never answered
 
-// Whole CTA.  `rec` (shared memory, complete and visible to the block) is stored into every rank's
-// mailbox, the sequence flag published, the peers' flags awaited (timeoutCycles, default ~4 s: a dead peer
-// fails the pass instead of hanging it; the rank that gives up poisons its flag at every peer so that they
-// give up in the same pass), and all records copied to mapped pinned host memory; hostSeq[0] is written
-// last, after system-scope fences by every writer, so the host can poll it instead of synchronising;
-// hostSeq[1] = 1 reports the timeout.
-__device__ __forceinline__ void exchange_record(const ShardRecord *rec, Mailbox *const *peers, int rank, int nranks,
-                                                unsigned long long seq, ShardRecord *hostOut, unsigned long long *hostSeq,
-                                                int *sTimeout, long long timeoutCycles)
+// 256 threads synchronised through named barrier 1 (the consumer threads of the pricing kernel, or the
+// whole block of the stand-alone exchange kernel).
+__device__ __forceinline__ void xchg_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// `rec` (shared memory, complete and visible to the 256 threads) is stored into every rank's mailbox, the
+// sequence flag published, the peers' flags awaited (timeoutCycles, default ~4 s: a dead peer fails the pass
+// instead of hanging it; the rank that gives up poisons its flag at every peer so that they give up in the
+// same pass).  Then the merge every rank computes identically: M = max over the ranks' maxima, the ranks'
+// in-band candidates concatenated in rank order (= position order), overflow if an in-band rank overflowed.
+// The merged block goes to `out` (mapped pinned host memory) - entries, header, a system-scope fence by every
+// writer, then out->seq = outSeq, which the host polls.  mPos / mViol: shared scratch for nranks x SHARD_LIST.
+__device__ __forceinline__ void exchange_merge(const ShardRecord *rec, Mailbox *const *peers, int rank, int nranks,
+                                               unsigned long long xseq, gne::LvResult *out, unsigned long long outSeq,
+                                               int *sTimeout, long long timeoutCycles, int64_t *mPos, double *mViol)
 {
-    const int t = threadIdx.x, nthr = blockDim.x;
-    const int b = (int) (seq & 1ull);
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    constexpr int NT = 256;
+    const int b = (int) (xseq & 1ull);
     constexpr int WORDS = (int) (sizeof(ShardRecord) / 8);
     const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
+    const int words = 3 + 2 * SHARD_LIST;               // (the whole record: positions and violations are contiguous)
+    static_assert(WORDS == 3 + 2 * SHARD_LIST, "ShardRecord layout");
     for (int p = 0; p < nranks; ++p) {
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(&peers[p]->rec[b][rank]);
-        for (int w = t; w < WORDS; w += nthr) dst[w] = src[w];
+        for (int i = t; i < words; i += NT) dst[i] = src[i];
     }
     if (t == 0) *sTimeout = 0;
     __threadfence_system();
-    __syncthreads();
-    if (t < nranks) *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[b][rank]) = seq;
+    xchg_sync();
+    if (t < nranks) *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[b][rank]) = xseq;
     Mailbox *self = peers[rank];
     if (t < nranks) {
         const long long t0 = clock64();
         while (true) {
             const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&self->flag[b][t]);
-            if (v == seq) break;
+            if (v == xseq) break;
             if (v == XCHG_POISON || clock64() - t0 > timeoutCycles) { *sTimeout = 1; break; }
         }
     }
-    __syncthreads();
+    xchg_sync();
     if (*sTimeout && t < nranks) {                      // fail fast everywhere: both generations of our flag at every peer
         *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[0][rank]) = XCHG_POISON;
         *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[1][rank]) = XCHG_POISON;
     }
     __threadfence_system();
-    for (int r = 0; r < nranks; ++r) {
-        const volatile unsigned long long *in = reinterpret_cast<const volatile unsigned long long *>(&self->rec[b][r]);
-        unsigned long long *out = reinterpret_cast<unsigned long long *>(&hostOut[r]);
-        for (int w = t; w < WORDS; w += nthr) out[w] = in[w];
+    // ---- merge (identical on every rank)
+    __shared__ double sMax[MAX_RANKS];
+    __shared__ int sAnyR[MAX_RANKS], sOvfR[MAX_RANKS], sCntR[MAX_RANKS], sWarpTot[NT / 32], sCarry;
+    if (t < nranks) {
+        const volatile ShardRecord *r = &self->rec[b][t];
+        sMax[t] = r->maxViol; sAnyR[t] = r->any; sOvfR[t] = r->overflow; sCntR[t] = (int) r->count;
     }
-    __syncthreads();
-    if (t == 0) hostSeq[1] = *sTimeout ? 1ull : 0ull;
-    __threadfence_system();
-    __syncthreads();
-    if (t == 0) *reinterpret_cast<volatile unsigned long long *>(hostSeq) = seq;
+    if (t == 0) sCarry = 0;
+    xchg_sync();
+    double M = -1.0;
+    bool any = false;
+    for (int r = 0; r < nranks; ++r) if (sAnyR[r]) { any = true; M = fmax(M, sMax[r]); }
+    const double thr = __dsub_rn(M, gne::LV_BAND);
+    bool bad = false;
+    for (int r = 0; r < nranks; ++r) if (sAnyR[r] && sMax[r] >= thr && sOvfR[r]) bad = true;
+    int total = 0;
+    if (any && !bad) {
+        for (int base = 0; base < nranks * SHARD_LIST; base += NT) {
+            const int idx = base + t, r = idx / SHARD_LIST, i = idx % SHARD_LIST;
+            int keep = 0;
+            int64_t p = 0;
+            double v = 0.0;
+            if (r < nranks && sAnyR[r] && sMax[r] >= thr && i < sCntR[r]) {
+                v = *reinterpret_cast<const volatile double *>(&self->rec[b][r].viol[i]);
+                p = *reinterpret_cast<const volatile int64_t *>(&self->rec[b][r].pos[i]);
+                keep = v >= thr;
+            }
+            int inc = keep;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+            if (lane == 31) sWarpTot[w] = inc;
+            xchg_sync();
+            int off = sCarry, tot = 0;
+#pragma unroll
+            for (int q = 0; q < NT / 32; ++q) { if (q < w) off += sWarpTot[q]; tot += sWarpTot[q]; }
+            if (keep) { mPos[off + inc - 1] = p; mViol[off + inc - 1] = v; }
+            xchg_sync();
+            if (t == 0) sCarry += tot;
+            xchg_sync();
+        }
+        total = sCarry;
+    }
+    // ---- publish (one warp; every writing lane fences its own stores, then the sequence number)
+    if (w == 0) {
+        const int nOut = (any && !bad) ? total : 0;
+        for (int r = lane; r < nOut; r += 32) { out->pos[r] = mPos[r]; out->viol[r] = mViol[r]; }
+        if (lane == 0) {
+            out->maxViol = any ? M : -1.0; out->any = any ? 1 : 0; out->count = nOut;
+            out->overflow = *sTimeout ? XCHG_TIMEOUT : (bad ? 1 : 0);
+        }
+        if (lane == 0 || lane < nOut) __threadfence_system();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&out->seq) = outSeq;
+    }
 }

@@ -1,35 +1,43 @@
-// genneteq_b200 — the LV (Dantzig) pricing pass for large shards: persistent CTAs, the five arc
-// columns streamed into shared memory by the TMA engine (cp.async.bulk + mbarrier, 3 stages), and
-// only the pi gathers on the LSU / L1TEX path.
+// genneteq_b200 — the LV (Dantzig) pricing pass, ONE launch per pivot: persistent warp-specialised CTAs.
 //
-// Why: the per-tile kernel (k_price_lv_tiles) is bound by L1TEX wavefronts with a dependent
-// chain index load -> gather.  Staging the columns through the async proxy takes the streaming
-// loads off that chain: with 3 stages in flight a CTA always finds its indices in shared memory
-// and issues its gathers at once.  Measured on B200 (profiles/r1_variants_c3.txt): 108.3 us per
-// 20M-arc pass with 16 warps/SM against 113.5 us for the per-tile kernel with 64 warps/SM;
-// 2 stages or >150 KB of staging (which starves the L1 the gathers live in) are 50 % slower.
+//   producer warp   one elected thread takes the next tile from a device-wide counter (dynamic scheduling: no CTA
+//                   is left with one tile more than its neighbours) and streams the tile's five arc columns into
+//                   shared memory with the TMA engine (cp.async.bulk + mbarrier complete_tx, 3 stages);
+//   consumer warps  (8 x 32 threads) wait for a stage, read their indices from shared memory, gather pi[tail] /
+//                   pi[head] through the LSU (the only L1TEX traffic left), compute the violation and release the
+//                   stage through an "empty" mbarrier - no block-wide barrier per tile, warps drift freely.
 //
-// Reduction: each thread keeps its largest and second-largest violation in registers; once per CTA
-// the threads within the band of the CTA maximum are recorded (CtaRec + candidate arrays).  The last
-// CTA to finish (ticket counter) reduces the per-CTA records to the exact global maximum and the
-// in-band list in position order, publishes the result block, and - in a sharded run - exchanges the
-// shard's record with the peer GPUs from the same kernel (gne_exchange.cuh): one launch per pass.
-// A violator can never be skipped wrongly; a list that overflows is reported and the caller falls
-// back to the ordered compaction.
+// What used to be three launches per pivot is folded into this kernel:
+//   * the relabel of the last pivot (k_update_small: <= 8 set-mirror records, <= 48 node records, <= 16 thetas,
+//     <= 160 potentials to finalize, all as kernel arguments) is applied by the first CTA to arrive while every
+//     CTA's TMA prologue is already in flight; the others wait for its release flag only before their first
+//     gather, and patch the (at most 8) rewritten arc records into their registers where a tile holds one;
+//   * the reduction over the per-CTA records is run by the last CTA to finish (ticket counter), which also resets
+//     the counters for the next pass, publishes the result block to mapped pinned host memory and - in a sharded
+//     run - exchanges the shard's record with the peer GPUs and merges theirs (gne_exchange.cuh).
+//
+// Reduction: each thread keeps its largest and second-largest violation in registers; once per CTA the threads
+// within the band of the CTA maximum are recorded (CtaRec + candidate arrays).  Lists no longer than the grid
+// (one tile per CTA: "single" mode) keep all four values of a thread, so every in-band candidate is recorded
+// exactly.  A violator can never be skipped wrongly; a list that overflows is reported and the caller falls back
+// to the ordered compaction.
 #pragma once
 #include "gne_kernels.cuh"
 #include "gne_exchange.cuh"
 
 namespace gne {
 
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 256;                         // consumer threads
+constexpr int ST_PRODUCER = 32;                         // + one producer warp
+constexpr int ST_BLOCK = ST_THREADS + ST_PRODUCER;
 constexpr int ST_ITEMS = 4;
 constexpr int ST_STAGES = 3;
 constexpr int ST_TILE = ST_THREADS * ST_ITEMS;          // 1024 arcs per stage
 constexpr int ST_STAGE_BYTES = 25 * ST_TILE;            // 25 600 B
 constexpr int ST_CTAS_PER_SM = 2;
 constexpr int ST_CAND = 96;                             // in-band candidates kept per CTA
-constexpr int ST_SMEM = 128 + ST_STAGES * ST_STAGE_BYTES;
+constexpr int ST_HEADER = 256;                          // full[3], empty[3] mbarriers, tile index per stage
+constexpr int ST_SMEM = ST_HEADER + ST_STAGES * ST_STAGE_BYTES;
 
 __device__ __forceinline__ uint32_t st_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void st_mbar_init(uint64_t *bar, uint32_t count)
@@ -39,6 +47,10 @@ __device__ __forceinline__ void st_mbar_init(uint64_t *bar, uint32_t count)
 __device__ __forceinline__ void st_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(st_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(st_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void st_mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -55,12 +67,24 @@ __device__ __forceinline__ void st_bulk_g2s(void *dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(st_smem_u32(dst)), "l"(src), "r"(bytes), "r"(st_smem_u32(bar)) : "memory");
 }
+// barrier over the 256 consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void st_sync_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long st_ld_acquire(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_st_release(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
 
 struct CtaRec {            // 64-byte record of one CTA; a lone in-band candidate travels in the record itself
     double max;            // -1 when the CTA saw no violator
-    int32_t cnt;           // threads whose largest violation lies within the band of `max` (may exceed ST_CAND: overflow)
+    int32_t cnt;           // candidates within the band of `max` (may exceed ST_CAND: overflow)
     int32_t pad;
-    int64_t pos0;          // cnt == 1: that thread's position, largest and second-largest violation
+    int64_t pos0;          // cnt == 1: that candidate's position, its violation and the owning thread's second largest
     double viol0;
     double second0;
     double pad2[3];
@@ -68,30 +92,33 @@ struct CtaRec {            // 64-byte record of one CTA; a lone in-band candidat
 struct LvCtas {
     CtaRec *rec;           // [G]
     int64_t *candPos;      // [G * ST_CAND] global positions, unordered           (read only when cnt > 1)
-    double *candViol;      // [G * ST_CAND] the thread's largest violation
-    double *candSecond;    // [G * ST_CAND] the same thread's second largest (in band => the thread may hide more)
+    double *candViol;      // [G * ST_CAND] the candidate's violation
+    double *candSecond;    // [G * ST_CAND] the owning thread's second largest (in band => the thread may hide more); -1 in single mode
 };
-// Where the last CTA of the pass leaves the result, and (sharded runs) the exchange that follows it.
+// Counters of the pass (device memory, zero between passes: the last CTA re-arms them) and where its result goes.
 struct LvFused {
-    unsigned int *ticket;          // device counter, zero between passes
-    LvResult *res;                 // result block: mapped pinned host memory (single GPU) or device memory (sharded)
+    unsigned int *ticket;          // last-CTA election
+    unsigned int *arrive;          // first-CTA election (who applies the folded update)
+    unsigned long long *tileCtr;   // next tile to stream
+    unsigned long long *updFlag;   // == seq once the folded update of this pass is visible device-wide
+    LvResult *res;                 // result block: mapped pinned host memory (single GPU) or device memory
     unsigned long long seq;        // published in res->seq last
     int resOnHost;                 // system-scope fences only when the host polls res
-    int nranks, rank;              // nranks > 1 and peers != nullptr: exchange_record() after the reduction
+    int single;                    // one tile per CTA (grid == number of tiles): exact candidates from registers
+    int nranks, rank;              // nranks > 1 and peers != nullptr: exchange + merge after the reduction ...
     Mailbox *const *peers;
-    ShardRecord *hostOut;
-    unsigned long long *hostSeq;
-    unsigned long long xseq;
+    LvResult *hostOut;             // ... and the MERGED block goes here (mapped pinned host memory), with seq
+    unsigned long long xseq;       // sequence number of the mailbox flags
     long long xTimeout;            // cycles a rank waits for its peers before failing the pass
     long long *stamps;             // debug (GNE_STAMPS builds): clock64 stamps of the last CTA
 };
+struct PotMut { double *a0; double *a1; int32_t *slot; double *theta; double *pi; };
 
-// Reduction over the per-CTA records by ONE CTA of ST_THREADS threads (the last one of the pass): exact
-// global maximum, then every recorded candidate within the band of it, sorted by position (the CTAs
-// interleave tiles, so their lists are merged by rank), published to f.res; in a sharded run the same
-// CTA then exchanges the shard's record with the peers.  `scratch` is the (drained) stage memory.
-// Records are read once, two per thread, straight from L2: the common case (one candidate) costs one
-// dependent load level before the result is written.
+// Reduction over the per-CTA records by the 256 consumer threads of ONE CTA (the last one of the pass): exact
+// global maximum, then every recorded candidate within the band of it, sorted by position (the CTAs interleave
+// tiles, so their lists are merged by rank), published to f.res; in a sharded run the same CTA instead exchanges
+// the shard's record with the peers, merges the ranks' records and publishes the merged block for the host.
+// `scratch` is the (drained) stage memory.  Records are read once, two per thread, straight from L2.
 __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const LvFused &f, unsigned char *scratch)
 {
     constexpr int NT = ST_THREADS, NW = ST_THREADS / 32, LIST = 1024, PER = 2;
@@ -103,7 +130,7 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
     __shared__ double sMaxW[NW];
     __shared__ int sCount, sOvf, sQ, sTimeout;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) { sCount = 0; sOvf = 0; sQ = 0; if (f.ticket) *f.ticket = 0u; }      // re-arm the ticket for the next pass
+    if (t == 0) { sCount = 0; sOvf = 0; sQ = 0; }
     double rmax[PER], rviol[PER], rsec[PER];
     int64_t rpos[PER];
     int rcnt[PER];
@@ -121,13 +148,10 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
     if (t == 0 && f.stamps) f.stamps[2] = clock64();
 #endif
     double m = fmax(rmax[0], rmax[1]);
-#ifdef GNE_STAMPS
-    if (t == 0 && f.stamps) f.stamps[3] = clock64();
-#endif
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) sMaxW[w] = m;
-    __syncthreads();
+    st_sync_consumers();
     double M = sMaxW[0];
 #pragma unroll
     for (int i = 1; i < NW; ++i) M = fmax(M, sMaxW[i]);
@@ -146,7 +170,7 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
             else qG[atomicAdd(&sQ, 1)] = g;
         }
     }
-    __syncthreads();
+    st_sync_consumers();
     const int nq = sQ;
     for (int qi = w; qi < nq; qi += NW) {                                 // one warp per multi-candidate record
         const int g = qG[qi];
@@ -160,7 +184,7 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
             }
         }
     }
-    if (nq > 0) __syncthreads();
+    if (nq > 0) st_sync_consumers();
     const int total = sCount;
     const bool bad = any && (sOvf || total > LIST);                       // longer lists go through the ordered compaction
     if (any && !bad) {
@@ -171,166 +195,225 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
             lRank[rank] = i;
         }
     }
-    __syncthreads();
+    st_sync_consumers();
 #ifdef GNE_STAMPS
     if (t == 0 && f.stamps) f.stamps[4] = clock64();
 #endif
-    LvResult *res = f.res;
-    // one warp publishes: entries, fence, header, fence, sequence number (towards the host the fences are PCIe
-    // round trips, so as few threads as possible execute them)
-    if (w == 0) {
-        // entries and header go out together; every writing lane fences its own stores (one round trip towards
-        // the host, all lanes in parallel), then the sequence number
-        const int nOut = (any && !bad) ? total : 0;
-        for (int r = lane; r < nOut; r += 32) { res->pos[r] = lPos[lRank[r]]; res->viol[r] = lViol[lRank[r]]; }
-        if (lane == 0) { res->maxViol = any ? M : -1.0; res->any = any ? 1 : 0; res->overflow = bad ? 1 : 0; res->count = nOut; }
-        if (lane == 0 || lane < nOut) { if (f.resOnHost) __threadfence_system(); else __threadfence(); }
-        __syncwarp();
+    const int nOut = (any && !bad) ? total : 0;
+    if (!(f.nranks > 1 && f.peers != nullptr)) {
+        // one warp publishes: entries and header together, every writing lane fences its own stores (towards the
+        // host a fence is a PCIe round trip: all lanes pay it in parallel, once), then the sequence number
+        if (w == 0) {
+            LvResult *res = f.res;
+            for (int r = lane; r < nOut; r += 32) { res->pos[r] = lPos[lRank[r]]; res->viol[r] = lViol[lRank[r]]; }
+            if (lane == 0) { res->maxViol = any ? M : -1.0; res->any = any ? 1 : 0; res->overflow = bad ? 1 : 0; res->count = nOut; }
+            if (lane == 0 || lane < nOut) { if (f.resOnHost) __threadfence_system(); else __threadfence(); }
+            __syncwarp();
 #ifdef GNE_STAMPS
-        if (lane == 0 && f.stamps) f.stamps[5] = clock64();
+            if (lane == 0 && f.stamps) f.stamps[5] = clock64();
 #endif
-        if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&res->seq) = f.seq;
-    }
-    if (f.nranks > 1 && f.peers != nullptr) {
-        // sharded run: this CTA also carries the shard's record to the peers (and theirs to the host)
-        const int nOut = (any && !bad) ? total : 0;
-        if (t == 0) {
-            xrec->maxViol = any ? M : -1.0; xrec->any = any ? 1 : 0; xrec->count = nOut;
-            xrec->overflow = (bad || nOut > SHARD_LIST) ? 1 : 0;
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&res->seq) = f.seq;
         }
-        if (t < SHARD_LIST && t < nOut) { xrec->pos[t] = lPos[lRank[t]]; xrec->viol[t] = lViol[lRank[t]]; }
-        __syncthreads();
-        exchange_record(xrec, f.peers, f.rank, f.nranks, f.xseq, f.hostOut, f.hostSeq, &sTimeout, f.xTimeout);
+        return;
     }
+    // sharded run: this CTA carries the shard's record to the peers, merges theirs and publishes the merged block
+    if (t == 0) {
+        xrec->maxViol = any ? M : -1.0; xrec->any = any ? 1 : 0; xrec->count = nOut;
+        xrec->overflow = (bad || nOut > SHARD_LIST) ? 1 : 0;
+    }
+    if (t < SHARD_LIST && t < nOut) { xrec->pos[t] = lPos[lRank[t]]; xrec->viol[t] = lViol[lRank[t]]; }
+    st_sync_consumers();
+    exchange_merge(xrec, f.peers, f.rank, f.nranks, f.xseq, f.hostOut, f.seq, &sTimeout, f.xTimeout,
+                   reinterpret_cast<int64_t *>(scratch), reinterpret_cast<double *>(scratch + 8 * LIST));
 }
 
-// Per tile the critical path is: wait for the stage, read the indices from shared memory, gather,
-// compare - nothing else.  Each thread keeps its largest violation (first position on ties) and its
-// second largest in registers; shared memory and atomics are touched once, after the last tile.
-// A thread can therefore contribute one candidate; if its second value is also within the band of
-// the global maximum the pass reports overflow (it may hide a third) and the caller falls back to
-// the ordered compaction - with ~75 k threads that happens only for long tie lists.
-__global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
-k_price_lv_stream(NbView nb, const double *__restrict__ pi, LvCtas out, int64_t numTiles, LvFused f)
+// The folded relabel of the last pivot (what k_update_small does as its own launch), by the 256 consumer threads of
+// the first CTA to arrive; releases f.updFlag = f.seq when everything is visible device-wide.
+__device__ __forceinline__ void st_apply_update(const SmallUpdate &u, const NbMut &nb, const PotMut &pm, const LvFused &f)
+{
+    const int t = threadIdx.x;
+    if (t < u.ops.n) {
+        const int64_t l = u.ops.local[t];
+        nb.tail[l] = u.ops.tail[t]; nb.head[l] = u.ops.head[t];
+        nb.cost[l] = u.ops.cost[t]; nb.mult[l] = u.ops.mult[t]; nb.state[l] = u.ops.state[t];
+    }
+    if (t < u.nNodes) { const int v = u.node[t]; pm.a0[v] = u.a0[t]; pm.a1[v] = u.a1[t]; pm.slot[v] = u.slot[t]; }
+    if (t < u.nTheta) pm.theta[u.tslot[t]] = u.theta[t];
+    st_sync_consumers();
+    if (t < u.nFinal) {
+        const int v = u.fnode[t];
+        pm.pi[v] = __dadd_rn(pm.a0[v], __dmul_rn(pm.a1[v], pm.theta[pm.slot[v]]));
+    }
+    __threadfence();
+    st_sync_consumers();
+    if (t == 0) st_st_release(f.updFlag, f.seq);
+}
+
+__global__ void __launch_bounds__(ST_BLOCK, ST_CTAS_PER_SM)
+k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __grid_constant__ LvCtas out, const int64_t numTiles,
+                  const __grid_constant__ LvFused f, const __grid_constant__ SmallUpdate u, const __grid_constant__ NbMut nbMut,
+                  const __grid_constant__ PotMut pm)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);                 // [ST_STAGES]
-    unsigned char *stage0 = smem + 128;
+    uint64_t *empty = full + ST_STAGES;                                  // [ST_STAGES]
+    volatile int64_t *sTile = reinterpret_cast<volatile int64_t *>(smem + 128);   // [ST_STAGES] tile in each stage, -1: none left
+    unsigned char *stage0 = smem + ST_HEADER;
     const int t = threadIdx.x;
     if (t == 0) {
-        for (int s = 0; s < ST_STAGES; ++s) st_mbar_init(&full[s], 1);
+        for (int s = 0; s < ST_STAGES; ++s) { st_mbar_init(&full[s], 1); st_mbar_init(&empty[s], ST_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    pdl_launch_dependents();
     __syncthreads();
-    pdl_wait();                                         // the relabel kernel's potentials and list edits are complete
-    auto issue = [&](int s, int64_t tile) {
-        unsigned char *b = stage0 + (size_t) s * ST_STAGE_BYTES;
-        const int64_t l0 = tile * ST_TILE;
-        st_mbar_expect_tx(&full[s], (uint32_t) ST_STAGE_BYTES);
-        st_bulk_g2s(b, nb.tail + l0, 4 * ST_TILE, &full[s]);
-        st_bulk_g2s(b + 4 * ST_TILE, nb.head + l0, 4 * ST_TILE, &full[s]);
-        st_bulk_g2s(b + 8 * ST_TILE, nb.cost + l0, 8 * ST_TILE, &full[s]);
-        st_bulk_g2s(b + 16 * ST_TILE, nb.mult + l0, 8 * ST_TILE, &full[s]);
-        st_bulk_g2s(b + 24 * ST_TILE, nb.state + l0, ST_TILE, &full[s]);
-    };
-    if (t == 0) {
-        for (int s = 0; s < ST_STAGES; ++s) {
-            const int64_t tile = blockIdx.x + (int64_t) s * gridDim.x;
-            if (tile < numTiles) issue(s, tile);
+    if (t >= ST_THREADS) {
+        // ---------------- producer warp: one thread streams tiles until the counter runs out
+        if (t == ST_THREADS) {
+            for (int it = 0;; ++it) {
+                const int s = it % ST_STAGES;
+                if (it >= ST_STAGES) st_mbar_wait(&empty[s], (uint32_t) (((it / ST_STAGES) - 1) & 1));
+                const int64_t tile = f.single ? (it == 0 ? (int64_t) blockIdx.x : numTiles) : (int64_t) atomicAdd(f.tileCtr, 1ull);
+                if (tile >= numTiles) { sTile[s] = -1; st_mbar_arrive(&full[s]); break; }
+                sTile[s] = tile;
+                unsigned char *b = stage0 + (size_t) s * ST_STAGE_BYTES;
+                const int64_t l0 = tile * ST_TILE;
+                st_mbar_expect_tx(&full[s], (uint32_t) ST_STAGE_BYTES);
+                st_bulk_g2s(b, nb.tail + l0, 4 * ST_TILE, &full[s]);
+                st_bulk_g2s(b + 4 * ST_TILE, nb.head + l0, 4 * ST_TILE, &full[s]);
+                st_bulk_g2s(b + 8 * ST_TILE, nb.cost + l0, 8 * ST_TILE, &full[s]);
+                st_bulk_g2s(b + 16 * ST_TILE, nb.mult + l0, 8 * ST_TILE, &full[s]);
+                st_bulk_g2s(b + 24 * ST_TILE, nb.state + l0, ST_TILE, &full[s]);
+            }
         }
+        return;
+    }
+    // ---------------- consumers
+    const int lane = t & 31;
+    const bool hasUpd = (u.ops.n | u.nNodes | u.nTheta | u.nFinal) != 0;
+    __shared__ int sUpd;
+    if (hasUpd) {
+        if (t == 0) sUpd = (atomicAdd(f.arrive, 1u) == 0u) ? 1 : 0;
+        st_sync_consumers();
+        if (sUpd) st_apply_update(u, nbMut, pm, f);
     }
     double v1 = -1.0, v2 = -1.0;                        // largest (first position on ties) and second largest
     int64_t p1 = 0;
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
+    double vv[ST_ITEMS];                                // single mode: the thread's four values
+    int64_t tileOfVv = 0;
+#pragma unroll
+    for (int k = 0; k < ST_ITEMS; ++k) vv[k] = -1.0;
+    for (int it = 0;; ++it) {
         const int s = it % ST_STAGES;
         st_mbar_wait(&full[s], (uint32_t) ((it / ST_STAGES) & 1));
+        const int64_t tile = sTile[s];
+        if (tile < 0) break;
         const unsigned char *sb = stage0 + (size_t) s * ST_STAGE_BYTES;
         const int32_t *sTail = reinterpret_cast<const int32_t *>(sb);
         const int32_t *sHead = reinterpret_cast<const int32_t *>(sb + 4 * ST_TILE);
         const double *sCost = reinterpret_cast<const double *>(sb + 8 * ST_TILE);
         const double *sMult = reinterpret_cast<const double *>(sb + 16 * ST_TILE);
         const int8_t *sState = reinterpret_cast<const int8_t *>(sb + 24 * ST_TILE);
+        int tl[ST_ITEMS], hd[ST_ITEMS];
+#pragma unroll
+        for (int k = 0; k < ST_ITEMS; ++k) { const int o = t + k * ST_THREADS; tl[k] = sTail[o]; hd[k] = sHead[o]; }
+        // a tile that holds one of the rewritten arc records (at most 8 per pivot, usually 2-3 in the whole list):
+        // the stream may have fetched it before or after the update wrote it - take the record from the arguments
+        bool patched = false;
+        for (int i = 0; i < u.ops.n; ++i) patched |= (u.ops.local[i] / ST_TILE == tile);
+        double cs[ST_ITEMS], mu[ST_ITEMS];
+        int st[ST_ITEMS];
+        if (patched) {
+#pragma unroll
+            for (int k = 0; k < ST_ITEMS; ++k) {
+                const int o = t + k * ST_THREADS;
+                cs[k] = sCost[o]; mu[k] = sMult[o]; st[k] = (int) sState[o];
+                for (int i = 0; i < u.ops.n; ++i)
+                    if (u.ops.local[i] == tile * ST_TILE + o) { tl[k] = u.ops.tail[i]; hd[k] = u.ops.head[i]; cs[k] = u.ops.cost[i]; mu[k] = u.ops.mult[i]; st[k] = (int) u.ops.state[i]; }
+            }
+        }
+        if (it == 0 && hasUpd) {                        // the relabel must be visible before the first gather
+            if (lane == 0) while (st_ld_acquire(f.updFlag) != f.seq) { }
+            __syncwarp();
+        }
         double pt[ST_ITEMS], ph[ST_ITEMS];
 #pragma unroll
-        for (int k = 0; k < ST_ITEMS; ++k) { const int o = t + k * ST_THREADS; pt[k] = ld_pi(pi, sTail[o]); ph[k] = ld_pi(pi, sHead[o]); }
+        for (int k = 0; k < ST_ITEMS; ++k) { pt[k] = pi[tl[k]]; ph[k] = pi[hd[k]]; }
 #pragma unroll
         for (int k = 0; k < ST_ITEMS; ++k) {
             const int o = t + k * ST_THREADS;
             const int64_t g = nb.lo + tile * ST_TILE + o;
-            const double v = (g < nb.end && g >= nb.begin) ? violation(red_cost(sCost[o], sMult[o], pt[k], ph[k]), (int) sState[o]) : -1.0;
-            if (v > v1) { v2 = v1; v1 = v; p1 = g; }      // positions rise within a thread: the first maximum stays
+            const double c = patched ? cs[k] : sCost[o], m = patched ? mu[k] : sMult[o];
+            const int sta = patched ? st[k] : (int) sState[o];
+            const double v = (g < nb.end && g >= nb.begin) ? violation(red_cost(c, m, pt[k], ph[k]), sta) : -1.0;
+            vv[k] = v;
+            if (v > v1) { v2 = v1; v1 = v; p1 = g; }      // tiles come in rising order and positions rise within a tile: the first maximum stays
             else if (v > v2) v2 = v;
         }
-        __syncthreads();                                // everyone is done with stage s
-        if (t == 0) {
-            const int64_t nt = tile + (int64_t) ST_STAGES * gridDim.x;
-            if (nt < numTiles) issue(s, nt);
-        }
+        tileOfVv = tile;
+        __syncwarp();
+        if (lane == 0) st_mbar_arrive(&empty[s]);       // this warp is done with stage s
     }
 #ifdef GNE_STAMPS
     const long long st0 = clock64();
 #endif
-    // once per CTA: maximum, then the threads within the band of it
+    // ---------------- once per CTA: maximum, then the candidates within the band of it
     __shared__ int sCnt, sLast;
+    __shared__ double sWarpMax[ST_THREADS / 32];
     __shared__ int64_t sPos[ST_CAND];
     __shared__ double sViol[ST_CAND], sSecond[ST_CAND];
     if (t == 0) sCnt = 0;
-    Best b; b.v = v1; b.p = p1;
-    b = block_best(b);                                  // two barriers inside: sCnt = 0 is visible afterwards
-    const double Mc = b.v;
+    double mx = v1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sWarpMax[t >> 5] = mx;
+    st_sync_consumers();
+    double Mc = sWarpMax[0];
+#pragma unroll
+    for (int i = 1; i < ST_THREADS / 32; ++i) Mc = fmax(Mc, sWarpMax[i]);
     if (Mc > 0.0) {
         const double thr = __dsub_rn(Mc, LV_BAND);
-        if (v1 >= thr) {
+        if (f.single) {
+#pragma unroll
+            for (int k = 0; k < ST_ITEMS; ++k) {
+                if (vv[k] >= thr) {
+                    const int slot = atomicAdd(&sCnt, 1);
+                    if (slot < ST_CAND) { sPos[slot] = nb.lo + tileOfVv * ST_TILE + t + k * ST_THREADS; sViol[slot] = vv[k]; sSecond[slot] = -1.0; }
+                }
+            }
+        } else if (v1 >= thr) {
             const int slot = atomicAdd(&sCnt, 1);
             if (slot < ST_CAND) { sPos[slot] = p1; sViol[slot] = v1; sSecond[slot] = v2; }
         }
     }
-    __syncthreads();
+    st_sync_consumers();
     const int cnt = sCnt;
-    if (cnt > 1) {                                      // rare: several threads of this CTA within the band
+    if (cnt > 1) {                                      // rare: several candidates of this CTA within the band
         for (int i = t; i < min(cnt, ST_CAND); i += ST_THREADS) {
             out.candPos[(int64_t) blockIdx.x * ST_CAND + i] = sPos[i];
             out.candViol[(int64_t) blockIdx.x * ST_CAND + i] = sViol[i];
             out.candSecond[(int64_t) blockIdx.x * ST_CAND + i] = sSecond[i];
         }
-        if (f.ticket != nullptr) __threadfence();
-        __syncthreads();
+        __threadfence();
+        st_sync_consumers();
     }
-    // ---- sharded runs: the last CTA to get here reduces the per-CTA records and runs the exchange (one launch
-    // per pass); single GPU: the reduction is its own small kernel behind a programmatic launch boundary, which
-    // costs the same latency as the fence + ticket here and keeps this kernel pure streaming
     if (t == 0) {
         CtaRec *r = out.rec + blockIdx.x;
         r->max = Mc > 0.0 ? Mc : -1.0; r->cnt = cnt; r->pad = 0;
         r->pos0 = sPos[0]; r->viol0 = sViol[0]; r->second0 = sSecond[0];       // meaningful when cnt == 1
-        sLast = 0;
-        if (f.ticket != nullptr) {                      // (no ticket: k_price_lv_reduce follows as its own launch)
-            __threadfence();
-            sLast = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-        }
+        __threadfence();
+        sLast = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
     }
-    __syncthreads();
+    st_sync_consumers();
     if (!sLast) return;
+    // ---------------- the last CTA of the pass: re-arm the counters, reduce, publish (and exchange)
 #ifdef GNE_STAMPS
     if (t == 0 && f.stamps) { f.stamps[0] = st0; f.stamps[1] = clock64(); }
 #endif
     __threadfence();
+    if (t == 0) { *f.ticket = 0u; *f.arrive = 0u; *f.tileCtr = 0ull; }
     lv_reduce_records(out, (int) gridDim.x, f, stage0);
 #ifdef GNE_STAMPS
     if (t == 0 && f.stamps) f.stamps[7] = clock64();
 #endif
-}
-
-// The same reduction as its own launch (single-GPU passes): one CTA, resident early through PDL.
-__global__ void __launch_bounds__(ST_THREADS)
-k_price_lv_reduce(LvCtas in, int G, LvFused f)
-{
-    __shared__ __align__(16) unsigned char scratch[25 * 1024];
-    pdl_launch_dependents();
-    pdl_wait();
-    lv_reduce_records(in, G, f, scratch);
 }
 
 } // namespace gne
