@@ -583,6 +583,22 @@ extern "C" int gne_pot_finalize(gne_dev *d)
     return GNE_OK;
 }
 
+extern "C" int gne_pot_finalize_slots(gne_dev *d, int count, const int32_t *slots)
+{
+    if (count <= 0) return GNE_OK;
+    CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
+    for (int k = 0; k < count; k += 8) {
+        SlotSet ss; ss.n = std::min(8, count - k);
+        for (int i = 0; i < 8; ++i) ss.slot[i] = i < ss.n ? slots[k + i] : -1;
+        k_pot_finalize_slots<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->a0, d->a1, d->slot, d->theta, d->pi, ss);
+        CK(cudaGetLastError());
+        ++d->launches;
+    }
+    d->h2dBytes += 4 * count;
+    return GNE_OK;
+}
+
 extern "C" int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const double *pi)
 {
     if (count <= 0) return GNE_OK;

@@ -2,6 +2,7 @@
 #include "gne_forest.h"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <time.h>
 
 namespace gneb200 {
@@ -12,6 +13,7 @@ void Forest::init(int nNodes, int64_t numVars, const int32_t *tailIn, const int3
 {
     n = nNodes; tail = tailIn; head = headIn;
     (void) numVars;
+    { const char *ff = getenv("GNE_FOREST_FAST"); fastSplit = !(ff && ff[0] == '0'); }
     node.assign((size_t) n, NodeRec());
     trees.clear(); freeSlots.clear(); stale.clear(); changed.clear(); changedFlag.clear(); dirtyNodes.clear();
     trees.reserve((size_t) n + 8);
@@ -42,11 +44,12 @@ int32_t Forest::newTree(int8_t type, int32_t rootNode)
     Tree &t = trees[slot];
     t.type = type; t.root = -1; t.extraArc = -1;
     t.nodes.clear(); t.arcs.clear(); t.threads.clear(); t.pending.clear();
+    t.tailArcs.clear(); t.ordFix.clear(); t.implicitOrder = false;
     t.rooted = false; t.threadsValid = false;
     touch(slot);
     if (rootNode >= 0) {
         t.root = rootNode;
-        t.nodes.push_back(rootNode);
+        pushNode(slot, rootNode);
         setSlot(rootNode, slot);
     }
     return slot;
@@ -57,6 +60,7 @@ void Forest::freeTree(int32_t slot)
     Tree &t = trees[slot];
     t.type = TREE_FREE; t.root = -1; t.extraArc = -1;
     t.nodes.clear(); t.arcs.clear(); t.threads.clear();
+    t.tailArcs.clear(); t.ordFix.clear(); t.implicitOrder = false;
     if (t.nodes.capacity() > 4096) {                    // give big buffers back, keep small ones for reuse
         std::vector<int32_t>().swap(t.nodes);
         std::vector<int32_t>().swap(t.arcs);
@@ -81,7 +85,7 @@ void Forest::incPush(int32_t v, int32_t arc, int32_t nbr, int32_t pos)
         for (int32_t k = 0; k < node[v].incLen; ++k) pool[ns + k] = pool[node[v].incStart + k];
         node[v].incStart = ns; node[v].incCap = nc;
     }
-    Inc e; e.arc = arc; e.nbr = nbr; e.pos = pos;
+    Inc e; e.arc = arc; e.nbr = nbr; e.pos = pos; e.ord = node[v].incLen;
     pool[node[v].incStart + node[v].incLen++] = e;
 }
 
@@ -111,7 +115,77 @@ void Forest::compactPool()
     pool.swap(np);
 }
 
-// Tree::mergeTxAndTII (trees.cpp:365-395)
+const Inc *Forest::entryOf(int32_t v, int32_t a) const
+{
+    const int64_t base = node[v].incStart;
+    for (int32_t k = 0; k < node[v].incLen; ++k) if (pool[base + k].arc == a) return &pool[base + k];
+    return nullptr;
+}
+
+void Forest::applyOrdFix(Tree &t)
+{
+    for (size_t q = 0; q < t.ordFix.size(); ++q) {
+        const int32_t v = t.ordFix[q];
+        const int64_t base = node[v].incStart;
+        for (int32_t k = 0; k < node[v].incLen; ++k) pool[base + k].ord = k;
+        node[v].flag &= (uint8_t) ~4;
+    }
+    t.ordFix.clear();
+}
+
+// Materialise arcs(tree) of a tree whose order is implicit: the split DFS (see split / splitFull) from the root over the
+// arcs that were in the tree at its last split - children in the incident order of THAT moment (`ord`), appended subtrees
+// (tail arcs) not entered - followed by the tail arcs in the order they were appended.  O(|tree|).
+void Forest::ensureArcs(int32_t slot)
+{
+    Tree &t = trees[slot];
+    if (!t.implicitOrder) return;
+    t.arcs.clear();
+    std::vector<int32_t> &st = stackA;
+    std::vector<std::pair<int32_t, int32_t> > &srt = sortBuf;
+    st.clear();
+    st.push_back(t.root);
+    while (!st.empty()) {
+        const int32_t nd = st.back(); st.pop_back();
+        const int32_t prev = (nd == t.root) ? -1 : node[nd].pred;
+        const int64_t base = node[nd].incStart;
+        const int32_t len = node[nd].incLen;
+        if (node[nd].flag & 4) {                         // entries out of snapshot order: visit them by `ord`
+            srt.clear();
+            for (int32_t k = 0; k < len; ++k) srt.push_back(std::make_pair(pool[base + k].ord, k));
+            std::sort(srt.begin(), srt.end());
+        }
+        for (int32_t q = 0; q < len; ++q) {
+            Inc &e = pool[base + ((node[nd].flag & 4) ? srt[q].second : q)];
+            if (e.pos >= POS_TAIL_BASE || e.pos == POS_TAIL_OTHER) continue;      // appended since the last split
+            if (e.nbr == prev) { e.pos = POS_NONE; continue; }
+            e.pos = (int32_t) t.arcs.size();
+            t.arcs.push_back(e.arc);
+            st.push_back(e.nbr);
+        }
+    }
+    const int32_t nBase = (int32_t) t.arcs.size();
+    for (size_t i = 0; i < t.tailArcs.size(); ++i) {
+        const int32_t a = t.tailArcs[i];
+        for (int side = 0; side < 2; ++side) {
+            const int32_t w = side ? head[a] : tail[a];
+            const int64_t base = node[w].incStart;
+            for (int32_t k = 0; k < node[w].incLen; ++k) {
+                Inc &e = pool[base + k];
+                if (e.arc != a) continue;
+                if (e.pos >= POS_TAIL_BASE) e.pos = nBase + (e.pos - POS_TAIL_BASE);
+                else if (e.pos == POS_TAIL_OTHER) e.pos = POS_NONE;
+            }
+        }
+        t.arcs.push_back(a);
+    }
+    t.tailArcs.clear();
+    t.implicitOrder = false;
+    applyOrdFix(t);
+    nodesMaterialized += (int64_t) t.nodes.size();
+}
+
+// Tree::mergeTxAndTII (trees.cpp:365-395): arcs(x) = arcs(x) ++ arcs(y) ++ [av]
 void Forest::mergeInto(int32_t tX, int32_t tII, int32_t av)
 {
     const double t0 = nowS();
@@ -122,24 +196,41 @@ void Forest::mergeInto(int32_t tX, int32_t tII, int32_t av)
         else { at.parent = head[av]; at.child = tail[av]; }
         trees[tX].pending.push_back(at);
     }
+    ensureArcs(tII);                                     // y's order becomes explicit: O(|y|), like everything below
     relabel(tII, tX);
     Tree &x = trees[tX];
     Tree &y = trees[tII];
-    // y's arcs keep their relative order behind x's: shift the positions held in y's incident entries
-    const int32_t shift = (int32_t) x.arcs.size();
-    if (shift && !y.arcs.empty()) {
+    if (x.implicitOrder) {
+        // y's arcs keep their relative order in x's tail: explicit positions POS_TAIL_BASE + index
+        const int32_t shift = POS_TAIL_BASE + (int32_t) x.tailArcs.size();
         for (size_t q = 0; q < y.nodes.size(); ++q) {
             const int32_t w = y.nodes[q];
             const int64_t base = node[w].incStart;
-            for (int32_t k = 0; k < node[w].incLen; ++k) if (pool[base + k].pos >= 0) pool[base + k].pos += shift;
+            for (int32_t k = 0; k < node[w].incLen; ++k) { Inc &e = pool[base + k]; e.pos = (e.pos >= 0) ? e.pos + shift : (int32_t) POS_TAIL_OTHER; }
         }
+        x.tailArcs.insert(x.tailArcs.end(), y.arcs.begin(), y.arcs.end());
+        const int32_t pav = POS_TAIL_BASE + (int32_t) x.tailArcs.size();
+        x.tailArcs.push_back(av);
+        incPush(tail[av], av, head[av], pav);
+        incPush(head[av], av, tail[av], POS_TAIL_OTHER);
+    } else {
+        // y's arcs keep their relative order behind x's: shift the positions held in y's incident entries
+        const int32_t shift = (int32_t) x.arcs.size();
+        if (shift && !y.arcs.empty()) {
+            for (size_t q = 0; q < y.nodes.size(); ++q) {
+                const int32_t w = y.nodes[q];
+                const int64_t base = node[w].incStart;
+                for (int32_t k = 0; k < node[w].incLen; ++k) if (pool[base + k].pos >= 0) pool[base + k].pos += shift;
+            }
+        }
+        x.arcs.insert(x.arcs.end(), y.arcs.begin(), y.arcs.end());
+        const int32_t pav = (int32_t) x.arcs.size();
+        x.arcs.push_back(av);
+        incPush(tail[av], av, head[av], pav);
+        incPush(head[av], av, tail[av], POS_NONE);
     }
-    x.nodes.insert(x.nodes.end(), y.nodes.begin(), y.nodes.end());
-    x.arcs.insert(x.arcs.end(), y.arcs.begin(), y.arcs.end());
-    const int32_t pav = (int32_t) x.arcs.size();
-    x.arcs.push_back(av);
-    incPush(tail[av], av, head[av], pav);
-    incPush(head[av], av, tail[av], -1);
+    for (size_t q = 0; q < y.nodes.size(); ++q) pushNode(tX, y.nodes[q]);
+    x.ordFix.insert(x.ordFix.end(), y.ordFix.begin(), y.ordFix.end());
     touch(tX);
     freeTree(tII);
     secsMerge += nowS() - t0;
@@ -149,9 +240,10 @@ void Forest::mergeInto(int32_t tX, int32_t tII, int32_t av)
 void Forest::expandWithArc(int32_t t, int32_t av)
 {
     const int32_t u = tail[av], v = head[av];
+    ensureArcs(t);
     Tree &x = trees[t];
-    if (node[u].slot != t) { x.nodes.push_back(u); setSlot(u, t); }
-    else if (node[v].slot != t) { x.nodes.push_back(v); setSlot(v, t); }
+    if (node[u].slot != t) { pushNode(t, u); setSlot(u, t); }
+    else if (node[v].slot != t) { pushNode(t, v); setSlot(v, t); }
     if (u != v) {
         const int32_t pav = (int32_t) x.arcs.size();
         x.arcs.push_back(av);
@@ -195,9 +287,10 @@ int Forest::insertArc(int32_t av)
 // reached through the removed arc becomes `bottom`, the rest `top`.  The discovery order IS the
 // new arcsInTree / nodesInTree order.  `top` keeps the old tree's slot (the reference creates two
 // fresh trees; tree ids have no observable effect), so its nodes keep their slot.
-int32_t Forest::split(int32_t tOld, int32_t removedArc)
+int32_t Forest::splitFull(int32_t tOld, int32_t removedArc)
 {
     const double t0 = nowS();
+    { Tree &o = trees[tOld]; applyOrdFix(o); o.tailArcs.clear(); o.implicitOrder = false; }   // a new explicit order is written below
     const int32_t bottom = newTree(TREE_II, -1);         // may grow `trees`: take references afterwards
     const int32_t top = tOld;
     const int32_t oldRoot = trees[top].root;
@@ -225,7 +318,7 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
         Tree &tc = trees[cur];
         setSlot(nd, cur);
         if (tc.nodes.empty()) tc.root = nd;
-        tc.nodes.push_back(nd);
+        pushNode(cur, nd);
         int32_t removedInd = -1, removedNbr = -1;
         const int64_t base = node[nd].incStart;
         const int32_t len = node[nd].incLen;
@@ -238,11 +331,12 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
                 curStack.push_back(e.nbr);
                 prevStack.push_back(nd);
             } else {
-                e.pos = -1;
+                e.pos = POS_NONE;
             }
         }
         if (removedInd >= 0) {
             pool[base + removedInd] = pool[base + len - 1];
+            pool[base + removedInd].ord = removedInd;
             --node[nd].incLen;
             if (prev > -2) {
                 curStack.push_back(-1);
@@ -253,8 +347,90 @@ int32_t Forest::split(int32_t tOld, int32_t removedArc)
         }
     }
     secsSplit += nowS() - t0;
-    nodesSplit += (int64_t) (trees[top].nodes.size() + trees[bottom].nodes.size());
+    nodesSplit += (int64_t) (trees[top].nodes.size() + trees[bottom].nodes.size()); ++callsSplitFull;
     if (trees[bottom].nodes.empty()) { freeTree(bottom); return -1; }
+    return bottom;
+}
+
+// Tree::splitTree without visiting the part that keeps the root.  What the reference's DFS (splitFull) produces for a tree
+// whose rooting is valid is known without running it:
+//   * bottom = the subtree under the removed arc (pred pointers), its root the arc's child end; top = the rest, same root;
+//   * arcs(top) / arcs(bottom) = the DFS order from those roots over the incident lists as they stand NOW - kept implicit:
+//     an arc's rank is (pop rank of the parent end, index in its list), and two parent ends compare at their lowest common
+//     ancestor by the list index of the branches (the later entry is popped first).  The lists only change afterwards by
+//     appends (merges) and by the swap-with-last removal done here, whose moved entries keep their old index in `ord`
+//     until the next split of the tree (Tree::ordFix).
+// Cost: O(|bottom|) + the two incident lists, instead of O(|tree|).  The arcs merged into the tree since its last split
+// (its tail) become part of the implicit order here, as the reference's DFS would re-sort them.
+int32_t Forest::split(int32_t top, int32_t removedArc)
+{
+    {
+        const Tree &o = trees[top];
+        if (!fastSplit || !o.rooted || !o.pending.empty() || o.root < 0) return splitFull(top, removedArc);
+    }
+    const double t0 = nowS();
+    const int32_t u = tail[removedArc], v = head[removedArc];
+    int32_t c;                                           // child end of the removed arc
+    if (node[v].predArc == removedArc && node[v].pred == u) c = v;
+    else if (node[u].predArc == removedArc && node[u].pred == v) c = u;
+    else return splitFull(top, removedArc);
+    const int32_t par = (c == v) ? u : v;
+    const int32_t bottom = newTree(TREE_II, -1);         // may grow `trees`: take references afterwards
+    Tree &o = trees[top];
+    Tree &bt = trees[bottom];
+    // the new snapshot: tail arcs and lagging list indices are absorbed into "the lists as they stand now"
+    for (size_t i = 0; i < o.tailArcs.size(); ++i) {
+        const int32_t a = o.tailArcs[i];
+        for (int side = 0; side < 2; ++side) {
+            const int32_t w = side ? head[a] : tail[a];
+            const int64_t base = node[w].incStart;
+            for (int32_t k = 0; k < node[w].incLen; ++k) if (pool[base + k].arc == a) pool[base + k].pos = POS_NONE;
+        }
+    }
+    o.tailArcs.clear();
+    applyOrdFix(o);
+    o.arcs.clear();
+    o.implicitOrder = true;
+    o.type = TREE_II; o.extraArc = -1;
+    o.threadsValid = false;                              // a block of the thread disappears; the rooting of the rest stays
+    touch(top);
+    // bottom: the subtree of c, rooted at c with the pred pointers it has
+    std::vector<int32_t> &st = stackA;
+    st.clear();
+    st.push_back(c);
+    int64_t visited = 0;
+    while (!st.empty()) {
+        const int32_t nd = st.back(); st.pop_back();
+        ++visited;
+        {   // leave nodes(top) by swap-with-last
+            const int32_t idx = node[nd].nodeIdx, last = o.nodes.back();
+            o.nodes[idx] = last; node[last].nodeIdx = idx; o.nodes.pop_back();
+        }
+        setSlot(nd, bottom);
+        pushNode(bottom, nd);
+        const int32_t prev = node[nd].pred;
+        const int64_t base = node[nd].incStart;
+        for (int32_t k = 0; k < node[nd].incLen; ++k) if (pool[base + k].nbr != prev) st.push_back(pool[base + k].nbr);
+    }
+    bt.root = c; bt.implicitOrder = true; bt.rooted = false;
+    node[c].pred = -1; node[c].predArc = -1; node[c].flag |= 1;
+    // remove the arc from the two incident lists (swap with last); the moved entries keep their snapshot index
+    for (int side = 0; side < 2; ++side) {
+        const int32_t w = side ? c : par;
+        const int64_t base = node[w].incStart;
+        const int32_t len = node[w].incLen;
+        for (int32_t k = 0; k < len; ++k) {
+            if (pool[base + k].arc != removedArc) continue;
+            if (k != len - 1) {
+                pool[base + k] = pool[base + len - 1];
+                if (!(node[w].flag & 4)) { node[w].flag |= 4; (side ? bt : o).ordFix.push_back(w); }
+            }
+            --node[w].incLen;
+            break;
+        }
+    }
+    secsSplit += nowS() - t0;
+    nodesSplit += visited; ++callsSplitFast;
     return bottom;
 }
 
@@ -296,7 +472,7 @@ void Forest::reindex(int32_t slot)
         const int32_t predNode = predStack.back(); predStack.pop_back();
         NodeRec &r = node[cur];
         const bool dirty = (r.flag & 1) || r.pred != predNode || r.predArc != pa || (predNode >= 0 && (node[predNode].flag & 2));
-        r.flag = dirty ? 2 : 0;
+        r.flag = (uint8_t) ((r.flag & 4) | (dirty ? 2 : 0));
         if (dirty) dirtyNodes.push_back(cur);
         r.depth = (predNode >= 0) ? node[predNode].depth + 1 : 0;
         r.predArc = pa;
@@ -337,7 +513,7 @@ void Forest::rethreadSubtree(int32_t slot, const Attach &at)
         const int32_t predNode = predStack.back(); predStack.pop_back();
         NodeRec &r = node[cur];
         const bool dirty = (r.flag & 1) || r.pred != predNode || r.predArc != pa || (node[predNode].flag & 2);
-        r.flag = dirty ? 2 : 0;
+        r.flag = (uint8_t) ((r.flag & 4) | (dirty ? 2 : 0));
         if (dirty) dirtyNodes.push_back(cur);
         r.depth = node[predNode].depth + 1;
         r.predArc = pa;
@@ -403,6 +579,7 @@ void Forest::updateTrees()
         if (t.type == TREE_FREE || t.upToDate) continue;
         const int32_t newRoot = (t.type == TREE_I) ? tail[t.extraArc] : t.root;   // keep the root on the cycle (:578)
         if (!t.rooted || newRoot != t.root) {
+            ensureArcs(slot);                            // an implicit order refers to the old rooting: write it down first
             t.root = newRoot;
             reindex(slot);
         } else {

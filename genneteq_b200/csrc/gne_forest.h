@@ -17,6 +17,7 @@
 // the node the arc was discovered from, so a DFS touches about two cache lines per node.
 #pragma once
 #include <stdint.h>
+#include <utility>
 #include <vector>
 
 namespace gneb200 {
@@ -34,22 +35,32 @@ struct Tree {
     std::vector<Attach> pending;
     int32_t root = -1;
     int32_t extraArc = -1;
-    std::vector<int32_t> nodes;                         // Tree::nodesInTree
-    std::vector<int32_t> arcs;                          // Tree::arcsInTree
+    std::vector<int32_t> nodes;                         // Tree::nodesInTree (as a set: its order has no observable effect)
+    std::vector<int32_t> arcs;                          // Tree::arcsInTree - materialised only while !implicitOrder
     std::vector<int32_t> threads;                       // Tree::threads (rebuilt lazily: Forest::ensureThreads)
+    // Implicit arcsInTree order (see Forest::split): the order is "the split DFS from `root` over the incident lists as they
+    // stood at the last split" for the arcs that were in the tree then, followed by `tailArcs` (arcs appended by merges
+    // since, with explicit positions).  Nothing of size |tree| is touched when a subtree is cut off.
+    bool implicitOrder = false;
+    std::vector<int32_t> tailArcs;
+    std::vector<int32_t> ordFix;                        // nodes whose incident entries' `ord` lag behind their physical index
 };
 
 // incident arc, the node at its other end, and (in the entry of the node the arc was discovered
 // from / appended at; -1 in the other one) its index in arcs(tree)
-struct Inc { int32_t arc, nbr, pos; };
+// `ord`: the entry's index in its node's list at the tree's last split (the order that split's DFS used); equals the
+// physical index except at the nodes listed in Tree::ordFix.
+struct Inc { int32_t arc, nbr, pos, ord; };
+enum { POS_NONE = -1, POS_TAIL_OTHER = -3, POS_TAIL_BASE = 1 << 30 };   // pos codes: not the holder / other end of a tail arc / holder of tail arc i
 
 struct alignas(64) NodeRec {                            // Node's tree fields (variables.h:63-76) + bookkeeping: one cache line
     int32_t slot = -1;                                  // memberOfTreeID (stable slot)
     int32_t pred = -1, predArc = -1, depth = -1, thread = -1;
     int32_t threadPos = -1;
+    int32_t nodeIdx = -1;                               // index in nodes(tree)
     int64_t incStart = 0;                               // this node's incident entries: pool[incStart .. incStart + incLen)
     int32_t incLen = 0, incCap = 0;
-    uint8_t flag = 1;                                   // bit0: slot changed since last re-thread, bit1: dirty in this pass
+    uint8_t flag = 1;                                   // bit0: slot changed since last re-thread, bit1: dirty in this pass, bit2: `ord` of the entries lags (Tree::ordFix)
 };
 
 class Forest {
@@ -74,8 +85,13 @@ class Forest {
     int32_t threadPosOf(int32_t v) const { return node[v].threadPos; }
     const Tree &tree(int32_t slot) const { return trees[slot]; }
     int8_t typeOf(int32_t v) const { return node[v].slot < 0 ? (int8_t) TREE_FREE : trees[node[v].slot].type; }
-    // index of basic arc a (ends u, v) in arcs(tree): scans the two short incident lists
+    // index of basic arc a (ends u, v) in arcs(tree): scans the two short incident lists (explicit order, or a tail arc)
     int32_t posOfArc(int32_t a, int32_t u, int32_t v) const;
+    // materialise arcs(tree) (and the positions in the incident entries) of a tree whose order is implicit
+    void ensureArcs(int32_t slot);
+    // the incident entry of arc a at node v (nullptr if absent)
+    const Inc *entryOf(int32_t v, int32_t a) const;
+    bool fastSplit = true;                              // GNE_FOREST_FAST=0: always the reference's full-DFS split
     int numSlots() const { return (int) trees.size(); }
 
     // slots whose structure or extra arc changed since the caller last cleared this list
@@ -89,7 +105,7 @@ class Forest {
 
     std::vector<NodeRec> node;
     double secsSplit = 0, secsReindex = 0, secsMerge = 0;
-    int64_t nodesSplit = 0, nodesReindex = 0, callsReindex = 0;   // wall-clock split of the forest work
+    int64_t nodesSplit = 0, nodesReindex = 0, callsReindex = 0, nodesMaterialized = 0, callsSplitFast = 0, callsSplitFull = 0;   // wall-clock split of the forest work
 
   private:
     int n = 0;
@@ -104,6 +120,7 @@ class Forest {
     void compactPool();
 
     std::vector<int32_t> stackA, stackB, stackC;        // DFS scratch
+    std::vector<std::pair<int32_t, int32_t> > sortBuf;
     std::vector<int32_t> oldNodes, oldArcs;             // the vectors of a tree being split
 
     int32_t newTree(int8_t type, int32_t rootNode);
@@ -114,6 +131,9 @@ class Forest {
     void mergeInto(int32_t tX, int32_t tII, int32_t av);
     void expandWithArc(int32_t t, int32_t av);
     int32_t split(int32_t t, int32_t removedArc);       // returns the slot of the bottom part; t keeps the top
+    int32_t splitFull(int32_t t, int32_t removedArc);   // the reference's DFS over the whole tree (trees.cpp:502-566)
+    void pushNode(int32_t slot, int32_t v) { node[v].nodeIdx = (int32_t) trees[slot].nodes.size(); trees[slot].nodes.push_back(v); }
+    void applyOrdFix(Tree &t);
     void reindex(int32_t slot);
     void rethreadSubtree(int32_t slot, const Attach &at);
 };

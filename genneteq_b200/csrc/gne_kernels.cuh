@@ -635,6 +635,21 @@ __global__ void k_pot_finalize(int n, const double *__restrict__ A0, const doubl
     if (i < n) pi[i] = __dadd_rn(A0[i], __dmul_rn(A1[i], __ldg(T + S[i])));
 }
 
+// the same for every node of (at most 8) given trees: one coalesced sweep over the slot column instead of a node
+// list - 4 B per node read, 24 B per member; what a changed theta of a big tree costs (gnePotential.cpp:127-135)
+struct SlotSet { int n; int32_t slot[8]; };
+__global__ void k_pot_finalize_slots(int n, const double *__restrict__ A0, const double *__restrict__ A1,
+                                     const int32_t *__restrict__ S, const double *__restrict__ T, double *__restrict__ pi, SlotSet ss)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t s = S[i];
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hit |= (k < ss.n && ss.slot[k] == s);
+    if (hit) pi[i] = __dadd_rn(A0[i], __dmul_rn(A1[i], __ldg(T + s)));
+}
+
 __global__ void k_pot_set(int64_t count, const int32_t *__restrict__ node, const double *__restrict__ val, double *pi)
 {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;

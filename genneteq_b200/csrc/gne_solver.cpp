@@ -208,6 +208,7 @@ void GenNetEq::checkVarForBlocking(int32_t v)                     // genneteq.h:
 void GenNetEq::computeFlowsTypeI(int32_t slot)                    // gneFlow.cpp:480-560
 {
     forest.ensureThreads(slot);
+    forest.ensureArcs(slot);                            // (the full sweep walks arcs(tree) in order)
     const Tree &t = forest.tree(slot);
     const int32_t ex = t.extraArc;
     const int32_t alpha = tail[ex], beta = head[ex];
@@ -370,6 +371,41 @@ void GenNetEq::computeFlowsSparse(int32_t slot, const int32_t *starts, int nStar
         // the child with the highest incident index is processed first: push it last
         for (size_t c = 0; c < actKids.size(); ++c) actStack.push_back(actKids[c]);
     }
+    // arcsInTree order of the active arcs when the tree's order is implicit (Forest::split): the split DFS restricted to
+    // the active nodes - a node's arcs in the snapshot order of its incident list (`ord`), its children entered from the
+    // last to the first - then the arcs appended since the last split (tail), by their explicit positions
+    const bool implicitOrder = t.implicitOrder;
+    if (implicitOrder) {
+        orderedArcs.clear(); activeKeys.clear();
+        actStack.clear();
+        actStack.push_back(nodeMark[h] - 1);
+        while (!actStack.empty()) {
+            const int32_t top = actStack.back(); actStack.pop_back();
+            const int32_t p = activeNodes[top];
+            ordKids.clear();
+            for (int32_t c = actHead[top]; c >= 0; c = actNext[c]) {
+                const int32_t a = forest.predArcOf(activeNodes[c]);
+                const Inc *e = forest.entryOf(p, a);
+                if (e->pos >= POS_TAIL_BASE || e->pos == POS_TAIL_OTHER) {
+                    // an appended subtree: all its arcs sit in the tail with explicit positions
+                    actKids.clear(); actKids.push_back(c);
+                    while (!actKids.empty()) {
+                        const int32_t x = actKids.back(); actKids.pop_back();
+                        const int32_t ax = forest.predArcOf(activeNodes[x]);
+                        activeKeys.push_back(std::make_pair(forest.posOfArc(ax, tail[ax], head[ax]), ax));
+                        for (int32_t y = actHead[x]; y >= 0; y = actNext[y]) actKids.push_back(y);
+                    }
+                } else {
+                    ordKids.push_back(std::make_pair(e->ord, c));
+                }
+            }
+            if (ordKids.size() > 1) std::sort(ordKids.begin(), ordKids.end());
+            for (size_t c = 0; c < ordKids.size(); ++c) orderedArcs.push_back(forest.predArcOf(activeNodes[ordKids[c].second]));
+            for (size_t c = 0; c < ordKids.size(); ++c) actStack.push_back(ordKids[c].second);     // the last entry is entered first
+        }
+        std::sort(activeKeys.begin(), activeKeys.end());
+        for (size_t k = 0; k < activeKeys.size(); ++k) orderedArcs.push_back(activeKeys[k].second);
+    }
     for (size_t q = 0; q < na; ++q) nodeMark[activeNodes[q]] = 0;
     activeNodes.swap(actOrder);
     activeArcs.clear();
@@ -396,13 +432,17 @@ void GenNetEq::computeFlowsSparse(int32_t slot, const int32_t *starts, int nStar
     const double theta = (-1.0 * supA0[h]) / supA1[h];
     supA0[h] = 0.0; supA1[h] = 0.0;
     // ratio test in arcsInTree order: sort the few active arcs by their index in arcs(tree)
-    activeKeys.clear();
-    for (size_t k = 0; k < activeArcs.size(); ++k) {
-        const int32_t a = activeArcs[k];
-        activeKeys.push_back(std::make_pair(forest.posOfArc(a, tail[a], head[a]), a));
+    if (implicitOrder) {
+        activeArcs = orderedArcs;
+    } else {
+        activeKeys.clear();
+        for (size_t k = 0; k < activeArcs.size(); ++k) {
+            const int32_t a = activeArcs[k];
+            activeKeys.push_back(std::make_pair(forest.posOfArc(a, tail[a], head[a]), a));
+        }
+        std::sort(activeKeys.begin(), activeKeys.end());
+        for (size_t k = 0; k < activeArcs.size(); ++k) activeArcs[k] = activeKeys[k].second;
     }
-    std::sort(activeKeys.begin(), activeKeys.end());
-    for (size_t k = 0; k < activeArcs.size(); ++k) activeArcs[k] = activeKeys[k].second;
     for (size_t k = 0; k < activeArcs.size(); ++k) {
         const int32_t a = activeArcs[k];
         const double p = flowA1[a] * theta;
@@ -466,7 +506,7 @@ inline bool GenNetEq::relabelNode(int32_t j, int32_t slot)
 
 int GenNetEq::computePotentials()
 {
-    upNode.clear(); upSlot.clear(); upA0.clear(); upA1.clear(); upThetaSlot.clear(); upTheta.clear(); upFinal.clear();
+    upNode.clear(); upSlot.clear(); upA0.clear(); upA1.clear(); upThetaSlot.clear(); upTheta.clear(); upFinal.clear(); upFinalSlots.clear();
     bool finalizeAll = false;
     if ((int) thetaOfSlot.size() < forest.numSlots()) thetaOfSlot.resize(forest.numSlots(), 0.0);
     if (allPotDirty) {
@@ -501,10 +541,11 @@ int GenNetEq::computePotentials()
         if (allPotDirty || memcmp(&thetaOfSlot[slot], &theta, 8) != 0) {
             thetaOfSlot[slot] = theta;
             upThetaSlot.push_back(slot); upTheta.push_back(theta);
-            // every node of the tree gets a new pi (theta multiplies a1 != 0)
+            // every node of the tree gets a new pi (theta multiplies a1 != 0): a short node list rides with the update,
+            // a big tree is finalized on the device by slot (no O(|tree|) list is built or sent)
             if (!finalizeAll) {
-                if (upFinal.size() + t.nodes.size() > (size_t) numNodes / 4) finalizeAll = true;
-                else upFinal.insert(upFinal.end(), t.nodes.begin(), t.nodes.end());
+                if (t.nodes.size() <= 64 && upFinal.size() + t.nodes.size() <= 160) upFinal.insert(upFinal.end(), t.nodes.begin(), t.nodes.end());
+                else upFinalSlots.push_back(slot);
             }
         }
     }
@@ -512,9 +553,11 @@ int GenNetEq::computePotentials()
     allPotDirty = false;
     if (!dev) return GNE_OK;                            // host-only replay
     // one call: queued setNBarc writes + dirty records + thetas + finalize (gnePotential.cpp:127-135)
-    return gne_pot_update_fused(dev, (int64_t) upNode.size(), upNode.data(), upA0.data(), upA1.data(), upSlot.data(),
-                                (int64_t) upThetaSlot.size(), upThetaSlot.data(), upTheta.data(),
-                                finalizeAll ? -1 : (int64_t) upFinal.size(), upFinal.data());
+    GNE_TRY(gne_pot_update_fused(dev, (int64_t) upNode.size(), upNode.data(), upA0.data(), upA1.data(), upSlot.data(),
+                                 (int64_t) upThetaSlot.size(), upThetaSlot.data(), upTheta.data(),
+                                 finalizeAll ? -1 : (int64_t) upFinal.size(), upFinal.data()));
+    if (!finalizeAll && !upFinalSlots.empty()) GNE_TRY(gne_pot_finalize_slots(dev, (int) upFinalSlots.size(), upFinalSlots.data()));
+    return GNE_OK;
 }
 
 int GenNetEq::fetchViolators(double threshold)
@@ -796,6 +839,7 @@ void GenNetEq::identifyLeavingVar()                               // :166-209
 
 void GenNetEq::applyTreeFlow(int32_t slot)                        // :79-91
 {
+    forest.ensureArcs(slot);
     const Tree &t = forest.tree(slot);
     for (size_t k = 0; k < t.arcs.size(); ++k) {
         const int32_t a = t.arcs[k];
@@ -1001,7 +1045,8 @@ int GenNetEq::replayTrace(int draws, int64_t p1, int64_t total, const int32_t *e
         fprintf(stderr, "host replay: pivot %.3f s, potentials %.3f s, periodic full flows %.3f s; flows %.3f s, trees %.3f s (split %.3f, reindex %.3f, merge %.3f)\n",
                 secsPivot, secsPotentials, secsTotal, secsFlows, secsTrees,
                 forest.secsSplit, forest.secsReindex, forest.secsMerge),
-        fprintf(stderr, "  nodes visited: split %lld, reindex %lld in %lld calls\n", (long long) forest.nodesSplit, (long long) forest.nodesReindex, (long long) forest.callsReindex);
+        fprintf(stderr, "  nodes visited: split %lld (%lld subtree cuts, %lld full DFS), reindex %lld in %lld calls, order materialised %lld\n", (long long) forest.nodesSplit,
+                (long long) forest.callsSplitFast, (long long) forest.callsSplitFull, (long long) forest.nodesReindex, (long long) forest.callsReindex, (long long) forest.nodesMaterialized);
     return GNE_OK;
 }
 

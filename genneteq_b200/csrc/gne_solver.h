@@ -157,14 +157,15 @@ class GenNetEq {
     bool costsOnDevice = false;
     std::vector<int64_t> listPos;
     std::vector<double> listViol;
-    std::vector<int32_t> upNode, upSlot, upThetaSlot, upFinal;
+    std::vector<int32_t> upNode, upSlot, upThetaSlot, upFinal, upFinalSlots;
     std::vector<double> upA0, upA1, upTheta;
     int status = GNE_OK;
     bool allPotDirty = true, hostOnly = false, sparseFlows = true;
     std::vector<int32_t> nodeMark;
     std::vector<int32_t> actHead, actNext, actOrder, actStack, actKids;
     std::vector<int32_t> activeNodes, activeArcsU, activeArcsV;
-    std::vector<std::pair<int32_t, int32_t> > activeKeys;
+    std::vector<std::pair<int32_t, int32_t> > activeKeys, ordKids;
+    std::vector<int32_t> orderedArcs;
 
     // ---- trace / counters
     int32_t *traceE = nullptr, *traceL = nullptr;

@@ -77,6 +77,9 @@ int gne_nb_read(gne_dev *d, int64_t lo, int64_t hi, int32_t *tail, int32_t *head
 int gne_pot_update_nodes(gne_dev *d, int64_t count, const int32_t *node, const double *a0, const double *a1, const int32_t *slot);
 int gne_pot_update_thetas(gne_dev *d, int64_t count, const int32_t *slot, const double *theta);
 int gne_pot_finalize(gne_dev *d);
+/* the same for every node of the given tree slots only (a tree whose theta changed): one sweep over the
+ * slot column, no node list crosses PCIe                                                       */
+int gne_pot_finalize_slots(gne_dev *d, int count, const int32_t *slots);
 /* all of the above for one pivot in one call (what the solver uses): queued gne_nb_write records,
  * dirty node records, dirty thetas, then the finalize of the nodes in fnode[0..nFinal)
  * (nFinal < 0: every node).  Small updates are one one-CTA kernel reading pinned host memory.  */
