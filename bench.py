@@ -130,12 +130,14 @@ def dbg(msg):
         sys.stderr.flush()
 
 
-def workload_config(wl, gpus, batch=None):
+def workload_config(wl, gpus, batch=None, window="start"):
     """The `config` object - identical in the b200 arm and the reference arm (it describes the workload, not the arm)."""
     n, m, seed, mode, rule, desc = WORKLOADS[wl]
     per_gpu = (25.0 * m / max(gpus, 1) + 8.0 * n) if batch is None else batch * (25.0 * m + 8.0 * n)
     cfg = {"workload": desc, "nodes": n, "arcs": m, "rule": rule,
-           "window": "Phase I from the initial basis: the timed steps are the pivots after the warm-up pivots",
+           "window": ("Phase I from the initial basis: the timed steps are the pivots after the warm-up pivots" if window == "start" else
+                      "deep state: Phase I re-entered at the basis reached after the recorded pivots of tests/golden/deep_%s.npz; "
+                      "the timed steps are the pivots after the warm-up pivots of the re-entered solve" % wl.replace("-", "_")),
            "l2": ("inputs larger than L2 (%.0f MB streamed per pass per GPU)" % (per_gpu / 1e6) if per_gpu >= 200e6 else
                   "L2 flushed between timed device steps (320 MB write)")}
     if batch is not None:
@@ -147,7 +149,7 @@ def workload_config(wl, gpus, batch=None):
 REF_WINDOW_OF = {"c3-lv": "c3_lv", "c2-lv": "c2_lv", "c2-qs": "c2_qs", "c4-batch": "c4_lv"}
 
 
-def parity_block(wl, e, l, dist, rank, world):
+def parity_block(wl, e, l, dist, rank, world, expect=None):
     """The pivots of the e2e window (and its warm-up) checked two ways: every rank holds the same (entering, leaving)
     sequence, and the sequence equals the prefix the UNMODIFIED reference wrote for this workload
     (tests/golden/ref_windows.npz, produced by tests/golden/make_ref_windows.py from oracle/_ref)."""
@@ -161,7 +163,15 @@ def parity_block(wl, e, l, dist, rank, world):
         dist.all_gather(allt, mine)
         blk["ranks_identical"] = all(bool(torch.equal(t, allt[0])) for t in allt)
     name = REF_WINDOW_OF.get(wl)
-    if name is not None:
+    if expect is not None:
+        # deep window: the recorded trace (whose every leaving arc the reference's own pivot() reproduced in replay,
+        # and whose continuation the reference solved identically: tests/golden/README.md) is the expectation
+        re_, rl_ = expect
+        k = min(len(e), len(re_))
+        ok = bool(np.array_equal(e[:k], re_[:k]) and np.array_equal(l[:k], rl_[:k]))
+        blk["vs_ref"] = "ok" if ok else "MISMATCH"
+        blk["ref_pivots_compared"] = int(k)
+    elif name is not None:
         from oracle_util import ref_window
         re_, rl_, md5 = ref_window(name)
         k = min(len(e), len(re_))
@@ -207,13 +217,31 @@ if kind == "reference":
     init_s = time.time() - t0
     ref.ref_set_rules(RULES[req["rule"]], RULES[req["rule"]])
     fin = C.c_int(0)
+    replay = None
+    if req.get("deep"):
+        # --window deep: reach the recorded basis with the reference's own pivot() applied to the recorded pivots
+        # (ref_driver.cpp replayTraced: every leaving arc is checked against the trace), then solve on from there
+        fx = np.load(req["deep"])
+        fe = np.ascontiguousarray(fx["e"], np.int32); fl = np.ascontiguousarray(fx["l"], np.int32)
+        ref.ref_replay.restype = C.c_long; ref.ref_trace_len.restype = C.c_long
+        t0 = time.time()
+        mm = ref.ref_replay(1, ip(fe), ip(fl), C.c_long(len(fe)), 1 if req["rule"].startswith("LV") else 0)
+        replay = dict(pivots=int(len(fe)), first_mismatch=int(mm), seconds=time.time() - t0)
+        if mm != -1: raise SystemExit("reference replay diverged from the recorded trace at pivot %%d" %% mm)
+        te = np.zeros(4096, np.int32); tl = np.zeros(4096, np.int32)
+        ref.ref_set_trace(ip(te), ip(tl), C.c_long(4096))
     def run(w, k):
         ref.ref_set_window(C.c_long(w))
         ref.ref_solve(1, C.c_long(w + k), C.byref(fin))
         t0 = np.zeros(5); t1 = np.zeros(5)
         ref.ref_get_window_timers(dp(t0)); ref.ref_get_timers(dp(t1))
+        if replay is not None:
+            k2 = min(int(ref.ref_trace_len()), 4096, len(fx["e2"]))
+            replay["continuation_pivots_compared"] = k2
+            replay["continuation_equals_recorded"] = bool(np.array_equal(te[:k2], fx["e2"][:k2]) and np.array_equal(tl[:k2], fx["l2"][:k2]))
         return t1 - t0
 else:
+    replay = None
     lib = oracle_lib()
     t0 = time.time()
     h = C.c_void_p(lib.orc_create(req["n"], C.c_long(req["m"]), ip(g["tail"]), ip(g["head"]), dp(g["ub"]), dp(g["cost"]),
@@ -231,7 +259,7 @@ else:
 # computePotentials + pricing + pivot of every iteration (the whole loop body of genneteq.cpp:82-106).
 # The sample is sized from a per-arc estimate (~55 ns per arc priced once the arc objects no longer fit in
 # cache) so that the run stays within the time budget; the window is pivots [warmup, warmup + steps).
-per = 55e-9 * req["m"] + 1.0e-7 * req["n"]
+per = 55e-9 * req["m"] + 1.0e-7 * req["n"] + (5.0e-8 * req["n"] if req.get("deep") else 0.0)
 steps, warmup = req["steps"], req["warmup"]
 if per * (steps + warmup) > req["budget_s"]:
     steps = max(3, int(req["budget_s"] / per) - warmup)
@@ -239,16 +267,20 @@ if per * (steps + warmup) > req["budget_s"]:
 tm = run(warmup, steps)
 loop_s = tm[0] + tm[1] + tm[2]
 out = dict(kind=kind, steps=steps, loop_s=loop_s, pricing_s=tm[0], potentials_s=tm[1], pivot_s=tm[2], arcs_priced=tm[4],
-           init_s=init_s, warmup=warmup)
+           init_s=init_s, warmup=warmup, replay=replay)
 json.dump(out, open(req["out"], "w"))
 """
 
 
-def run_reference_sample(wl, steps, warmup, budget_s):
+def deep_fixture(wl):
+    return os.path.join(ROOT, "tests", "golden", "deep_%s.npz" % wl.replace("-", "_"))
+
+
+def run_reference_sample(wl, steps, warmup, budget_s, deep=False):
     n, m, seed, mode, rule, desc = WORKLOADS[wl]
     d = tempfile.mkdtemp(prefix="gne_bench_")
     req = dict(n=n, m=m, seed=seed, mode=mode, rule=rule, steps=steps, warmup=warmup, budget_s=budget_s,
-               out=os.path.join(d, "out.json"))
+               out=os.path.join(d, "out.json"), deep=deep_fixture(wl) if deep else None)
     rp = os.path.join(d, "req.json")
     json.dump(req, open(rp, "w"))
     code = _REF_CHILD % dict(root=ROOT)
@@ -261,17 +293,19 @@ def reference_arm(args):
     if rank != 0:
         return 0
     n, m, seed, mode, rule, desc = WORKLOADS[args.workload]
-    r = run_reference_sample(args.workload, args.steps, max(args.warmup, 1), budget_s=150.0)
+    deep = args.window == "deep"
+    r = run_reference_sample(args.workload, args.steps, max(args.warmup, 1), budget_s=150.0, deep=deep)
     value = r["arcs_priced"] / r["loop_s"]
     cores = 1
-    sample = "%d simplex iterations after %d warm-up iterations, Phase I from the initial basis, single thread (the reference has none)" % (
-        r["steps"], r["warmup"])
+    sample = "%d simplex iterations after %d warm-up iterations, %s, single thread (the reference has none)" % (
+        r["steps"], r["warmup"], "Phase I from the recorded deep basis (reached by replaying the recorded pivots through the reference's own pivot())"
+        if deep else "Phase I from the initial basis")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": r["steps"],
         "warmup": r["warmup"], "ms_per_step": 1e3 * r["loop_s"] / r["steps"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.workload, args.gpus),
-        "host_cores_present": os.cpu_count(),
+        "config": workload_config(args.workload, args.gpus, window=args.window),
+        "host_cores_present": os.cpu_count(), "replay": r.get("replay"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample,
                          "pricing_only_arcs_per_s": r["arcs_priced"] / r["pricing_s"] if r["pricing_s"] > 0 else None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -297,8 +331,11 @@ def b200_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, m, seed, mode, rule, desc = WORKLOADS[args.workload]
     g, rule, desc = make_instance(args.workload)
+    deep = args.window == "deep"
+    fx = np.load(deep_fixture(args.workload)) if deep else None
+    P = len(fx["e"]) if deep else 0
     s = gne.Solver(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"], device=local, rule1=rule,
-                   trace_cap=max(1024, args.steps + args.warmup + 16))
+                   trace_cap=max(1024, P + args.steps + args.warmup + 16))
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -319,6 +356,10 @@ def b200_arm(args):
     # ---- e2e: one gne_solver_solve call; W warm-up pivots, then exactly K pivots timed inside the
     # library's loop (host clock, device synchronised at both edges of the window)
     W = max(args.warmup, 3)
+    if deep:
+        t0 = time.time()
+        s.solve(True, P)                        # untimed: reach the recorded basis (the trace is compared below)
+        dbg("deep basis reached: %d pivots in %.1f s" % (P, time.time() - t0))
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -334,15 +375,24 @@ def b200_arm(args):
     pivots = int(c1["pivots"] - c0["pivots"])
     arcs_e2e = c1["arcs_priced"] - c0["arcs_priced"]
     te, tl = s.trace
-    parity = parity_block(args.workload, te, tl, dist, rank, world)
+    parity = parity_block(args.workload, te, tl, dist, rank, world,
+                          expect=(np.concatenate([fx["e"], fx["e2"]]), np.concatenate([fx["l"], fx["l2"]])) if deep else None)
     dev = s.device()
     N = m
     # ---- device-resident steps: K x (finalize + pricing pass + reduction [+ exchange]), CUDA events
     flush = (25.0 * N / world + 8 * n) < 200e6  # per-GPU working set not larger than L2 => flush between steps
-    dev.bench_price_lv(max(args.warmup, 3), flush)
-    barrier()
-    dbg("device warm-up steps done")
-    ms_step, ms_tiles = dev.bench_price_lv(args.steps, flush)
+    qs_arcs = None
+    if rule.startswith("QS") and world == 1:
+        # the block rule's own kernels (k_qs_tiles + k_qs_finish per window), as the solver issues them
+        dev.bench_price_qs(max(args.warmup, 3), n, flush)
+        ms_step, qs_launched, qs_scanned = dev.bench_price_qs(args.steps, n, flush)
+        ms_tiles = ms_step
+        qs_arcs = (float(qs_launched.sum()), float(qs_scanned.sum()), float(qs_launched.mean()))
+    else:
+        dev.bench_price_lv(max(args.warmup, 3), flush)
+        barrier()
+        dbg("device warm-up steps done")
+        ms_step, ms_tiles = dev.bench_price_lv(args.steps, flush)
     barrier()
     dbg("device steps done: kernel ms mean %.4f min %.4f max %.4f | step ms mean %.4f min %.4f max %.4f" % (
         ms_tiles.mean(), ms_tiles.min(), ms_tiles.max(), ms_step.mean(), ms_step.min(), ms_step.max()))
@@ -352,7 +402,7 @@ def b200_arm(args):
             if name.startswith(("production", "tma<256thr,4it,3st> 148x2", "k_price_lv")):
                 dbg("variant %-60s mean %.2f us best %.2f us" % (name, mean * 1e3, best * 1e3))
     launches = int(s.counters()["launches"] - c0["launches"])     # e2e window + device steps (warm-up excluded from neither)
-    lv_kernel = {"stream": "k_price_lv_stream", "tiles": "k_price_lv_tiles"}[dev.last_lv_kernel()]
+    lv_kernel = "k_qs_tiles + k_qs_finish" if qs_arcs else {"stream": "k_price_lv_stream", "tiles": "k_price_lv_tiles"}[dev.last_lv_kernel()]
     dev.close()
     if dist is not None:
         t = torch.tensor([e2e_s, float(ms_step.sum()), float(ms_tiles.mean())], dtype=torch.float64, device="cuda")
@@ -371,12 +421,16 @@ def b200_arm(args):
     peak, peak_src = peaks()
     shard_arcs = N / world
     alg_bytes = 25.0 * shard_arcs + 8.0 * n
+    if qs_arcs:
+        # block rule: a pass prices a window of the list, not the list - arcs the kernels covered per pass
+        value = qs_arcs[0] / (step_sum_ms * 1e-3)
+        alg_bytes = 25.0 * qs_arcs[2] + 8.0 * n
     achieved = alg_bytes / (tiles_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": step_sum_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.workload, world),
+        "config": workload_config(args.workload, world, window=args.window),
         "sharding": "contiguous position ranges over %d GPU(s); per-pivot exchange of the per-shard record: %s" % (world, xmode),
         "parity": parity,
         "e2e": {"value": arcs_e2e / e2e_s, "unit": UNIT,
@@ -390,9 +444,12 @@ def b200_arm(args):
                      "traffic": ncu_traffic(args.workload, world, lv_kernel), "kernel": lv_kernel, "kernel_ms": tiles_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
     }
+    if qs_arcs:
+        line["block_rule"] = {"arcs_covered_by_kernels_per_pass": qs_arcs[2], "arcs_consumed_by_rule_per_pass": qs_arcs[1] / args.steps,
+                              "note": "value / roofline count the arcs the window kernels priced; a pass = window kernel + finish kernel per window"}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = run_reference_sample(args.workload, 12, 2, budget_s=25.0)
+            r = run_reference_sample(args.workload, 12, 2, budget_s=25.0, deep=deep)
             line["cpu_baseline"] = {
                 "value": r["arcs_priced"] / r["loop_s"], "unit": UNIT, "cores": 1, "kind": r["kind"],
                 "sample": "%d simplex iterations after %d warm-up iterations of the same workload, single thread "
@@ -585,6 +642,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3-lv", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--window", default="start", choices=["start", "deep"],
+                    help="start: pivots from the initial basis (default); deep: from the recorded basis of tests/golden/deep_<workload>.npz")
     ap.add_argument("--batch", type=int, default=32, help="instances per GPU for --workload c4-batch")
     args = ap.parse_args()
     if args.workload == "c4-batch":

@@ -70,6 +70,7 @@ SIGNATURES = {
     "gne_dev_last_lv_kernel": (C.c_int, [_vp]),
     "gne_dev_launch_count": (C.c_int64, [_vp]),
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
+    "gne_bench_price_qs": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _f32p, _i64p, _i64p]),
     "gne_comm_unique_id": (C.c_int, [_u8p]),
     "gne_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
     "gne_comm_init_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -337,6 +338,12 @@ class Device:
                                    _p(mt, _f32p)), "gne_bench_price_lv")
         return ms, mt
 
+
+    def bench_price_qs(self, reps, want, flush_l2=False):
+        """`reps` quickSelect passes, device-timed: (ms per pass, arcs the kernels covered, arcs the rule consumed)."""
+        ms = np.zeros(reps, np.float32); al = np.zeros(reps, np.int64); sc = np.zeros(reps, np.int64)
+        _ck(lib.gne_bench_price_qs(self.h, reps, 1 if flush_l2 else 0, want, _p(ms, _f32p), _p(al, _i64p), _p(sc, _i64p)), "gne_bench_price_qs")
+        return ms, al, sc
 
     def bench_variants(self, reps=10):
         """Tuning builds only (GNE_TUNING_LIB=1 + `make -C genneteq_b200/csrc tuning`)."""

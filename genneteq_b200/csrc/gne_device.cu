@@ -136,6 +136,7 @@ struct gne_dev {
     int64_t launches = 0;
     int64_t h2dBytes = 0, d2hBytes = 0;
     int64_t qsWindow = 0;                          // adaptive window of the quickSelect scan
+    int64_t qsArcsLaunched = 0;                    // arcs the quickSelect kernels were launched over (whole windows)
     NbWriteOps pending{};                          // queued gne_nb_write records (<= 8)
     bool stageInFlight = false;                    // the staging buffer feeds a kernel not yet synchronised
     LvCtas lvc{};                                  // per-CTA records of the TMA-streamed LV pass
@@ -1061,6 +1062,7 @@ static int qs_scan(gne_dev *d, int64_t cursor, int64_t N, int64_t jTotal, int64_
         const int64_t jHi = std::min(jTotal, jLo + d->qsWindow);
         const int G = (int) ((jHi - jLo + QTILE - 1) / QTILE);
         if (d->timing) CK(cudaEventRecord(d->ev0, d->stream));
+        d->qsArcsLaunched += jHi - jLo;
         k_qs_tiles<<<G, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, d->qs);
         k_qs_finish<<<1, TILE_THREADS, 0, d->stream>>>(nb, d->pi, cursor, N, jLo, jHi, jTotal, d->qs, G, want, d->qsDev, st, first, ++d->qsSeq);
         if (d->timing) CK(cudaEventRecord(d->ev1, d->stream));
@@ -1287,6 +1289,37 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
         CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
         for (int i = 0; i < reps; ++i) CK(cudaEventElapsedTime(pass == 0 ? &msTiles[i] : &msStep[i], d->benchEv[2 * i], d->benchEv[2 * i + 1]));
     }
+    return GNE_OK;
+}
+
+// The block rule's device leg: `reps` quickSelect passes as the solver issues them (window kernel + finish kernel per
+// window, the cursor advancing by what each pass scanned), each pass timed with CUDA events around its kernels.
+// arcsLaunched[i] = arcs the kernels of pass i were launched over (whole windows), arcsScanned[i] = what the rule consumed.
+extern "C" int gne_bench_price_qs(gne_dev *d, int reps, int flushL2, int64_t want, float *msStep, int64_t *arcsLaunched, int64_t *arcsScanned)
+{
+    CK(cudaSetDevice(d->device));
+    if (d->nranks != 1) { gne_set_error("gne_bench_price_qs: single GPU only"); return GNE_ERR_UNSUPPORTED; }
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    if (flushL2 && !d->flushBuf) {
+        d->flushLen = (int64_t) 40 * 1024 * 1024;
+        CK(cudaMalloc(&d->flushBuf, 8 * (size_t) d->flushLen));
+    }
+    const bool keep = d->timing;
+    d->timing = true;
+    const int64_t N = d->N;
+    int64_t cursor = 0;
+    for (int i = 0; i < reps; ++i) {
+        if (flushL2) { k_flush_l2<<<148 * 8, 256, 0, d->stream>>>(d->flushBuf, d->flushLen); ++d->launches; }
+        const int64_t before = d->qsArcsLaunched;
+        float ms = 0.f;
+        rc = qs_scan(d, cursor, N, N, want, &ms); if (rc) { d->timing = keep; return rc; }
+        msStep[i] = ms;
+        arcsLaunched[i] = d->qsArcsLaunched - before;
+        const int64_t sc = (d->qsState->stopJ >= 0) ? d->qsState->stopJ + 1 : N;
+        arcsScanned[i] = sc;
+        cursor += sc; if (cursor >= N) cursor -= N;
+    }
+    d->timing = keep;
     return GNE_OK;
 }
 

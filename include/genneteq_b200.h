@@ -150,6 +150,10 @@ int64_t gne_dev_launch_count(gne_dev *d);
  * between steps, outside the events.                                                          */
 int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles);
 
+/* the same for the block rule: `reps` quickSelect passes as gne_price_qs issues them (cursor advancing), each timed
+ * with CUDA events around its kernels; arcsLaunched = arcs the kernels covered, arcsScanned = arcs the rule consumed */
+int gne_bench_price_qs(gne_dev *d, int reps, int flushL2, int64_t want, float *msStep, int64_t *arcsLaunched, int64_t *arcsScanned);
+
 /* --- multi-GPU exchange (one process per GPU; NCCL over NVLink) --- */
 /* 128-byte opaque id made on rank 0 and broadcast by the caller (torch.distributed)           */
 int gne_comm_unique_id(uint8_t id[128]);

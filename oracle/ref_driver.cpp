@@ -169,6 +169,32 @@ class RefDriver : public GenNetEq
         return loopIter;
     }
 
+    // ---- replay of a recorded pivot sequence with the reference's OWN pivot(): the entering arc of each pivot comes
+    // from the trace (no pricing pass, no potentials - pivot() reads neither), flows / ratio test / leaving arc / basis
+    // and tree updates are the reference's, and the leaving arc it picks is compared with the trace.  `draws` = drand48
+    // calls the rule would have made per pricing call (LV 1, QS / CL / FV 0); the cycling override draws once
+    // (gnePivotRules.cpp:307-362).  Reaches a state deep in a solve in minutes instead of hours; returns the index of
+    // the first pivot whose leaving arc differs from the trace, or -1.
+    long replayTraced(bool usePresolve, const int *e, const int *l, long count, int draws)
+    {
+        initializeStats(usePresolve);
+        setVariableCosts();
+        computeFlows();
+        for (long k = 0; k < count; ++k) {
+            if ((loopIter % 1000) == 0) computeFlows(2);
+            if (cyclingDetected) (void) drand48();
+            else for (int d = 0; d < draws; ++d) (void) drand48();
+            eVar = vars[e[k]];
+            isOptimal = false;
+            pivot();
+            if (lVar == NULL || lVar->varIndex != l[k]) return k;
+            ++loopIter;
+            ++pivotsDone;
+            presolve ? ++phaseIiters : ++phaseIIiters;
+        }
+        return -1;
+    }
+
     // ---- one pricing call at the current state, leaving the solver state untouched
     // (drand48 stream and rule cursors saved/restored), for same-state A/B timing.
     int priceOnce(double *secs)
@@ -260,6 +286,11 @@ long ref_trace_len(void) { return g_solver->traceLen; }
 long ref_solve(int presolve, long maxPivots, int *finished)
 {
     return g_solver->solveTraced(presolve != 0, maxPivots, finished);
+}
+
+long ref_replay(int presolve, const int *e, const int *l, long count, int draws)
+{
+    return g_solver->replayTraced(presolve != 0, e, l, count, draws);
 }
 
 int ref_price_once(double *secs) { return g_solver->priceOnce(secs); }
