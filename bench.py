@@ -544,6 +544,11 @@ def batch_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     W = max(args.warmup, 3)
+    # every instance's persistent pricing pass gets its share of the CTA slots (2 per SM) so that the B passes are
+    # resident together instead of queueing behind each other
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    ctas = max(1, (2 * sms) // B)
+    os.environ["GNE_STREAM_CTAS"] = str(ctas)
     solvers = []
     for i in range(B):
         g = gne.generate_instance(n, m, seed0 + rank * B + i, mode)
@@ -589,7 +594,10 @@ def batch_arm(args):
     for t in threads:
         t.join()
     torch.cuda.synchronize()
-    dev_wall = time.perf_counter() - t0
+    dev_wall_host = time.perf_counter() - t0
+    # device time of the leg: every instance's steps are bracketed by CUDA events on its own stream (both loops of
+    # gne_bench_price_lv); the batch is done when the slowest instance is
+    dev_wall = max(float(r[0].sum() + r[1].sum()) for r in res) * 1e-3
     clocks = sampler.stop()
     tiles_ms = float(np.mean([r[1].mean() for r in res]))
     launches += sum(d.launch_count() for d in devs) - launches_before
@@ -617,9 +625,12 @@ def batch_arm(args):
             "parity": parity,
             "e2e": {"value": arcs / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(pivots, 1), "d2h_bytes_per_step": d2h / max(pivots, 1),
                     "pivots_per_s": pivots / wall, "ms_per_pivot_per_instance": 1e3 * wall / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": alg / (tiles_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (tiles_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_price_lv_tiles (one instance's pass, timed while the other streams run)",
+            "gpu_launches": int(launches), "clocks": clocks, "device_leg_host_wall_s": dev_wall_host,
+            # per GPU: the B concurrent passes together move B x (25 B x arcs + 8 B x nodes) per round of passes
+            "roofline": {"bound": "hbm", "achieved": B * alg * 2 * args.steps / dev_wall / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": B * alg * 2 * args.steps / dev_wall / 1e9 / peak, "traffic": None,
+                         "kernel": "k_price_lv_stream, %d CTAs per instance, the %d instances of a GPU resident together "
+                                   "(aggregate bytes of all passes / wall time of the device leg; kernel_ms = one instance's pass)" % (ctas, B),
                          "kernel_ms": tiles_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
     if not args.no_cpu_baseline and world == 1:
         r = batch_reference(args, B, 12, 2)

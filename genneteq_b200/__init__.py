@@ -68,6 +68,8 @@ SIGNATURES = {
     "gne_dev_set_timing": (C.c_int, [_vp, C.c_int]),
     "gne_dev_set_lv_kernel": (C.c_int, [_vp, C.c_int]),
     "gne_dev_last_lv_kernel": (C.c_int, [_vp]),
+    "gne_dev_set_fast_math": (C.c_int, [_vp, C.c_int]),
+    "gne_dev_set_stream_ctas": (C.c_int, [_vp, C.c_int]),
     "gne_dev_launch_count": (C.c_int64, [_vp]),
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
     "gne_bench_price_qs": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _f32p, _i64p, _i64p]),
@@ -316,6 +318,19 @@ class Device:
         rc = np.empty(hi - lo)
         _ck(lib.gne_reduced_costs(self.h, lo, hi, _p(rc, _f64p)), "gne_reduced_costs")
         return rc
+
+    def pot_finalize_slots(self, slots):
+        """pi = a0 + a1 * theta[slot] for every node of the given tree slots only (gne_pot_finalize_slots)."""
+        sl = _arr(slots, np.int32)
+        _ck(lib.gne_pot_finalize_slots(self.h, len(sl), _p(sl, _i32p)), "gne_pot_finalize_slots")
+
+    def set_stream_ctas(self, ctas):
+        """CTAs of this handle's persistent LV pass (0 = the whole device); batches share the SMs."""
+        _ck(lib.gne_dev_set_stream_ctas(self.h, int(ctas)), "gne_dev_set_stream_ctas")
+
+    def set_fast_math(self, on):
+        """Fused multiply-add in the reduced cost / potential finalize (non-parity mode); per device."""
+        _ck(lib.gne_dev_set_fast_math(self.h, 1 if on else 0), "gne_dev_set_fast_math")
 
     def set_lv_kernel(self, mode):
         _ck(lib.gne_dev_set_lv_kernel(self.h, dict(auto=0, tiles=1, stream=2)[mode]), "gne_dev_set_lv_kernel")

@@ -141,6 +141,7 @@ struct gne_dev {
     bool stageInFlight = false;                    // the staging buffer feeds a kernel not yet synchronised
     LvCtas lvc{};                                  // per-CTA records of the TMA-streamed LV pass
     int streamGrid = 0;                            // 2 CTAs per SM
+    int streamGridFull = 0;                        // ... of the whole device (gne_dev_set_stream_ctas lowers streamGrid for batches)
     unsigned int *lvTicket = nullptr;              // counters of the streamed pass, one 128-byte line each (zero between passes):
     unsigned int *lvArrive = nullptr;              //   last-CTA ticket, first-CTA election, next tile, update-visible flag
     unsigned long long *lvTileCtr = nullptr, *lvUpdFlag = nullptr;
@@ -279,6 +280,8 @@ static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cudaDevice);
         d->streamGrid = sms * ST_CTAS_PER_SM;
         if (d->streamGrid > 2 * ST_THREADS) d->streamGrid = 2 * ST_THREADS;        // the reduction reads two records per thread
+        d->streamGridFull = d->streamGrid;
+        { const char *sg = getenv("GNE_STREAM_CTAS"); if (sg && atoi(sg) > 0) d->streamGrid = std::min(d->streamGridFull, atoi(sg)); }
         CK(cudaMalloc(&d->lvc.rec, sizeof(CtaRec) * (size_t) d->streamGrid));
         CK(cudaMalloc(&d->lvTicket, 512)); CK(cudaMemset(d->lvTicket, 0, 512));
         d->lvArrive = d->lvTicket + 32;
@@ -294,6 +297,7 @@ static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity
     memset(d->lvRes, 0, sizeof(LvResult));
     { const char *tm = getenv("GNE_TIMING"); d->timing = tm && tm[0] == '1'; }
     { const char *pd = getenv("GNE_PDL"); d->pdl = !(pd && pd[0] == '0'); }
+    { const char *fm = getenv("GNE_FAST_MATH"); const int v = (fm && fm[0] == '1') ? 1 : 0; CK(cudaMemcpyToSymbol(c_gne_fast_math, &v, sizeof(int))); }
     { const char *lk = getenv("GNE_LV_KERNEL"); if (lk) d->lvKernelMode = !strcmp(lk, "stream") ? 2 : (!strcmp(lk, "tiles") ? 1 : 0); }
     memset(d->qsState, 0, sizeof(QsState));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
@@ -335,6 +339,21 @@ extern "C" int gne_dev_sync(gne_dev *d)
 
 extern "C" int gne_dev_last_kernel_ms(gne_dev *d, float *ms) { *ms = d->lastMs; return GNE_OK; }
 extern "C" int gne_dev_set_timing(gne_dev *d, int on) { d->timing = on != 0; return GNE_OK; }
+extern "C" int gne_dev_set_stream_ctas(gne_dev *d, int ctas)
+{
+    if (ctas < 0) { gne_set_error("gne_dev_set_stream_ctas: negative"); return GNE_ERR_ARG; }
+    d->streamGrid = ctas == 0 ? d->streamGridFull : std::min(ctas, d->streamGridFull);
+    return GNE_OK;
+}
+extern "C" int gne_dev_set_fast_math(gne_dev *d, int on)
+{
+    CK(cudaSetDevice(d->device));
+    { int rcf = flush_pending(d); if (rcf) return rcf; }
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    const int v = on ? 1 : 0;
+    CK(cudaMemcpyToSymbol(c_gne_fast_math, &v, sizeof(int)));
+    return GNE_OK;
+}
 extern "C" int gne_dev_set_lv_kernel(gne_dev *d, int mode) { if (mode < 0 || mode > 2) return GNE_ERR_ARG; d->lvKernelMode = mode; return GNE_OK; }
 extern "C" int gne_dev_last_lv_kernel(gne_dev *d) { return d->lastWasStream ? 2 : 1; }
 extern "C" int64_t gne_dev_launch_count(gne_dev *d) { return d->launches; }

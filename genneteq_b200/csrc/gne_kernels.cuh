@@ -40,10 +40,23 @@ struct NbView {                            // shard of the nonbasic list; index 
     int32_t tile0;                         // tile index of blockIdx.x == 0 (range-restricted passes; default 0)
 };
 
+// "fast, non-parity" mode: 0 = the reference's arithmetic, bit for bit (default); 1 = fused multiply-add
+// in the reduced cost and the potential finalize - one rounding less per value, so the last bit (and with it a pivot
+// tie-break) may differ from the reference; flows / potentials / objective agree to ~1e-9 relative.  Per device,
+// set through gne_dev_set_fast_math.
+__constant__ int c_gne_fast_math = 0;
+
 // computeArcRedCost (genneteq.h:312-318): (cost - pi[tail]) + (mult * pi[head]), unfused
 __device__ __forceinline__ double red_cost(double cost, double mult, double pit, double pih)
 {
+    if (c_gne_fast_math) return fma(mult, pih, __dsub_rn(cost, pit));
     return __dadd_rn(__dsub_rn(cost, pit), __dmul_rn(mult, pih));
+}
+// finalizePotentialsTypeI (gnePotential.cpp:130): pi = a0 + a1 * theta, unfused
+__device__ __forceinline__ double pot_value(double a0, double a1, double theta)
+{
+    if (c_gne_fast_math) return fma(a1, theta, a0);
+    return __dadd_rn(a0, __dmul_rn(a1, theta));
 }
 
 // gnePivotRules.cpp:406-407: violation magnitude |rc| or -1 when the arc is not eligible
@@ -632,7 +645,7 @@ __global__ void k_pot_finalize(int n, const double *__restrict__ A0, const doubl
                                const int32_t *__restrict__ S, const double *__restrict__ T, double *__restrict__ pi)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pi[i] = __dadd_rn(A0[i], __dmul_rn(A1[i], __ldg(T + S[i])));
+    if (i < n) pi[i] = pot_value(A0[i], A1[i], __ldg(T + S[i]));
 }
 
 // the same for every node of (at most 8) given trees: one coalesced sweep over the slot column instead of a node
@@ -647,7 +660,7 @@ __global__ void k_pot_finalize_slots(int n, const double *__restrict__ A0, const
     bool hit = false;
 #pragma unroll
     for (int k = 0; k < 8; ++k) hit |= (k < ss.n && ss.slot[k] == s);
-    if (hit) pi[i] = __dadd_rn(A0[i], __dmul_rn(A1[i], __ldg(T + s)));
+    if (hit) pi[i] = pot_value(A0[i], A1[i], __ldg(T + s));
 }
 
 __global__ void k_pot_set(int64_t count, const int32_t *__restrict__ node, const double *__restrict__ val, double *pi)
@@ -679,7 +692,7 @@ k_update_fused(NbMut nb, NbWriteOps ops, FusedUpdate u, double *A0, double *A1, 
     __syncthreads();
     for (int64_t i = t; i < u.nFinal; i += blockDim.x) {
         const int v = u.fnode[i];
-        pi[v] = __dadd_rn(A0[v], __dmul_rn(A1[v], T[S[v]]));
+        pi[v] = pot_value(A0[v], A1[v], T[S[v]]);
     }
 }
 
@@ -708,7 +721,7 @@ k_update_small(NbMut nb, const __grid_constant__ SmallUpdate u, double *A0, doub
     __syncthreads();
     if (t < u.nFinal) {
         const int v = u.fnode[t];
-        pi[v] = __dadd_rn(A0[v], __dmul_rn(A1[v], T[S[v]]));
+        pi[v] = pot_value(A0[v], A1[v], T[S[v]]);
     }
 }
 
@@ -718,7 +731,7 @@ __global__ void k_pot_finalize_list(int64_t count, const int32_t *__restrict__ f
                                     double *__restrict__ pi)
 {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) { const int v = fnode[i]; pi[v] = __dadd_rn(A0[v], __dmul_rn(A1[v], __ldg(T + S[v]))); }
+    if (i < count) { const int v = fnode[i]; pi[v] = pot_value(A0[v], A1[v], __ldg(T + S[v])); }
 }
 
 __global__ void k_flush_l2(double *buf, int64_t n)

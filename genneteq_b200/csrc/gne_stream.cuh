@@ -242,7 +242,7 @@ __device__ __forceinline__ void st_apply_update(const SmallUpdate &u, const NbMu
     st_sync_consumers();
     if (t < u.nFinal) {
         const int v = u.fnode[t];
-        pm.pi[v] = __dadd_rn(pm.a0[v], __dmul_rn(pm.a1[v], pm.theta[pm.slot[v]]));
+        pm.pi[v] = pot_value(pm.a0[v], pm.a1[v], pm.theta[pm.slot[v]]);
     }
     __threadfence();
     st_sync_consumers();

@@ -139,6 +139,15 @@ int gne_dev_set_timing(gne_dev *d, int on);
  * least ~2.4M arcs, the one-CTA-per-tile kernel below that or while streamed lists keep overflowing),
  * 1 = per-tile kernel, 2 = TMA-streamed kernel.  gne_dev_last_lv_kernel: 1 or 2, the one last used.  */
 int gne_dev_set_lv_kernel(gne_dev *d, int mode);
+/* CTAs of the persistent LV pass: 0 = two per SM of the whole device (default: one instance owns the GPU); a batch
+ * of B independent instances on one GPU gives each handle ~(2 x SMs) / B so that all their passes are resident
+ * together instead of queueing behind each other (GNE_STREAM_CTAS in the environment at create time does the same) */
+int gne_dev_set_stream_ctas(gne_dev *d, int ctas);
+/* "fast, non-parity" arithmetic: on != 0 lets the device fuse the multiply-add of the reduced cost
+ * (genneteq.h:315-316) and of the potential finalize (gnePotential.cpp:130).  One rounding less per value: the
+ * pivot sequence may leave the reference's at a tie; flows / potentials / objective agree to ~1e-9 relative.
+ * Off by default (GNE_FAST_MATH=1 in the environment turns it on at create time); per device, not per handle. */
+int gne_dev_set_fast_math(gne_dev *d, int on);
 int gne_dev_last_lv_kernel(gne_dev *d);
 /* number of kernels this handle has launched since creation                                   */
 int64_t gne_dev_launch_count(gne_dev *d);

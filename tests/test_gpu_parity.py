@@ -424,6 +424,76 @@ def test_c2_prefix_window_equals_oracle(gne, rule, K):
     s.close(); o.close()
 
 
+def test_potential_finalize_by_slot(gne):
+    """gne_pot_finalize_slots: only the nodes of the named trees get a new pi (a changed theta of a big tree costs one
+    sweep over the slot column, no node list); the others keep theirs bit for bit."""
+    rng = np.random.default_rng(5)
+    n = 70001
+    a0 = rng.uniform(-1e3, 1e3, n); a1 = rng.uniform(-3, 3, n)
+    slot = rng.integers(0, 40, n).astype(np.int32)
+    theta = rng.uniform(-50, 50, 40)
+    d = gne.Device(n, 4096)
+    d.pot_update_nodes(np.arange(n, dtype=np.int32), a0, a1, slot)
+    d.pot_update_thetas(np.arange(40, dtype=np.int32), theta)
+    d.pot_finalize()
+    before = d.pot_get_all()
+    changed = np.array([3, 17, 18, 0, 39, 5, 6, 7, 8, 9, 21], np.int32)          # > 8: two launches
+    theta2 = theta.copy(); theta2[changed] = rng.uniform(-50, 50, len(changed))
+    d.pot_update_thetas(np.arange(40, dtype=np.int32), theta2)                     # every theta uploaded, only `changed` finalized
+    d.pot_finalize_slots(changed)
+    got = d.pot_get_all()
+    hit = np.isin(slot, changed)
+    exp = np.where(hit, a0 + a1 * theta2[slot], before)
+    assert np.array_equal(got, exp)
+    d.close()
+
+
+def test_lv_pass_with_a_share_of_the_ctas(gne):
+    """gne_dev_set_stream_ctas (batches: every instance's persistent pass gets its share of the CTA slots): the same
+    result as with the whole device, for a share of 1, 9 and 37 CTAs."""
+    rng = np.random.default_rng(11)
+    n, N = 20000, 700_003
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N, "near")
+    d = gne.Device(n, N + 16)
+    d.nb_reset(tail, head, cost, mult, state)
+    d.pot_set_all(pi)
+    oL, olst, oany = oracle_lv(tail, head, cost, mult, state, pi)
+    for ctas in (1, 9, 37, 0):
+        d.set_stream_ctas(ctas)
+        L, lst, anyv = d.price_lv()
+        assert (L, anyv) == (oL, oany) and np.array_equal(lst, olst), ctas
+    d.close()
+
+
+@pytest.mark.parametrize("name,rule", [("c1_wide_s7", "LV"), ("c1_wide_s7", "QS"), ("s_lossy_s4", "LV"), ("s_near1_s6", "CL"), ("lossy3k_s5", "LV")])
+def test_fast_math_mode_stays_within_tolerance(gne, name, rule):
+    """the FMA-enabled "fast, non-parity" mode (gne_dev_set_fast_math).  The pivot sequence may leave the
+    reference's at a tie, but the solve must end at the same optimum: objective within 1e-9 relative of the reference's,
+    and - where the reference's final flows / potentials are stored - those within 1e-9 relative too (scale: the largest
+    magnitude of the vector).  The switch is per device: it is turned off again and the exact mode must still be bit-exact."""
+    z, inst = load_gold(name)
+    probe = gne.Device(16, 4096)
+    try:
+        probe.set_fast_math(True)
+        s, p1, p2 = solve_gpu(gne, inst, rule)
+        obj = float(z[rule + "_objective"])
+        assert abs(s.objective - obj) <= 1e-9 * max(1.0, abs(obj)), (s.objective, obj)
+        if rule + "_flows" in z.files:
+            fl, rf = s.flows(), z[rule + "_flows"]
+            assert np.max(np.abs(fl - rf)) <= 1e-9 * max(1.0, np.max(np.abs(rf)))
+            po, rp = s.potentials(), z[rule + "_potentials"]
+            assert np.max(np.abs(po - rp)) <= 1e-9 * max(1.0, np.max(np.abs(rp)))
+        same = np.array_equal(s.trace[0], z[rule + "_e"])
+        print("fast math, %s %s: %d+%d pivots (reference %s), trace %s" % (name, rule, p1, p2, tuple(int(v) for v in z[rule + "_p"]),
+                                                                          "identical" if same else "differs"))
+        s.close()
+    finally:
+        probe.set_fast_math(False)
+    s, p1, p2 = solve_gpu(gne, inst, rule)
+    assert np.array_equal(s.trace[0], z[rule + "_e"]) and np.array_equal(s.trace[1], z[rule + "_l"])
+    s.close(); probe.close()
+
+
 REF_WINDOWS = [("c2_lv", 100_000, 2_000_000, 21, "LV", 2000), ("c2_qs", 100_000, 2_000_000, 21, "QS", 2000),
                ("c4_lv", 50_000, 1_000_000, 1000, "LV", 2000), ("c3_lv", 1_000_000, 20_000_000, 31, "LV", 600)]
 

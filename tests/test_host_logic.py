@@ -311,3 +311,19 @@ def test_reference_arm_generator_library_matches_the_product(gne):
         assert rc == 0
         for k, v in (("tail", t), ("head", h), ("ub", ub), ("cost", c), ("mult", mu), ("supply", s)):
             assert np.array_equal(a[k], v), k
+
+
+def test_host_replay_deep_c2_trace(gne):
+    """Deep into a configs[1]-size solve (100k nodes / 2M arcs, 56 000 Dantzig pivots: one basis tree of ~50k nodes, cut
+    subtrees of thousands of nodes): the host engine - subtree-cut split with the implicit arcsInTree order, partial
+    re-threading, sparse flows - must pick every recorded leaving arc.  The recorded trace itself was checked against the
+    UNMODIFIED reference (tests/golden/verify_deep_fixture.py: its own pivot() reproduces every leaving arc, and its own
+    solve continues with exactly the recorded pivots)."""
+    from oracle_util import generate_native, Instance
+    z = np.load(os.path.join(ROOT, "tests", "golden", "deep_c2_lv.npz"))
+    g = generate_native(int(z["n"]), int(z["m"]), int(z["seed"]), str(z["mode"]))
+    inst = Instance(g["n"], g["tail"], g["head"], g["ub"], g["cost"], g["mult"], g["supply"])
+    e = np.ascontiguousarray(z["e"]); l = np.ascontiguousarray(z["l"])
+    mm, flows, pots, obj = gne.host_replay(inst.n, inst.tail, inst.head, inst.ub, inst.cost, inst.mult, inst.supply, inst.big_m,
+                                           1, len(e), e, l)
+    assert mm == -1, ("leaving arc differs at pivot", mm)
