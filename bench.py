@@ -518,6 +518,9 @@ def batch_reference(args, count, steps, warmup):
 
 def batch_arm(args):
     import threading as th
+    # one hardware work queue per instance stream (the default of 8 connections makes 32 streams share queues, and
+    # kernels of different instances then wait for each other); must be set before the CUDA context exists
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import genneteq_b200 as gne
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -587,17 +590,22 @@ def batch_arm(args):
 
     def steps(i):
         res[i] = devs[i].bench_price_lv(args.steps, False)
+    # device clock around the whole leg: an event before the first launch and one after every instance stream has
+    # drained (the handles' streams are independent of torch's, so the second event is recorded after a device sync)
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev0.record()
     threads = [th.Thread(target=steps, args=(i,)) for i in range(B)]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
     torch.cuda.synchronize()
+    ev1.record()
+    torch.cuda.synchronize()
     dev_wall_host = time.perf_counter() - t0
-    # device time of the leg: every instance's steps are bracketed by CUDA events on its own stream (both loops of
-    # gne_bench_price_lv); the batch is done when the slowest instance is
-    dev_wall = max(float(r[0].sum() + r[1].sum()) for r in res) * 1e-3
+    dev_wall = ev0.elapsed_time(ev1) * 1e-3
+    busy = max(float(r[0].sum() + r[1].sum()) for r in res) * 1e-3     # the busiest instance stream's kernel time
     clocks = sampler.stop()
     tiles_ms = float(np.mean([r[1].mean() for r in res]))
     launches += sum(d.launch_count() for d in devs) - launches_before
@@ -625,12 +633,12 @@ def batch_arm(args):
             "parity": parity,
             "e2e": {"value": arcs / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(pivots, 1), "d2h_bytes_per_step": d2h / max(pivots, 1),
                     "pivots_per_s": pivots / wall, "ms_per_pivot_per_instance": 1e3 * wall / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "device_leg_host_wall_s": dev_wall_host,
+            "gpu_launches": int(launches), "clocks": clocks, "device_leg_host_wall_s": dev_wall_host, "busiest_stream_kernel_s": busy,
             # per GPU: the B concurrent passes together move B x (25 B x arcs + 8 B x nodes) per round of passes
             "roofline": {"bound": "hbm", "achieved": B * alg * 2 * args.steps / dev_wall / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": B * alg * 2 * args.steps / dev_wall / 1e9 / peak, "traffic": None,
                          "kernel": "k_price_lv_stream, %d CTAs per instance, the %d instances of a GPU resident together "
-                                   "(aggregate bytes of all passes / wall time of the device leg; kernel_ms = one instance's pass)" % (ctas, B),
+                                   "(aggregate bytes of all passes / device time of the whole leg; kernel_ms = one instance's pass)" % (ctas, B),
                          "kernel_ms": tiles_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
     if not args.no_cpu_baseline and world == 1:
         r = batch_reference(args, B, 12, 2)

@@ -1028,10 +1028,11 @@ extern "C" int gne_price_violators(gne_dev *d, double threshold, int64_t *count,
     return GNE_OK;
 }
 
+static int exchange_blobs(gne_dev *d, const unsigned long long *mine, unsigned long long *all);
+
 extern "C" int gne_price_first(gne_dev *d, int64_t *pos)
 {
     CK(cudaSetDevice(d->device));
-    if (d->nranks != 1) { gne_set_error("gne_price_first: not implemented for a sharded list"); return GNE_ERR_UNSUPPORTED; }
     int rc = gne_dev_flush(d); if (rc) return rc;
     const int G = tiles_for(d);
     CK(cudaEventRecord(d->ev0, d->stream));
@@ -1042,7 +1043,14 @@ extern "C" int gne_price_first(gne_dev *d, int64_t *pos)
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1));
     d->d2hBytes += 8;
-    const unsigned long long v = (unsigned long long) d->hostScalar[1];
+    unsigned long long v = (unsigned long long) d->hostScalar[1];
+    if (d->nranks > 1) {
+        // sharded list: the first violator is the lowest of the shards' first positions (one 128-byte blob per rank)
+        unsigned long long mine[BLOB_WORDS] = { 0 }, all[BLOB_WORDS * MAX_RANKS];
+        mine[0] = v;
+        rc = exchange_blobs(d, mine, all); if (rc) return rc;
+        for (int r = 0; r < d->nranks; ++r) v = std::min(v, all[(size_t) r * BLOB_WORDS]);
+    }
     *pos = (v == ~0ull) ? -1 : (int64_t) v;
     return GNE_OK;
 }
@@ -1138,7 +1146,6 @@ extern "C" int gne_price_scan_list(gne_dev *d, int64_t cursor, int64_t want, int
                                    int64_t *listPos, double *listViol, int64_t cap, int64_t *newCursor, int64_t *scanned)
 {
     CK(cudaSetDevice(d->device));
-    if (d->nranks != 1) { gne_set_error("gne_price_scan_list: not implemented for a sharded list"); return GNE_ERR_UNSUPPORTED; }
     const int64_t N = d->N;
     *count = 0; *scanned = 0;
     if (cursor >= N) cursor = 0;                        // :622
@@ -1156,6 +1163,19 @@ extern "C" int gne_price_scan_list(gne_dev *d, int64_t cursor, int64_t want, int
         if (seg[k][1] <= seg[k][0]) continue;
         int64_t total = 0;
         int rc = viol_count_device(d, 0.0, &total, nullptr, nullptr, seg[k][0], seg[k][1]); if (rc) return rc;
+        if (d->nranks > 1) {
+            // sharded list: every rank compacts its part of the segment; the parts concatenated in rank order are the
+            // segment in position (= scan) order
+            rc = viol_write_device(d, 0.0, total, seg[k][0], seg[k][1]); if (rc) return rc;
+            std::vector<int64_t> gp;
+            std::vector<double> gv;
+            rc = sharded_gather_lists(d, total, gp, gv); if (rc) return rc;
+            total = (int64_t) gp.size();
+            if (got + total > cap) { *count = got + total; gne_set_error("gne_price_scan_list: cap too small"); return GNE_ERR_CAPACITY; }
+            if (total > 0) { memcpy(listPos + got, gp.data(), 8 * (size_t) total); memcpy(listViol + got, gv.data(), 8 * (size_t) total); }
+            got += total;
+            continue;
+        }
         if (got + total > cap) { *count = got + total; gne_set_error("gne_price_scan_list: cap too small"); return GNE_ERR_CAPACITY; }
         rc = viol_write_device(d, 0.0, total, seg[k][0], seg[k][1]); if (rc) return rc;
         if (total > 0) {

@@ -104,5 +104,9 @@ if __name__ == "__main__":
         make("e_nosupply_s12", 40, 200, 12, "wide", er, tweak="nosupply")
         make("e_two_nodes_s13", 2, 2, 13, "wide", er)
         make("e_three_nodes_s14", 3, 6, 14, "pow2", er)
+    if "medium" in which:
+        # several 2048-position tiles (so that a list sharded over 2-4 ranks has more than one non-empty shard) for the rules
+        # the small fixtures cover only within one tile: FV, CL2, CLW2 (which no other fixture holds), RV, RLV
+        make("m_wide_s9", 600, 9000, 9, "wide", ["FV", "CL2", "CLW2", "RV", "RLV", "QS"], save_instance=True)
     if "lossy3k" in which:
         make("lossy3k_s5", 3000, 60000, 5, "lossy", ["LV"], keep_state=False)

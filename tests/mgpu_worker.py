@@ -123,6 +123,27 @@ def main():
         s.close()
         boot.finish(out, ok, "comm mode %d" % mode_id)
         return
+    if mode == "medium":
+        # 600 nodes / 9000 arcs over the ranks (more than one non-empty shard): sharded first-violator (min over the shards'
+        # first positions), sharded candidate-list-2 (cursor-ordered concatenation of the shards' parts), random rules
+        boot = Boot(rank, world, local)
+        from test_oracle_pinned import load
+        z, mi = load("m_wide_s9")
+        ok = True
+        note = ""
+        for r in rule.split(","):
+            s = gne.Solver(mi.n, mi.tail, mi.head, mi.ub, mi.cost, mi.mult, mi.supply, device=boot.device, rule1=r)
+            boot.attach(s)
+            p1, p2 = s.solve_both()
+            e, l = s.trace
+            good = (p1, p2) == tuple(int(v) for v in z[r + "_p"]) and np.array_equal(e, z[r + "_e"]) and np.array_equal(l, z[r + "_l"])
+            good = good and np.array_equal(s.flows(), z[r + "_flows"]) and s.objective == float(z[r + "_objective"])
+            if not good:
+                note += " " + r
+            ok = ok and good
+            s.close()
+        boot.finish(out, ok, note)
+        return
     if mode == "edge":
         # lists shorter than 2048 x ranks: some ranks own EMPTY shards; every edge fixture, rules LV / QS / CL
         boot = Boot(rank, world, local)

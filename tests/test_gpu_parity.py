@@ -424,6 +424,21 @@ def test_c2_prefix_window_equals_oracle(gne, rule, K):
     s.close(); o.close()
 
 
+@pytest.mark.parametrize("rn", ["FV", "CL2", "CLW2", "RV", "RLV", "QS"])
+def test_medium_fixture_rules_spanning_several_tiles(gne, rn):
+    """600 nodes / 9000 arcs: the rules the small fixtures exercise only inside one tile (and CLW2, which has no other
+    fixture); trace, flows, potentials, objective equal the unmodified reference's."""
+    z, inst = load_gold("m_wide_s9")
+    s, p1, p2 = solve_gpu(gne, inst, rn)
+    e, l = s.trace
+    assert (p1, p2) == tuple(int(v) for v in z[rn + "_p"])
+    assert np.array_equal(e, z[rn + "_e"]) and np.array_equal(l, z[rn + "_l"])
+    assert s.objective == float(z[rn + "_objective"])
+    assert np.array_equal(s.flows(), z[rn + "_flows"])
+    assert np.array_equal(s.potentials(), z[rn + "_potentials"])
+    s.close()
+
+
 def test_potential_finalize_by_slot(gne):
     """gne_pot_finalize_slots: only the nodes of the named trees get a new pi (a changed theta of a big tree costs one
     sweep over the slot column, no node list); the others keep theirs bit for bit."""

@@ -103,3 +103,16 @@ def test_sharded_lists_shorter_than_the_shard_grid(tmp_path, nproc, exchange):
         if gne.cuda_device_count() < nproc:
             env["GNE_TEST_BOOT"] = "host"
         assert launch("nccl", nproc, str(tmp_path / "c1x8.txt"), 29671, env, "LV") == "OK"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nproc,exchange", [(2, "p2p"), (4, "fallback")])
+def test_sharded_first_violator_and_candidate_list_2(tmp_path, nproc, exchange):
+    """gnePivotRules.cpp:206-228 / :613-677 over a sharded list: FV = the lowest of the shards' first violating positions,
+    CL2 / CLW2 = the shards' parts of the scanned range concatenated in cursor order, RV through the gathered violator
+    lists; 600 nodes / 9000 arcs (several non-empty shards) must reproduce the reference on every rank."""
+    import genneteq_b200 as gne
+    env = fallback_env(gne, nproc) if exchange == "fallback" else {}
+    if gne.cuda_device_count() < nproc:
+        env["GNE_TEST_BOOT"] = "host"
+    assert launch("medium", nproc, str(tmp_path / "medium.txt"), 29680 + nproc, env, "FV,CL2,CLW2,RV") == "OK"

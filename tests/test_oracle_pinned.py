@@ -185,3 +185,11 @@ def test_native_generator_library_matches_the_product_generator():
     b = generate_native(5000, 60000, 77, "lossy")
     for k in ("tail", "head", "ub", "cost", "mult", "supply"):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("rn", ["FV", "CL2", "CLW2", "RV", "RLV", "QS"])
+def test_medium_fixture_rules_spanning_several_tiles(rn):
+    """600 nodes / 9000 arcs (m_wide_s9): first-violator, both candidate-list-2 ids (CLW2 has no other fixture), the random
+    rules and quickSelect on a list of several 2048-position tiles; port == unmodified reference."""
+    z, inst = load("m_wide_s9")
+    check(z, inst, rn)
