@@ -63,6 +63,7 @@ SIGNATURES = {
     "gne_price_scan_list": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _f64p, C.c_int64, _i64p, _i64p]),
     "gne_price_violators": (C.c_int, [_vp, C.c_double, _i64p, _i64p, _f64p, C.c_int64]),
     "gne_price_first": (C.c_int, [_vp, _i64p]),
+    "gne_price_eqf": (C.c_int, [_vp, C.c_int, _i64p, _i32p, _f64p, _f64p, _f64p]),
     "gne_reduced_costs": (C.c_int, [_vp, C.c_int64, C.c_int64, _f64p]),
     "gne_dev_last_kernel_ms": (C.c_int, [_vp, _f32p]),
     "gne_dev_set_timing": (C.c_int, [_vp, C.c_int]),
@@ -317,6 +318,13 @@ class Device:
         hi = self.N if hi is None else hi
         rc = np.empty(hi - lo)
         _ck(lib.gne_reduced_costs(self.h, lo, hi, _p(rc, _f64p)), "gne_reduced_costs")
+        return rc
+
+    def price_eqf(self, row_start, node, val, cost):
+        """Reduced costs of equal-flow variables given as CSR rows (gne_price_eqf)."""
+        rs = _arr(row_start, np.int64); nd = _arr(node, np.int32); vl = _arr(val, np.float64); cs = _arr(cost, np.float64)
+        rc = np.zeros(len(cs))
+        _ck(lib.gne_price_eqf(self.h, len(cs), _p(rs, _i64p), _p(nd, _i32p), _p(vl, _f64p), _p(cs, _f64p), _p(rc, _f64p)), "gne_price_eqf")
         return rc
 
     def pot_finalize_slots(self, slots):

@@ -141,6 +141,7 @@ struct gne_dev {
     bool stageInFlight = false;                    // the staging buffer feeds a kernel not yet synchronised
     LvCtas lvc{};                                  // per-CTA records of the TMA-streamed LV pass
     int streamGrid = 0;                            // 2 CTAs per SM
+    int stStages = ST_STAGES, stCtasPerSm = ST_CTAS_PER_SM;     // shape of the streamed pass (GNE_ST_SHAPE="stages,ctas" for tuning runs)
     int streamGridFull = 0;                        // ... of the whole device (gne_dev_set_stream_ctas lowers streamGrid for batches)
     unsigned int *lvTicket = nullptr;              // counters of the streamed pass, one 128-byte line each (zero between passes):
     unsigned int *lvArrive = nullptr;              //   last-CTA ticket, first-CTA election, next tile, update-visible flag
@@ -228,6 +229,18 @@ static int ensure_out(gne_dev *d, int64_t cap)
 static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi);
 static int flush_pending(gne_dev *d);
 
+// The streamed LV pass in its production shape (3 stages of 25.6 KB, 2 CTAs per SM) and the shapes kept for tuning runs.
+typedef void (*StKernel)(const NbView, const double *, const LvCtas, const int64_t, const LvFused, const SmallUpdate, const NbMut, const PotMut);
+static StKernel st_kernel_for(int stages, int ctasPerSm)
+{
+    if (stages == 3 && ctasPerSm == 2) return k_price_lv_stream<3, 2>;
+    if (stages == 2 && ctasPerSm == 2) return k_price_lv_stream<2, 2>;
+    if (stages == 2 && ctasPerSm == 3) return k_price_lv_stream<2, 3>;
+    if (stages == 4 && ctasPerSm == 2) return k_price_lv_stream<4, 2>;
+    if (stages == 3 && ctasPerSm == 1) return k_price_lv_stream<3, 1>;
+    return nullptr;
+}
+
 extern "C" int gne_dev_create(gne_dev **out, int cudaDevice, int n, int64_t nbCapacity, int64_t shardLo, int64_t shardHi)
 {
     if (!out || n <= 0 || nbCapacity <= 0 || shardLo < 0 || shardHi < shardLo) { gne_set_error("gne_dev_create: bad argument"); return GNE_ERR_ARG; }
@@ -278,7 +291,9 @@ static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cudaDevice);
-        d->streamGrid = sms * ST_CTAS_PER_SM;
+        { const char *sh = getenv("GNE_ST_SHAPE"); int a = 0, b = 0; if (sh && sscanf(sh, "%d,%d", &a, &b) == 2) { d->stStages = a; d->stCtasPerSm = b; } }
+        if (!st_kernel_for(d->stStages, d->stCtasPerSm)) { gne_set_error("GNE_ST_SHAPE=%d,%d is not an instantiated shape of the streamed pass", d->stStages, d->stCtasPerSm); return GNE_ERR_ARG; }
+        d->streamGrid = sms * d->stCtasPerSm;
         if (d->streamGrid > 2 * ST_THREADS) d->streamGrid = 2 * ST_THREADS;        // the reduction reads two records per thread
         d->streamGridFull = d->streamGrid;
         { const char *sg = getenv("GNE_STREAM_CTAS"); if (sg && atoi(sg) > 0) d->streamGrid = std::min(d->streamGridFull, atoi(sg)); }
@@ -289,7 +304,7 @@ static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity
         d->lvUpdFlag = reinterpret_cast<unsigned long long *>(d->lvTicket + 96);
         CK(cudaMalloc(&d->lvc.candPos, 8 * (size_t) d->streamGrid * ST_CAND)); CK(cudaMalloc(&d->lvc.candViol, 8 * (size_t) d->streamGrid * ST_CAND));
         CK(cudaMalloc(&d->lvc.candSecond, 8 * (size_t) d->streamGrid * ST_CAND));
-        CK(cudaFuncSetAttribute(k_price_lv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        CK(cudaFuncSetAttribute(st_kernel_for(d->stStages, d->stCtasPerSm), cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem_bytes(d->stStages)));
     }
     CK(cudaHostAlloc(&d->lvRes, sizeof(LvResult), cudaHostAllocMapped));
     CK(cudaHostAlloc(&d->qsState, sizeof(QsState), cudaHostAllocMapped));
@@ -825,7 +840,7 @@ static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEve
         PotMut pm; pm.a0 = d->a0; pm.a1 = d->a1; pm.slot = d->slot; pm.theta = d->theta; pm.pi = d->pi;
         const int grid = f.single ? (int) std::max<int64_t>(1, numTiles) : d->streamGrid;
         if (evA) CK(cudaEventRecord(evA, d->stream));
-        k_price_lv_stream<<<grid, ST_BLOCK, ST_SMEM, d->stream>>>(nb, (const double *) d->pi, d->lvc, numTiles, f, su, mm, pm);
+        st_kernel_for(d->stStages, d->stCtasPerSm)<<<grid, ST_BLOCK, st_smem_bytes(d->stStages), d->stream>>>(nb, (const double *) d->pi, d->lvc, numTiles, f, su, mm, pm);
         CK(cudaGetLastError());
         ++d->launches;
         if (evB) CK(cudaEventRecord(evB, d->stream));
@@ -1052,6 +1067,42 @@ extern "C" int gne_price_first(gne_dev *d, int64_t *pos)
         for (int r = 0; r < d->nranks; ++r) v = std::min(v, all[(size_t) r * BLOB_WORDS]);
     }
     *pos = (v == ~0ull) ? -1 : (int64_t) v;
+    return GNE_OK;
+}
+
+// Reduced cost of p equal-flow variables (computeEqfRedCost, genneteq.h:321-330) against the device's potentials.
+// Rows in CSR form, entries of a row sorted by node.  The rows travel with the call (they change only when the set of
+// nonbasic equal-flow variables does; p and the rows are small next to the arc list).
+extern "C" int gne_price_eqf(gne_dev *d, int p, const int64_t *rowStart, const int32_t *node, const double *val,
+                             const double *cost, double *rc)
+{
+    if (p < 0 || (p > 0 && (!rowStart || !cost || !rc))) { gne_set_error("gne_price_eqf: bad argument"); return GNE_ERR_ARG; }
+    if (p == 0) return GNE_OK;
+    const int64_t nnz = rowStart[p];
+    if (rowStart[0] != 0 || nnz < 0) { gne_set_error("gne_price_eqf: rowStart must start at 0 and rise"); return GNE_ERR_ARG; }
+    for (int k = 0; k < p; ++k) if (rowStart[k + 1] < rowStart[k]) { gne_set_error("gne_price_eqf: rowStart must rise"); return GNE_ERR_ARG; }
+    for (int64_t q = 0; q < nnz; ++q) if (node[q] < 0 || node[q] >= d->n) { gne_set_error("gne_price_eqf: node out of range"); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(d->device));
+    int rcf = gne_dev_flush(d); if (rcf) return rcf;
+    const size_t bytes = 8 * (size_t) (p + 1) + 12 * (size_t) nnz + 16 * (size_t) p + 64;
+    rcf = ensure_stage(d, bytes); if (rcf) return rcf;
+    if (d->stageInFlight) { CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false; }
+    char *h = (char *) d->stageHost;
+    size_t o = 0;
+    const size_t oRow = o; memcpy(h + o, rowStart, 8 * (size_t) (p + 1)); o += 8 * (size_t) (p + 1);
+    const size_t oVal = o; if (nnz) memcpy(h + o, val, 8 * (size_t) nnz); o += 8 * (size_t) nnz;
+    const size_t oCost = o; memcpy(h + o, cost, 8 * (size_t) p); o += 8 * (size_t) p;
+    const size_t oRc = o; o += 8 * (size_t) p;
+    const size_t oNode = o; if (nnz) memcpy(h + o, node, 4 * (size_t) nnz); o += 4 * (size_t) nnz;
+    CK(cudaMemcpyAsync(d->stageDev, h, o, cudaMemcpyHostToDevice, d->stream));
+    char *g = (char *) d->stageDev;
+    k_price_eqf<<<blocks_for(p, 128), 128, 0, d->stream>>>(p, (const int64_t *) (g + oRow), (const int32_t *) (g + oNode), (const double *) (g + oVal),
+                                                          (const double *) (g + oCost), d->pi, (double *) (g + oRc));
+    CK(cudaGetLastError());
+    ++d->launches;
+    CK(cudaMemcpyAsync(rc, g + oRc, 8 * (size_t) p, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    d->h2dBytes += (int64_t) o; d->d2hBytes += 8 * p;
     return GNE_OK;
 }
 

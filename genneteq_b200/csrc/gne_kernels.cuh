@@ -484,6 +484,23 @@ k_reduced_costs(NbView nb, const double *__restrict__ pi, int64_t lo, int64_t hi
 }
 
 // ------------------------------------------------------------------------------------------
+// computeEqfRedCost (genneteq.h:321-330) for every nonbasic equal-flow variable: rc = cost - sum_i nodeVals[i] * pi[i],
+// the subtractions in node order.  nodeVals is dense in the reference but zero off the nodes the set's arcs touch, and
+// x - 0 * pi == x exactly, so the sparse row (entries sorted by node) subtracted in order gives the same bits.  The sum
+// is order-dependent, so one thread walks one row; p (the number of sets) is small and rows are short.
+// ------------------------------------------------------------------------------------------
+__global__ void k_price_eqf(int p, const int64_t *__restrict__ rowStart, const int32_t *__restrict__ node,
+                            const double *__restrict__ val, const double *__restrict__ cost, const double *__restrict__ pi,
+                            double *__restrict__ rc)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p) return;
+    double x = cost[k];
+    for (int64_t q = rowStart[k]; q < rowStart[k + 1]; ++q) x = __dsub_rn(x, __dmul_rn(val[q], pi[node[q]]));
+    rc[k] = x;
+}
+
+// ------------------------------------------------------------------------------------------
 // quickSelect scan (gnePivotRules.cpp:742-756) over a window [jLo, jHi) of *virtual* indices
 // j = (pos - cursor) mod N; one CTA per QTILE virtual indices, thread t owns j = base + t + 256 k.
 // ------------------------------------------------------------------------------------------

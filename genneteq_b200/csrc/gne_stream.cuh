@@ -31,13 +31,14 @@ constexpr int ST_THREADS = 256;                         // consumer threads
 constexpr int ST_PRODUCER = 32;                         // + one producer warp
 constexpr int ST_BLOCK = ST_THREADS + ST_PRODUCER;
 constexpr int ST_ITEMS = 4;
-constexpr int ST_STAGES = 3;
+constexpr int ST_STAGES = 3;                            // production shape: 3 stages x 2 CTAs per SM (see st_kernel_for)
 constexpr int ST_TILE = ST_THREADS * ST_ITEMS;          // 1024 arcs per stage
 constexpr int ST_STAGE_BYTES = 25 * ST_TILE;            // 25 600 B
 constexpr int ST_CTAS_PER_SM = 2;
 constexpr int ST_CAND = 96;                             // in-band candidates kept per CTA
-constexpr int ST_HEADER = 256;                          // full[3], empty[3] mbarriers, tile index per stage
+constexpr int ST_HEADER = 256;                          // full[], empty[] mbarriers, tile index per stage (up to 4 stages)
 constexpr int ST_SMEM = ST_HEADER + ST_STAGES * ST_STAGE_BYTES;
+constexpr int st_smem_bytes(int stages) { return ST_HEADER + stages * ST_STAGE_BYTES; }
 
 __device__ __forceinline__ uint32_t st_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void st_mbar_init(uint64_t *bar, uint32_t count)
@@ -249,19 +250,20 @@ __device__ __forceinline__ void st_apply_update(const SmallUpdate &u, const NbMu
     if (t == 0) st_st_release(f.updFlag, f.seq);
 }
 
-__global__ void __launch_bounds__(ST_BLOCK, ST_CTAS_PER_SM)
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(ST_BLOCK, MINB)
 k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __grid_constant__ LvCtas out, const int64_t numTiles,
                   const __grid_constant__ LvFused f, const __grid_constant__ SmallUpdate u, const __grid_constant__ NbMut nbMut,
                   const __grid_constant__ PotMut pm)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem);                 // [ST_STAGES]
-    uint64_t *empty = full + ST_STAGES;                                  // [ST_STAGES]
-    volatile int64_t *sTile = reinterpret_cast<volatile int64_t *>(smem + 128);   // [ST_STAGES] tile in each stage, -1: none left
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);                 // [STAGES]
+    uint64_t *empty = full + 4;                                  // [STAGES]
+    volatile int64_t *sTile = reinterpret_cast<volatile int64_t *>(smem + 128);   // [STAGES] tile in each stage, -1: none left
     unsigned char *stage0 = smem + ST_HEADER;
     const int t = threadIdx.x;
     if (t == 0) {
-        for (int s = 0; s < ST_STAGES; ++s) { st_mbar_init(&full[s], 1); st_mbar_init(&empty[s], ST_THREADS / 32); }
+        for (int s = 0; s < STAGES; ++s) { st_mbar_init(&full[s], 1); st_mbar_init(&empty[s], ST_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -269,8 +271,8 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
         // ---------------- producer warp: one thread streams tiles until the counter runs out
         if (t == ST_THREADS) {
             for (int it = 0;; ++it) {
-                const int s = it % ST_STAGES;
-                if (it >= ST_STAGES) st_mbar_wait(&empty[s], (uint32_t) (((it / ST_STAGES) - 1) & 1));
+                const int s = it % STAGES;
+                if (it >= STAGES) st_mbar_wait(&empty[s], (uint32_t) (((it / STAGES) - 1) & 1));
                 const int64_t tile = f.single ? (it == 0 ? (int64_t) blockIdx.x : numTiles) : (int64_t) atomicAdd(f.tileCtr, 1ull);
                 if (tile >= numTiles) { sTile[s] = -1; st_mbar_arrive(&full[s]); break; }
                 sTile[s] = tile;
@@ -302,8 +304,8 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
 #pragma unroll
     for (int k = 0; k < ST_ITEMS; ++k) vv[k] = -1.0;
     for (int it = 0;; ++it) {
-        const int s = it % ST_STAGES;
-        st_mbar_wait(&full[s], (uint32_t) ((it / ST_STAGES) & 1));
+        const int s = it % STAGES;
+        st_mbar_wait(&full[s], (uint32_t) ((it / STAGES) & 1));
         const int64_t tile = sTile[s];
         if (tile < 0) break;
         const unsigned char *sb = stage0 + (size_t) s * ST_STAGE_BYTES;

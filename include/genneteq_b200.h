@@ -127,6 +127,12 @@ int gne_price_violators(gne_dev *d, double threshold, int64_t *count, int64_t *l
 /* getFirstVarWithViolation (gnePivotRules.cpp:206-228): lowest violating position or -1       */
 int gne_price_first(gne_dev *d, int64_t *pos);
 
+/* computeEqfRedCost (genneteq.h:321-330) for p equal-flow variables: rc[k] = cost[k] - sum nodeVals_k[i] * pi[i], the
+ * subtractions in node order as the reference's dense loop does them (zero entries change nothing, so the rows are
+ * passed sparse: CSR, entries of a row sorted by node).  The first piece of the equal-flow path; the
+ * solver mirror still refuses instances with equal-flow sets (Type II pivots and the s x s systems are not built). */
+int gne_price_eqf(gne_dev *d, int p, const int64_t *rowStart, const int32_t *node, const double *val, const double *cost, double *rc);
+
 /* reduced cost of every position in [lo, hi) (tests, verifyOptimality)                        */
 int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc);
 

@@ -901,6 +901,17 @@ double orc_big_m(long m, const double *cost, const double *ub)
     return numArcs * maxCost * maxCap;                      // graph.cpp:43
 }
 
+// computeEqfRedCost (genneteq.h:321-330), dense as the reference runs it: rc = cost; for every node i in order
+// rc -= nodeVals[i] * potential[i].  nodeVals: p rows of n doubles.
+void orc_price_eqf_dense(int p, int n, const double *nodeVals, const double *cost, const double *pi, double *rc)
+{
+    for (int k = 0; k < p; ++k) {
+        double x = cost[k];
+        for (int i = 0; i < n; ++i) x -= nodeVals[(size_t) k * n + i] * pi[i];
+        rc[k] = x;
+    }
+}
+
 double orc_drand48(unsigned long long *state)
 {
     const unsigned long long a = 0x5DEECE66DULL, c = 0xBULL, mask = (1ULL << 48) - 1ULL;

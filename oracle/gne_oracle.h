@@ -14,6 +14,8 @@ typedef struct OrcSolver OrcSolver;
 
 /* graph.cpp:43  bigM = numArcs * maxArcCost * maxArcCapacity */
 double orc_big_m(long m, const double *cost, const double *ub);
+/* computeEqfRedCost (genneteq.h:321-330) over dense nodeVals rows (p x n) */
+void orc_price_eqf_dense(int p, int n, const double *nodeVals, const double *cost, const double *pi, double *rc);
 
 /* arcs must be sorted by (tail, head): that is the varIndex order of gneInit.cpp:82-107 */
 OrcSolver *orc_create(int n, long m, const int *tail, const int *head, const double *ub,

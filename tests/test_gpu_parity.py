@@ -439,6 +439,33 @@ def test_medium_fixture_rules_spanning_several_tiles(gne, rn):
     s.close()
 
 
+def test_equal_flow_reduced_costs_match_the_dense_loop(gne):
+    """computeEqfRedCost (genneteq.h:321-330): cost - sum_i nodeVals[i] * pi[i], subtracted in node order.  The device walks
+    the sparse rows (entries sorted by node); the oracle runs the reference's dense loop over all n nodes: bit-equal, also
+    with an empty row, a row touching every node and cancelling terms."""
+    rng = np.random.default_rng(17)
+    n, p = 5000, 37
+    pi = rng.uniform(-100, 100, n)
+    dense = np.zeros((p, n))
+    for k in range(p):
+        cnt = 0 if k == 3 else (n if k == 5 else int(rng.integers(1, 400)))
+        idx = np.sort(rng.choice(n, cnt, replace=False))
+        dense[k, idx] = rng.choice([1.0, -1.0, 0.5, 2.0, 0.731, -1.25], cnt) * rng.uniform(0.5, 1.5, cnt)
+    dense[7, :] = 0.0; dense[7, 10] = 1.0; dense[7, 11] = -1.0; pi[10] = pi[11] = 1e15          # cancellation
+    cost = rng.uniform(-50, 50, p)
+    exp = np.zeros(p)
+    oracle_lib().orc_price_eqf_dense(p, n, dp(np.ascontiguousarray(dense)), dp(cost), dp(pi), dp(exp))
+    rows = [np.flatnonzero(dense[k]) for k in range(p)]
+    row_start = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    node = np.concatenate(rows).astype(np.int32)
+    val = np.concatenate([dense[k, rows[k]] for k in range(p)])
+    d = gne.Device(n, 4096)
+    d.pot_set_all(pi)
+    got = d.price_eqf(row_start, node, val, cost)
+    assert np.array_equal(got, exp)
+    d.close()
+
+
 def test_potential_finalize_by_slot(gne):
     """gne_pot_finalize_slots: only the nodes of the named trees get a new pi (a changed theta of a big tree costs one
     sweep over the slot column, no node list); the others keep theirs bit for bit."""
