@@ -552,6 +552,7 @@ def batch_arm(args):
     sms = torch.cuda.get_device_properties(local).multi_processor_count
     ctas = max(1, (2 * sms) // B)
     os.environ["GNE_STREAM_CTAS"] = str(ctas)
+    os.environ.setdefault("GNE_POLL_SLEEP_US", "20")    # B host threads on fewer cores: the result poll sleeps between looks
     solvers = []
     for i in range(B):
         g = gne.generate_instance(n, m, seed0 + rank * B + i, mode)

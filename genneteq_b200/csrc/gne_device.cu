@@ -18,6 +18,7 @@
 #include <dlfcn.h>
 #include <vector>
 #include <sched.h>
+#include <time.h>
 
 using namespace gne;
 
@@ -166,6 +167,7 @@ struct gne_dev {
     void *hostGatherCtx = nullptr;
     char *agDev = nullptr;                         // NCCL staging of small host all-gathers
     size_t agBytes = 0;
+    long pollSleepNs = 0;                          // > 0: the result poll sleeps this long between looks (batches)
     long long xTimeoutCycles = 8000000000ll;       // peer wait inside the exchange kernels (GNE_EXCHANGE_TIMEOUT_S, default ~4 s)
     int rank = 0, nranks = 1;
     void *gatherSend = nullptr, *gatherRecv = nullptr, *gatherHost = nullptr;
@@ -313,6 +315,7 @@ static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity
     { const char *tm = getenv("GNE_TIMING"); d->timing = tm && tm[0] == '1'; }
     { const char *pd = getenv("GNE_PDL"); d->pdl = !(pd && pd[0] == '0'); }
     { const char *fm = getenv("GNE_FAST_MATH"); const int v = (fm && fm[0] == '1') ? 1 : 0; CK(cudaMemcpyToSymbol(c_gne_fast_math, &v, sizeof(int))); }
+    { const char *ps = getenv("GNE_POLL_SLEEP_US"); if (ps && atof(ps) > 0.0) d->pollSleepNs = (long) (atof(ps) * 1000.0); }
     { const char *lk = getenv("GNE_LV_KERNEL"); if (lk) d->lvKernelMode = !strcmp(lk, "stream") ? 2 : (!strcmp(lk, "tiles") ? 1 : 0); }
     memset(d->qsState, 0, sizeof(QsState));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
@@ -879,8 +882,13 @@ static int wait_host_seq(gne_dev *d, const volatile unsigned long long *seq, uns
     unsigned long spins = 0;
     while (*seq != expect) {
         // batches run one host thread per instance, possibly more threads than cores: after the first few
-        // microseconds of polling give the core away between polls
-        if (++spins > 4096 && (spins & 63) == 0) sched_yield();
+        // microseconds of polling give the core away between polls - by a short sleep when the handle was told
+        // so (GNE_POLL_SLEEP_US: the pass of a batch instance takes >100 us, the other instances' threads need the core),
+        // else by a yield
+        if (++spins > 4096 && (spins & 63) == 0) {
+            if (d->pollSleepNs > 0) { struct timespec ts = { 0, d->pollSleepNs }; nanosleep(&ts, nullptr); }
+            else sched_yield();
+        }
         if ((spins & 0xfffff) == 0) {                    // now and then
             cudaError_t q = cudaStreamQuery(d->stream);
             if (q == cudaSuccess) { if (*seq == expect) break; gne_set_error("pricing pass finished without publishing its result"); return GNE_ERR_CUDA; }

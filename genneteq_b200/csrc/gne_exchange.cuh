@@ -55,16 +55,23 @@ __device__ __forceinline__ void exchange_merge(const ShardRecord *rec, Mailbox *
     const int b = (int) (xseq & 1ull);
     constexpr int WORDS = (int) (sizeof(ShardRecord) / 8);
     const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
-    const int words = 3 + 2 * SHARD_LIST;               // (the whole record: positions and violations are contiguous)
     static_assert(WORDS == 3 + 2 * SHARD_LIST, "ShardRecord layout");
-    for (int p = 0; p < nranks; ++p) {
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&peers[p]->rec[b][rank]);
-        for (int i = t; i < words; i += NT) dst[i] = src[i];
+    // only what the record holds travels: the 24-byte header and `count` (position, violation) pairs - usually one;
+    // thread i < 3 + 2 cnt carries one word to every peer
+    const int cnt = (rec->count < 0 || rec->overflow) ? 0 : (rec->count > SHARD_LIST ? SHARD_LIST : (int) rec->count);
+    if (t < 3 + 2 * cnt) {
+        const int wi = t < 3 + cnt ? t : t - cnt + SHARD_LIST;           // words [0, 3 + cnt) and [3 + SHARD_LIST, 3 + SHARD_LIST + cnt)
+        const unsigned long long v = src[wi];
+        for (int p = 0; p < nranks; ++p) reinterpret_cast<unsigned long long *>(&peers[p]->rec[b][rank])[wi] = v;
     }
     if (t == 0) *sTimeout = 0;
-    __threadfence_system();
     xchg_sync();
-    if (t < nranks) *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[b][rank]) = xseq;
+    // the barrier orders the CTA's stores before the flag writers' fence (cumulativity): one system-scope fence per
+    // flag-writing thread instead of one per thread
+    if (t < nranks) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[b][rank]) = xseq;
+    }
     Mailbox *self = peers[rank];
     if (t < nranks) {
         const long long t0 = clock64();
@@ -74,12 +81,12 @@ __device__ __forceinline__ void exchange_merge(const ShardRecord *rec, Mailbox *
             if (v == XCHG_POISON || clock64() - t0 > timeoutCycles) { *sTimeout = 1; break; }
         }
     }
+    if (t < nranks) __threadfence_system();             // acquire side: the records behind the observed flags
     xchg_sync();
     if (*sTimeout && t < nranks) {                      // fail fast everywhere: both generations of our flag at every peer
         *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[0][rank]) = XCHG_POISON;
         *reinterpret_cast<volatile unsigned long long *>(&peers[t]->flag[1][rank]) = XCHG_POISON;
     }
-    __threadfence_system();
     // ---- merge (identical on every rank)
     __shared__ double sMax[MAX_RANKS];
     __shared__ int sAnyR[MAX_RANKS], sOvfR[MAX_RANKS], sCntR[MAX_RANKS], sWarpTot[NT / 32], sCarry;

@@ -55,12 +55,28 @@ class GpuGenNetEq : public GenNetEq
         ArcVar *a = setNBarc[p];
         GCK(gne_nb_write(dev, p, a->tail, a->head, a->cost, a->mult, (int8_t) a->setLoc));
     }
-    void pushPotentials()                                   // after computePotentials(), genneteq.cpp:97
+    // after computePotentials(), genneteq.cpp:97.  The reference recomputes every node's potential each iteration, but
+    // only the trees the last pivot touched get new values: a host-side shadow copy finds them (one pass over n doubles,
+    // cheap next to the reference's own O(n) sweep) and only those cross PCIe - the dirty-set hook of mode A.
+    void pushPotentials()
     {
-        std::vector<double> pi(numNodes);
-        for (int i = 0; i < numNodes; ++i) pi[i] = nodes[i].potential;
-        GCK(gne_pot_set_all(dev, pi.data()));
+        if ((int) shadowPi.size() != numNodes) {            // first call: everything
+            shadowPi.resize(numNodes);
+            for (int i = 0; i < numNodes; ++i) shadowPi[i] = nodes[i].potential;
+            GCK(gne_pot_set_all(dev, shadowPi.data()));
+            return;
+        }
+        dirtyIdx.clear(); dirtyVal.clear();
+        for (int i = 0; i < numNodes; ++i) {
+            const double v = nodes[i].potential;
+            if (memcmp(&v, &shadowPi[i], sizeof(double)) != 0) { shadowPi[i] = v; dirtyIdx.push_back(i); dirtyVal.push_back(v); }
+        }
+        potentialBytes += 12 * (long) dirtyIdx.size();
+        if (!dirtyIdx.empty()) GCK(gne_pot_set(dev, (int64_t) dirtyIdx.size(), dirtyIdx.data(), dirtyVal.data()));
     }
+    std::vector<double> shadowPi, dirtyVal;
+    std::vector<int32_t> dirtyIdx;
+    long potentialBytes = 0;
     Variable *gpuLargestViolation()                         // getVarWithLargestViolation, gnePivotRules.cpp:133-157
     {
         double L; int64_t cnt; int any;
