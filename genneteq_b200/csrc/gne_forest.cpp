@@ -196,40 +196,35 @@ void Forest::mergeInto(int32_t tX, int32_t tII, int32_t av)
         else { at.parent = head[av]; at.child = tail[av]; }
         trees[tX].pending.push_back(at);
     }
-    ensureArcs(tII);                                     // y's order becomes explicit: O(|y|), like everything below
-    relabel(tII, tX);
+    ensureArcs(tII);                                     // y's order explicit (a cut subtree already is: split wrote it)
     Tree &x = trees[tX];
     Tree &y = trees[tII];
-    if (x.implicitOrder) {
-        // y's arcs keep their relative order in x's tail: explicit positions POS_TAIL_BASE + index
-        const int32_t shift = POS_TAIL_BASE + (int32_t) x.tailArcs.size();
-        for (size_t q = 0; q < y.nodes.size(); ++q) {
-            const int32_t w = y.nodes[q];
-            const int64_t base = node[w].incStart;
-            for (int32_t k = 0; k < node[w].incLen; ++k) { Inc &e = pool[base + k]; e.pos = (e.pos >= 0) ? e.pos + shift : (int32_t) POS_TAIL_OTHER; }
-        }
+    // one pass over y's nodes: membership (Tree::setTreeIDAndType, trees.cpp:220-230), nodes(x), and the positions of y's
+    // arcs, which keep their relative order behind x's - in x's tail (explicit positions POS_TAIL_BASE + index) when
+    // x's order is implicit, else shifted behind arcs(x)
+    const bool tailMode = x.implicitOrder;
+    const int32_t shift = tailMode ? POS_TAIL_BASE + (int32_t) x.tailArcs.size() : (int32_t) x.arcs.size();
+    for (size_t q = 0; q < y.nodes.size(); ++q) {
+        const int32_t w = y.nodes[q];
+        setSlot(w, tX);
+        pushNode(tX, w);
+        const int64_t base = node[w].incStart;
+        if (tailMode) { for (int32_t k = 0; k < node[w].incLen; ++k) { Inc &e = pool[base + k]; e.pos = (e.pos >= 0) ? e.pos + shift : (int32_t) POS_TAIL_OTHER; } }
+        else if (shift) { for (int32_t k = 0; k < node[w].incLen; ++k) if (pool[base + k].pos >= 0) pool[base + k].pos += shift; }
+    }
+    if (tailMode) {
         x.tailArcs.insert(x.tailArcs.end(), y.arcs.begin(), y.arcs.end());
         const int32_t pav = POS_TAIL_BASE + (int32_t) x.tailArcs.size();
         x.tailArcs.push_back(av);
         incPush(tail[av], av, head[av], pav);
         incPush(head[av], av, tail[av], POS_TAIL_OTHER);
     } else {
-        // y's arcs keep their relative order behind x's: shift the positions held in y's incident entries
-        const int32_t shift = (int32_t) x.arcs.size();
-        if (shift && !y.arcs.empty()) {
-            for (size_t q = 0; q < y.nodes.size(); ++q) {
-                const int32_t w = y.nodes[q];
-                const int64_t base = node[w].incStart;
-                for (int32_t k = 0; k < node[w].incLen; ++k) if (pool[base + k].pos >= 0) pool[base + k].pos += shift;
-            }
-        }
         x.arcs.insert(x.arcs.end(), y.arcs.begin(), y.arcs.end());
         const int32_t pav = (int32_t) x.arcs.size();
         x.arcs.push_back(av);
         incPush(tail[av], av, head[av], pav);
         incPush(head[av], av, tail[av], POS_NONE);
     }
-    for (size_t q = 0; q < y.nodes.size(); ++q) pushNode(tX, y.nodes[q]);
     x.ordFix.insert(x.ordFix.end(), y.ordFix.begin(), y.ordFix.end());
     touch(tX);
     freeTree(tII);
@@ -394,7 +389,9 @@ int32_t Forest::split(int32_t top, int32_t removedArc)
     o.type = TREE_II; o.extraArc = -1;
     o.threadsValid = false;                              // a block of the thread disappears; the rooting of the rest stays
     touch(top);
-    // bottom: the subtree of c, rooted at c with the pred pointers it has
+    // bottom: the subtree of c, visited in the split DFS order from c over the lists as they stand (the removed arc
+    // skipped), so that arcs(bottom) and the positions in its incident entries are written in the same pass: bottom is
+    // almost always merged into another tree right away, which needs its order explicit
     std::vector<int32_t> &st = stackA;
     st.clear();
     st.push_back(c);
@@ -410,11 +407,18 @@ int32_t Forest::split(int32_t top, int32_t removedArc)
         pushNode(bottom, nd);
         const int32_t prev = node[nd].pred;
         const int64_t base = node[nd].incStart;
-        for (int32_t k = 0; k < node[nd].incLen; ++k) if (pool[base + k].nbr != prev) st.push_back(pool[base + k].nbr);
+        for (int32_t k = 0; k < node[nd].incLen; ++k) {
+            Inc &e = pool[base + k];
+            if (e.nbr == prev) { e.pos = POS_NONE; continue; }            // (for c: the removed arc's entry, nbr == par)
+            e.pos = (int32_t) bt.arcs.size();
+            bt.arcs.push_back(e.arc);
+            st.push_back(e.nbr);
+        }
     }
-    bt.root = c; bt.implicitOrder = true; bt.rooted = false;
+    bt.root = c; bt.implicitOrder = false; bt.rooted = false;
     node[c].pred = -1; node[c].predArc = -1; node[c].flag |= 1;
-    // remove the arc from the two incident lists (swap with last); the moved entries keep their snapshot index
+    // remove the arc from the two incident lists (swap with last).  In top the moved entry keeps its snapshot index
+    // (`ord`) until the next split; bottom's order is explicit, so there the index is simply brought up to date
     for (int side = 0; side < 2; ++side) {
         const int32_t w = side ? c : par;
         const int64_t base = node[w].incStart;
@@ -423,7 +427,8 @@ int32_t Forest::split(int32_t top, int32_t removedArc)
             if (pool[base + k].arc != removedArc) continue;
             if (k != len - 1) {
                 pool[base + k] = pool[base + len - 1];
-                if (!(node[w].flag & 4)) { node[w].flag |= 4; (side ? bt : o).ordFix.push_back(w); }
+                if (side) pool[base + k].ord = k;
+                else if (!(node[w].flag & 4)) { node[w].flag |= 4; o.ordFix.push_back(w); }
             }
             --node[w].incLen;
             break;
@@ -432,6 +437,93 @@ int32_t Forest::split(int32_t top, int32_t removedArc)
     secsSplit += nowS() - t0;
     nodesSplit += visited; ++callsSplitFast;
     return bottom;
+}
+
+bool Forest::rehang(int32_t out, int32_t in)
+{
+    if (!fastSplit) return false;
+    const int32_t u = tail[out], v = head[out];
+    const int32_t t = node[u].slot;
+    if (t < 0 || node[v].slot != t || node[tail[in]].slot != t || node[head[in]].slot != t) return false;
+    {
+        const Tree &o = trees[t];
+        if (o.type != TREE_I || out == o.extraArc || tail[in] == head[in] || !o.rooted || !o.pending.empty() || o.root < 0) return false;
+    }
+    int32_t c;                                           // child end of the leaving arc
+    if (node[v].predArc == out && node[v].pred == u) c = v;
+    else if (node[u].predArc == out && node[u].pred == v) c = u;
+    else return false;
+    const int32_t par = (c == v) ? u : v;
+    // x is in the subtree of c  <=>  climbing from x to c's depth ends at c
+    const int32_t dc = node[c].depth;
+    auto below = [&](int32_t x) { while (node[x].depth > dc) x = node[x].pred; return x == c; };
+    const int32_t ex = trees[t].extraArc;
+    if (below(head[ex]) || below(tail[ex])) return false;                 // the leaving arc is on the cycle: the root may change
+    const bool tb = below(tail[in]), hb = below(head[in]);
+    if (tb == hb) return false;                                           // the entering arc does not reconnect the two parts
+    const double t0 = nowS();
+    Tree &o = trees[t];
+    // (1) what split() does to the part that keeps the root: a new snapshot of the implicit order
+    for (size_t i = 0; i < o.tailArcs.size(); ++i) {
+        const int32_t a = o.tailArcs[i];
+        for (int side = 0; side < 2; ++side) {
+            const int32_t w = side ? head[a] : tail[a];
+            const int64_t base = node[w].incStart;
+            for (int32_t k = 0; k < node[w].incLen; ++k) if (pool[base + k].arc == a) pool[base + k].pos = POS_NONE;
+        }
+    }
+    o.tailArcs.clear();
+    applyOrdFix(o);
+    if (!o.implicitOrder) { o.arcs.clear(); o.implicitOrder = true; }
+    o.threadsValid = false;
+    // (2) arcs(bottom) in the split DFS order from c (lists as they stand, the leaving arc skipped), written straight
+    //     into the tail: arcs(t) = arcs(top) ++ arcs(bottom) ++ [in], as mergeInto would leave them
+    std::vector<int32_t> &st = stackA;
+    st.clear();
+    st.push_back(c);
+    int64_t visited = 0;
+    while (!st.empty()) {
+        const int32_t nd = st.back(); st.pop_back();
+        ++visited;
+        const int32_t prev = node[nd].pred;
+        const int64_t base = node[nd].incStart;
+        const int32_t len = node[nd].incLen;
+        for (int32_t k = 0; k < len; ++k) {
+            Inc &e = pool[base + k];
+            if (e.nbr == prev) { e.pos = (e.arc == out) ? (int32_t) POS_NONE : (int32_t) POS_TAIL_OTHER; continue; }   // (no parallel tree arcs)
+            e.pos = POS_TAIL_BASE + (int32_t) o.tailArcs.size();
+            o.tailArcs.push_back(e.arc);
+            st.push_back(e.nbr);
+        }
+    }
+    // (3) the leaving arc leaves the two incident lists (swap with last); moved entries keep their snapshot index
+    for (int side = 0; side < 2; ++side) {
+        const int32_t w = side ? c : par;
+        const int64_t base = node[w].incStart;
+        const int32_t len = node[w].incLen;
+        for (int32_t k = 0; k < len; ++k) {
+            if (pool[base + k].arc != out) continue;
+            if (k != len - 1) {
+                pool[base + k] = pool[base + len - 1];
+                if (!(node[w].flag & 4)) { node[w].flag |= 4; o.ordFix.push_back(w); }
+            }
+            --node[w].incLen;
+            break;
+        }
+    }
+    // (4) the entering arc: appended to both lists and to the tail, the subtree re-rooted from its end by updateTrees
+    Attach at;
+    at.arc = in;
+    if (tb) { at.parent = head[in]; at.child = tail[in]; } else { at.parent = tail[in]; at.child = head[in]; }
+    o.pending.push_back(at);
+    const int32_t pav = POS_TAIL_BASE + (int32_t) o.tailArcs.size();
+    o.tailArcs.push_back(in);
+    incPush(tail[in], in, head[in], pav);
+    incPush(head[in], in, tail[in], POS_TAIL_OTHER);
+    touch(t);
+    secsSplit += nowS() - t0;
+    nodesSplit += visited; ++callsRehang;
+    return true;
 }
 
 // Tree::removeFromTrees (trees.cpp:456-499)

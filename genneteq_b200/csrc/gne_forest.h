@@ -71,6 +71,11 @@ class Forest {
     // negative code where the reference prints and exit(-1)s.
     int insertArc(int32_t av);
     int removeArc(int32_t av);
+    // removeArc(out) followed by insertArc(in) in one step, for the common pivot inside one type I tree: `out` is a tree arc
+    // off the cycle and `in` hangs the subtree it cuts off back into the rest.  Same resulting lists, orders and rooting
+    // as the two calls (split + re-insertion of the extra arc + merge), without moving the subtree's nodes to another
+    // tree slot and back.  Returns false (nothing done) when the pivot is not of that shape.
+    bool rehang(int32_t out, int32_t in);
     void updateTrees();
     // The preorder thread of a tree is only needed by the full flow recompute, the full potential
     // sweep and the accessors used in tests; pivots that keep a tree's root only re-thread the
@@ -105,7 +110,7 @@ class Forest {
 
     std::vector<NodeRec> node;
     double secsSplit = 0, secsReindex = 0, secsMerge = 0;
-    int64_t nodesSplit = 0, nodesReindex = 0, callsReindex = 0, nodesMaterialized = 0, callsSplitFast = 0, callsSplitFull = 0;   // wall-clock split of the forest work
+    int64_t nodesSplit = 0, nodesReindex = 0, callsReindex = 0, nodesMaterialized = 0, callsSplitFast = 0, callsSplitFull = 0, callsRehang = 0;   // wall-clock split of the forest work
 
   private:
     int n = 0;

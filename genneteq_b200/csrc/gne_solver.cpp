@@ -904,8 +904,17 @@ int GenNetEq::updateBasis()                                       // :254-309
     } else {
         GNE_TRY(removeFromNB(eVar));
         const double t0 = wallNow();
-        GNE_TRY(removeFromB(lVar));
-        GNE_TRY(insertIntoB(eVar));
+        if (forest.rehang(lVar, eVar)) {
+            // the forest did removeArc(lVar) + insertArc(eVar) in one step; the set bookkeeping of removeFromB / insertIntoB
+            const int32_t prevInd = setInd[lVar];
+            const int32_t mv = setBarc.back();
+            setBarc[prevInd] = mv; setInd[mv] = prevInd; setBarc.pop_back();
+            setLoc[lVar] = NIL; setInd[lVar] = -1;
+            setBarc.push_back(eVar); setLoc[eVar] = B_var; setInd[eVar] = (int32_t) setBarc.size() - 1;
+        } else {
+            GNE_TRY(removeFromB(lVar));
+            GNE_TRY(insertIntoB(eVar));
+        }
         secsTrees += wallNow() - t0;
         if (flow[lVar] > (0.5 * UB[lVar])) GNE_TRY(insertIntoNB(lVar, U_var));
         else GNE_TRY(insertIntoNB(lVar, L_var));
@@ -1045,8 +1054,8 @@ int GenNetEq::replayTrace(int draws, int64_t p1, int64_t total, const int32_t *e
         fprintf(stderr, "host replay: pivot %.3f s, potentials %.3f s, periodic full flows %.3f s; flows %.3f s, trees %.3f s (split %.3f, reindex %.3f, merge %.3f)\n",
                 secsPivot, secsPotentials, secsTotal, secsFlows, secsTrees,
                 forest.secsSplit, forest.secsReindex, forest.secsMerge),
-        fprintf(stderr, "  nodes visited: split %lld (%lld subtree cuts, %lld full DFS), reindex %lld in %lld calls, order materialised %lld\n", (long long) forest.nodesSplit,
-                (long long) forest.callsSplitFast, (long long) forest.callsSplitFull, (long long) forest.nodesReindex, (long long) forest.callsReindex, (long long) forest.nodesMaterialized);
+        fprintf(stderr, "  nodes visited: split %lld (%lld subtree cuts, %lld re-hangs, %lld full DFS), reindex %lld in %lld calls, order materialised %lld\n", (long long) forest.nodesSplit,
+                (long long) forest.callsSplitFast, (long long) forest.callsRehang, (long long) forest.callsSplitFull, (long long) forest.nodesReindex, (long long) forest.callsReindex, (long long) forest.nodesMaterialized);
     return GNE_OK;
 }
 

@@ -273,7 +273,11 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
             for (int it = 0;; ++it) {
                 const int s = it % STAGES;
                 if (it >= STAGES) st_mbar_wait(&empty[s], (uint32_t) (((it / STAGES) - 1) & 1));
-                const int64_t tile = f.single ? (it == 0 ? (int64_t) blockIdx.x : numTiles) : (int64_t) atomicAdd(f.tileCtr, 1ull);
+                // the first STAGES tiles of a CTA are its own (no round trip to the counter before the first load is
+                // issued); from then on the next tile comes from the device-wide counter
+                const int64_t tile = f.single ? (it == 0 ? (int64_t) blockIdx.x : numTiles)
+                                   : (it < STAGES ? (int64_t) blockIdx.x + (int64_t) it * gridDim.x
+                                                  : (int64_t) STAGES * gridDim.x + (int64_t) atomicAdd(f.tileCtr, 1ull));
                 if (tile >= numTiles) { sTile[s] = -1; st_mbar_arrive(&full[s]); break; }
                 sTile[s] = tile;
                 unsigned char *b = stage0 + (size_t) s * ST_STAGE_BYTES;
