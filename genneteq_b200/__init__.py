@@ -18,6 +18,8 @@ RULES = dict(LV=0, LVW=1, LVA=2, LVE=3, FV=4, SD=5, RV=6, RWV=7, RLV=8, RLVW=9, 
 AT_LOWER, AT_UPPER = 1, 2
 TOL = 1.0e-13
 
+if os.environ.get("GNE_LIB"):                            # a differently built library (make EXTRA=-DGNE_STAMPS OUT=...: tools/stamps_probe.py)
+    LIB_PATH = os.path.join(_HERE, "lib", os.environ["GNE_LIB"])
 if os.environ.get("GNE_TUNING_LIB") == "1":              # tools/variants.py: the library built with `make tuning`
     LIB_PATH = os.path.join(_HERE, "lib", "libgenneteq_b200_tuning.so")
 if not os.path.exists(LIB_PATH):

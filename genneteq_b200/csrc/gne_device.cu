@@ -843,6 +843,21 @@ static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEve
         NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
         PotMut pm; pm.a0 = d->a0; pm.a1 = d->a1; pm.slot = d->slot; pm.theta = d->theta; pm.pi = d->pi;
         const int grid = f.single ? (int) std::max<int64_t>(1, numTiles) : d->streamGrid;
+#ifdef GNE_STAMPS
+        static long long *stampsDev = nullptr, *stampsHost = nullptr;
+        static long passes = 0;
+        if (!stampsDev) { cudaMalloc(&stampsDev, 128); cudaHostAlloc(&stampsHost, 128, cudaHostAllocDefault); }
+        if (passes > 0 && passes % 50 == 0) {
+            cudaStreamSynchronize(d->stream);
+            cudaMemcpy(stampsHost, stampsDev, 64, cudaMemcpyDeviceToHost);
+            const long long *h = stampsHost;
+            fprintf(stderr, "[stamps] grid %d tiles %lld: first CTA in -> last CTA at its first gather %lld ns | -> last CTA leaves the loop %lld | ticket %lld | records loaded %lld | merged %lld | published %lld | done %lld  (total %lld ns)\n",
+                    grid, (long long) numTiles, h[1] - h[0], h[2] - h[0], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
+        }
+        ++passes;
+        { long long init[8] = { 0x7fffffffffffffffll, 0, 0, 0, 0, 0, 0, 0 }; cudaMemcpyAsync(stampsDev, init, 64, cudaMemcpyHostToDevice, d->stream); }
+        f.stamps = stampsDev;
+#endif
         if (evA) CK(cudaEventRecord(evA, d->stream));
         st_kernel_for(d->stStages, d->stCtasPerSm)<<<grid, ST_BLOCK, st_smem_bytes(d->stStages), d->stream>>>(nb, (const double *) d->pi, d->lvc, numTiles, f, su, mm, pm);
         CK(cudaGetLastError());

@@ -81,6 +81,13 @@ __device__ __forceinline__ void st_st_release(unsigned long long *p, unsigned lo
     asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ long long st_globaltimer()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct CtaRec {            // 64-byte record of one CTA; a lone in-band candidate travels in the record itself
     double max;            // -1 when the CTA saw no violator
     int32_t cnt;           // candidates within the band of `max` (may exceed ST_CAND: overflow)
@@ -146,7 +153,7 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
         }
     }
 #ifdef GNE_STAMPS
-    if (t == 0 && f.stamps) f.stamps[2] = clock64();
+    if (t == 0 && f.stamps) f.stamps[4] = st_globaltimer();              // per-CTA records loaded
 #endif
     double m = fmax(rmax[0], rmax[1]);
 #pragma unroll
@@ -198,7 +205,7 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
     }
     st_sync_consumers();
 #ifdef GNE_STAMPS
-    if (t == 0 && f.stamps) f.stamps[4] = clock64();
+    if (t == 0 && f.stamps) f.stamps[5] = st_globaltimer();              // merged and sorted
 #endif
     const int nOut = (any && !bad) ? total : 0;
     if (!(f.nranks > 1 && f.peers != nullptr)) {
@@ -211,7 +218,7 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
             if (lane == 0 || lane < nOut) { if (f.resOnHost) __threadfence_system(); else __threadfence(); }
             __syncwarp();
 #ifdef GNE_STAMPS
-            if (lane == 0 && f.stamps) f.stamps[5] = clock64();
+            if (lane == 0 && f.stamps) f.stamps[6] = st_globaltimer();      // entries + header written and fenced
 #endif
             if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&res->seq) = f.seq;
         }
@@ -262,6 +269,9 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
     volatile int64_t *sTile = reinterpret_cast<volatile int64_t *>(smem + 128);   // [STAGES] tile in each stage, -1: none left
     unsigned char *stage0 = smem + ST_HEADER;
     const int t = threadIdx.x;
+#ifdef GNE_STAMPS
+    if (t == 0 && f.stamps) atomicMin(reinterpret_cast<unsigned long long *>(f.stamps + 0), (unsigned long long) st_globaltimer());   // first CTA in
+#endif
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) { st_mbar_init(&full[s], 1); st_mbar_init(&empty[s], ST_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -340,6 +350,9 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
             if (lane == 0) while (st_ld_acquire(f.updFlag) != f.seq) { }
             __syncwarp();
         }
+#ifdef GNE_STAMPS
+        if (it == 0 && t == 0 && f.stamps) atomicMax(reinterpret_cast<unsigned long long *>(f.stamps + 1), (unsigned long long) st_globaltimer());   // last CTA to reach its first gather
+#endif
         double pt[ST_ITEMS], ph[ST_ITEMS];
 #pragma unroll
         for (int k = 0; k < ST_ITEMS; ++k) { pt[k] = pi[tl[k]]; ph[k] = pi[hd[k]]; }
@@ -359,7 +372,7 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
         if (lane == 0) st_mbar_arrive(&empty[s]);       // this warp is done with stage s
     }
 #ifdef GNE_STAMPS
-    const long long st0 = clock64();
+    const long long st0 = st_globaltimer();
 #endif
     // ---------------- once per CTA: maximum, then the candidates within the band of it
     __shared__ int sCnt, sLast;
@@ -412,13 +425,13 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
     if (!sLast) return;
     // ---------------- the last CTA of the pass: re-arm the counters, reduce, publish (and exchange)
 #ifdef GNE_STAMPS
-    if (t == 0 && f.stamps) { f.stamps[0] = st0; f.stamps[1] = clock64(); }
+    if (t == 0 && f.stamps) { f.stamps[2] = st0; f.stamps[3] = st_globaltimer(); }     // last CTA: loop done / ticket taken
 #endif
     __threadfence();
     if (t == 0) { *f.ticket = 0u; *f.arrive = 0u; *f.tileCtr = 0ull; }
     lv_reduce_records(out, (int) gridDim.x, f, stage0);
 #ifdef GNE_STAMPS
-    if (t == 0 && f.stamps) f.stamps[7] = clock64();
+    if (t == 0 && f.stamps) f.stamps[7] = st_globaltimer();              // last CTA done
 #endif
 }
 
