@@ -55,6 +55,7 @@ SIGNATURES = {
     "gne_pot_finalize": (C.c_int, [_vp]),
     "gne_pot_finalize_slots": (C.c_int, [_vp, C.c_int, _i32p]),
     "gne_pot_update_fused": (C.c_int, [_vp, C.c_int64, _i32p, _f64p, _f64p, _i32p, C.c_int64, _i32p, _f64p, C.c_int64, _i32p]),
+    "gne_pot_update_fused_pi": (C.c_int, [_vp, C.c_int64, _i32p, _f64p, _f64p, _i32p, C.c_int64, _i32p, _f64p, C.c_int64, _i32p, _f64p]),
     "gne_pot_set": (C.c_int, [_vp, C.c_int64, _i32p, _f64p]),
     "gne_pot_set_all": (C.c_int, [_vp, _f64p]),
     "gne_pot_get_all": (C.c_int, [_vp, _f64p]),

@@ -158,6 +158,7 @@ struct gne_dev {
     bool timing = false;                           // bracket pricing kernels with CUDA events (gne_dev_set_timing)
     std::vector<cudaEvent_t> benchEv;              // per-step event pairs of gne_bench_price_lv
     bool exchangeFused = false;                    // the last streamed pass carried the shard exchange itself
+    bool fastMath = false;                         // gne_dev_set_fast_math / GNE_FAST_MATH
     bool pdl = true;                               // programmatic dependent launch between a pivot's kernels (GNE_PDL=0 disables)
     unsigned long long lvSeq = 0;                  // sequence number of the last LV pass launched
     unsigned long long qsSeq = 0;
@@ -315,7 +316,7 @@ static int dev_create_fill(gne_dev *d, int cudaDevice, int n, int64_t nbCapacity
     memset(d->lvRes, 0, sizeof(LvResult));
     { const char *tm = getenv("GNE_TIMING"); d->timing = tm && tm[0] == '1'; }
     { const char *pd = getenv("GNE_PDL"); d->pdl = !(pd && pd[0] == '0'); }
-    { const char *fm = getenv("GNE_FAST_MATH"); const int v = (fm && fm[0] == '1') ? 1 : 0; CK(cudaMemcpyToSymbol(c_gne_fast_math, &v, sizeof(int))); }
+    { const char *fm = getenv("GNE_FAST_MATH"); const int v = (fm && fm[0] == '1') ? 1 : 0; CK(cudaMemcpyToSymbol(c_gne_fast_math, &v, sizeof(int))); d->fastMath = v != 0; }
     { const char *ps = getenv("GNE_POLL_SLEEP_US"); if (ps && atof(ps) > 0.0) d->pollSleepNs = (long) (atof(ps) * 1000.0); }
     { const char *lk = getenv("GNE_LV_KERNEL"); if (lk) d->lvKernelMode = !strcmp(lk, "stream") ? 2 : (!strcmp(lk, "tiles") ? 1 : 0); }
     memset(d->qsState, 0, sizeof(QsState));
@@ -371,6 +372,7 @@ extern "C" int gne_dev_set_fast_math(gne_dev *d, int on)
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     const int v = on ? 1 : 0;
     CK(cudaMemcpyToSymbol(c_gne_fast_math, &v, sizeof(int)));
+    d->fastMath = on != 0;
     return GNE_OK;
 }
 extern "C" int gne_dev_set_lv_kernel(gne_dev *d, int mode) { if (mode < 0 || mode > 2) return GNE_ERR_ARG; d->lvKernelMode = mode; return GNE_OK; }
@@ -549,6 +551,13 @@ extern "C" int gne_pot_update_fused(gne_dev *d, int64_t nNodes, const int32_t *n
                                     const int32_t *slot, int64_t nTheta, const int32_t *tslot, const double *theta,
                                     int64_t nFinal, const int32_t *fnode)
 {
+    return gne_pot_update_fused_pi(d, nNodes, node, a0, a1, slot, nTheta, tslot, theta, nFinal, fnode, nullptr);
+}
+
+extern "C" int gne_pot_update_fused_pi(gne_dev *d, int64_t nNodes, const int32_t *node, const double *a0, const double *a1,
+                                       const int32_t *slot, int64_t nTheta, const int32_t *tslot, const double *theta,
+                                       int64_t nFinal, const int32_t *fnode, const double *fpi)
+{
     CK(cudaSetDevice(d->device));
     const bool full = nFinal < 0;
     const int64_t nf = full ? 0 : nFinal;
@@ -562,7 +571,9 @@ extern "C" int gne_pot_update_fused(gne_dev *d, int64_t nNodes, const int32_t *n
         SmallUpdate &su = d->pendingSmall;
         NbWriteOps &q = pending_of(d);
         su.ops = q;
-        su.nNodes = (int) nNodes; su.nTheta = (int) nTheta; su.nFinal = (int) nf; su.pad = 0;
+        su.nNodes = (int) nNodes; su.nTheta = (int) nTheta; su.nFinal = (int) nf;
+        su.hasPi = (fpi != nullptr && !d->fastMath) ? 1 : 0;             // (the fused mode finalizes on the device, with its FMA)
+        if (su.hasPi) for (int64_t i = 0; i < nf; ++i) su.fpi[i] = fpi[i];
         for (int64_t i = 0; i < nNodes; ++i) { su.node[i] = node[i]; su.a0[i] = a0[i]; su.a1[i] = a1[i]; su.slot[i] = slot[i]; }
         for (int64_t i = 0; i < nTheta; ++i) { su.tslot[i] = tslot[i]; su.theta[i] = theta[i]; }
         for (int64_t i = 0; i < nf; ++i) su.fnode[i] = fnode[i];
@@ -804,7 +815,7 @@ static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEve
         const bool fromPending = !replay && d->havePendingSmall;
         if (replay) su = *replay;
         else if (fromPending) su = d->pendingSmall;
-        else { su.ops.n = 0; su.nNodes = su.nTheta = su.nFinal = su.pad = 0; }
+        else { su.ops.n = 0; su.nNodes = su.nTheta = su.nFinal = su.hasPi = 0; }
         NbWriteOps &q = pending_of(d);
         if (q.n > 0) {
             // set-mirror writes queued after the update: fold them in (a later write to a position replaces the earlier one)
@@ -920,9 +931,32 @@ static int wait_host_seq(gne_dev *d, const volatile unsigned long long *seq, uns
     return GNE_OK;
 }
 
-static int wait_lv_result(gne_dev *d)
+// The result of the pass just launched, as the host reads it: from the fast header alone when that says everything
+// (at most one candidate - the maximum itself - and no overflow code), else from the full block, which the device wrote
+// and fenced before the header.
+struct LvView { double maxViol; int any, overflow; int64_t count; const int64_t *pos; const double *viol; };
+
+static int wait_lv_result(gne_dev *d, LvView *v)
 {
-    int rc = wait_host_seq(d, &d->lvRes->seq, d->lvSeq); if (rc) return rc;
+    const volatile LvResult *r = d->lvRes;
+    int rc = wait_host_seq(d, &r->hSeqA, d->lvSeq); if (rc) return rc;
+    const unsigned long long want = d->lvSeq & ((1ull << 48) - 1ull);
+    unsigned long spins = 0;
+    while ((r->hTagB >> 16) != want) {                   // the second 16-byte chunk lands with (or right behind) the first
+        if (++spins > (1ul << 28)) { gne_set_error("pricing pass published half a result header"); return GNE_ERR_CUDA; }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    const unsigned long long tag = r->hTagB;
+    v->any = (int) ((tag >> 1) & 1ull); v->overflow = (int) ((tag >> 2) & 3ull);
+    const int64_t hc = (int64_t) ((tag >> 4) & 4095ull);
+    if (hc <= 1 && !v->overflow) {
+        v->maxViol = r->hMax; v->count = hc;
+        v->pos = const_cast<const int64_t *>(reinterpret_cast<const volatile int64_t *>(&r->hPos0));
+        v->viol = const_cast<const double *>(&r->hMax);
+    } else {
+        v->maxViol = r->maxViol; v->count = r->count; v->any = r->any; v->overflow = r->overflow;
+        v->pos = const_cast<const int64_t *>(r->pos); v->viol = const_cast<const double *>(r->viol);
+    }
     if (d->timing) { CK(cudaEventSynchronize(d->ev1)); CK(cudaEventElapsedTime(&d->lastMs, d->ev0, d->ev1)); }
     else d->lastMs = 0.f;
     return GNE_OK;
@@ -951,8 +985,9 @@ extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t 
     } else {
         // single GPU, or sharded over peer mailboxes (the merged block arrives like a single GPU's)
         if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
-        rc = wait_lv_result(d); if (rc) return rc;
-        const LvResult *r = d->lvRes;
+        LvView view;
+        rc = wait_lv_result(d, &view); if (rc) return rc;
+        const LvView *r = &view;
         if (r->overflow == XCHG_TIMEOUT) { gne_set_error("sharded exchange timed out waiting for a peer rank"); return GNE_ERR_COMM; }
         d->d2hBytes += 24 + 16 * std::min<int64_t>(r->count, LV_LIST_CAP);
         anyV = r->any;

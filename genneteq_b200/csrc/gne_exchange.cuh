@@ -129,16 +129,16 @@ __device__ __forceinline__ void exchange_merge(const ShardRecord *rec, Mailbox *
         }
         total = sCarry;
     }
-    // ---- publish (one warp; every writing lane fences its own stores, then the sequence number)
+    // ---- publish (one warp): the fast header alone when it says everything, else the full block first (fenced)
     if (w == 0) {
         const int nOut = (any && !bad) ? total : 0;
-        for (int r = lane; r < nOut; r += 32) { out->pos[r] = mPos[r]; out->viol[r] = mViol[r]; }
-        if (lane == 0) {
-            out->maxViol = any ? M : -1.0; out->any = any ? 1 : 0; out->count = nOut;
-            out->overflow = *sTimeout ? XCHG_TIMEOUT : (bad ? 1 : 0);
+        const int ovf = *sTimeout ? XCHG_TIMEOUT : (bad ? 1 : 0);
+        if (nOut > 1 || ovf) {
+            for (int r = lane; r < nOut; r += 32) { out->pos[r] = mPos[r]; out->viol[r] = mViol[r]; }
+            if (lane == 0) { out->maxViol = any ? M : -1.0; out->any = any ? 1 : 0; out->count = nOut; out->overflow = ovf; }
+            if (lane == 0 || lane < nOut) __threadfence_system();
+            __syncwarp();
         }
-        if (lane == 0 || lane < nOut) __threadfence_system();
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&out->seq) = outSeq;
+        if (lane == 0) gne::lv_fast_header(out, any ? M : -1.0, nOut > 0 ? mPos[0] : 0, outSeq, nOut, any ? 1 : 0, ovf);
     }
 }

@@ -205,16 +205,37 @@ k_price_lv_tiles(NbView nb, const double *__restrict__ pi, LvTiles out)
     }
 }
 
-// Result block of the LV pass (mapped pinned host memory, written by the finish kernel).
+// Result block of the LV pass (mapped pinned host memory, written by the last CTA of the pass / the finish kernel).
+// The host polls the FAST HEADER: two 16-byte chunks, each written by ONE 16-byte store and each carrying the sequence
+// number of the pass, so payload and sequence number arrive together and no fence (a PCIe round trip, ~2 us) stands
+// between them.  A pass with at most one candidate - nearly all of them - is complete in the header: the candidate is
+// the maximum itself (hPos0, hMax).  Longer lists and overflow codes use the full block below, written and fenced
+// BEFORE the header.
 struct LvResult {
-    double maxViol;        // exact fp64 maximum of |rc| over violators, -1 if none
+    double hMax;                   // chunk A: exact fp64 maximum of |rc| over violators (-1 if none) ...
+    unsigned long long hSeqA;      //          ... and the sequence number of the pass
+    long long hPos0;               // chunk B: position of the first candidate ...
+    unsigned long long hTagB;      //          ... and seq << 16 | count (12 bits, saturating) << 4 | overflow (2 bits) << 2 | any << 1 | 1
+    double maxViol;        // the full block: same maximum
     int32_t any;           // at least one violator
-    int32_t overflow;      // candidate list incomplete (a tile had > CAND_K, or > LV_LIST_CAP total)
+    int32_t overflow;      // 1: candidate list incomplete (too many in a tile / CTA / in total); 2: a peer rank never answered
     int64_t count;         // candidates with |rc| >= maxViol - LV_BAND, position order
     int64_t pos[LV_LIST_CAP];
     double viol[LV_LIST_CAP];
-    unsigned long long seq;        // written last (after a system-scope fence): the host spins on it instead of a stream sync
+    unsigned long long seq;        // (kept for readers of a device-resident block)
 };
+__device__ __forceinline__ void lv_store16(void *p, unsigned long long a, unsigned long long b)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+}
+// one thread: the fast header of a pass whose full block (if it is needed: count > 1 or overflow) is already visible
+__device__ __forceinline__ void lv_fast_header(LvResult *res, double M, long long pos0, unsigned long long seq, long long count, int any, int overflow)
+{
+    const unsigned long long c = count > 4095 ? 4095ull : (unsigned long long) (count < 0 ? 0 : count);
+    const unsigned long long tag = (seq << 16) | (c << 4) | ((unsigned long long) (overflow & 3) << 2) | ((unsigned long long) (any ? 1 : 0) << 1) | 1ull;
+    lv_store16(&res->hMax, (unsigned long long) __double_as_longlong(M), seq);
+    lv_store16(&res->hPos0, (unsigned long long) pos0, tag);
+}
 
 // LV pass, stage 2 (one CTA of 1024 threads): global maximum over the tile maxima, then the
 // candidates of the (few) tiles whose maximum reaches the band, gathered in position order.
@@ -229,8 +250,9 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long
     __shared__ int sSorted[FIN_QCAP];
     __shared__ int sScan[FIN_THREADS / 32];
     __shared__ int sCount, sOvf;
+    __shared__ int64_t sPos0;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) { sCount = 0; sOvf = 0; }
+    if (t == 0) { sCount = 0; sOvf = 0; sPos0 = 0; }
     pdl_launch_dependents();
     pdl_wait();
     // pass 1: maximum of the tile maxima; loads issued in independent batches of 8 (a dependent
@@ -256,6 +278,7 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long
             res->maxViol = -1.0; res->any = 0; res->overflow = 0; res->count = 0;
             __threadfence_system();
             *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+            lv_fast_header(res, -1.0, 0, seq, 0, 0, 0);
         }
         return;
     }
@@ -276,6 +299,7 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long
             res->maxViol = M; res->any = 1; res->overflow = 1; res->count = 0;
             __threadfence_system();
             *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+            lv_fast_header(res, M, 0, seq, 0, 1, 1);
         }
         return;
     }
@@ -309,8 +333,10 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long
         for (int i = 0; i < c; ++i) {
             const double vv = tiles.candViol[(int64_t) g * CAND_K + i];
             if (vv >= thr) {
-                res->pos[off] = lo + (int64_t) g * TILE + tiles.candOff[(int64_t) g * CAND_K + i];
+                const int64_t pp = lo + (int64_t) g * TILE + tiles.candOff[(int64_t) g * CAND_K + i];
+                res->pos[off] = pp;
                 res->viol[off] = vv;
+                if (off == 0) sPos0 = pp;
                 ++off;
             }
         }
@@ -321,7 +347,10 @@ k_price_lv_finish(LvTiles tiles, int G, int64_t lo, LvResult *res, unsigned long
         __threadfence_system();
     }
     __syncthreads();
-    if (t == 0) *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+    if (t == 0) {
+        *reinterpret_cast<volatile unsigned long long *>(&res->seq) = seq;
+        lv_fast_header(res, M, sPos0, seq, bad ? 0 : total, 1, bad ? 1 : 0);   // (every entry was fenced above)
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -718,8 +747,10 @@ k_update_fused(NbMut nb, NbWriteOps ops, FusedUpdate u, double *A0, double *A1, 
 constexpr int SU_NODES = 48, SU_THETAS = 16, SU_FINAL = 160;
 struct SmallUpdate {
     NbWriteOps ops;
-    int nNodes, nTheta, nFinal, pad;
-    double a0[SU_NODES], a1[SU_NODES], theta[SU_THETAS];
+    int nNodes, nTheta, nFinal;
+    int hasPi;                              // fpi[] holds the finalized potentials (computed by the host with the same unfused
+                                            // operations): the finalize is then plain stores, no dependent loads
+    double a0[SU_NODES], a1[SU_NODES], theta[SU_THETAS], fpi[SU_FINAL];
     int32_t node[SU_NODES], slot[SU_NODES], tslot[SU_THETAS], fnode[SU_FINAL];
 };
 
@@ -738,7 +769,7 @@ k_update_small(NbMut nb, const __grid_constant__ SmallUpdate u, double *A0, doub
     __syncthreads();
     if (t < u.nFinal) {
         const int v = u.fnode[t];
-        pi[v] = pot_value(A0[v], A1[v], T[S[v]]);
+        pi[v] = u.hasPi ? u.fpi[t] : pot_value(A0[v], A1[v], T[S[v]]);
     }
 }
 

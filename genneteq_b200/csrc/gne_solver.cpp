@@ -553,9 +553,14 @@ int GenNetEq::computePotentials()
     allPotDirty = false;
     if (!dev) return GNE_OK;                            // host-only replay
     // one call: queued setNBarc writes + dirty records + thetas + finalize (gnePotential.cpp:127-135)
-    GNE_TRY(gne_pot_update_fused(dev, (int64_t) upNode.size(), upNode.data(), upA0.data(), upA1.data(), upSlot.data(),
-                                 (int64_t) upThetaSlot.size(), upThetaSlot.data(), upTheta.data(),
-                                 finalizeAll ? -1 : (int64_t) upFinal.size(), upFinal.data()));
+    // short finalize lists travel with their values: pi = a0 + a1 * theta by the same unfused operations the device would
+    // use (hostPotential), so the relabel folded into the next pricing pass is stores only
+    upPi.clear();
+    if (!finalizeAll && upFinal.size() <= 160) for (size_t i = 0; i < upFinal.size(); ++i) upPi.push_back(hostPotential(upFinal[i]));
+    GNE_TRY(gne_pot_update_fused_pi(dev, (int64_t) upNode.size(), upNode.data(), upA0.data(), upA1.data(), upSlot.data(),
+                                    (int64_t) upThetaSlot.size(), upThetaSlot.data(), upTheta.data(),
+                                    finalizeAll ? -1 : (int64_t) upFinal.size(), upFinal.data(),
+                                    (!finalizeAll && upFinal.size() <= 160) ? upPi.data() : nullptr));
     if (!finalizeAll && !upFinalSlots.empty()) GNE_TRY(gne_pot_finalize_slots(dev, (int) upFinalSlots.size(), upFinalSlots.data()));
     return GNE_OK;
 }

@@ -158,7 +158,7 @@ class GenNetEq {
     std::vector<int64_t> listPos;
     std::vector<double> listViol;
     std::vector<int32_t> upNode, upSlot, upThetaSlot, upFinal, upFinalSlots;
-    std::vector<double> upA0, upA1, upTheta;
+    std::vector<double> upA0, upA1, upTheta, upPi;
     int status = GNE_OK;
     bool allPotDirty = true, hostOnly = false, sparseFlows = true;
     std::vector<int32_t> nodeMark;

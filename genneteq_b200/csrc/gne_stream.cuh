@@ -209,18 +209,25 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
 #endif
     const int nOut = (any && !bad) ? total : 0;
     if (!(f.nranks > 1 && f.peers != nullptr)) {
-        // one warp publishes: entries and header together, every writing lane fences its own stores (towards the
-        // host a fence is a PCIe round trip: all lanes pay it in parallel, once), then the sequence number
+        // one warp publishes.  At most one candidate (the maximum itself) and no overflow: everything the host needs is
+        // in the fast header - two 16-byte stores, no fence.  Otherwise the full block first, every writing lane fencing
+        // its own stores (towards the host a fence is a PCIe round trip: all lanes pay it in parallel, once), then the header.
         if (w == 0) {
             LvResult *res = f.res;
-            for (int r = lane; r < nOut; r += 32) { res->pos[r] = lPos[lRank[r]]; res->viol[r] = lViol[lRank[r]]; }
-            if (lane == 0) { res->maxViol = any ? M : -1.0; res->any = any ? 1 : 0; res->overflow = bad ? 1 : 0; res->count = nOut; }
-            if (lane == 0 || lane < nOut) { if (f.resOnHost) __threadfence_system(); else __threadfence(); }
-            __syncwarp();
+            const bool full = nOut > 1 || bad || !f.resOnHost;
+            if (full) {
+                for (int r = lane; r < nOut; r += 32) { res->pos[r] = lPos[lRank[r]]; res->viol[r] = lViol[lRank[r]]; }
+                if (lane == 0) { res->maxViol = any ? M : -1.0; res->any = any ? 1 : 0; res->overflow = bad ? 1 : 0; res->count = nOut; }
+                if (lane == 0 || lane < nOut) { if (f.resOnHost) __threadfence_system(); else __threadfence(); }
+                __syncwarp();
+            }
 #ifdef GNE_STAMPS
-            if (lane == 0 && f.stamps) f.stamps[6] = st_globaltimer();      // entries + header written and fenced
+            if (lane == 0 && f.stamps) f.stamps[6] = st_globaltimer();      // full block (if any) written and fenced
 #endif
-            if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&res->seq) = f.seq;
+            if (lane == 0) {
+                if (!f.resOnHost) *reinterpret_cast<volatile unsigned long long *>(&res->seq) = f.seq;
+                lv_fast_header(res, any ? M : -1.0, nOut > 0 ? lPos[lRank[0]] : 0, f.seq, nOut, any ? 1 : 0, bad ? 1 : 0);
+            }
         }
         return;
     }
@@ -247,10 +254,14 @@ __device__ __forceinline__ void st_apply_update(const SmallUpdate &u, const NbMu
     }
     if (t < u.nNodes) { const int v = u.node[t]; pm.a0[v] = u.a0[t]; pm.a1[v] = u.a1[t]; pm.slot[v] = u.slot[t]; }
     if (t < u.nTheta) pm.theta[u.tslot[t]] = u.theta[t];
-    st_sync_consumers();
-    if (t < u.nFinal) {
-        const int v = u.fnode[t];
-        pm.pi[v] = pot_value(pm.a0[v], pm.a1[v], pm.theta[pm.slot[v]]);
+    if (u.hasPi) {                                       // the host sent the finalized values: plain stores, no barrier, no loads
+        if (t < u.nFinal) pm.pi[u.fnode[t]] = u.fpi[t];
+    } else {
+        st_sync_consumers();
+        if (t < u.nFinal) {
+            const int v = u.fnode[t];
+            pm.pi[v] = pot_value(pm.a0[v], pm.a1[v], pm.theta[pm.slot[v]]);
+        }
     }
     __threadfence();
     st_sync_consumers();

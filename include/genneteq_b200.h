@@ -86,6 +86,12 @@ int gne_pot_finalize_slots(gne_dev *d, int count, const int32_t *slots);
 int gne_pot_update_fused(gne_dev *d, int64_t nNodes, const int32_t *node, const double *a0, const double *a1,
                          const int32_t *slot, int64_t nTheta, const int32_t *tslot, const double *theta,
                          int64_t nFinal, const int32_t *fnode);
+/* the same with the finalized potentials supplied: fpi[i] = the new pi of fnode[i], computed by the caller with the
+ * reference's unfused operations (a0 + a1 * theta).  The device then only stores them - the relabel folded into the
+ * pricing pass needs no dependent loads before its release flag.  fpi == NULL: as gne_pot_update_fused.          */
+int gne_pot_update_fused_pi(gne_dev *d, int64_t nNodes, const int32_t *node, const double *a0, const double *a1,
+                            const int32_t *slot, int64_t nTheta, const int32_t *tslot, const double *theta,
+                            int64_t nFinal, const int32_t *fnode, const double *fpi);
 /* direct write of pi (callers that computed potentials themselves)                            */
 int gne_pot_set(gne_dev *d, int64_t count, const int32_t *node, const double *pi);
 int gne_pot_set_all(gne_dev *d, const double *pi);
