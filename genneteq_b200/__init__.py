@@ -61,6 +61,9 @@ SIGNATURES = {
     "gne_pot_get_all": (C.c_int, [_vp, _f64p]),
     "gne_price_lv": (C.c_int, [_vp, _f64p, _i64p, _i64p, C.c_int64, C.POINTER(C.c_int)]),
     "gne_price_lv_begin": (C.c_int, [_vp, _f64p, _i64p, C.POINTER(C.c_int)]),
+    "gne_price_lv_launch": (C.c_int, [_vp]),
+    "gne_price_lv_ready": (C.c_int, [_vp]),
+    "gne_price_lv_complete": (C.c_int, [_vp, _f64p, _i64p, C.POINTER(C.c_int)]),
     "gne_price_lv_at": (C.c_int, [_vp, C.c_int64, _i64p]),
     "gne_price_qs": (C.c_int, [_vp, C.c_int64, C.c_int64, _i64p, _f64p, _i64p, _i64p, _i64p]),
     "gne_price_scan_list": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _f64p, C.c_int64, _i64p, _i64p]),
@@ -90,6 +93,7 @@ SIGNATURES = {
     "gne_solver_set_comm_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gne_solver_set_trace": (C.c_int, [_vp, _i32p, _i32p, C.c_int64]),
     "gne_solver_trace_len": (C.c_int64, [_vp]),
+    "gne_solver_solve_batch": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, C.c_int, _i64p, C.POINTER(C.c_int)]),
     "gne_solver_solve": (C.c_int, [_vp, C.c_int, C.c_int64, _i64p, C.POINTER(C.c_int)]),
     "gne_solver_num_nodes": (C.c_int, [_vp]),
     "gne_solver_num_vars": (C.c_int64, [_vp]),
@@ -528,6 +532,16 @@ class Solver:
     def device(self):
         h = lib.gne_solver_device(self.h)
         return _BorrowedDevice(_vp(h), self.n + 16, self.M - self.n + 16, self.M - self.n) if h else None
+
+
+def solve_batch(solvers, presolve, max_pivots=-1, threads=0):
+    """gne_solver_solve for several independent solvers at once: `threads` host threads (0 = one per core) interleave them.
+    Returns [(iterations, finished)] per solver."""
+    B = len(solvers)
+    hs = (_vp * B)(*[s.h for s in solvers])
+    it = np.zeros(B, np.int64); fin = (C.c_int * B)()
+    _ck(lib.gne_solver_solve_batch(hs, B, 1 if presolve else 0, max_pivots, threads, _p(it, _i64p), fin), "gne_solver_solve_batch")
+    return [(int(it[i]), bool(fin[i])) for i in range(B)]
 
 
 def forest_replay(n, tail, head, supply, e, l):

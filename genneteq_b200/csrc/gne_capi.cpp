@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gneb200;
@@ -257,6 +258,47 @@ extern "C" int gne_shard_range(int64_t m, int rank, int nranks, int64_t *lo, int
 
 extern "C" int gne_solver_destroy(gne_solver *s) { delete s; return GNE_OK; }
 extern "C" int gne_solver_set_rules(gne_solver *s, int p1, int p2) { s->solver.phaseIpivot = p1; s->solver.phaseIIpivot = p2; return GNE_OK; }
+// One host thread per group of solvers; a thread keeps stepping the solvers of its group round-robin and never
+// blocks on the device while another of its solvers has host work to do.
+extern "C" int gne_solver_solve_batch(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int64_t *iters, int *finished) {
+    return guarded("gne_solver_solve_batch", [&]() -> int {
+        if (B <= 0 || !s || !iters || !finished) { gne_set_error("gne_solver_solve_batch: bad argument"); return GNE_ERR_ARG; }
+        int T = threads > 0 ? threads : (int) std::thread::hardware_concurrency();
+        if (T <= 0) T = 1;
+        if (T > B) T = B;
+        std::vector<int> status((size_t) B, GNE_OK);
+        std::vector<std::string> errors((size_t) B);
+        auto work = [&](int w) {
+            std::vector<int> mine;
+            for (int i = w; i < B; i += T) mine.push_back(i);
+            std::vector<char> live(mine.size(), 1);
+            size_t alive = 0;
+            for (size_t k = 0; k < mine.size(); ++k) {
+                const int i = mine[k];
+                iters[i] = 0; finished[i] = 1;
+                status[i] = s[i]->solver.solveBegin(presolve != 0, maxPivots);
+                if (status[i] != GNE_OK) { errors[i] = gne_last_error(); live[k] = 0; } else ++alive;
+            }
+            while (alive > 0) {
+                for (size_t k = 0; k < mine.size(); ++k) {
+                    if (!live[k]) continue;
+                    const int i = mine[k];
+                    // with a single live solver left there is nothing to interleave with: block in the step
+                    const int r = s[i]->solver.solveStep(alive == 1);
+                    if (r == 1) continue;
+                    if (r < 0) { status[i] = -r; errors[i] = gne_last_error(); }
+                    else { status[i] = s[i]->solver.solveEnd(&iters[i], &finished[i]); if (status[i] != GNE_OK) errors[i] = gne_last_error(); }
+                    live[k] = 0; --alive;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
+        work(0);
+        for (size_t k = 0; k < pool.size(); ++k) pool[k].join();
+        for (int i = 0; i < B; ++i) if (status[i] != GNE_OK) { gne_set_error("solver %d of the batch: %s", i, errors[i].c_str()); return status[i]; }
+        return GNE_OK; });
+}
 extern "C" int gne_solver_set_comm_host(gne_solver *s, int rank, int nranks, gne_allgather_fn allgather, void *ctx) {
     return guarded("gne_solver_set_comm_host", [&]() -> int {
         if (!allgather) { gne_set_error("gne_solver_set_comm_host: no all-gather callback"); return GNE_ERR_ARG; }

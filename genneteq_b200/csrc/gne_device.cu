@@ -158,6 +158,7 @@ struct gne_dev {
     bool timing = false;                           // bracket pricing kernels with CUDA events (gne_dev_set_timing)
     std::vector<cudaEvent_t> benchEv;              // per-step event pairs of gne_bench_price_lv
     bool exchangeFused = false;                    // the last streamed pass carried the shard exchange itself
+    bool lvLaunched = false;                       // a pass started by gne_price_lv_launch awaits gne_price_lv_complete
     bool fastMath = false;                         // gne_dev_set_fast_math / GNE_FAST_MATH
     bool pdl = true;                               // programmatic dependent launch between a pivot's kernels (GNE_PDL=0 disables)
     unsigned long long lvSeq = 0;                  // sequence number of the last LV pass launched
@@ -972,10 +973,38 @@ static const int64_t LV_DEVICE_LIST_MIN = 4096;
 static int launch_shard_exchange(gne_dev *d);
 static int sharded_band_fallback(gne_dev *d, double M, std::vector<int64_t> &list, double *largest);
 
-extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t *count, int *any)
+// The LV pass in two halves, so that a host thread can look after another instance while the pass runs:
+// gne_price_lv_launch starts it, gne_price_lv_ready says (without blocking) whether its result has arrived,
+// gne_price_lv_complete waits for it and resolves the offending list.  gne_price_lv_begin = launch + complete.
+extern "C" int gne_price_lv_launch(gne_dev *d)
 {
     CK(cudaSetDevice(d->device));
     int rc = price_lv_local(d); if (rc) return rc;       // (queued updates ride with the pass or are launched ahead of it)
+    if (d->nranks > 1 && d->p2p) { rc = launch_shard_exchange(d); if (rc) return rc; }
+    d->lvLaunched = true;
+    return GNE_OK;
+}
+
+extern "C" int gne_price_lv_ready(gne_dev *d)
+{
+    if (!d->lvLaunched) return 1;
+    if (d->nranks > 1 && !d->p2p) return 1;              // (the all-gather path blocks in complete)
+    const volatile LvResult *r = d->lvRes;
+    return r->hSeqA == d->lvSeq && (r->hTagB >> 16) == (d->lvSeq & ((1ull << 48) - 1ull)) ? 1 : 0;
+}
+
+extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t *count, int *any)
+{
+    int rc = gne_price_lv_launch(d); if (rc) return rc;
+    return gne_price_lv_complete(d, largestViolation, count, any);
+}
+
+extern "C" int gne_price_lv_complete(gne_dev *d, double *largestViolation, int64_t *count, int *any)
+{
+    if (!d->lvLaunched) { gne_set_error("gne_price_lv_complete: no pass was launched"); return GNE_ERR_ARG; }
+    d->lvLaunched = false;
+    CK(cudaSetDevice(d->device));
+    int rc = GNE_OK;
     d->lvMode = 0; d->lvList.clear(); d->lvCount = 0;
     double L = -1.0;
     int anyV = 0;
@@ -984,7 +1013,6 @@ extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t 
         rc = gne_dev_price_lv_sharded(d, &L, d->lvList, &anyV); if (rc) return rc;
     } else {
         // single GPU, or sharded over peer mailboxes (the merged block arrives like a single GPU's)
-        if (d->nranks > 1) { rc = launch_shard_exchange(d); if (rc) return rc; }
         LvView view;
         rc = wait_lv_result(d, &view); if (rc) return rc;
         const LvView *r = &view;

@@ -603,12 +603,19 @@ int GenNetEq::getVarWithLargestViolation(int32_t *out)            // :133-157 (L
 {
     isOptimal = true;
     offendingVars.clear();
+    GNE_TRY(gne_price_lv_launch(dev));
+    return completeLargestViolation(out);
+}
+
+// second half of getVarWithLargestViolation: the pass has been launched (gne_price_lv_launch)
+int GenNetEq::completeLargestViolation(int32_t *out)
+{
     double largest = -1.0;
     int64_t cnt = 0;
     int any = 0;
     // the device leaves offendingVars where it is (it can be hundreds of thousands long in Phase I);
     // only its length and the member drand48 picks are needed here
-    GNE_TRY(gne_price_lv_begin(dev, &largest, &cnt, &any));
+    GNE_TRY(gne_price_lv_complete(dev, &largest, &cnt, &any));
     arcsPriced += (double) setNBarc.size();
     float ms = 0; gne_dev_last_kernel_ms(dev, &ms); kernelMs += ms;
     if (any) isOptimal = false;
@@ -1075,19 +1082,38 @@ void GenNetEq::checkFeasibility()                                 // :227-288
         if (isArtificial[setNBarc[*it]]) { isInfeasible = true; return; }
 }
 
-int GenNetEq::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished)   // :60-117
+// GenNetEq::solve (genneteq.cpp:60-117) as a state machine, so that one host thread can drive several solvers:
+//   solveBegin   everything before the loop;
+//   solveStep    advances by one stage and never blocks on the device unless `block`: PREP (loop head: window / progress
+//                hooks, periodic flows, computePotentials, then either the LV pass is LAUNCHED or - any other rule - the
+//                entering variable is selected synchronously), WAIT (the launched pass: complete it when its result is
+//                there), then the pivot.  Returns 1 while there is more to do, 0 when the loop has ended, < 0 on error
+//                (the status is then in stepStatus);
+//   solveEnd     everything after the loop.
+// solve() = solveBegin + blocking solveStep until 0 + solveEnd.
+int GenNetEq::solveBegin(bool usePresolve, int64_t maxPivots)
 {
     const bool pIwasInfeasible = usePresolve ? false : isInfeasible;
     initializeStats(usePresolve);
     GNE_TRY(setVariableCosts());
-    *finished = 1;
-    *iters = 0;
-    if (!presolve && pIwasInfeasible) { isInfeasible = true; return GNE_OK; }
-    const double t0 = wallNow();
+    stFinished = 1;
+    stSkip = false;
+    stStage = 0;
+    if (!presolve && pIwasInfeasible) { isInfeasible = true; stSkip = true; return GNE_OK; }
+    stT0 = wallNow();
     computeFlows(0);
-    int64_t budget = maxPivots;
+    stMaxPivots = maxPivots;
+    stBudget = maxPivots;
     callPivots = 0;
-    while (!isOptimal && !isUnbounded) {
+    return GNE_OK;
+}
+
+#define STEP_TRY(call) do { int rc_ = (call); if (rc_ != GNE_OK) return -rc_; } while (0)
+int GenNetEq::solveStep(bool block)
+{
+    if (stSkip) return 0;
+    if (stStage == 0) {
+        if (!(!isOptimal && !isUnbounded)) return 0;
         if (winStart >= 0 && callPivots == winStart && winT0 == 0.0) { gne_dev_sync(dev); getCounters(winC0); winT0 = wallNow(); }
         if (winStart >= 0 && callPivots == winStart + winLen && winT1 == 0.0) { gne_dev_sync(dev); winT1 = wallNow(); getCounters(winC1); }
         if (progEvery > 0 && progBuf && callPivots % progEvery == 0 && progRows < progCap) {
@@ -1098,34 +1124,76 @@ int GenNetEq::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *fi
             for (int sl = 0; sl < forest.numSlots(); ++sl) if (forest.tree(sl).type != TREE_FREE) big = std::max(big, forest.tree(sl).nodes.size());
             row[13] = (double) big;
         }
-        if (maxPivots >= 0 && budget == 0) { *finished = 0; break; }
+        if (stMaxPivots >= 0 && stBudget == 0) { stFinished = 0; return 0; }
         if ((loopIter % 1000) == 0) computeFlows(2);
         const double a = wallNow();
-        GNE_TRY(computePotentials());
-        const double b = wallNow();
-        GNE_TRY(identifyEnteringVariable());
-        const double c = wallNow();
-        secsPotentials += b - a; secsPricing += c - b;
-        if (eVar != -1) {
-            GNE_TRY(pivot());
-            secsPivot += wallNow() - c;
-            if (lVar != -1) {
-                if (traceLen < traceCap) { traceE[traceLen] = eVar; traceL[traceLen] = lVar; }
-                ++traceLen;
-            }
-            ++loopIter; ++pivots; ++callPivots;
-            if (presolve) ++phaseIiters; else ++phaseIIiters;
-            if (budget > 0) --budget;
+        STEP_TRY(computePotentials());
+        stB = wallNow();
+        secsPotentials += stB - a;
+        const int rule = presolve ? phaseIpivot : phaseIIpivot;
+        const bool lvRule = rule == GNE_LV || rule == GNE_LVW || rule == GNE_LVA || rule == GNE_LVE;
+        if (lvRule && !cyclingDetected) {
+            // getVarWithLargestViolation, first half: the pass is on its way
+            isOptimal = true;
+            offendingVars.clear();
+            STEP_TRY(gne_price_lv_launch(dev));
+            stStage = 1;
+            if (!block) return 1;
+        } else {
+            STEP_TRY(identifyEnteringVariable());
+            stStage = 2;
         }
     }
-    if (*finished) {
+    if (stStage == 1) {
+        if (!block && !gne_price_lv_ready(dev)) return 1;
+        STEP_TRY(completeLargestViolation(&eVar));
+        stStage = 2;
+    }
+    // stage 2: the pivot
+    const double c = wallNow();
+    secsPricing += c - stB;
+    if (eVar != -1) {
+        STEP_TRY(pivot());
+        secsPivot += wallNow() - c;
+        if (lVar != -1) {
+            if (traceLen < traceCap) { traceE[traceLen] = eVar; traceL[traceLen] = lVar; }
+            ++traceLen;
+        }
+        ++loopIter; ++pivots; ++callPivots;
+        if (presolve) ++phaseIiters; else ++phaseIIiters;
+        if (stBudget > 0) --stBudget;
+    }
+    stStage = 0;
+    return 1;
+}
+
+#undef STEP_TRY
+
+int GenNetEq::solveEnd(int64_t *iters, int *finished)
+{
+    *finished = stFinished;
+    *iters = 0;
+    if (stSkip) return GNE_OK;
+    if (stFinished) {
         computeFlows(0);
         if (presolve) checkFeasibility();
         GNE_TRY(verifyOptimality());
     }
-    secsTotal += wallNow() - t0;
+    secsTotal += wallNow() - stT0;
     *iters = loopIter;
     return GNE_OK;
+}
+
+int GenNetEq::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished)   // :60-117
+{
+    *finished = 1; *iters = 0;
+    GNE_TRY(solveBegin(usePresolve, maxPivots));
+    while (true) {
+        const int r = solveStep(true);
+        if (r < 0) return -r;
+        if (r == 0) break;
+    }
+    return solveEnd(iters, finished);
 }
 
 void GenNetEq::getFlows(double *out) const { memcpy(out, flow.data(), sizeof(double) * (size_t) M); }

@@ -67,6 +67,10 @@ class GenNetEq {
 
     int initialize(Graph *g, int initType, int cudaDevice);          // gneInit.cpp:25-44
     int solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished);   // genneteq.cpp:60-117
+    // the same loop in pieces (gne_solver_solve_batch: one host thread interleaves several solvers)
+    int solveBegin(bool usePresolve, int64_t maxPivots);
+    int solveStep(bool block);                          // 1: more to do, 0: loop ended, < 0: -(gne_status)
+    int solveEnd(int64_t *iters, int *finished);
 
     int phaseIpivot = GNE_LVW, phaseIIpivot = GNE_LVW;               // main.cpp:72-73 defaults
 
@@ -167,6 +171,12 @@ class GenNetEq {
     std::vector<std::pair<int32_t, int32_t> > activeKeys, ordKids;
     std::vector<int32_t> orderedArcs;
 
+    // ---- state of the step-wise solve loop
+    int stStage = 0, stFinished = 1;
+    bool stSkip = false;
+    int64_t stMaxPivots = -1, stBudget = -1;
+    double stT0 = 0.0, stB = 0.0;
+
     // ---- trace / counters
     int32_t *traceE = nullptr, *traceL = nullptr;
     int64_t traceCap = 0, traceLen = 0;
@@ -214,6 +224,7 @@ class GenNetEq {
     int identifyEnteringVariable();
     int selectEnteringVariable(int32_t *out);
     int getVarWithLargestViolation(int32_t *out);
+    int completeLargestViolation(int32_t *out);
     int getFirstVarWithViolation(int32_t *out);
     int getRandomVarWithViolation(int32_t *out);
     int getRandomVarWeightedByViolation(int32_t *out);

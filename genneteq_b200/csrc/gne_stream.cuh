@@ -29,7 +29,8 @@ namespace gne {
 
 constexpr int ST_THREADS = 256;                         // consumer threads
 constexpr int ST_PRODUCER = 32;                         // + one producer warp
-constexpr int ST_BLOCK = ST_THREADS + ST_PRODUCER;
+constexpr int ST_UPDATER = 32;                          // + one warp that applies the folded relabel (in the elected CTA) and leaves
+constexpr int ST_BLOCK = ST_THREADS + ST_PRODUCER + ST_UPDATER;
 constexpr int ST_ITEMS = 4;
 constexpr int ST_STAGES = 3;                            // production shape: 3 stages x 2 CTAs per SM (see st_kernel_for)
 constexpr int ST_TILE = ST_THREADS * ST_ITEMS;          // 1024 arcs per stage
@@ -242,30 +243,30 @@ __device__ __noinline__ void lv_reduce_records(const LvCtas &in, int G, const Lv
                    reinterpret_cast<int64_t *>(scratch), reinterpret_cast<double *>(scratch + 8 * LIST));
 }
 
-// The folded relabel of the last pivot (what k_update_small does as its own launch), by the 256 consumer threads of
-// the first CTA to arrive; releases f.updFlag = f.seq when everything is visible device-wide.
-__device__ __forceinline__ void st_apply_update(const SmallUpdate &u, const NbMut &nb, const PotMut &pm, const LvFused &f)
+// The folded relabel of the last pivot (what k_update_small does as its own launch), by ONE warp - the updater warp of the
+// first CTA whose updater gets there; releases f.updFlag = f.seq when everything is visible device-wide.  The consumer
+// warps never wait for the election: they only look at the flag before their first gather.
+__device__ __forceinline__ void st_apply_update_warp(const SmallUpdate &u, const NbMut &nb, const PotMut &pm, const LvFused &f, int lane)
 {
-    const int t = threadIdx.x;
-    if (t < u.ops.n) {
-        const int64_t l = u.ops.local[t];
-        nb.tail[l] = u.ops.tail[t]; nb.head[l] = u.ops.head[t];
-        nb.cost[l] = u.ops.cost[t]; nb.mult[l] = u.ops.mult[t]; nb.state[l] = u.ops.state[t];
+    for (int i = lane; i < u.ops.n; i += 32) {
+        const int64_t l = u.ops.local[i];
+        nb.tail[l] = u.ops.tail[i]; nb.head[l] = u.ops.head[i];
+        nb.cost[l] = u.ops.cost[i]; nb.mult[l] = u.ops.mult[i]; nb.state[l] = u.ops.state[i];
     }
-    if (t < u.nNodes) { const int v = u.node[t]; pm.a0[v] = u.a0[t]; pm.a1[v] = u.a1[t]; pm.slot[v] = u.slot[t]; }
-    if (t < u.nTheta) pm.theta[u.tslot[t]] = u.theta[t];
-    if (u.hasPi) {                                       // the host sent the finalized values: plain stores, no barrier, no loads
-        if (t < u.nFinal) pm.pi[u.fnode[t]] = u.fpi[t];
+    for (int i = lane; i < u.nNodes; i += 32) { const int v = u.node[i]; pm.a0[v] = u.a0[i]; pm.a1[v] = u.a1[i]; pm.slot[v] = u.slot[i]; }
+    for (int i = lane; i < u.nTheta; i += 32) pm.theta[u.tslot[i]] = u.theta[i];
+    if (u.hasPi) {                                       // the host sent the finalized values: plain stores, no loads
+        for (int i = lane; i < u.nFinal; i += 32) pm.pi[u.fnode[i]] = u.fpi[i];
     } else {
-        st_sync_consumers();
-        if (t < u.nFinal) {
-            const int v = u.fnode[t];
+        __syncwarp();                                    // the records and thetas above are visible to the whole warp
+        for (int i = lane; i < u.nFinal; i += 32) {
+            const int v = u.fnode[i];
             pm.pi[v] = pot_value(pm.a0[v], pm.a1[v], pm.theta[pm.slot[v]]);
         }
     }
     __threadfence();
-    st_sync_consumers();
-    if (t == 0) st_st_release(f.updFlag, f.seq);
+    __syncwarp();
+    if (lane == 0) st_st_release(f.updFlag, f.seq);
 }
 
 template <int STAGES, int MINB>
@@ -311,17 +312,21 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
                 st_bulk_g2s(b + 24 * ST_TILE, nb.state + l0, ST_TILE, &full[s]);
             }
         }
+        if (t >= ST_THREADS + ST_PRODUCER) {
+            // ---------------- updater warp: the first one to arrive (device-wide) applies the folded relabel
+            const int lane = t & 31;
+            if ((u.ops.n | u.nNodes | u.nTheta | u.nFinal) != 0) {
+                unsigned int first = 0u;
+                if (lane == 0) first = (atomicAdd(f.arrive, 1u) == 0u) ? 1u : 0u;
+                first = __shfl_sync(0xffffffffu, first, 0);
+                if (first) st_apply_update_warp(u, nbMut, pm, f, lane);
+            }
+        }
         return;
     }
     // ---------------- consumers
     const int lane = t & 31;
     const bool hasUpd = (u.ops.n | u.nNodes | u.nTheta | u.nFinal) != 0;
-    __shared__ int sUpd;
-    if (hasUpd) {
-        if (t == 0) sUpd = (atomicAdd(f.arrive, 1u) == 0u) ? 1 : 0;
-        st_sync_consumers();
-        if (sUpd) st_apply_update(u, nbMut, pm, f);
-    }
     double v1 = -1.0, v2 = -1.0;                        // largest (first position on ties) and second largest
     int64_t p1 = 0;
     double vv[ST_ITEMS];                                // single mode: the thread's four values
@@ -357,9 +362,9 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
                     if (u.ops.local[i] == tile * ST_TILE + o) { tl[k] = u.ops.tail[i]; hd[k] = u.ops.head[i]; cs[k] = u.ops.cost[i]; mu[k] = u.ops.mult[i]; st[k] = (int) u.ops.state[i]; }
             }
         }
-        if (it == 0 && hasUpd) {                        // the relabel must be visible before the first gather
-            if (lane == 0) while (st_ld_acquire(f.updFlag) != f.seq) { }
-            __syncwarp();
+        if (it == 0 && hasUpd) {                        // the relabel must be visible before the first gather:
+            if (t == 0) while (st_ld_acquire(f.updFlag) != f.seq) { }   // one poller per CTA (2 368 warps on one line would
+            st_sync_consumers();                                        // delay the very store they wait for)
         }
 #ifdef GNE_STAMPS
         if (it == 0 && t == 0 && f.stamps) atomicMax(reinterpret_cast<unsigned long long *>(f.stamps + 1), (unsigned long long) st_globaltimer());   // last CTA to reach its first gather

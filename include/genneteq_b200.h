@@ -110,6 +110,11 @@ int gne_price_lv(gne_dev *d, double *largestViolation, int64_t *count, int64_t *
  * picks offendingVars[drand48() * size], gnePivotRules.cpp:152-153): begin runs the pass and keeps
  * the list inside the handle — long exact-tie lists stay on the device — at(i) returns member i.   */
 int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t *count, int *any);
+/* the same in two halves, so that one host thread can drive several instances: launch starts the pass, ready says
+ * without blocking whether its result has arrived (1 / 0), complete waits for it and resolves the list              */
+int gne_price_lv_launch(gne_dev *d);
+int gne_price_lv_ready(gne_dev *d);
+int gne_price_lv_complete(gne_dev *d, double *largestViolation, int64_t *count, int *any);
 int gne_price_lv_at(gne_dev *d, int64_t index, int64_t *pos);
 
 /* quickSelect's arc loop (gnePivotRules.cpp:742-756): scan from `cursor` (wrapping) until `want`
@@ -213,6 +218,11 @@ int64_t gne_solver_trace_len(const gne_solver *s);
 /* GenNetEq::solve(usePresolve) (genneteq.cpp:60-117).  maxPivots < 0: to termination.
  * *iters = loopIter; *finished = 0 when the pivot budget stopped it.                          */
 int gne_solver_solve(gne_solver *s, int presolve, int64_t maxPivots, int64_t *iters, int *finished);
+/* gne_solver_solve for B independent solvers at once (configs[3]: a batch of instances on one GPU), driven by `threads`
+ * host threads (0 = one per core, at most B): each thread interleaves its share of the solvers - while one solver's
+ * pricing pass runs on the device it does the host work (pivot, relabel) of another - so the host never oversubscribes
+ * its cores and every instance stream stays busy.  iters / finished: arrays of B.                                  */
+int gne_solver_solve_batch(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int64_t *iters, int *finished);
 
 int gne_solver_num_nodes(const gne_solver *s);
 int64_t gne_solver_num_vars(const gne_solver *s);
