@@ -567,7 +567,8 @@ def batch_arm(args):
     # (gne_solver_solve_batch) - while one instance's pass runs on the device its thread pivots another one
     for s in solvers:
         s.set_window(W, args.steps)
-    gne.solve_batch(solvers, True, W + args.steps, threads=min(B, os.cpu_count() or 1))
+    nthreads = args.batch_threads if args.batch_threads > 0 else min(B, os.cpu_count() or 1)
+    gne.solve_batch(solvers, True, W + args.steps, threads=nthreads)
     wins = [s.window() for s in solvers]
     edges = [s.window_edges for s in solvers]
     # instance 0 of rank 0 is the (seed 1000) instance the reference's prefix fixture was written for
@@ -627,7 +628,7 @@ def batch_arm(args):
             "ms_per_step": 1e3 * dev_wall / (2 * args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": workload_config("c4-batch", world, batch=B),
-            "sharding": "replicas only: one solver handle / CUDA stream per instance, min(B, cores) host threads interleaving them, no collective",
+            "sharding": "replicas only: one solver handle / CUDA stream per instance, %d host threads interleaving them, no collective" % nthreads,
             "parity": parity,
             "e2e": {"value": arcs / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(pivots, 1), "d2h_bytes_per_step": d2h / max(pivots, 1),
                     "pivots_per_s": pivots / wall, "ms_per_pivot_per_instance": 1e3 * wall / args.steps},
@@ -662,6 +663,7 @@ def main():
     ap.add_argument("--window", default="start", choices=["start", "deep"],
                     help="start: pivots from the initial basis (default); deep: from the recorded basis of tests/golden/deep_<workload>.npz")
     ap.add_argument("--batch", type=int, default=32, help="instances per GPU for --workload c4-batch")
+    ap.add_argument("--batch-threads", type=int, default=0, help="host threads driving the batch (0: min(batch, cores))")
     args = ap.parse_args()
     if args.workload == "c4-batch":
         return batch_arm(args)

@@ -466,6 +466,47 @@ def test_equal_flow_reduced_costs_match_the_dense_loop(gne):
     d.close()
 
 
+def test_batch_driver_interleaves_without_changing_any_solve(gne):
+    """gne_solver_solve_batch (configs[3]: several independent instances on one GPU, fewer host threads than instances, each
+    thread stepping its solvers round-robin through launch / ready / complete): every instance must produce exactly the
+    pivots, flows and objective it produces alone - for the Dantzig rule (asynchronous passes) and for rules that price
+    synchronously (QS, CL) - including instances that finish at different times and the 2- and 3-node graphs."""
+    names = ["s_wide_s3", "s_lossy_s4", "s_pow2_s5", "s_near1_s6", "e_two_nodes_s13", "e_three_nodes_s14", "e_nosupply_s12"]
+    for rule in ("LV", "QS", "CL"):
+        loaded = [load_gold(nm) for nm in names]
+        solvers = [gne.Solver(i.n, i.tail, i.head, i.ub, i.cost, i.mult, i.supply, rule1=rule) for (_, i) in loaded]
+        r1 = gne.solve_batch(solvers, True, threads=3)
+        r2 = gne.solve_batch(solvers, False, threads=2)
+        for (z, inst), s, a, b in zip(loaded, solvers, r1, r2):
+            assert (a[0], b[0]) == tuple(int(v) for v in z[rule + "_p"])
+            e, l = s.trace
+            assert np.array_equal(e, z[rule + "_e"]) and np.array_equal(l, z[rule + "_l"])
+            assert s.objective == float(z[rule + "_objective"])
+            assert np.array_equal(s.flows(), z[rule + "_flows"])
+            assert np.array_equal(s.potentials(), z[rule + "_potentials"])
+            s.close()
+
+
+def test_lv_pass_in_two_halves(gne):
+    """gne_price_lv_launch / _ready / _complete: the same result as gne_price_lv_begin; ready turns 1 without blocking."""
+    import time
+    rng = np.random.default_rng(23)
+    n, N = 30000, 2_000_003
+    tail, head, cost, mult, state, pi = random_soa(rng, n, N)
+    d = gne.Device(n, N + 16)
+    d.nb_reset(tail, head, cost, mult, state)
+    d.pot_set_all(pi)
+    exp = d.price_lv_begin()
+    gne._ck(gne.lib.gne_price_lv_launch(d.h), "gne_price_lv_launch")
+    t0 = time.time()
+    while not gne.lib.gne_price_lv_ready(d.h):
+        assert time.time() - t0 < 10.0
+    largest = C.c_double(0); count = C.c_int64(0); anyv = C.c_int(0)
+    gne._ck(gne.lib.gne_price_lv_complete(d.h, C.byref(largest), C.byref(count), C.byref(anyv)), "gne_price_lv_complete")
+    assert (largest.value, count.value, bool(anyv.value)) == exp
+    d.close()
+
+
 def test_potential_finalize_by_slot(gne):
     """gne_pot_finalize_slots: only the nodes of the named trees get a new pi (a changed theta of a big tree costs one
     sweep over the slot column, no node list); the others keep theirs bit for bit."""
