@@ -550,7 +550,10 @@ def batch_arm(args):
     # every instance's persistent pricing pass gets its share of the CTA slots (2 per SM) so that the B passes are
     # resident together instead of queueing behind each other
     sms = torch.cuda.get_device_properties(local).multi_processor_count
-    ctas = max(1, (2 * sms) // B)
+    per = max(0, min(args.batch_group, 8))
+    # launch groups (the default): `per` instances per launch of the batched kernel, together on the 2 x SMs CTA slots;
+    # --batch-group 0: one launch and one stream per instance, every pass on a 1/B share
+    ctas = args.batch_ctas if args.batch_ctas > 0 else max(1, (2 * sms) // (per if per > 0 else B))
     os.environ["GNE_STREAM_CTAS"] = str(ctas)
     os.environ.setdefault("GNE_POLL_SLEEP_US", "20")    # B host threads on fewer cores: the result poll sleeps between looks
     solvers = []
@@ -567,8 +570,17 @@ def batch_arm(args):
     # (gne_solver_solve_batch) - while one instance's pass runs on the device its thread pivots another one
     for s in solvers:
         s.set_window(W, args.steps)
-    nthreads = args.batch_threads if args.batch_threads > 0 else min(B, os.cpu_count() or 1)
-    gne.solve_batch(solvers, True, W + args.steps, threads=nthreads)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if args.batch_threads > 0:
+        nthreads = args.batch_threads
+    elif per > 0:
+        # grouped launches: a few threads per rank are enough (a thread pivots one instance while its others are priced);
+        # leave cores to the other ranks of the node
+        nthreads = max(1, min(B // max(per // 2, 1), max(2, cores // max(world, 1) - 1), 8))
+    else:
+        nthreads = min(B, cores)
+    bstats = {}
+    gne.solve_batch(solvers, True, W + args.steps, threads=nthreads, per_launch=per, stats=bstats)
     wins = [s.window() for s in solvers]
     edges = [s.window_edges for s in solvers]
     # instance 0 of rank 0 is the (seed 1000) instance the reference's prefix fixture was written for
@@ -579,8 +591,62 @@ def batch_arm(args):
     h2d = sum(w[2]["h2d_bytes"] - w[1]["h2d_bytes"] for w in wins)
     d2h = sum(w[2]["d2h_bytes"] - w[1]["d2h_bytes"] for w in wins)
     launches = sum(w[2]["launches"] - w[1]["launches"] for w in wins)
-    # device-resident leg: every instance replays K device steps on its own stream, all streams concurrently
     devs = [s.device() for s in solvers]
+    if per > 0:
+        # (the handles count one launch per pass; grouped, a launch carries several passes: scale by the measured ratio)
+        passes_all = sum(w[2]["launches"] for w in wins)
+        launches = launches * bstats.get("group_launches", passes_all) / max(passes_all, 1)
+        # device-resident leg: K rounds of passes over all instances, `per` instances per launch of the batched kernel,
+        # launches alternating between two streams; device clock (events) around all rounds
+        gne.bench_lv_groups(devs, 3, per, 2)
+        dev_ms, dev_launches = gne.bench_lv_groups(devs, args.steps, per, 2)
+        one_ms, _ = gne.bench_lv_groups(devs[:per], args.steps, per, 1)       # one launch at a time: the kernel's own duration
+        clocks = sampler.stop()
+        dev_wall = dev_ms * 1e-3
+        for s in solvers:
+            s.close()
+        if dist is not None:
+            t = torch.tensor([wall, dev_wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall, dev_wall = (float(x) for x in t.cpu())
+            tot = torch.tensor([arcs, pivots, h2d, d2h, launches + dev_launches], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            arcs, pivots, h2d, d2h, launches = (float(x) for x in tot.cpu())
+            dist.barrier()
+            dist.destroy_process_group()
+        else:
+            launches += dev_launches
+        if rank != 0:
+            return 0
+        peak, peak_src = peaks()
+        alg = 25.0 * m + 8.0 * n
+        line = {"metric": METRIC, "value": world * B * m * args.steps / dev_wall, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": 1e3 * dev_wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config("c4-batch", world, batch=B),
+                "sharding": "replicas only: %d instances per GPU, their LV passes in launch groups of %d (one grid, %d CTAs per instance), "
+                            "%d host threads per rank interleaving them, no collective" % (B, per, ctas, nthreads),
+                "parity": parity,
+                "e2e": {"value": arcs / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(pivots, 1), "d2h_bytes_per_step": d2h / max(pivots, 1),
+                        "pivots_per_s": pivots / wall, "ms_per_pivot_per_instance": 1e3 * wall / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "host_cores_present": os.cpu_count(), "host_cores_usable": cores,
+                # per GPU: a round of passes moves B x (25 B x arcs + 8 B x nodes)
+                "roofline": {"bound": "hbm", "achieved": B * alg * args.steps / dev_wall / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": B * alg * args.steps / dev_wall / 1e9 / peak, "traffic": None,
+                             "kernel": "k_price_lv_batch: %d instances per launch, %d CTAs per instance (aggregate bytes of all passes / "
+                                       "device time of the whole leg; kernel_ms = one launch timed alone)" % (per, ctas),
+                             "kernel_ms": one_ms / args.steps, "algorithmic_bytes_per_launch": per * alg, "peak_source": peak_src}}
+        if not args.no_cpu_baseline and world == 1:
+            r = batch_reference(args, B, 12, 2)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                                    "sample": "%d instances, one reference process per instance on %d host cores, %d iterations after %d warm-up" % (
+                                        r["instances"], r["cores"], r["steps"], r["warmup"]), "ms_per_pivot": r["ms_per_pivot"]}
+        print(json.dumps(line))
+        sys.stdout.flush()
+        if parity["vs_ref"] == "MISMATCH":
+            sys.stderr.write("bench.py: PARITY FAILURE %r\n" % (parity,))
+            return 3
+        return 0
+    # device-resident leg: every instance replays K device steps on its own stream, all streams concurrently
     for d in devs:
         d.bench_price_lv(3, False)
     torch.cuda.synchronize()
@@ -663,7 +729,9 @@ def main():
     ap.add_argument("--window", default="start", choices=["start", "deep"],
                     help="start: pivots from the initial basis (default); deep: from the recorded basis of tests/golden/deep_<workload>.npz")
     ap.add_argument("--batch", type=int, default=32, help="instances per GPU for --workload c4-batch")
-    ap.add_argument("--batch-threads", type=int, default=0, help="host threads driving the batch (0: min(batch, cores))")
+    ap.add_argument("--batch-threads", type=int, default=0, help="host threads driving the batch (0: chosen from the cores available)")
+    ap.add_argument("--batch-group", type=int, default=8, help="instances per launch of the batched LV kernel (1..8; 0: one launch per instance)")
+    ap.add_argument("--batch-ctas", type=int, default=0, help="CTAs per instance (0: 2 x SMs / instances per launch)")
     args = ap.parse_args()
     if args.workload == "c4-batch":
         return batch_arm(args)

@@ -80,6 +80,15 @@ SIGNATURES = {
     "gne_dev_launch_count": (C.c_int64, [_vp]),
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
     "gne_bench_price_qs": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _f32p, _i64p, _i64p]),
+    "gne_bench_lv_groups": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _i64p]),
+    "gne_lv_group_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int]),
+    "gne_lv_group_add": (C.c_int, [_vp, _vp]),
+    "gne_lv_group_launch": (C.c_int, [_vp]),
+    "gne_lv_group_pending": (C.c_int, [_vp]),
+    "gne_lv_group_launch_count": (C.c_int64, [_vp]),
+    "gne_lv_group_destroy": (C.c_int, [_vp]),
+    "gne_dev_cuda_device": (C.c_int, [_vp]),
+    "gne_solver_solve_batch_grouped": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _i64p, C.POINTER(C.c_int), _i64p]),
     "gne_comm_unique_id": (C.c_int, [_u8p]),
     "gne_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
     "gne_comm_init_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -534,14 +543,56 @@ class Solver:
         return _BorrowedDevice(_vp(h), self.n + 16, self.M - self.n + 16, self.M - self.n) if h else None
 
 
-def solve_batch(solvers, presolve, max_pivots=-1, threads=0):
-    """gne_solver_solve for several independent solvers at once: `threads` host threads (0 = one per core) interleave them.
-    Returns [(iterations, finished)] per solver."""
+def solve_batch(solvers, presolve, max_pivots=-1, threads=0, per_launch=0, stats=None):
+    """gne_solver_solve for several independent solvers at once: `threads` host threads (0 = one per core) interleave them;
+    per_launch > 0: the LV passes of a thread's solvers leave in launch groups of up to per_launch instances (one grid).
+    Returns [(iterations, finished)] per solver; stats (a dict) receives group_launches."""
     B = len(solvers)
     hs = (_vp * B)(*[s.h for s in solvers])
     it = np.zeros(B, np.int64); fin = (C.c_int * B)()
-    _ck(lib.gne_solver_solve_batch(hs, B, 1 if presolve else 0, max_pivots, threads, _p(it, _i64p), fin), "gne_solver_solve_batch")
+    if per_launch > 0:
+        gl = np.zeros(1, np.int64)
+        _ck(lib.gne_solver_solve_batch_grouped(hs, B, 1 if presolve else 0, max_pivots, threads, per_launch, _p(it, _i64p), fin,
+                                               _p(gl, _i64p)), "gne_solver_solve_batch_grouped")
+        if stats is not None:
+            stats["group_launches"] = int(gl[0])
+    else:
+        _ck(lib.gne_solver_solve_batch(hs, B, 1 if presolve else 0, max_pivots, threads, _p(it, _i64p), fin), "gne_solver_solve_batch")
     return [(int(it[i]), bool(fin[i])) for i in range(B)]
+
+
+class LvGroup:
+    """gne_lv_group: the LV passes of several device handles of one GPU in one launch."""
+
+    def __init__(self, device=0, max_pending=0):
+        self.h = _vp()
+        _ck(lib.gne_lv_group_create(C.byref(self.h), device, max_pending), "gne_lv_group_create")
+
+    def add(self, dev):
+        _ck(lib.gne_lv_group_add(self.h, dev.h), "gne_lv_group_add")
+
+    def launch(self):
+        _ck(lib.gne_lv_group_launch(self.h), "gne_lv_group_launch")
+
+    def pending(self):
+        return int(lib.gne_lv_group_pending(self.h))
+
+    def launch_count(self):
+        return int(lib.gne_lv_group_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            lib.gne_lv_group_destroy(self.h)
+            self.h = _vp()
+
+
+def bench_lv_groups(devs, reps, per_launch, n_streams=2):
+    """Device leg of a batch: (device ms of `reps` rounds of passes over all handles, launches of the batched kernel)."""
+    B = len(devs)
+    hs = (_vp * B)(*[d.h for d in devs])
+    ms = np.zeros(1, np.float32); ln = np.zeros(1, np.int64)
+    _ck(lib.gne_bench_lv_groups(hs, B, reps, per_launch, n_streams, _p(ms, _f32p), _p(ln, _i64p)), "gne_bench_lv_groups")
+    return float(ms[0]), int(ln[0])
 
 
 def forest_replay(n, tail, head, supply, e, l):

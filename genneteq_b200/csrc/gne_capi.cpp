@@ -10,6 +10,8 @@
 #include <map>
 #include <string>
 #include <thread>
+#include <sys/prctl.h>
+#include <time.h>
 #include <vector>
 
 using namespace gneb200;
@@ -259,45 +261,120 @@ extern "C" int gne_shard_range(int64_t m, int rank, int nranks, int64_t *lo, int
 extern "C" int gne_solver_destroy(gne_solver *s) { delete s; return GNE_OK; }
 extern "C" int gne_solver_set_rules(gne_solver *s, int p1, int p2) { s->solver.phaseIpivot = p1; s->solver.phaseIIpivot = p2; return GNE_OK; }
 // One host thread per group of solvers; a thread keeps stepping the solvers of its group round-robin and never
-// blocks on the device while another of its solvers has host work to do.
-extern "C" int gne_solver_solve_batch(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int64_t *iters, int *finished) {
-    return guarded("gne_solver_solve_batch", [&]() -> int {
-        if (B <= 0 || !s || !iters || !finished) { gne_set_error("gne_solver_solve_batch: bad argument"); return GNE_ERR_ARG; }
-        int T = threads > 0 ? threads : (int) std::thread::hardware_concurrency();
-        if (T <= 0) T = 1;
-        if (T > B) T = B;
-        std::vector<int> status((size_t) B, GNE_OK);
-        std::vector<std::string> errors((size_t) B);
-        auto work = [&](int w) {
-            std::vector<int> mine;
-            for (int i = w; i < B; i += T) mine.push_back(i);
-            std::vector<char> live(mine.size(), 1);
-            size_t alive = 0;
-            for (size_t k = 0; k < mine.size(); ++k) {
-                const int i = mine[k];
-                iters[i] = 0; finished[i] = 1;
-                status[i] = s[i]->solver.solveBegin(presolve != 0, maxPivots);
-                if (status[i] != GNE_OK) { errors[i] = gne_last_error(); live[k] = 0; } else ++alive;
-            }
-            while (alive > 0) {
-                for (size_t k = 0; k < mine.size(); ++k) {
-                    if (!live[k]) continue;
-                    const int i = mine[k];
-                    // with a single live solver left there is nothing to interleave with: block in the step
-                    const int r = s[i]->solver.solveStep(alive == 1);
-                    if (r == 1) continue;
-                    if (r < 0) { status[i] = -r; errors[i] = gne_last_error(); }
-                    else { status[i] = s[i]->solver.solveEnd(&iters[i], &finished[i]); if (status[i] != GNE_OK) errors[i] = gne_last_error(); }
-                    live[k] = 0; --alive;
+// blocks on the device while another of its solvers has host work to do.  With perLaunch > 0 the LV passes a thread has
+// prepared during one sweep over its solvers leave in launch groups (gne_lv_group: one grid for up to perLaunch
+// instances) instead of one launch each: the per-instance launch cost is what limits a batch of small instances.
+static int solve_batch_impl(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int perLaunch,
+                            int64_t *iters, int *finished, int64_t *groupLaunches)
+{
+    if (B <= 0 || !s || !iters || !finished || perLaunch < 0) { gne_set_error("gne_solver_solve_batch: bad argument"); return GNE_ERR_ARG; }
+    int T = threads > 0 ? threads : (int) std::thread::hardware_concurrency();
+    if (T <= 0) T = 1;
+    if (T > B) T = B;
+    std::vector<int> status((size_t) B, GNE_OK);
+    std::vector<std::string> errors((size_t) B);
+    std::vector<int64_t> launchesOf((size_t) T, 0);
+    auto work = [&](int w) {
+        std::vector<int> mine;
+        for (int i = w; i < B; i += T) mine.push_back(i);
+        std::vector<char> live(mine.size(), 1);
+        size_t alive = 0;
+        gne_lv_group *group = nullptr;
+        for (size_t k = 0; k < mine.size(); ++k) {
+            const int i = mine[k];
+            iters[i] = 0; finished[i] = 1;
+            status[i] = s[i]->solver.solveBegin(presolve != 0, maxPivots);
+            if (status[i] != GNE_OK) { errors[i] = gne_last_error(); live[k] = 0; } else ++alive;
+        }
+        // (the device handles exist once solveBegin has run: now the thread's launch group can be made on their device)
+        if (perLaunch > 0) {
+            for (size_t k = 0; k < mine.size() && !group; ++k) {
+                gne_dev *d0 = live[k] ? s[mine[k]]->solver.device() : nullptr;
+                if (d0 && gne_lv_group_create(&group, gne_dev_cuda_device(d0), perLaunch) != GNE_OK) {
+                    const std::string why = gne_last_error();
+                    for (size_t q = 0; q < mine.size(); ++q) if (live[q]) { status[mine[q]] = GNE_ERR_CUDA; errors[mine[q]] = why; live[q] = 0; }
+                    alive = 0; group = nullptr;
+                    break;
                 }
             }
-        };
-        std::vector<std::thread> pool;
-        for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
-        work(0);
-        for (size_t k = 0; k < pool.size(); ++k) pool[k].join();
-        for (int i = 0; i < B; ++i) if (status[i] != GNE_OK) { gne_set_error("solver %d of the batch: %s", i, errors[i].c_str()); return status[i]; }
-        return GNE_OK; });
+            for (size_t k = 0; k < mine.size(); ++k) s[mine[k]]->solver.lvGroup = group;
+        }
+        prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);   // (the default 50 us slack would stretch the short sleeps below)
+        bool groupFailed = false;
+        // GNE_BATCH_STATS=1: where this thread's time goes (stderr, once per thread at the end)
+        static const bool wantStats = getenv("GNE_BATCH_STATS") != nullptr;
+        auto nowNs = []() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (int64_t) t.tv_sec * 1000000000ll + t.tv_nsec; };
+        int64_t nsStep1 = 0, nsStep2 = 0, nsLaunch = 0, nsSleep = 0, nsIdleSweep = 0, nStep1 = 0, nStep2 = 0, nLaunch = 0, nSleep = 0, nIdle = 0;
+        const int64_t tStart = wantStats ? nowNs() : 0;
+        while (alive > 0) {
+            bool progressed = false;
+            const int64_t tSweep = wantStats ? nowNs() : 0;
+            for (size_t k = 0; k < mine.size(); ++k) {
+                if (!live[k]) continue;
+                const int i = mine[k];
+                // a solver whose result has arrived is taken through its pivot AND the preparation of its next pass
+                // (two steps) before the next solver is looked at; with a single live solver left there is nothing to
+                // interleave with: block in the step
+                const int64_t t0 = wantStats ? nowNs() : 0;
+                int r = s[i]->solver.solveStep(alive == 1);
+                if (r == 2) continue;
+                progressed = true;
+                const int64_t t1 = wantStats ? nowNs() : 0;
+                if (r == 1) r = s[i]->solver.solveStep(alive == 1);
+                if (wantStats) { const int64_t t2 = nowNs(); nsStep1 += t1 - t0; nsStep2 += t2 - t1; ++nStep1; ++nStep2; }
+                if (r == 1 || r == 2) continue;
+                if (r < 0) { status[i] = -r; errors[i] = gne_last_error(); }
+                else { status[i] = s[i]->solver.solveEnd(&iters[i], &finished[i]); if (status[i] != GNE_OK) errors[i] = gne_last_error(); }
+                live[k] = 0; --alive;
+            }
+            // whatever this sweep has parked goes out now
+            const int64_t tL = wantStats ? nowNs() : 0;
+            if (wantStats && !progressed) { nsIdleSweep += tL - tSweep; ++nIdle; }
+            if (group && gne_lv_group_pending(group) > 0) {
+                if (gne_lv_group_launch(group) != GNE_OK) { groupFailed = true; break; }
+                if (wantStats) { nsLaunch += nowNs() - tL; ++nLaunch; }
+            }
+            // every pass of this thread's solvers is still running: leave the core to the other threads for a moment
+            // (a thread that spins through its quantum is descheduled for milliseconds as soon as anything else
+            // wants a core, and its instances stall with it)
+            if (!progressed) {
+                const int64_t tS = wantStats ? nowNs() : 0;
+                struct timespec ts = { 0, 2000 }; nanosleep(&ts, nullptr);
+                if (wantStats) { nsSleep += nowNs() - tS; ++nSleep; }
+            }
+        }
+        if (wantStats) {
+            double sc = 0, sp = 0, so = 0;
+            for (size_t k = 0; k < mine.size(); ++k) { sc += s[mine[k]]->solver.secsComplete; sp += s[mine[k]]->solver.pivotSeconds(); so += s[mine[k]]->solver.potentialSeconds(); }
+            fprintf(stderr, "[batch thread %d] inside its solvers: complete %.3f ms, pivot %.3f ms, potentials %.3f ms\n", w, 1e3 * sc, 1e3 * sp, 1e3 * so);
+        }
+        if (wantStats)
+            fprintf(stderr, "[batch thread %d] %zu solvers, %.3f ms total | first steps (complete+pivot) %lld x %.2f us | second steps (prep+park) %lld x %.2f us | "
+                    "explicit launches %lld x %.2f us | idle sweeps %lld x %.2f us | sleeps %lld x %.2f us\n", w, mine.size(), 1e-6 * (nowNs() - tStart),
+                    (long long) nStep1, nStep1 ? 1e-3 * nsStep1 / nStep1 : 0.0, (long long) nStep2, nStep2 ? 1e-3 * nsStep2 / nStep2 : 0.0,
+                    (long long) nLaunch, nLaunch ? 1e-3 * nsLaunch / nLaunch : 0.0, (long long) nIdle, nIdle ? 1e-3 * nsIdleSweep / nIdle : 0.0,
+                    (long long) nSleep, nSleep ? 1e-3 * nsSleep / nSleep : 0.0);
+        if (groupFailed) {
+            const std::string why = gne_last_error();
+            for (size_t k = 0; k < mine.size(); ++k) if (live[k]) { status[mine[k]] = GNE_ERR_CUDA; errors[mine[k]] = why; }
+        }
+        for (size_t k = 0; k < mine.size(); ++k) s[mine[k]]->solver.lvGroup = nullptr;
+        if (group) { launchesOf[(size_t) w] = gne_lv_group_launch_count(group); gne_lv_group_destroy(group); }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (size_t k = 0; k < pool.size(); ++k) pool[k].join();
+    if (groupLaunches) { *groupLaunches = 0; for (int w = 0; w < T; ++w) *groupLaunches += launchesOf[(size_t) w]; }
+    for (int i = 0; i < B; ++i) if (status[i] != GNE_OK) { gne_set_error("solver %d of the batch: %s", i, errors[i].c_str()); return status[i]; }
+    return GNE_OK;
+}
+extern "C" int gne_solver_solve_batch(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int64_t *iters, int *finished) {
+    return guarded("gne_solver_solve_batch", [&]() -> int { return solve_batch_impl(s, B, presolve, maxPivots, threads, 0, iters, finished, nullptr); });
+}
+extern "C" int gne_solver_solve_batch_grouped(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int perLaunch,
+                                              int64_t *iters, int *finished, int64_t *groupLaunches) {
+    return guarded("gne_solver_solve_batch_grouped", [&]() -> int { return solve_batch_impl(s, B, presolve, maxPivots, threads, perLaunch, iters, finished, groupLaunches); });
 }
 extern "C" int gne_solver_set_comm_host(gne_solver *s, int rank, int nranks, gne_allgather_fn allgather, void *ctx) {
     return guarded("gne_solver_set_comm_host", [&]() -> int {

@@ -159,6 +159,7 @@ struct gne_dev {
     std::vector<cudaEvent_t> benchEv;              // per-step event pairs of gne_bench_price_lv
     bool exchangeFused = false;                    // the last streamed pass carried the shard exchange itself
     bool lvLaunched = false;                       // a pass started by gne_price_lv_launch awaits gne_price_lv_complete
+    cudaStream_t passStream = nullptr;             // the stream that pass runs on (the handle's own, or its launch group's)
     bool fastMath = false;                         // gne_dev_set_fast_math / GNE_FAST_MATH
     bool pdl = true;                               // programmatic dependent launch between a pivot's kernels (GNE_PDL=0 disables)
     unsigned long long lvSeq = 0;                  // sequence number of the last LV pass launched
@@ -379,6 +380,7 @@ extern "C" int gne_dev_set_fast_math(gne_dev *d, int on)
 extern "C" int gne_dev_set_lv_kernel(gne_dev *d, int mode) { if (mode < 0 || mode > 2) return GNE_ERR_ARG; d->lvKernelMode = mode; return GNE_OK; }
 extern "C" int gne_dev_last_lv_kernel(gne_dev *d) { return d->lastWasStream ? 2 : 1; }
 extern "C" int64_t gne_dev_launch_count(gne_dev *d) { return d->launches; }
+extern "C" int gne_dev_cuda_device(const gne_dev *d) { return d ? d->device : -1; }
 void gne_dev_traffic(gne_dev *d, int64_t *h2d, int64_t *d2h) { *h2d = d->h2dBytes; *d2h = d->d2hBytes; }
 
 // ------------------------------------------------------------------------------------------
@@ -806,55 +808,70 @@ static cudaError_t launch_k(gne_dev *d, bool dependent, void (*kernel)(KArgs...)
 // the bench helper's idempotent copy of the last one) and the queued set-mirror writes itself, prices, reduces in its
 // last CTA and, sharded over peer mailboxes, exchanges + merges there too (result block in d->lvRes either way).
 // Per-tile kernels: queued work is launched first, then tiles + finish (+ a stand-alone exchange by the caller).
+// Arguments of one streamed LV pass over this shard (consumes the queued argument-only update and set-mirror writes).
+static int fill_stream_pass(gne_dev *d, LvResult *target, bool withExchange, const SmallUpdate *replay, LvPass &P)
+{
+    SmallUpdate &su = P.u;
+    const bool fromPending = !replay && d->havePendingSmall;
+    if (replay) su = *replay;
+    else if (fromPending) su = d->pendingSmall;
+    else { su.ops.n = 0; su.nNodes = su.nTheta = su.nFinal = su.hasPi = 0; }
+    NbWriteOps &q = pending_of(d);
+    if (q.n > 0) {
+        // set-mirror writes queued after the update: fold them in (a later write to a position replaces the earlier one)
+        bool fits = true;
+        NbWriteOps merged = su.ops;
+        for (int k = 0; k < q.n && fits; ++k) {
+            int i = -1;
+            for (int j = 0; j < merged.n; ++j) if (merged.local[j] == q.local[k]) i = j;
+            if (i < 0) { if (merged.n == 8) { fits = false; break; } i = merged.n++; }
+            merged.local[i] = q.local[k]; merged.tail[i] = q.tail[k]; merged.head[i] = q.head[k];
+            merged.cost[i] = q.cost[k]; merged.mult[i] = q.mult[k]; merged.state[i] = q.state[k];
+        }
+        if (fits) { su.ops = merged; d->h2dBytes += 25 * q.n; q.n = 0; }
+        else {                                       // too many: launch everything queued, the pass carries nothing
+            int rc = flush_pending(d); if (rc) return rc;
+            if (!replay) { su.ops.n = 0; su.nNodes = su.nTheta = su.nFinal = 0; }
+        }
+    }
+    if (fromPending) d->havePendingSmall = false;
+    P.nb = view_of(d);
+    P.pi = d->pi;
+    P.out = d->lvc;
+    P.numTiles = P.nb.end > P.nb.lo ? (P.nb.end - P.nb.lo + ST_TILE - 1) / ST_TILE : 0;
+    LvFused &f = P.f;
+    memset(&f, 0, sizeof(f));
+    f.ticket = d->lvTicket; f.arrive = d->lvArrive; f.tileCtr = d->lvTileCtr; f.updFlag = d->lvUpdFlag;
+    f.res = target; f.seq = ++d->lvSeq; f.resOnHost = (target == d->lvRes) ? 1 : 0;
+    f.single = P.numTiles <= (int64_t) d->streamGrid ? 1 : 0;
+    f.nranks = 1;
+    if (withExchange && d->nranks > 1 && d->p2p) {
+        // sharded over peer mailboxes: the last CTA exchanges the shard's record, merges the ranks' records and
+        // publishes the merged block where the host polls
+        f.nranks = d->nranks; f.rank = d->rank; f.peers = (Mailbox *const *) d->peersDev;
+        f.hostOut = d->lvRes;
+        f.xseq = ++d->xseq; f.xTimeout = d->xTimeoutCycles;
+        d->exchangeFused = true;
+    }
+    NbMut &mm = P.nbMut; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
+    PotMut &pm = P.pm; pm.a0 = d->a0; pm.a1 = d->a1; pm.slot = d->slot; pm.theta = d->theta; pm.pi = d->pi;
+    P.grid = f.single ? (int) std::max<int64_t>(1, P.numTiles) : d->streamGrid;
+    return GNE_OK;
+}
+
 static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEvent_t evB, bool withExchange = true,
                           const SmallUpdate *replay = nullptr)
 {
     d->lastWasStream = use_stream_kernel(d);
     d->exchangeFused = false;
+    d->passStream = d->stream;
     if (d->lastWasStream) {
-        static thread_local SmallUpdate su;
-        const bool fromPending = !replay && d->havePendingSmall;
-        if (replay) su = *replay;
-        else if (fromPending) su = d->pendingSmall;
-        else { su.ops.n = 0; su.nNodes = su.nTheta = su.nFinal = su.hasPi = 0; }
-        NbWriteOps &q = pending_of(d);
-        if (q.n > 0) {
-            // set-mirror writes queued after the update: fold them in (a later write to a position replaces the earlier one)
-            bool fits = true;
-            NbWriteOps merged = su.ops;
-            for (int k = 0; k < q.n && fits; ++k) {
-                int i = -1;
-                for (int j = 0; j < merged.n; ++j) if (merged.local[j] == q.local[k]) i = j;
-                if (i < 0) { if (merged.n == 8) { fits = false; break; } i = merged.n++; }
-                merged.local[i] = q.local[k]; merged.tail[i] = q.tail[k]; merged.head[i] = q.head[k];
-                merged.cost[i] = q.cost[k]; merged.mult[i] = q.mult[k]; merged.state[i] = q.state[k];
-            }
-            if (fits) { su.ops = merged; d->h2dBytes += 25 * q.n; q.n = 0; }
-            else {                                       // too many: launch everything queued, the pass carries nothing
-                int rc = flush_pending(d); if (rc) return rc;
-                if (!replay) { su.ops.n = 0; su.nNodes = su.nTheta = su.nFinal = 0; }
-            }
-        }
-        if (fromPending) d->havePendingSmall = false;
-        NbView nb = view_of(d);
-        const int64_t numTiles = nb.end > nb.lo ? (nb.end - nb.lo + ST_TILE - 1) / ST_TILE : 0;
-        LvFused f;
-        memset(&f, 0, sizeof(f));
-        f.ticket = d->lvTicket; f.arrive = d->lvArrive; f.tileCtr = d->lvTileCtr; f.updFlag = d->lvUpdFlag;
-        f.res = target; f.seq = ++d->lvSeq; f.resOnHost = (target == d->lvRes) ? 1 : 0;
-        f.single = numTiles <= (int64_t) d->streamGrid ? 1 : 0;
-        f.nranks = 1;
-        if (withExchange && d->nranks > 1 && d->p2p) {
-            // sharded over peer mailboxes: the last CTA exchanges the shard's record, merges the ranks' records and
-            // publishes the merged block where the host polls
-            f.nranks = d->nranks; f.rank = d->rank; f.peers = (Mailbox *const *) d->peersDev;
-            f.hostOut = d->lvRes;
-            f.xseq = ++d->xseq; f.xTimeout = d->xTimeoutCycles;
-            d->exchangeFused = true;
-        }
-        NbMut mm; mm.tail = d->tail; mm.head = d->head; mm.cost = d->cost; mm.mult = d->mult; mm.state = d->state;
-        PotMut pm; pm.a0 = d->a0; pm.a1 = d->a1; pm.slot = d->slot; pm.theta = d->theta; pm.pi = d->pi;
-        const int grid = f.single ? (int) std::max<int64_t>(1, numTiles) : d->streamGrid;
+        static thread_local LvPass P;
+        int rcf = fill_stream_pass(d, target, withExchange, replay, P); if (rcf) return rcf;
+        LvFused &f = P.f;
+        const int grid = P.grid;
+        const int64_t numTiles = P.numTiles;
+        (void) numTiles;
 #ifdef GNE_STAMPS
         static long long *stampsDev = nullptr, *stampsHost = nullptr;
         static long passes = 0;
@@ -871,7 +888,7 @@ static int launch_lv_pass(gne_dev *d, LvResult *target, cudaEvent_t evA, cudaEve
         f.stamps = stampsDev;
 #endif
         if (evA) CK(cudaEventRecord(evA, d->stream));
-        st_kernel_for(d->stStages, d->stCtasPerSm)<<<grid, ST_BLOCK, st_smem_bytes(d->stStages), d->stream>>>(nb, (const double *) d->pi, d->lvc, numTiles, f, su, mm, pm);
+        st_kernel_for(d->stStages, d->stCtasPerSm)<<<grid, ST_BLOCK, st_smem_bytes(d->stStages), d->stream>>>(P.nb, P.pi, P.out, P.numTiles, f, P.u, P.nbMut, P.pm);
         CK(cudaGetLastError());
         ++d->launches;
         if (evB) CK(cudaEventRecord(evB, d->stream));
@@ -923,7 +940,7 @@ static int wait_host_seq(gne_dev *d, const volatile unsigned long long *seq, uns
             else sched_yield();
         }
         if ((spins & 0xfffff) == 0) {                    // now and then
-            cudaError_t q = cudaStreamQuery(d->stream);
+            cudaError_t q = cudaStreamQuery(d->passStream ? d->passStream : d->stream);
             if (q == cudaSuccess) { if (*seq == expect) break; gne_set_error("pricing pass finished without publishing its result"); return GNE_ERR_CUDA; }
             if (q != cudaErrorNotReady) { gne_set_error("pricing pass failed: %s", cudaGetErrorString(q)); return GNE_ERR_CUDA; }
         }
@@ -991,6 +1008,89 @@ extern "C" int gne_price_lv_ready(gne_dev *d)
     if (d->nranks > 1 && !d->p2p) return 1;              // (the all-gather path blocks in complete)
     const volatile LvResult *r = d->lvRes;
     return r->hSeqA == d->lvSeq && (r->hTagB >> 16) == (d->lvSeq & ((1ull << 48) - 1ull)) ? 1 : 0;
+}
+
+// ---- launch groups: the LV passes of several independent instances of one GPU in ONE launch (k_price_lv_batch) ----
+// A group belongs to one host thread.  gne_lv_group_add stands for gne_price_lv_launch: the handle's pass is prepared
+// (sequence number, folded relabel, counters) and parked in the group; gne_lv_group_launch sends everything parked as one
+// grid, each instance on its own share of the CTAs.  ready / complete then work per handle as after a launch of its own.
+struct gne_lv_group {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    int maxPending = LVB_MAX;
+    int64_t launches = 0, passes = 0;
+    LvBatch args;
+};
+
+extern "C" int gne_lv_group_create(gne_lv_group **out, int cudaDevice, int maxPending)
+{
+    if (!out) { gne_set_error("gne_lv_group_create: bad argument"); return GNE_ERR_ARG; }
+    const int cnt = gne_cuda_device_count();
+    if (cnt <= 0) { gne_set_error("no CUDA device: genneteq_b200 has no CPU fallback"); return GNE_ERR_CUDA; }
+    if (cudaDevice < 0 || cudaDevice >= cnt) { gne_set_error("cuda device %d out of range (%d present)", cudaDevice, cnt); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(cudaDevice));
+    gne_lv_group *g = new gne_lv_group();
+    g->device = cudaDevice;
+    g->maxPending = (maxPending <= 0 || maxPending > LVB_MAX) ? LVB_MAX : maxPending;
+    g->args.count = 0; g->args.ctasPer = 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_price_lv_batch<ST_STAGES, ST_CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem_bytes(ST_STAGES));
+    if (e != cudaSuccess) { gne_set_error("gne_lv_group_create: %s", cudaGetErrorString(e)); delete g; return GNE_ERR_CUDA; }
+    *out = g;
+    return GNE_OK;
+}
+
+extern "C" int gne_lv_group_launch(gne_lv_group *g)
+{
+    if (!g) return GNE_ERR_ARG;
+    if (g->args.count == 0) return GNE_OK;
+    CK(cudaSetDevice(g->device));
+    k_price_lv_batch<ST_STAGES, ST_CTAS_PER_SM><<<g->args.count * g->args.ctasPer, ST_BLOCK, st_smem_bytes(ST_STAGES), g->stream>>>(g->args);
+    g->args.count = 0; g->args.ctasPer = 0;
+    CK(cudaGetLastError());
+    ++g->launches;
+    return GNE_OK;
+}
+
+static int lv_group_add(gne_lv_group *g, gne_dev *d, const SmallUpdate *replay);
+extern "C" int gne_lv_group_add(gne_lv_group *g, gne_dev *d) { return lv_group_add(g, d, nullptr); }
+
+static int lv_group_add(gne_lv_group *g, gne_dev *d, const SmallUpdate *replay)
+{
+    if (!g || !d) return GNE_ERR_ARG;
+    if (d->lvLaunched) { gne_set_error("gne_lv_group_add: the handle's previous pass was not completed"); return GNE_ERR_ARG; }
+    // passes the batched kernel does not cover go out as launches of their own: sharded handles, the per-tile kernel
+    // (short lists, overflow hold-off), timed passes, tuning shapes, another device
+    if (d->device != g->device || d->nranks > 1 || d->timing || !use_stream_kernel(d) || d->stStages != ST_STAGES || d->stCtasPerSm != ST_CTAS_PER_SM)
+        return gne_price_lv_launch(d);
+    CK(cudaSetDevice(d->device));
+    d->lastWasStream = true;
+    d->exchangeFused = false;
+    LvPass &P = g->args.p[g->args.count];
+    int rc = fill_stream_pass(d, d->lvRes, false, replay, P); if (rc) return rc;
+    // work still queued on the handle's own stream (bulk uploads, a flushed update) precedes the pass
+    if (cudaStreamQuery(d->stream) == cudaErrorNotReady) { CK(cudaEventRecord(g->ev, d->stream)); CK(cudaStreamWaitEvent(g->stream, g->ev, 0)); }
+    d->passStream = g->stream;
+    d->lvLaunched = true;
+    ++d->launches; ++g->passes;
+    g->args.ctasPer = std::max(g->args.ctasPer, P.grid);
+    if (++g->args.count >= g->maxPending) return gne_lv_group_launch(g);
+    return GNE_OK;
+}
+
+extern "C" int gne_lv_group_pending(const gne_lv_group *g) { return g ? g->args.count : 0; }
+extern "C" int64_t gne_lv_group_launch_count(const gne_lv_group *g) { return g ? g->launches : 0; }
+
+extern "C" int gne_lv_group_destroy(gne_lv_group *g)
+{
+    if (!g) return GNE_OK;
+    cudaSetDevice(g->device);
+    if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
+    if (g->ev) cudaEventDestroy(g->ev);
+    delete g;
+    return GNE_OK;
 }
 
 extern "C" int gne_price_lv_begin(gne_dev *d, double *largestViolation, int64_t *count, int *any)
@@ -1477,6 +1577,58 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
 // The block rule's device leg: `reps` quickSelect passes as the solver issues them (window kernel + finish kernel per
 // window, the cursor advancing by what each pass scanned), each pass timed with CUDA events around its kernels.
 // arcsLaunched[i] = arcs the kernels of pass i were launched over (whole windows), arcsScanned[i] = what the rule consumed.
+// Device-resident leg of a batch (configs[3]): `reps` rounds of LV passes over the B handles (each replaying its last
+// argument-only relabel, idempotent), `perLaunch` instances per launch of the batched kernel, the launches spread
+// round-robin over `nStreams` launch groups so that one launch's tail overlaps the next one's start.  *msTotal: device
+// time of all rounds (events on the first stream, which waits for the others).
+extern "C" int gne_bench_lv_groups(gne_dev **devs, int B, int reps, int perLaunch, int nStreams, float *msTotal, int64_t *launches)
+{
+    if (!devs || B <= 0 || reps <= 0 || !msTotal) { gne_set_error("gne_bench_lv_groups: bad argument"); return GNE_ERR_ARG; }
+    nStreams = std::max(1, std::min(nStreams, 8));
+    std::vector<gne_lv_group *> gr((size_t) nStreams, nullptr);
+    int rc = GNE_OK;
+    for (int i = 0; i < B && rc == GNE_OK; ++i) rc = gne_dev_flush(devs[i]);
+    for (int k = 0; k < nStreams && rc == GNE_OK; ++k) rc = gne_lv_group_create(&gr[(size_t) k], devs[0]->device, perLaunch);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<cudaEvent_t> done((size_t) nStreams, nullptr);
+    auto body = [&]() -> int {
+        CK(cudaSetDevice(devs[0]->device));
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (int k = 0; k < nStreams; ++k) CK(cudaEventCreateWithFlags(&done[(size_t) k], cudaEventDisableTiming));
+        for (int i = 0; i < B; ++i) { CK(cudaStreamSynchronize(devs[i]->stream)); devs[i]->lvLaunched = false; }
+        const int per = gr[0]->maxPending;
+        for (int round = -1; round < reps; ++round) {              // round -1: warm-up, untimed
+            if (round == 0) {
+                CK(cudaDeviceSynchronize());
+                CK(cudaEventRecord(e0, gr[0]->stream));
+                for (int k = 1; k < nStreams; ++k) CK(cudaStreamWaitEvent(gr[(size_t) k]->stream, e0, 0));
+            }
+            int launchNo = 0;
+            for (int i0 = 0; i0 < B; i0 += per, ++launchNo) {
+                gne_lv_group *g = gr[(size_t) (launchNo % nStreams)];
+                for (int i = i0; i < std::min(B, i0 + per); ++i) {
+                    gne_dev *d = devs[i];
+                    d->lvLaunched = false;
+                    int r = lv_group_add(g, d, d->haveLastSmall ? &d->lastSmall : nullptr); if (r) return r;
+                }
+                int r = gne_lv_group_launch(g); if (r) return r;
+            }
+        }
+        for (int k = 1; k < nStreams; ++k) { CK(cudaEventRecord(done[(size_t) k], gr[(size_t) k]->stream)); CK(cudaStreamWaitEvent(gr[0]->stream, done[(size_t) k], 0)); }
+        CK(cudaEventRecord(e1, gr[0]->stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(msTotal, e0, e1));
+        for (int i = 0; i < B; ++i) devs[i]->lvLaunched = false;
+        if (launches) { *launches = 0; for (int k = 0; k < nStreams; ++k) *launches += gr[(size_t) k]->launches; }
+        return GNE_OK;
+    };
+    if (rc == GNE_OK) rc = body();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    for (int k = 0; k < nStreams; ++k) { if (done[(size_t) k]) cudaEventDestroy(done[(size_t) k]); gne_lv_group_destroy(gr[(size_t) k]); }
+    return rc;
+}
+
 extern "C" int gne_bench_price_qs(gne_dev *d, int reps, int flushL2, int64_t want, float *msStep, int64_t *arcsLaunched, int64_t *arcsScanned)
 {
     CK(cudaSetDevice(d->device));

@@ -1087,8 +1087,8 @@ void GenNetEq::checkFeasibility()                                 // :227-288
 //   solveStep    advances by one stage and never blocks on the device unless `block`: PREP (loop head: window / progress
 //                hooks, periodic flows, computePotentials, then either the LV pass is LAUNCHED or - any other rule - the
 //                entering variable is selected synchronously), WAIT (the launched pass: complete it when its result is
-//                there), then the pivot.  Returns 1 while there is more to do, 0 when the loop has ended, < 0 on error
-//                (the status is then in stepStatus);
+//                there), then the pivot.  Returns 1 while there is more to do (2: nothing could be done, the pass is still
+//                running), 0 when the loop has ended, -(gne_status) on error;
 //   solveEnd     everything after the loop.
 // solve() = solveBegin + blocking solveStep until 0 + solveEnd.
 int GenNetEq::solveBegin(bool usePresolve, int64_t maxPivots)
@@ -1136,7 +1136,8 @@ int GenNetEq::solveStep(bool block)
             // getVarWithLargestViolation, first half: the pass is on its way
             isOptimal = true;
             offendingVars.clear();
-            STEP_TRY(gne_price_lv_launch(dev));
+            // (a solver of a batch parks the pass in its thread's launch group: one launch for several instances)
+            STEP_TRY(lvGroup ? gne_lv_group_add(lvGroup, dev) : gne_price_lv_launch(dev));
             stStage = 1;
             if (!block) return 1;
         } else {
@@ -1145,8 +1146,11 @@ int GenNetEq::solveStep(bool block)
         }
     }
     if (stStage == 1) {
-        if (!block && !gne_price_lv_ready(dev)) return 1;
+        if (!block && !gne_price_lv_ready(dev)) return 2;       // still waiting: nothing was done
+        if (block && lvGroup) STEP_TRY(gne_lv_group_launch(lvGroup));     // (nothing may stay parked while this thread waits)
+        const double c0 = wallNow();
         STEP_TRY(completeLargestViolation(&eVar));
+        secsComplete += wallNow() - c0;
         stStage = 2;
     }
     // stage 2: the pivot

@@ -69,8 +69,12 @@ class GenNetEq {
     int solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished);   // genneteq.cpp:60-117
     // the same loop in pieces (gne_solver_solve_batch: one host thread interleaves several solvers)
     int solveBegin(bool usePresolve, int64_t maxPivots);
-    int solveStep(bool block);                          // 1: more to do, 0: loop ended, < 0: -(gne_status)
+    int solveStep(bool block);                          // 1: more to do (2: still waiting for the device), 0: loop ended, < 0: -(gne_status)
     int solveEnd(int64_t *iters, int *finished);
+    gne_lv_group *lvGroup = nullptr;                    // set by the batch driver: LV passes go out through this launch group
+    double secsComplete = 0.0;                          // step-wise loop: time inside completeLargestViolation (result already there or awaited)
+    double pivotSeconds() const { return secsPivot; }
+    double potentialSeconds() const { return secsPotentials; }
 
     int phaseIpivot = GNE_LVW, phaseIIpivot = GNE_LVW;               // main.cpp:72-73 defaults
 

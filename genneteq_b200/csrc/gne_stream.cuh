@@ -269,13 +269,13 @@ __device__ __forceinline__ void st_apply_update_warp(const SmallUpdate &u, const
     if (lane == 0) st_st_release(f.updFlag, f.seq);
 }
 
-template <int STAGES, int MINB>
-__global__ void __launch_bounds__(ST_BLOCK, MINB)
-k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __grid_constant__ LvCtas out, const int64_t numTiles,
-                  const __grid_constant__ LvFused f, const __grid_constant__ SmallUpdate u, const __grid_constant__ NbMut nbMut,
-                  const __grid_constant__ PotMut pm)
+// One CTA of a pass: CTA `blk` of the `grd` CTAs that price this list (a launch of its own: block index and grid size of
+// that launch; a batched launch: the instance's share of the grid).  All arguments live in kernel-parameter space.
+template <int STAGES>
+__device__ __forceinline__ void lv_stream_cta(const NbView &nb, const double *pi, const LvCtas &out, const int64_t numTiles,
+                                              const LvFused &f, const SmallUpdate &u, const NbMut &nbMut, const PotMut &pm,
+                                              const int blk, const int grd, unsigned char *smem)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);                 // [STAGES]
     uint64_t *empty = full + 4;                                  // [STAGES]
     volatile int64_t *sTile = reinterpret_cast<volatile int64_t *>(smem + 128);   // [STAGES] tile in each stage, -1: none left
@@ -297,9 +297,9 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
                 if (it >= STAGES) st_mbar_wait(&empty[s], (uint32_t) (((it / STAGES) - 1) & 1));
                 // the first STAGES tiles of a CTA are its own (no round trip to the counter before the first load is
                 // issued); from then on the next tile comes from the device-wide counter
-                const int64_t tile = f.single ? (it == 0 ? (int64_t) blockIdx.x : numTiles)
-                                   : (it < STAGES ? (int64_t) blockIdx.x + (int64_t) it * gridDim.x
-                                                  : (int64_t) STAGES * gridDim.x + (int64_t) atomicAdd(f.tileCtr, 1ull));
+                const int64_t tile = f.single ? (it == 0 ? (int64_t) blk : numTiles)
+                                   : (it < STAGES ? (int64_t) blk + (int64_t) it * grd
+                                                  : (int64_t) STAGES * grd + (int64_t) atomicAdd(f.tileCtr, 1ull));
                 if (tile >= numTiles) { sTile[s] = -1; st_mbar_arrive(&full[s]); break; }
                 sTile[s] = tile;
                 unsigned char *b = stage0 + (size_t) s * ST_STAGE_BYTES;
@@ -423,19 +423,19 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
     const int cnt = sCnt;
     if (cnt > 1) {                                      // rare: several candidates of this CTA within the band
         for (int i = t; i < min(cnt, ST_CAND); i += ST_THREADS) {
-            out.candPos[(int64_t) blockIdx.x * ST_CAND + i] = sPos[i];
-            out.candViol[(int64_t) blockIdx.x * ST_CAND + i] = sViol[i];
-            out.candSecond[(int64_t) blockIdx.x * ST_CAND + i] = sSecond[i];
+            out.candPos[(int64_t) blk * ST_CAND + i] = sPos[i];
+            out.candViol[(int64_t) blk * ST_CAND + i] = sViol[i];
+            out.candSecond[(int64_t) blk * ST_CAND + i] = sSecond[i];
         }
         __threadfence();
         st_sync_consumers();
     }
     if (t == 0) {
-        CtaRec *r = out.rec + blockIdx.x;
+        CtaRec *r = out.rec + blk;
         r->max = Mc > 0.0 ? Mc : -1.0; r->cnt = cnt; r->pad = 0;
         r->pos0 = sPos[0]; r->viol0 = sViol[0]; r->second0 = sSecond[0];       // meaningful when cnt == 1
         __threadfence();
-        sLast = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        sLast = (atomicAdd(f.ticket, 1u) == (unsigned int) grd - 1u) ? 1 : 0;
     }
     st_sync_consumers();
     if (!sLast) return;
@@ -445,10 +445,55 @@ k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __g
 #endif
     __threadfence();
     if (t == 0) { *f.ticket = 0u; *f.arrive = 0u; *f.tileCtr = 0ull; }
-    lv_reduce_records(out, (int) gridDim.x, f, stage0);
+    lv_reduce_records(out, grd, f, stage0);
 #ifdef GNE_STAMPS
     if (t == 0 && f.stamps) f.stamps[7] = st_globaltimer();              // last CTA done
 #endif
+}
+
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(ST_BLOCK, MINB)
+k_price_lv_stream(const __grid_constant__ NbView nb, const double *pi, const __grid_constant__ LvCtas out, const int64_t numTiles,
+                  const __grid_constant__ LvFused f, const __grid_constant__ SmallUpdate u, const __grid_constant__ NbMut nbMut,
+                  const __grid_constant__ PotMut pm)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    lv_stream_cta<STAGES>(nb, pi, out, numTiles, f, u, nbMut, pm, (int) blockIdx.x, (int) gridDim.x, smem);
+}
+
+// The passes of several INDEPENDENT instances in one launch (configs[3]: a batch of instances on one GPU).  The grid is
+// cut into equal shares of `ctasPer` CTAs; share i runs instance i's pass exactly as a launch of its own would (its own
+// counters, result block, folded relabel), with `grid` <= ctasPer CTAs taking part.  Everything - up to LVB_MAX complete
+// argument sets - travels as kernel parameters: one launch per group of instances instead of one per instance, and no
+// copy engine involved.
+struct LvPass {
+    NbView nb;
+    const double *pi;
+    LvCtas out;
+    int64_t numTiles;
+    LvFused f;
+    SmallUpdate u;
+    NbMut nbMut;
+    PotMut pm;
+    int grid;
+};
+constexpr int LVB_MAX = 8;
+struct LvBatch {
+    int count, ctasPer;
+    LvPass p[LVB_MAX];
+};
+static_assert(sizeof(LvBatch) <= 32764, "kernel parameters are limited to 32 764 bytes");
+
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(ST_BLOCK, MINB)
+k_price_lv_batch(const __grid_constant__ LvBatch B)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int inst = (int) blockIdx.x / B.ctasPer;
+    const int blk = (int) blockIdx.x - inst * B.ctasPer;
+    const LvPass &P = B.p[inst];
+    if (blk >= P.grid) return;
+    lv_stream_cta<STAGES>(P.nb, P.pi, P.out, P.numTiles, P.f, P.u, P.nbMut, P.pm, blk, P.grid, smem);
 }
 
 } // namespace gne

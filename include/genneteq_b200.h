@@ -117,6 +117,20 @@ int gne_price_lv_ready(gne_dev *d);
 int gne_price_lv_complete(gne_dev *d, double *largestViolation, int64_t *count, int *any);
 int gne_price_lv_at(gne_dev *d, int64_t index, int64_t *pos);
 
+/* Launch groups (configs[3], SURVEY 8e "batches: replicas, 32 instances per GPU"): the LV passes of several independent
+ * handles of ONE GPU go out as one grid, each instance on its own share of the CTAs, instead of one launch per instance.
+ * A group belongs to one host thread.  gne_lv_group_add(g, d) stands for gne_price_lv_launch(d): the pass is prepared and
+ * parked; gne_lv_group_launch sends everything parked (add launches by itself once `maxPending` passes - at most 8, 0 = 8 -
+ * are parked).  gne_price_lv_ready / _complete then work per handle as usual.  A pass the batched kernel does not cover
+ * (sharded handle, per-tile kernel, another device) is launched on its own by add.                                    */
+typedef struct gne_lv_group gne_lv_group;
+int gne_lv_group_create(gne_lv_group **out, int cudaDevice, int maxPending);
+int gne_lv_group_add(gne_lv_group *g, gne_dev *d);
+int gne_lv_group_launch(gne_lv_group *g);
+int gne_lv_group_pending(const gne_lv_group *g);
+int64_t gne_lv_group_launch_count(const gne_lv_group *g);
+int gne_lv_group_destroy(gne_lv_group *g);
+
 /* quickSelect's arc loop (gnePivotRules.cpp:742-756): scan from `cursor` (wrapping) until `want`
  * violators were seen or the list is exhausted; best = first strictly-largest |rc|.
  * *bestPos = -1 when there is no violator.  *newCursor is the cursor after the scan (the
@@ -168,6 +182,8 @@ int gne_dev_set_fast_math(gne_dev *d, int on);
 int gne_dev_last_lv_kernel(gne_dev *d);
 /* number of kernels this handle has launched since creation                                   */
 int64_t gne_dev_launch_count(gne_dev *d);
+/* the CUDA device the handle lives on                                                          */
+int gne_dev_cuda_device(const gne_dev *d);
 /* replay timing helper for bench.py: runs `reps` device steps on the resident state — the relabel
  * (withFinalize 0: none, 1: finalize of every node, 2: replay of the handle's last argument-only
  * update, i.e. what a pivot of the current window really launches; falls back to 1), the LV pricing
@@ -179,6 +195,11 @@ int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, floa
 /* the same for the block rule: `reps` quickSelect passes as gne_price_qs issues them (cursor advancing), each timed
  * with CUDA events around its kernels; arcsLaunched = arcs the kernels covered, arcsScanned = arcs the rule consumed */
 int gne_bench_price_qs(gne_dev *d, int reps, int flushL2, int64_t want, float *msStep, int64_t *arcsLaunched, int64_t *arcsScanned);
+
+/* the device leg of a batch: `reps` rounds of LV passes over the B handles (each replaying its last argument-only relabel),
+ * `perLaunch` instances per launch of the batched kernel, launches spread over `nStreams` launch groups; *msTotal = device
+ * time of all rounds, *launches (may be NULL) = launches of the batched kernel, warm-up round included           */
+int gne_bench_lv_groups(gne_dev **devs, int B, int reps, int perLaunch, int nStreams, float *msTotal, int64_t *launches);
 
 /* --- multi-GPU exchange (one process per GPU; NCCL over NVLink) --- */
 /* 128-byte opaque id made on rank 0 and broadcast by the caller (torch.distributed)           */
@@ -223,6 +244,10 @@ int gne_solver_solve(gne_solver *s, int presolve, int64_t maxPivots, int64_t *it
  * pricing pass runs on the device it does the host work (pivot, relabel) of another - so the host never oversubscribes
  * its cores and every instance stream stays busy.  iters / finished: arrays of B.                                  */
 int gne_solver_solve_batch(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int64_t *iters, int *finished);
+/* the same with the LV passes of a thread's solvers sent in launch groups of up to `perLaunch` instances (1..8; 0 = one
+ * launch per instance as above); *groupLaunches (may be NULL): launches of the batched kernel                      */
+int gne_solver_solve_batch_grouped(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int perLaunch,
+                                   int64_t *iters, int *finished, int64_t *groupLaunches);
 
 int gne_solver_num_nodes(const gne_solver *s);
 int64_t gne_solver_num_vars(const gne_solver *s);

@@ -1,0 +1,2 @@
+/* TEST INFRASTRUCTURE — see gsl_linalg.h in this directory. */
+#include "gsl_linalg.h"

@@ -487,6 +487,78 @@ def test_batch_driver_interleaves_without_changing_any_solve(gne):
             s.close()
 
 
+def test_batch_driver_with_launch_groups(gne):
+    """gne_solver_solve_batch_grouped: the LV passes of a thread's solvers leave as ONE launch of the batched kernel
+    (k_price_lv_batch, up to per_launch instances per grid).  Every instance must still produce exactly the pivots, flows
+    and objective it produces alone; rules that price synchronously (QS) pass through untouched."""
+    names = ["s_wide_s3", "s_lossy_s4", "s_pow2_s5", "s_near1_s6", "e_two_nodes_s13", "e_three_nodes_s14", "e_nosupply_s12"]
+    for rule, threads, per in (("LV", 1, 8), ("LV", 3, 2), ("LV", 2, 3), ("QS", 2, 4)):
+        loaded = [load_gold(nm) for nm in names]
+        solvers = [gne.Solver(i.n, i.tail, i.head, i.ub, i.cost, i.mult, i.supply, rule1=rule) for (_, i) in loaded]
+        st = {}
+        r1 = gne.solve_batch(solvers, True, threads=threads, per_launch=per, stats=st)
+        r2 = gne.solve_batch(solvers, False, threads=threads, per_launch=per)
+        if rule == "LV":
+            total = sum(a[0] for a in r1)
+            assert 0 < st["group_launches"] < total, (st, total)          # fewer launches than passes: they did travel together
+        for (z, inst), s, a, b in zip(loaded, solvers, r1, r2):
+            assert (a[0], b[0]) == tuple(int(v) for v in z[rule + "_p"])
+            e, l = s.trace
+            assert np.array_equal(e, z[rule + "_e"]) and np.array_equal(l, z[rule + "_l"])
+            assert s.objective == float(z[rule + "_objective"])
+            assert np.array_equal(s.flows(), z[rule + "_flows"])
+            assert np.array_equal(s.potentials(), z[rule + "_potentials"])
+            s.close()
+
+
+def test_lv_group_passes_equal_the_sequential_rule(gne):
+    """gne_lv_group: several handles' passes in one grid (lists of one tile, of a few tiles - one CTA each - and lists streamed
+    by a share of the CTAs, tie-heavy and near-tie data) give each handle the result of a launch of its own, pass after pass
+    (the counters re-arm), whether the group is sent explicitly or launches itself when full."""
+    import time
+    rng = np.random.default_rng(41)
+    shapes = [(50, 7, "cont", 0), (300, 2049, "ties", 0), (5000, 262144, "near", 9), (20000, 700_003, "cont", 37),
+              (1000, 10000, "near", 0), (20000, 1_000_003, "ties", 9), (3000, 40_000, "cont", 5)]
+    devs, exp = [], []
+    for n, N, mode, ctas in shapes:
+        tail, head, cost, mult, state, pi = random_soa(rng, n, N, mode)
+        d = gne.Device(n, N + 16)
+        d.nb_reset(tail, head, cost, mult, state)
+        d.pot_set_all(pi)
+        if ctas:
+            d.set_stream_ctas(ctas)
+        devs.append(d)
+        oL, olst, oany = oracle_lv(tail, head, cost, mult, state, pi)
+        exp.append((oL, len(olst), oany, olst))
+    for max_pending in (0, 3):
+        g = gne.LvGroup(0, max_pending)
+        for rep in range(3):
+            for d in devs:
+                g.add(d)
+            assert g.pending() <= len(devs)
+            g.launch()
+            assert g.pending() == 0
+            for d, (oL, ocount, oany, olst) in zip(devs, exp):
+                t0 = time.time()
+                while not gne.lib.gne_price_lv_ready(d.h):
+                    assert time.time() - t0 < 10.0
+                largest = C.c_double(0); count = C.c_int64(0); anyv = C.c_int(0)
+                gne._ck(gne.lib.gne_price_lv_complete(d.h, C.byref(largest), C.byref(count), C.byref(anyv)), "gne_price_lv_complete")
+                assert (largest.value, count.value, bool(anyv.value)) == (oL, ocount, oany)
+                if 0 < ocount <= 4096:
+                    pos = C.c_int64(0)
+                    for k in (0, ocount - 1):
+                        gne._ck(gne.lib.gne_price_lv_at(d.h, k, C.byref(pos)), "gne_price_lv_at")
+                        assert pos.value == olst[k]
+        # (handles whose tie-heavy lists keep overflowing are held off to the per-tile kernel and launch on their own)
+        assert 3 <= g.launch_count() <= (3 if max_pending == 0 else 9)
+        g.close()
+    # a handle on its own afterwards: the group left its counters armed
+    for d, (oL, ocount, oany, olst) in zip(devs, exp):
+        assert d.price_lv_begin() == (oL, ocount, oany)
+        d.close()
+
+
 def test_lv_pass_in_two_halves(gne):
     """gne_price_lv_launch / _ready / _complete: the same result as gne_price_lv_begin; ready turns 1 without blocking."""
     import time
