@@ -95,6 +95,11 @@ SIGNATURES = {
     "gne_comm_destroy": (C.c_int, [_vp]),
     "gne_comm_mode": (C.c_int, [_vp]),
     "gne_solver_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_double]),
+    "gne_solver_create_eqf": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, C.c_int,
+                                        _f64p, C.c_double]),
+    "gne_solver_num_sets": (C.c_int, [_vp]),
+    "gne_host_replay_eqf": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, C.c_int, _f64p, C.c_double, C.c_int, C.c_int,
+                                      C.c_int64, C.c_int64, _i32p, _i32p, _i64p, _f64p, _f64p, _f64p]),
     "gne_solver_create_from_col": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_char_p]),
     "gne_solver_destroy": (C.c_int, [_vp]),
     "gne_solver_set_rules": (C.c_int, [_vp, C.c_int, C.c_int]),
@@ -140,6 +145,9 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+
+(GNE_OK, GNE_ERR_CUDA, GNE_ERR_ARG, GNE_ERR_CAPACITY, GNE_ERR_TREE, GNE_ERR_CYCLING, GNE_ERR_UNSUPPORTED, GNE_ERR_COMM) = range(8)
 
 
 class GneError(RuntimeError):
@@ -415,10 +423,18 @@ class Solver:
                 "d2h_bytes", "launches", "pivots", "trees_s", "flows_s")
 
     def __init__(self, n=None, tail=None, head=None, ub=None, cost=None, mult=None, supply=None, big_m=-1.0,
-                 col_path=None, device=0, rule1="LVW", rule2=None, trace_cap=4_000_000):
+                 col_path=None, device=0, rule1="LVW", rule2=None, trace_cap=4_000_000, eqf=None, num_sets=0):
+        """eqf / num_sets: equal-flow sets (eqf[a] = 1-based set of arc a, 0: none) - gne_solver_create_eqf."""
         self.h = _vp()
         if col_path is not None:
             _ck(lib.gne_solver_create_from_col(C.byref(self.h), device, col_path.encode()), "gne_solver_create_from_col")
+        elif num_sets > 0:
+            tail = _arr(tail, np.int32); head = _arr(head, np.int32)
+            ub = _arr(ub, np.float64); cost = _arr(cost, np.float64); mult = _arr(mult, np.float64)
+            supply = _arr(supply, np.float64); eqf = _arr(eqf, np.int32)
+            _ck(lib.gne_solver_create_eqf(C.byref(self.h), device, n, len(tail), _p(tail, _i32p), _p(head, _i32p), _p(ub, _f64p),
+                                          _p(cost, _f64p), _p(mult, _f64p), _p(eqf, _i32p), num_sets, _p(supply, _f64p), big_m),
+                "gne_solver_create_eqf")
         else:
             tail = _arr(tail, np.int32); head = _arr(head, np.int32)
             ub = _arr(ub, np.float64); cost = _arr(cost, np.float64); mult = _arr(mult, np.float64)
@@ -427,6 +443,7 @@ class Solver:
                                       _p(cost, _f64p), _p(mult, _f64p), _p(supply, _f64p), big_m), "gne_solver_create")
         self.n = lib.gne_solver_num_nodes(self.h)
         self.M = lib.gne_solver_num_vars(self.h)
+        self.num_sets = lib.gne_solver_num_sets(self.h)          # > 0: the equal-flow engine runs this instance
         r1 = RULES[rule1] if isinstance(rule1, str) else rule1
         r2 = r1 if rule2 is None else (RULES[rule2] if isinstance(rule2, str) else rule2)
         lib.gne_solver_set_rules(self.h, r1, r2)
@@ -614,6 +631,21 @@ def host_replay(n, tail, head, ub, cost, mult, supply, big_m, draws, p1, e, l, s
     _ck(lib.gne_host_replay(n, len(tail), _p(tail, _i32p), _p(head, _i32p), _p(ub, _f64p), _p(cost, _f64p), _p(mult, _f64p),
                             _p(supply, _f64p), big_m, draws, 1 if sparse_flows else 0, p1, len(e), _p(e, _i32p), _p(l, _i32p),
                             C.byref(mm), _p(flows, _f64p), _p(pots, _f64p), C.byref(obj)), "gne_host_replay")
+    return mm.value, flows, pots, obj.value
+
+
+def host_replay_eqf(n, tail, head, ub, cost, mult, eqf, num_sets, supply, big_m, draws, p1, e, l, num_vars):
+    """The same for an instance with equal-flow sets (gne_host_replay_eqf); num_vars = arc variables + sets;
+    draws = drand48 calls per pricing, one number or (Phase I, Phase II)."""
+    d1, d2 = draws if isinstance(draws, tuple) else (draws, draws)
+    tail = _arr(tail, np.int32); head = _arr(head, np.int32); ub = _arr(ub, np.float64); cost = _arr(cost, np.float64)
+    mult = _arr(mult, np.float64); supply = _arr(supply, np.float64); e = _arr(e, np.int32); l = _arr(l, np.int32)
+    eqf = _arr(eqf, np.int32)
+    mm = C.c_int64(0); obj = C.c_double(0)
+    flows = np.empty(num_vars); pots = np.empty(n)
+    _ck(lib.gne_host_replay_eqf(n, len(tail), _p(tail, _i32p), _p(head, _i32p), _p(ub, _f64p), _p(cost, _f64p), _p(mult, _f64p),
+                                _p(eqf, _i32p), num_sets, _p(supply, _f64p), big_m, d1, d2, p1, len(e), _p(e, _i32p), _p(l, _i32p),
+                                C.byref(mm), _p(flows, _f64p), _p(pots, _f64p), C.byref(obj)), "gne_host_replay_eqf")
     return mm.value, flows, pots, obj.value
 
 

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <string>
 #include <thread>
@@ -35,7 +36,7 @@ int Graph::initializeFromArrays(int n, int64_t m, const int32_t *t, const int32_
 {
     if (n <= 0 || m < 0) { gne_set_error("Graph: bad sizes"); return GNE_ERR_ARG; }
     numNodes = n; numEqualFlowSets = 0;
-    tail.clear(); head.clear(); cap.clear(); cost.clear(); mult.clear();
+    tail.clear(); head.clear(); cap.clear(); cost.clear(); mult.clear(); eqfOf.clear(); eqfNodeVals.clear();
     double maxCost = 0.0, maxCap = 0.0;                 // graph.cpp:36-37, 412-417
     for (int64_t a = 0; a < m; ++a) {
         if (t[a] < 0 || t[a] >= n || h[a] < 0 || h[a] >= n) { gne_set_error("Graph: arc %lld has a node out of range", (long long) a); return GNE_ERR_ARG; }
@@ -54,6 +55,49 @@ int Graph::initializeFromArrays(int n, int64_t m, const int32_t *t, const int32_
     return GNE_OK;
 }
 
+int Graph::initializeFromArraysEqf(int n, int64_t m, const int32_t *t, const int32_t *h, const double *ub, const double *c,
+                                   const double *mu, const int32_t *eqf, int numSets, const double *sup, double bigMIn)
+{
+    if (numSets < 0 || (numSets > 0 && !eqf)) { gne_set_error("Graph: bad equal-flow arguments"); return GNE_ERR_ARG; }
+    if (numSets > 0 && (double) numSets * (double) n > 4.0e9) { gne_set_error("Graph: %d sets x %d nodes is beyond the dense rows this path keeps", numSets, n); return GNE_ERR_ARG; }
+    int rc = initializeFromArrays(n, m, t, h, ub, c, mu, sup, bigMIn);
+    if (rc) return rc;
+    numEqualFlowSets = numSets;
+    eqfOf.clear(); eqfNodeVals.assign((size_t) numSets * (size_t) n, 0.0);
+    for (int64_t a = 0; a < m; ++a) {
+        const int r = numSets > 0 ? eqf[a] - 1 : -1;    // EQF_IND_OFFSET, graph.h:18
+        if (r >= numSets) { gne_set_error("Graph: arc %lld names equal-flow set %d of %d", (long long) a, r + 1, numSets); return GNE_ERR_ARG; }
+        if (r >= 0) {                                   // graph.cpp:403-410, in the order the arcs are given
+            eqfNodeVals[(size_t) r * n + t[a]] += 1.0;
+            eqfNodeVals[(size_t) r * n + h[a]] += -1.0 * mu[a];
+        }
+        if (ub[a] <= 0.0) continue;
+        eqfOf.push_back(r < 0 ? -1 : r);
+    }
+    return GNE_OK;
+}
+
+void Graph::toEqfInstance(EqfInstance &out) const
+{
+    out.n = numNodes; out.p = numEqualFlowSets; out.bigM = bigM;
+    out.tail.clear(); out.head.clear(); out.cap.clear(); out.cost.clear(); out.mult.clear();
+    out.supply = supplies;
+    out.numOrigArcs.assign((size_t) numEqualFlowSets, 0);
+    out.setUB.assign((size_t) numEqualFlowSets, std::numeric_limits<double>::max());       // gneInit.cpp:69
+    out.setCost.assign((size_t) numEqualFlowSets, 0.0);
+    for (size_t a = 0; a < tail.size(); ++a) {          // (tail, head) order, arcs with capacity > 0 only: gneInit.cpp:82-105
+        const int r = eqfOf.empty() ? -1 : eqfOf[a];
+        if (r < 0) {
+            out.tail.push_back(tail[a]); out.head.push_back(head[a]); out.cap.push_back(cap[a]); out.cost.push_back(cost[a]); out.mult.push_back(mult[a]);
+        } else {
+            out.setCost[(size_t) r] += cost[a];
+            out.numOrigArcs[(size_t) r] += 1;
+            if (out.setUB[(size_t) r] > cap[a]) out.setUB[(size_t) r] = cap[a];
+        }
+    }
+    out.nodeVals = eqfNodeVals;
+}
+
 int Graph::initialize(Config *conf)
 {
     FILE *f = fopen(conf->inFile, "r");
@@ -62,7 +106,8 @@ int Graph::initialize(Config *conf)
     long arcsRead = 0;
     bool haveP = false;
     double maxCost = 0.0, maxCap = 0.0;
-    struct Rec { double ub, cost, mult; };
+    struct Rec { double ub, cost, mult; int eq; };
+    std::vector<double> nodeVals;                       // d_r(i), increments in FILE order (graph.cpp:403-410)
     std::map<std::pair<int32_t, int32_t>, Rec> arcs;    // a later line overwrites (dense matrices do, graph.cpp:406-410)
     std::vector<double> sup;
     char *line = nullptr;
@@ -73,9 +118,10 @@ int Graph::initialize(Config *conf)
         if (line[0] == 'p') {                           // processProblemLine, graph.cpp:358-372
             char tmp[64];
             if (sscanf(line, "p %63s %d %d %d", tmp, &n, &numArcs, &numEq) != 4) { gne_set_error("Improperly formatted problem line"); rc = GNE_ERR_ARG; break; }
-            if (numEq != 0) { gne_set_error("equal-flow sets are out of scope"); rc = GNE_ERR_UNSUPPORTED; break; }
-            if (n <= 0 || numArcs < 0 || n > (1 << 30)) { gne_set_error("problem line: bad sizes (n = %d, arcs = %d)", n, numArcs); rc = GNE_ERR_ARG; break; }
+            if (n <= 0 || numArcs < 0 || n > (1 << 30) || numEq < 0) { gne_set_error("problem line: bad sizes (n = %d, arcs = %d, sets = %d)", n, numArcs, numEq); rc = GNE_ERR_ARG; break; }
+            if ((double) numEq * (double) n > 4.0e9) { gne_set_error("problem line: %d sets x %d nodes is beyond the dense rows this path keeps", numEq, n); rc = GNE_ERR_ARG; break; }
             sup.assign(n, 0.0);
+            nodeVals.assign((size_t) numEq * (size_t) n, 0.0);
             haveP = true;
         } else if (line[0] == 'a' || line[0] == 'e') {  // processArcLine, graph.cpp:382-419 ('e' lines fail its sscanf)
             int n1, n2, eq;
@@ -85,8 +131,13 @@ int Graph::initialize(Config *conf)
                 gne_set_error("Improperly formatted arc line"); rc = GNE_ERR_ARG; break;
             }
             if (!haveP || n1 < 1 || n1 > n || n2 < 1 || n2 > n) { gne_set_error("arc line names a node out of range"); rc = GNE_ERR_ARG; break; }
-            if (eq - 1 >= 0) { gne_set_error("equal-flow sets are out of scope"); rc = GNE_ERR_UNSUPPORTED; break; }
+            if (eq - 1 >= numEq) { gne_set_error("arc line names equal-flow set %d of %d", eq, numEq); rc = GNE_ERR_ARG; break; }
             Rec r; r.ub = ub; r.cost = c; r.mult = mu;  // the lower bound is parsed and dropped (graph.cpp:386-410)
+            r.eq = eq - 1 >= 0 ? eq - 1 : -1;           // EQF_IND_OFFSET
+            if (r.eq >= 0) {
+                nodeVals[(size_t) r.eq * n + (n1 - 1)] += 1.0;
+                nodeVals[(size_t) r.eq * n + (n2 - 1)] += -1.0 * mu;
+            }
             arcs[std::make_pair((int32_t) (n1 - 1), (int32_t) (n2 - 1))] = r;
             if (maxCost < c) maxCost = c;
             if (maxCap < ub) maxCap = ub;
@@ -103,13 +154,15 @@ int Graph::initialize(Config *conf)
     if (rc) return rc;
     if (!haveP) { gne_set_error("no problem line"); return GNE_ERR_ARG; }
     if (arcsRead != numArcs) { gne_set_error("Number of arcs specified does not match the number of arcs in the file"); return GNE_ERR_ARG; }
-    numNodes = n; numEqualFlowSets = 0;
-    tail.clear(); head.clear(); cap.clear(); cost.clear(); mult.clear();
+    numNodes = n; numEqualFlowSets = numEq;
+    tail.clear(); head.clear(); cap.clear(); cost.clear(); mult.clear(); eqfOf.clear();
     for (std::map<std::pair<int32_t, int32_t>, Rec>::const_iterator it = arcs.begin(); it != arcs.end(); ++it) {
         if (it->second.ub <= 0.0) continue;
         tail.push_back(it->first.first); head.push_back(it->first.second);
         cap.push_back(it->second.ub); cost.push_back(it->second.cost); mult.push_back(it->second.mult);
+        eqfOf.push_back(it->second.eq);
     }
+    eqfNodeVals.swap(nodeVals);
     supplies = sup;
     bigM = numArcs * maxCost * maxCap;                  // graph.cpp:43
     return GNE_OK;
@@ -214,7 +267,27 @@ extern "C" int gne_read_col(const char *path, int *n, int64_t *m, int32_t *tail,
 // ------------------------------------------------------------------------------------------
 struct gne_solver {
     GenNetEq solver;
+    EqfSolver *eq = nullptr;                            // instances with equal-flow sets run in this engine instead (gne_eqf.h)
+    ~gne_solver() { delete eq; }
 };
+#define NO_EQF(s, what) do { if ((s)->eq) { gne_set_error(what ": not available for instances with equal-flow sets"); return GNE_ERR_UNSUPPORTED; } } while (0)
+
+static int make_solver(gne_solver **out, Graph &g, int initType, int cudaDevice)
+{
+    gne_solver *s = new gne_solver();
+    int rc;
+    if (g.getNumEqualFlowSets() > 0) {
+        EqfInstance inst;
+        g.toEqfInstance(inst);
+        s->eq = new EqfSolver();
+        rc = s->eq->initialize(inst, cudaDevice);
+    } else {
+        rc = s->solver.initialize(&g, initType, cudaDevice);
+    }
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return GNE_OK;
+}
 
 extern "C" int gne_solver_create(gne_solver **out, int cudaDevice, int n, int64_t m, const int32_t *tail, const int32_t *head,
                                  const double *ub, const double *cost, const double *mult, const double *supply, double bigM)
@@ -225,11 +298,21 @@ extern "C" int gne_solver_create(gne_solver **out, int cudaDevice, int n, int64_
     Graph g;
     int rc = g.initializeFromArrays(n, m, tail, head, ub, cost, mult, supply, bigM);
     if (rc) return rc;
-    gne_solver *s = new gne_solver();
-    rc = s->solver.initialize(&g, 0, cudaDevice);
-    if (rc) { delete s; return rc; }
-    *out = s;
-    return GNE_OK;
+    return make_solver(out, g, 0, cudaDevice);
+    });
+}
+
+extern "C" int gne_solver_create_eqf(gne_solver **out, int cudaDevice, int n, int64_t m, const int32_t *tail, const int32_t *head,
+                                     const double *ub, const double *cost, const double *mult, const int32_t *eqf, int numSets,
+                                     const double *supply, double bigM)
+{
+    return guarded("gne_solver_create_eqf", [&]() -> int {
+    if (!out) return GNE_ERR_ARG;
+    if (gne_cuda_device_count() <= 0) { gne_set_error("no CUDA device: genneteq_b200 has no CPU fallback"); return GNE_ERR_CUDA; }
+    Graph g;
+    int rc = g.initializeFromArraysEqf(n, m, tail, head, ub, cost, mult, eqf, numSets, supply, bigM);
+    if (rc) return rc;
+    return make_solver(out, g, 0, cudaDevice);
     });
 }
 
@@ -243,11 +326,7 @@ extern "C" int gne_solver_create_from_col(gne_solver **out, int cudaDevice, cons
     Graph g;
     int rc = g.initialize(&conf);
     if (rc) return rc;
-    gne_solver *s = new gne_solver();
-    rc = s->solver.initialize(&g, conf.initType, cudaDevice);
-    if (rc) { delete s; return rc; }
-    *out = s;
-    return GNE_OK;
+    return make_solver(out, g, conf.initType, cudaDevice);
     });
 }
 
@@ -259,7 +338,11 @@ extern "C" int gne_shard_range(int64_t m, int rank, int nranks, int64_t *lo, int
 }
 
 extern "C" int gne_solver_destroy(gne_solver *s) { delete s; return GNE_OK; }
-extern "C" int gne_solver_set_rules(gne_solver *s, int p1, int p2) { s->solver.phaseIpivot = p1; s->solver.phaseIIpivot = p2; return GNE_OK; }
+extern "C" int gne_solver_set_rules(gne_solver *s, int p1, int p2)
+{
+    if (s->eq) { s->eq->phaseIpivot = p1; s->eq->phaseIIpivot = p2; return GNE_OK; }
+    s->solver.phaseIpivot = p1; s->solver.phaseIIpivot = p2; return GNE_OK;
+}
 // One host thread per group of solvers; a thread keeps stepping the solvers of its group round-robin and never
 // blocks on the device while another of its solvers has host work to do.  With perLaunch > 0 the LV passes a thread has
 // prepared during one sweep over its solvers leave in launch groups (gne_lv_group: one grid for up to perLaunch
@@ -268,6 +351,7 @@ static int solve_batch_impl(gne_solver **s, int B, int presolve, int64_t maxPivo
                             int64_t *iters, int *finished, int64_t *groupLaunches)
 {
     if (B <= 0 || !s || !iters || !finished || perLaunch < 0) { gne_set_error("gne_solver_solve_batch: bad argument"); return GNE_ERR_ARG; }
+    for (int i = 0; i < B; ++i) NO_EQF(s[i], "gne_solver_solve_batch");
     int T = threads > 0 ? threads : (int) std::thread::hardware_concurrency();
     if (T <= 0) T = 1;
     if (T > B) T = B;
@@ -379,52 +463,61 @@ extern "C" int gne_solver_solve_batch_grouped(gne_solver **s, int B, int presolv
 extern "C" int gne_solver_set_comm_host(gne_solver *s, int rank, int nranks, gne_allgather_fn allgather, void *ctx) {
     return guarded("gne_solver_set_comm_host", [&]() -> int {
         if (!allgather) { gne_set_error("gne_solver_set_comm_host: no all-gather callback"); return GNE_ERR_ARG; }
+        NO_EQF(s, "gne_solver_set_comm_host");
         uint8_t none[128] = { 0 };
         return s->solver.setComm(none, rank, nranks, allgather, ctx); });
 }
 extern "C" int gne_solver_set_comm(gne_solver *s, const uint8_t id[128], int rank, int nranks) {
-    return guarded("gne_solver_set_comm", [&]() -> int { return s->solver.setComm(id, rank, nranks);     });
+    return guarded("gne_solver_set_comm", [&]() -> int { NO_EQF(s, "gne_solver_set_comm"); return s->solver.setComm(id, rank, nranks);     });
 }
-extern "C" int gne_solver_set_trace(gne_solver *s, int32_t *e, int32_t *l, int64_t cap) { s->solver.setTrace(e, l, cap); return GNE_OK; }
-extern "C" int64_t gne_solver_trace_len(const gne_solver *s) { return s->solver.getTraceLen(); }
+extern "C" int gne_solver_set_trace(gne_solver *s, int32_t *e, int32_t *l, int64_t cap)
+{
+    if (s->eq) s->eq->setTrace(e, l, cap); else s->solver.setTrace(e, l, cap);
+    return GNE_OK;
+}
+extern "C" int64_t gne_solver_trace_len(const gne_solver *s) { return s->eq ? s->eq->getTraceLen() : s->solver.getTraceLen(); }
 extern "C" int gne_solver_solve(gne_solver *s, int presolve, int64_t maxPivots, int64_t *iters, int *finished)
 {
     return guarded("gne_solver_solve", [&]() -> int {
     int64_t it = 0;
     int fin = 0;
-    int rc = s->solver.solve(presolve != 0, maxPivots, &it, &fin);
+    int rc = s->eq ? s->eq->solve(presolve != 0, maxPivots, &it, &fin) : s->solver.solve(presolve != 0, maxPivots, &it, &fin);
     if (iters) *iters = it;
     if (finished) *finished = fin;
     return rc;
     });
 }
-extern "C" int gne_solver_num_nodes(const gne_solver *s) { return s->solver.getNumNodes(); }
-extern "C" int64_t gne_solver_num_vars(const gne_solver *s) { return s->solver.getNumVars(); }
-extern "C" double gne_solver_objective(const gne_solver *s) { return s->solver.getFlowCost(); }
-extern "C" int gne_solver_feasible(const gne_solver *s) { return s->solver.getIsInfeasible() ? 0 : 1; }
-extern "C" int gne_solver_get_flows(gne_solver *s, double *out) { s->solver.getFlows(out); return GNE_OK; }
+extern "C" int gne_solver_num_nodes(const gne_solver *s) { return s->eq ? s->eq->getNumNodes() : s->solver.getNumNodes(); }
+extern "C" int64_t gne_solver_num_vars(const gne_solver *s) { return s->eq ? s->eq->getNumVars() : s->solver.getNumVars(); }
+extern "C" int gne_solver_num_sets(const gne_solver *s) { return s->eq ? s->eq->getNumSets() : 0; }
+extern "C" double gne_solver_objective(const gne_solver *s) { return s->eq ? s->eq->getFlowCost() : s->solver.getFlowCost(); }
+extern "C" int gne_solver_feasible(const gne_solver *s) { return (s->eq ? s->eq->getIsInfeasible() : s->solver.getIsInfeasible()) ? 0 : 1; }
+extern "C" int gne_solver_get_flows(gne_solver *s, double *out) { if (s->eq) s->eq->getFlows(out); else s->solver.getFlows(out); return GNE_OK; }
 extern "C" int gne_solver_get_potentials(gne_solver *s, double *out) {
+    if (s->eq) { s->eq->getPotentials(out); return GNE_OK; }
     return guarded("gne_solver_get_potentials", [&]() -> int { return s->solver.getPotentials(out);     });
 }
 extern "C" int gne_solver_compute_potentials(gne_solver *s)
 {
+    NO_EQF(s, "gne_solver_compute_potentials");
     int rc = s->solver.refreshPotentials();
     if (rc) return rc;
     return gne_dev_sync(s->solver.device());
 }
-extern "C" int gne_solver_get_states(gne_solver *s, int32_t *out) { s->solver.getStates(out); return GNE_OK; }
+extern "C" int gne_solver_get_states(gne_solver *s, int32_t *out) { if (s->eq) s->eq->getStates(out); else s->solver.getStates(out); return GNE_OK; }
 extern "C" int gne_solver_get_forest(gne_solver *s, int32_t *tree, int32_t *pred, int32_t *predArc, int32_t *depth, int32_t *thread)
 {
+    NO_EQF(s, "gne_solver_get_forest");
     Forest &f = s->solver.getForestMutable();
     const int n = s->solver.getNumNodes();
     for (int sl = 0; sl < f.numSlots(); ++sl) f.ensureThreads(sl);
     for (int i = 0; i < n; ++i) { tree[i] = f.node[i].slot; pred[i] = f.node[i].pred; predArc[i] = f.node[i].predArc; depth[i] = f.node[i].depth; thread[i] = f.node[i].thread; }
     return GNE_OK;
 }
-extern "C" int gne_solver_get_counters(const gne_solver *s, double *out12) { s->solver.getCounters(out12); return GNE_OK; }
-extern "C" gne_dev *gne_solver_device(gne_solver *s) { return s->solver.device(); }
-extern "C" int gne_solver_set_window(gne_solver *s, int64_t startPivot, int64_t numPivots) { s->solver.setWindow(startPivot, numPivots); return GNE_OK; }
-extern "C" int gne_solver_set_progress(gne_solver *s, int64_t every, double *buf, int64_t capRows) { s->solver.setProgress(every, buf, capRows); return GNE_OK; }
+extern "C" int gne_solver_get_counters(const gne_solver *s, double *out12) { if (s->eq) s->eq->getCounters(out12); else s->solver.getCounters(out12); return GNE_OK; }
+extern "C" gne_dev *gne_solver_device(gne_solver *s) { return s->eq ? s->eq->device() : s->solver.device(); }
+extern "C" int gne_solver_set_window(gne_solver *s, int64_t startPivot, int64_t numPivots) { NO_EQF(s, "gne_solver_set_window"); s->solver.setWindow(startPivot, numPivots); return GNE_OK; }
+extern "C" int gne_solver_set_progress(gne_solver *s, int64_t every, double *buf, int64_t capRows) { NO_EQF(s, "gne_solver_set_progress"); s->solver.setProgress(every, buf, capRows); return GNE_OK; }
 extern "C" int64_t gne_solver_progress_rows(const gne_solver *s) { return s->solver.getProgressRows(); }
 extern "C" int gne_solver_get_window(const gne_solver *s, double *out27) { s->solver.getWindow(out27); return GNE_OK; }
 
@@ -480,6 +573,30 @@ extern "C" int gne_host_replay(int n, int64_t m, const int32_t *tail, const int3
     if (rc) return rc;
     if (flowsOut) s.getFlows(flowsOut);
     if (potentialsOut) s.getHostPotentials(potentialsOut);
+    if (objective) *objective = s.getFlowCost();
+    return GNE_OK;
+    });
+}
+
+extern "C" int gne_host_replay_eqf(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub, const double *cost,
+                                   const double *mult, const int32_t *eqf, int numSets, const double *supply, double bigM,
+                                   int drawsPhaseI, int drawsPhaseII, int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
+                                   int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective)
+{
+    return guarded("gne_host_replay_eqf", [&]() -> int {
+    Graph g;
+    int rc = g.initializeFromArraysEqf(n, m, tail, head, ub, cost, mult, eqf, numSets, supply, bigM);
+    if (rc) return rc;
+    if (numSets <= 0) { gne_set_error("gne_host_replay_eqf: no equal-flow sets (use gne_host_replay)"); return GNE_ERR_ARG; }
+    EqfInstance inst;
+    g.toEqfInstance(inst);
+    EqfSolver s;
+    rc = s.initialize(inst, 0, true);
+    if (rc) return rc;
+    rc = s.replayTrace(drawsPhaseI, drawsPhaseII, phase1Pivots, totalPivots, e, l, mismatch);
+    if (rc) return rc;
+    if (flowsOut) s.getFlows(flowsOut);
+    if (potentialsOut) s.getPotentials(potentialsOut);
     if (objective) *objective = s.getFlowCost();
     return GNE_OK;
     });

@@ -1,0 +1,1317 @@
+// genneteq_b200 — solver for instances with equal-flow sets (see gne_eqf.h).  All `file:line` citations are into the
+// reference.  Host arithmetic is compiled -ffp-contract=off: every a*b+c below rounds twice, as the reference's does.
+#include "gne_eqf.h"
+#include "gne_internal.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <stack>
+#include <time.h>
+
+namespace gneb200 {
+
+static const double TOL = GNE_ROUNDOFF_TOLERANCE;                  // main.h:36-43
+#define GNE_TRY(call) do { int rc_ = (call); if (rc_ != GNE_OK) return rc_; } while (0)
+
+static double wallNow()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1.0e-9 * (double) ts.tv_nsec;
+}
+
+double EqfSolver::drand48()                                        // glibc, never seeded by the reference: X0 = 0
+{
+    rand48State = (0x5DEECE66DULL * rand48State + 0xBULL) & ((1ULL << 48) - 1ULL);
+    return ldexp((double) rand48State, -48);
+}
+
+EqfSolver::~EqfSolver()
+{
+    for (size_t i = 0; i < setBtI.size(); ++i) delete setBtI[i];
+    for (size_t i = 0; i < setBtII.size(); ++i) delete setBtII[i];
+    if (dev) gne_dev_destroy(dev);
+}
+
+void EqfSolver::getCounters(double *out12) const
+{
+    int64_t h2d = 0, d2h = 0;
+    if (dev) gne_dev_traffic(dev, &h2d, &d2h);
+    out12[0] = secsPricing; out12[1] = secsPotentials; out12[2] = secsPivot; out12[3] = secsTotal;
+    out12[4] = arcsPriced; out12[5] = 0.0; out12[6] = (double) h2d; out12[7] = (double) d2h;
+    out12[8] = dev ? (double) gne_dev_launch_count(dev) : 0.0; out12[9] = (double) pivots;
+    out12[10] = (double) pivotsTII; out12[11] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// gneInit.cpp:25-186 (initialType is forced to SELFLOOPS there, :31)
+// ------------------------------------------------------------------------------------------
+int EqfSolver::initialize(const EqfInstance &g, int cudaDev, bool hostOnlyReplay)
+{
+    hostOnly = hostOnlyReplay;
+    if (g.n <= 0 || g.p <= 0) { gne_set_error("EqfSolver: needs nodes and at least one equal-flow set"); return GNE_ERR_ARG; }
+    cudaDevice = cudaDev;
+    numNodes = g.n; numSets = g.p; bigM = g.bigM;
+    const int64_t m = (int64_t) g.tail.size();
+    A = m + numNodes;
+    V = A + numSets;
+    tail.assign((size_t) A, 0); head.assign((size_t) A, 0); mult.assign((size_t) A, 0.0);
+    UB.assign((size_t) V, 0.0); actualCost.assign((size_t) V, 0.0); isArtificial.assign((size_t) V, 0);
+    for (int64_t a = 0; a < m; ++a) {                   // :82-95
+        tail[a] = g.tail[a]; head[a] = g.head[a]; UB[a] = g.cap[a]; actualCost[a] = g.cost[a]; mult[a] = g.mult[a];
+    }
+    supply = g.supply;
+    for (int i = 0; i < numNodes; ++i) {                // :110-127 artificial self-loops
+        const int64_t a = m + i;
+        tail[a] = i; head[a] = i; UB[a] = DBL_MAX; actualCost[a] = bigM;
+        mult[a] = (supply[i] >= 0.0) ? 0.5 : 2.0;
+        isArtificial[a] = 1;
+    }
+    numOrigArcs = g.numOrigArcs;
+    for (int r = 0; r < numSets; ++r) {                 // :64-79, 96-103 (isArtificial never set for a set: `r == numEqualFlowSets` is never true)
+        UB[A + r] = g.setUB[r]; actualCost[A + r] = g.setCost[r];
+    }
+    nodeVals = g.nodeVals;
+    csrStart.assign((size_t) numSets + 1, 0); csrNode.clear(); csrVal.clear();
+    for (int r = 0; r < numSets; ++r) {
+        for (int i = 0; i < numNodes; ++i) {
+            const double d = nodeVals[(size_t) r * numNodes + i];
+            if (d != 0.0) { csrNode.push_back(i); csrVal.push_back(d); }
+        }
+        csrStart[(size_t) r + 1] = (int64_t) csrNode.size();
+    }
+    cost.assign((size_t) V, 0.0); flow.assign((size_t) V, 0.0); deltaFlow.assign((size_t) V, 0.0);
+    flowA0.assign((size_t) A, 0.0); flowA1.assign((size_t) A, 0.0);
+    setLoc.assign((size_t) V, NIL); setInd.assign((size_t) V, -1);
+    potential.assign(numNodes, 0.0); potA0.assign(numNodes, 0.0); potA1.assign(numNodes, 0.0); potTheta.assign(numNodes, -2);
+    supA0.assign(numNodes, 0.0); supA1.assign(numNodes, 0.0);
+    memberOfTreeID.assign(numNodes, -1); memberOfTreeType.assign(numNodes, T_NONE);
+    depth.assign(numNodes, -1); thread.assign(numNodes, -1); pred.assign(numNodes, -1); predArc.assign(numNodes, -1);
+    incidentArcs.assign(numNodes, std::vector<int32_t>());
+    // the nonbasic arc list never holds more than m + p arcs (|setBarc| = n - |setBeqf| >= n - p)
+    if (!hostOnly) GNE_TRY(gne_dev_create(&dev, cudaDevice, numNodes, m + numSets + 16, 0, m + numSets + 16));
+    for (int64_t a = 0; a < A; ++a) {                   // formInitialBFS :174-186
+        if (isArtificial[a]) GNE_TRY(insertIntoB((int32_t) a));
+        else GNE_TRY(insertIntoNB((int32_t) a, L_var));
+    }
+    for (int r = 0; r < numSets; ++r) GNE_TRY(insertIntoNB((int32_t) (A + r), L_var));
+    updateTrees();
+    phaseIiters = 0; phaseIIiters = 0;
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// trees.cpp, restated on flat node arrays (ids, not pointers)
+// ------------------------------------------------------------------------------------------
+EqfSolver::ETree *EqfSolver::createNewTree(int8_t type, int rNode)      // :183-203
+{
+    ETree *t = new ETree();
+    std::vector<ETree *> &set = (type == T_I) ? setBtI : setBtII;
+    t->id = (int) set.size(); t->type = type; t->root = -1; t->upToDate = false; t->extraArc = -1;
+    set.push_back(t);
+    if (rNode >= 0) {
+        t->root = rNode;
+        t->nodesInTree.push_back(rNode);
+        memberOfTreeID[rNode] = t->id; memberOfTreeType[rNode] = t->type;
+    }
+    return t;
+}
+
+void EqfSolver::setTreeIDAndType(ETree *t, int newID, int8_t newType)   // :218-229
+{
+    t->id = newID; t->type = newType;
+    for (size_t k = 0; k < t->nodesInTree.size(); ++k) {
+        const int i = t->nodesInTree[k];
+        memberOfTreeID[i] = newID; memberOfTreeType[i] = newType;
+    }
+}
+
+void EqfSolver::removeTree(ETree *t)                               // :232-256: the last tree of the type takes the freed id
+{
+    std::vector<ETree *> &set = (t->type == T_I) ? setBtI : setBtII;
+    const int oldID = t->id;
+    if ((size_t) oldID < set.size() - 1) {
+        ETree *last = set.back();
+        setTreeIDAndType(last, oldID, t->type);
+        set[(size_t) oldID] = last;
+    }
+    set.pop_back();
+}
+
+void EqfSolver::convertTItoTII(ETree *t)                           // :259-272 (upToDate is left as it is)
+{
+    const int newID = (int) setBtII.size();
+    removeTree(t);
+    setTreeIDAndType(t, newID, T_II);
+    t->extraArc = -1;
+    setBtII.push_back(t);
+}
+
+void EqfSolver::convertTIItoTI(ETree *t, int32_t av)               // :275-288
+{
+    const int newID = (int) setBtI.size();
+    removeTree(t);
+    setTreeIDAndType(t, newID, T_I);
+    t->extraArc = av;
+    setBtI.push_back(t);
+}
+
+int EqfSolver::insertIntoTrees(int32_t av)                         // :294-363
+{
+    const int u = tail[av], v = head[av];
+    const int tUID = memberOfTreeID[u], tVID = memberOfTreeID[v];
+    const int8_t tUType = memberOfTreeType[u], tVType = memberOfTreeType[v];
+    if (tUID != -1 && tVID != -1) {
+        if (tUID == tVID && tUType == tVType) {
+            if (tUType == T_I) { gne_set_error("Error: Insertion adds cycle to type I tree"); return GNE_ERR_TREE; }
+            convertTIItoTI(setBtII[(size_t) tUID], av);
+        } else if (tUType == T_II && tVType == T_II) {
+            mergeTxAndTII(setBtII[(size_t) tUID], setBtII[(size_t) tVID], av);
+        } else if (tUType == T_I && tVType == T_II) {
+            mergeTxAndTII(setBtI[(size_t) tUID], setBtII[(size_t) tVID], av);
+        } else if (tUType == T_II && tVType == T_I) {
+            mergeTxAndTII(setBtI[(size_t) tVID], setBtII[(size_t) tUID], av);
+        } else {
+            gne_set_error("Error: Insertion merges two type I trees"); return GNE_ERR_TREE;
+        }
+    } else {
+        ETree *tUV;
+        if (tUID == -1 && tVID == -1) tUV = createNewTree(u == v ? T_I : T_II, u);
+        else if (tUID != -1) tUV = (tUType == T_I) ? setBtI[(size_t) tUID] : setBtII[(size_t) tUID];
+        else tUV = (tVType == T_I) ? setBtI[(size_t) tVID] : setBtII[(size_t) tVID];
+        expandTreeUsingArc(tUV, av);
+    }
+    return GNE_OK;
+}
+
+void EqfSolver::mergeTxAndTII(ETree *tX, ETree *tII, int32_t av)   // :366-392
+{
+    removeTree(tII);                                    // (may hand tII's id to tX when tX is the last type II tree)
+    setTreeIDAndType(tII, tX->id, tX->type);
+    tX->nodesInTree.insert(tX->nodesInTree.end(), tII->nodesInTree.begin(), tII->nodesInTree.end());
+    tX->arcsInTree.insert(tX->arcsInTree.end(), tII->arcsInTree.begin(), tII->arcsInTree.end());
+    tX->arcsInTree.push_back(av);
+    incidentArcs[tail[av]].push_back(av);
+    incidentArcs[head[av]].push_back(av);
+    tX->upToDate = false;
+    delete tII;
+}
+
+void EqfSolver::expandTreeUsingArc(ETree *t, int32_t av)           // :395-428 (the id alone is compared, as there)
+{
+    const int u = tail[av], v = head[av];
+    if (memberOfTreeID[u] != t->id) {
+        t->nodesInTree.push_back(u);
+        memberOfTreeID[u] = t->id; memberOfTreeType[u] = t->type;
+    } else if (memberOfTreeID[v] != t->id) {
+        t->nodesInTree.push_back(v);
+        memberOfTreeID[v] = t->id; memberOfTreeType[v] = t->type;
+    }
+    if (u != v) {
+        t->arcsInTree.push_back(av);
+        incidentArcs[u].push_back(av);
+        incidentArcs[v].push_back(av);
+    } else {
+        t->extraArc = av;
+    }
+    t->upToDate = false;
+}
+
+int EqfSolver::removeFromTrees(int32_t av)                         // :450-494
+{
+    const int u = tail[av], v = head[av];
+    const int tUID = memberOfTreeID[u], tVID = memberOfTreeID[v];
+    const int8_t tUType = memberOfTreeType[u], tVType = memberOfTreeType[v];
+    if (tUID != tVID || tUType != tVType) { gne_set_error("Error: Attempting to remove arc spanning two trees"); return GNE_ERR_TREE; }
+    ETree *tUV = (tUType == T_I) ? setBtI[(size_t) tUID] : setBtII[(size_t) tUID];
+    if (tUV->type == T_I && av == tUV->extraArc) {
+        convertTItoTII(tUV);
+    } else {
+        removeTree(tUV);
+        splitTree(tUV, av);
+        if (tUV->type == T_I) GNE_TRY(insertIntoTrees(tUV->extraArc));
+        delete tUV;
+    }
+    return GNE_OK;
+}
+
+void EqfSolver::splitTree(ETree *tX, int32_t removedArc)           // :497-566: the DFS that defines the parts' node and arc order
+{
+    ETree *tTop = createNewTree(T_II, -1);
+    ETree *tBottom = createNewTree(T_II, -1);
+    ETree *tCur = tTop;
+    std::stack<int> curNodeStack, prevNodeStack;
+    curNodeStack.push(tX->root);
+    prevNodeStack.push(-1);
+    while (!curNodeStack.empty()) {
+        int curNode = curNodeStack.top(); curNodeStack.pop();
+        if (curNode < 0) {                              // the bottom part is done
+            tCur = tTop;
+            if (curNodeStack.empty()) break;
+            curNode = curNodeStack.top(); curNodeStack.pop();
+        }
+        const int prevNode = prevNodeStack.top(); prevNodeStack.pop();
+        memberOfTreeID[curNode] = tCur->id; memberOfTreeType[curNode] = tCur->type;
+        if (tCur->nodesInTree.empty()) tCur->root = curNode;
+        tCur->nodesInTree.push_back(curNode);
+        std::vector<int32_t> &inc = incidentArcs[curNode];
+        int removedArcInd = -1;
+        for (int k = 0; k < (int) inc.size(); ++k) {
+            const int32_t nextArc = inc[(size_t) k];
+            if (nextArc == removedArc) { removedArcInd = k; continue; }
+            const int nextNode = (tail[nextArc] == curNode) ? head[nextArc] : tail[nextArc];
+            if (nextNode != prevNode) {
+                tCur->arcsInTree.push_back(nextArc);
+                curNodeStack.push(nextNode);
+                prevNodeStack.push(curNode);
+            }
+        }
+        if (removedArcInd >= 0) {
+            inc[(size_t) removedArcInd] = inc.back();
+            inc.pop_back();
+            if (prevNode > -2) {                        // first end of the removed arc: its other end starts the bottom part
+                const int nextNode = (tail[removedArc] == curNode) ? head[removedArc] : tail[removedArc];
+                curNodeStack.push(-1);
+                curNodeStack.push(nextNode);
+                prevNodeStack.push(-2);
+                tCur = tBottom;
+            }
+        }
+    }
+}
+
+void EqfSolver::updateTrees()                                      // :572-591
+{
+    for (size_t k = 0; k < setBtI.size(); ++k) {
+        ETree *t = setBtI[k];
+        if (!t->upToDate) { t->root = tail[t->extraArc]; initializeTreeIndices(t); t->upToDate = true; }
+    }
+    for (size_t k = 0; k < setBtII.size(); ++k) {
+        ETree *t = setBtII[k];
+        if (!t->upToDate) { initializeTreeIndices(t); t->upToDate = true; }
+    }
+}
+
+void EqfSolver::initializeTreeIndices(ETree *t)                    // :597-644
+{
+    std::stack<int> curNodeStack;
+    std::stack<int32_t> predArcStack;
+    std::vector<int32_t> &threads = t->threads;
+    threads.clear();
+    curNodeStack.push(t->root);
+    while (!curNodeStack.empty()) {
+        const int curNode = curNodeStack.top(); curNodeStack.pop();
+        int predNode = -1;
+        if (!threads.empty()) {
+            const int32_t pa = predArcStack.top(); predArcStack.pop();
+            predNode = (curNode == tail[pa]) ? head[pa] : tail[pa];
+            depth[curNode] = depth[predNode] + 1;
+            predArc[curNode] = pa;
+            thread[threads.back()] = curNode;
+        } else {
+            depth[curNode] = 0;
+            predArc[curNode] = -1;
+        }
+        pred[curNode] = predNode;
+        threads.push_back(curNode);
+        const std::vector<int32_t> &inc = incidentArcs[curNode];
+        for (int k = (int) inc.size() - 1; k >= 0; --k) {
+            const int32_t av = inc[(size_t) k];
+            const int u = tail[av], v = head[av];
+            if (u == predNode || v == predNode) continue;
+            curNodeStack.push(curNode == u ? v : u);
+            predArcStack.push(av);
+        }
+    }
+    thread[threads.back()] = t->root;
+}
+
+// ------------------------------------------------------------------------------------------
+// basis sets: gnePivot.cpp:487-600; setNBarc is mirrored on the device (position order)
+// ------------------------------------------------------------------------------------------
+int EqfSolver::insertIntoB(int32_t v)
+{
+    if (isArc(v)) {
+        setBarc.push_back(v); setLoc[v] = B_var; setInd[v] = (int32_t) setBarc.size() - 1;
+        GNE_TRY(insertIntoTrees(v));
+    } else {
+        setBeqf.push_back(v); setLoc[v] = B_var; setInd[v] = (int32_t) setBeqf.size() - 1;
+    }
+    return GNE_OK;
+}
+
+int EqfSolver::removeFromB(int32_t v)
+{
+    std::vector<int32_t> &set = isArc(v) ? setBarc : setBeqf;
+    const int32_t prevInd = setInd[v];
+    const int32_t mv = set.back();
+    set[(size_t) prevInd] = mv; setInd[mv] = prevInd; set.pop_back();
+    if (isArc(v)) GNE_TRY(removeFromTrees(v));
+    setLoc[v] = NIL; setInd[v] = -1;
+    return GNE_OK;
+}
+
+int EqfSolver::insertIntoNB(int32_t v, int8_t loc)
+{
+    if (isArc(v)) {
+        setNBarc.push_back(v); setLoc[v] = loc; setInd[v] = (int32_t) setNBarc.size() - 1;
+        if (costsOnDevice) {
+            GNE_TRY(gne_nb_write(dev, (int64_t) setNBarc.size() - 1, tail[v], head[v], cost[v], mult[v], loc));
+            GNE_TRY(gne_nb_set_count(dev, (int64_t) setNBarc.size()));
+        }
+    } else {
+        setNBeqf.push_back(v); setLoc[v] = loc; setInd[v] = (int32_t) setNBeqf.size() - 1;
+    }
+    return GNE_OK;
+}
+
+int EqfSolver::removeFromNB(int32_t v)
+{
+    std::vector<int32_t> &set = isArc(v) ? setNBarc : setNBeqf;
+    const int32_t prevInd = setInd[v];
+    const int32_t mv = set.back();
+    set[(size_t) prevInd] = mv; setInd[mv] = prevInd; set.pop_back();
+    setLoc[v] = NIL; setInd[v] = -1;
+    if (isArc(v) && costsOnDevice) {
+        if (mv != v) GNE_TRY(gne_nb_write(dev, prevInd, tail[mv], head[mv], cost[mv], mult[mv], setLoc[mv]));
+        GNE_TRY(gne_nb_set_count(dev, (int64_t) setNBarc.size()));
+    }
+    return GNE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the s x s systems: GSL's gsl_linalg_LU_decomp / gsl_linalg_LU_solve (linalg/lu.c of GSL 1.x - 2.5), row-major
+// ------------------------------------------------------------------------------------------
+void EqfSolver::lu_decomp(std::vector<double> &a, int s, std::vector<int> &perm)
+{
+    perm.resize((size_t) s);
+    for (int i = 0; i < s; ++i) perm[(size_t) i] = i;
+    for (int j = 0; j + 1 < s; ++j) {
+        double big = fabs(a[(size_t) j * s + j]);       // pivot: the FIRST row of largest magnitude in column j
+        int piv = j;
+        for (int i = j + 1; i < s; ++i) {
+            const double aij = fabs(a[(size_t) i * s + j]);
+            if (aij > big) { big = aij; piv = i; }
+        }
+        if (piv != j) {
+            for (int k = 0; k < s; ++k) std::swap(a[(size_t) j * s + k], a[(size_t) piv * s + k]);
+            std::swap(perm[(size_t) j], perm[(size_t) piv]);
+        }
+        const double ajj = a[(size_t) j * s + j];
+        if (ajj != 0.0) {
+            for (int i = j + 1; i < s; ++i) {
+                const double aij = a[(size_t) i * s + j] / ajj;
+                a[(size_t) i * s + j] = aij;
+                for (int k = j + 1; k < s; ++k) a[(size_t) i * s + k] = a[(size_t) i * s + k] - aij * a[(size_t) j * s + k];
+            }
+        }
+    }
+}
+
+void EqfSolver::lu_solve(const std::vector<double> &lu, int s, const std::vector<int> &perm, const std::vector<double> &b,
+                         std::vector<double> &x)
+{
+    x.resize((size_t) s);
+    for (int i = 0; i < s; ++i) x[(size_t) i] = b[(size_t) perm[(size_t) i]];       // gsl_permute_vector
+    for (int i = 1; i < s; ++i) {                       // dtrsv Lower / NoTrans / Unit (gslcblas source_trsv_r.h)
+        double tmp = x[(size_t) i];
+        for (int j = 0; j < i; ++j) tmp -= lu[(size_t) i * s + j] * x[(size_t) j];
+        x[(size_t) i] = tmp;
+    }
+    if (s > 0) {                                        // dtrsv Upper / NoTrans / NonUnit
+        x[(size_t) s - 1] = x[(size_t) s - 1] / lu[(size_t) (s - 1) * s + (s - 1)];
+        for (int i = s - 2; i >= 0; --i) {
+            double tmp = x[(size_t) i];
+            for (int j = i + 1; j < s; ++j) tmp -= lu[(size_t) i * s + j] * x[(size_t) j];
+            x[(size_t) i] = tmp / lu[(size_t) i * s + i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// gnePotential.cpp
+// ------------------------------------------------------------------------------------------
+int EqfSolver::computePotentials()                                 // :28-61
+{
+    for (size_t k = 0; k < setBtI.size(); ++k) {
+        computePotentialsInTermsOfRoot(setBtI[k]);
+        finalizePotentialsTypeI(setBtI[k]);
+    }
+    for (size_t k = 0; k < setBtII.size(); ++k) computePotentialsInTermsOfRoot(setBtII[k]);
+    if (!setBeqf.empty()) computePotentialsWithEqFlowSets();
+    // the device prices against these: all of them can change in one pivot (the s x s solve couples every type II tree)
+    if (!hostOnly) GNE_TRY(gne_pot_set_all(dev, potential.data()));
+    return GNE_OK;
+}
+
+void EqfSolver::computePotentialsInTermsOfRoot(ETree *t)           // :64-110
+{
+    const int thetaID = (t->type == T_I) ? -1 : t->id;
+    const std::vector<int32_t> &th = t->threads;
+    const int h = th[0];
+    potA0[h] = 0.0; potA1[h] = 1.0; potTheta[h] = thetaID;
+    for (size_t q = 1; q < th.size(); ++q) {
+        const int j = th[q];
+        const int i = pred[j];
+        const int32_t pa = predArc[j];
+        const double c = cost[pa], mu = mult[pa];
+        if (tail[pa] == i) {
+            potA0[j] = (potA0[i] - c) / mu;
+            potA1[j] = potA1[i] / mu;
+        } else {
+            potA0[j] = (mu * potA0[i]) + c;
+            potA1[j] = mu * potA1[i];
+        }
+        potTheta[j] = thetaID;
+    }
+}
+
+void EqfSolver::finalizePotentialsTypeI(ETree *t)                  // :113-138
+{
+    const int32_t ex = t->extraArc;
+    const int alpha = tail[ex], beta = head[ex];
+    const double cAB = cost[ex], muAB = mult[ex];
+    const double thetaValue = (cAB - potA0[alpha] + muAB * potA0[beta]) / (potA1[alpha] - muAB * potA1[beta]);
+    for (size_t k = 0; k < t->nodesInTree.size(); ++k) {
+        const int i = t->nodesInTree[k];
+        potential[i] = potA0[i] + potA1[i] * thetaValue;
+        potA0[i] = 0.0; potA1[i] = 0.0; potTheta[i] = -2;
+    }
+}
+
+void EqfSolver::computePotentialsWithEqFlowSets()                  // :142-214
+{
+    const int s = (int) setBeqf.size();
+    std::vector<double> mat((size_t) s * s, 0.0), rhs((size_t) s, 0.0), x, rowVals((size_t) s);
+    std::vector<int> perm;
+    for (int b = 0; b < s; ++b) {
+        const int32_t v = setBeqf[(size_t) b];
+        const double *dr = &nodeVals[(size_t) (v - A) * numNodes];
+        double rhsVal = cost[v];
+        std::fill(rowVals.begin(), rowVals.end(), 0.0);
+        for (int i = 0; i < numNodes; ++i) {
+            const double dri = dr[i];
+            if (memberOfTreeType[i] == T_I) {
+                rhsVal -= dri * potential[i];
+            } else {
+                rhsVal -= dri * potA0[i];
+                rowVals[(size_t) potTheta[i]] += dri * potA1[i];
+            }
+        }
+        rhs[(size_t) b] = rhsVal;
+        for (int k = 0; k < s; ++k) mat[(size_t) b * s + k] = rowVals[(size_t) k];
+    }
+    lu_decomp(mat, s, perm);
+    lu_solve(mat, s, perm, rhs, x);
+    for (int i = 0; i < numNodes; ++i) {
+        if (memberOfTreeType[i] == T_I) continue;
+        potential[i] = potA0[i] + potA1[i] * x[(size_t) potTheta[i]];
+        potA0[i] = 0.0; potA1[i] = 0.0; potTheta[i] = -2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// genneteq.h:334-403
+// ------------------------------------------------------------------------------------------
+double EqfSolver::computeDeltaVar(int32_t v) const                 // :356-403 (initialType is SELFLOOPS: no artificial-cost branch)
+{
+    const double xVar = flow[v], yVar = deltaFlow[v];
+    if (yVar > TOL) {
+        if (fabs(UB[v] - xVar) < TOL) return 0.0;
+        return (UB[v] - xVar) / yVar;
+    } else if (yVar < (-1.0 * TOL)) {
+        if (fabs(xVar) < TOL) return 0.0;
+        return xVar / (-1.0 * yVar);
+    }
+    return DBL_MAX;
+}
+
+void EqfSolver::checkVarForBlocking(int32_t v)                     // :334-354
+{
+    const double deltaVar = computeDeltaVar(v);
+    if (delta > deltaVar + TOL) blockingVars.clear();
+    if (delta >= deltaVar - TOL) { delta = deltaVar; blockingVars.push_back(v); }
+}
+
+// ------------------------------------------------------------------------------------------
+// gneFlow.cpp
+// ------------------------------------------------------------------------------------------
+void EqfSolver::computeFlows(int updateOption)                     // :30-56
+{
+    flowCost = 0.0;
+    if (!setBeqf.empty()) {
+        setSupplyWithThetas();
+        computeBoundedFlows(true);
+        computeFlowsWithEqFlowSets();
+    } else {
+        setSupplyWithEqs();
+        computeBoundedFlows(false);
+    }
+    for (size_t k = 0; k < setBtI.size(); ++k) computeFlowsTypeI(setBtI[k]);
+    setFlowValues(updateOption);
+}
+
+void EqfSolver::setFlowValues(int updateOption)                    // :59-150 (the error report is the reference's printf only)
+{
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<int32_t> &set = pass == 0 ? setBarc : setBeqf;
+        for (size_t k = 0; k < set.size(); ++k) {
+            const int32_t v = set[k];
+            if (updateOption == 0 || updateOption > 1) flow[v] = deltaFlow[v];
+            if (updateOption == 0) { deltaFlow[v] = 0.0; flowCost += flow[v] * cost[v]; }
+            else { flowCost += flow[v] * cost[v]; deltaFlow[v] = 0.0; }
+        }
+    }
+}
+
+void EqfSolver::computeFlowsPivotingTI(int32_t eav, ETree *tU, ETree *tV)      // :155-185
+{
+    if (setLoc[eav] == L_var) {
+        if (tail[eav] == head[eav]) supA0[tail[eav]] = -1.0 * (1.0 - mult[eav]);
+        else { supA0[tail[eav]] = -1.0; supA0[head[eav]] = mult[eav]; }
+    } else {
+        if (tail[eav] == head[eav]) supA0[tail[eav]] = (1.0 - mult[eav]);
+        else { supA0[tail[eav]] = 1.0; supA0[head[eav]] = -1.0 * mult[eav]; }
+    }
+    computeFlowsTypeI(tU);
+    if (tU->id != tV->id) computeFlowsTypeI(tV);
+}
+
+void EqfSolver::computeFlowsPivotingTII(int32_t var)               // :188-209
+{
+    if (!setBeqf.empty()) {
+        setSupplyWithThetas(var);
+        computeFlowsWithEqFlowSets();
+    } else {
+        setSupplyWithEqs(var);
+    }
+    for (size_t k = 0; k < setBtI.size(); ++k) computeFlowsTypeI(setBtI[k]);
+}
+
+void EqfSolver::computeFlowsWithEqFlowSets()                       // :212-256
+{
+    const int s = (int) setBeqf.size();
+    for (int b = 0; b < s; ++b) {
+        const double *dr = &nodeVals[(size_t) (setBeqf[(size_t) b] - A) * numNodes];
+        for (int i = 0; i < numNodes; ++i) swt[(size_t) i * S + b + 1] -= dr[i];
+    }
+    std::vector<double> mat((size_t) s * s, 0.0), rhs((size_t) s, 0.0), x;
+    std::vector<int> perm;
+    for (size_t t = 0; t < setBtII.size(); ++t) {
+        const int h = computeFlowsTypeII(setBtII[t]);
+        const double *rootSupply = &swt[(size_t) h * S];
+        rhs[t] = (-1.0) * rootSupply[0];
+        for (int b = 0; b < s; ++b) mat[t * s + b] = rootSupply[b + 1];
+    }
+    lu_decomp(mat, s, perm);
+    lu_solve(mat, s, perm, rhs, x);
+    computeNumericFlowsAndSupply(x);
+}
+
+void EqfSolver::computeNumericFlowsAndSupply(const std::vector<double> &x)     // :259-306
+{
+    const int s = (int) setBeqf.size();
+    for (size_t t = 0; t < setBtII.size(); ++t) {
+        const std::vector<int32_t> &arcs = setBtII[t]->arcsInTree;
+        for (size_t k = 0; k < arcs.size(); ++k) {
+            const int32_t av = arcs[k];
+            const int j = (predArc[tail[av]] == av) ? tail[av] : head[av];         // the arc's flow vector sits in its lower end's row
+            const double *avFlow = &fwt[(size_t) j * S];
+            double actualFlow = avFlow[0];
+            for (int b = 0; b < s; ++b) actualFlow += avFlow[b + 1] * x[(size_t) b];
+            deltaFlow[av] = actualFlow;
+            checkVarForBlocking(av);
+        }
+    }
+    for (int b = 0; b < s; ++b) {
+        const int32_t v = setBeqf[(size_t) b];
+        deltaFlow[v] = x[(size_t) b];
+        checkVarForBlocking(v);
+    }
+    for (int i = 0; i < numNodes; ++i) {
+        const double *sup = &swt[(size_t) i * S];
+        double actualSupply = sup[0];
+        for (int b = 0; b < s; ++b) actualSupply += sup[b + 1] * x[(size_t) b];
+        supA0[i] = actualSupply;
+        if (memberOfTreeType[i] == T_II) supA0[i] = 0.0;
+        supA1[i] = 0.0;
+    }
+}
+
+void EqfSolver::computeBoundedFlows(bool withEqFlowSets)           // :312-368
+{
+    for (size_t k = 0; k < setNBarc.size(); ++k) {
+        const int32_t a = setNBarc[k];
+        if (setLoc[a] == L_var) { flow[a] = 0.0; continue; }
+        flow[a] = UB[a];
+        flowCost += flow[a] * cost[a];
+        if (withEqFlowSets) {
+            swt[(size_t) tail[a] * S] -= flow[a];
+            swt[(size_t) head[a] * S] += flow[a] * mult[a];
+        } else {
+            supA0[tail[a]] -= flow[a];
+            supA0[head[a]] += flow[a] * mult[a];
+        }
+    }
+    for (size_t k = 0; k < setNBeqf.size(); ++k) {
+        const int32_t v = setNBeqf[k];
+        if (setLoc[v] == L_var) { flow[v] = 0.0; continue; }
+        flow[v] = UB[v];
+        flowCost += flow[v] * cost[v];
+        const double *dr = &nodeVals[(size_t) (v - A) * numNodes];
+        if (withEqFlowSets) for (int i = 0; i < numNodes; ++i) swt[(size_t) i * S] -= flow[v] * dr[i];
+        else for (int i = 0; i < numNodes; ++i) supA0[i] -= flow[v] * dr[i];
+    }
+}
+
+void EqfSolver::setSupplyWithThetas()                              // :374-383
+{
+    S = (int) setBeqf.size() + 1;
+    swt.assign((size_t) numNodes * S, 0.0);
+    fwt.assign((size_t) numNodes * S, 0.0);
+    for (int i = 0; i < numNodes; ++i) swt[(size_t) i * S] = supply[i];
+}
+
+void EqfSolver::setSupplyWithEqs()                                 // :386-394
+{
+    for (int i = 0; i < numNodes; ++i) { supA0[i] = supply[i]; supA1[i] = 0.0; }
+}
+
+void EqfSolver::setSupplyWithThetas(int32_t var)                   // :397-438
+{
+    S = (int) setBeqf.size() + 1;
+    swt.assign((size_t) numNodes * S, 0.0);
+    fwt.assign((size_t) numNodes * S, 0.0);
+    if (isArc(var)) {
+        const int u = tail[var], v = head[var];
+        if (setLoc[var] == L_var) {
+            if (u == v) swt[(size_t) u * S] = -1.0 * (1.0 - mult[var]);
+            else { swt[(size_t) u * S] = -1.0; swt[(size_t) v * S] = mult[var]; }
+        } else {
+            if (u == v) swt[(size_t) u * S] = 1.0 - mult[var];
+            else { swt[(size_t) u * S] = 1.0; swt[(size_t) v * S] = -1.0 * mult[var]; }
+        }
+    } else {
+        const double *dr = &nodeVals[(size_t) (var - A) * numNodes];
+        if (setLoc[var] == L_var) for (int i = 0; i < numNodes; ++i) swt[(size_t) i * S] = -1.0 * dr[i];
+        else for (int i = 0; i < numNodes; ++i) swt[(size_t) i * S] = dr[i];
+    }
+}
+
+void EqfSolver::setSupplyWithEqs(int32_t var)                      // :441-474
+{
+    if (isArc(var)) {
+        const int u = tail[var], v = head[var];
+        if (setLoc[var] == L_var) {
+            if (u == v) supA0[u] = -1.0 * (1.0 - mult[var]);
+            else { supA0[u] = -1.0; supA0[v] = mult[var]; }
+        } else {
+            if (u == v) supA0[u] = 1.0 - mult[var];
+            else { supA0[u] = 1.0; supA0[v] = -1.0 * mult[var]; }
+        }
+    } else {
+        const double *dr = &nodeVals[(size_t) (var - A) * numNodes];
+        if (setLoc[var] == L_var) for (int i = 0; i < numNodes; ++i) supA0[i] = -1.0 * dr[i];
+        else for (int i = 0; i < numNodes; ++i) supA0[i] = dr[i];
+    }
+}
+
+void EqfSolver::computeFlowsTypeI(ETree *t)                        // :480-560
+{
+    const int32_t ex = t->extraArc;
+    const int alpha = tail[ex], beta = head[ex];
+    const double muAB = mult[ex];
+    flowA0[ex] = 0.0; flowA1[ex] = 1.0;
+    supA1[alpha] -= 1.0;
+    supA1[beta] += muAB;
+    const std::vector<int32_t> &th = t->threads;
+    const int h = t->root;
+    for (size_t q = th.size(); q-- > 1;) {              // reverse thread order, the root (th[0]) excluded
+        const int j = th[q];
+        const int32_t av = predArc[j];
+        if (tail[av] == j) {
+            const int i = head[av];
+            const double muJI = mult[av];
+            flowA0[av] = supA0[j]; flowA1[av] = supA1[j];
+            supA0[i] += supA0[j] * muJI;
+            supA1[i] += supA1[j] * muJI;
+        } else {
+            const int i = tail[av];
+            const double muIJ = mult[av];
+            flowA0[av] = supA0[j] / (-1.0 * muIJ);
+            flowA1[av] = supA1[j] / (-1.0 * muIJ);
+            supA0[i] += supA0[j] / muIJ;
+            supA1[i] += supA1[j] / muIJ;
+        }
+        supA0[j] = 0.0; supA1[j] = 0.0;
+    }
+    const double theta = (-1.0 * supA0[h]) / supA1[h];
+    supA0[h] = 0.0; supA1[h] = 0.0;
+    for (size_t k = 0; k < t->arcsInTree.size(); ++k) {
+        const int32_t av = t->arcsInTree[k];
+        deltaFlow[av] = flowA0[av] + flowA1[av] * theta;
+        flowA0[av] = 0.0; flowA1[av] = 0.0;
+        checkVarForBlocking(av);
+    }
+    deltaFlow[ex] = flowA0[ex] + flowA1[ex] * theta;
+    flowA0[ex] = 0.0; flowA1[ex] = 0.0;
+    checkVarForBlocking(ex);
+}
+
+int EqfSolver::computeFlowsTypeII(ETree *t)                        // :563-592
+{
+    const std::vector<int32_t> &th = t->threads;
+    const int h = t->root;
+    for (size_t q = th.size(); q-- > 1;) {
+        const int j = th[q];
+        const int32_t av = predArc[j];
+        double *ej = &swt[(size_t) j * S];
+        double *fj = &fwt[(size_t) j * S];
+        if (tail[av] == j) {
+            double *ei = &swt[(size_t) head[av] * S];
+            const double muJI = mult[av];
+            for (int k = 0; k < S; ++k) {
+                const double e_j_k = ej[k];
+                fj[k] = e_j_k;
+                ei[k] += e_j_k * muJI;
+            }
+        } else {
+            double *ei = &swt[(size_t) tail[av] * S];
+            const double muIJ = mult[av];
+            for (int k = 0; k < S; ++k) {
+                const double e_j_k = ej[k];
+                fj[k] = (-1.0 * e_j_k) / muIJ;
+                ei[k] += e_j_k / muIJ;
+            }
+        }
+    }
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------
+// gnePivot.cpp
+// ------------------------------------------------------------------------------------------
+int EqfSolver::pivot()                                             // :28-60
+{
+    if (isArc(eVar) && memberOfTreeType[tail[eVar]] == T_I && memberOfTreeType[head[eVar]] == T_I) {
+        pivotTI(eVar);
+    } else {
+        pivotTII();
+        ++pivotsTII;
+    }
+    if (lVar == -1) return GNE_OK;
+    GNE_TRY(updateBasis());
+    checkForCycling();
+    return status;
+}
+
+void EqfSolver::pivotTI(int32_t eav)                               // :63-119
+{
+    ETree *tU = setBtI[(size_t) memberOfTreeID[tail[eav]]];
+    ETree *tV = setBtI[(size_t) memberOfTreeID[head[eav]]];
+    delta = DBL_MAX;
+    computeFlowsPivotingTI(eav, tU, tV);
+    identifyLeavingVar();
+    if (lVar == -1) return;
+    for (int side = 0; side < 2; ++side) {
+        ETree *t = side == 0 ? tU : tV;
+        if (side == 1 && tU->id == tV->id) break;
+        for (size_t k = 0; k < t->arcsInTree.size(); ++k) {
+            const int32_t av = t->arcsInTree[k];
+            flow[av] += (delta * deltaFlow[av]);
+            flowCost += cost[av] * (delta * deltaFlow[av]);
+            deltaFlow[av] = 0.0;
+        }
+        const int32_t ex = t->extraArc;
+        flow[ex] += (delta * deltaFlow[ex]);
+        flowCost += cost[ex] * (delta * deltaFlow[ex]);
+        deltaFlow[ex] = 0.0;
+    }
+    if (setLoc[eav] == L_var) { flow[eav] = delta; flowCost += cost[eav] * delta; }
+    else { flow[eav] = UB[eav] - delta; flowCost -= cost[eav] * delta; }
+}
+
+void EqfSolver::pivotTII()                                         // :122-160
+{
+    delta = DBL_MAX;
+    computeFlowsPivotingTII(eVar);
+    identifyLeavingVar();
+    if (lVar == -1) return;
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<int32_t> &set = pass == 0 ? setBarc : setBeqf;
+        for (size_t k = 0; k < set.size(); ++k) {
+            const int32_t v = set[k];
+            flow[v] += (delta * deltaFlow[v]);
+            flowCost += cost[v] * (delta * deltaFlow[v]);
+            deltaFlow[v] = 0.0;
+        }
+    }
+    if (setLoc[eVar] == L_var) { flow[eVar] = delta; flowCost += cost[eVar] * delta; }
+    else { flow[eVar] = UB[eVar] - delta; flowCost -= cost[eVar] * delta; }
+}
+
+void EqfSolver::identifyLeavingVar()                               // :166-209 (an empty list ends the solve as unbounded instead of indexing it)
+{
+    if (UB[eVar] <= delta + TOL) {
+        delta = UB[eVar];
+        lVar = eVar;
+    } else {
+        if (blockingVars.empty()) { isUnbounded = true; lVar = -1; return; }
+        lVar = blockingVars[(size_t) (drand48() * blockingVars.size())];
+    }
+    if (delta <= TOL) { ++totalDegenPivots; ++consecutiveDegenPivots; }
+    else consecutiveDegenPivots = 0;
+}
+
+int EqfSolver::updateBasis()                                       // :254-309
+{
+    if (eVar == lVar) {
+        const int8_t was = setLoc[eVar];
+        GNE_TRY(removeFromNB(eVar));
+        GNE_TRY(insertIntoNB(eVar, was == L_var ? U_var : L_var));
+    } else {
+        GNE_TRY(removeFromNB(eVar));
+        GNE_TRY(removeFromB(lVar));
+        GNE_TRY(insertIntoB(eVar));
+        if (flow[lVar] > (0.5 * UB[lVar])) GNE_TRY(insertIntoNB(lVar, U_var));
+        else GNE_TRY(insertIntoNB(lVar, L_var));
+        updateTrees();
+    }
+    if (setLoc[lVar] == L_var) {
+        if (fabs(flow[lVar] - 0.0) > TOL) flow[lVar] = 0.0;
+    } else {
+        if (fabs(flow[lVar] - UB[lVar]) > TOL) flow[lVar] = UB[lVar];
+    }
+    return GNE_OK;
+}
+
+void EqfSolver::checkForCycling()                                  // :312-356
+{
+    if (cycleList.size() >= 10) cycleList.pop_back();
+    cycleList.push_front(std::make_pair(eVar, lVar));
+    cyclingDetected = false;
+    std::list<std::pair<int32_t, int32_t> >::iterator it = cycleList.begin();
+    for (++it; it != cycleList.end(); ++it) {
+        if (cycleList.front().first == it->first && cycleList.front().second == it->second) { cyclingDetected = true; break; }
+    }
+    if (cyclingDetected) {
+        ++totalCyclesDetected;
+        ++consecutiveCycles;
+        if (consecutiveCycles > 5) { gne_set_error("Stuck in cycling loop.  Retry with different pivots."); status = GNE_ERR_CYCLING; }
+    } else {
+        consecutiveCycles = 0;
+    }
+    lastEVarInd = eVar;
+}
+
+// ------------------------------------------------------------------------------------------
+// gnePivotRules.cpp: the arc loops run on the device, the set loops continue their state on the host
+// ------------------------------------------------------------------------------------------
+bool EqfSolver::violates(int32_t v, double rc) const               // :406-407 and its copies
+{
+    return (setLoc[v] == L_var && rc < (-1.0 * TOL)) || (setLoc[v] == U_var && rc > TOL);
+}
+
+double EqfSolver::hostRedCost(int32_t v) const                     // genneteq.h:312-330 against the host's copy of the potentials
+{
+    if (isArc(v)) return cost[v] - potential[tail[v]] + mult[v] * potential[head[v]];
+    const double *dr = &nodeVals[(size_t) (v - A) * numNodes];
+    double rc = cost[v];
+    for (int i = 0; i < numNodes; ++i) rc -= (dr[i] * potential[i]);
+    return rc;
+}
+
+int EqfSolver::priceSets()                                         // computeEqfRedCost of every nonbasic set, setNBeqf order
+{
+    const int q = (int) setNBeqf.size();
+    eqfRc.resize((size_t) q);
+    if (q == 0) return GNE_OK;
+    std::vector<int64_t> rowStart((size_t) q + 1, 0);
+    std::vector<int32_t> node;
+    std::vector<double> val, c((size_t) q);
+    for (int k = 0; k < q; ++k) {
+        const int r = (int) (setNBeqf[(size_t) k] - A);
+        node.insert(node.end(), csrNode.begin() + csrStart[(size_t) r], csrNode.begin() + csrStart[(size_t) r + 1]);
+        val.insert(val.end(), csrVal.begin() + csrStart[(size_t) r], csrVal.begin() + csrStart[(size_t) r + 1]);
+        rowStart[(size_t) k + 1] = (int64_t) node.size();
+        c[(size_t) k] = cost[setNBeqf[(size_t) k]];
+    }
+    return gne_price_eqf(dev, q, rowStart.data(), node.data(), val.data(), c.data(), eqfRc.data());
+}
+
+int EqfSolver::fetchViolators()                                    // computeReducedCosts(false), gnePotential.cpp:217-246
+{
+    isOptimal = true;
+    int64_t cnt = 0;
+    if (listPos.size() < 1024) { listPos.resize(1024); listViol.resize(1024); }
+    int rc = gne_price_violators(dev, 0.0, &cnt, listPos.data(), listViol.data(), (int64_t) listPos.size());
+    if (rc == GNE_ERR_CAPACITY) {
+        listPos.resize((size_t) cnt + 1024); listViol.resize((size_t) cnt + 1024);
+        rc = gne_price_violators(dev, 0.0, &cnt, listPos.data(), listViol.data(), (int64_t) listPos.size());
+    }
+    if (rc) return rc;
+    arcsPriced += (double) setNBarc.size();
+    offendingVars.resize((size_t) cnt); offendingViol.resize((size_t) cnt);
+    for (int64_t i = 0; i < cnt; ++i) { offendingVars[(size_t) i] = setNBarc[(size_t) listPos[(size_t) i]]; offendingViol[(size_t) i] = listViol[(size_t) i]; }
+    GNE_TRY(priceSets());
+    for (size_t k = 0; k < setNBeqf.size(); ++k) {
+        if (violates(setNBeqf[k], eqfRc[k])) { offendingVars.push_back(setNBeqf[k]); offendingViol.push_back(fabs(eqfRc[k])); }
+    }
+    if (!offendingVars.empty()) isOptimal = false;
+    return GNE_OK;
+}
+
+// order 0: arcs then sets (getVarWithLargestViolation :133-157), 1: arcs first (:160-180), 2: sets first (:183-203)
+int EqfSolver::getVarWithLargestViolation(int order, bool useWeighted, int32_t *out)
+{
+    isOptimal = true;
+    double L = -1.0;
+    int64_t arcCount = 0;
+    std::vector<int32_t> sets;                          // the set members of offendingVars (always behind the arc members)
+    bool arcsPricedNow = false;
+    // the set loop of computeEqfsWithLargestViolation (:415-429) continuing checkVarForOffending's state (:431-452)
+    auto setPass = [&](bool weighted) {
+        for (size_t k = 0; k < setNBeqf.size(); ++k) {
+            const int32_t v = setNBeqf[k];
+            const double rc = eqfRc[k];
+            if (!violates(v, rc)) continue;
+            isOptimal = false;
+            const double frc = weighted ? fabs(rc) / numOrigArcs[(size_t) (v - A)] : fabs(rc);
+            if (L < frc - TOL) { arcCount = 0; sets.clear(); }
+            if (L <= frc + TOL) { L = frc; sets.push_back(v); }
+        }
+    };
+    auto arcPass = [&]() -> int {                       // only ever entered with L == -1 and an empty list
+        int any = 0;
+        GNE_TRY(gne_price_lv_begin(dev, &L, &arcCount, &any));
+        arcsPriced += (double) setNBarc.size();
+        arcsPricedNow = true;
+        if (any) isOptimal = false;
+        return GNE_OK;
+    };
+    // (the sets are priced before the arc pass is started: nothing else touches the handle between the pass and the
+    //  gne_price_lv_at that resolves the picked member of a list the device kept)
+    if (order == 2) {
+        GNE_TRY(priceSets());
+        setPass(false);
+        lastViolation = L;
+        if (sets.empty()) { GNE_TRY(arcPass()); lastViolation = L; }
+    } else if (order == 0) {
+        GNE_TRY(priceSets());
+        GNE_TRY(arcPass());
+        setPass(useWeighted);
+        lastViolation = L;
+    } else {
+        GNE_TRY(arcPass());
+        lastViolation = L;
+        if (arcCount == 0) { GNE_TRY(priceSets()); setPass(false); lastViolation = L; }
+    }
+    const size_t total = (size_t) arcCount + sets.size();
+    if (total == 0) { *out = -1; return GNE_OK; }
+    const size_t idx = (size_t) (drand48() * total);
+    if (idx < (size_t) arcCount) {
+        if (!arcsPricedNow) { gne_set_error("EqfSolver: arc member without an arc pass"); return GNE_ERR_ARG; }
+        int64_t pos = -1;
+        GNE_TRY(gne_price_lv_at(dev, (int64_t) idx, &pos));
+        *out = setNBarc[(size_t) pos];
+    } else {
+        *out = sets[idx - (size_t) arcCount];
+    }
+    return GNE_OK;
+}
+
+int EqfSolver::getFirstVarWithViolation(int32_t *out)              // :206-228
+{
+    isOptimal = true;
+    int64_t pos = -1;
+    GNE_TRY(gne_price_first(dev, &pos));
+    arcsPriced += (double) (pos < 0 ? (int64_t) setNBarc.size() : pos + 1);
+    if (pos >= 0) { isOptimal = false; *out = setNBarc[(size_t) pos]; return GNE_OK; }
+    GNE_TRY(priceSets());
+    for (size_t k = 0; k < setNBeqf.size(); ++k) {
+        if (violates(setNBeqf[k], eqfRc[k])) { isOptimal = false; *out = setNBeqf[k]; return GNE_OK; }
+    }
+    *out = -1;
+    return GNE_OK;
+}
+
+int EqfSolver::getRandomVarWithViolation(int32_t *out)             // :273-281
+{
+    GNE_TRY(fetchViolators());
+    if (offendingVars.empty()) { *out = -1; return GNE_OK; }
+    *out = offendingVars[(size_t) (drand48() * offendingVars.size())];
+    return GNE_OK;
+}
+
+int EqfSolver::getRandomVarWeightedByViolation(int32_t *out)       // :284-304
+{
+    GNE_TRY(fetchViolators());
+    *out = -1;
+    if (!offendingVars.empty()) {
+        double sum = 0.0;
+        for (size_t i = 0; i < offendingVars.size(); ++i) sum += offendingViol[i];
+        const double level = drand48() * sum;
+        double run = 0.0;
+        for (size_t i = 0; i < offendingVars.size(); ++i) {
+            run += offendingViol[i];
+            if (level <= run) { *out = offendingVars[i]; break; }
+        }
+    }
+    return GNE_OK;
+}
+
+int EqfSolver::getRandomVarWithLargeViolation(bool useWeighted, int32_t *out)  // :307-362
+{
+    GNE_TRY(fetchViolators());                          // arcs in position order, then the sets
+    std::priority_queue<VarWithViol, std::vector<VarWithViol>, violcomp> q;
+    for (size_t i = 0; i < offendingVars.size(); ++i) {
+        const int32_t v = offendingVars[i];
+        VarWithViol vv; vv.var = v;
+        vv.violation = (!isArc(v) && useWeighted) ? -1.0 * offendingViol[i] / numOrigArcs[(size_t) (v - A)] : -1.0 * offendingViol[i];
+        q.push(vv);
+        while ((int) q.size() > numLargestViolVarsToTrack) q.pop();
+    }
+    std::vector<int32_t> fin;
+    while (!q.empty()) { fin.push_back(q.top().var); q.pop(); }
+    if (fin.empty()) { *out = -1; return GNE_OK; }
+    *out = fin[(size_t) (drand48() * fin.size())];
+    return GNE_OK;
+}
+
+int EqfSolver::getVarBySimAnnealing(bool arcsFirst, int32_t *out)  // :364-396
+{
+    if (drand48() < lastViolation / baselineViolation) GNE_TRY(getVarWithLargestViolation(arcsFirst ? 1 : 2, false, out));
+    else GNE_TRY(getVarWithLargestViolation(0, true, out));
+    if (arcsFirst && lastViolation * 100 < baselineViolation && baselineViolation > 5000) baselineViolation = lastViolation;
+    return GNE_OK;
+}
+
+int EqfSolver::getNextCandidate(bool useWeighted, int32_t *out)    // :456-535
+{
+    isOptimal = true;
+    if (itersSinceUpdate < 0 || itersSinceUpdate > majorIterationLength) {
+        while (!candidateList.empty()) candidateList.pop();        // updateCandidateList
+        GNE_TRY(fetchViolators());
+        for (size_t i = 0; i < offendingVars.size(); ++i) {
+            const int32_t v = offendingVars[i];
+            VarWithViol vv; vv.var = v;
+            vv.violation = (!isArc(v) && useWeighted) ? offendingViol[i] / numOrigArcs[(size_t) (v - A)] : offendingViol[i];
+            candidateList.push(vv);
+        }
+        itersSinceUpdate = 0;
+    } else {
+        ++itersSinceUpdate;
+    }
+    int32_t found = -1;
+    while (!candidateList.empty()) {
+        const int32_t c = candidateList.top().var;
+        candidateList.pop();
+        const bool atLB = (setLoc[c] == L_var);
+        const double rc = hostRedCost(c);              // one variable against the host's copy of the potentials
+        if ((atLB && rc < (-1.0 * TOL)) || (!atLB && rc > TOL)) { isOptimal = false; found = c; break; }
+    }
+    if (found == -1 && itersSinceUpdate > 0) {
+        itersSinceUpdate = -1;
+        return getNextCandidate(false, out);            // (the reference's retry drops useWeighted, :494)
+    }
+    *out = found;
+    return GNE_OK;
+}
+
+int EqfSolver::quickSelect(bool useWeighted, int32_t *out)         // :710-764
+{
+    isOptimal = true;
+    int32_t bestVar = -1;
+    double largestViol = 0.0;
+    if (nbArcPivotInd >= (int64_t) setNBarc.size()) nbArcPivotInd = 0;
+    if (nbEqfPivotInd >= (int64_t) setNBeqf.size()) nbEqfPivotInd = 0;
+    const int64_t nbArcPivotStart = nbArcPivotInd, nbEqfPivotStart = nbEqfPivotInd;
+    int eqfViolations = 0;
+    bool exhaustedEqfs = setNBeqf.empty();
+    if (!exhaustedEqfs) GNE_TRY(priceSets());
+    while (eqfViolations < 1 && !exhaustedEqfs) {
+        const int32_t v = setNBeqf[(size_t) nbEqfPivotInd];
+        const double rc = eqfRc[(size_t) nbEqfPivotInd];
+        if (violates(v, rc)) {
+            isOptimal = false;
+            ++eqfViolations;
+            const double frc = useWeighted ? fabs(rc) / numOrigArcs[(size_t) (v - A)] : fabs(rc);
+            if (frc > largestViol) { largestViol = frc; bestVar = v; }
+        }
+        nbEqfPivotInd = (nbEqfPivotInd + 1) % (int64_t) setNBeqf.size();
+        exhaustedEqfs = (nbEqfPivotInd == nbEqfPivotStart);
+    }
+    if (!setNBarc.empty()) {
+        // the arc loop: first strictly-largest |rc| among the scanned arcs; it replaces the set only when strictly larger
+        int64_t bestPos = -1, newCursor = nbArcPivotStart, scanned = 0, violations = 0;
+        double bestViol = 0.0;
+        GNE_TRY(gne_price_qs(dev, nbArcPivotStart, (int64_t) numNodes, &bestPos, &bestViol, &newCursor, &scanned, &violations));
+        arcsPriced += (double) scanned;
+        if (violations > 0) isOptimal = false;
+        if (bestPos >= 0 && bestViol > largestViol) { largestViol = bestViol; bestVar = setNBarc[(size_t) bestPos]; }
+        nbArcPivotInd = newCursor;
+    }
+    if ((loopIter % majorIterationLength) > 0) { nbArcPivotInd = nbArcPivotStart; nbEqfPivotInd = nbEqfPivotStart; }
+    *out = bestVar;
+    return GNE_OK;
+}
+
+int EqfSolver::selectEnteringVariable(int32_t *out)                // :36-127
+{
+    if (cyclingDetected) return getRandomVarWithLargeViolation(false, out);
+    const int rule = presolve ? phaseIpivot : phaseIIpivot;
+    switch (rule) {
+      case GNE_LV: return getVarWithLargestViolation(0, false, out);
+      case GNE_LVW: return getVarWithLargestViolation(0, true, out);
+      case GNE_LVA: return getVarWithLargestViolation(1, false, out);
+      case GNE_LVE: return getVarWithLargestViolation(2, false, out);
+      case GNE_FV: return getFirstVarWithViolation(out);
+      case GNE_RV: return getRandomVarWithViolation(out);
+      case GNE_RWV: return getRandomVarWeightedByViolation(out);
+      case GNE_RLV: return getRandomVarWithLargeViolation(false, out);
+      case GNE_RLVW: return getRandomVarWithLargeViolation(true, out);
+      case GNE_CL: return getNextCandidate(false, out);
+      case GNE_CLW: return getNextCandidate(true, out);
+      case GNE_SAA: return getVarBySimAnnealing(true, out);
+      case GNE_SAE: return getVarBySimAnnealing(false, out);
+      case GNE_QS: return quickSelect(false, out);
+      case GNE_QSW: return quickSelect(true, out);
+    }
+    gne_set_error("pivot rule %d is not available with equal-flow sets (SD, CL2, CLW2)", rule);
+    return GNE_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------
+// genneteq.cpp
+// ------------------------------------------------------------------------------------------
+void EqfSolver::initializeStats(bool usePresolve)                  // :123-167
+{
+    presolve = usePresolve;
+    isOptimal = false; isInfeasible = false; isUnbounded = false;
+    loopIter = 0;
+    consecutiveCycles = 0; consecutiveDegenPivots = 0; totalCyclesDetected = 0; totalDegenPivots = 0;
+    cyclingDetected = false;
+    lastEVarInd = -1;
+    itersSinceUpdate = -1;
+    numLargestViolVarsToTrack = 5;
+    majorIterationLength = 3;
+    nbArcPivotInd = 0; nbEqfPivotInd = 0;
+    baselineViolation = lastViolation;
+}
+
+int EqfSolver::setVariableCosts()                                  // :304-323 + the device's cost column
+{
+    if (presolve) for (int64_t i = 0; i < V; ++i) cost[(size_t) i] = isArtificial[(size_t) i] ? 1.0 : 0.0;
+    else for (int64_t i = 0; i < V; ++i) cost[(size_t) i] = actualCost[(size_t) i];
+    if (hostOnly) return GNE_OK;
+    const size_t N = setNBarc.size();
+    std::vector<int32_t> t(N), h(N);
+    std::vector<double> c(N), mu(N);
+    std::vector<int8_t> st(N);
+    for (size_t p = 0; p < N; ++p) { const int32_t a = setNBarc[p]; t[p] = tail[a]; h[p] = head[a]; c[p] = cost[a]; mu[p] = mult[a]; st[p] = setLoc[a]; }
+    GNE_TRY(gne_nb_reset(dev, (int64_t) N, t.data(), h.data(), c.data(), mu.data(), st.data()));
+    costsOnDevice = true;
+    return GNE_OK;
+}
+
+void EqfSolver::checkFeasibility()                                 // :227-288 (useArtificialCosts is empty with SELFLOOPS)
+{
+    isInfeasible = false;
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<int32_t> &set = pass == 0 ? setBarc : setBeqf;
+        for (size_t k = 0; k < set.size(); ++k) {
+            const int32_t v = set[k];
+            if ((isArtificial[v] && flow[v] > TOL) || (flow[v] < 0.0 - TOL) || (flow[v] > UB[v] + TOL)) { isInfeasible = true; return; }
+        }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<int32_t> &set = pass == 0 ? setNBarc : setNBeqf;
+        for (size_t k = 0; k < set.size(); ++k) if (isArtificial[set[k]] && setLoc[set[k]] == U_var) { isInfeasible = true; return; }
+    }
+}
+
+int EqfSolver::verifyOptimality()                                  // gnePotential.cpp:249-288 (its printf report aside)
+{
+    GNE_TRY(computePotentials());
+    return fetchViolators();
+}
+
+int EqfSolver::replayTrace(int draws1, int draws2, int64_t p1, int64_t total, const int32_t *e, const int32_t *l, int64_t *mismatch)
+{
+    if (!hostOnly) { gne_set_error("replayTrace needs a host-only solver"); return GNE_ERR_ARG; }
+    *mismatch = -1;
+    int64_t k = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        const bool pre = (phase == 0);
+        const int draws = pre ? draws1 : draws2;
+        const bool pIwasInfeasible = pre ? false : isInfeasible;
+        initializeStats(pre);
+        GNE_TRY(setVariableCosts());
+        if (!presolve && pIwasInfeasible) { isInfeasible = true; break; }
+        computeFlows(0);
+        const int64_t end = pre ? p1 : total;
+        for (; k < end; ++k) {
+            if ((loopIter % 1000) == 0) computeFlows(2);
+            GNE_TRY(computePotentials());
+            if (cyclingDetected) (void) drand48();
+            else for (int d = 0; d < draws; ++d) (void) drand48();
+            eVar = e[k];
+            if (eVar < 0 || eVar >= V || (setLoc[eVar] != L_var && setLoc[eVar] != U_var)) { *mismatch = k; return GNE_OK; }
+            GNE_TRY(pivot());
+            if (lVar != l[k]) { *mismatch = k; return GNE_OK; }
+            ++loopIter; ++pivots;
+        }
+        if (!cyclingDetected && draws == 2) (void) drand48();
+        computeFlows(0);
+        if (presolve) checkFeasibility();
+        GNE_TRY(computePotentials());
+    }
+    return GNE_OK;
+}
+
+int EqfSolver::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished)   // :60-117
+{
+    if (hostOnly) { gne_set_error("solve needs a device: genneteq_b200 has no CPU fallback"); return GNE_ERR_CUDA; }
+    *finished = 1; *iters = 0;
+    const bool pIwasInfeasible = usePresolve ? false : isInfeasible;
+    initializeStats(usePresolve);
+    GNE_TRY(setVariableCosts());
+    if (!presolve && pIwasInfeasible) { isInfeasible = true; return GNE_OK; }
+    const double t0 = wallNow();
+    computeFlows(0);
+    int64_t budget = maxPivots;
+    while (!isOptimal && !isUnbounded) {
+        if (maxPivots >= 0 && budget == 0) { *finished = 0; break; }
+        if ((loopIter % 1000) == 0) computeFlows(2);
+        const double a = wallNow();
+        GNE_TRY(computePotentials());
+        const double b = wallNow();
+        secsPotentials += b - a;
+        GNE_TRY(selectEnteringVariable(&eVar));
+        const double c = wallNow();
+        secsPricing += c - b;
+        if (eVar != -1) {
+            GNE_TRY(pivot());
+            secsPivot += wallNow() - c;
+            if (lVar != -1) {
+                if (traceLen < traceCap) { traceE[traceLen] = eVar; traceL[traceLen] = lVar; }
+                ++traceLen;
+            }
+            ++loopIter; ++pivots;
+            if (presolve) ++phaseIiters; else ++phaseIIiters;
+            if (budget > 0) --budget;
+        }
+    }
+    if (*finished) {
+        computeFlows(0);
+        if (presolve) checkFeasibility();
+        GNE_TRY(verifyOptimality());
+    }
+    secsTotal += wallNow() - t0;
+    *iters = loopIter;
+    return GNE_OK;
+}
+
+} // namespace gneb200

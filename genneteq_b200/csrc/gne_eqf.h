@@ -8,21 +8,23 @@
 // O(n s) on the host in the reference too - so this engine restates the reference's data flow directly on flat arrays
 // (same member names, same operation order), and keeps on the device what stays data-parallel:
 //   * pricing of the nonbasic arcs   - the same device-resident structure-of-arrays mirror and kernels as at p = 0
-//                                      (gne_price_lv_* / gne_price_first / gne_price_violators);
-//   * pricing of the equal-flow sets - gne_price_eqf (computeEqfRedCost, genneteq.h:321-330: one dense row per set);
+//                                      (gne_price_lv_* / gne_price_qs / gne_price_first / gne_price_violators);
+//   * pricing of the equal-flow sets - gne_price_eqf (computeEqfRedCost, genneteq.h:321-330: one row per set);
 //   * potentials                     - uploaded whole after each computePotentials (all of them can change through the
 //                                      s x s solve).
 // The s x s systems use an LU with partial pivoting in GSL's operation order (gsl_linalg_LU_decomp / _solve of GSL 1.x-2.5
 // with gslcblas' reference dtrsv loops; the reference links -lgsl -lgslcblas, version not pinned): see lu_decomp / lu_solve.
 // Parity is pinned against the unmodified reference compiled with the same restatement of those two GSL calls
-// (the gsl_mini header tree of the test infrastructure), fixtures tests/golden/q_*.npz - "reference + restated GSL", not a GSL build.
+// (the gsl_mini header tree of the test infrastructure), fixtures tests/golden/q_*.npz - "reference + restated GSL", not a
+// GSL build.
 //
-// Pricing rules with sets: LV, LVW, LVA, LVE, FV and the cycling override (RLV / RLVW); the others return
-// GNE_ERR_UNSUPPORTED for p > 0.
+// Pricing rules with sets: every rule id of main.h:17-34 except SD (stale in the reference too) and CL2 / CLW2 (their
+// rebuild interleaves one drand48 draw per scanned variable, gnePivotRules.cpp:651): those return GNE_ERR_UNSUPPORTED.
 #pragma once
 #include "../../include/genneteq_b200.h"
 
 #include <list>
+#include <queue>
 #include <stdint.h>
 #include <utility>
 #include <vector>
@@ -48,7 +50,11 @@ struct EqfInstance {
 class EqfSolver {
   public:
     ~EqfSolver();
-    int initialize(const EqfInstance &g, int cudaDevice);                                    // gneInit.cpp:25-44 (SELFLOOPS)
+    int initialize(const EqfInstance &g, int cudaDevice, bool hostOnlyReplay = false);       // gneInit.cpp:25-44 (SELFLOOPS)
+    // host-only replay of a recorded solve (no device, no pricing): the entering variable of every pivot comes from the
+    // trace; flows, the s x s systems, ratio test, leaving variable, tree surgery and potentials run as in solve() and
+    // the leaving variable is compared (*mismatch = first differing pivot or -1).  draws: drand48 calls per pricing, per phase.
+    int replayTrace(int draws1, int draws2, int64_t p1, int64_t total, const int32_t *e, const int32_t *l, int64_t *mismatch);
     int solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished);           // genneteq.cpp:60-117
     int phaseIpivot = GNE_LVW, phaseIIpivot = GNE_LVW;
 
@@ -69,7 +75,6 @@ class EqfSolver {
   private:
     enum { B_var = 0, L_var = 1, U_var = 2, NIL = 3 };                 // variables.h:23
     enum { T_NONE = 0, T_I = 1, T_II = 2 };                            // variables.h:25
-    enum { THETA_I = -1, NULL_THETA = -2 };
 
     struct ETree {                                                     // trees.h:24-109
         int id = -1;
@@ -79,6 +84,8 @@ class EqfSolver {
         int32_t extraArc = -1;
         std::vector<int32_t> nodesInTree, arcsInTree, threads;
     };
+    struct VarWithViol { int32_t var; double violation; };            // variables.h:210-222
+    struct violcomp { bool operator()(const VarWithViol &a, const VarWithViol &b) const { return a.violation < b.violation; } };
 
     // ---- sizes (variables: arcs 0..A-1 with the artificial self-loops last, then the sets A..A+p-1)
     int numNodes = 0, numSets = 0;
@@ -89,7 +96,8 @@ class EqfSolver {
     bool isOptimal = false, isInfeasible = false, isUnbounded = false;
     int phaseIiters = 0, phaseIIiters = 0, loopIter = 0;
     int consecutiveCycles = 0, consecutiveDegenPivots = 0, totalCyclesDetected = 0, totalDegenPivots = 0;
-    int numLargestViolVarsToTrack = 5;
+    int numLargestViolVarsToTrack = 5, majorIterationLength = 3, itersSinceUpdate = -1;
+    int64_t nbArcPivotInd = 0, nbEqfPivotInd = 0;
     // ---- variables
     std::vector<int32_t> tail, head, setInd, numOrigArcs;
     std::vector<double> mult, UB, cost, actualCost, flow, deltaFlow, flowA0, flowA1;
@@ -101,9 +109,9 @@ class EqfSolver {
     // ---- nodes
     std::vector<double> supply, potential, potA0, potA1, supA0, supA1;
     std::vector<int32_t> potTheta;
-    std::vector<double> swt;                                           // supplyWithThetas: [n * (s + 1)]
-    std::vector<double> fwt;                                           // flowWithThetas of Type II tree arcs: [row * (s + 1)]
-    std::vector<int32_t> fwtRow;                                       // per arc: its row in fwt during a flow computation
+    int S = 1;                                                         // s + 1 of the flow computation under way
+    std::vector<double> swt;                                           // supplyWithThetas: [n * S]
+    std::vector<double> fwt;                                           // flowWithThetas of predArc(j): [n * S], row j
     std::vector<int32_t> memberOfTreeID, depth, thread, pred, predArc;
     std::vector<int8_t> memberOfTreeType;
     std::vector<std::vector<int32_t> > incidentArcs;
@@ -118,13 +126,17 @@ class EqfSolver {
     std::list<std::pair<int32_t, int32_t> > cycleList;
     int lastEVarInd = -1;
     double lastViolation = 100000, baselineViolation = 100000;
+    std::priority_queue<VarWithViol, std::vector<VarWithViol>, violcomp> candidateList;
     uint64_t rand48State = 0;
     double drand48();
     // ---- device
     gne_dev *dev = nullptr;
     int cudaDevice = 0;
+    bool costsOnDevice = false, hostOnly = false;
     std::vector<int64_t> listPos;
     std::vector<double> listViol, eqfRc;
+    std::vector<int32_t> offendingVars;
+    std::vector<double> offendingViol;
     // ---- trace / counters
     int32_t *traceE = nullptr, *traceL = nullptr;
     int64_t traceCap = 0, traceLen = 0, pivots = 0, pivotsTII = 0;
@@ -180,9 +192,17 @@ class EqfSolver {
     int removeFromNB(int32_t v);
     int selectEnteringVariable(int32_t *out);
     int priceSets();                                                   // reduced cost of every nonbasic set -> eqfRc (setNBeqf order)
+    bool violates(int32_t v, double rc) const;
+    double hostRedCost(int32_t v) const;
+    int fetchViolators();                                              // computeReducedCosts(false): offendingVars / offendingViol
     int getVarWithLargestViolation(int order, bool useWeighted, int32_t *out);
     int getFirstVarWithViolation(int32_t *out);
+    int getRandomVarWithViolation(int32_t *out);
+    int getRandomVarWeightedByViolation(int32_t *out);
     int getRandomVarWithLargeViolation(bool useWeighted, int32_t *out);
+    int getVarBySimAnnealing(bool arcsFirst, int32_t *out);
+    int getNextCandidate(bool useWeighted, int32_t *out);
+    int quickSelect(bool useWeighted, int32_t *out);
     // ---- the s x s systems
     static void lu_decomp(std::vector<double> &a, int s, std::vector<int> &perm);
     static void lu_solve(const std::vector<double> &lu, int s, const std::vector<int> &perm, const std::vector<double> &b, std::vector<double> &x);

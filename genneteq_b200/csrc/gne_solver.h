@@ -13,6 +13,7 @@
 // nonbasic records and the pricing result cross PCIe per pivot.
 #pragma once
 #include "gne_forest.h"
+#include "gne_eqf.h"
 #include "../../include/genneteq_b200.h"
 
 #include <list>
@@ -39,6 +40,12 @@ class Graph {
     int initialize(Config *conf);                       // graph.cpp:31-53 (returns gne_status)
     int initializeFromArrays(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub,
                              const double *cost, const double *mult, const double *supply, double bigMIn);
+    // the same with equal-flow sets: eqf[a] = 1-based set of arc a (0: none), as the last field of an `a` line
+    int initializeFromArraysEqf(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub,
+                                const double *cost, const double *mult, const int32_t *eqf, int numSets,
+                                const double *supply, double bigMIn);
+    // what GenNetEq::initializeVars makes of the sets (gneInit.cpp:64-103)
+    void toEqfInstance(EqfInstance &out) const;
     int getNumNodes() const { return numNodes; }
     int64_t getNumArcs() const { return (int64_t) tail.size(); }
     int getNumEqualFlowSets() const { return numEqualFlowSets; }
@@ -48,6 +55,9 @@ class Graph {
     // arcs that exist (capacity > 0, gneInit.cpp:84), sorted by (tail, head)
     std::vector<int32_t> tail, head;
     std::vector<double> cap, cost, mult, supplies;
+    // with equal-flow sets: per kept arc its set (-1: none), and d_r(i) (graph.cpp:403-410), row r = set r, n values each
+    std::vector<int32_t> eqfOf;
+    std::vector<double> eqfNodeVals;
 
   private:
     int numNodes = 0;

@@ -30,7 +30,7 @@ typedef enum {
     GNE_ERR_CAPACITY = 3,      /* caller's output buffer too small; *count still holds the need  */
     GNE_ERR_TREE = 4,          /* basis forest invariant broken (reference: exit(-1), trees.cpp:310-313,327-330,469-472) */
     GNE_ERR_CYCLING = 5,       /* >5 consecutive cycles (reference: exit(-1), gnePivot.cpp:342-345) */
-    GNE_ERR_UNSUPPORTED = 6,   /* equal-flow sets / pivotTII / rule SD: out of scope              */
+    GNE_ERR_UNSUPPORTED = 6,   /* rule SD; with equal-flow sets: CL2 / CLW2, sharding, batches     */
     GNE_ERR_COMM = 7           /* NCCL error                                                      */
 } gne_status;
 
@@ -154,8 +154,7 @@ int gne_price_first(gne_dev *d, int64_t *pos);
 
 /* computeEqfRedCost (genneteq.h:321-330) for p equal-flow variables: rc[k] = cost[k] - sum nodeVals_k[i] * pi[i], the
  * subtractions in node order as the reference's dense loop does them (zero entries change nothing, so the rows are
- * passed sparse: CSR, entries of a row sorted by node).  The first piece of the equal-flow path; the
- * solver mirror still refuses instances with equal-flow sets (Type II pivots and the s x s systems are not built). */
+ * passed sparse: CSR, entries of a row sorted by node).  SURVEY 8 a12; the equal-flow engine calls it every pivot.    */
 int gne_price_eqf(gne_dev *d, int p, const int64_t *rowStart, const int32_t *node, const double *val, const double *cost, double *rc);
 
 /* reduced cost of every position in [lo, hi) (tests, verifyOptimality)                        */
@@ -225,7 +224,17 @@ typedef struct gne_solver gne_solver;
  * the varIndex order of gneInit.cpp:82-107.  bigM as graph.cpp:43, or < 0 to have it computed. */
 int gne_solver_create(gne_solver **out, int cudaDevice, int n, int64_t m, const int32_t *tail, const int32_t *head,
                       const double *ub, const double *cost, const double *mult, const double *supply, double bigM);
-/* the reference's text format (graph.cpp:358-447) read sparsely                               */
+/* The same for an instance WITH equal-flow sets: eqf[a] = 1-based set of arc a, 0 for an arc outside
+ * every set - the last field of an `a` line (graph.cpp:382-419); numSets = the `p` line's fourth number.  Each set is
+ * one variable behind the arc variables (varIndex = arc variables + set, gneInit.cpp:149-162): its flow is the common
+ * flow of its member arcs.  Such an instance runs in the equal-flow engine (Type II trees, pivotTII gnePivot.cpp:122-160,
+ * the s x s systems of gnePotential.cpp:142-214 / gneFlow.cpp:212-256 with GSL's LU order restated); arcs and sets are
+ * priced on the device.  Rules SD, CL2 and CLW2, sharding, batches and the window / progress / forest accessors return
+ * GNE_ERR_UNSUPPORTED for it.  d_r(i) is accumulated in the order the arcs are given (a file: in file order).      */
+int gne_solver_create_eqf(gne_solver **out, int cudaDevice, int n, int64_t m, const int32_t *tail, const int32_t *head,
+                          const double *ub, const double *cost, const double *mult, const int32_t *eqf, int numSets,
+                          const double *supply, double bigM);
+/* the reference's text format (graph.cpp:358-447) read sparsely; a file with equal-flow sets gives the equal-flow engine */
 int gne_solver_create_from_col(gne_solver **out, int cudaDevice, const char *path);
 int gne_solver_destroy(gne_solver *s);
 /* globals phaseIpivot / phaseIIpivot (main.cpp:21-22)                                        */
@@ -251,6 +260,7 @@ int gne_solver_solve_batch_grouped(gne_solver **s, int B, int presolve, int64_t 
 
 int gne_solver_num_nodes(const gne_solver *s);
 int64_t gne_solver_num_vars(const gne_solver *s);
+int gne_solver_num_sets(const gne_solver *s);      /* equal-flow variables (the last ones of the variable vector) */
 double gne_solver_objective(const gne_solver *s);
 int gne_solver_feasible(const gne_solver *s);
 int gne_solver_get_flows(gne_solver *s, double *out);
@@ -293,6 +303,13 @@ int gne_host_replay(int n, int64_t m, const int32_t *tail, const int32_t *head, 
                     const double *mult, const double *supply, double bigM, int drawsPerPricing, int sparseFlows,
                     int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
                     int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective);
+
+/* the same for an instance with equal-flow sets (arguments as gne_solver_create_eqf): Type II trees, pivotTII, both s x s
+ * systems, tree ids - everything but the pricing - against a recorded trace, without a device                     */
+int gne_host_replay_eqf(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub, const double *cost,
+                        const double *mult, const int32_t *eqf, int numSets, const double *supply, double bigM,
+                        int drawsPhaseI, int drawsPhaseII, int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
+                        int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective);
 
 /* the contiguous position range [*lo, *hi) of the nonbasic list (m real arcs) that `rank` of `nranks` prices:
  * boundaries on multiples of 2048, ranges never overlap, *lo == *hi for a rank left without positions

@@ -1,0 +1,169 @@
+"""Equal-flow sets: the equal-flow engine against fixtures written by the unmodified reference
+(tests/golden/q_*.npz, make_eqf_golden.py; the reference compiled against oracle/gsl_mini's restatement of GSL's LU).
+
+CPU part: the host logic - Type II trees, tree ids, pivotTII, the (s+1)-vector flows, both s x s systems, potentials -
+replayed without a device (entering variables from the trace), every leaving variable and the final state compared.
+GPU part: the whole solve with arcs and sets priced on the device, every rule the engine offers, the text loader."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+DRAWS = dict(LV=1, LVW=1, LVA=1, LVE=1, FV=0, RV=1, RWV=1, RLV=1, RLVW=1, CL=0, CLW=0, SAA=2, SAE=2, QS=0, QSW=0)
+FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "q_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def gne():
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import genneteq_b200
+    return genneteq_b200
+
+
+def rules_of(z):
+    return sorted(k[:-2] for k in z.files if k.endswith("_e"))
+
+
+def same(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+def same_scalar(a, b):
+    return a == b or (np.isnan(a) and np.isnan(b))
+
+
+def test_fixtures_present():
+    assert len(FIXTURES) >= 6, FIXTURES
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_eqf_host_logic_replays_reference_traces(gne, name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    n, p = int(z["n"]), int(z["p"])
+    checked = 0
+    for rn in rules_of(z):
+        r1, r2 = rn.split("+") if "+" in rn else (rn, rn)
+        p1, p2 = (int(v) for v in z[rn + "_p"])
+        mm, flows, pots, obj = gne.host_replay_eqf(n, z["tail"], z["head"], z["ub"], z["cost"], z["mult"], z["eqf"], p, z["supply"],
+                                                   -1.0, (DRAWS[r1], DRAWS[r2]), p1, z[rn + "_e"], z[rn + "_l"], len(z[rn + "_flows"]))
+        assert mm == -1, (name, rn, "leaving variable differs at pivot", mm, "of", p1, p2)
+        assert same(flows, z[rn + "_flows"]), (name, rn)
+        assert same(pots, z[rn + "_potentials"]), (name, rn)
+        assert same_scalar(obj, float(z[rn + "_objective"])), (name, rn)
+        checked += 1
+    assert checked >= 2
+
+
+def test_eqf_fixtures_exercise_type_two_pivots():
+    """The fixtures must reach what they are for: sets entering and leaving the basis (pivotTII, gnePivot.cpp:122-160)."""
+    total_in = total_out = 0
+    for name in FIXTURES:
+        z = np.load(os.path.join(GOLD, name + ".npz"))
+        nvars = int(np.sum((z["ub"] > 0.0) & (z["eqf"] == 0))) + int(z["n"])
+        for rn in rules_of(z):
+            total_in += int(np.sum(z[rn + "_e"] >= nvars))
+            total_out += int(np.sum(z[rn + "_l"] >= nvars))
+    assert total_in > 500 and total_out > 500
+
+
+def test_eqf_replay_detects_a_wrong_trace(gne):
+    z = np.load(os.path.join(GOLD, "q_wide_s21.npz"))
+    l = z["LV_l"].copy()
+    k = 40
+    l[k] = l[k] + 1 if l[k] + 1 != z["LV_e"][k] else l[k] + 2
+    mm, *_ = gne.host_replay_eqf(int(z["n"]), z["tail"], z["head"], z["ub"], z["cost"], z["mult"], z["eqf"], int(z["p"]), z["supply"],
+                                 -1.0, 1, int(z["LV_p"][0]), z["LV_e"], l, len(z["LV_flows"]))
+    assert mm == k
+
+
+def test_eqf_arguments_are_validated(gne):
+    z = np.load(os.path.join(GOLD, "q_wide_s21.npz"))
+    bad = z["eqf"].copy()
+    bad[3] = int(z["p"]) + 1                            # names a set beyond the problem line's count
+    with pytest.raises(gne.GneError):
+        gne.host_replay_eqf(int(z["n"]), z["tail"], z["head"], z["ub"], z["cost"], z["mult"], bad, int(z["p"]), z["supply"],
+                            -1.0, 1, 0, z["LV_e"][:0], z["LV_l"][:0], len(z["LV_flows"]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU: the solve itself
+# ------------------------------------------------------------------------------------------------------------------
+def solve_fixture(gne, z, rn, **kw):
+    r1, r2 = rn.split("+") if "+" in rn else (rn, rn)
+    s = gne.Solver(int(z["n"]), z["tail"], z["head"], z["ub"], z["cost"], z["mult"], z["supply"], rule1=r1, rule2=r2,
+                   eqf=z["eqf"], num_sets=int(z["p"]), **kw)
+    return s
+
+
+def check_against(z, rn, s, p1, p2):
+    assert (p1, p2) == tuple(int(v) for v in z[rn + "_p"]), rn
+    e, l = s.trace
+    assert np.array_equal(e, z[rn + "_e"]) and np.array_equal(l, z[rn + "_l"]), rn
+    assert same_scalar(s.objective, float(z[rn + "_objective"])), rn
+    assert same(s.flows(), z[rn + "_flows"]), rn
+    assert same(s.potentials(), z[rn + "_potentials"]), rn
+    assert s.feasible == bool(int(z[rn + "_feasible"])), rn
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FIXTURES)
+def test_eqf_solve_equals_reference_every_rule(gne, name):
+    """Arcs priced by the LV / QS / first-violator / compaction kernels, sets by k_price_eqf, selection state carried from
+    one to the other on the host: identical pivots, flows, potentials and objective for every rule of the fixture."""
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    for rn in rules_of(z):
+        s = solve_fixture(gne, z, rn)
+        assert s.num_sets == int(z["p"])
+        p1, p2 = s.solve_both()
+        check_against(z, rn, s, p1, p2)
+        c = s.counters()
+        assert c["launches"] > 0 and c["arcs_priced"] > 0
+        s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["q_wide_s21", "q_near1_s24"])
+def test_eqf_text_loader(gne, tmp_path, name):
+    """The reference's text format with sets (graph.cpp:382-419): d_r(i) summed in FILE order (the second fixture's `a` lines
+    are shuffled), variables numbered in (tail, head) order."""
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    col = tmp_path / "inst.col"
+    col.write_bytes(z["col_text"].tobytes())
+    for rn in ("LV", "QS"):
+        s = gne.Solver(col_path=str(col), rule1=rn)
+        assert s.num_sets == int(z["p"]) and s.n == int(z["n"])
+        p1, p2 = s.solve_both()
+        check_against(z, rn, s, p1, p2)
+        s.close()
+
+
+@pytest.mark.gpu
+def test_eqf_unsupported_pieces_say_so(gne):
+    z = np.load(os.path.join(GOLD, "q_wide_s21.npz"))
+    for rn in ("SD", "CL2", "CLW2"):
+        s = solve_fixture(gne, z, rn)
+        with pytest.raises(gne.GneError) as ei:
+            s.solve(True)
+        assert ei.value.code == gne.GNE_ERR_UNSUPPORTED
+        s.close()
+    s = solve_fixture(gne, z, "LV")
+    with pytest.raises(gne.GneError):
+        s.forest()
+    s.close()
+
+
+@pytest.mark.gpu
+def test_eqf_pivot_budget_and_resume(gne):
+    """A solve cut by the pivot budget continues to the same trace."""
+    z = np.load(os.path.join(GOLD, "q_pow2_s23.npz"))
+    s = solve_fixture(gne, z, "LV")
+    it, fin = s.solve(True, 50)
+    assert (it, fin) == (50, False)
+    e, l = s.trace
+    assert np.array_equal(e, z["LV_e"][:50]) and np.array_equal(l, z["LV_l"][:50])
+    s.close()
