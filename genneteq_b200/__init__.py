@@ -133,6 +133,8 @@ SIGNATURES = {
                                       _f64p, _i64p, _i64p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gne_write_col": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
     "gne_read_col": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), _i64p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p]),
+    "gne_read_col_eqf": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), _i64p, C.POINTER(C.c_int), _i32p, _i32p, _f64p, _f64p, _f64p, _i32p,
+                                   _f64p, _f64p]),
     "gne_write_bin": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
     "gne_read_bin_header": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), _i64p]),
     "gne_read_bin": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]),
@@ -211,6 +213,18 @@ def read_instance(path, binary=False):
     if not binary:
         out["big_m"] = big.value
     return out
+
+
+def read_instance_eqf(path):
+    """A text instance that may hold equal-flow sets (gne_read_col_eqf): read_instance's dict plus eqf, num_sets."""
+    n = C.c_int(0); m = C.c_int64(0); p = C.c_int(0); big = C.c_double(0)
+    _ck(lib.gne_read_col_eqf(path.encode(), C.byref(n), C.byref(m), C.byref(p), None, None, None, None, None, None, None,
+                             C.byref(big)), "gne_read_col_eqf")
+    t = np.empty(m.value, np.int32); h = np.empty(m.value, np.int32); q = np.empty(m.value, np.int32)
+    ub = np.empty(m.value); c = np.empty(m.value); mu = np.empty(m.value); s = np.empty(n.value)
+    _ck(lib.gne_read_col_eqf(path.encode(), C.byref(n), C.byref(m), C.byref(p), _p(t, _i32p), _p(h, _i32p), _p(ub, _f64p),
+                             _p(c, _f64p), _p(mu, _f64p), _p(q, _i32p), _p(s, _f64p), C.byref(big)), "gne_read_col_eqf")
+    return dict(n=n.value, tail=t, head=h, ub=ub, cost=c, mult=mu, supply=s, eqf=q, num_sets=p.value, big_m=big.value)
 
 
 class Device:

@@ -250,6 +250,7 @@ extern "C" int gne_read_col(const char *path, int *n, int64_t *m, int32_t *tail,
     Graph g;
     int rc = g.initialize(&conf);
     if (rc) return rc;
+    if (g.getNumEqualFlowSets() > 0) { gne_set_error("gne_read_col: the file has equal-flow sets (use gne_read_col_eqf)"); return GNE_ERR_UNSUPPORTED; }
     const int64_t cnt = g.getNumArcs();
     if (tail) {
         if (*m < cnt || *n < g.getNumNodes()) { gne_set_error("gne_read_col: arrays too small"); return GNE_ERR_CAPACITY; }
@@ -257,6 +258,31 @@ extern "C" int gne_read_col(const char *path, int *n, int64_t *m, int32_t *tail,
         for (int i = 0; i < g.getNumNodes(); ++i) supply[i] = g.supply(i);
     }
     *n = g.getNumNodes(); *m = cnt;
+    if (bigM) *bigM = g.getBigM();
+    return GNE_OK;
+    });
+}
+
+extern "C" int gne_read_col_eqf(const char *path, int *n, int64_t *m, int *numSets, int32_t *tail, int32_t *head, double *ub,
+                                double *cost, double *mult, int32_t *eqf, double *supply, double *bigM)
+{
+    return guarded("gne_read_col_eqf", [&]() -> int {
+    if (!n || !m || !numSets) { gne_set_error("gne_read_col_eqf: bad argument"); return GNE_ERR_ARG; }
+    Config conf;
+    conf.inFile = path;
+    Graph g;
+    int rc = g.initialize(&conf);
+    if (rc) return rc;
+    const int64_t cnt = g.getNumArcs();
+    if (tail) {
+        if (*m < cnt || *n < g.getNumNodes()) { gne_set_error("gne_read_col_eqf: arrays too small"); return GNE_ERR_CAPACITY; }
+        for (int64_t a = 0; a < cnt; ++a) {
+            tail[a] = g.tail[a]; head[a] = g.head[a]; ub[a] = g.cap[a]; cost[a] = g.cost[a]; mult[a] = g.mult[a];
+            if (eqf) eqf[a] = g.eqfOf.empty() ? 0 : g.eqfOf[(size_t) a] + 1;
+        }
+        for (int i = 0; i < g.getNumNodes(); ++i) supply[i] = g.supply(i);
+    }
+    *n = g.getNumNodes(); *m = cnt; *numSets = g.getNumEqualFlowSets();
     if (bigM) *bigM = g.getBigM();
     return GNE_OK;
     });

@@ -1276,7 +1276,7 @@ extern "C" int gne_price_eqf(gne_dev *d, int p, const int64_t *rowStart, const i
     for (int64_t q = 0; q < nnz; ++q) if (node[q] < 0 || node[q] >= d->n) { gne_set_error("gne_price_eqf: node out of range"); return GNE_ERR_ARG; }
     CK(cudaSetDevice(d->device));
     int rcf = gne_dev_flush(d); if (rcf) return rcf;
-    const size_t bytes = 8 * (size_t) (p + 1) + 12 * (size_t) nnz + 16 * (size_t) p + 64;
+    const size_t bytes = 8 * (size_t) (p + 1) + 12 * (size_t) nnz + 16 * (size_t) p + 8 + 64;
     rcf = ensure_stage(d, bytes); if (rcf) return rcf;
     if (d->stageInFlight) { CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false; }
     char *h = (char *) d->stageHost;
@@ -1285,13 +1285,15 @@ extern "C" int gne_price_eqf(gne_dev *d, int p, const int64_t *rowStart, const i
     const size_t oVal = o; if (nnz) memcpy(h + o, val, 8 * (size_t) nnz); o += 8 * (size_t) nnz;
     const size_t oCost = o; memcpy(h + o, cost, 8 * (size_t) p); o += 8 * (size_t) p;
     const size_t oRc = o; o += 8 * (size_t) p;
+    const size_t oCnt = o; memset(h + o, 0, 8); o += 8;       // non-finite potentials (see k_price_eqf)
     const size_t oNode = o; if (nnz) memcpy(h + o, node, 4 * (size_t) nnz); o += 4 * (size_t) nnz;
     CK(cudaMemcpyAsync(d->stageDev, h, o, cudaMemcpyHostToDevice, d->stream));
     char *g = (char *) d->stageDev;
+    k_count_nonfinite<<<blocks_for(d->n, 256), 256, 0, d->stream>>>(d->n, d->pi, (unsigned long long *) (g + oCnt));
     k_price_eqf<<<blocks_for(p, 128), 128, 0, d->stream>>>(p, (const int64_t *) (g + oRow), (const int32_t *) (g + oNode), (const double *) (g + oVal),
-                                                          (const double *) (g + oCost), d->pi, (double *) (g + oRc));
+                                                          (const double *) (g + oCost), d->pi, (const unsigned long long *) (g + oCnt), (double *) (g + oRc));
     CK(cudaGetLastError());
-    ++d->launches;
+    d->launches += 2;
     CK(cudaMemcpyAsync(rc, g + oRc, 8 * (size_t) p, cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->h2dBytes += (int64_t) o; d->d2hBytes += 8 * p;

@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stack>
 #include <time.h>
@@ -1282,16 +1284,23 @@ int EqfSolver::solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *f
     const double t0 = wallNow();
     computeFlows(0);
     int64_t budget = maxPivots;
+    // GNE_EQF_DEBUG=k: a line per stage from pivot k on (stderr; which call a stuck solve sits in)
+    const char *dbgEnv = getenv("GNE_EQF_DEBUG");
+    const long dbgFrom = dbgEnv ? atol(dbgEnv) : -1;
     while (!isOptimal && !isUnbounded) {
         if (maxPivots >= 0 && budget == 0) { *finished = 0; break; }
         if ((loopIter % 1000) == 0) computeFlows(2);
+        const bool dbg = dbgFrom >= 0 && loopIter >= dbgFrom;
+        if (dbg) fprintf(stderr, "[eqf %d] potentials (s = %zu, trees %zu + %zu)\n", loopIter, setBeqf.size(), setBtI.size(), setBtII.size());
         const double a = wallNow();
         GNE_TRY(computePotentials());
         const double b = wallNow();
         secsPotentials += b - a;
+        if (dbg) fprintf(stderr, "[eqf %d] pricing (rule %d, cycling %d)\n", loopIter, presolve ? phaseIpivot : phaseIIpivot, (int) cyclingDetected);
         GNE_TRY(selectEnteringVariable(&eVar));
         const double c = wallNow();
         secsPricing += c - b;
+        if (dbg) fprintf(stderr, "[eqf %d] entering %d, optimal %d, objective %.17g\n", loopIter, eVar, (int) isOptimal, flowCost);
         if (eVar != -1) {
             GNE_TRY(pivot());
             secsPivot += wallNow() - c;

@@ -518,15 +518,32 @@ k_reduced_costs(NbView nb, const double *__restrict__ pi, int64_t lo, int64_t hi
 // x - 0 * pi == x exactly, so the sparse row (entries sorted by node) subtracted in order gives the same bits.  The sum
 // is order-dependent, so one thread walks one row; p (the number of sets) is small and rows are short.
 // ------------------------------------------------------------------------------------------
+// The reference's loop is DENSE (genneteq.h:324-326): a node outside the set still contributes 0 * pi[i], which is NaN
+// when pi[i] is NaN or infinite - and the reference does reach such states (a singular s x s system).  The sparse walk
+// therefore counts the non-finite potentials it met; if the potential vector holds more of them (k_count_nonfinite), a
+// zero entry would have multiplied one and the dense loop's result is NaN.
+__global__ void k_count_nonfinite(int n, const double *__restrict__ pi, unsigned long long *__restrict__ count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && !isfinite(pi[i]);
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long) __popc(m));
+}
+
 __global__ void k_price_eqf(int p, const int64_t *__restrict__ rowStart, const int32_t *__restrict__ node,
                             const double *__restrict__ val, const double *__restrict__ cost, const double *__restrict__ pi,
-                            double *__restrict__ rc)
+                            const unsigned long long *__restrict__ nonFinite, double *__restrict__ rc)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= p) return;
     double x = cost[k];
-    for (int64_t q = rowStart[k]; q < rowStart[k + 1]; ++q) x = __dsub_rn(x, __dmul_rn(val[q], pi[node[q]]));
-    rc[k] = x;
+    unsigned long long met = 0;
+    for (int64_t q = rowStart[k]; q < rowStart[k + 1]; ++q) {
+        const double v = pi[node[q]];
+        if (!isfinite(v)) ++met;
+        x = __dsub_rn(x, __dmul_rn(val[q], v));
+    }
+    rc[k] = (*nonFinite > met) ? __longlong_as_double(0x7ff8000000000000ll) : x;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -330,6 +330,11 @@ int gne_write_col(const char *path, int n, int64_t m, const int32_t *tail, const
                   const double *cost, const double *mult, const double *supply);
 int gne_read_col(const char *path, int *n, int64_t *m, int32_t *tail, int32_t *head, double *ub, double *cost,
                  double *mult, double *supply, double *bigM);
+/* the same for a file with equal-flow sets (gne_read_col answers GNE_ERR_UNSUPPORTED for one): eqf[a] = 1-based set of
+ * arc a or 0, *numSets = the problem line's count.  (d_r(i) is summed in file order only by gne_solver_create_from_col;
+ * the arrays come back in (tail, head) order.)                                                                  */
+int gne_read_col_eqf(const char *path, int *n, int64_t *m, int *numSets, int32_t *tail, int32_t *head, double *ub,
+                     double *cost, double *mult, int32_t *eqf, double *supply, double *bigM);
 int gne_write_bin(const char *path, int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub,
                   const double *cost, const double *mult, const double *supply);
 int gne_read_bin_header(const char *path, int *n, int64_t *m);

@@ -90,6 +90,22 @@ def test_eqf_arguments_are_validated(gne):
                             -1.0, 1, 0, z["LV_e"][:0], z["LV_l"][:0], len(z["LV_flows"]))
 
 
+@pytest.mark.parametrize("name", ["q_wide_s21", "q_near1_s24"])
+def test_eqf_text_reader_returns_the_set_column(gne, tmp_path, name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    col = tmp_path / "inst.col"
+    col.write_bytes(z["col_text"].tobytes())
+    r = gne.read_instance_eqf(str(col))
+    assert (r["n"], r["num_sets"]) == (int(z["n"]), int(z["p"]))
+    keep = z["ub"] > 0.0
+    for k in ("tail", "head", "ub", "cost", "mult", "eqf"):
+        assert np.array_equal(r[k], z[k][keep]), k
+    assert np.array_equal(r["supply"], z["supply"])
+    with pytest.raises(gne.GneError) as ei:
+        gne.read_instance(str(col))
+    assert ei.value.code == gne.GNE_ERR_UNSUPPORTED
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU: the solve itself
 # ------------------------------------------------------------------------------------------------------------------

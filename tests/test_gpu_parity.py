@@ -463,6 +463,17 @@ def test_equal_flow_reduced_costs_match_the_dense_loop(gne):
     d.pot_set_all(pi)
     got = d.price_eqf(row_start, node, val, cost)
     assert np.array_equal(got, exp)
+    # non-finite potentials (the reference reaches them through a singular s x s system): the dense loop multiplies them by
+    # the zero entries too (0 * inf = NaN), so a row that does not touch the bad node must come out NaN all the same, a
+    # row whose only bad node carries a non-zero entry keeps its signed infinity
+    for bad_nodes, bad_vals in (([123], [np.inf]), ([123, 4000], [np.nan, -np.inf]), ([int(rows[9][0])], [np.inf])):
+        pi2 = pi.copy()
+        pi2[bad_nodes] = bad_vals
+        oracle_lib().orc_price_eqf_dense(p, n, dp(np.ascontiguousarray(dense)), dp(cost), dp(pi2), dp(exp))
+        d.pot_set_all(pi2)
+        got = d.price_eqf(row_start, node, val, cost)
+        assert np.array_equal(got, exp, equal_nan=True), (bad_nodes, got[:12], exp[:12])
+        assert np.isnan(got[3]) and np.isnan(exp[3])                # the empty row
     d.close()
 
 

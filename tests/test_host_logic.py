@@ -237,7 +237,9 @@ print("FLOW-CHECK-OK")
     ("p efpgn 2 2 0\na 1 2 0.0 5.0 1.0 1.0 0\nn 1 1\nn 2 -1\n", 2),             # fewer arcs than announced
     ("p efpgn 2 1 0\na 1 2 0.0 5.0 1.0\nn 1 1\nn 2 -1\n", 2),                   # short arc line
     ("p efpgn 2 1 0\na 1 2 0.0 5.0 1.0 1.0 0\nn 7 1\n", 2),                     # node line out of range
-    ("p efpgn 2 1 1\na 1 2 0.0 5.0 1.0 1.0 1\nn 1 1\nn 2 -1\n", 6),             # equal-flow sets: GNE_ERR_UNSUPPORTED
+    ("p efpgn 2 1 1\na 1 2 0.0 5.0 1.0 1.0 1\nn 1 1\nn 2 -1\n", 6),             # equal-flow sets: gne_read_col has no column for them
+    ("p efpgn 2 1 1\na 1 2 0.0 5.0 1.0 1.0 2\nn 1 1\nn 2 -1\n", 2),             # arc names a set beyond the problem line's count
+    ("p efpgn 2 1 -3\n", 2),                                                   # negative set count
     ("p efpgn -1 0 0\n", 2),                                                    # negative node count (no exception across the C ABI)
     ("p efpgn 0 0 0\n", 2),
     ("p efpgn 3 -5 0\n", 2),                                                    # negative arc count
