@@ -382,6 +382,7 @@ def b200_arm(args):
     # ---- device-resident steps: K x (finalize + pricing pass + reduction [+ exchange]), CUDA events
     flush = (25.0 * N / world + 8 * n) < 200e6  # per-GPU working set not larger than L2 => flush between steps
     qs_arcs = None
+    burst_ms = None
     if rule.startswith("QS") and world == 1:
         # the block rule's own kernels (k_qs_tiles + k_qs_finish per window), as the solver issues them
         dev.bench_price_qs(max(args.warmup, 3), n, flush)
@@ -393,6 +394,8 @@ def b200_arm(args):
         barrier()
         dbg("device warm-up steps done")
         ms_step, ms_tiles = dev.bench_price_lv(args.steps, flush)
+        # the same launch in a burst (one event pair around all of them): what the per-launch event bracket adds
+        burst_ms = dev.bench_price_lv_burst(args.steps) if (world == 1 and not flush) else None
     barrier()
     dbg("device steps done: kernel ms mean %.4f min %.4f max %.4f | step ms mean %.4f min %.4f max %.4f" % (
         ms_tiles.mean(), ms_tiles.min(), ms_tiles.max(), ms_step.mean(), ms_step.min(), ms_step.max()))
@@ -444,6 +447,10 @@ def b200_arm(args):
                      "traffic": ncu_traffic(args.workload, world, lv_kernel), "kernel": lv_kernel, "kernel_ms": tiles_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
     }
+    if burst_ms:
+        # informational: `achieved` / `frac` above stay on the per-launch bracket (kernel_ms)
+        line["roofline"]["kernel_ms_in_a_burst"] = burst_ms
+        line["roofline"]["frac_in_a_burst"] = alg_bytes / (burst_ms * 1e-3) / 1e9 / peak
     if qs_arcs:
         line["block_rule"] = {"arcs_covered_by_kernels_per_pass": qs_arcs[2], "arcs_consumed_by_rule_per_pass": qs_arcs[1] / args.steps,
                               "note": "value / roofline count the arcs the window kernels priced; a pass = window kernel + finish kernel per window"}
@@ -574,9 +581,10 @@ def batch_arm(args):
     if args.batch_threads > 0:
         nthreads = args.batch_threads
     elif per > 0:
-        # grouped launches: a few threads per rank are enough (a thread pivots one instance while its others are priced);
-        # leave cores to the other ranks of the node
-        nthreads = max(1, min(B // max(per // 2, 1), max(2, cores // max(world, 1) - 1), 8))
+        # grouped launches: ONE host thread per rank drives all B instances (it pivots one while the others are priced).
+        # Measured on one GPU, 32 instances: 1 thread 118 k pivots/s, 2 threads 57 k, 4 threads 76 k, 8 threads 116 k - and with
+        # 3 threads per rank on an 8-GPU box (32 cores) 22 k per rank: the threads' launch groups take turns on the device
+        nthreads = 1
     else:
         nthreads = min(B, cores)
     bstats = {}

@@ -79,6 +79,7 @@ SIGNATURES = {
     "gne_dev_set_stream_ctas": (C.c_int, [_vp, C.c_int]),
     "gne_dev_launch_count": (C.c_int64, [_vp]),
     "gne_bench_price_lv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p]),
+    "gne_bench_price_lv_burst": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
     "gne_bench_price_qs": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _f32p, _i64p, _i64p]),
     "gne_bench_lv_groups": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _i64p]),
     "gne_lv_group_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int]),
@@ -399,6 +400,12 @@ class Device:
                                    _p(mt, _f32p)), "gne_bench_price_lv")
         return ms, mt
 
+
+    def bench_price_lv_burst(self, reps, with_finalize=2):
+        """ms per launch of `reps` LV passes queued back to back between one pair of events (single GPU)."""
+        ms = np.zeros(1, np.float32)
+        _ck(lib.gne_bench_price_lv_burst(self.h, reps, int(with_finalize), _p(ms, _f32p)), "gne_bench_price_lv_burst")
+        return float(ms[0]) / reps
 
     def bench_price_qs(self, reps, want, flush_l2=False):
         """`reps` quickSelect passes, device-timed: (ms per pass, arcs the kernels covered, arcs the rule consumed)."""

@@ -1576,6 +1576,30 @@ extern "C" int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFin
     return GNE_OK;
 }
 
+// The same pass `reps` times back to back between ONE pair of events (no event, flush or host work between the launches):
+// the average duration of a launch in a burst - the front end prepares launch k+1 while launch k runs, so this is the
+// kernel without the per-launch event bracket of gne_bench_price_lv.  Single GPU only; L2 is not flushed (configs[2] and
+// larger stream more than L2 holds).
+extern "C" int gne_bench_price_lv_burst(gne_dev *d, int reps, int withFinalize, float *msTotal)
+{
+    if (!d || reps <= 0 || !msTotal) { gne_set_error("gne_bench_price_lv_burst: bad argument"); return GNE_ERR_ARG; }
+    if (d->nranks > 1) { gne_set_error("gne_bench_price_lv_burst: single GPU only"); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(d->device));
+    int rc = gne_dev_flush(d); if (rc) return rc;
+    if (!d->ev2) { CK(cudaEventCreate(&d->ev2)); CK(cudaEventCreate(&d->ev3)); }
+    const bool replay = withFinalize == 2 && d->haveLastSmall && use_stream_kernel(d);
+    for (int i = -3; i < reps; ++i) {                       // three untimed launches first
+        if (i == 0) CK(cudaEventRecord(d->ev2, d->stream));
+        rc = launch_lv_pass(d, d->lvRes, nullptr, nullptr, true, replay ? &d->lastSmall : nullptr);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(d->ev3, d->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
+    CK(cudaEventElapsedTime(msTotal, d->ev2, d->ev3));
+    return GNE_OK;
+}
+
 // The block rule's device leg: `reps` quickSelect passes as the solver issues them (window kernel + finish kernel per
 // window, the cursor advancing by what each pass scanned), each pass timed with CUDA events around its kernels.
 // arcsLaunched[i] = arcs the kernels of pass i were launched over (whole windows), arcsScanned[i] = what the rule consumed.

@@ -157,6 +157,7 @@ void EqfSolver::convertTIItoTI(ETree *t, int32_t av)               // :275-288
     removeTree(t);
     setTreeIDAndType(t, newID, T_I);
     t->extraArc = av;
+    t->potDirty = true;                                 // (theta comes from the new extra arc even when the rooting stays)
     setBtI.push_back(t);
 }
 
@@ -198,6 +199,7 @@ void EqfSolver::mergeTxAndTII(ETree *tX, ETree *tII, int32_t av)   // :366-392
     incidentArcs[tail[av]].push_back(av);
     incidentArcs[head[av]].push_back(av);
     tX->upToDate = false;
+    tX->potDirty = true;
     delete tII;
 }
 
@@ -219,6 +221,7 @@ void EqfSolver::expandTreeUsingArc(ETree *t, int32_t av)           // :395-428 (
         t->extraArc = av;
     }
     t->upToDate = false;
+    t->potDirty = true;
 }
 
 int EqfSolver::removeFromTrees(int32_t av)                         // :450-494
@@ -288,7 +291,7 @@ void EqfSolver::updateTrees()                                      // :572-591
 {
     for (size_t k = 0; k < setBtI.size(); ++k) {
         ETree *t = setBtI[k];
-        if (!t->upToDate) { t->root = tail[t->extraArc]; initializeTreeIndices(t); t->upToDate = true; }
+        if (!t->upToDate) { t->root = tail[t->extraArc]; initializeTreeIndices(t); t->upToDate = true; t->potDirty = true; }
     }
     for (size_t k = 0; k < setBtII.size(); ++k) {
         ETree *t = setBtII[k];
@@ -437,14 +440,33 @@ void EqfSolver::lu_solve(const std::vector<double> &lu, int s, const std::vector
 // ------------------------------------------------------------------------------------------
 int EqfSolver::computePotentials()                                 // :28-61
 {
+    // The reference recomputes every tree every iteration.  A Type I tree's potentials depend only on its own arcs, rooting,
+    // extra arc and costs: untouched since the last call (potDirty) they would come out bit for bit the same, so the tree is
+    // skipped.  Type II trees are coupled through the s x s system and are always recomputed.
+    upNodes.clear();
     for (size_t k = 0; k < setBtI.size(); ++k) {
-        computePotentialsInTermsOfRoot(setBtI[k]);
-        finalizePotentialsTypeI(setBtI[k]);
+        ETree *t = setBtI[k];
+        if (!t->potDirty) continue;
+        computePotentialsInTermsOfRoot(t);
+        finalizePotentialsTypeI(t);
+        t->potDirty = false;
+        upNodes.insert(upNodes.end(), t->nodesInTree.begin(), t->nodesInTree.end());
     }
-    for (size_t k = 0; k < setBtII.size(); ++k) computePotentialsInTermsOfRoot(setBtII[k]);
+    for (size_t k = 0; k < setBtII.size(); ++k) {
+        computePotentialsInTermsOfRoot(setBtII[k]);
+        upNodes.insert(upNodes.end(), setBtII[k]->nodesInTree.begin(), setBtII[k]->nodesInTree.end());
+    }
     if (!setBeqf.empty()) computePotentialsWithEqFlowSets();
-    // the device prices against these: all of them can change in one pivot (the s x s solve couples every type II tree)
-    if (!hostOnly) GNE_TRY(gne_pot_set_all(dev, potential.data()));
+    if (hostOnly) return GNE_OK;
+    // the device prices against these; only the rewritten ones travel (all of them when that is most of the vector)
+    if (!potsOnDevice || upNodes.size() * 2 > (size_t) numNodes) {
+        GNE_TRY(gne_pot_set_all(dev, potential.data()));
+        potsOnDevice = true;
+    } else if (!upNodes.empty()) {
+        upPi.resize(upNodes.size());
+        for (size_t q = 0; q < upNodes.size(); ++q) upPi[q] = potential[(size_t) upNodes[q]];
+        GNE_TRY(gne_pot_set(dev, (int64_t) upNodes.size(), upNodes.data(), upPi.data()));
+    }
     return GNE_OK;
 }
 
@@ -1207,6 +1229,7 @@ int EqfSolver::setVariableCosts()                                  // :304-323 +
 {
     if (presolve) for (int64_t i = 0; i < V; ++i) cost[(size_t) i] = isArtificial[(size_t) i] ? 1.0 : 0.0;
     else for (int64_t i = 0; i < V; ++i) cost[(size_t) i] = actualCost[(size_t) i];
+    for (size_t k = 0; k < setBtI.size(); ++k) setBtI[k]->potDirty = true;       // every potential depends on the costs
     if (hostOnly) return GNE_OK;
     const size_t N = setNBarc.size();
     std::vector<int32_t> t(N), h(N);

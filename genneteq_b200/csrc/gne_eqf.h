@@ -83,6 +83,9 @@ class EqfSolver {
         bool upToDate = false;
         int32_t extraArc = -1;
         std::vector<int32_t> nodesInTree, arcsInTree, threads;
+        // not in the reference: a Type I tree whose arcs, rooting, extra arc and costs did not change since its potentials
+        // were last computed would get the same bits again (they depend on nothing else) - it is skipped
+        bool potDirty = true;
     };
     struct VarWithViol { int32_t var; double violation; };            // variables.h:210-222
     struct violcomp { bool operator()(const VarWithViol &a, const VarWithViol &b) const { return a.violation < b.violation; } };
@@ -132,9 +135,11 @@ class EqfSolver {
     // ---- device
     gne_dev *dev = nullptr;
     int cudaDevice = 0;
-    bool costsOnDevice = false, hostOnly = false;
+    bool costsOnDevice = false, hostOnly = false, potsOnDevice = false;
     std::vector<int64_t> listPos;
     std::vector<double> listViol, eqfRc;
+    std::vector<int32_t> upNodes;                                      // nodes whose potential the last computePotentials rewrote
+    std::vector<double> upPi;
     std::vector<int32_t> offendingVars;
     std::vector<double> offendingViol;
     // ---- trace / counters

@@ -191,6 +191,10 @@ int gne_dev_cuda_device(const gne_dev *d);
  * between steps, outside the events.                                                          */
 int gne_bench_price_lv(gne_dev *d, int reps, int flushL2, int withFinalize, float *msStep, float *msTiles);
 
+/* the LV pass `reps` times back to back between ONE pair of events: *msTotal / reps = the average duration of a launch in
+ * a burst (no per-launch event bracket; single GPU)                                                              */
+int gne_bench_price_lv_burst(gne_dev *d, int reps, int withFinalize, float *msTotal);
+
 /* the same for the block rule: `reps` quickSelect passes as gne_price_qs issues them (cursor advancing), each timed
  * with CUDA events around its kernels; arcsLaunched = arcs the kernels covered, arcsScanned = arcs the rule consumed */
 int gne_bench_price_qs(gne_dev *d, int reps, int flushL2, int64_t want, float *msStep, int64_t *arcsLaunched, int64_t *arcsScanned);
