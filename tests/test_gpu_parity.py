@@ -383,9 +383,13 @@ def test_col_file_loader_and_error_codes(gne, tmp_path):
     s.close()
     bad = str(tmp_path / "bad.col")
     open(bad, "w").write("p efpgn 3 2 1\na 1 2 0.0 5.0 1.0 1.0 1\na 2 3 0.0 5.0 1.0 1.0 0\nn 1 1\nn 2 0\nn 3 -1\n")
-    with pytest.raises(gne.GneError) as ei:
+    s = gne.Solver(col_path=bad)                         # a file with an equal-flow set loads into the equal-flow engine (tests/test_eqf.py)
+    assert s.num_sets == 1 and s.M == 1 + 3 + 1          # one arc outside the set, three artificial self-loops, the set
+    s.close()
+    open(bad, "w").write("p efpgn 3 2 1\na 1 2 0.0 5.0 1.0 1.0 2\na 2 3 0.0 5.0 1.0 1.0 0\nn 1 1\nn 2 0\nn 3 -1\n")
+    with pytest.raises(gne.GneError) as ei:              # names set 2 of 1
         gne.Solver(col_path=bad)
-    assert ei.value.code == 6                            # GNE_ERR_UNSUPPORTED: equal-flow sets
+    assert ei.value.code == 2
     with pytest.raises(gne.GneError):
         gne.Solver(col_path=str(tmp_path / "missing.col"))
     with pytest.raises(gne.GneError):                    # rule SD is out of scope
