@@ -581,14 +581,15 @@ def batch_arm(args):
     if args.batch_threads > 0:
         nthreads = args.batch_threads
     elif per > 0:
-        # grouped launches: ONE host thread per rank drives all B instances (it pivots one while the others are priced).
-        # Measured on one GPU, 32 instances: 1 thread 118 k pivots/s, 2 threads 57 k, 4 threads 76 k, 8 threads 116 k - and with
-        # 3 threads per rank on an 8-GPU box (32 cores) 22 k per rank: the threads' launch groups take turns on the device
-        nthreads = 1
+        # grouped launches: two host threads per rank drive the B instances (each pivots one instance while the others are
+        # priced).  Measured on one GPU, 32 instances, windows aligned: 1 thread 129 k pivots/s, 2 threads 186 k (the device
+        # leg's own pace), 8 threads 180 k
+        nthreads = 2
     else:
         nthreads = min(B, cores)
     bstats = {}
-    gne.solve_batch(solvers, True, W + args.steps, threads=nthreads, per_launch=per, stats=bstats)
+    # (every instance waits at pivot W for the others: the timed windows then run side by side whatever the first pivots cost)
+    gne.solve_batch(solvers, True, W + args.steps, threads=nthreads, per_launch=per, stats=bstats, align_pivot=W)
     wins = [s.window() for s in solvers]
     edges = [s.window_edges for s in solvers]
     # instance 0 of rank 0 is the (seed 1000) instance the reference's prefix fixture was written for

@@ -110,6 +110,8 @@ SIGNATURES = {
     "gne_solver_trace_len": (C.c_int64, [_vp]),
     "gne_solver_solve_batch": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, C.c_int, _i64p, C.POINTER(C.c_int)]),
     "gne_solver_solve": (C.c_int, [_vp, C.c_int, C.c_int64, _i64p, C.POINTER(C.c_int)]),
+    "gne_solver_solve_batch_ex": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, _i64p,
+                                            C.POINTER(C.c_int), _i64p]),
     "gne_solver_num_nodes": (C.c_int, [_vp]),
     "gne_solver_num_vars": (C.c_int64, [_vp]),
     "gne_solver_objective": (C.c_double, [_vp]),
@@ -581,14 +583,21 @@ class Solver:
         return _BorrowedDevice(_vp(h), self.n + 16, self.M - self.n + 16, self.M - self.n) if h else None
 
 
-def solve_batch(solvers, presolve, max_pivots=-1, threads=0, per_launch=0, stats=None):
+def solve_batch(solvers, presolve, max_pivots=-1, threads=0, per_launch=0, stats=None, align_pivot=-1):
     """gne_solver_solve for several independent solvers at once: `threads` host threads (0 = one per core) interleave them;
-    per_launch > 0: the LV passes of a thread's solvers leave in launch groups of up to per_launch instances (one grid).
+    per_launch > 0: the LV passes of a thread's solvers leave in launch groups of up to per_launch instances (one grid);
+    align_pivot >= 0: no solver starts that pivot before all have reached it (gne_solver_solve_batch_ex).
     Returns [(iterations, finished)] per solver; stats (a dict) receives group_launches."""
     B = len(solvers)
     hs = (_vp * B)(*[s.h for s in solvers])
     it = np.zeros(B, np.int64); fin = (C.c_int * B)()
-    if per_launch > 0:
+    if align_pivot >= 0:
+        gl = np.zeros(1, np.int64)
+        _ck(lib.gne_solver_solve_batch_ex(hs, B, 1 if presolve else 0, max_pivots, threads, per_launch, align_pivot, _p(it, _i64p), fin,
+                                          _p(gl, _i64p)), "gne_solver_solve_batch_ex")
+        if stats is not None:
+            stats["group_launches"] = int(gl[0])
+    elif per_launch > 0:
         gl = np.zeros(1, np.int64)
         _ck(lib.gne_solver_solve_batch_grouped(hs, B, 1 if presolve else 0, max_pivots, threads, per_launch, _p(it, _i64p), fin,
                                                _p(gl, _i64p)), "gne_solver_solve_batch_grouped")

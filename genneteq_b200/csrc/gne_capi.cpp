@@ -4,6 +4,7 @@
 #include "gne_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -373,8 +374,10 @@ extern "C" int gne_solver_set_rules(gne_solver *s, int p1, int p2)
 // blocks on the device while another of its solvers has host work to do.  With perLaunch > 0 the LV passes a thread has
 // prepared during one sweep over its solvers leave in launch groups (gne_lv_group: one grid for up to perLaunch
 // instances) instead of one launch each: the per-instance launch cost is what limits a batch of small instances.
+// alignPivot >= 0: no solver starts its pivot number alignPivot before every solver of the batch has got there (or ended):
+// the instances then run that part of their solves side by side whatever their first pivots cost (bench.py's window).
 static int solve_batch_impl(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int perLaunch,
-                            int64_t *iters, int *finished, int64_t *groupLaunches)
+                            int64_t *iters, int *finished, int64_t *groupLaunches, int64_t alignPivot = -1)
 {
     if (B <= 0 || !s || !iters || !finished || perLaunch < 0) { gne_set_error("gne_solver_solve_batch: bad argument"); return GNE_ERR_ARG; }
     for (int i = 0; i < B; ++i) NO_EQF(s[i], "gne_solver_solve_batch");
@@ -384,6 +387,8 @@ static int solve_batch_impl(gne_solver **s, int B, int presolve, int64_t maxPivo
     std::vector<int> status((size_t) B, GNE_OK);
     std::vector<std::string> errors((size_t) B);
     std::vector<int64_t> launchesOf((size_t) T, 0);
+    std::atomic<int> arrived(0);                        // solvers that have reached alignPivot (or ended before it)
+    std::vector<char> hasArrived((size_t) B, 0);
     auto work = [&](int w) {
         std::vector<int> mine;
         for (int i = w; i < B; i += T) mine.push_back(i);
@@ -395,6 +400,7 @@ static int solve_batch_impl(gne_solver **s, int B, int presolve, int64_t maxPivo
             iters[i] = 0; finished[i] = 1;
             status[i] = s[i]->solver.solveBegin(presolve != 0, maxPivots);
             if (status[i] != GNE_OK) { errors[i] = gne_last_error(); live[k] = 0; } else ++alive;
+            if (!live[k] && alignPivot >= 0) { hasArrived[(size_t) i] = 1; arrived.fetch_add(1); }
         }
         // (the device handles exist once solveBegin has run: now the thread's launch group can be made on their device)
         if (perLaunch > 0) {
@@ -422,6 +428,10 @@ static int solve_batch_impl(gne_solver **s, int B, int presolve, int64_t maxPivo
             for (size_t k = 0; k < mine.size(); ++k) {
                 if (!live[k]) continue;
                 const int i = mine[k];
+                if (alignPivot >= 0 && s[i]->solver.atLoopHead() && s[i]->solver.pivotsThisCall() == alignPivot) {
+                    if (!hasArrived[(size_t) i]) { hasArrived[(size_t) i] = 1; arrived.fetch_add(1); }
+                    if (arrived.load() < B) continue;   // (held at the line until the whole batch stands there)
+                }
                 // a solver whose result has arrived is taken through its pivot AND the preparation of its next pass
                 // (two steps) before the next solver is looked at; with a single live solver left there is nothing to
                 // interleave with: block in the step
@@ -430,17 +440,26 @@ static int solve_batch_impl(gne_solver **s, int B, int presolve, int64_t maxPivo
                 if (r == 2) continue;
                 progressed = true;
                 const int64_t t1 = wantStats ? nowNs() : 0;
+                // (the pivot is done: the preparation of the next pass follows at once - unless that pass is the one behind the
+                //  starting line and the rest of the batch is not there yet; the check at the top of the sweep lets it go later)
+                if (r == 1 && alignPivot >= 0 && s[i]->solver.atLoopHead() && s[i]->solver.pivotsThisCall() == alignPivot) {
+                    if (!hasArrived[(size_t) i]) { hasArrived[(size_t) i] = 1; arrived.fetch_add(1); }
+                    if (arrived.load() < B) continue;
+                }
                 if (r == 1) r = s[i]->solver.solveStep(alive == 1);
                 if (wantStats) { const int64_t t2 = nowNs(); nsStep1 += t1 - t0; nsStep2 += t2 - t1; ++nStep1; ++nStep2; }
                 if (r == 1 || r == 2) continue;
                 if (r < 0) { status[i] = -r; errors[i] = gne_last_error(); }
                 else { status[i] = s[i]->solver.solveEnd(&iters[i], &finished[i]); if (status[i] != GNE_OK) errors[i] = gne_last_error(); }
                 live[k] = 0; --alive;
+                if (alignPivot >= 0 && !hasArrived[(size_t) i]) { hasArrived[(size_t) i] = 1; arrived.fetch_add(1); }
             }
-            // whatever this sweep has parked goes out now
+            // whatever has been parked and not sent yet goes out now
             const int64_t tL = wantStats ? nowNs() : 0;
             if (wantStats && !progressed) { nsIdleSweep += tL - tSweep; ++nIdle; }
-            if (group && gne_lv_group_pending(group) > 0) {
+            // (only when the sweep found nothing else to do: while solvers keep coming in, their passes fill the group - a
+            //  launch of two instances occupies the device about as long as a launch of eight)
+            if (group && gne_lv_group_pending(group) > 0 && !progressed) {
                 if (gne_lv_group_launch(group) != GNE_OK) { groupFailed = true; break; }
                 if (wantStats) { nsLaunch += nowNs() - tL; ++nLaunch; }
             }
@@ -485,6 +504,10 @@ extern "C" int gne_solver_solve_batch(gne_solver **s, int B, int presolve, int64
 extern "C" int gne_solver_solve_batch_grouped(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int perLaunch,
                                               int64_t *iters, int *finished, int64_t *groupLaunches) {
     return guarded("gne_solver_solve_batch_grouped", [&]() -> int { return solve_batch_impl(s, B, presolve, maxPivots, threads, perLaunch, iters, finished, groupLaunches); });
+}
+extern "C" int gne_solver_solve_batch_ex(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int perLaunch, int64_t alignPivot,
+                                         int64_t *iters, int *finished, int64_t *groupLaunches) {
+    return guarded("gne_solver_solve_batch_ex", [&]() -> int { return solve_batch_impl(s, B, presolve, maxPivots, threads, perLaunch, iters, finished, groupLaunches, alignPivot); });
 }
 extern "C" int gne_solver_set_comm_host(gne_solver *s, int rank, int nranks, gne_allgather_fn allgather, void *ctx) {
     return guarded("gne_solver_set_comm_host", [&]() -> int {

@@ -83,6 +83,9 @@ class GenNetEq {
     int solveEnd(int64_t *iters, int *finished);
     gne_lv_group *lvGroup = nullptr;                    // set by the batch driver: LV passes go out through this launch group
     double secsComplete = 0.0;                          // step-wise loop: time inside completeLargestViolation (result already there or awaited)
+    // step-wise loop: at the loop head (nothing in flight) with this many pivots of the current call behind it
+    bool atLoopHead() const { return stStage == 0; }
+    int64_t pivotsThisCall() const { return callPivots; }
     double pivotSeconds() const { return secsPivot; }
     double potentialSeconds() const { return secsPotentials; }
 

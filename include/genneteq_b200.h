@@ -262,6 +262,12 @@ int gne_solver_solve_batch(gne_solver **s, int B, int presolve, int64_t maxPivot
 int gne_solver_solve_batch_grouped(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int perLaunch,
                                    int64_t *iters, int *finished, int64_t *groupLaunches);
 
+/* the same with a starting line: alignPivot >= 0 holds every solver before its pivot number alignPivot (of this call) until
+ * all solvers of the batch have got there or ended, so that what follows runs side by side whatever the instances' first
+ * pivots cost (a phase's first relabel sweeps every node)                                                          */
+int gne_solver_solve_batch_ex(gne_solver **s, int B, int presolve, int64_t maxPivots, int threads, int perLaunch, int64_t alignPivot,
+                              int64_t *iters, int *finished, int64_t *groupLaunches);
+
 int gne_solver_num_nodes(const gne_solver *s);
 int64_t gne_solver_num_vars(const gne_solver *s);
 int gne_solver_num_sets(const gne_solver *s);      /* equal-flow variables (the last ones of the variable vector) */

@@ -45,14 +45,11 @@ def make_instance(n, m, seed, mode, p, k, shuffled=False, cap_scale=1.0):
     lines = ["p efpgn %d %d %d\n" % (n, len(arcs), p)]
     for a in order:
         (i, j, ub, cost, g) = arcs[a]
-        lines.append("a %d %d 0.0 %.6f %.6f %.6f %d\n" % (i + 1, j + 1, ub * cost_scale_cap(a, eqf, cap_scale), cost, g, eqf.get(a, 0)))
+        cap = ub * (cap_scale if a in eqf else 1.0)     # (cap_scale: tighter or looser capacities on the member arcs)
+        lines.append("a %d %d 0.0 %.6f %.6f %.6f %d\n" % (i + 1, j + 1, cap, cost, g, eqf.get(a, 0)))
     for i in range(n):
         lines.append("n %d %.6f\n" % (i + 1, sup[i]))
     return "".join(lines)
-
-
-def cost_scale_cap(a, eqf, cap_scale):
-    return cap_scale if a in eqf else 1.0
 
 
 def parse_col(text):
