@@ -1144,6 +1144,128 @@ int EqfSolver::getNextCandidate(bool useWeighted, int32_t *out)    // :456-535
     return GNE_OK;
 }
 
+// updateCandidateList2 (:613-677): arcs and sets are scanned from their rolling cursors, interleaved by one drand48 draw per
+// step while both sides last, until clMaxSize (= n) violators are listed.  The device supplies which positions violate
+// (every arc violator in position order with |rc|, the sets' reduced costs); the host replays the walk - no reduced cost is
+// computed here - and jumps over the draw-free stretches.
+int EqfSolver::updateCandidateList2()
+{
+    candidateList2.clear(); candidateViol2.clear();
+    const int64_t nA = (int64_t) setNBarc.size(), nE = (int64_t) setNBeqf.size();
+    const size_t clMaxSize = (size_t) numNodes;
+    const double arcProb = ((double) nA) / ((double) (nA + nE));
+    if (nbArcPivotInd >= nA) nbArcPivotInd = 0;
+    if (nbEqfPivotInd >= nE) nbEqfPivotInd = 0;
+    const int64_t startA = nbArcPivotInd, startE = nbEqfPivotInd;
+    bool exA = (nA == 0), exE = (nE == 0);
+    // arc violators in position order
+    int64_t cnt = 0;
+    if (nA > 0) {
+        if (listPos.size() < 1024) { listPos.resize(1024); listViol.resize(1024); }
+        int rc = gne_price_violators(dev, 0.0, &cnt, listPos.data(), listViol.data(), (int64_t) listPos.size());
+        if (rc == GNE_ERR_CAPACITY) {
+            listPos.resize((size_t) cnt + 1024); listViol.resize((size_t) cnt + 1024);
+            rc = gne_price_violators(dev, 0.0, &cnt, listPos.data(), listViol.data(), (int64_t) listPos.size());
+        }
+        if (rc) return rc;
+    }
+    if (nE > 0) GNE_TRY(priceSets());
+    // the next violator at or behind the cursor, cyclically; `left` = violators the cursor has not passed yet
+    int64_t vNext = cnt ? (int64_t) (std::lower_bound(listPos.begin(), listPos.begin() + cnt, startA) - listPos.begin()) % cnt : 0;
+    int64_t left = cnt, scanned = 0;
+    auto tryToAddArc = [&]() {                          // :680-689 + the cursor step of its callers
+        if (left > 0 && listPos[(size_t) vNext] == nbArcPivotInd) {
+            isOptimal = false;
+            candidateList2.push_back(setNBarc[(size_t) nbArcPivotInd]); candidateViol2.push_back(listViol[(size_t) vNext]);
+            vNext = (vNext + 1) % cnt; --left;
+        }
+        nbArcPivotInd = (nbArcPivotInd + 1) % nA;
+        exA = (nbArcPivotInd == startA);
+        ++scanned;
+    };
+    auto tryToAddEqf = [&]() {                          // :692-701
+        const int32_t v = setNBeqf[(size_t) nbEqfPivotInd];
+        const double rc = eqfRc[(size_t) nbEqfPivotInd];
+        if (violates(v, rc)) { isOptimal = false; candidateList2.push_back(v); candidateViol2.push_back(fabs(rc)); }
+        nbEqfPivotInd = (nbEqfPivotInd + 1) % nE;
+        exE = (nbEqfPivotInd == startE);
+    };
+    for (int i = 0; i < 5 && !exA; ++i) tryToAddArc();                 // numArcsToAlwaysCheck
+    for (int i = 0; i < 1 && !exE; ++i) tryToAddEqf();                 // numEqfsToAlwaysCheck
+    while (candidateList2.size() < clMaxSize && !exA && !exE) {
+        if (drand48() < arcProb) tryToAddArc();
+        else tryToAddEqf();
+    }
+    if (exA) while (candidateList2.size() < clMaxSize && !exE) tryToAddEqf();
+    if (exE && !exA && candidateList2.size() < clMaxSize) {
+        // no draws from here on: the arcs up to the violator that fills the list, or all that are left
+        const int64_t want = (int64_t) (clMaxSize - candidateList2.size());
+        const int64_t take = std::min(want, left);
+        int64_t lastPos = -1;
+        for (int64_t k = 0; k < take; ++k) {
+            lastPos = listPos[(size_t) vNext];
+            isOptimal = false;
+            candidateList2.push_back(setNBarc[(size_t) lastPos]); candidateViol2.push_back(listViol[(size_t) vNext]);
+            vNext = (vNext + 1) % cnt; --left;
+        }
+        int64_t end;                                    // the cursor afterwards
+        if (take == want) end = (lastPos + 1) % nA;     // the list is full right behind that violator
+        else end = startA;                              // ran once round
+        scanned += (end - nbArcPivotInd + nA) % nA + ((end == nbArcPivotInd) ? nA : 0);
+        nbArcPivotInd = end;
+    }
+    arcsPriced += (double) scanned;
+    return GNE_OK;
+}
+
+int EqfSolver::getNextCandidate2(bool useWeighted, int32_t *out)   // :550-610
+{
+    isOptimal = true;
+    if (itersSinceUpdate < 0 || itersSinceUpdate > majorIterationLength) {
+        GNE_TRY(updateCandidateList2());
+        itersSinceUpdate = 0;
+    } else {
+        ++itersSinceUpdate;
+    }
+    int32_t ev = -1;
+    int64_t evInd = -1;
+    double largest = -1.0;
+    size_t k = 0;
+    while (k < candidateList2.size()) {
+        const int32_t c = candidateList2[k];
+        const bool atLB = (setLoc[c] == L_var);
+        bool viol;
+        double a;
+        if (itersSinceUpdate > 0) {
+            const double rc = hostRedCost(c);           // one list member against the host's copy of the potentials
+            viol = (atLB && rc < (-1.0 * TOL)) || (!atLB && rc > TOL);
+            a = fabs(rc);
+        } else {                                        // "reduced cost is up to date": the value of the list pass
+            viol = true;
+            a = candidateViol2[k];
+        }
+        if (viol) {
+            isOptimal = false;
+            if (!isArc(c) && useWeighted) a = a / numOrigArcs[(size_t) (c - A)];
+            if (largest < a) { largest = a; ev = c; evInd = (int64_t) k; }
+            ++k;
+        } else {
+            candidateList2[k] = candidateList2.back(); candidateList2.pop_back();
+            candidateViol2[k] = candidateViol2.back(); candidateViol2.pop_back();
+        }
+    }
+    if (ev == -1 && itersSinceUpdate > 0) {
+        itersSinceUpdate = -1;
+        return getNextCandidate2(false, out);           // (the reference's retry drops useWeighted, :588)
+    }
+    if (evInd >= 0) {
+        candidateList2[(size_t) evInd] = candidateList2.back(); candidateList2.pop_back();
+        candidateViol2[(size_t) evInd] = candidateViol2.back(); candidateViol2.pop_back();
+    }
+    *out = ev;
+    return GNE_OK;
+}
+
 int EqfSolver::quickSelect(bool useWeighted, int32_t *out)         // :710-764
 {
     isOptimal = true;
@@ -1200,10 +1322,12 @@ int EqfSolver::selectEnteringVariable(int32_t *out)                // :36-127
       case GNE_CLW: return getNextCandidate(true, out);
       case GNE_SAA: return getVarBySimAnnealing(true, out);
       case GNE_SAE: return getVarBySimAnnealing(false, out);
+      case GNE_CL2: return getNextCandidate2(false, out);
+      case GNE_CLW2: return getNextCandidate2(true, out);
       case GNE_QS: return quickSelect(false, out);
       case GNE_QSW: return quickSelect(true, out);
     }
-    gne_set_error("pivot rule %d is not available with equal-flow sets (SD, CL2, CLW2)", rule);
+    gne_set_error("pivot rule %d is not available with equal-flow sets (SD)", rule);
     return GNE_ERR_UNSUPPORTED;
 }
 

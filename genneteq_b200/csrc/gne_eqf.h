@@ -18,8 +18,7 @@
 // (the gsl_mini header tree of the test infrastructure), fixtures tests/golden/q_*.npz - "reference + restated GSL", not a
 // GSL build.
 //
-// Pricing rules with sets: every rule id of main.h:17-34 except SD (stale in the reference too) and CL2 / CLW2 (their
-// rebuild interleaves one drand48 draw per scanned variable, gnePivotRules.cpp:651): those return GNE_ERR_UNSUPPORTED.
+// Pricing rules with sets: every rule id of main.h:17-34 except SD (stale in the reference too): GNE_ERR_UNSUPPORTED.
 #pragma once
 #include "../../include/genneteq_b200.h"
 
@@ -130,6 +129,8 @@ class EqfSolver {
     int lastEVarInd = -1;
     double lastViolation = 100000, baselineViolation = 100000;
     std::priority_queue<VarWithViol, std::vector<VarWithViol>, violcomp> candidateList;
+    std::vector<int32_t> candidateList2;                               // :550-705
+    std::vector<double> candidateViol2;                                // |redCost| a member had when the list was built
     uint64_t rand48State = 0;
     double drand48();
     // ---- device
@@ -207,6 +208,8 @@ class EqfSolver {
     int getRandomVarWithLargeViolation(bool useWeighted, int32_t *out);
     int getVarBySimAnnealing(bool arcsFirst, int32_t *out);
     int getNextCandidate(bool useWeighted, int32_t *out);
+    int updateCandidateList2();
+    int getNextCandidate2(bool useWeighted, int32_t *out);
     int quickSelect(bool useWeighted, int32_t *out);
     // ---- the s x s systems
     static void lu_decomp(std::vector<double> &a, int s, std::vector<int> &perm);

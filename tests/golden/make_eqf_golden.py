@@ -137,16 +137,16 @@ def make(name, n, m, seed, mode, p, k, rules, shuffled=False, keep_col=False, ca
 
 
 if __name__ == "__main__":
-    allr = ["LV", "LVW", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "QS", "QSW"]
+    allr = ["LV", "LVW", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "CL2", "CLW2", "QS", "QSW"]
     which = sys.argv[1:] or ["small", "medium"]
     if "small" in which:
         make("q_wide_s21", 60, 400, 21, "wide", 4, 3, allr, keep_col=True)
         make("q_lossy_s22", 150, 1200, 22, "lossy", 8, 4, allr)
         make("q_pow2_s23", 100, 800, 23, "pow2", 5, 3, allr)
         make("q_near1_s24", 80, 600, 24, "near1", 6, 2, allr, shuffled=True, keep_col=True)
-        make("q_mixed_s25", 90, 700, 25, "wide", 5, 3, ["QS+LV", "LVE+CL", "FV+LVA", "LVW+QSW"])
+        make("q_mixed_s25", 90, 700, 25, "wide", 5, 3, ["QS+LV", "LVE+CL", "FV+LVA", "LVW+QSW", "CL2+QS"])
     if "medium" in which:
         # several 2048-position tiles of nonbasic arcs, more sets.  (At this size the reference often ends with a NaN objective -
         # a singular s x s system, no pivot-size check in its LU use; rule CL does here.  The fixture keeps that run: the
         # restatement has to walk through the same NaNs to the same pivots.)
-        make("q_pow2_s29", 600, 9000, 29, "pow2", 10, 4, ["LV", "LVW", "QS", "FV", "CL"])
+        make("q_pow2_s29", 600, 9000, 29, "pow2", 10, 4, ["LV", "LVW", "QS", "FV", "CL", "CL2", "CLW2"])
