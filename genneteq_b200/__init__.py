@@ -99,6 +99,7 @@ SIGNATURES = {
     "gne_solver_create_eqf": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, C.c_int,
                                         _f64p, C.c_double]),
     "gne_solver_num_sets": (C.c_int, [_vp]),
+    "gne_host_lu_solve": (C.c_int, [C.c_int, _f64p, _f64p, _f64p, _f64p, _i32p]),
     "gne_host_replay_eqf": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, C.c_int, _f64p, C.c_double, C.c_int, C.c_int,
                                       C.c_int64, C.c_int64, _i32p, _i32p, _i64p, _f64p, _f64p, _f64p]),
     "gne_solver_create_from_col": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_char_p]),
@@ -662,6 +663,15 @@ def host_replay(n, tail, head, ub, cost, mult, supply, big_m, draws, p1, e, l, s
                             _p(supply, _f64p), big_m, draws, 1 if sparse_flows else 0, p1, len(e), _p(e, _i32p), _p(l, _i32p),
                             C.byref(mm), _p(flows, _f64p), _p(pots, _f64p), C.byref(obj)), "gne_host_replay")
     return mm.value, flows, pots, obj.value
+
+
+def host_lu_solve(a, b):
+    """The equal-flow engine's s x s solve (gne_host_lu_solve): returns (x, lu, perm)."""
+    a = _arr(a, np.float64); b = _arr(b, np.float64)
+    s = len(b)
+    x = np.empty(s); lu = np.empty((s, s)); perm = np.empty(s, np.int32)
+    _ck(lib.gne_host_lu_solve(s, _p(a, _f64p), _p(b, _f64p), _p(x, _f64p), _p(lu, _f64p), _p(perm, _i32p)), "gne_host_lu_solve")
+    return x, lu, perm
 
 
 def host_replay_eqf(n, tail, head, ub, cost, mult, eqf, num_sets, supply, big_m, draws, p1, e, l, num_vars):

@@ -627,6 +627,19 @@ extern "C" int gne_host_replay(int n, int64_t m, const int32_t *tail, const int3
     });
 }
 
+extern "C" int gne_host_lu_solve(int s, const double *a, const double *b, double *x, double *lu, int32_t *perm)
+{
+    return guarded("gne_host_lu_solve", [&]() -> int {
+    if (s <= 0 || !a || !b || !x) { gne_set_error("gne_host_lu_solve: bad argument"); return GNE_ERR_ARG; }
+    std::vector<double> m(a, a + (size_t) s * s), rhs(b, b + s), sol;
+    std::vector<int> p;
+    EqfSolver::luSolve(m, s, rhs, p, sol);
+    for (int i = 0; i < s; ++i) { x[i] = sol[(size_t) i]; if (perm) perm[i] = p[(size_t) i]; }
+    if (lu) for (size_t i = 0; i < (size_t) s * s; ++i) lu[i] = m[i];
+    return GNE_OK;
+    });
+}
+
 extern "C" int gne_host_replay_eqf(int n, int64_t m, const int32_t *tail, const int32_t *head, const double *ub, const double *cost,
                                    const double *mult, const int32_t *eqf, int numSets, const double *supply, double bigM,
                                    int drawsPhaseI, int drawsPhaseII, int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,

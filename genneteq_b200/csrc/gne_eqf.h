@@ -69,6 +69,9 @@ class EqfSolver {
     void getStates(int32_t *out) const { for (int64_t v = 0; v < V; ++v) out[v] = setLoc[(size_t) v]; }
     void getCounters(double *out12) const;
     int64_t typeIIPivots() const { return pivotsTII; }
+    // the s x s solve on its own (tests): a = row-major s x s (overwritten by its LU), perm = row permutation, x = solution
+    static void luSolve(std::vector<double> &a, int s, const std::vector<double> &b, std::vector<int> &perm, std::vector<double> &x)
+    { lu_decomp(a, s, perm); lu_solve(a, s, perm, b, x); }
     gne_dev *device() { return dev; }
 
   private:

@@ -321,6 +321,11 @@ int gne_host_replay_eqf(int n, int64_t m, const int32_t *tail, const int32_t *he
                         int drawsPhaseI, int drawsPhaseII, int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
                         int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective);
 
+/* the s x s solve of the equal-flow engine on its own (host-only; tests): LU with partial pivoting in GSL 1.x's operation
+ * order (gsl_linalg_LU_decomp + gsl_linalg_LU_solve, as gnePotential.cpp:196-197 and gneFlow.cpp:236-237 call them).
+ * a: row-major s x s, b: right-hand side, x: solution; lu (s x s) and perm (s) may be NULL                          */
+int gne_host_lu_solve(int s, const double *a, const double *b, double *x, double *lu, int32_t *perm);
+
 /* the contiguous position range [*lo, *hi) of the nonbasic list (m real arcs) that `rank` of `nranks` prices:
  * boundaries on multiples of 2048, ranges never overlap, *lo == *hi for a rank left without positions
  * (lists shorter than 2048 x nranks).  What gne_solver_set_comm uses; host-only.                     */
