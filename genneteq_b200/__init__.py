@@ -99,6 +99,8 @@ SIGNATURES = {
     "gne_solver_create_eqf": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, C.c_int,
                                         _f64p, C.c_double]),
     "gne_solver_num_sets": (C.c_int, [_vp]),
+    "gne_host_replay_eqf_col": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, _i32p, _i32p, _i64p, C.c_int64, _f64p, _f64p,
+                                          _f64p]),
     "gne_host_lu_solve": (C.c_int, [C.c_int, _f64p, _f64p, _f64p, _f64p, _i32p]),
     "gne_host_replay_eqf": (C.c_int, [C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, C.c_int, _f64p, C.c_double, C.c_int, C.c_int,
                                       C.c_int64, C.c_int64, _i32p, _i32p, _i64p, _f64p, _f64p, _f64p]),
@@ -662,6 +664,17 @@ def host_replay(n, tail, head, ub, cost, mult, supply, big_m, draws, p1, e, l, s
     _ck(lib.gne_host_replay(n, len(tail), _p(tail, _i32p), _p(head, _i32p), _p(ub, _f64p), _p(cost, _f64p), _p(mult, _f64p),
                             _p(supply, _f64p), big_m, draws, 1 if sparse_flows else 0, p1, len(e), _p(e, _i32p), _p(l, _i32p),
                             C.byref(mm), _p(flows, _f64p), _p(pots, _f64p), C.byref(obj)), "gne_host_replay")
+    return mm.value, flows, pots, obj.value
+
+
+def host_replay_eqf_col(path, n, draws, p1, e, l, num_vars):
+    """gne_host_replay_eqf_col: the host-only replay of an equal-flow instance read from a text file."""
+    d1, d2 = draws if isinstance(draws, tuple) else (draws, draws)
+    e = _arr(e, np.int32); l = _arr(l, np.int32)
+    mm = C.c_int64(0); obj = C.c_double(0)
+    flows = np.empty(num_vars); pots = np.empty(n)
+    _ck(lib.gne_host_replay_eqf_col(path.encode(), d1, d2, p1, len(e), _p(e, _i32p), _p(l, _i32p), C.byref(mm), num_vars,
+                                    _p(flows, _f64p), _p(pots, _f64p), C.byref(obj)), "gne_host_replay_eqf_col")
     return mm.value, flows, pots, obj.value
 
 

@@ -664,6 +664,33 @@ extern "C" int gne_host_replay_eqf(int n, int64_t m, const int32_t *tail, const 
     });
 }
 
+extern "C" int gne_host_replay_eqf_col(const char *path, int drawsPhaseI, int drawsPhaseII, int64_t phase1Pivots, int64_t totalPivots,
+                                       const int32_t *e, const int32_t *l, int64_t *mismatch, int64_t numVars, double *flowsOut,
+                                       double *potentialsOut, double *objective)
+{
+    return guarded("gne_host_replay_eqf_col", [&]() -> int {
+    if (!path || !mismatch) { gne_set_error("gne_host_replay_eqf_col: bad argument"); return GNE_ERR_ARG; }
+    Config conf;
+    conf.inFile = path;
+    Graph g;
+    int rc = g.initialize(&conf);
+    if (rc) return rc;
+    if (g.getNumEqualFlowSets() <= 0) { gne_set_error("gne_host_replay_eqf_col: the file has no equal-flow sets"); return GNE_ERR_ARG; }
+    EqfInstance inst;
+    g.toEqfInstance(inst);
+    EqfSolver s;
+    rc = s.initialize(inst, 0, true);
+    if (rc) return rc;
+    if (flowsOut && numVars != s.getNumVars()) { gne_set_error("gne_host_replay_eqf_col: %lld variables, buffer for %lld", (long long) s.getNumVars(), (long long) numVars); return GNE_ERR_CAPACITY; }
+    rc = s.replayTrace(drawsPhaseI, drawsPhaseII, phase1Pivots, totalPivots, e, l, mismatch);
+    if (rc) return rc;
+    if (flowsOut) s.getFlows(flowsOut);
+    if (potentialsOut) s.getPotentials(potentialsOut);
+    if (objective) *objective = s.getFlowCost();
+    return GNE_OK;
+    });
+}
+
 // ------------------------------------------------------------------------------------------
 // synthetic instances (gne_generate.cpp; the same file also builds the reference arm's stand-alone generator library)
 // ------------------------------------------------------------------------------------------

@@ -321,6 +321,12 @@ int gne_host_replay_eqf(int n, int64_t m, const int32_t *tail, const int32_t *he
                         int drawsPhaseI, int drawsPhaseII, int64_t phase1Pivots, int64_t totalPivots, const int32_t *e, const int32_t *l,
                         int64_t *mismatch, double *flowsOut, double *potentialsOut, double *objective);
 
+/* the same from a text file, read the way gne_solver_create_from_col reads it (d_r(i) in file order, duplicate lines
+ * overwriting); numVars = size of flowsOut (arc variables + sets), potentialsOut holds n values                       */
+int gne_host_replay_eqf_col(const char *path, int drawsPhaseI, int drawsPhaseII, int64_t phase1Pivots, int64_t totalPivots,
+                            const int32_t *e, const int32_t *l, int64_t *mismatch, int64_t numVars, double *flowsOut,
+                            double *potentialsOut, double *objective);
+
 /* the s x s solve of the equal-flow engine on its own (host-only; tests): LU with partial pivoting in GSL 1.x's operation
  * order (gsl_linalg_LU_decomp + gsl_linalg_LU_solve, as gnePotential.cpp:196-197 and gneFlow.cpp:236-237 call them).
  * a: row-major s x s, b: right-hand side, x: solution; lu (s x s) and perm (s) may be NULL                          */

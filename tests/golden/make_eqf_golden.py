@@ -52,6 +52,65 @@ def make_instance(n, m, seed, mode, p, k, shuffled=False, cap_scale=1.0):
     return "".join(lines)
 
 
+def make_edge_instance(n=40, m=220, seed=31):
+    """Loader edge cases in one file (graph.cpp:382-419, gneInit.cpp:64-103): a set of one arc; a set whose arcs share a node
+    (d_r(i) = 1 - mult there); a set with a member of capacity 0 (no variable, not counted in UB / cost / numOrigArcs, but its
+    +1 / -mult still sit in d_r); a set nobody names (UB = max double, d_r = 0); a set of two antiparallel arcs; a duplicate
+    `a` line (the later one overwrites capacity, cost and multiplier; the arc count of the problem line includes it)."""
+    arcs, sup = generate(n, m, seed, "wide")
+    key = {(a[0], a[1]): k for k, a in enumerate(arcs)}
+    eqf = {}
+    rng = random.Random(seed * 31 + 7)
+    free = [k for k, a in enumerate(arcs) if (a[0] + 1) % n != a[1]]            # keep the ring out of the sets
+    rng.shuffle(free)
+    take = iter(free)
+    for _ in range(3):
+        eqf[next(take)] = 1
+    eqf[next(take)] = 2
+    # set 3: u -> v and v -> w
+    by_tail = {}
+    for k in free:
+        by_tail.setdefault(arcs[k][0], []).append(k)
+    for k in free:
+        if k in eqf:
+            continue
+        nxt = [q for q in by_tail.get(arcs[k][1], []) if q not in eqf and q != k]
+        if nxt:
+            eqf[k] = 3; eqf[nxt[0]] = 3
+            break
+    zero_cap = None
+    for _ in range(3):
+        k = next(take)
+        while k in eqf:
+            k = next(take)
+        eqf[k] = 4
+        zero_cap = k
+    # set 5 stays empty; set 6: an antiparallel pair (added if the generator made none)
+    pair = [(k, key[(a[1], a[0])]) for k, a in enumerate(arcs) if (a[1], a[0]) in key and k not in eqf and key[(a[1], a[0])] not in eqf]
+    extra = []
+    if pair:
+        eqf[pair[0][0]] = 6; eqf[pair[0][1]] = 6
+    else:
+        k = next(take)
+        while k in eqf:
+            k = next(take)
+        eqf[k] = 6
+        extra.append((arcs[k][1], arcs[k][0], 37.5, 12.25, 0.9, 6))
+    dup = next(take)
+    while dup in eqf:
+        dup = next(take)
+    lines = []
+    for k, (i, j, ub, cost, g) in enumerate(arcs):
+        cap = 0.0 if k == zero_cap else ub
+        lines.append("a %d %d 0.0 %.6f %.6f %.6f %d\n" % (i + 1, j + 1, cap, cost, g, eqf.get(k, 0)))
+    for (i, j, ub, cost, g, r) in extra:
+        lines.append("a %d %d 0.0 %.6f %.6f %.6f %d\n" % (i + 1, j + 1, ub, cost, g, r))
+    (i, j, ub, cost, g) = arcs[dup]
+    lines.append("a %d %d 0.0 %.6f %.6f %.6f 0\n" % (i + 1, j + 1, ub * 0.5, cost + 3.0, g))      # the duplicate line
+    head = ["p efpgn %d %d %d\n" % (n, len(lines), 6)]
+    return "".join(head + lines + ["n %d %.6f\n" % (i + 1, sup[i]) for i in range(n)])
+
+
 def parse_col(text):
     """(n, p, tail, head, ub, cost, mult, eqf, supply): arcs in FILE order, values as sscanf reads them."""
     n = p = 0
@@ -100,15 +159,18 @@ def ref_cli(col, rule1, rule2, tmp):
                 trace_md5=hashlib.md5(txt.encode()).hexdigest(), feasible=int(feasible))
 
 
-def make(name, n, m, seed, mode, p, k, rules, shuffled=False, keep_col=False, cap_scale=1.0):
-    text = make_instance(n, m, seed, mode, p, k, shuffled, cap_scale)
+def make(name, n, m, seed, mode, p, k, rules, shuffled=False, keep_col=False, cap_scale=1.0, text=None):
+    if text is None:
+        text = make_instance(n, m, seed, mode, p, k, shuffled, cap_scale)
     out = {}
     (n_, p_, tail, head, ub, cost, mult, eqf, sup) = parse_col(text)
     # the arrays the C ABI takes: arcs sorted by (tail, head) - for a shuffled file d_r(i) is then summed in another
     # order than the file's, which is why the shuffled fixture also carries the text
     o = np.lexsort((head, tail))
+    pairs = set(zip(tail.tolist(), head.tolist()))
     out.update(n=n_, p=p_, tail=tail[o], head=head[o], ub=ub[o], cost=cost[o], mult=mult[o], eqf=eqf[o], supply=sup,
-               col_md5=hashlib.md5(text.encode()).hexdigest(), shuffled=int(shuffled))
+               col_md5=hashlib.md5(text.encode()).hexdigest(), shuffled=int(shuffled),
+               arrays_ok=int(len(pairs) == len(tail)))     # 0: duplicate `a` lines - only the text describes the instance
     if keep_col:
         out["col_text"] = np.frombuffer(text.encode(), np.uint8)
     nvars = int(np.sum((ub > 0.0) & (eqf == 0))) + n_
@@ -138,13 +200,17 @@ def make(name, n, m, seed, mode, p, k, rules, shuffled=False, keep_col=False, ca
 
 if __name__ == "__main__":
     allr = ["LV", "LVW", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "CL2", "CLW2", "QS", "QSW"]
-    which = sys.argv[1:] or ["small", "medium"]
+    which = sys.argv[1:] or ["small", "edge", "medium"]
     if "small" in which:
         make("q_wide_s21", 60, 400, 21, "wide", 4, 3, allr, keep_col=True)
         make("q_lossy_s22", 150, 1200, 22, "lossy", 8, 4, allr)
         make("q_pow2_s23", 100, 800, 23, "pow2", 5, 3, allr)
         make("q_near1_s24", 80, 600, 24, "near1", 6, 2, allr, shuffled=True, keep_col=True)
         make("q_mixed_s25", 90, 700, 25, "wide", 5, 3, ["QS+LV", "LVE+CL", "FV+LVA", "LVW+QSW", "CL2+QS"])
+    if "edge" in which:
+        # (the arrays of this fixture are the file's lines in (tail, head) order, duplicate included: only the text goes
+        #  through the loader the way the reference reads it - the tests use col_text)
+        make("q_edge_s31", 0, 0, 0, "", 0, 0, ["LV", "LVE", "QS", "CL", "CL2", "FV"], keep_col=True, text=make_edge_instance())
     if "medium" in which:
         # several 2048-position tiles of nonbasic arcs, more sets.  (At this size the reference often ends with a NaN objective -
         # a singular s x s system, no pivot-size check in its LU use; rule CL does here.  The fixture keeps that run: the
