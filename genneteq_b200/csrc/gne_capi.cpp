@@ -512,12 +512,12 @@ extern "C" int gne_solver_solve_batch_ex(gne_solver **s, int B, int presolve, in
 extern "C" int gne_solver_set_comm_host(gne_solver *s, int rank, int nranks, gne_allgather_fn allgather, void *ctx) {
     return guarded("gne_solver_set_comm_host", [&]() -> int {
         if (!allgather) { gne_set_error("gne_solver_set_comm_host: no all-gather callback"); return GNE_ERR_ARG; }
-        NO_EQF(s, "gne_solver_set_comm_host");
         uint8_t none[128] = { 0 };
+        if (s->eq) return s->eq->setComm(none, rank, nranks, allgather, ctx);
         return s->solver.setComm(none, rank, nranks, allgather, ctx); });
 }
 extern "C" int gne_solver_set_comm(gne_solver *s, const uint8_t id[128], int rank, int nranks) {
-    return guarded("gne_solver_set_comm", [&]() -> int { NO_EQF(s, "gne_solver_set_comm"); return s->solver.setComm(id, rank, nranks);     });
+    return guarded("gne_solver_set_comm", [&]() -> int { if (s->eq) return s->eq->setComm(id, rank, nranks, nullptr, nullptr); return s->solver.setComm(id, rank, nranks);     });
 }
 extern "C" int gne_solver_set_trace(gne_solver *s, int32_t *e, int32_t *l, int64_t cap)
 {

@@ -104,6 +104,23 @@ int EqfSolver::initialize(const EqfInstance &g, int cudaDev, bool hostOnlyReplay
     return GNE_OK;
 }
 
+int EqfSolver::setComm(const uint8_t id[128], int rank, int nranks, gne_allgather_fn hostGather, void *hostCtx)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) { gne_set_error("setComm: bad rank %d of %d", rank, nranks); return GNE_ERR_ARG; }
+    if (hostOnly || costsOnDevice) { gne_set_error("setComm must precede the first solve"); return GNE_ERR_ARG; }
+    // the handle made by initialize() covers the whole list: replace it by one for this rank's position range
+    const int64_t list = A - numNodes + numSets;        // the nonbasic arc list never grows beyond m + p
+    int64_t lo = 0, hi = 0;
+    GNE_TRY(gne_shard_range(list, rank, nranks, &lo, &hi));
+    if (dev) { gne_dev_destroy(dev); dev = nullptr; }
+    GNE_TRY(gne_dev_create(&dev, cudaDevice, numNodes, list + 16, lo, hi));
+    if (nranks > 1) {
+        if (hostGather) GNE_TRY(gne_comm_init_host(dev, rank, nranks, hostGather, hostCtx));
+        else GNE_TRY(gne_comm_init(dev, id, rank, nranks));
+    }
+    return GNE_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // trees.cpp, restated on flat node arrays (ids, not pointers)
 // ------------------------------------------------------------------------------------------

@@ -55,6 +55,10 @@ class EqfSolver {
     // the leaving variable is compared (*mismatch = first differing pivot or -1).  draws: drand48 calls per pricing, per phase.
     int replayTrace(int draws1, int draws2, int64_t p1, int64_t total, const int32_t *e, const int32_t *l, int64_t *mismatch);
     int solve(bool usePresolve, int64_t maxPivots, int64_t *iters, int *finished);           // genneteq.cpp:60-117
+    // shard the pricing of the nonbasic arcs over ranks (before the first solve): every rank runs this same host engine and
+    // prices its position range; the device layer merges (gne_price_lv_* / _qs / _first / _violators are shard-aware), the
+    // sets are priced on every rank.  hostGather != NULL: the caller's all-gather instead of NCCL (ranks may share a device)
+    int setComm(const uint8_t id[128], int rank, int nranks, gne_allgather_fn hostGather, void *hostCtx);
     int phaseIpivot = GNE_LVW, phaseIIpivot = GNE_LVW;
 
     void setTrace(int32_t *e, int32_t *l, int64_t cap) { traceE = e; traceL = l; traceCap = cap; traceLen = 0; }

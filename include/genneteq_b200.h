@@ -30,7 +30,7 @@ typedef enum {
     GNE_ERR_CAPACITY = 3,      /* caller's output buffer too small; *count still holds the need  */
     GNE_ERR_TREE = 4,          /* basis forest invariant broken (reference: exit(-1), trees.cpp:310-313,327-330,469-472) */
     GNE_ERR_CYCLING = 5,       /* >5 consecutive cycles (reference: exit(-1), gnePivot.cpp:342-345) */
-    GNE_ERR_UNSUPPORTED = 6,   /* rule SD; with equal-flow sets: sharding, batches, windows       */
+    GNE_ERR_UNSUPPORTED = 6,   /* rule SD; with equal-flow sets: batches, windows, forest access  */
     GNE_ERR_COMM = 7           /* NCCL error                                                      */
 } gne_status;
 
@@ -233,7 +233,7 @@ int gne_solver_create(gne_solver **out, int cudaDevice, int n, int64_t m, const 
  * one variable behind the arc variables (varIndex = arc variables + set, gneInit.cpp:149-162): its flow is the common
  * flow of its member arcs.  Such an instance runs in the equal-flow engine (Type II trees, pivotTII gnePivot.cpp:122-160,
  * the s x s systems of gnePotential.cpp:142-214 / gneFlow.cpp:212-256 with GSL's LU order restated); arcs and sets are
- * priced on the device.  Rule SD, sharding, batches and the window / progress / forest accessors return
+ * priced on the device.  Rule SD, batches and the window / progress / forest accessors return
  * GNE_ERR_UNSUPPORTED for it.  d_r(i) is accumulated in the order the arcs are given (a file: in file order).      */
 int gne_solver_create_eqf(gne_solver **out, int cudaDevice, int n, int64_t m, const int32_t *tail, const int32_t *head,
                           const double *ub, const double *cost, const double *mult, const int32_t *eqf, int numSets,

@@ -123,6 +123,30 @@ def main():
         s.close()
         boot.finish(out, ok, "comm mode %d" % mode_id)
         return
+    if mode == "eqf":
+        # an instance WITH equal-flow sets (600 nodes / 9000 arcs / 10 sets: several 2048-position tiles) over the ranks: every
+        # rank runs the equal-flow host engine, prices its range of the arcs (LV / QS / first violator / compaction, merged by
+        # the device layer) and all of the sets; fixture written by the reference (tests/golden/q_pow2_s29.npz)
+        boot = Boot(rank, world, local)
+        z = np.load(os.path.join(HERE, "golden", "q_pow2_s29.npz"))
+        ok = True
+        note = ""
+        for r in rule.split(","):
+            s = gne.Solver(int(z["n"]), z["tail"], z["head"], z["ub"], z["cost"], z["mult"], z["supply"], device=boot.device, rule1=r,
+                           eqf=z["eqf"], num_sets=int(z["p"]))
+            boot.attach(s)
+            p1, p2 = s.solve_both()
+            e, l = s.trace
+            good = (p1, p2) == tuple(int(v) for v in z[r + "_p"]) and np.array_equal(e, z[r + "_e"]) and np.array_equal(l, z[r + "_l"])
+            good = good and np.array_equal(s.flows(), z[r + "_flows"], equal_nan=True)
+            good = good and np.array_equal(s.potentials(), z[r + "_potentials"], equal_nan=True)
+            good = good and boot.same_everywhere(np.concatenate([e, l]))
+            if not good:
+                note += " %s(%d+%d pivots)" % (r, p1, p2)
+            ok = ok and good
+            s.close()
+        boot.finish(out, ok, note)
+        return
     if mode == "medium":
         # 600 nodes / 9000 arcs over the ranks (more than one non-empty shard): sharded first-violator (min over the shards'
         # first positions), sharded candidate-list-2 (cursor-ordered concatenation of the shards' parts), random rules
