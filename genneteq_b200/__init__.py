@@ -99,6 +99,9 @@ SIGNATURES = {
     "gne_solver_create_eqf": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, C.c_int,
                                         _f64p, C.c_double]),
     "gne_solver_num_sets": (C.c_int, [_vp]),
+    "gne_eqf_set_rows": (C.c_int, [_vp, C.c_int, _i64p, _i32p, _f64p]),
+    "gne_price_eqf_launch": (C.c_int, [_vp, C.c_int, _i32p, _f64p, C.c_int64]),
+    "gne_price_eqf_fetch": (C.c_int, [_vp, C.c_int, _f64p]),
     "gne_host_replay_eqf_col": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, _i32p, _i32p, _i64p, C.c_int64, _f64p, _f64p,
                                           _f64p]),
     "gne_host_lu_solve": (C.c_int, [C.c_int, _f64p, _f64p, _f64p, _f64p, _i32p]),
@@ -369,6 +372,19 @@ class Device:
         rs = _arr(row_start, np.int64); nd = _arr(node, np.int32); vl = _arr(val, np.float64); cs = _arr(cost, np.float64)
         rc = np.zeros(len(cs))
         _ck(lib.gne_price_eqf(self.h, len(cs), _p(rs, _i64p), _p(nd, _i32p), _p(vl, _f64p), _p(cs, _f64p), _p(rc, _f64p)), "gne_price_eqf")
+        return rc
+
+    def eqf_set_rows(self, row_start, node, val):
+        """The rows of all equal-flow variables, kept on the device (gne_eqf_set_rows)."""
+        rs = _arr(row_start, np.int64); nd = _arr(node, np.int32); vl = _arr(val, np.float64)
+        _ck(lib.gne_eqf_set_rows(self.h, len(rs) - 1, _p(rs, _i64p), _p(nd, _i32p), _p(vl, _f64p)), "gne_eqf_set_rows")
+
+    def price_eqf_resident(self, ids, cost, non_finite):
+        """gne_price_eqf_launch + gne_price_eqf_fetch: reduced costs of the listed resident rows."""
+        ii = _arr(ids, np.int32); cs = _arr(cost, np.float64)
+        _ck(lib.gne_price_eqf_launch(self.h, len(ii), _p(ii, _i32p), _p(cs, _f64p), int(non_finite)), "gne_price_eqf_launch")
+        rc = np.zeros(len(ii))
+        _ck(lib.gne_price_eqf_fetch(self.h, len(ii), _p(rc, _f64p)), "gne_price_eqf_fetch")
         return rc
 
     def pot_finalize_slots(self, slots):

@@ -93,6 +93,13 @@ bool nccl_load()
 // handle
 // ------------------------------------------------------------------------------------------
 struct gne_dev {
+    // equal-flow rows kept on the device (gne_eqf_set_rows) and the mapped result block of gne_price_eqf_launch / _fetch
+    int eqfP = 0;
+    int64_t *eqfRowStart = nullptr;
+    int32_t *eqfNode = nullptr;
+    double *eqfVal = nullptr;
+    double *eqfOut = nullptr;                      // mapped pinned: EQF_CALL_MAX values, then the sequence word
+    unsigned long long eqfSeq = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -337,9 +344,10 @@ extern "C" int gne_dev_destroy(gne_dev *d)
     void *dev[] = { d->tail, d->head, d->cost, d->mult, d->state, d->a0, d->a1, d->theta, d->pi, d->slot,
                     d->lv.tileMax, d->lv.tileCnt, d->lv.candOff, d->lv.candViol, d->tileCnt, d->tileOff,
                     d->qs.cnt, d->qs.bestV, d->qs.bestJ, d->firstPos, d->tileVmin, d->tileVmax, d->lvc.rec, d->lvTicket, d->lvc.candPos, d->lvc.candViol, d->lvc.candSecond, d->qsDev, d->stageDev, d->outPos, d->outViol,
-                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev, d->agDev };
+                    d->flushBuf, d->gatherSend, d->gatherRecv, d->cntDev, d->xSend, d->xRecv, d->lvResDev, d->peersDev, d->blobDev, d->agDev,
+                    d->eqfRowStart, d->eqfNode, d->eqfVal };
     for (void *p : dev) if (p) cudaFree(p);
-    void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes, d->blobHost };
+    void *host[] = { d->lvRes, d->qsState, d->hostScalar, d->stageHost, d->gatherHost, d->selRes, d->blobHost, d->eqfOut };
     for (void *p : host) if (p) cudaFreeHost(p);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
@@ -1297,6 +1305,70 @@ extern "C" int gne_price_eqf(gne_dev *d, int p, const int64_t *rowStart, const i
     CK(cudaMemcpyAsync(rc, g + oRc, 8 * (size_t) p, cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream)); d->stageInFlight = false;
     d->h2dBytes += (int64_t) o; d->d2hBytes += 8 * p;
+    return GNE_OK;
+}
+
+// The rows of ALL p equal-flow variables, once; gne_price_eqf_launch then names the ones to price.
+extern "C" int gne_eqf_set_rows(gne_dev *d, int p, const int64_t *rowStart, const int32_t *node, const double *val)
+{
+    if (!d || p <= 0 || !rowStart || rowStart[0] != 0) { gne_set_error("gne_eqf_set_rows: bad argument"); return GNE_ERR_ARG; }
+    const int64_t nnz = rowStart[p];
+    for (int k = 0; k < p; ++k) if (rowStart[k + 1] < rowStart[k]) { gne_set_error("gne_eqf_set_rows: rowStart must rise"); return GNE_ERR_ARG; }
+    for (int64_t q = 0; q < nnz; ++q) if (node[q] < 0 || node[q] >= d->n) { gne_set_error("gne_eqf_set_rows: node out of range"); return GNE_ERR_ARG; }
+    CK(cudaSetDevice(d->device));
+    CK(cudaStreamSynchronize(d->stream));
+    if (d->eqfRowStart) { cudaFree(d->eqfRowStart); d->eqfRowStart = nullptr; }
+    if (d->eqfNode) { cudaFree(d->eqfNode); d->eqfNode = nullptr; }
+    if (d->eqfVal) { cudaFree(d->eqfVal); d->eqfVal = nullptr; }
+    d->eqfP = 0;
+    CK(cudaMalloc(&d->eqfRowStart, 8 * (size_t) (p + 1)));
+    CK(cudaMalloc(&d->eqfNode, 4 * (size_t) std::max<int64_t>(nnz, 1)));
+    CK(cudaMalloc(&d->eqfVal, 8 * (size_t) std::max<int64_t>(nnz, 1)));
+    CK(cudaMemcpy(d->eqfRowStart, rowStart, 8 * (size_t) (p + 1), cudaMemcpyHostToDevice));
+    if (nnz) { CK(cudaMemcpy(d->eqfNode, node, 4 * (size_t) nnz, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d->eqfVal, val, 8 * (size_t) nnz, cudaMemcpyHostToDevice)); }
+    if (!d->eqfOut) { CK(cudaHostAlloc(&d->eqfOut, 8 * (EQF_CALL_MAX + 8), cudaHostAllocMapped)); memset(d->eqfOut, 0, 8 * (EQF_CALL_MAX + 8)); }
+    d->eqfP = p;
+    d->h2dBytes += 8 * (p + 1) + 12 * nnz;
+    return GNE_OK;
+}
+
+// Reduced cost of the q listed sets against the device's potentials: one kernel, queued behind whatever the stream holds;
+// gne_price_eqf_fetch waits for its sequence word (the arc pass may be launched in between).  GNE_ERR_CAPACITY: more than
+// EQF_CALL_MAX sets or no resident rows - the caller uses gne_price_eqf.
+extern "C" int gne_price_eqf_launch(gne_dev *d, int q, const int32_t *setIds, const double *cost, int64_t nonFinitePotentials)
+{
+    if (!d || q < 0 || (q > 0 && (!setIds || !cost)) || nonFinitePotentials < 0) { gne_set_error("gne_price_eqf_launch: bad argument"); return GNE_ERR_ARG; }
+    if (q == 0) return GNE_OK;
+    if (q > EQF_CALL_MAX || d->eqfP <= 0) { gne_set_error("gne_price_eqf_launch: %d sets (at most %d) or no resident rows", q, EQF_CALL_MAX); return GNE_ERR_CAPACITY; }
+    static thread_local EqfCall c;
+    c.q = q; c.nonFinite = (unsigned long long) nonFinitePotentials; c.seq = ++d->eqfSeq;
+    for (int k = 0; k < q; ++k) {
+        if (setIds[k] < 0 || setIds[k] >= d->eqfP) { gne_set_error("gne_price_eqf_launch: set %d out of range", setIds[k]); return GNE_ERR_ARG; }
+        c.id[k] = setIds[k]; c.cost[k] = cost[k];
+    }
+    CK(cudaSetDevice(d->device));
+    int rcf = flush_pending(d); if (rcf) return rcf;
+    k_price_eqf_resident<<<1, EQF_CALL_MAX, 0, d->stream>>>(c, d->eqfRowStart, d->eqfNode, d->eqfVal, d->pi, d->eqfOut,
+                                                           (volatile unsigned long long *) (d->eqfOut + EQF_CALL_MAX));
+    CK(cudaGetLastError());
+    ++d->launches;
+    d->h2dBytes += 12 * q;
+    return GNE_OK;
+}
+
+extern "C" int gne_price_eqf_fetch(gne_dev *d, int q, double *rc)
+{
+    if (!d || q < 0 || (q > 0 && !rc) || q > EQF_CALL_MAX) { gne_set_error("gne_price_eqf_fetch: bad argument"); return GNE_ERR_ARG; }
+    if (q == 0) return GNE_OK;
+    if (!d->eqfOut || d->eqfSeq == 0) { gne_set_error("gne_price_eqf_fetch: nothing was launched"); return GNE_ERR_ARG; }
+    const cudaStream_t keep = d->passStream;
+    d->passStream = d->stream;                           // (the kernel ran on the handle's own stream: that is the one to query)
+    int rcw = wait_host_seq(d, (const volatile unsigned long long *) (d->eqfOut + EQF_CALL_MAX), d->eqfSeq);
+    d->passStream = keep;
+    if (rcw) return rcw;
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    for (int k = 0; k < q; ++k) rc[k] = const_cast<const volatile double *>(d->eqfOut)[k];
+    d->d2hBytes += 8 * q;
     return GNE_OK;
 }
 

@@ -92,8 +92,14 @@ int EqfSolver::initialize(const EqfInstance &g, int cudaDev, bool hostOnlyReplay
     memberOfTreeID.assign(numNodes, -1); memberOfTreeType.assign(numNodes, T_NONE);
     depth.assign(numNodes, -1); thread.assign(numNodes, -1); pred.assign(numNodes, -1); predArc.assign(numNodes, -1);
     incidentArcs.assign(numNodes, std::vector<int32_t>());
+    threadPos.assign(numNodes, -1); posInTree.assign((size_t) A, -1); nodeStamp.assign(numNodes, 0); stampNow = 0;
+    sparseFlows = !(getenv("GNE_EQF_DENSE") && atoi(getenv("GNE_EQF_DENSE")) != 0);
     // the nonbasic arc list never holds more than m + p arcs (|setBarc| = n - |setBeqf| >= n - p)
-    if (!hostOnly) GNE_TRY(gne_dev_create(&dev, cudaDevice, numNodes, m + numSets + 16, 0, m + numSets + 16));
+    if (!hostOnly) {
+        GNE_TRY(gne_dev_create(&dev, cudaDevice, numNodes, m + numSets + 16, 0, m + numSets + 16));
+        GNE_TRY(gne_eqf_set_rows(dev, numSets, csrStart.data(), csrNode.data(), csrVal.data()));
+        setsResident = true;
+    }
     for (int64_t a = 0; a < A; ++a) {                   // formInitialBFS :174-186
         if (isArtificial[a]) GNE_TRY(insertIntoB((int32_t) a));
         else GNE_TRY(insertIntoNB((int32_t) a, L_var));
@@ -114,6 +120,7 @@ int EqfSolver::setComm(const uint8_t id[128], int rank, int nranks, gne_allgathe
     GNE_TRY(gne_shard_range(list, rank, nranks, &lo, &hi));
     if (dev) { gne_dev_destroy(dev); dev = nullptr; }
     GNE_TRY(gne_dev_create(&dev, cudaDevice, numNodes, list + 16, lo, hi));
+    GNE_TRY(gne_eqf_set_rows(dev, numSets, csrStart.data(), csrNode.data(), csrVal.data()));
     if (nranks > 1) {
         if (hostGather) GNE_TRY(gne_comm_init_host(dev, rank, nranks, hostGather, hostCtx));
         else GNE_TRY(gne_comm_init(dev, id, rank, nranks));
@@ -211,7 +218,11 @@ void EqfSolver::mergeTxAndTII(ETree *tX, ETree *tII, int32_t av)   // :366-392
     removeTree(tII);                                    // (may hand tII's id to tX when tX is the last type II tree)
     setTreeIDAndType(tII, tX->id, tX->type);
     tX->nodesInTree.insert(tX->nodesInTree.end(), tII->nodesInTree.begin(), tII->nodesInTree.end());
-    tX->arcsInTree.insert(tX->arcsInTree.end(), tII->arcsInTree.begin(), tII->arcsInTree.end());
+    for (size_t k = 0; k < tII->arcsInTree.size(); ++k) {
+        posInTree[(size_t) tII->arcsInTree[k]] = (int32_t) tX->arcsInTree.size();
+        tX->arcsInTree.push_back(tII->arcsInTree[k]);
+    }
+    posInTree[(size_t) av] = (int32_t) tX->arcsInTree.size();
     tX->arcsInTree.push_back(av);
     incidentArcs[tail[av]].push_back(av);
     incidentArcs[head[av]].push_back(av);
@@ -231,6 +242,7 @@ void EqfSolver::expandTreeUsingArc(ETree *t, int32_t av)           // :395-428 (
         memberOfTreeID[v] = t->id; memberOfTreeType[v] = t->type;
     }
     if (u != v) {
+        posInTree[(size_t) av] = (int32_t) t->arcsInTree.size();
         t->arcsInTree.push_back(av);
         incidentArcs[u].push_back(av);
         incidentArcs[v].push_back(av);
@@ -285,6 +297,7 @@ void EqfSolver::splitTree(ETree *tX, int32_t removedArc)           // :497-566: 
             if (nextArc == removedArc) { removedArcInd = k; continue; }
             const int nextNode = (tail[nextArc] == curNode) ? head[nextArc] : tail[nextArc];
             if (nextNode != prevNode) {
+                posInTree[(size_t) nextArc] = (int32_t) tCur->arcsInTree.size();
                 tCur->arcsInTree.push_back(nextArc);
                 curNodeStack.push(nextNode);
                 prevNodeStack.push(curNode);
@@ -337,6 +350,7 @@ void EqfSolver::initializeTreeIndices(ETree *t)                    // :597-644
             predArc[curNode] = -1;
         }
         pred[curNode] = predNode;
+        threadPos[curNode] = (int32_t) threads.size();
         threads.push_back(curNode);
         const std::vector<int32_t> &inc = incidentArcs[curNode];
         for (int k = (int) inc.size() - 1; k >= 0; --k) {
@@ -517,7 +531,9 @@ void EqfSolver::finalizePotentialsTypeI(ETree *t)                  // :113-138
     const double thetaValue = (cAB - potA0[alpha] + muAB * potA0[beta]) / (potA1[alpha] - muAB * potA1[beta]);
     for (size_t k = 0; k < t->nodesInTree.size(); ++k) {
         const int i = t->nodesInTree[k];
+        const double was = potential[i];
         potential[i] = potA0[i] + potA1[i] * thetaValue;
+        nonFinitePots += (int) !std::isfinite(potential[i]) - (int) !std::isfinite(was);
         potA0[i] = 0.0; potA1[i] = 0.0; potTheta[i] = -2;
     }
 }
@@ -527,29 +543,46 @@ void EqfSolver::computePotentialsWithEqFlowSets()                  // :142-214
     const int s = (int) setBeqf.size();
     std::vector<double> mat((size_t) s * s, 0.0), rhs((size_t) s, 0.0), x, rowVals((size_t) s);
     std::vector<int> perm;
+    // The reference's row loop is dense over the nodes (:159-168).  A node outside the set contributes dri = 0: `rhs -= 0 * pi`
+    // and `row += 0 * a1` change nothing (rhs and row never hold -0.0: they start at +0.0 or a cost, x - x rounds to +0.0) -
+    // unless the potential term is not finite (0 * inf = NaN).  So the sparse rows are walked when every term is finite, the
+    // dense loop otherwise (the reference does reach NaN states; the fixtures keep such runs).
+    bool finite = true;
+    for (int i = 0; i < numNodes && finite; ++i)
+        finite = (memberOfTreeType[i] == T_I) ? std::isfinite(potential[i]) : (std::isfinite(potA0[i]) && std::isfinite(potA1[i]));
     for (int b = 0; b < s; ++b) {
         const int32_t v = setBeqf[(size_t) b];
-        const double *dr = &nodeVals[(size_t) (v - A) * numNodes];
+        const int r = (int) (v - A);
         double rhsVal = cost[v];
         std::fill(rowVals.begin(), rowVals.end(), 0.0);
-        for (int i = 0; i < numNodes; ++i) {
-            const double dri = dr[i];
+        auto term = [&](int i, double dri) {
             if (memberOfTreeType[i] == T_I) {
                 rhsVal -= dri * potential[i];
             } else {
                 rhsVal -= dri * potA0[i];
                 rowVals[(size_t) potTheta[i]] += dri * potA1[i];
             }
+        };
+        if (finite) {
+            for (int64_t q = csrStart[(size_t) r]; q < csrStart[(size_t) r + 1]; ++q) term(csrNode[(size_t) q], csrVal[(size_t) q]);
+        } else {
+            const double *dr = &nodeVals[(size_t) r * numNodes];
+            for (int i = 0; i < numNodes; ++i) term(i, dr[i]);
         }
         rhs[(size_t) b] = rhsVal;
         for (int k = 0; k < s; ++k) mat[(size_t) b * s + k] = rowVals[(size_t) k];
     }
     lu_decomp(mat, s, perm);
     lu_solve(mat, s, perm, rhs, x);
-    for (int i = 0; i < numNodes; ++i) {
-        if (memberOfTreeType[i] == T_I) continue;
-        potential[i] = potA0[i] + potA1[i] * x[(size_t) potTheta[i]];
-        potA0[i] = 0.0; potA1[i] = 0.0; potTheta[i] = -2;
+    for (size_t t = 0; t < setBtII.size(); ++t) {       // (:203-210 walks all nodes and skips the Type I ones)
+        const std::vector<int32_t> &nodes = setBtII[t]->nodesInTree;
+        for (size_t k = 0; k < nodes.size(); ++k) {
+            const int i = nodes[k];
+            const double was = potential[i];
+            potential[i] = potA0[i] + potA1[i] * x[(size_t) potTheta[i]];
+            nonFinitePots += (int) !std::isfinite(potential[i]) - (int) !std::isfinite(was);
+            potA0[i] = 0.0; potA1[i] = 0.0; potTheta[i] = -2;
+        }
     }
 }
 
@@ -607,18 +640,7 @@ void EqfSolver::setFlowValues(int updateOption)                    // :59-150 (t
     }
 }
 
-void EqfSolver::computeFlowsPivotingTI(int32_t eav, ETree *tU, ETree *tV)      // :155-185
-{
-    if (setLoc[eav] == L_var) {
-        if (tail[eav] == head[eav]) supA0[tail[eav]] = -1.0 * (1.0 - mult[eav]);
-        else { supA0[tail[eav]] = -1.0; supA0[head[eav]] = mult[eav]; }
-    } else {
-        if (tail[eav] == head[eav]) supA0[tail[eav]] = (1.0 - mult[eav]);
-        else { supA0[tail[eav]] = 1.0; supA0[head[eav]] = -1.0 * mult[eav]; }
-    }
-    computeFlowsTypeI(tU);
-    if (tU->id != tV->id) computeFlowsTypeI(tV);
-}
+// (computeFlowsPivotingTI, gneFlow.cpp:155-185, lives in pivotTI: the supply injection and the two trees' sweeps)
 
 void EqfSolver::computeFlowsPivotingTII(int32_t var)               // :188-209
 {
@@ -634,9 +656,10 @@ void EqfSolver::computeFlowsPivotingTII(int32_t var)               // :188-209
 void EqfSolver::computeFlowsWithEqFlowSets()                       // :212-256
 {
     const int s = (int) setBeqf.size();
-    for (int b = 0; b < s; ++b) {
-        const double *dr = &nodeVals[(size_t) (setBeqf[(size_t) b] - A) * numNodes];
-        for (int i = 0; i < numNodes; ++i) swt[(size_t) i * S + b + 1] -= dr[i];
+    for (int b = 0; b < s; ++b) {                       // (:216-221 is dense over the nodes: x - 0.0 is x, so only the entries)
+        const int r = (int) (setBeqf[(size_t) b] - A);
+        for (int64_t q = csrStart[(size_t) r]; q < csrStart[(size_t) r + 1]; ++q)
+            swt[(size_t) csrNode[(size_t) q] * S + b + 1] -= csrVal[(size_t) q];
     }
     std::vector<double> mat((size_t) s * s, 0.0), rhs((size_t) s, 0.0), x;
     std::vector<int> perm;
@@ -711,7 +734,7 @@ void EqfSolver::setSupplyWithThetas()                              // :374-383
 {
     S = (int) setBeqf.size() + 1;
     swt.assign((size_t) numNodes * S, 0.0);
-    fwt.assign((size_t) numNodes * S, 0.0);
+    fwt.resize((size_t) numNodes * S);                  // (every row read later is written first, by computeFlowsTypeII)
     for (int i = 0; i < numNodes; ++i) swt[(size_t) i * S] = supply[i];
 }
 
@@ -724,7 +747,7 @@ void EqfSolver::setSupplyWithThetas(int32_t var)                   // :397-438
 {
     S = (int) setBeqf.size() + 1;
     swt.assign((size_t) numNodes * S, 0.0);
-    fwt.assign((size_t) numNodes * S, 0.0);
+    fwt.resize((size_t) numNodes * S);
     if (isArc(var)) {
         const int u = tail[var], v = head[var];
         if (setLoc[var] == L_var) {
@@ -801,6 +824,81 @@ void EqfSolver::computeFlowsTypeI(ETree *t)                        // :480-560
     checkVarForBlocking(ex);
 }
 
+// computeFlowsTypeI for a PIVOT between Type I trees, where every supply is zero except at the entering arc's ends (`sources`)
+// and - through theta - at the extra arc's ends: e(j) and x(predArc(j)) are then exact zeros off the root paths of those <= 4
+// nodes, a zero flow change neither blocks (computeDeltaVar: max) nor moves a flow, so only the path nodes are swept - in reverse
+// thread order, which is the order the reference adds the children's contributions in - and only the path arcs are ratio-tested,
+// in arcsInTree order.  Same values as the full sweep; only the sign of exact zeros can differ.  Returns false (nothing touched)
+// when the tree's indices do not allow it; a theta that is not finite (0 * inf would make every arc NaN) falls back to the
+// reference's full final loop.
+bool EqfSolver::computeFlowsTypeISparse(ETree *t, const int32_t *sources, int numSources, std::vector<int32_t> &arcsOut)
+{
+    arcsOut.clear();
+    if (!sparseFlows || !t->upToDate || t->threads.empty() || t->threads[0] != t->root) return false;
+    const int32_t ex = t->extraArc;
+    const int alpha = tail[ex], beta = head[ex];
+    const double muAB = mult[ex];
+    const int h = t->root;
+    // the active nodes: the union of the root paths
+    if (++stampNow == INT32_MAX) { std::fill(nodeStamp.begin(), nodeStamp.end(), 0); stampNow = 1; }
+    activeNodes.clear();
+    auto climb = [&](int j) {
+        while (j != -1 && nodeStamp[(size_t) j] != stampNow) { nodeStamp[(size_t) j] = stampNow; activeNodes.push_back(j); j = pred[j]; }
+    };
+    for (int k = 0; k < numSources; ++k) climb(sources[k]);
+    climb(alpha); climb(beta);
+    if (nodeStamp[(size_t) h] != stampNow) return false;            // (cannot happen in a consistent tree)
+    flowA0[ex] = 0.0; flowA1[ex] = 1.0;
+    supA1[alpha] -= 1.0;
+    supA1[beta] += muAB;
+    std::sort(activeNodes.begin(), activeNodes.end(), [&](int32_t a, int32_t b) { return threadPos[(size_t) a] > threadPos[(size_t) b]; });
+    for (size_t q = 0; q < activeNodes.size(); ++q) {
+        const int j = activeNodes[q];
+        if (j == h) continue;
+        const int32_t av = predArc[j];
+        arcsOut.push_back(av);
+        if (tail[av] == j) {
+            const int i = head[av];
+            const double muJI = mult[av];
+            flowA0[av] = supA0[j]; flowA1[av] = supA1[j];
+            supA0[i] += supA0[j] * muJI;
+            supA1[i] += supA1[j] * muJI;
+        } else {
+            const int i = tail[av];
+            const double muIJ = mult[av];
+            flowA0[av] = supA0[j] / (-1.0 * muIJ);
+            flowA1[av] = supA1[j] / (-1.0 * muIJ);
+            supA0[i] += supA0[j] / muIJ;
+            supA1[i] += supA1[j] / muIJ;
+        }
+        supA0[j] = 0.0; supA1[j] = 0.0;
+    }
+    const double theta = (-1.0 * supA0[h]) / supA1[h];
+    supA0[h] = 0.0; supA1[h] = 0.0;
+    if (!std::isfinite(theta)) {
+        // every arc of the tree turns NaN in the reference (0 + 0 * theta): its full final loop, and a full apply afterwards
+        arcsOut.clear(); arcsOut.push_back(-1);
+        for (size_t k = 0; k < t->arcsInTree.size(); ++k) {
+            const int32_t av = t->arcsInTree[k];
+            deltaFlow[av] = flowA0[av] + flowA1[av] * theta;
+            flowA0[av] = 0.0; flowA1[av] = 0.0;
+            checkVarForBlocking(av);
+        }
+    } else {
+        std::sort(arcsOut.begin(), arcsOut.end(), [&](int32_t a, int32_t b) { return posInTree[(size_t) a] < posInTree[(size_t) b]; });
+        for (size_t k = 0; k < arcsOut.size(); ++k) {
+            const int32_t av = arcsOut[k];
+            deltaFlow[av] = flowA0[av] + flowA1[av] * theta;
+            flowA0[av] = 0.0; flowA1[av] = 0.0;
+            checkVarForBlocking(av);
+        }
+    }
+    deltaFlow[ex] = flowA0[ex] + flowA1[ex] * theta;
+    flowA0[ex] = 0.0; flowA1[ex] = 0.0;
+    checkVarForBlocking(ex);
+    return true;
+}
+
 int EqfSolver::computeFlowsTypeII(ETree *t)                        // :563-592
 {
     const std::vector<int32_t> &th = t->threads;
@@ -836,14 +934,19 @@ int EqfSolver::computeFlowsTypeII(ETree *t)                        // :563-592
 // ------------------------------------------------------------------------------------------
 int EqfSolver::pivot()                                             // :28-60
 {
+    const double t0 = wallNow();
     if (isArc(eVar) && memberOfTreeType[tail[eVar]] == T_I && memberOfTreeType[head[eVar]] == T_I) {
         pivotTI(eVar);
+        secsFlowsTI += wallNow() - t0;
     } else {
         pivotTII();
         ++pivotsTII;
+        secsFlowsTII += wallNow() - t0;
     }
     if (lVar == -1) return GNE_OK;
+    const double t1 = wallNow();
     GNE_TRY(updateBasis());
+    secsBasis += wallNow() - t1;
     checkForCycling();
     return status;
 }
@@ -853,14 +956,38 @@ void EqfSolver::pivotTI(int32_t eav)                               // :63-119
     ETree *tU = setBtI[(size_t) memberOfTreeID[tail[eav]]];
     ETree *tV = setBtI[(size_t) memberOfTreeID[head[eav]]];
     delta = DBL_MAX;
-    computeFlowsPivotingTI(eav, tU, tV);
+    // computeFlowsPivotingTI (gneFlow.cpp:155-185): the supply injection, then the two trees - path-sparse where possible
+    if (setLoc[eav] == L_var) {
+        if (tail[eav] == head[eav]) supA0[tail[eav]] = -1.0 * (1.0 - mult[eav]);
+        else { supA0[tail[eav]] = -1.0; supA0[head[eav]] = mult[eav]; }
+    } else {
+        if (tail[eav] == head[eav]) supA0[tail[eav]] = (1.0 - mult[eav]);
+        else { supA0[tail[eav]] = 1.0; supA0[head[eav]] = -1.0 * mult[eav]; }
+    }
+    const bool same = (tU->id == tV->id);
+    const int32_t ends[2] = { tail[eav], head[eav] };
+    bool sparseU, sparseV = true;
+    if (same) {
+        sparseU = computeFlowsTypeISparse(tU, ends, 2, activeArcsU);
+        if (!sparseU) computeFlowsTypeI(tU);
+    } else {
+        sparseU = computeFlowsTypeISparse(tU, ends, 1, activeArcsU);
+        if (!sparseU) computeFlowsTypeI(tU);
+        sparseV = computeFlowsTypeISparse(tV, ends + 1, 1, activeArcsV);
+        if (!sparseV) computeFlowsTypeI(tV);
+    }
     identifyLeavingVar();
     if (lVar == -1) return;
     for (int side = 0; side < 2; ++side) {
         ETree *t = side == 0 ? tU : tV;
-        if (side == 1 && tU->id == tV->id) break;
-        for (size_t k = 0; k < t->arcsInTree.size(); ++k) {
-            const int32_t av = t->arcsInTree[k];
+        if (side == 1 && same) break;
+        const bool sparse = side == 0 ? sparseU : sparseV;
+        const std::vector<int32_t> &act = side == 0 ? activeArcsU : activeArcsV;
+        // (an arc off the root paths has deltaFlow = +-0: `flow += delta * 0` and `flowCost += cost * (delta * 0)` move nothing)
+        const bool full = !sparse || (!act.empty() && act[0] == -1) || !std::isfinite(delta);
+        const std::vector<int32_t> &arcs = full ? t->arcsInTree : act;
+        for (size_t k = 0; k < arcs.size(); ++k) {
+            const int32_t av = arcs[k];
             flow[av] += (delta * deltaFlow[av]);
             flowCost += cost[av] * (delta * deltaFlow[av]);
             deltaFlow[av] = 0.0;
@@ -964,11 +1091,28 @@ double EqfSolver::hostRedCost(int32_t v) const                     // genneteq.h
     return rc;
 }
 
-int EqfSolver::priceSets()                                         // computeEqfRedCost of every nonbasic set, setNBeqf order
+// computeEqfRedCost of every nonbasic set, setNBeqf order.  Up to 128 nonbasic sets: the rows are resident, the call travels as
+// kernel arguments and the answer comes back through mapped memory (launch now, fetch later - the arc pass goes in between);
+// more: the rows travel with the call (gne_price_eqf).
+int EqfSolver::priceSetsLaunch()
 {
     const int q = (int) setNBeqf.size();
     eqfRc.resize((size_t) q);
+    setsLaunched = false;
+    if (q == 0 || !setsResident || q > 128) return GNE_OK;
+    std::vector<int32_t> ids((size_t) q);
+    std::vector<double> c((size_t) q);
+    for (int k = 0; k < q; ++k) { ids[(size_t) k] = (int32_t) (setNBeqf[(size_t) k] - A); c[(size_t) k] = cost[setNBeqf[(size_t) k]]; }
+    GNE_TRY(gne_price_eqf_launch(dev, q, ids.data(), c.data(), nonFinitePots));
+    setsLaunched = true;
+    return GNE_OK;
+}
+
+int EqfSolver::priceSetsFetch()
+{
+    const int q = (int) setNBeqf.size();
     if (q == 0) return GNE_OK;
+    if (setsLaunched) { setsLaunched = false; return gne_price_eqf_fetch(dev, q, eqfRc.data()); }
     std::vector<int64_t> rowStart((size_t) q + 1, 0);
     std::vector<int32_t> node;
     std::vector<double> val, c((size_t) q);
@@ -980,6 +1124,12 @@ int EqfSolver::priceSets()                                         // computeEqf
         c[(size_t) k] = cost[setNBeqf[(size_t) k]];
     }
     return gne_price_eqf(dev, q, rowStart.data(), node.data(), val.data(), c.data(), eqfRc.data());
+}
+
+int EqfSolver::priceSets()
+{
+    GNE_TRY(priceSetsLaunch());
+    return priceSetsFetch();
 }
 
 int EqfSolver::fetchViolators()                                    // computeReducedCosts(false), gnePotential.cpp:217-246
@@ -1040,8 +1190,9 @@ int EqfSolver::getVarWithLargestViolation(int order, bool useWeighted, int32_t *
         lastViolation = L;
         if (sets.empty()) { GNE_TRY(arcPass()); lastViolation = L; }
     } else if (order == 0) {
-        GNE_TRY(priceSets());
+        GNE_TRY(priceSetsLaunch());                     // queued ahead of the arc pass: the wait for the pass covers both
         GNE_TRY(arcPass());
+        GNE_TRY(priceSetsFetch());
         setPass(useWeighted);
         lastViolation = L;
     } else {
@@ -1420,7 +1571,7 @@ int EqfSolver::replayTrace(int draws1, int draws2, int64_t p1, int64_t total, co
         const int64_t end = pre ? p1 : total;
         for (; k < end; ++k) {
             if ((loopIter % 1000) == 0) computeFlows(2);
-            GNE_TRY(computePotentials());
+            { const double q0 = wallNow(); GNE_TRY(computePotentials()); secsPotentials += wallNow() - q0; }
             if (cyclingDetected) (void) drand48();
             else for (int d = 0; d < draws; ++d) (void) drand48();
             eVar = e[k];
@@ -1434,6 +1585,9 @@ int EqfSolver::replayTrace(int draws1, int draws2, int64_t p1, int64_t total, co
         if (presolve) checkFeasibility();
         GNE_TRY(computePotentials());
     }
+    if (getenv("GNE_HOST_PROFILE"))
+        fprintf(stderr, "eqf host replay: %lld pivots (%lld through pivotTII): potentials %.3f s, flows of Type I pivots %.3f s, of Type II pivots %.3f s, "
+                "basis + trees %.3f s\n", (long long) pivots, (long long) pivotsTII, secsPotentials, secsFlowsTI, secsFlowsTII, secsBasis);
     return GNE_OK;
 }
 

@@ -122,6 +122,13 @@ class EqfSolver {
     std::vector<double> swt;                                           // supplyWithThetas: [n * S]
     std::vector<double> fwt;                                           // flowWithThetas of predArc(j): [n * S], row j
     std::vector<int32_t> memberOfTreeID, depth, thread, pred, predArc;
+    // not in the reference: a node's index in its tree's thread vector and an arc's index in its tree's arcsInTree - what the
+    // path-sparse flow computation of a Type I pivot orders its few active nodes and arcs by
+    std::vector<int32_t> threadPos, posInTree;
+    std::vector<int32_t> nodeStamp;                                    // active-node marks (value = stampNow)
+    int32_t stampNow = 0;
+    std::vector<int32_t> activeNodes, activeArcs, activeArcsU, activeArcsV;
+    bool sparseFlows = true;                                           // GNE_EQF_DENSE=1 turns the path-sparse computation off
     std::vector<int8_t> memberOfTreeType;
     std::vector<std::vector<int32_t> > incidentArcs;
     // ---- basis
@@ -154,6 +161,7 @@ class EqfSolver {
     int32_t *traceE = nullptr, *traceL = nullptr;
     int64_t traceCap = 0, traceLen = 0, pivots = 0, pivotsTII = 0;
     double secsPricing = 0, secsPotentials = 0, secsPivot = 0, secsTotal = 0, arcsPriced = 0;
+    double secsFlowsTI = 0, secsFlowsTII = 0, secsBasis = 0;           // inside secsPivot
     int status = GNE_OK;
 
     // ---- trees.cpp
@@ -177,7 +185,6 @@ class EqfSolver {
     double computeDeltaVar(int32_t v) const;
     void computeFlows(int updateOption);
     void setFlowValues(int updateOption);
-    void computeFlowsPivotingTI(int32_t eav, ETree *tU, ETree *tV);
     void computeFlowsPivotingTII(int32_t var);
     void computeFlowsWithEqFlowSets();
     void computeNumericFlowsAndSupply(const std::vector<double> &x);
@@ -187,6 +194,7 @@ class EqfSolver {
     void setSupplyWithEqs();
     void setSupplyWithEqs(int32_t var);
     void computeFlowsTypeI(ETree *t);
+    bool computeFlowsTypeISparse(ETree *t, const int32_t *sources, int numSources, std::vector<int32_t> &arcsOut);
     int computeFlowsTypeII(ETree *t);
     int computePotentials();
     void computePotentialsInTermsOfRoot(ETree *t);
@@ -205,6 +213,10 @@ class EqfSolver {
     int removeFromNB(int32_t v);
     int selectEnteringVariable(int32_t *out);
     int priceSets();                                                   // reduced cost of every nonbasic set -> eqfRc (setNBeqf order)
+    int priceSetsLaunch();                                             // the same in two halves: the arc pass can be queued in between
+    int priceSetsFetch();
+    bool setsResident = false, setsLaunched = false;                   // rows on the device (gne_eqf_set_rows); a launch awaits its fetch
+    int64_t nonFinitePots = 0;                                         // potentials that are NaN or infinite right now
     bool violates(int32_t v, double rc) const;
     double hostRedCost(int32_t v) const;
     int fetchViolators();                                              // computeReducedCosts(false): offendingVars / offendingViol

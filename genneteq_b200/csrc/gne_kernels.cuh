@@ -546,6 +546,39 @@ __global__ void k_price_eqf(int p, const int64_t *__restrict__ rowStart, const i
     rc[k] = (*nonFinite > met) ? __longlong_as_double(0x7ff8000000000000ll) : x;
 }
 
+// The same against rows that stay on the device (the equal-flow engine prices its nonbasic sets every pivot): which sets, their
+// costs and the number of non-finite potentials (the caller computed the potentials, so it knows) travel as kernel arguments,
+// the reduced costs land in mapped pinned host memory behind a sequence word - no copy in either direction, no stream
+// synchronisation; the host reads them after the arc pass it launched right behind this kernel.
+#define EQF_CALL_MAX 128
+struct EqfCall {
+    int q;
+    unsigned long long nonFinite, seq;
+    int32_t id[EQF_CALL_MAX];
+    double cost[EQF_CALL_MAX];
+};
+
+__global__ void __launch_bounds__(EQF_CALL_MAX)
+k_price_eqf_resident(const __grid_constant__ EqfCall c, const int64_t *__restrict__ rowStart, const int32_t *__restrict__ node,
+                     const double *__restrict__ val, const double *__restrict__ pi, double *out, volatile unsigned long long *seqOut)
+{
+    const int k = threadIdx.x;
+    if (k < c.q) {
+        const int r = c.id[k];
+        double x = c.cost[k];
+        unsigned long long met = 0;
+        for (int64_t q = rowStart[r]; q < rowStart[r + 1]; ++q) {
+            const double v = pi[node[q]];
+            if (!isfinite(v)) ++met;
+            x = __dsub_rn(x, __dmul_rn(val[q], v));
+        }
+        out[k] = (c.nonFinite > met) ? __longlong_as_double(0x7ff8000000000000ll) : x;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (k == 0) *seqOut = c.seq;
+}
+
 // ------------------------------------------------------------------------------------------
 // quickSelect scan (gnePivotRules.cpp:742-756) over a window [jLo, jHi) of *virtual* indices
 // j = (pos - cursor) mod N; one CTA per QTILE virtual indices, thread t owns j = base + t + 256 k.

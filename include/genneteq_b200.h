@@ -157,6 +157,15 @@ int gne_price_first(gne_dev *d, int64_t *pos);
  * passed sparse: CSR, entries of a row sorted by node).  SURVEY 8 a12; the equal-flow engine calls it every pivot.    */
 int gne_price_eqf(gne_dev *d, int p, const int64_t *rowStart, const int32_t *node, const double *val, const double *cost, double *rc);
 
+/* The same without a copy or a stream synchronisation per call (what the equal-flow engine uses every pivot): the rows of all
+ * p sets go to the device once (gne_eqf_set_rows); gne_price_eqf_launch names the q <= 128 sets to price (setIds: row numbers),
+ * their costs and how many of the potentials the caller last set are not finite - as kernel arguments -, the kernel is queued
+ * behind whatever the handle's stream holds and writes into mapped host memory; gne_price_eqf_fetch waits for it (another pass
+ * may be launched in between: one wait then covers both).  GNE_ERR_CAPACITY from launch: use gne_price_eqf.            */
+int gne_eqf_set_rows(gne_dev *d, int p, const int64_t *rowStart, const int32_t *node, const double *val);
+int gne_price_eqf_launch(gne_dev *d, int q, const int32_t *setIds, const double *cost, int64_t nonFinitePotentials);
+int gne_price_eqf_fetch(gne_dev *d, int q, double *rc);
+
 /* reduced cost of every position in [lo, hi) (tests, verifyOptimality)                        */
 int gne_reduced_costs(gne_dev *d, int64_t lo, int64_t hi, double *rc);
 

@@ -467,6 +467,10 @@ def test_equal_flow_reduced_costs_match_the_dense_loop(gne):
     d.pot_set_all(pi)
     got = d.price_eqf(row_start, node, val, cost)
     assert np.array_equal(got, exp)
+    # the same rows kept on the device, a subset of them named per call (gne_eqf_set_rows / gne_price_eqf_launch / _fetch)
+    d.eqf_set_rows(row_start, node, val)
+    for ids in (np.arange(p), np.array([5, 3, 36, 7, 0]), np.array([11])):
+        assert np.array_equal(d.price_eqf_resident(ids, cost[ids], 0), exp[ids]), ids
     # non-finite potentials (the reference reaches them through a singular s x s system): the dense loop multiplies them by
     # the zero entries too (0 * inf = NaN), so a row that does not touch the bad node must come out NaN all the same, a
     # row whose only bad node carries a non-zero entry keeps its signed infinity
@@ -478,6 +482,8 @@ def test_equal_flow_reduced_costs_match_the_dense_loop(gne):
         got = d.price_eqf(row_start, node, val, cost)
         assert np.array_equal(got, exp, equal_nan=True), (bad_nodes, got[:12], exp[:12])
         assert np.isnan(got[3]) and np.isnan(exp[3])                # the empty row
+        got = d.price_eqf_resident(np.arange(p), cost, len(bad_nodes))           # (the caller states how many potentials are not finite)
+        assert np.array_equal(got, exp, equal_nan=True), (bad_nodes, got[:12], exp[:12])
     d.close()
 
 
