@@ -122,10 +122,10 @@ def test_sharded_first_violator_and_candidate_list_2(tmp_path, nproc, exchange):
 @pytest.mark.parametrize("nproc,exchange", [(2, "p2p"), (3, "fallback")])
 def test_sharded_equal_flow_instance(tmp_path, nproc, exchange):
     """An instance with equal-flow sets sharded over the ranks (gne_solver_set_comm[_host] on the equal-flow engine): arcs priced
-    per shard and merged, sets priced on every rank; Dantzig, block rule, first violator, candidate lists 1 and 2 - every rank
+    per shard and merged, sets priced on every rank; Dantzig, block rule, candidate lists 1 and 2 - every rank
     the reference's trace, flows and potentials (fixture q_pow2_s29, written by the reference)."""
     gne = pytest.importorskip("genneteq_b200")
     if gne.cuda_device_count() < 1:
         pytest.skip("needs a GPU")
     env = fallback_env(gne, nproc) if exchange == "fallback" else {}
-    assert launch("eqf", nproc, str(tmp_path / "eqf.txt"), 29690 + nproc, env, "LV,QS,FV,CLW2" if exchange == "p2p" else "LV,CL,CL2") == "OK"
+    assert launch("eqf", nproc, str(tmp_path / "eqf.txt"), 29690 + nproc, env, "LV,QS,CLW2" if exchange == "p2p" else "LV,CL,CL2") == "OK"
