@@ -644,13 +644,16 @@ void EqfSolver::setFlowValues(int updateOption)                    // :59-150 (t
 
 void EqfSolver::computeFlowsPivotingTII(int32_t var)               // :188-209
 {
+    const double t0 = wallNow();
     if (!setBeqf.empty()) {
         setSupplyWithThetas(var);
         computeFlowsWithEqFlowSets();
     } else {
         setSupplyWithEqs(var);
     }
+    const double t1 = wallNow();
     for (size_t k = 0; k < setBtI.size(); ++k) computeFlowsTypeI(setBtI[k]);
+    secsTIIsets += t1 - t0; secsTIItrees += wallNow() - t1;
 }
 
 void EqfSolver::computeFlowsWithEqFlowSets()                       // :212-256
@@ -1587,7 +1590,7 @@ int EqfSolver::replayTrace(int draws1, int draws2, int64_t p1, int64_t total, co
     }
     if (getenv("GNE_HOST_PROFILE"))
         fprintf(stderr, "eqf host replay: %lld pivots (%lld through pivotTII): potentials %.3f s, flows of Type I pivots %.3f s, of Type II pivots %.3f s, "
-                "basis + trees %.3f s\n", (long long) pivots, (long long) pivotsTII, secsPotentials, secsFlowsTI, secsFlowsTII, secsBasis);
+                "basis + trees %.3f s; inside the Type II pivots: sets / Type II trees / systems %.3f s, Type I trees %.3f s\n", (long long) pivots, (long long) pivotsTII, secsPotentials, secsFlowsTI, secsFlowsTII, secsBasis, secsTIIsets, secsTIItrees);
     return GNE_OK;
 }
 

@@ -162,6 +162,7 @@ class EqfSolver {
     int64_t traceCap = 0, traceLen = 0, pivots = 0, pivotsTII = 0;
     double secsPricing = 0, secsPotentials = 0, secsPivot = 0, secsTotal = 0, arcsPriced = 0;
     double secsFlowsTI = 0, secsFlowsTII = 0, secsBasis = 0;           // inside secsPivot
+    double secsTIIsets = 0, secsTIItrees = 0;                          // inside secsFlowsTII
     int status = GNE_OK;
 
     // ---- trees.cpp
