@@ -91,6 +91,42 @@ def test_eqf_fixtures_exercise_type_two_pivots():
     assert total_in > 500 and total_out > 500
 
 
+def test_eqf_path_sparse_and_full_sweeps_agree():
+    """GNE_EQF_DENSE=1 turns the path-sparse Type I sweeps off (the reference's full sweeps run instead): the same replays must
+    pass - the two differ only in which exact zeros they compute."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np, genneteq_b200 as gne\n"
+            "import glob, os\n"
+            "D = dict(LV=1, LVE=1, QS=0, CL=0, FV=0, RLV=1)\n"
+            "n = 0\n"
+            "for f in sorted(glob.glob(os.path.join(%r, 'q_*.npz'))):\n"
+            "    z = np.load(f)\n"
+            "    if 'arrays_ok' in z.files and int(z['arrays_ok']) == 0: continue\n"
+            "    for rn in D:\n"
+            "        if rn + '_e' not in z.files: continue\n"
+            "        mm, fl, po, ob = gne.host_replay_eqf(int(z['n']), z['tail'], z['head'], z['ub'], z['cost'], z['mult'], z['eqf'], int(z['p']),\n"
+            "                                             z['supply'], -1.0, D[rn], int(z[rn + '_p'][0]), z[rn + '_e'], z[rn + '_l'], len(z[rn + '_flows']))\n"
+            "        assert mm == -1 and np.array_equal(fl, z[rn + '_flows'], equal_nan=True) and np.array_equal(po, z[rn + '_potentials'], equal_nan=True), (f, rn)\n"
+            "        n += 1\n"
+            "print('DENSE-OK', n)\n" % (ROOT, GOLD))
+    env = dict(os.environ)
+    env["GNE_EQF_DENSE"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DENSE-OK" in r.stdout, r.stdout[-500:] + r.stderr[-2000:]
+    assert int(r.stdout.split("DENSE-OK")[1].split()[0]) >= 20
+
+
+def test_eqf_no_cpu_fallback(gne):
+    """Without a device an instance with sets is refused like any other (the host-only replay is test infrastructure)."""
+    if gne.cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    z = np.load(os.path.join(GOLD, "q_wide_s21.npz"))
+    with pytest.raises(gne.GneError) as ei:
+        gne.Solver(int(z["n"]), z["tail"], z["head"], z["ub"], z["cost"], z["mult"], z["supply"], eqf=z["eqf"], num_sets=int(z["p"]))
+    assert "no CPU fallback" in str(ei.value)
+
+
 def test_eqf_replay_detects_a_wrong_trace(gne):
     z = np.load(os.path.join(GOLD, "q_wide_s21.npz"))
     l = z["LV_l"].copy()
