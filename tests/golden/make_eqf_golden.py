@@ -28,8 +28,9 @@ from gen_instance import generate  # noqa: E402
 from oracle_util import REF_DRIVER, RULES  # noqa: E402
 
 
-def make_instance(n, m, seed, mode, p, k, shuffled=False, cap_scale=1.0):
+def make_instance(n, m, seed, mode, p, k, shuffled=False, cap_scale=1.0, supply_scale=1.0):
     arcs, sup = generate(n, m, seed, mode)
+    sup = [supply_scale * v for v in sup]               # (x 40: demand beyond the capacities, Phase I ends infeasible; x 0: nothing to ship)
     rng = random.Random(seed * 7919 + 13)
     idx = list(range(len(arcs)))
     rng.shuffle(idx)
@@ -159,9 +160,9 @@ def ref_cli(col, rule1, rule2, tmp):
                 trace_md5=hashlib.md5(txt.encode()).hexdigest(), feasible=int(feasible))
 
 
-def make(name, n, m, seed, mode, p, k, rules, shuffled=False, keep_col=False, cap_scale=1.0, text=None):
+def make(name, n, m, seed, mode, p, k, rules, shuffled=False, keep_col=False, cap_scale=1.0, text=None, supply_scale=1.0):
     if text is None:
-        text = make_instance(n, m, seed, mode, p, k, shuffled, cap_scale)
+        text = make_instance(n, m, seed, mode, p, k, shuffled, cap_scale, supply_scale)
     out = {}
     (n_, p_, tail, head, ub, cost, mult, eqf, sup) = parse_col(text)
     # the arrays the C ABI takes: arcs sorted by (tail, head) - for a shuffled file d_r(i) is then summed in another
@@ -200,7 +201,7 @@ def make(name, n, m, seed, mode, p, k, rules, shuffled=False, keep_col=False, ca
 
 if __name__ == "__main__":
     allr = ["LV", "LVW", "LVA", "LVE", "FV", "RV", "RWV", "RLV", "RLVW", "CL", "CLW", "SAA", "SAE", "CL2", "CLW2", "QS", "QSW"]
-    which = sys.argv[1:] or ["small", "edge", "medium"]
+    which = sys.argv[1:] or ["small", "edge", "ends", "medium"]
     if "small" in which:
         make("q_wide_s21", 60, 400, 21, "wide", 4, 3, allr, keep_col=True)
         make("q_lossy_s22", 150, 1200, 22, "lossy", 8, 4, allr)
@@ -211,6 +212,14 @@ if __name__ == "__main__":
         # (the arrays of this fixture are the file's lines in (tail, head) order, duplicate included: only the text goes
         #  through the loader the way the reference reads it - the tests use col_text)
         make("q_edge_s31", 0, 0, 0, "", 0, 0, ["LV", "LVE", "QS", "CL", "CL2", "FV"], keep_col=True, text=make_edge_instance())
+    if "ends" in which:
+        # how a solve with sets ends when it cannot end well: infeasible demand, no supply at all, tight set capacities, and
+        # the smallest graphs that can hold a set
+        er = ["LV", "LVE", "QS", "CL", "CL2", "FV", "RV"]
+        make("q_infeasible_s41", 70, 350, 41, "wide", 4, 3, er, supply_scale=40.0)
+        make("q_nosupply_s42", 40, 200, 42, "wide", 3, 2, er, supply_scale=0.0)
+        make("q_tightsets_s43", 80, 500, 43, "lossy", 6, 3, er, cap_scale=0.05)
+        make("q_three_nodes_s44", 3, 6, 44, "pow2", 1, 2, er)
     if "medium" in which:
         # several 2048-position tiles of nonbasic arcs, more sets.  (At this size the reference often ends with a NaN objective -
         # a singular s x s system, no pivot-size check in its LU use; rule CL does here.  The fixture keeps that run: the

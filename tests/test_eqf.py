@@ -233,12 +233,18 @@ def test_eqf_optimum_against_an_independent_lp_solver(name):
         U[j] = ub[mem].min()
     A = sp.csr_matrix((vals, (rows, cols)), shape=(n, nv))
     res = so.linprog(c, A_eq=A, b_eq=sup, bounds=np.column_stack([np.zeros(nv), U]), method="highs")
+    verdicts = [int(z[rn + "_feasible"]) for rn in rules_of(z)]
+    if not any(verdicts):
+        # every run of the reference ended Phase I infeasible (no Phase II pivots): the LP solver must say so too
+        assert res.status == 2, (name, res.status)
+        assert all(int(z[rn + "_p"][1]) == 0 for rn in rules_of(z))
+        return
     assert res.status == 0
     checked = 0
     for rn in rules_of(z):
         obj = float(z[rn + "_objective"])
-        if not np.isfinite(obj) or not int(z[rn + "_feasible"]) or int(z[rn + "_p"][1]) == 0:
-            continue                                    # runs in which the reference itself ended in NaN / stopped after Phase I
+        if not np.isfinite(obj) or not int(z[rn + "_feasible"]):
+            continue                                    # runs in which the reference itself ended in NaN / infeasible after Phase I
         x = z[rn + "_flows"]
         xa = np.concatenate([x[:len(free)], x[len(free) + n:]])                # arc variables, (artificial self-loops), sets
         if (name, rn) in REFERENCE_WENT_ASTRAY:
