@@ -6,6 +6,10 @@
 //
 //   gne_gpu_driver -1 <rule> -2 <rule> -T trace.txt [-A every] file.col        rules: 0/1 (LV/LVW), 16/17 (QS/QSW)
 //
+// Instances WITH equal-flow sets run too (the reference's own Type II trees, pivotTII and s x s solves - GSL's LU through
+// oracle/gsl_mini): the arcs are priced by gne_price_lv / gne_price_qs, the nonbasic sets by gne_price_eqf, and the
+// reference's own checkVarForOffending continues over the sets' values (computeEqfsWithLargestViolation, :415-429).
+//
 // -A every: same-state A/B.  At every `every`-th iteration the reference's OWN
 // selectEnteringVariable() (host, gnePivotRules.cpp:36-127) and the GPU path price the same state - the drand48
 // state (seed48), the quickSelect cursor and the optimality flag are saved and restored in between - the two
@@ -77,36 +81,94 @@ class GpuGenNetEq : public GenNetEq
     std::vector<double> shadowPi, dirtyVal;
     std::vector<int32_t> dirtyIdx;
     long potentialBytes = 0;
-    Variable *gpuLargestViolation()                         // getVarWithLargestViolation, gnePivotRules.cpp:133-157
+    // computeEqfRedCost (genneteq.h:321-330) of every nonbasic set on the device: rows = the sets' nodeVals, sparse
+    std::vector<double> setRc;
+    void priceSets()
+    {
+        const int q = (int) setNBeqf.size();
+        setRc.assign(q, 0.0);
+        if (q == 0) return;
+        std::vector<int64_t> rowStart(q + 1, 0);
+        std::vector<int32_t> node;
+        std::vector<double> val, cost(q);
+        for (int k = 0; k < q; ++k) {
+            EqFlowVar *v = setNBeqf[k];
+            for (int i = 0; i < numNodes; ++i) if (v->nodeVals[i] != 0.0) { node.push_back(i); val.push_back(v->nodeVals[i]); }
+            rowStart[k + 1] = (int64_t) node.size();
+            cost[k] = v->cost;
+        }
+        GCK(gne_price_eqf(dev, q, rowStart.data(), node.data(), val.data(), cost.data(), setRc.data()));
+    }
+    static bool violates(Variable *v, double rc)
+    {
+        return ((v->setLoc == L_var) && (rc < (-1.0 * ROUNDOFF_TOLERANCE))) || ((v->setLoc == U_var) && (rc > ROUNDOFF_TOLERANCE));
+    }
+    Variable *gpuLargestViolation(bool useWeighted)         // getVarWithLargestViolation, gnePivotRules.cpp:133-157
     {
         double L; int64_t cnt; int any;
         pos.resize(setNBarc.size() + 16);
         GCK(gne_price_lv(dev, &L, &cnt, pos.data(), (int64_t) pos.size(), &any));
         isOptimal = !any;
-        lastViolation = L;
         offendingVars.clear();
         for (int64_t i = 0; i < cnt; ++i) offendingVars.push_back(setNBarc[pos[i]]);
+        if (!setNBeqf.empty()) {                            // computeEqfsWithLargestViolation (:415-429) with the device's values
+            priceSets();
+            for (size_t k = 0; k < setNBeqf.size(); ++k) {
+                EqFlowVar *nbeq = setNBeqf[k];
+                const double rc = setRc[k];
+                if (!violates(nbeq, rc)) continue;
+                isOptimal = false;
+                const double frc = useWeighted ? fabs(rc) / nbeq->numOrigArcs : fabs(rc);
+                // checkVarForOffending (:431-452; defined inline in gnePivotRules.cpp, so not linkable - its two lines, with
+                // trackLowestVarIndex off as genneteq.cpp:144 sets it), continuing the arc pass's state
+                if (L < frc - ROUNDOFF_TOLERANCE) offendingVars.clear();
+                if (L <= frc + ROUNDOFF_TOLERANCE) { L = frc; offendingVars.push_back(nbeq); }
+            }
+        }
+        lastViolation = L;
         if (offendingVars.empty()) return NULL;
         return offendingVars[drand48() * offendingVars.size()];          // the reference's own draw (:153)
     }
-    Variable *gpuQuickSelect()                              // quickSelect, gnePivotRules.cpp:710-764
+    Variable *gpuQuickSelect(bool useWeighted)              // quickSelect, gnePivotRules.cpp:710-764
     {
         isOptimal = true;
+        Variable *bestVar = NULL;
+        double largestViol = 0.0;
         if (nbArcPivotInd >= (int) setNBarc.size()) nbArcPivotInd = 0;
-        int64_t best, cur, scanned, viol;
-        double bv;
-        const int start = nbArcPivotInd;
-        GCK(gne_price_qs(dev, start, numNodes, &best, &bv, &cur, &scanned, &viol));
-        if (viol > 0) isOptimal = false;
-        nbArcPivotInd = ((loopIter % majorIterationLength) > 0) ? start : (int) cur;
-        return best >= 0 ? setNBarc[best] : NULL;
+        if (nbEqfPivotInd >= (int) setNBeqf.size()) nbEqfPivotInd = 0;
+        const int start = nbArcPivotInd, startE = nbEqfPivotInd;
+        int eqfViolations = 0;
+        bool exhaustedEqfs = setNBeqf.empty();
+        if (!exhaustedEqfs) priceSets();
+        while ((eqfViolations < 1) && !exhaustedEqfs) {     // the set loop (:723-738) over the device's values
+            EqFlowVar *eqfv = setNBeqf[nbEqfPivotInd];
+            const double rc = setRc[nbEqfPivotInd];
+            if (violates(eqfv, rc)) {
+                isOptimal = false;
+                ++eqfViolations;
+                const double frc = useWeighted ? fabs(rc) / eqfv->numOrigArcs : fabs(rc);
+                if (frc > largestViol) { largestViol = frc; bestVar = eqfv; }
+            }
+            nbEqfPivotInd = (nbEqfPivotInd + 1) % setNBeqf.size();
+            exhaustedEqfs = (nbEqfPivotInd == startE);
+        }
+        int64_t best = -1, cur = start, scanned, viol = 0;
+        double bv = 0.0;
+        if (!setNBarc.empty()) {
+            GCK(gne_price_qs(dev, start, numNodes, &best, &bv, &cur, &scanned, &viol));
+            if (viol > 0) isOptimal = false;
+            if (best >= 0 && bv > largestViol) bestVar = setNBarc[best];   // an arc replaces the set only when strictly larger
+            nbArcPivotInd = (int) cur;
+        }
+        if ((loopIter % majorIterationLength) > 0) { nbArcPivotInd = start; nbEqfPivotInd = startE; }
+        return bestVar;
     }
     Variable *gpuSelect()
     {
         if (cyclingDetected && useRandomJumpWhenCycling) return getRandomVarWithLargeViolation();   // host (:43-46), rare
         const int rule = presolve ? phaseIpivot : phaseIIpivot;
-        if (rule == QS || rule == QSW) return gpuQuickSelect();
-        return gpuLargestViolation();
+        if (rule == QS || rule == QSW) return gpuQuickSelect(rule == QSW);
+        return gpuLargestViolation(rule == LVW);
     }
 
     static double nowS() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
@@ -117,14 +179,14 @@ class GpuGenNetEq : public GenNetEq
         unsigned short zero[3] = { 0, 0, 0 }, saved[3];
         memcpy(saved, seed48(zero), sizeof(saved));         // read the generator state ...
         seed48(saved);                                      // ... and put it back
-        const int cursor = nbArcPivotInd, sinceUpdate = itersSinceUpdate;
+        const int cursor = nbArcPivotInd, cursorE = nbEqfPivotInd, sinceUpdate = itersSinceUpdate;
         const double viol = lastViolation;
         const bool opt = isOptimal;
         const double t0 = nowS();
         Variable *hostVar = selectEnteringVariable();       // reference, host (also writes av->redCost: harmless)
         const double t1 = nowS();
         const bool hostOpt = isOptimal;
-        seed48(saved); nbArcPivotInd = cursor; itersSinceUpdate = sinceUpdate; lastViolation = viol; isOptimal = opt;
+        seed48(saved); nbArcPivotInd = cursor; nbEqfPivotInd = cursorE; itersSinceUpdate = sinceUpdate; lastViolation = viol; isOptimal = opt;
         offendingVars.clear();
         const double t2 = nowS();
         Variable *gpuVar = gpuSelect();
@@ -159,15 +221,16 @@ class GpuGenNetEq : public GenNetEq
             pushPotentials();                                               // <-- potentials to the device
             eVar = (abEvery > 0 && (loopIter % abEvery) == 0) ? selectBothWays() : gpuSelect();   // <-- identifyEnteringVariable() on the GPU
             if (eVar != NULL) {
-                const int64_t pe = eVar->setInd, last = (int64_t) setNBarc.size() - 1;
+                // (positions are those of setNBarc: a set's setInd points into setNBeqf and is none of the mirror's business)
+                const int64_t pe = (eVar->varType == ARC_VAR) ? eVar->setInd : -1, last = (int64_t) setNBarc.size() - 1;
                 pivot();
                 if (lVar != NULL) {
                     if (trace) fprintf(trace, "P %d %d %d\n", loopIter, eVar->varIndex, lVar->varIndex);
                     // the positions updateBasis touched: eVar's old slot (the last element moved in),
                     // the last slot(s) (pushes), and wherever the leaving / flipped variable landed
-                    mirrorWrite(pe); mirrorWrite(last); mirrorWrite(last - 1);
-                    if (lVar->setLoc != B_var) mirrorWrite(lVar->setInd);
-                    if (eVar->setLoc != B_var) mirrorWrite(eVar->setInd);
+                    mirrorWrite(pe); mirrorWrite(last); mirrorWrite(last - 1); mirrorWrite(last + 1);
+                    if (lVar->varType == ARC_VAR && lVar->setLoc != B_var) mirrorWrite(lVar->setInd);
+                    if (eVar->varType == ARC_VAR && eVar->setLoc != B_var) mirrorWrite(eVar->setInd);
                     GCK(gne_nb_set_count(dev, (int64_t) setNBarc.size()));
                 }
                 ++loopIter;

@@ -70,6 +70,31 @@ def test_reference_engine_with_gpu_pricing(fixture, rule, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fixture,rule,extra", [("q_wide_s21", "LV", ()), ("q_wide_s21", "LVW", ()), ("q_wide_s21", "QS", ()), ("q_near1_s24", "QSW", ()),
+                                                ("q_near1_s24", "LV", ("-A", "3")), ("q_edge_s31", "QS", ("-A", "2"))])
+def test_reference_engine_with_gpu_pricing_and_equal_flow_sets(fixture, rule, extra, tmp_path):
+    """Mode A on instances WITH equal-flow sets: the reference's own engine (Type II trees, pivotTII, its s x s solves) with the
+    arcs priced by gne_price_lv / gne_price_qs and the sets by gne_price_eqf reproduces the reference's own trace; with -A the
+    reference's selectEnteringVariable() and the GPU path are compared from the same state as well."""
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/gne_gpu_driver not built (needs /root/reference at build time)")
+    z = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    col = str(tmp_path / (fixture + ".col"))
+    open(col, "wb").write(z["col_text"].tobytes())
+    r = RULES[rule]
+    trace = str(tmp_path / "trace.txt")
+    piv, obj = _run_driver(col, r, r, trace, extra)
+    assert np.array_equal(piv[:, 1], z[rule + "_e"]) and np.array_equal(piv[:, 2], z[rule + "_l"])
+    assert hashlib.md5(open(trace, "rb").read()).hexdigest() == str(z[rule + "_md5"])
+    assert obj == float(z[rule + "_objective"])
+    if extra:
+        ab = [ln for ln in _run_driver.last_stdout.splitlines() if ln.startswith("A/B")]
+        assert ab, _run_driver.last_stdout[-500:]
+        f = ab[-1].split()
+        assert int(f[2]) > 10 and int(f[4]) == 0, ab[-1]            # "A/B samples N mismatches M ..."
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fixture,rule,every", [("c1_wide_s7", "LV", 5), ("c1_wide_s7", "QS", 3), ("s_lossy_s4", "LV", 1),
                                                 ("e_nosupply_s12", "QS", 1)])
 def test_same_state_ab_against_the_reference_rule(fixture, rule, every, tmp_path):
